@@ -1,0 +1,200 @@
+// TEST INFRASTRUCTURE ONLY -- CPU oracle (see cvprims.h). Build: -O2 -ffp-contract=off, no -march=native.
+#include "cvprims.h"
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+
+namespace orbo {
+
+int cv_round(float v) { return (int)lrintf(v); }
+int cv_round_d(double v) { return (int)lrint(v); }
+int cv_floor(float v) { return (int)std::floor(v); }
+int cv_ceil(float v) { return (int)std::ceil(v); }
+
+// ---------------------------------------------------------------------------------------------
+// resize, INTER_LINEAR, 8UC1. Fixed point: 11-bit coefficients, horizontal pass keeps 8+11 bits,
+// vertical pass drops 4 bits of the row sums and 16 of each product, rounds once (+2 >> 2).
+// ---------------------------------------------------------------------------------------------
+void resize_axis_table(int ssize, int dsize, int* ofs, int16_t* coef) {
+    const double scale = 1.0 / ((double)dsize / (double)ssize);
+    for (int d = 0; d < dsize; ++d) {
+        float f = (float)((d + 0.5) * scale - 0.5);
+        int s = cv_floor(f);
+        f -= (float)s;
+        if (s < 0) { s = 0; f = 0.f; }
+        if (s >= ssize - 1) { s = ssize - 1; f = 0.f; }
+        ofs[d] = s;
+        coef[2 * d + 0] = (int16_t)cv_round((1.f - f) * 2048.f);
+        coef[2 * d + 1] = (int16_t)cv_round(f * 2048.f);
+    }
+}
+
+void resize_linear_u8(const uint8_t* src, int sw, int sh, int sstride,
+                      uint8_t* dst, int dw, int dh, int dstride) {
+    std::vector<int> xofs(dw), yofs(dh);
+    std::vector<int16_t> xa(2 * dw), yb(2 * dh);
+    resize_axis_table(sw, dw, xofs.data(), xa.data());
+    resize_axis_table(sh, dh, yofs.data(), yb.data());
+    std::vector<int> row0(dw), row1(dw);
+    for (int dy = 0; dy < dh; ++dy) {
+        const int sy0 = yofs[dy];
+        const int sy1 = std::min(sy0 + 1, sh - 1);
+        const uint8_t* s0 = src + (size_t)sy0 * sstride;
+        const uint8_t* s1 = src + (size_t)sy1 * sstride;
+        for (int dx = 0; dx < dw; ++dx) {
+            const int x0 = xofs[dx];
+            const int x1 = std::min(x0 + 1, sw - 1);
+            const int a0 = xa[2 * dx], a1 = xa[2 * dx + 1];
+            row0[dx] = s0[x0] * a0 + s0[x1] * a1;
+            row1[dx] = s1[x0] * a0 + s1[x1] * a1;
+        }
+        const int b0 = yb[2 * dy], b1 = yb[2 * dy + 1];
+        uint8_t* d = dst + (size_t)dy * dstride;
+        for (int dx = 0; dx < dw; ++dx)
+            d[dx] = (uint8_t)((((b0 * (row0[dx] >> 4)) >> 16) + ((b1 * (row1[dx] >> 4)) >> 16) + 2) >> 2);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// copyMakeBorder, BORDER_REFLECT_101:  gfedcb|abcdefgh|gfedcba
+// ---------------------------------------------------------------------------------------------
+static inline int reflect101(int i, int n) {
+    if (n == 1) return 0;
+    while (i < 0 || i >= n) {
+        if (i < 0) i = -i;
+        else i = 2 * n - 2 - i;
+    }
+    return i;
+}
+
+void copy_make_border_reflect101(const uint8_t* src, int w, int h, int sstride,
+                                 uint8_t* dst, int dstride, int border) {
+    for (int y = 0; y < h + 2 * border; ++y) {
+        const uint8_t* s = src + (size_t)reflect101(y - border, h) * sstride;
+        uint8_t* d = dst + (size_t)y * dstride;
+        for (int x = 0; x < w + 2 * border; ++x) d[x] = s[reflect101(x - border, w)];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// FAST 9/16
+// ---------------------------------------------------------------------------------------------
+static const int kCircle[16][2] = {{0, 3},  {1, 3},   {2, 2},   {3, 1},  {3, 0},  {3, -1}, {2, -2}, {1, -3},
+                                   {0, -3}, {-1, -3}, {-2, -2}, {-3, -1}, {-3, 0}, {-3, 1}, {-2, 2}, {-1, 3}};
+
+int fast_score(const uint8_t* p, int stride) {
+    const int v = p[0];
+    int d[25];
+    for (int k = 0; k < 16; ++k) d[k] = (int)p[kCircle[k][1] * stride + kCircle[k][0]] - v;
+    for (int k = 16; k < 25; ++k) d[k] = d[k - 16];
+    int best = -256;
+    for (int k = 0; k < 16; ++k) {
+        int mn = 256, mx = -256;
+        for (int j = 0; j < 9; ++j) {
+            mn = std::min(mn, d[k + j]);
+            mx = std::max(mx, d[k + j]);
+        }
+        best = std::max(best, std::max(mn, -mx));  // brighter arc: min(p-v); darker arc: min(v-p) = -max(p-v)
+    }
+    return best - 1;
+}
+
+// Necessary condition for a 9-arc at threshold t: of every opposing pair (k, k+8) at least one pixel lies in the
+// arc, so all 8 pairs must hold a brighter (or all 8 a darker) pixel.  Only an accelerator: fast_score decides.
+static inline bool maybe_corner(const uint8_t* p, int stride, int t) {
+    const int v = p[0];
+    int flags = 3;
+    for (int k = 0; k < 8 && flags; ++k) {
+        const int a = (int)p[kCircle[k][1] * stride + kCircle[k][0]] - v;
+        const int b = (int)p[kCircle[k + 8][1] * stride + kCircle[k + 8][0]] - v;
+        flags &= ((a > t || b > t) ? 1 : 0) | ((a < -t || b < -t) ? 2 : 0);
+    }
+    return flags != 0;
+}
+
+void fast9_16(const uint8_t* img, int w, int h, int stride, int threshold, bool nonmax,
+              std::vector<KeyPoint>& out) {
+    out.clear();
+    threshold = std::min(std::max(threshold, 0), 255);
+    if (w < 7 || h < 7) return;
+    // score map over the 3-px inset interior, 0 elsewhere and for non-corners
+    std::vector<int> sc((size_t)w * h, 0);
+    for (int y = 3; y < h - 3; ++y)
+        for (int x = 3; x < w - 3; ++x) {
+            if (!maybe_corner(img + (size_t)y * stride + x, stride, threshold)) continue;
+            const int s = fast_score(img + (size_t)y * stride + x, stride);
+            if (s >= threshold) sc[(size_t)y * w + x] = nonmax ? s : 1;
+        }
+    for (int y = 3; y < h - 3; ++y)
+        for (int x = 3; x < w - 3; ++x) {
+            const int s = sc[(size_t)y * w + x];
+            if (s == 0) continue;
+            bool keep = true;
+            if (nonmax) {
+                for (int dy = -1; dy <= 1 && keep; ++dy)
+                    for (int dx = -1; dx <= 1; ++dx) {
+                        if (dx == 0 && dy == 0) continue;
+                        if (s <= sc[(size_t)(y + dy) * w + (x + dx)]) { keep = false; break; }
+                    }
+            }
+            if (keep) {
+                KeyPoint kp;
+                kp.x = (float)x; kp.y = (float)y; kp.size = 7.f; kp.angle = -1.f;
+                kp.response = nonmax ? (float)s : 0.f;
+                kp.octave = 0; kp.class_id = -1;
+                out.push_back(kp);
+            }
+        }
+}
+
+// ---------------------------------------------------------------------------------------------
+// GaussianBlur 7x7 sigma 2, 8U bit-exact fixed point: kernel [18 34 48 56 48 34 18]/256 per axis,
+// exact integer accumulation, one rounding (v + 2^15) >> 16, reflect-101 borders.
+// ---------------------------------------------------------------------------------------------
+void gaussian_blur_7x7_s2(const uint8_t* src, int w, int h, int sstride, uint8_t* dst, int dstride) {
+    static const int K[7] = {18, 34, 48, 56, 48, 34, 18};
+    std::vector<uint16_t> tmp((size_t)w * h);
+    for (int y = 0; y < h; ++y) {
+        const uint8_t* s = src + (size_t)y * sstride;
+        for (int x = 0; x < w; ++x) {
+            int acc = 0;
+            for (int k = 0; k < 7; ++k) acc += K[k] * s[reflect101(x + k - 3, w)];
+            tmp[(size_t)y * w + x] = (uint16_t)acc;  // <= 255*256
+        }
+    }
+    for (int y = 0; y < h; ++y) {
+        uint8_t* d = dst + (size_t)y * dstride;
+        for (int x = 0; x < w; ++x) {
+            uint32_t acc = 0;
+            for (int k = 0; k < 7; ++k) acc += (uint32_t)K[k] * tmp[(size_t)reflect101(y + k - 3, h) * w + x];
+            d[x] = (uint8_t)((acc + 32768u) >> 16);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// fastAtan2: float32 odd polynomial on the octant, no FMA contraction (build with -ffp-contract=off)
+// ---------------------------------------------------------------------------------------------
+float fast_atan2(float y, float x) {
+    const float P1 = 57.283626556396484f, P3 = -18.66744613647461f, P5 = 8.914000511169434f,
+                P7 = -2.539724588394165f;
+    const float eps = (float)DBL_EPSILON;
+    const float ax = std::fabs(x), ay = std::fabs(y);
+    float a, c, c2;
+    if (ax >= ay) {
+        c = ay / (ax + eps);
+        c2 = c * c;
+        a = (((P7 * c2 + P5) * c2 + P3) * c2 + P1) * c;
+    } else {
+        c = ax / (ay + eps);
+        c2 = c * c;
+        a = 90.f - (((P7 * c2 + P5) * c2 + P3) * c2 + P1) * c;
+    }
+    if (x < 0) a = 180.f - a;
+    if (y < 0) a = 360.f - a;
+    return a;
+}
+
+}  // namespace orbo

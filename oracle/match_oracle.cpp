@@ -1,0 +1,348 @@
+// TEST INFRASTRUCTURE ONLY -- CPU oracle (see match_oracle.h). Build: -O2 -ffp-contract=off.
+#include "match_oracle.h"
+
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstring>
+
+namespace orbo {
+
+// ORBmatcher.cc:1675-1691 -- SWAR bit count over 8 int32 words
+int descriptor_distance(const uint8_t* a, const uint8_t* b) {
+    int dist = 0;
+    for (int i = 0; i < 8; ++i) {
+        uint32_t wa, wb;
+        std::memcpy(&wa, a + 4 * i, 4);
+        std::memcpy(&wb, b + 4 * i, 4);
+        uint32_t v = wa ^ wb;
+        v = v - ((v >> 1) & 0x55555555u);
+        v = (v & 0x33333333u) + ((v >> 2) & 0x33333333u);
+        dist += (int)((((v + (v >> 4)) & 0x0F0F0F0Fu) * 0x01010101u) >> 24);
+    }
+    return dist;
+}
+
+// ORBmatcher.cc:1629-1670
+void three_maxima(const int* sz, int L, int& i1, int& i2, int& i3) {
+    int m1 = 0, m2 = 0, m3 = 0;
+    i1 = i2 = i3 = -1;
+    for (int i = 0; i < L; ++i) {
+        const int s = sz[i];
+        if (s > m1) { m3 = m2; m2 = m1; m1 = s; i3 = i2; i2 = i1; i1 = i; }
+        else if (s > m2) { m3 = m2; m2 = s; i3 = i2; i2 = i; }
+        else if (s > m3) { m3 = s; i3 = i; }
+    }
+    if ((float)m2 < 0.1f * (float)m1) { i2 = -1; i3 = -1; }
+    else if ((float)m3 < 0.1f * (float)m1) { i3 = -1; }
+}
+
+// e.g. ORBmatcher.cc:475-481 ; factor = 1.0f/HISTO_LENGTH is the upstream quirk (bins are 30 degrees wide)
+int rotation_bin(float a1, float a2) {
+    const float factor = 1.0f / HISTO_LENGTH;
+    float rot = a1 - a2;
+    if (rot < 0.0) rot += 360.0f;
+    int bin = (int)std::round(rot * factor);
+    if (bin == HISTO_LENGTH) bin = 0;
+    return bin;
+}
+
+// Frame.cc:574-589 + 726-736
+void FrameArrays::buildGrid() {
+    std::vector<std::vector<int>> cells(GRID_COLS * GRID_ROWS);
+    for (int i = 0; i < n; ++i) {
+        const int px = (int)std::round((keysUn[i].x - minX) * invW);
+        const int py = (int)std::round((keysUn[i].y - minY) * invH);
+        if (px < 0 || px >= GRID_COLS || py < 0 || py >= GRID_ROWS) continue;
+        cells[px * GRID_ROWS + py].push_back(i);
+    }
+    cellStart.assign(GRID_COLS * GRID_ROWS + 1, 0);
+    cellIdx.clear();
+    for (int c = 0; c < GRID_COLS * GRID_ROWS; ++c) {
+        cellStart[c] = (int)cellIdx.size();
+        cellIdx.insert(cellIdx.end(), cells[c].begin(), cells[c].end());
+    }
+    cellStart[GRID_COLS * GRID_ROWS] = (int)cellIdx.size();
+}
+
+// Frame.cc:671-724
+void FrameArrays::featuresInArea(float x, float y, float r, int minLevel, int maxLevel, std::vector<int>& out) const {
+    out.clear();
+    const int c0 = std::max(0, (int)std::floor((x - minX - r) * invW));
+    if (c0 >= GRID_COLS) return;
+    const int c1 = std::min(GRID_COLS - 1, (int)std::ceil((x - minX + r) * invW));
+    if (c1 < 0) return;
+    const int r0 = std::max(0, (int)std::floor((y - minY - r) * invH));
+    if (r0 >= GRID_ROWS) return;
+    const int r1 = std::min(GRID_ROWS - 1, (int)std::ceil((y - minY + r) * invH));
+    if (r1 < 0) return;
+    const bool checkLevels = (minLevel > 0) || (maxLevel >= 0);
+    for (int ix = c0; ix <= c1; ++ix)
+        for (int iy = r0; iy <= r1; ++iy) {
+            const int c = ix * GRID_ROWS + iy;
+            for (int k = cellStart[c]; k < cellStart[c + 1]; ++k) {
+                const KeyPoint& kp = keysUn[cellIdx[k]];
+                if (checkLevels) {
+                    if (kp.octave < minLevel) continue;
+                    if (maxLevel >= 0 && kp.octave > maxLevel) continue;
+                }
+                const float dx = kp.x - x, dy = kp.y - y;
+                if (std::fabs(dx) < r && std::fabs(dy) < r) out.push_back(cellIdx[k]);
+            }
+        }
+}
+
+// Shared tail of every search: prune matches whose rotation bin is not one of the three dominant ones.
+namespace {
+struct RotHist {
+    std::vector<int> bins[HISTO_LENGTH];
+    void add(float a1, float a2, int v) { bins[rotation_bin(a1, a2)].push_back(v); }
+    template <class F> void pruneMinor(F drop) const {
+        int sz[HISTO_LENGTH], i1, i2, i3;
+        for (int i = 0; i < HISTO_LENGTH; ++i) sz[i] = (int)bins[i].size();
+        three_maxima(sz, HISTO_LENGTH, i1, i2, i3);
+        for (int i = 0; i < HISTO_LENGTH; ++i) {
+            if (i == i1 || i == i2 || i == i3) continue;
+            for (int v : bins[i]) drop(v);
+        }
+    }
+};
+}  // namespace
+
+// ORBmatcher.cc:405-520
+int search_for_initialization(const FrameArrays& F1, const FrameArrays& F2, float* prevXY, int* m12,
+                              int windowSize, float nnratio, bool checkOri) {
+    int nmatches = 0;
+    std::fill(m12, m12 + F1.n, -1);
+    RotHist hist;
+    std::vector<int> matchedDist(F2.n, INT_MAX), m21(F2.n, -1), cand;
+    for (int i1 = 0; i1 < F1.n; ++i1) {
+        const int level1 = F1.keysUn[i1].octave;
+        if (level1 > 0) continue;
+        F2.featuresInArea(prevXY[2 * i1], prevXY[2 * i1 + 1], (float)windowSize, level1, level1, cand);
+        if (cand.empty()) continue;
+        const uint8_t* d1 = F1.desc + (size_t)i1 * 32;
+        int best = INT_MAX, second = INT_MAX, bestIdx = -1;
+        for (int i2 : cand) {
+            const int dist = descriptor_distance(d1, F2.desc + (size_t)i2 * 32);
+            if (matchedDist[i2] <= dist) continue;
+            if (dist < best) { second = best; best = dist; bestIdx = i2; }
+            else if (dist < second) second = dist;
+        }
+        if (best <= TH_LOW && (float)best < (float)second * nnratio) {
+            if (m21[bestIdx] >= 0) { m12[m21[bestIdx]] = -1; --nmatches; }
+            m12[i1] = bestIdx;
+            m21[bestIdx] = i1;
+            matchedDist[bestIdx] = best;
+            ++nmatches;
+            if (checkOri) hist.add(F1.keysUn[i1].angle, F2.keysUn[bestIdx].angle, i1);
+        }
+    }
+    if (checkOri)
+        hist.pruneMinor([&](int i1) { if (m12[i1] >= 0) { m12[i1] = -1; --nmatches; } });
+    for (int i1 = 0; i1 < F1.n; ++i1)
+        if (m12[i1] >= 0) {
+            prevXY[2 * i1] = F2.keysUn[m12[i1]].x;
+            prevXY[2 * i1 + 1] = F2.keysUn[m12[i1]].y;
+        }
+    return nmatches;
+}
+
+// ORBmatcher.cc:1341-1498 (projection itself, :1376-1388, stays with the caller)
+int search_by_projection_frame(const FrameArrays& cur, const float* sf, const float* uRight, float mbf,
+                               const ProjQuery* q, const uint8_t* qdesc, int nq, float th, int mode,
+                               const uint8_t* curOccupied, int* curMatch, bool checkOri) {
+    int nmatches = 0;
+    std::vector<uint8_t> occ(curOccupied, curOccupied + cur.n);
+    std::fill(curMatch, curMatch + cur.n, -1);
+    RotHist hist;
+    std::vector<int> cand;
+    for (int i = 0; i < nq; ++i) {
+        if (!q[i].valid) continue;
+        const float u = q[i].u, v = q[i].v;
+        if (u < cur.minX || u > cur.maxX) continue;
+        if (v < cur.minY || v > cur.maxY) continue;
+        const int oct = q[i].octave;
+        const float radius = th * sf[oct];
+        if (mode == 1) cur.featuresInArea(u, v, radius, oct, -1, cand);
+        else if (mode == 2) cur.featuresInArea(u, v, radius, 0, oct, cand);
+        else cur.featuresInArea(u, v, radius, oct - 1, oct + 1, cand);
+        if (cand.empty()) continue;
+        const uint8_t* d = qdesc + (size_t)i * 32;
+        int best = 256, bestIdx = -1;
+        for (int i2 : cand) {
+            if (occ[i2]) continue;
+            if (uRight && uRight[i2] > 0) {
+                const float ur = u - mbf * q[i].invz;
+                const float er = std::fabs(ur - uRight[i2]);
+                if (er > radius) continue;
+            }
+            const int dist = descriptor_distance(d, cur.desc + (size_t)i2 * 32);
+            if (dist < best) { best = dist; bestIdx = i2; }
+        }
+        if (best <= TH_HIGH) {
+            curMatch[bestIdx] = i;
+            occ[bestIdx] = q[i].obsPositive ? 1 : 0;
+            ++nmatches;
+            if (checkOri) hist.add(q[i].angle, cur.keysUn[bestIdx].angle, bestIdx);
+        }
+    }
+    if (checkOri)
+        hist.pruneMinor([&](int i2) { curMatch[i2] = -1; --nmatches; });
+    return nmatches;
+}
+
+// ORBmatcher.cc:45-129 (+131-137)
+int search_by_projection_points(const FrameArrays& F, const float* sf, const float* uRight, const MapPointQuery* q,
+                                const uint8_t* qdesc, int nq, float th, float nnratio, const uint8_t* occupied,
+                                int* match) {
+    int nmatches = 0;
+    std::vector<uint8_t> occ(occupied, occupied + F.n);
+    std::fill(match, match + F.n, -1);
+    const bool bFactor = th != 1.0;
+    std::vector<int> cand;
+    for (int i = 0; i < nq; ++i) {
+        if (!q[i].inView) continue;
+        const int lvl = q[i].level;
+        float r = ((double)q[i].viewCos > 0.998) ? 2.5f : 4.0f;
+        if (bFactor) r *= th;
+        F.featuresInArea(q[i].projX, q[i].projY, r * sf[lvl], lvl - 1, lvl, cand);
+        if (cand.empty()) continue;
+        const uint8_t* d = qdesc + (size_t)i * 32;
+        int best = 256, bestLevel = -1, second = 256, secondLevel = -1, bestIdx = -1;
+        for (int idx : cand) {
+            if (occ[idx]) continue;
+            if (uRight && uRight[idx] > 0) {
+                const float er = std::fabs(q[i].projXR - uRight[idx]);
+                if (er > r * sf[lvl]) continue;
+            }
+            const int dist = descriptor_distance(d, F.desc + (size_t)idx * 32);
+            if (dist < best) {
+                second = best; best = dist; secondLevel = bestLevel;
+                bestLevel = F.keysUn[idx].octave; bestIdx = idx;
+            } else if (dist < second) {
+                secondLevel = F.keysUn[idx].octave; second = dist;
+            }
+        }
+        if (best <= TH_HIGH) {
+            if (bestLevel == secondLevel && (float)best > nnratio * (float)second) continue;
+            match[bestIdx] = i;
+            occ[bestIdx] = q[i].obsPositive ? 1 : 0;
+            ++nmatches;
+        }
+    }
+    return nmatches;
+}
+
+// ORBmatcher.cc:140-157
+static bool epipolar_ok(const KeyPoint& k1, const KeyPoint& k2, const EpiParams& ep) {
+    const float* F = ep.F12;  // row-major 3x3
+    const float a = k1.x * F[0] + k1.y * F[3] + F[6];
+    const float b = k1.x * F[1] + k1.y * F[4] + F[7];
+    const float c = k1.x * F[2] + k1.y * F[5] + F[8];
+    const float num = a * k2.x + b * k2.y + c;
+    const float den = a * a + b * b;
+    if (den == 0) return false;
+    const float dsqr = num * num / den;
+    return (double)dsqr < 3.84 * (double)ep.levelSigma2_2[k2.octave];
+}
+
+// ORBmatcher.cc:657-823
+int search_for_triangulation(const FrameArrays& K1, const FrameArrays& K2, const FeatVec& fv1, const FeatVec& fv2,
+                             const uint8_t* has1, const uint8_t* has2, const float* uR1, const float* uR2,
+                             const EpiParams& ep, bool onlyStereo, bool checkOri, int* m12) {
+    int nmatches = 0;
+    std::fill(m12, m12 + K1.n, -1);
+    RotHist hist;
+    int a = 0, b = 0;
+    while (a < fv1.nNodes && b < fv2.nNodes) {
+        if (fv1.nodeId[a] < fv2.nodeId[b]) { ++a; continue; }   // lower_bound on a sorted map == skip ahead
+        if (fv1.nodeId[a] > fv2.nodeId[b]) { ++b; continue; }
+        for (int p1 = fv1.start[a]; p1 < fv1.start[a + 1]; ++p1) {
+            const int idx1 = fv1.idx[p1];
+            if (has1[idx1]) continue;
+            const bool stereo1 = uR1 ? (uR1[idx1] >= 0) : false;
+            if (onlyStereo && !stereo1) continue;
+            const KeyPoint& kp1 = K1.keysUn[idx1];
+            const uint8_t* d1 = K1.desc + (size_t)idx1 * 32;
+            int best = TH_LOW, bestIdx = -1;
+            for (int p2 = fv2.start[b]; p2 < fv2.start[b + 1]; ++p2) {
+                const int idx2 = fv2.idx[p2];
+                if (has2[idx2]) continue;   // vbMatched2 is never set in the reference (:725)
+                const bool stereo2 = uR2 ? (uR2[idx2] >= 0) : false;
+                if (onlyStereo && !stereo2) continue;
+                const int dist = descriptor_distance(d1, K2.desc + (size_t)idx2 * 32);
+                if (dist > TH_LOW || dist > best) continue;
+                const KeyPoint& kp2 = K2.keysUn[idx2];
+                if (!stereo1 && !stereo2) {
+                    const float dex = ep.ex - kp2.x, dey = ep.ey - kp2.y;
+                    if (dex * dex + dey * dey < 100 * ep.scaleFactors2[kp2.octave]) continue;
+                }
+                if (epipolar_ok(kp1, kp2, ep)) { bestIdx = idx2; best = dist; }
+            }
+            if (bestIdx >= 0) {
+                m12[idx1] = bestIdx;
+                ++nmatches;
+                if (checkOri) hist.add(kp1.angle, K2.keysUn[bestIdx].angle, idx1);
+            }
+        }
+        ++a; ++b;
+    }
+    if (checkOri)
+        hist.pruneMinor([&](int i1) { m12[i1] = -1; --nmatches; });
+    return nmatches;
+}
+
+int bruteforce_match(const uint8_t* q, const float* qAngle, int nq, const uint8_t* t, const float* tAngle, int nt,
+                     float nnratio, bool checkOri, int* bestDist, int* secondDist, int* bestIdx, int* m12) {
+    int nmatches = 0;
+    RotHist hist;
+    for (int i = 0; i < nq; ++i) {
+        int best = INT_MAX, second = INT_MAX, idx = -1;
+        for (int j = 0; j < nt; ++j) {
+            const int dist = descriptor_distance(q + (size_t)i * 32, t + (size_t)j * 32);
+            if (dist < best) { second = best; best = dist; idx = j; }
+            else if (dist < second) second = dist;
+        }
+        bestDist[i] = best; secondDist[i] = second; bestIdx[i] = idx;
+        m12[i] = -1;
+        if (best <= TH_LOW && (float)best < (float)second * nnratio) {
+            m12[i] = idx;
+            ++nmatches;
+            if (checkOri) hist.add(qAngle[i], tAngle[idx], i);
+        }
+    }
+    if (checkOri)
+        hist.pruneMinor([&](int i1) { if (m12[i1] >= 0) { m12[i1] = -1; --nmatches; } });
+    return nmatches;
+}
+
+// ORBmatcher.cc:566-618 + 634-652 with every index in one shared node and every map point valid
+int kf_pair_match_count(const uint8_t* d1, const float* a1, int n1, const uint8_t* d2, const float* a2, int n2,
+                        float nnratio, bool checkOri, int* m12out) {
+    int nmatches = 0;
+    std::vector<uint8_t> matched2(n2, 0);
+    std::vector<int> m12(n1, -1);
+    RotHist hist;
+    for (int i1 = 0; i1 < n1; ++i1) {
+        int best = 256, second = 256, bestIdx = -1;
+        for (int i2 = 0; i2 < n2; ++i2) {
+            if (matched2[i2]) continue;
+            const int dist = descriptor_distance(d1 + (size_t)i1 * 32, d2 + (size_t)i2 * 32);
+            if (dist < best) { second = best; best = dist; bestIdx = i2; }
+            else if (dist < second) second = dist;
+        }
+        if (best < TH_LOW && (float)best < nnratio * (float)second) {
+            m12[i1] = bestIdx;
+            matched2[bestIdx] = 1;
+            if (checkOri) hist.add(a1[i1], a2[bestIdx], i1);
+            ++nmatches;
+        }
+    }
+    if (checkOri)
+        hist.pruneMinor([&](int i1) { m12[i1] = -1; --nmatches; });
+    if (m12out) std::copy(m12.begin(), m12.end(), m12out);
+    return nmatches;
+}
+
+}  // namespace orbo

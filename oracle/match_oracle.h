@@ -1,0 +1,94 @@
+// TEST INFRASTRUCTURE ONLY -- CPU oracle of the reference's ORBmatcher search loops on plain arrays.
+//
+// Restates (all in /root/reference/src):
+//   ORBmatcher::DescriptorDistance                       ORBmatcher.cc:1675-1691
+//   ORBmatcher::ComputeThreeMaxima                       ORBmatcher.cc:1629-1670
+//   Frame::AssignFeaturesToGrid / PosInGrid              Frame.cc:574-589, 726-736
+//   Frame::GetFeaturesInArea                             Frame.cc:671-724  (KeyFrame.cc:1138-1177)
+//   ORBmatcher::SearchForInitialization                  ORBmatcher.cc:405-520
+//   ORBmatcher::SearchByProjection(Frame&,Frame&,th,mono) ORBmatcher.cc:1341-1498
+//   ORBmatcher::SearchByProjection(Frame&,vector<MP*>,th) ORBmatcher.cc:45-129
+//   ORBmatcher::SearchForTriangulation                   ORBmatcher.cc:657-823 (+140-157)
+//   ORBmatcher::SearchByBoW(KF,KF) inner loop            ORBmatcher.cc:566-618 (brute-force / all-pairs)
+// The object graphs (Frame, KeyFrame, MapPoint) are flattened to the arrays the loops actually read.
+#pragma once
+#include <cstdint>
+#include <vector>
+
+#include "cvprims.h"
+
+namespace orbo {
+
+constexpr int TH_HIGH = 100;
+constexpr int TH_LOW = 50;
+constexpr int HISTO_LENGTH = 30;
+constexpr int GRID_COLS = 64;   // Frame.h:42
+constexpr int GRID_ROWS = 48;   // Frame.h:41
+
+int descriptor_distance(const uint8_t* a, const uint8_t* b);
+void three_maxima(const int* histoSizes, int L, int& i1, int& i2, int& i3);
+int rotation_bin(float a1, float a2);  // bin of (a1 - a2) as every search computes it
+
+// What the search loops read of a Frame / KeyFrame.
+struct FrameArrays {
+    int n = 0;
+    const KeyPoint* keysUn = nullptr;   // pt, angle, octave
+    const uint8_t* desc = nullptr;      // n x 32
+    float minX = 0, minY = 0, maxX = 0, maxY = 0;   // mnMinX ... (static Frame members)
+    float invW = 0, invH = 0;           // mfGridElementWidthInv / HeightInv
+    // CSR form of mGrid[64][48]: cell id = ix*48+iy, members in push_back order
+    std::vector<int> cellStart, cellIdx;
+    void buildGrid();                   // AssignFeaturesToGrid
+    // GetFeaturesInArea; minLevel=-1,maxLevel=-1 reproduces the defaults (and the KeyFrame overload)
+    void featuresInArea(float x, float y, float r, int minLevel, int maxLevel, std::vector<int>& out) const;
+};
+
+int search_for_initialization(const FrameArrays& F1, const FrameArrays& F2, float* prevMatchedXY /* n1 x 2, in/out */,
+                              int* matches12 /* n1 */, int windowSize, float nnratio, bool checkOri);
+
+struct ProjQuery {          // one LastFrame keypoint with a map point (ORBmatcher.cc:1365-1410)
+    float u, v;             // projection into the current frame (host computes it)
+    float invz;             // 1/z in the current camera, for the stereo check
+    int32_t octave;         // LastFrame.mvKeys[i].octave
+    int32_t valid;          // pMP != NULL && !outlier && invz >= 0
+    int32_t obsPositive;    // pMP->Observations() > 0 (what a later query's skip test reads)
+    float angle;            // LastFrame.mvKeysUn[i].angle
+};
+// mode: 0 = [oct-1, oct+1] (mono / no motion), 1 = forward (>= oct), 2 = backward (0..oct)
+// curOccupied[i2] != 0 : CurrentFrame.mvpMapPoints[i2] already holds a point with observations
+// curMatch[i2] (out)   : index of the query assigned to keypoint i2, or -1
+int search_by_projection_frame(const FrameArrays& cur, const float* scaleFactors, const float* uRight /* may be null */,
+                               float mbf, const ProjQuery* q, const uint8_t* qdesc, int nq, float th, int mode,
+                               const uint8_t* curOccupied, int* curMatch, bool checkOri);
+
+struct MapPointQuery {      // ORBmatcher.cc:45-129
+    float projX, projY, projXR;
+    float viewCos;
+    int32_t level;          // mnTrackScaleLevel
+    int32_t inView;         // mbTrackInView && !isBad()
+    int32_t obsPositive;
+};
+int search_by_projection_points(const FrameArrays& F, const float* scaleFactors, const float* uRight,
+                                const MapPointQuery* q, const uint8_t* qdesc, int nq, float th, float nnratio,
+                                const uint8_t* occupied, int* match /* n, out */);
+
+// SearchForTriangulation. Feature vectors are given as node-sorted CSR: nodeId[k], start[k]..start[k+1] into idx[].
+struct FeatVec { int nNodes; const int* nodeId; const int* start; const int* idx; };
+struct EpiParams { float F12[9]; float ex, ey; const float* scaleFactors2; const float* levelSigma2_2; };
+int search_for_triangulation(const FrameArrays& K1, const FrameArrays& K2, const FeatVec& fv1, const FeatVec& fv2,
+                             const uint8_t* hasMapPoint1, const uint8_t* hasMapPoint2, const float* uRight1,
+                             const float* uRight2, const EpiParams& ep, bool onlyStereo, bool checkOri,
+                             int* matches12 /* n1, out */);
+
+// Brute force, every query against every train descriptor (no window, no one-to-one constraint):
+// best / second / index with strict '<' (first wins), accept best<=TH_LOW && best < (float)second*ratio,
+// then the rotation-histogram pruning.  (SearchForInitialization's inner loop + accept rule, ORBmatcher.cc:432-461)
+int bruteforce_match(const uint8_t* q, const float* qAngle, int nq, const uint8_t* t, const float* tAngle, int nt,
+                     float nnratio, bool checkOri, int* bestDist, int* secondDist, int* bestIdx, int* matches12);
+
+// All-pairs keyframe matching count with SearchByBoW(KF,KF) semantics minus the BoW gating
+// (ORBmatcher.cc:566-618 + 634-652): one-to-one through vbMatched2, best<TH_LOW, ratio on floats.
+int kf_pair_match_count(const uint8_t* d1, const float* a1, int n1, const uint8_t* d2, const float* a2, int n2,
+                        float nnratio, bool checkOri, int* matches12 /* may be null */);
+
+}  // namespace orbo
