@@ -1,0 +1,198 @@
+/* orbb200 -- B200-native (sm_100a) ORB feature extraction and binary-descriptor Hamming matching.
+ *
+ * C ABI of the drop-in replacement for the data-parallel front-end of hwb0314/VI-ORB-SLAM-ICRA2018:
+ *   ORB_SLAM2::ORBextractor            /root/reference/include/ORBextractor.h:44-131, src/ORBextractor.cc
+ *   ORB_SLAM2::ORBmatcher (searches)   /root/reference/include/ORBmatcher.h:41-83,    src/ORBmatcher.cc
+ *   Frame grid (candidate lists)       /root/reference/src/Frame.cc:574-589, 671-736
+ *
+ * Plain pointers and sizes only; no C++ or torch types cross this boundary.  Every entry point returns an
+ * orb_status; orb_last_error() gives the message of the last failure on the calling thread.  All compute runs in
+ * CUDA kernels: there is no CPU fallback, and a missing/failed device is an error, never a silent slow path.
+ * "host" entry points take host pointers and are synchronous; "_device" entry points take device pointers, enqueue on
+ * the handle's stream (or the one given) and return without synchronising.
+ *
+ * The C++ adapter with the reference's own class names and signatures is adapter/ORBextractor.h, adapter/ORBmatcher.h.
+ */
+#ifndef ORBB200_H
+#define ORBB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORBB200_VERSION 100
+
+typedef enum {
+    ORB_OK = 0,
+    ORB_ERR_INVALID = 1,      /* bad argument (null pointer, size out of range, geometry the reference cannot handle) */
+    ORB_ERR_CAPACITY = 2,     /* an output or workspace bound given at create time would be exceeded */
+    ORB_ERR_CUDA = 3,         /* a CUDA call failed; see orb_last_error() */
+    ORB_ERR_UNSUPPORTED = 4
+} orb_status;
+
+/* cv::KeyPoint, byte for byte (28 B): what ORBextractor::operator() fills (ORBextractor.cc:839-849, 1112-1121) */
+typedef struct {
+    float x, y;        /* pt, level-0 pixel coordinates */
+    float size;        /* (int)(31 * mvScaleFactor[octave]) */
+    float angle;       /* IC_Angle, degrees in [0, 360) */
+    float response;    /* FAST score */
+    int32_t octave;
+    int32_t class_id;  /* -1 */
+} orb_keypoint;
+
+const char* orb_last_error(void);
+int orb_version(void);
+/* number of visible CUDA devices, or a negative value when the runtime cannot be initialised */
+int orb_device_count(void);
+
+/* ================================================================================================ extractor */
+typedef struct orbx_extractor* orbx_handle;
+
+/* ORBextractor::ORBextractor(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST)   (ORBextractor.cc:412-472)
+ * max_width/max_height/max_batch size the device arena once; extract calls never allocate.              */
+int orbx_create(int nfeatures, float scale_factor, int nlevels, int ini_th_fast, int min_th_fast,
+                int max_width, int max_height, int max_batch, int device, orbx_handle* out);
+int orbx_destroy(orbx_handle h);
+
+/* Upper bound on keypoints per frame (sum over levels of max(N_l + 2, 4*nIni)); size outputs with it. */
+int orbx_keypoint_capacity(orbx_handle h, int* cap);
+
+/* ORBextractor::operator()(image, mask, keypoints, descriptors)   (ORBextractor.cc:1045-1126; mask is ignored there)
+ * image: 8-bit grayscale, `stride` bytes per row. keypoints[capacity], descriptors[capacity*32]; *n_out = count.
+ * An empty image (width or height 0, or null pointer) returns ORB_OK with *n_out = 0 (ORBextractor.cc:1048). */
+int orbx_extract(orbx_handle h, const uint8_t* image, int width, int height, int stride,
+                 orb_keypoint* keypoints, uint8_t* descriptors, int capacity, int* n_out);
+
+/* The same operator over n_frames independent frames of one size (frame f at images + f*frame_stride).
+ * Outputs for frame f start at keypoints + f*capacity and descriptors + f*capacity*32; n_out[f] = count.       */
+int orbx_extract_batch(orbx_handle h, const uint8_t* images, int n_frames, int width, int height, int stride,
+                       size_t frame_stride, orb_keypoint* keypoints, uint8_t* descriptors, int capacity, int* n_out);
+
+/* Device-resident variant: all pointers are device pointers, work is enqueued on `stream` (a cudaStream_t, NULL =
+ * the handle's own stream) without synchronising; n_frames <= max_batch.                                           */
+int orbx_extract_batch_device(orbx_handle h, const uint8_t* d_images, int n_frames, int width, int height, int stride,
+                              size_t frame_stride, orb_keypoint* d_keypoints, uint8_t* d_descriptors, int capacity,
+                              int* d_n_out, void* stream);
+int orbx_synchronize(orbx_handle h);
+
+/* Getters of ORBextractor.h:81-101 (+ mnFeaturesPerLevel and umax for tests). Arrays hold nlevels (umax: 16) values. */
+int orbx_get_levels(orbx_handle h, int* nlevels);
+int orbx_get_scale_tables(orbx_handle h, float* scale_factors, float* inv_scale_factors, float* level_sigma2,
+                          float* inv_level_sigma2, int* features_per_level, int* umax);
+/* mvImagePyramid[level] of frame `frame` of the last call (ORBextractor.h:103): the padded (w+38)x(h+38) buffer is
+ * copied to `out` (may be NULL to query the size); *w,*h are the level size without the 19-px frame.           */
+int orbx_get_level(orbx_handle h, int frame, int level, uint8_t* out, int* w, int* hgt);
+/* GetTimeOfComputePyramid / ...KeyPointsOctTree / ...Descriptor (ORBextractor.h:51-53), milliseconds of the last
+ * host call measured with CUDA events on the handle's stream.                                                  */
+int orbx_stage_times(orbx_handle h, double* ms3);
+
+/* Introspection for stage-by-stage parity tests (not part of the reference surface). */
+int orbx_debug_candidates(orbx_handle h, int frame, int level, orb_keypoint* out, int cap, int* n);
+int orbx_debug_blurred(orbx_handle h, int frame, int level, uint8_t* out /* w*h */);
+/* number of kernel launches issued by the last extract call */
+int orbx_last_launch_count(orbx_handle h, int* n);
+
+/* ================================================================================================== matcher */
+typedef struct orbm_matcher* orbm_handle;
+typedef struct orbm_frame_s* orbm_frame;
+
+int orbm_create(int device, orbm_handle* out);
+int orbm_destroy(orbm_handle h);
+int orbm_synchronize(orbm_handle h);
+int orbm_last_launch_count(orbm_handle h, int* n);
+
+/* ORBmatcher::DescriptorDistance (ORBmatcher.cc:1675-1691) for n independent pairs a[i], b[i] (32 B each). */
+int orbm_distance(orbm_handle h, const uint8_t* a, const uint8_t* b, int n, int* dist_out);
+
+/* What the search loops read of a Frame / KeyFrame: undistorted keypoints (pt, angle, octave), descriptors and the
+ * static image bounds mnMinX.. (Frame.cc:782-808).  The 64x48 grid is built on the device exactly as
+ * AssignFeaturesToGrid / PosInGrid do (Frame.cc:574-589, 726-736).                                             */
+int orbm_frame_create(orbm_handle h, const orb_keypoint* keys_un, const uint8_t* descriptors, int n,
+                      float min_x, float min_y, float max_x, float max_y, orbm_frame* out);
+int orbm_frame_destroy(orbm_frame f);
+/* mGrid as CSR: cell id = ix*48+iy; cell_start[3073], cell_idx[n] */
+int orbm_frame_grid(orbm_frame f, int* cell_start, int* cell_idx);
+/* Frame::GetFeaturesInArea (Frame.cc:671-724) for nq queries (x,y,r triples); min_level = max_level = -1 gives the
+ * KeyFrame overload (KeyFrame.cc:1138-1177). idx_out[q*cap ...], count_out[q] (count may exceed cap: truncated). */
+int orbm_features_in_area(orbm_frame f, const float* xyr, int nq, int min_level, int max_level, int* idx_out, int cap,
+                          int* count_out);
+
+/* ORBmatcher(nnratio, checkOri).SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize)
+ * (ORBmatcher.cc:405-520). prev_matched_xy: n1 x 2 floats, updated in place; matches12: n1 ints.                  */
+int orbm_search_for_initialization(orbm_handle h, orbm_frame f1, orbm_frame f2, float* prev_matched_xy, int* matches12,
+                                   int window_size, float nnratio, int check_orientation, int* nmatches);
+
+/* One LastFrame keypoint that carries a map point (ORBmatcher.cc:1365-1410). The host projects (cv::Mat GEMM). */
+typedef struct {
+    float u, v;            /* projection into the current frame */
+    float invz;            /* 1/z in the current camera (stereo check) */
+    int32_t octave;        /* LastFrame.mvKeys[i].octave */
+    int32_t valid;         /* pMP && !outlier && invz >= 0 */
+    int32_t obs_positive;  /* pMP->Observations() > 0 */
+    float angle;           /* LastFrame.mvKeysUn[i].angle */
+} orbm_proj_query;
+/* SearchByProjection(Frame& Current, const Frame& Last, th, bMono)  (ORBmatcher.cc:1341-1498).
+ * mode 0: octave window [o-1,o+1]; 1: forward (>= o); 2: backward (0..o).  u_right may be NULL (monocular).
+ * occupied[n_cur] != 0: keypoint already holds a map point with observations.  cur_match[n_cur]: query index or -1. */
+int orbm_search_by_projection(orbm_handle h, orbm_frame cur, const float* scale_factors, int nlevels,
+                              const float* u_right, float mbf, const orbm_proj_query* queries,
+                              const uint8_t* query_desc, int nq, float th, int mode, const uint8_t* occupied,
+                              int* cur_match, int check_orientation, int* nmatches);
+
+typedef struct {
+    float proj_x, proj_y, proj_xr;
+    float view_cos;
+    int32_t level;         /* mnTrackScaleLevel */
+    int32_t in_view;       /* mbTrackInView && !isBad() */
+    int32_t obs_positive;
+} orbm_point_query;
+/* SearchByProjection(Frame& F, const vector<MapPoint*>&, th)  (ORBmatcher.cc:45-129) */
+int orbm_search_by_projection_points(orbm_handle h, orbm_frame f, const float* scale_factors, int nlevels,
+                                     const float* u_right, const orbm_point_query* queries, const uint8_t* query_desc,
+                                     int nq, float th, float nnratio, const uint8_t* occupied, int* match,
+                                     int* nmatches);
+
+/* SearchForTriangulation(pKF1, pKF2, F12, vMatchedPairs, bOnlyStereo)  (ORBmatcher.cc:657-823, 140-157).
+ * Feature vectors (DBoW2 node -> keypoint indices) as node-sorted CSR.  has_point*: keypoint already has a map point.
+ * f12: row-major 3x3; (ex,ey): epipole in image 2 (host computes it, ORBmatcher.cc:664-670).
+ * matches12[n1] = index in KF2 or -1 (the reference's pair list is the entries >= 0 in ascending order).          */
+int orbm_search_for_triangulation(orbm_handle h, orbm_frame kf1, orbm_frame kf2,
+                                  int n_nodes1, const int* node_id1, const int* node_start1, const int* node_idx1,
+                                  int n_nodes2, const int* node_id2, const int* node_start2, const int* node_idx2,
+                                  const uint8_t* has_point1, const uint8_t* has_point2,
+                                  const float* u_right1, const float* u_right2,
+                                  const float* f12, float ex, float ey,
+                                  const float* scale_factors2, const float* level_sigma2_2, int nlevels,
+                                  int only_stereo, int check_orientation, int* matches12, int* nmatches);
+
+/* Brute-force matching of n_pairs independent (query set, train set) pairs: every query against every train
+ * descriptor, best / second-best / index with the reference's strict '<' (first wins), acceptance
+ * best <= TH_LOW && best < (float)second * nnratio, rotation-histogram pruning (ORBmatcher.cc:432-461, 473-512).
+ * Layout: queries[pair][nq][32], trains[pair][nt][32], angles [pair][n]; outputs [pair][nq]; nmatches[pair].
+ * best/second/idx may be NULL.                                                                                   */
+int orbm_bruteforce(orbm_handle h, const uint8_t* queries, const float* q_angles, int nq, const uint8_t* trains,
+                    const float* t_angles, int nt, int n_pairs, float nnratio, int check_orientation,
+                    int* best, int* second, int* idx, int* matches12, int* nmatches);
+int orbm_bruteforce_device(orbm_handle h, const uint8_t* d_queries, const float* d_q_angles, int nq,
+                           const uint8_t* d_trains, const float* d_t_angles, int nt, int n_pairs, float nnratio,
+                           int check_orientation, int* d_best, int* d_second, int* d_idx, int* d_matches12,
+                           int* d_nmatches, void* stream);
+
+/* All-pairs keyframe matching: for query keyframes [q_begin, q_end) against all n_kf keyframes of the table
+ * (n_kf x n_desc x 32 B, angles n_kf x n_desc), the number of matches under SearchByBoW(KF,KF) semantics without the
+ * vocabulary gating (ORBmatcher.cc:566-618, 634-652).  counts: (q_end-q_begin) x n_kf int32, device memory.
+ * db_begin/db_end restrict the db keyframes (columns) computed by this call.                                       */
+int orbm_allpairs_device(orbm_handle h, const uint8_t* d_table, const float* d_angles, int n_kf, int n_desc,
+                         int q_begin, int q_end, int db_begin, int db_end, float nnratio, int check_orientation,
+                         int* d_counts, void* stream);
+
+/* Measured POPC-pipe throughput of this GPU (the roofline denominator for matching): 32-bit POPC per second. */
+int orbm_popc_peak(orbm_handle h, double* popc_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ORBB200_H */

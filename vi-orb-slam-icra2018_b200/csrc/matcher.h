@@ -1,0 +1,24 @@
+// Internal declarations shared by the matcher translation units.
+#pragma once
+#include "common.cuh"
+
+namespace orbb {
+
+int launch_bruteforce(const uint8_t* dq, const float* dqa, int nq, const uint8_t* dt, const float* dta, int nt,
+                      int nPairs, float ratio, int checkOri, int* dBestKey, int* dSecondKey, int* dBest, int* dSecond,
+                      int* dIdx, int* dM12, int* dN, cudaStream_t st, int* launches);
+int launch_allpairs(const uint8_t* dTable, const float* dAngles, int nKf, int nDesc, int qBegin, int qEnd, int dbBegin,
+                    int dbEnd, float ratio, int checkOri, int* dCounts, cudaStream_t st, int* launches);
+int launch_distance(const uint8_t* da, const uint8_t* db, int n, int* dOut, cudaStream_t st, int* launches);
+int measure_popc_peak(cudaStream_t st, double* popcPerS);
+
+}  // namespace orbb
+
+// One matcher = one device, one stream, growable workspaces; not re-entrant per handle (ORBmatcher itself is a
+// stateless value type constructed per call site, ORBmatcher.h:41).
+struct orbm_matcher {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int launches = 0;
+    orbb::DevBuf in0, in1, in2, in3, in4, in5, out0, out1, out2, out3, out4, ws0, ws1, ws2;
+};

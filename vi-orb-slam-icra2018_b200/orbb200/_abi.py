@@ -1,0 +1,57 @@
+"""ctypes signatures of include/orbb200.h (kept in the same order as the header)."""
+import ctypes as C
+
+vp, i32, f32, sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
+
+SIGNATURES = {
+    "orb_last_error": (C.c_char_p, []),
+    "orb_version": (i32, []),
+    "orb_device_count": (i32, []),
+    # extractor
+    "orbx_create": (i32, [i32, f32, i32, i32, i32, i32, i32, i32, i32, vp]),
+    "orbx_destroy": (i32, [vp]),
+    "orbx_keypoint_capacity": (i32, [vp, vp]),
+    "orbx_extract": (i32, [vp, vp, i32, i32, i32, vp, vp, i32, vp]),
+    "orbx_extract_batch": (i32, [vp, vp, i32, i32, i32, i32, sz, vp, vp, i32, vp]),
+    "orbx_extract_batch_device": (i32, [vp, vp, i32, i32, i32, i32, sz, vp, vp, i32, vp, vp]),
+    "orbx_synchronize": (i32, [vp]),
+    "orbx_get_levels": (i32, [vp, vp]),
+    "orbx_get_scale_tables": (i32, [vp, vp, vp, vp, vp, vp, vp]),
+    "orbx_get_level": (i32, [vp, i32, i32, vp, vp, vp]),
+    "orbx_stage_times": (i32, [vp, vp]),
+    "orbx_debug_candidates": (i32, [vp, i32, i32, vp, i32, vp]),
+    "orbx_debug_blurred": (i32, [vp, i32, i32, vp]),
+    "orbx_last_launch_count": (i32, [vp, vp]),
+    # matcher
+    "orbm_create": (i32, [i32, vp]),
+    "orbm_destroy": (i32, [vp]),
+    "orbm_synchronize": (i32, [vp]),
+    "orbm_last_launch_count": (i32, [vp, vp]),
+    "orbm_distance": (i32, [vp, vp, vp, i32, vp]),
+    "orbm_frame_create": (i32, [vp, vp, vp, i32, f32, f32, f32, f32, vp]),
+    "orbm_frame_destroy": (i32, [vp]),
+    "orbm_frame_grid": (i32, [vp, vp, vp]),
+    "orbm_features_in_area": (i32, [vp, vp, i32, i32, i32, vp, i32, vp]),
+    "orbm_search_for_initialization": (i32, [vp, vp, vp, vp, vp, i32, f32, i32, vp]),
+    "orbm_search_by_projection": (i32, [vp, vp, vp, i32, vp, f32, vp, vp, i32, f32, i32, vp, vp, i32, vp]),
+    "orbm_search_by_projection_points": (i32, [vp, vp, vp, i32, vp, vp, vp, i32, f32, f32, vp, vp, vp]),
+    "orbm_search_for_triangulation": (i32, [vp, vp, vp, i32, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, f32, f32,
+                                            vp, vp, i32, i32, i32, vp, vp]),
+    "orbm_bruteforce": (i32, [vp, vp, vp, i32, vp, vp, i32, i32, f32, i32, vp, vp, vp, vp, vp]),
+    "orbm_bruteforce_device": (i32, [vp, vp, vp, i32, vp, vp, i32, i32, f32, i32, vp, vp, vp, vp, vp, vp]),
+    "orbm_allpairs_device": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, f32, i32, vp, vp]),
+    "orbm_popc_peak": (i32, [vp, vp]),
+}
+
+
+def declare(lib):
+    missing = []
+    for name, (res, args) in SIGNATURES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError:
+            missing.append(name)
+            continue
+        fn.restype = res
+        fn.argtypes = args
+    return missing
