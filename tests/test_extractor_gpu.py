@@ -1,0 +1,124 @@
+"""GPU parity of the extractor (kernels 1-6) against the CPU oracle, stage by stage and end to end.
+
+Bar: bit-exact for images, candidate lists (order included), selected set and order, descriptors, coordinates,
+octaves, responses; angles within 1e-4 degrees (north star) -- and in practice bit-exact too, asserted separately.
+"""
+import numpy as np
+import pytest
+
+import orbb200
+from orbb200.synth import synth_frame
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    # seed, w, h, nfeatures, noise_only
+    (0, 752, 480, 1000, False),     # EuRoC mono (config 1)
+    (1, 752, 480, 2000, False),     # EuRoC initialisation extractor (2 x nFeatures, Tracking.cc:822)
+    (2, 1241, 376, 2000, False),    # KITTI (config 2)
+    (3, 752, 480, 1000, True),      # pure-noise stress: ~20k level-0 candidates
+    (4, 640, 480, 500, False),
+    (5, 400, 300, 1500, False),     # more features wanted than the small levels can give
+    (6, 333, 251, 300, False),      # odd sizes
+]
+
+
+def _assert_same_keypoints(got, ref):
+    assert len(got) == len(ref)
+    for f in ("x", "y", "size", "response", "octave", "class_id"):
+        assert np.array_equal(got[f], ref[f]), f
+    assert np.allclose(got["angle"], ref["angle"], rtol=0, atol=1e-4)
+
+
+@pytest.mark.parametrize("seed,w,h,nf,noise", CASES)
+def test_extract_matches_oracle(oracle, seed, w, h, nf, noise):
+    img = synth_frame(seed, w, h, noise_only=noise)
+    ex = orbb200.Extractor(nf, 1.2, 8, 20, 7, max_width=w, max_height=h, max_batch=1)
+    oe = oracle.extractor(nf, 1.2, 8, 20, 7)
+    kps, desc = ex(img)
+    rk, rd = oe.extract(img)
+    # constructor tables (ORBextractor.cc:412-472)
+    t, rt = ex.tables(), oe.tables()
+    for k in rt:
+        assert np.array_equal(t[k], rt[k]), k
+    # stage by stage
+    for l in range(8):
+        assert ex.level_size(l) == oe.level_size(l)
+        assert np.array_equal(ex.level(l), oe.level_padded(l)), "pyramid level %d" % l
+        c, rc = ex.candidates(l), oe.level_candidates(l)
+        assert len(c) == len(rc), "candidate count level %d" % l
+        assert c.tobytes() == rc.tobytes(), "candidates level %d" % l
+        rb = oe.level_blurred(l)
+        if rb is not None:
+            assert np.array_equal(ex.blurred(l), rb), "blur level %d" % l
+    # end to end
+    _assert_same_keypoints(kps, rk)
+    assert np.array_equal(kps["angle"].view(np.uint32), rk["angle"].view(np.uint32)), "angles not bit-exact"
+    assert np.array_equal(desc, rd)
+    assert len(kps) <= ex.capacity
+    assert ex.launch_count() == 12
+    ex.close()
+
+
+def test_batch_equals_single_and_oracle(oracle):
+    frames = np.stack([synth_frame(100 + i, 752, 480) for i in range(5)] + [synth_frame(200, 752, 480, noise_only=True)])
+    ex = orbb200.Extractor(1000, max_width=752, max_height=480, max_batch=4)   # 6 frames -> chunks of 4 + 2
+    oe = oracle.extractor(1000)
+    res = ex.extract_batch(frames)
+    for i, (k, d) in enumerate(res):
+        rk, rd = oe.extract(frames[i])
+        _assert_same_keypoints(k, rk)
+        assert np.array_equal(d, rd)
+    ex.close()
+
+
+def test_strided_input_and_size_change(oracle):
+    big = synth_frame(7, 800, 500)
+    view = big[10:490, 20:772]                     # 752x480 view with stride 800
+    ex = orbb200.Extractor(1000, max_width=752, max_height=480)
+    oe = oracle.extractor(1000)
+    k, d = ex(view)
+    rk, rd = oe.extract(np.ascontiguousarray(view))
+    _assert_same_keypoints(k, rk)
+    assert np.array_equal(d, rd)
+    small = synth_frame(8, 512, 384)               # a different size on the same handle
+    k, d = ex(small)
+    rk, rd = oe.extract(small)
+    _assert_same_keypoints(k, rk)
+    assert np.array_equal(d, rd)
+    ex.close()
+
+
+def test_empty_and_invalid(oracle):
+    ex = orbb200.Extractor(1000, max_width=752, max_height=480)
+    k, d = ex(np.zeros((0, 0), np.uint8))          # empty image: no keypoints, no error (ORBextractor.cc:1048)
+    assert len(k) == 0 and d.shape == (0, 32)
+    k, d = ex(np.full((480, 752), 128, np.uint8))  # flat image: zero keypoints (descriptors released, :1080)
+    assert len(k) == 0
+    with pytest.raises(orbb200.OrbError):
+        ex(np.zeros((40, 40), np.uint8))           # top level below 62 px: the reference divides by zero here
+    with pytest.raises(orbb200.OrbError):
+        orbb200.Extractor(0)
+    ex.close()
+
+
+def test_device_resident_batch(oracle):
+    torch = pytest.importorskip("torch")
+    frames = np.stack([synth_frame(300 + i, 752, 480) for i in range(3)])
+    ex = orbb200.Extractor(1000, max_width=752, max_height=480, max_batch=3)
+    d_img = torch.from_numpy(frames).cuda()
+    cap = ex.capacity
+    d_kps = torch.zeros((3, cap, 7), dtype=torch.int32, device="cuda")
+    d_desc = torch.zeros((3, cap, 32), dtype=torch.uint8, device="cuda")
+    d_n = torch.zeros(3, dtype=torch.int32, device="cuda")
+    ex.extract_batch_device(d_img, d_kps, d_desc, d_n)
+    ex.synchronize()
+    n = d_n.cpu().numpy()
+    kraw = d_kps.cpu().numpy()
+    oe = oracle.extractor(1000)
+    for i in range(3):
+        rk, rd = oe.extract(frames[i])
+        k = kraw[i, :n[i]].copy().view(orbb200.KP_DTYPE).reshape(-1)
+        _assert_same_keypoints(k, rk)
+        assert np.array_equal(d_desc[i, :n[i]].cpu().numpy(), rd)
+    ex.close()

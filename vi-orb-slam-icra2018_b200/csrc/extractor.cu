@@ -1,0 +1,494 @@
+// Extractor handle: constructor tables, per-image-size geometry, device arena, launch sequencing, C-ABI entry points.
+//   ORBextractor::ORBextractor   ORBextractor.cc:412-472     (scale tables, features per level, umax)
+//   ORBextractor::operator()     ORBextractor.cc:1045-1126   (pyramid -> keypoints -> blur + descriptors)
+// Everything per pixel / per keypoint runs in the kernels of pyramid.cu, fast.cu, octree.cu, blur.cu, brief.cu; the
+// host code here only derives sizes and tables (the same float expressions as the reference, compiled without FMA
+// contraction) and enqueues 12 launches per batch on one stream.
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "extractor.h"
+
+using namespace orbb;
+
+namespace {
+
+inline int cv_round_f(float v) { return (int)lrintf(v); }
+inline int round_up(int v, int a) { return (v + a - 1) / a * a; }
+inline long long round_up_ll(long long v, long long a) { return (v + a - 1) / a * a; }
+
+// cv::resize INTER_LINEAR per-axis table (imgproc/resize.cpp): source index and 11-bit coefficient pair
+void resize_axis_table(int ssize, int dsize, int* ofs, short2* coef) {
+    const double scale = 1.0 / ((double)dsize / (double)ssize);
+    for (int d = 0; d < dsize; ++d) {
+        float f = (float)((d + 0.5) * scale - 0.5);
+        int s = (int)floorf(f);
+        f -= (float)s;
+        if (s < 0) { s = 0; f = 0.f; }
+        if (s >= ssize - 1) { s = ssize - 1; f = 0.f; }
+        ofs[d] = s;
+        coef[d].x = (short)cv_round_f((1.f - f) * 2048.f);
+        coef[d].y = (short)cv_round_f(f * 2048.f);
+    }
+}
+
+}  // namespace
+
+struct orbx_extractor {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    // ctor state
+    int nfeatures = 0, nlevels = 0, iniTh = 0, minTh = 0;
+    double scaleFactor = 1;
+    std::vector<float> scale, invScale, sigma2, invSigma2;
+    std::vector<int> perLevel;
+    int umax[16];
+    int maxW = 0, maxH = 0, maxBatch = 1;
+    // geometry of the current image size
+    int curW = -1, curH = -1;
+    ExtractParams P;
+    std::vector<Cell> cells;
+    std::vector<BlurTile> tiles;
+    int kpCapacity = 0;       // upper bound on keypoints per frame
+    int otSmem = 0, otKeyCap = 0, otNodeCap = 0, otCellCap = 0;
+    // device memory
+    DevBuf pyr, blur, slots, cellCount, sel, selCount, keyWs, dCells, dTiles, dTabOfs, dTabCoef;
+    DevBuf dImages, dKps, dDesc, dCount;
+    int lastFrames = 0, lastCapacity = 0;
+    int launches = 0;
+    double stageMs[3] = {0, 0, 0};
+    bool timed = false;
+};
+
+namespace {
+
+int configure(orbx_extractor* e, int w, int h, int nFrames) {
+    if (e->curW == w && e->curH == h && nFrames <= e->lastFrames) return ORB_OK;
+    const int nl = e->nlevels;
+    ExtractParams& P = e->P;
+    std::vector<LevelGeom> lv(nl);
+    long long pyrOff = 0, blurOff = 0, slotOff = 0, keyOff = 0;
+    int tabOff = 0, selOff = 0, cellBase = 0;
+    std::vector<Cell> cells;
+    std::vector<BlurTile> tiles;
+    int tw, th;
+    blur_tile_dims(&tw, &th);
+    int nodeCap = 8, cellCap = 1;
+    for (int l = 0; l < nl; ++l) {
+        LevelGeom& L = lv[l];
+        L.w = cv_round_f((float)w * e->invScale[l]);   // :1133
+        L.h = cv_round_f((float)h * e->invScale[l]);
+        if (L.w < 62 || L.h < 62)
+            return fail(ORB_ERR_INVALID, "level %d is %dx%d: the reference's cell grid needs at least 62x62 (ORBextractor.cc:783-789)",
+                        l, L.w, L.h);
+        if (L.w > 4096 + 32 || L.h > 4096 + 32) return fail(ORB_ERR_INVALID, "level %d is %dx%d: larger than 4128", l, L.w, L.h);
+        L.pitch = round_up(kPadLeft + L.w + kEdge, 16);
+        L.bpitch = round_up(L.w, 16);
+        L.pyrOff = pyrOff;
+        pyrOff = round_up_ll(pyrOff + (long long)L.pitch * (L.h + 2 * kEdge), 256);
+        L.blurOff = blurOff;
+        blurOff = round_up_ll(blurOff + (long long)L.bpitch * L.h, 256);
+        L.xTab = tabOff;
+        tabOff += L.w;
+        L.yTab = tabOff;
+        tabOff += L.h;
+        // cell grid (:775-789)
+        const int minB = kEdge - 3;
+        const int maxBX = L.w - kEdge + 3, maxBY = L.h - kEdge + 3;
+        const float width = (float)(maxBX - minB), height = (float)(maxBY - minB);
+        const int nCols = (int)(width / 30.f), nRows = (int)(height / 30.f);
+        const int wCell = (int)ceilf(width / nCols), hCell = (int)ceilf(height / nRows);
+        if (wCell > kCellMax || hCell > kCellMax) return fail(ORB_ERR_INVALID, "level %d: cell %dx%d too large", l, wCell, hCell);
+        L.slotCap = ((wCell + 1) / 2) * ((hCell + 1) / 2);
+        L.slotBase = slotOff;
+        L.cellBase = cellBase;
+        for (int i = 0; i < nRows; ++i)
+            for (int j = 0; j < nCols; ++j) {
+                Cell c;
+                c.level = (short)l;
+                c.x0 = (short)(kEdge + j * wCell);
+                c.y0 = (short)(kEdge + i * hCell);
+                c.cw = (short)std::min(wCell, (L.w - kEdge) - c.x0);
+                c.ch = (short)std::min(hCell, (L.h - kEdge) - c.y0);
+                c.pad = 0;
+                if (c.cw <= 0 || c.ch <= 0) continue;   // the reference skips it or FAST sees a ROI thinner than 7 px
+                c.slot = (int)slotOff;
+                slotOff += L.slotCap;
+                cells.push_back(c);
+            }
+        L.nCells = (int)cells.size() - cellBase;
+        cellBase = (int)cells.size();
+        cellCap = std::max(cellCap, L.nCells);
+        // quadtree (:545-560)
+        L.nFeatures = e->perLevel[l];
+        L.winW = maxBX - minB;
+        L.winH = maxBY - minB;
+        L.nIni = (int)roundf(width / height);
+        if (L.nIni < 1) return fail(ORB_ERR_INVALID, "level %d: aspect ratio %dx%d gives no quadtree root (ORBextractor.cc:545)", l, L.w, L.h);
+        L.hX = width / L.nIni;
+        L.selCap = std::max(L.nFeatures + 3, 4 * L.nIni) + 1;
+        L.selBase = selOff;
+        selOff += L.selCap;
+        nodeCap = std::max(nodeCap, L.selCap);
+        L.keyWsCap = L.nCells * L.slotCap + 2;
+        L.keyWsOff = keyOff;
+        keyOff += L.keyWsCap + (L.keyWsCap + 1) / 2 + 2;
+        L.scale = e->scale[l];
+        L.patchSize = (float)(int)((float)kPatch * e->scale[l]);   // :837, 848
+        for (int ty = 0; ty < ceil_div(L.h, th); ++ty)
+            for (int tx = 0; tx < ceil_div(L.w, tw); ++tx) tiles.push_back(BlurTile{(short)l, (short)tx, (short)ty, 0});
+    }
+    if (nodeCap > 65535) return fail(ORB_ERR_INVALID, "nfeatures too large for the quadtree kernel");
+    ORB_CHECK(octree_smem_plan(nodeCap, cellCap, &e->otSmem, &e->otKeyCap));
+    e->otNodeCap = nodeCap;
+    e->otCellCap = cellCap;
+
+    // resize tables
+    std::vector<int> tabOfs(tabOff);
+    std::vector<short2> tabCoef(tabOff);
+    for (int l = 1; l < nl; ++l) {
+        resize_axis_table(lv[l - 1].w, lv[l].w, &tabOfs[lv[l].xTab], &tabCoef[lv[l].xTab]);
+        resize_axis_table(lv[l - 1].h, lv[l].h, &tabOfs[lv[l].yTab], &tabCoef[lv[l].yTab]);
+    }
+
+    // arena
+    const long long F = std::max(nFrames, e->maxBatch);
+    ORB_CHECK(e->pyr.reserve((size_t)(pyrOff * F) + 256));
+    ORB_CHECK(e->blur.reserve((size_t)(blurOff * F) + 256));
+    ORB_CHECK(e->slots.reserve((size_t)(slotOff * F) * 4 + 256));
+    ORB_CHECK(e->cellCount.reserve((size_t)cells.size() * F * 4 + 256));
+    ORB_CHECK(e->sel.reserve((size_t)selOff * F * sizeof(SelKey) + 256));
+    ORB_CHECK(e->selCount.reserve((size_t)nl * F * 4 + 256));
+    ORB_CHECK(e->keyWs.reserve((size_t)(keyOff * F) * 4 + 256));
+    ORB_CHECK(e->dCells.reserve(cells.size() * sizeof(Cell) + 16));
+    ORB_CHECK(e->dTiles.reserve(tiles.size() * sizeof(BlurTile) + 16));
+    ORB_CHECK(e->dTabOfs.reserve(tabOfs.size() * 4 + 16));
+    ORB_CHECK(e->dTabCoef.reserve(tabCoef.size() * 4 + 16));
+    ORB_CUDA(cudaMemcpyAsync(e->dCells.p, cells.data(), cells.size() * sizeof(Cell), cudaMemcpyHostToDevice, e->stream));
+    ORB_CUDA(cudaMemcpyAsync(e->dTiles.p, tiles.data(), tiles.size() * sizeof(BlurTile), cudaMemcpyHostToDevice, e->stream));
+    ORB_CUDA(cudaMemcpyAsync(e->dTabOfs.p, tabOfs.data(), tabOfs.size() * 4, cudaMemcpyHostToDevice, e->stream));
+    ORB_CUDA(cudaMemcpyAsync(e->dTabCoef.p, tabCoef.data(), tabCoef.size() * 4, cudaMemcpyHostToDevice, e->stream));
+    ORB_CUDA(cudaStreamSynchronize(e->stream));   // the host vectors go out of scope
+
+    std::memset(&P, 0, sizeof P);
+    P.nLevels = nl;
+    P.iniTh = e->iniTh;
+    P.minTh = e->minTh;
+    P.nCellsTotal = (int)cells.size();
+    P.selPerFrame = selOff;
+    P.pyrFrameBytes = pyrOff;
+    P.blurFrameBytes = blurOff;
+    P.slotFrameEntries = slotOff;
+    P.keyWsFrameEntries = keyOff;
+    P.pyr = e->pyr.as<unsigned char>();
+    P.blur = e->blur.as<unsigned char>();
+    P.slots = e->slots.as<unsigned int>();
+    P.cellCount = e->cellCount.as<int>();
+    P.sel = e->sel.as<SelKey>();
+    P.selCount = e->selCount.as<int>();
+    P.keyWs = e->keyWs.as<unsigned int>();
+    P.cells = e->dCells.as<Cell>();
+    P.tabOfs = e->dTabOfs.as<int>();
+    P.tabCoef = e->dTabCoef.as<short2>();
+    std::memcpy(P.umax, e->umax, sizeof P.umax);
+    for (int l = 0; l < nl; ++l) P.lv[l] = lv[l];
+    e->cells.swap(cells);
+    e->tiles.swap(tiles);
+    e->kpCapacity = selOff;
+    e->curW = w;
+    e->curH = h;
+    e->lastFrames = (int)F;
+    return ORB_OK;
+}
+
+// enqueue one batch (device pointers), no synchronisation
+int enqueue(orbx_extractor* e, const uint8_t* dImages, int nFrames, int w, int h, int stride, size_t frameStride,
+            orb_keypoint* dKps, uint8_t* dDesc, int capacity, int* dCount, cudaStream_t st, bool timed) {
+    ORB_CHECK(configure(e, w, h, nFrames));
+    ExtractParams P = e->P;
+    P.nFrames = nFrames;
+    P.outCapacity = capacity;
+    e->lastCapacity = capacity;
+    e->timed = timed;
+    if (timed) ORB_CUDA(cudaEventRecord(e->ev[0], st));
+    ORB_CHECK(launch_pyramid(P, dImages, w, h, stride, frameStride, st, &e->launches));
+    if (timed) ORB_CUDA(cudaEventRecord(e->ev[1], st));
+    ORB_CHECK(launch_fast(P, st, &e->launches));
+    ORB_CHECK(launch_octree(P, e->otSmem, e->otKeyCap, e->otNodeCap, e->otCellCap, st, &e->launches));
+    if (timed) ORB_CUDA(cudaEventRecord(e->ev[2], st));
+    ORB_CHECK(launch_blur(P, e->dTiles.as<BlurTile>(), (int)e->tiles.size(), st, &e->launches));
+    ORB_CHECK(launch_brief(P, std::min(capacity, e->kpCapacity), dKps, dDesc, dCount, st, &e->launches));
+    if (timed) ORB_CUDA(cudaEventRecord(e->ev[3], st));
+    return ORB_OK;
+}
+
+}  // namespace
+
+#define ORBX_ENTER(h)                                                                                  \
+    if (!(h)) return fail(ORB_ERR_INVALID, "%s: null extractor handle", __func__);                     \
+    DeviceGuard guard__((h)->device);                                                                  \
+    if (!guard__.ok) return fail(ORB_ERR_CUDA, "%s: cannot select device %d", __func__, (h)->device);
+
+extern "C" {
+
+int orbx_create(int nfeatures, float scaleFactor, int nlevels, int iniTh, int minTh, int maxW, int maxH, int maxBatch,
+                int device, orbx_handle* out) {
+    if (!out) return fail(ORB_ERR_INVALID, "orbx_create: null out");
+    *out = nullptr;
+    if (nfeatures < 1 || nlevels < 1 || nlevels > kMaxLevels || !(scaleFactor > 1.0f) || iniTh < 1 || minTh < 1 ||
+        iniTh > 255 || minTh > iniTh || maxBatch < 1)
+        return fail(ORB_ERR_INVALID, "orbx_create: need nfeatures>=1, 1<=nlevels<=%d, scaleFactor>1, 1<=minThFAST<=iniThFAST<=255, max_batch>=1",
+                    kMaxLevels);
+    int n = 0;
+    ORB_CUDA(cudaGetDeviceCount(&n));
+    if (device < 0 || device >= n) return fail(ORB_ERR_INVALID, "orbx_create: device %d of %d", device, n);
+    DeviceGuard g(device);
+    if (!g.ok) return fail(ORB_ERR_CUDA, "orbx_create: cannot select device %d", device);
+
+    orbx_extractor* e = new orbx_extractor;
+    e->device = device;
+    e->nfeatures = nfeatures; e->nlevels = nlevels; e->iniTh = iniTh; e->minTh = minTh;
+    e->scaleFactor = (double)scaleFactor;
+    e->maxW = maxW; e->maxH = maxH; e->maxBatch = maxBatch;
+    // scale tables (:417-434): float * double member, stored as float
+    e->scale.assign(nlevels, 1.f);
+    e->sigma2.assign(nlevels, 1.f);
+    for (int i = 1; i < nlevels; ++i) {
+        e->scale[i] = (float)((double)e->scale[i - 1] * e->scaleFactor);
+        e->sigma2[i] = e->scale[i] * e->scale[i];
+    }
+    e->invScale.resize(nlevels);
+    e->invSigma2.resize(nlevels);
+    for (int i = 0; i < nlevels; ++i) {
+        e->invScale[i] = 1.0f / e->scale[i];
+        e->invSigma2[i] = 1.0f / e->sigma2[i];
+    }
+    // features per level (:436-448)
+    e->perLevel.assign(nlevels, 0);
+    const float factor = (float)(1.0 / e->scaleFactor);
+    float desired = (float)nfeatures * (1.f - factor) / (1.f - (float)pow((double)factor, (double)nlevels));
+    int sum = 0;
+    for (int l = 0; l < nlevels - 1; ++l) {
+        e->perLevel[l] = cv_round_f(desired);
+        sum += e->perLevel[l];
+        desired *= factor;
+    }
+    e->perLevel[nlevels - 1] = std::max(nfeatures - sum, 0);
+    // circular patch extents (:456-471)
+    {
+        int* um = e->umax;
+        std::memset(um, 0, sizeof e->umax);
+        const int vmax = (int)floorf(kHalfPatch * sqrtf(2.f) / 2 + 1);
+        const int vmin = (int)ceilf(kHalfPatch * sqrtf(2.f) / 2);
+        const double hp2 = kHalfPatch * kHalfPatch;
+        for (int v = 0; v <= vmax; ++v) um[v] = (int)lrint(sqrt(hp2 - v * v));
+        for (int v = kHalfPatch, v0 = 0; v >= vmin; --v) {
+            while (um[v0] == um[v0 + 1]) ++v0;
+            um[v] = v0;
+            ++v0;
+        }
+    }
+    cudaError_t ce = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 4 && ce == cudaSuccess; ++i) ce = cudaEventCreate(&e->ev[i]);
+    if (ce != cudaSuccess) {
+        delete e;
+        return fail(ORB_ERR_CUDA, "orbx_create: %s", cudaGetErrorString(ce));
+    }
+    int st = upload_brief_pattern();
+    if (st == ORB_OK && maxW > 0 && maxH > 0) st = configure(e, maxW, maxH, maxBatch);
+    if (st != ORB_OK) {
+        orbx_destroy(e);
+        return st;
+    }
+    *out = e;
+    return ORB_OK;
+}
+
+int orbx_destroy(orbx_handle e) {
+    if (!e) return ORB_OK;
+    DeviceGuard g(e->device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    DevBuf* bufs[] = {&e->pyr, &e->blur, &e->slots, &e->cellCount, &e->sel, &e->selCount, &e->keyWs, &e->dCells,
+                      &e->dTiles, &e->dTabOfs, &e->dTabCoef, &e->dImages, &e->dKps, &e->dDesc, &e->dCount};
+    for (DevBuf* b : bufs) b->release();
+    for (int i = 0; i < 4; ++i)
+        if (e->ev[i]) cudaEventDestroy(e->ev[i]);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+    return ORB_OK;
+}
+
+int orbx_keypoint_capacity(orbx_handle e, int* cap) {
+    if (!e || !cap) return fail(ORB_ERR_INVALID, "orbx_keypoint_capacity: null argument");
+    // bound for any image size: sum over levels of max(N_l + 3, 4*nIni) + 1, nIni <= round(4096/62) levels aside
+    if (e->curW > 0) { *cap = e->kpCapacity; return ORB_OK; }
+    int c = 0;
+    for (int l = 0; l < e->nlevels; ++l) c += std::max(e->perLevel[l] + 3, 4 * 8) + 1;
+    *cap = c;
+    return ORB_OK;
+}
+
+int orbx_extract_batch_device(orbx_handle e, const uint8_t* dImages, int nFrames, int w, int h, int stride,
+                              size_t frameStride, orb_keypoint* dKps, uint8_t* dDesc, int capacity, int* dCount,
+                              void* stream) {
+    ORBX_ENTER(e);
+    if (nFrames < 0) return fail(ORB_ERR_INVALID, "orbx_extract_batch_device: negative frame count");
+    if (nFrames == 0) return ORB_OK;
+    if (nFrames > 65535) return fail(ORB_ERR_INVALID, "orbx_extract_batch_device: at most 65535 frames per call");
+    if (!dImages || !dKps || !dDesc || !dCount || w <= 0 || h <= 0 || stride < w || capacity < 1)
+        return fail(ORB_ERR_INVALID, "orbx_extract_batch_device: bad arguments");
+    e->launches = 0;
+    cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
+    return enqueue(e, dImages, nFrames, w, h, stride, frameStride, dKps, dDesc, capacity, dCount, st, stream == nullptr);
+}
+
+int orbx_extract_batch(orbx_handle e, const uint8_t* images, int nFrames, int w, int h, int stride, size_t frameStride,
+                       orb_keypoint* kps, uint8_t* desc, int capacity, int* nOut) {
+    ORBX_ENTER(e);
+    if (nFrames < 0) return fail(ORB_ERR_INVALID, "orbx_extract_batch: negative frame count");
+    if (nFrames == 0) return ORB_OK;
+    if (!nOut) return fail(ORB_ERR_INVALID, "orbx_extract_batch: null n_out");
+    if (!images || w <= 0 || h <= 0) {   // empty image: outputs untouched (:1048-1049)
+        for (int f = 0; f < nFrames; ++f) nOut[f] = 0;
+        return ORB_OK;
+    }
+    if (!kps || !desc || stride < w || capacity < 1) return fail(ORB_ERR_INVALID, "orbx_extract_batch: bad arguments");
+    e->launches = 0;
+    const int chunk = std::min(e->maxBatch, 65535);
+    const size_t imgBytes = (size_t)stride * h;
+    ORB_CHECK(configure(e, w, h, std::min(nFrames, chunk)));
+    ORB_CHECK(e->dImages.reserve((size_t)chunk * imgBytes));
+    ORB_CHECK(e->dKps.reserve((size_t)chunk * capacity * sizeof(orb_keypoint)));
+    ORB_CHECK(e->dDesc.reserve((size_t)chunk * capacity * 32));
+    ORB_CHECK(e->dCount.reserve((size_t)chunk * 4));
+    cudaStream_t st = e->stream;
+    int status = ORB_OK;
+    for (int f0 = 0; f0 < nFrames; f0 += chunk) {
+        const int nf = std::min(chunk, nFrames - f0);
+        if (frameStride == imgBytes) {
+            ORB_CUDA(cudaMemcpyAsync(e->dImages.p, images + (size_t)f0 * frameStride, (size_t)nf * imgBytes, cudaMemcpyHostToDevice, st));
+        } else {
+            for (int f = 0; f < nf; ++f)
+                ORB_CUDA(cudaMemcpyAsync(e->dImages.as<uint8_t>() + (size_t)f * imgBytes, images + (size_t)(f0 + f) * frameStride,
+                                         imgBytes, cudaMemcpyHostToDevice, st));
+        }
+        ORB_CHECK(enqueue(e, e->dImages.as<uint8_t>(), nf, w, h, stride, imgBytes, e->dKps.as<orb_keypoint>(),
+                          e->dDesc.as<uint8_t>(), capacity, e->dCount.as<int>(), st, f0 == 0));
+        ORB_CUDA(cudaMemcpyAsync(nOut + f0, e->dCount.p, (size_t)nf * 4, cudaMemcpyDeviceToHost, st));
+        ORB_CUDA(cudaMemcpyAsync(kps + (size_t)f0 * capacity, e->dKps.p, (size_t)nf * capacity * sizeof(orb_keypoint),
+                                 cudaMemcpyDeviceToHost, st));
+        ORB_CUDA(cudaMemcpyAsync(desc + (size_t)f0 * capacity * 32, e->dDesc.p, (size_t)nf * capacity * 32, cudaMemcpyDeviceToHost, st));
+        ORB_CUDA(cudaStreamSynchronize(st));
+        if (f0 == 0) {
+            float ms;
+            for (int i = 0; i < 3; ++i)
+                if (cudaEventElapsedTime(&ms, e->ev[i], e->ev[i + 1]) == cudaSuccess) e->stageMs[i] = ms;
+        }
+        for (int f = 0; f < nf; ++f)
+            if (nOut[f0 + f] > capacity) {
+                status = fail(ORB_ERR_CAPACITY, "frame %d has %d keypoints, capacity %d (see orbx_keypoint_capacity)", f0 + f,
+                              nOut[f0 + f], capacity);
+                nOut[f0 + f] = capacity;
+            }
+    }
+    return status;
+}
+
+int orbx_extract(orbx_handle e, const uint8_t* image, int w, int h, int stride, orb_keypoint* kps, uint8_t* desc,
+                 int capacity, int* nOut) {
+    return orbx_extract_batch(e, image, 1, w, h, stride, (size_t)stride * (h > 0 ? h : 0), kps, desc, capacity, nOut);
+}
+
+int orbx_synchronize(orbx_handle e) {
+    ORBX_ENTER(e);
+    ORB_CUDA(cudaStreamSynchronize(e->stream));
+    return ORB_OK;
+}
+
+int orbx_get_levels(orbx_handle e, int* nlevels) {
+    if (!e || !nlevels) return fail(ORB_ERR_INVALID, "orbx_get_levels: null argument");
+    *nlevels = e->nlevels;
+    return ORB_OK;
+}
+
+int orbx_get_scale_tables(orbx_handle e, float* sf, float* inv, float* s2, float* is2, int* perLevel, int* umax) {
+    if (!e) return fail(ORB_ERR_INVALID, "orbx_get_scale_tables: null handle");
+    for (int i = 0; i < e->nlevels; ++i) {
+        if (sf) sf[i] = e->scale[i];
+        if (inv) inv[i] = e->invScale[i];
+        if (s2) s2[i] = e->sigma2[i];
+        if (is2) is2[i] = e->invSigma2[i];
+        if (perLevel) perLevel[i] = e->perLevel[i];
+    }
+    if (umax) std::memcpy(umax, e->umax, sizeof e->umax);
+    return ORB_OK;
+}
+
+int orbx_get_level(orbx_handle e, int frame, int level, uint8_t* out, int* w, int* hgt) {
+    ORBX_ENTER(e);
+    if (e->curW < 0) return fail(ORB_ERR_INVALID, "orbx_get_level: no image processed yet");
+    if (level < 0 || level >= e->nlevels || frame < 0 || frame >= e->lastFrames) return fail(ORB_ERR_INVALID, "orbx_get_level: bad frame/level");
+    const LevelGeom& L = e->P.lv[level];
+    if (w) *w = L.w;
+    if (hgt) *hgt = L.h;
+    if (!out) return ORB_OK;
+    ORB_CUDA(cudaStreamSynchronize(e->stream));
+    const unsigned char* src = e->P.pyr + (size_t)frame * e->P.pyrFrameBytes + L.pyrOff + (kPadLeft - kEdge);
+    ORB_CUDA(cudaMemcpy2D(out, L.w + 2 * kEdge, src, L.pitch, L.w + 2 * kEdge, L.h + 2 * kEdge, cudaMemcpyDeviceToHost));
+    return ORB_OK;
+}
+
+int orbx_stage_times(orbx_handle e, double* ms3) {
+    if (!e || !ms3) return fail(ORB_ERR_INVALID, "orbx_stage_times: null argument");
+    for (int i = 0; i < 3; ++i) ms3[i] = e->stageMs[i];
+    return ORB_OK;
+}
+
+int orbx_debug_candidates(orbx_handle e, int frame, int level, orb_keypoint* out, int cap, int* n) {
+    ORBX_ENTER(e);
+    if (e->curW < 0 || level < 0 || level >= e->nlevels || frame < 0 || frame >= e->lastFrames || !n)
+        return fail(ORB_ERR_INVALID, "orbx_debug_candidates: bad arguments");
+    const LevelGeom& L = e->P.lv[level];
+    ORB_CUDA(cudaStreamSynchronize(e->stream));
+    std::vector<int> counts(L.nCells);
+    std::vector<unsigned int> slots((size_t)L.nCells * L.slotCap);
+    if (L.nCells) {
+        ORB_CUDA(cudaMemcpy(counts.data(), e->P.cellCount + (size_t)frame * e->P.nCellsTotal + L.cellBase, (size_t)L.nCells * 4,
+                            cudaMemcpyDeviceToHost));
+        ORB_CUDA(cudaMemcpy(slots.data(), e->P.slots + (size_t)frame * e->P.slotFrameEntries + L.slotBase, slots.size() * 4,
+                            cudaMemcpyDeviceToHost));
+    }
+    int k = 0;
+    for (int c = 0; c < L.nCells; ++c)
+        for (int i = 0; i < counts[c]; ++i, ++k) {
+            if (k >= cap) continue;
+            const unsigned int v = slots[(size_t)c * L.slotCap + i];
+            orb_keypoint o;
+            o.x = (float)(v >> 20); o.y = (float)((v >> 8) & 0xfff); o.size = 7.f; o.angle = -1.f;
+            o.response = (float)(v & 0xff); o.octave = 0; o.class_id = -1;
+            out[k] = o;
+        }
+    *n = k;
+    return ORB_OK;
+}
+
+int orbx_debug_blurred(orbx_handle e, int frame, int level, uint8_t* out) {
+    ORBX_ENTER(e);
+    if (e->curW < 0 || level < 0 || level >= e->nlevels || frame < 0 || frame >= e->lastFrames || !out)
+        return fail(ORB_ERR_INVALID, "orbx_debug_blurred: bad arguments");
+    const LevelGeom& L = e->P.lv[level];
+    ORB_CUDA(cudaStreamSynchronize(e->stream));
+    ORB_CUDA(cudaMemcpy2D(out, L.w, e->P.blur + (size_t)frame * e->P.blurFrameBytes + L.blurOff, L.bpitch, L.w, L.h,
+                          cudaMemcpyDeviceToHost));
+    return ORB_OK;
+}
+
+int orbx_last_launch_count(orbx_handle e, int* n) {
+    if (!e || !n) return fail(ORB_ERR_INVALID, "orbx_last_launch_count: null argument");
+    *n = e->launches;
+    return ORB_OK;
+}
+
+}  // extern "C"

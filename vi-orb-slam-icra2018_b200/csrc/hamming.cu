@@ -324,11 +324,8 @@ int launch_allpairs(const uint8_t* dTable, const float* dAngles, int nKf, int nD
         return fail(ORB_ERR_INVALID, "allpairs: bad ranges");
     const int nQ = qEnd - qBegin, nDb = dbEnd - dbBegin;
     if (nQ == 0 || nDb == 0) return ORB_OK;
-    static bool attrSet = false;
-    if (!attrSet) {
-        ORB_CUDA(cudaFuncSetAttribute(allpairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ApShared)));
-        attrSet = true;
-    }
+    // per device and cheap; set every time so that matchers on different GPUs of one process all get it
+    ORB_CUDA(cudaFuncSetAttribute(allpairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ApShared)));
     // enough blocks to fill the GPU several times over, long enough runs that the query registers are amortised
     int dbPerBlock = 64;
     while (dbPerBlock > 8 && (long long)nQ * ceil_div(nDb, dbPerBlock) < 148 * 6) dbPerBlock >>= 1;
