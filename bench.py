@@ -1,0 +1,340 @@
+#!/usr/bin/env python3
+"""Benchmark of the ORB front-end hot path on B200 (BASELINE.json metric: "ORB extract frames/s @752x480 1k kp;
+Hamming compares/s; % roofline").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--frames B] [--impl ours|reference]
+
+One step = one pass of ORBextractor::operator() over a batch of B synthetic EuRoC-shaped frames per GPU
+(BASELINE.json configs[2] shape; ORBextractor(1000, 1.2, 8, 20, 7)).  Prints ONE JSON line (rank 0):
+  value        whole-job frames/s with the batch resident in HBM (CUDA events on the launching stream, max over ranks)
+  e2e          the same through the C-ABI host entry point orbx_extract_batch: pinned host input, H2D, kernels, D2H of
+               keypoints/descriptors/counts inside the timed region
+  roofline     dominant kernel of the extraction: algorithmic bytes per launch / its CUDA-event time, vs measured HBM peak
+  hamming      config-4 brute-force matcher (1024 pairs of 2000x2000): compares/s and fraction of the measured POPC peak
+  cpu_baseline the reference's CPU extractor (oracle/_ref, else the oracle port) on a bounded sample, single thread
+`--impl reference` times the CPU reference on all host cores instead (rank 0 only).
+Multi-GPU: frames are independent, so ranks shard the batch with no data-path collective (weak scaling).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "vi-orb-slam-icra2018_b200"))
+
+W, H, NFEAT, NLEVELS, SCALE, INI_TH, MIN_TH = 752, 480, 1000, 8, 1.2, 20, 7
+METRIC = "ORB extract frames/s @752x480 1k kp"
+
+
+def level_sizes(w, h):
+    import numpy as np
+    s = np.float32(1.0)
+    out = []
+    for l in range(NLEVELS):
+        inv = np.float32(1.0) / s
+        out.append((int(np.rint(np.float32(w) * inv)), int(np.rint(np.float32(h) * inv))))
+        s = np.float32(np.float64(s) * np.float64(np.float32(SCALE)))
+    return out
+
+
+def algorithmic_bytes(w, h, nkp):
+    """SURVEY.md section 8d staged model, bytes per frame and per kernel group."""
+    lv = level_sizes(w, h)
+    px = sum(a * b for a, b in lv)
+    padded = sum((a + 38) * (b + 38) for a, b in lv)
+    pyr = w * h + sum(a * b for a, b in lv[:-1]) + padded
+    return {"pyramid": pyr, "fast": px, "quadtree": 0, "blur": 2 * px, "brief": nkp * 60,
+            "total": pyr + px + 2 * px + nkp * 60}
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.p = index, [], None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.p:
+            self.p.terminate()
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = max([int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()] or [0])
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].startswith("Active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def cpu_reference(frames, procs, seconds_budget, native=True):
+    """frames/s of the reference CPU extractor on `procs` cores, bounded sample."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    try:
+        import ref_runner
+        kind = "orb_ref_o3" if native and ref_runner.ref_binary("orb_ref_o3") else "orb_ref"
+        if ref_runner.ref_binary(kind):
+            probe = ref_runner.ref_bench(frames[:2], 1, nfeatures=NFEAT, kind=kind, procs=1)
+            iters = max(1, int(seconds_budget / max(probe["ms_per_frame"] * 1e-3 * len(frames), 1e-3)))
+            r = ref_runner.ref_bench(frames, iters, nfeatures=NFEAT, kind=kind, procs=procs)
+            return {"value": r["frames_per_s"], "unit": "frames/s", "cores": procs, "kind": "reference",
+                    "sample": "%d synthetic 752x480 frames x %d passes per core through oracle/_ref/%s (the reference's own "
+                              "ORBextractor.cc on the cv2-pinned primitive models)" % (len(frames), iters, kind),
+                    "ms_per_frame_one_core": r["ms_per_frame"],
+                    "stage_ms": [r["ms_pyramid"], r["ms_keypoints"], r["ms_descriptors"]]}
+    except Exception as ex:  # the binary may not run on this host; fall back to the port
+        sys.stderr.write("oracle/_ref unavailable (%s), timing the oracle port\n" % ex)
+    from oracle_py import Oracle
+    ex = Oracle().extractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH)
+    t0 = time.perf_counter()
+    n = 0
+    while time.perf_counter() - t0 < seconds_budget:
+        ex.extract(frames[n % len(frames)])
+        n += 1
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": "frames/s", "cores": 1, "kind": "port",
+            "sample": "%d extractions of synthetic 752x480 frames through oracle/liborb_oracle.so" % n}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import numpy as np
+    from orbb200.synth import synth_frame
+    frames = [synth_frame(s, W, H) for s in range(4)]
+    procs = os.cpu_count() or 1
+    t0 = time.perf_counter()
+    vals = []
+    for _ in range(args.warmup + args.steps):
+        vals.append(cpu_reference(frames, procs, seconds_budget=max(2.0, 40.0 / (args.warmup + args.steps))))
+    base = vals[-1]
+    timed = vals[args.warmup:]
+    value = sum(v["value"] for v in timed) / len(timed)
+    base["value"] = value
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * (time.perf_counter() - t0) / len(vals),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "configs[2] shape: synthetic EuRoC 752x480 frames, ORBextractor(1000,1.2,8,20,7), "
+                                   "CPU reference on all host cores, bounded sample per step"},
+            "cpu_baseline": base,
+            "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--frames", type=int, default=1024, help="frames per GPU per step")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--no-hamming", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import orbb200
+    from orbb200.synth import synth_frames_torch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    B, K, Wm = args.frames, args.steps, max(args.warmup, 3)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if not dist:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- inputs: B distinct frames per rank, resident in HBM (B*361 KB > 126 MB L2 for B >= 350) and pinned on the host
+    chunks = [synth_frames_torch(min(128, B - i), W, H, seed=1000 * rank + i, device=dev) for i in range(0, B, 128)]
+    d_images = torch.cat(chunks)
+    del chunks
+    h_images = torch.empty((B, H, W), dtype=torch.uint8, pin_memory=True)
+    h_images.copy_(d_images)
+    ex = orbb200.Extractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, max_width=W, max_height=H, max_batch=B, device=local)
+    cap = ex.capacity
+    d_kps = torch.empty((B, cap, 7), dtype=torch.int32, device=dev)
+    d_desc = torch.empty((B, cap, 32), dtype=torch.uint8, device=dev)
+    d_n = torch.empty(B, dtype=torch.int32, device=dev)
+    stream = torch.cuda.Stream(device=dev)
+
+    def step():
+        ex.extract_batch_device(d_images, d_kps, d_desc, d_n, stream=stream.cuda_stream)
+
+    for _ in range(Wm):
+        step()
+    stream.synchronize()
+    launches_per_step = ex.launch_count()
+    nkp = float(d_n.float().mean().item())
+
+    # ---- timed region: K steps, kernels bracketed by events on the launching stream
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    ex.set_profiling(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(K):
+        step()
+    e1.record(stream)
+    stream.synchronize()
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    kernel_ms, ncalls = ex.kernel_times()
+    ex.set_profiling(False)
+    clocks = sampler.stop()
+    value = world * B * K / (ms_total * 1e-3)
+
+    # ---- e2e: host buffers through the C ABI (pinned input, H2D + kernels + D2H per step)
+    h_kps = torch.empty((B, cap, 7), dtype=torch.int32, pin_memory=True)
+    h_desc = torch.empty((B, cap, 32), dtype=torch.uint8, pin_memory=True)
+    h_n = torch.empty(B, dtype=torch.int32, pin_memory=True)
+    import ctypes as C
+
+    def e2e_step():
+        orbb200._check(ex.L.orbx_extract_batch(ex.h, C.c_void_p(h_images.data_ptr()), B, W, H, W, C.c_size_t(W * H),
+                                               C.c_void_p(h_kps.data_ptr()), C.c_void_p(h_desc.data_ptr()), cap,
+                                               C.c_void_p(h_n.data_ptr())))
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(2, K // 2)
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = world * B * e2e_steps / e2e_s
+    e2e_launches = ex.launch_count() * e2e_steps
+
+    line = None
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm = float(peaks.get("hbm_gbs", 6650.0))
+        alg = algorithmic_bytes(W, H, nkp)
+        names = ["pyramid", "fast", "quadtree", "blur", "brief"]
+        per_kernel = {n: kernel_ms[i] / max(ncalls, 1) for i, n in enumerate(names)}
+        dom = max(names, key=lambda n: per_kernel[n])
+        # the quadtree kernel moves almost no bytes (latency-bound list surgery): its roofline entry is the time share
+        dom_bw = "fast" if dom == "quadtree" else dom
+        ach = alg[dom_bw] * B / (per_kernel[dom_bw] * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
+            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "configs[2] shape: batch of %d synthetic EuRoC 752x480 frames per GPU, "
+                                   "ORBextractor(1000,1.2,8,20,7), extraction sharded by frame" % B,
+                       "frames_per_gpu_per_step": B, "l2": "inputs larger than L2 (%d MB per step per GPU)" % (B * W * H >> 20),
+                       "keypoints_per_frame": nkp},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": B * W * H,
+                    "d2h_bytes_per_step": B * (cap * 60 + 4), "steps": e2e_steps},
+            "gpu_launches": launches_per_step * K,
+            "roofline": {"bound": "hbm", "kernel": dom_bw, "achieved": ach, "peak": hbm, "unit": "GB/s",
+                         "frac": ach / hbm, "traffic": None,
+                         "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
+                         "algorithmic_bytes_per_launch": alg[dom_bw] * B, "launch_ms": per_kernel[dom_bw],
+                         "dominant_by_time": dom},
+            "kernels_ms_per_step": per_kernel,
+            "extract_roofline": {"algorithmic_bytes_per_frame": alg["total"],
+                                 "achieved_gbs": alg["total"] * value / world / 1e9,
+                                 "frac_of_hbm": alg["total"] * value / world / 1e9 / hbm},
+        }
+
+    # ---- Hamming matcher, config 4: 1024 pairs of 2000 x 2000 descriptors, ratio test + rotation histogram
+    if not args.no_hamming:
+        m = orbb200.Matcher(local)
+        P, n = 1024, 2000
+        g = torch.Generator(device=dev)
+        g.manual_seed(7 + rank)
+        q = torch.randint(0, 256, (P, n, 32), dtype=torch.uint8, device=dev, generator=g)
+        t = torch.randint(0, 256, (P, n, 32), dtype=torch.uint8, device=dev, generator=g)
+        t[:, : n // 2] = q[:, : n // 2] ^ (torch.randint(0, 256, (P, n // 2, 32), dtype=torch.uint8, device=dev, generator=g)
+                                          & torch.randint(0, 256, (P, n // 2, 32), dtype=torch.uint8, device=dev, generator=g)
+                                          & torch.randint(0, 256, (P, n // 2, 32), dtype=torch.uint8, device=dev, generator=g))
+        qa = torch.rand((P, n), device=dev, generator=g) * 360
+        ta = torch.rand((P, n), device=dev, generator=g) * 360
+        outs = [torch.empty((P, n), dtype=torch.int32, device=dev) for _ in range(4)]
+        nm = torch.empty(P, dtype=torch.int32, device=dev)
+
+        def hstep():
+            m.bruteforce_device(q, qa, t, ta, 0.9, True, outs[0], outs[1], outs[2], outs[3], nm, stream=stream.cuda_stream)
+
+        for _ in range(3):
+            hstep()
+        stream.synchronize()
+        popc = m.popc_peak()
+        barrier()
+        h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        h0.record(stream)
+        for _ in range(K):
+            hstep()
+        h1.record(stream)
+        stream.synchronize()
+        barrier()
+        hms = max_over_ranks(h0.elapsed_time(h1))
+        cps = world * P * n * n * K / (hms * 1e-3)
+        if rank == 0:
+            line["hamming"] = {"workload": "configs[3]: %d pairs/GPU of 2000x2000 descriptors, ratio 0.9 + rotation histogram" % P,
+                               "value": cps, "unit": "compares/s", "ms_per_step": hms / K,
+                               "roofline": {"bound": "popc", "achieved": cps / world * 8 / 1e9, "peak": popc / 1e9,
+                                            "unit": "GPOPC32/s", "frac": cps / world * 8 / popc,
+                                            "peak_source": "orbm_popc_peak microbenchmark in this run"},
+                               "gpu_launches": 2 * K, "matches_per_pair": float(nm.float().mean().item())}
+        m.close()
+
+    # ---- CPU baseline beside it (rank 0, N=1 only): bounded sample, single thread
+    if rank == 0 and world == 1 and not args.no_cpu:
+        frames = [h_images[i].numpy().copy() for i in range(4)]
+        line["cpu_baseline"] = cpu_reference(frames, 1, seconds_budget=12.0)
+    if rank == 0:
+        print(json.dumps(line))
+    ex.close()
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

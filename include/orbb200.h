@@ -94,6 +94,12 @@ int orbx_debug_candidates(orbx_handle h, int frame, int level, orb_keypoint* out
 int orbx_debug_blurred(orbx_handle h, int frame, int level, uint8_t* out /* w*h */);
 /* number of kernel launches issued by the last extract call */
 int orbx_last_launch_count(orbx_handle h, int* n);
+/* Per-kernel device timing for benchmarks: when on, every extract call brackets its kernels with CUDA events on the
+ * launching stream (no synchronisation added).  orbx_kernel_times synchronises, returns the milliseconds summed over
+ * the calls since the last query for [0] pyramid (all levels) [1] FAST cells [2] quadtree+orientation [3] blur
+ * [4] BRIEF+assembly, the number of calls in *n_calls, and resets the accumulation.                              */
+int orbx_set_profiling(orbx_handle h, int on);
+int orbx_kernel_times(orbx_handle h, double* ms5, int* n_calls);
 
 /* ================================================================================================== matcher */
 typedef struct orbm_matcher* orbm_handle;

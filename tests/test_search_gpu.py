@@ -1,0 +1,180 @@
+"""GPU parity of the Frame grid and the windowed / vocabulary-gated searches against the oracle restatement of
+Frame.cc:574-736 and ORBmatcher.cc:45-129, 405-520, 657-823, 1341-1498.  Everything here is integer or bit-exact float."""
+import numpy as np
+import pytest
+
+import orbb200
+from orbb200.synth import shifted_pair
+
+pytestmark = pytest.mark.gpu
+
+SF = np.array([1.2 ** i for i in range(8)], np.float32)
+
+
+@pytest.fixture(scope="module")
+def pair(oracle):
+    """Two views of one synthetic scene (second shifted by (+7,+3) px), 2000 features each (config 1 / 2 inputs)."""
+    out = {}
+    for name, (w, h) in (("euroc", (752, 480)), ("kitti", (1241, 376))):
+        a, b = shifted_pair(3, w, h)
+        oe = oracle.extractor(2000)
+        ka, da = oe.extract(a)
+        kb, db = oe.extract(b)
+        out[name] = (ka, da, kb, db, (0.0, 0.0, float(w), float(h)))
+    return out
+
+
+def _frames(matcher, oracle, k, d, bounds):
+    return matcher.frame(k, d, bounds), oracle.frame(k, d, bounds)
+
+
+@pytest.mark.parametrize("name", ["euroc", "kitti"])
+def test_grid_and_area(matcher, oracle, pair, name):
+    ka, da, kb, db, bounds = pair[name]
+    # keys outside the bounds must be dropped (PosInGrid false), keys on a .5 boundary go to round-half-away
+    k = ka.copy()
+    k["x"][:5] = [-3.0, bounds[2] + 5, 0.0, bounds[2], bounds[2] * (10.5 / 64)]
+    k["y"][5:9] = [-1.0, bounds[3] + 9, bounds[3], bounds[3] * (7.5 / 48)]
+    g, o = _frames(matcher, oracle, k, da, bounds)
+    gs, gi = g.grid()
+    os_, oi = o.grid()
+    assert np.array_equal(gs, os_) and np.array_equal(gi, oi)
+    assert gs[-1] < len(k)
+    rng = np.random.default_rng(1)
+    xyr = np.stack([rng.uniform(-50, bounds[2] + 50, 300), rng.uniform(-50, bounds[3] + 50, 300),
+                    rng.choice([2.5, 15.0, 30.0, 100.0, 400.0], 300)], 1).astype(np.float32)
+    for (mn, mx) in ((-1, -1), (0, 0), (2, 4), (3, -1), (0, 7)):
+        got = g.area(xyr, mn, mx)
+        for i in range(len(xyr)):
+            ref = o.area(float(xyr[i, 0]), float(xyr[i, 1]), float(xyr[i, 2]), mn, mx)
+            assert np.array_equal(got[i], ref), (i, mn, mx)
+
+
+@pytest.mark.parametrize("name,ratio,ori,window", [("euroc", 0.9, True, 100), ("euroc", 0.9, False, 30),
+                                                    ("kitti", 0.6, True, 100)])
+def test_search_for_initialization(matcher, oracle, pair, name, ratio, ori, window):
+    ka, da, kb, db, bounds = pair[name]
+    g1, o1 = _frames(matcher, oracle, ka, da, bounds)
+    g2, o2 = _frames(matcher, oracle, kb, db, bounds)
+    prev = np.stack([ka["x"], ka["y"]], 1).astype(np.float32)   # Tracking.cc:1637-1639
+    n, m12, p = matcher.search_for_initialization(g1, g2, prev, window, ratio, ori)
+    rn, rm12, rp = o1.search_init(o2, prev, window, ratio, ori)
+    assert n == rn and np.array_equal(m12, rm12) and np.array_equal(p, rp)
+    assert n > 50
+    # second call with the updated vbPrevMatched, roles of the frames kept (as the tracker does frame after frame)
+    n2, m12b, p2 = matcher.search_for_initialization(g1, g2, p, window, ratio, ori)
+    rn2, rm12b, rp2 = o1.search_init(o2, rp, window, ratio, ori)
+    assert n2 == rn2 and np.array_equal(m12b, rm12b) and np.array_equal(p2, rp2)
+
+
+def _proj_queries(rng, ka, n_levels=8):
+    q = np.zeros(len(ka), orbb200.PROJ_QUERY_DTYPE)
+    q["u"] = ka["x"] - 7 + rng.normal(0, 1.5, len(ka))
+    q["v"] = ka["y"] - 3 + rng.normal(0, 1.5, len(ka))
+    q["invz"] = rng.uniform(0.02, 0.5, len(ka))
+    q["octave"] = ka["octave"]
+    q["valid"] = rng.random(len(ka)) < 0.8
+    q["obs_positive"] = rng.random(len(ka)) < 0.9
+    q["angle"] = ka["angle"]
+    q["u"][:3] = [-5, 1e4, 10]
+    q["v"][:3] = [10, 10, -8]
+    return q
+
+
+@pytest.mark.parametrize("name,th,mode,stereo,ori", [("kitti", 15.0, 0, False, True), ("kitti", 30.0, 0, False, True),
+                                                      ("euroc", 7.0, 1, True, True), ("euroc", 15.0, 2, True, False)])
+def test_search_by_projection(matcher, oracle, pair, name, th, mode, stereo, ori):
+    ka, da, kb, db, bounds = pair[name]
+    rng = np.random.default_rng(int(th) + mode)
+    g, o = _frames(matcher, oracle, kb, db, bounds)
+    q = _proj_queries(rng, ka)
+    occ = (rng.random(len(kb)) < 0.1).astype(np.uint8)
+    ur = None
+    mbf = 0.0
+    if stereo:
+        mbf = 40.0
+        ur = np.where(rng.random(len(kb)) < 0.6, kb["x"] - mbf * rng.uniform(0.02, 0.5, len(kb)), -1).astype(np.float32)
+    n, match = matcher.search_by_projection(g, SF, q, da, th, mode, occ, ur, mbf, ori)
+    oq = q.view(np.dtype([(a, b) for a, b in zip(("u", "v", "invz", "octave", "valid", "obsPositive", "angle"),
+                                                   ("<f4", "<f4", "<f4", "<i4", "<i4", "<i4", "<f4"))]))
+    rn, rmatch = o.search_projection(SF, oq, da, th, mode, occ, ur, mbf, ori)
+    assert n == rn and np.array_equal(match, rmatch)
+    if not stereo:
+        assert n > 100
+
+
+@pytest.mark.parametrize("name,th,ratio", [("euroc", 1.0, 0.8), ("kitti", 3.0, 0.8), ("euroc", 5.0, 0.6)])
+def test_search_by_projection_points(matcher, oracle, pair, name, th, ratio):
+    ka, da, kb, db, bounds = pair[name]
+    rng = np.random.default_rng(int(th * 10))
+    g, o = _frames(matcher, oracle, kb, db, bounds)
+    q = np.zeros(len(ka), orbb200.POINT_QUERY_DTYPE)
+    q["proj_x"] = ka["x"] - 7 + rng.normal(0, 1.0, len(ka))
+    q["proj_y"] = ka["y"] - 3 + rng.normal(0, 1.0, len(ka))
+    q["proj_xr"] = q["proj_x"] - 5
+    q["view_cos"] = rng.choice([0.9, 0.998, 0.9985, 1.0], len(ka))
+    q["level"] = np.clip(ka["octave"] + rng.integers(0, 2, len(ka)), 0, 7)
+    q["in_view"] = rng.random(len(ka)) < 0.85
+    q["obs_positive"] = rng.random(len(ka)) < 0.9
+    occ = (rng.random(len(kb)) < 0.05).astype(np.uint8)
+    ur = np.where(rng.random(len(kb)) < 0.3, kb["x"] - 5 + rng.normal(0, 3, len(kb)), -1).astype(np.float32)
+    n, match = matcher.search_by_projection_points(g, SF, q, da, th, ratio, occ, ur)
+    oq = q.view(np.dtype([(a, b) for a, b in zip(("projX", "projY", "projXR", "viewCos", "level", "inView", "obsPositive"),
+                                                   ("<f4", "<f4", "<f4", "<f4", "<i4", "<i4", "<i4"))]))
+    rn, rmatch = o.search_points(SF, oq, da, th, ratio, occ, ur)
+    assert n == rn and np.array_equal(match, rmatch)
+    assert n > 50
+
+
+def _feature_vector(keys, dx, dy, cell=48):
+    """Stand-in for DBoW2::FeatureVector (node id -> keypoint indices, ascending ids): a coarse spatial hash, shifted so
+    that corresponding points of the two views mostly share a node."""
+    node = ((keys["y"] + dy) // cell).astype(np.int64) * 100 + ((keys["x"] + dx) // cell).astype(np.int64)
+    ids = np.unique(node)
+    start, idx = [0], []
+    for i in ids:
+        members = np.nonzero(node == i)[0]
+        idx.extend(members.tolist())
+        start.append(len(idx))
+    return ids.astype(np.int32), np.array(start, np.int32), np.array(idx, np.int32)
+
+
+@pytest.mark.parametrize("name,only_stereo,ori", [("euroc", False, False), ("kitti", False, True), ("euroc", True, True)])
+def test_search_for_triangulation(matcher, oracle, pair, name, only_stereo, ori):
+    ka, da, kb, db, bounds = pair[name]
+    rng = np.random.default_rng(5 + only_stereo)
+    g1, o1 = _frames(matcher, oracle, ka, da, bounds)
+    g2, o2 = _frames(matcher, oracle, kb, db, bounds)
+    fv1 = _feature_vector(ka, 0, 0)
+    fv2 = _feature_vector(kb, 7, 3)
+    fv2 = (fv2[0][::1].copy(), fv2[1], fv2[2])
+    # pure image translation t=(-7,-3,0): F12 = [t]x, epipolar lines are parallel to t
+    F12 = np.array([[0, 0, -3.0], [0, 0, 7.0], [3.0, -7.0, 0]], np.float32) * 1e-2
+    has1 = (rng.random(len(ka)) < 0.3).astype(np.uint8)
+    has2 = (rng.random(len(kb)) < 0.3).astype(np.uint8)
+    ur1 = np.where(rng.random(len(ka)) < 0.5, 10.0, -1.0).astype(np.float32) if only_stereo else None
+    ur2 = np.where(rng.random(len(kb)) < 0.5, 10.0, -1.0).astype(np.float32) if only_stereo else None
+    sigma2 = (SF * SF).astype(np.float32)
+    n, m12 = matcher.search_for_triangulation(g1, g2, fv1, fv2, F12, 3000.0, 200.0, SF, sigma2, has1, has2, ur1, ur2,
+                                              only_stereo, ori)
+    rn, rm12 = o1.search_triangulation(o2, fv1, fv2, F12, 3000.0, 200.0, SF, sigma2, has1, has2, ur1, ur2, only_stereo, ori)
+    assert n == rn and np.array_equal(m12, rm12)
+    assert n > 20
+
+
+def test_search_edge_cases(matcher, oracle, pair):
+    ka, da, kb, db, bounds = pair["euroc"]
+    empty = matcher.frame(ka[:0], da[:0], bounds)
+    g2 = matcher.frame(kb, db, bounds)
+    n, m12, p = matcher.search_for_initialization(empty, g2, np.zeros((0, 2), np.float32))
+    assert n == 0 and len(m12) == 0
+    g1 = matcher.frame(ka, da, bounds)
+    n, m12, p = matcher.search_for_initialization(g1, empty, np.stack([ka["x"], ka["y"]], 1))
+    assert n == 0 and (m12 == -1).all()
+    q = np.zeros(4, orbb200.PROJ_QUERY_DTYPE)
+    q["valid"] = 1
+    q["octave"] = 9                                  # outside the scale table
+    with pytest.raises(orbb200.OrbError):
+        matcher.search_by_projection(g2, SF, q, da[:4], 15.0)
+    with pytest.raises(orbb200.OrbError):
+        matcher.frame(ka, da, (0.0, 0.0, 0.0, 480.0))   # empty bounds

@@ -60,6 +60,10 @@ struct orbx_extractor {
     int launches = 0;
     double stageMs[3] = {0, 0, 0};
     bool timed = false;
+    // optional per-kernel event sets (orbx_set_profiling)
+    bool profiling = false;
+    std::vector<cudaEvent_t> profEvents;   // 6 per profiled call
+    int profCalls = 0;
 };
 
 namespace {
@@ -212,15 +216,32 @@ int enqueue(orbx_extractor* e, const uint8_t* dImages, int nFrames, int w, int h
     P.outCapacity = capacity;
     e->lastCapacity = capacity;
     e->timed = timed;
+    cudaEvent_t* pe = nullptr;
+    if (e->profiling && e->profCalls < 4096) {
+        if ((int)e->profEvents.size() < 6 * (e->profCalls + 1)) {
+            for (int i = 0; i < 6; ++i) {
+                cudaEvent_t ev;
+                ORB_CUDA(cudaEventCreate(&ev));
+                e->profEvents.push_back(ev);
+            }
+        }
+        pe = &e->profEvents[6 * e->profCalls++];
+    }
     if (timed) ORB_CUDA(cudaEventRecord(e->ev[0], st));
+    if (pe) ORB_CUDA(cudaEventRecord(pe[0], st));
     ORB_CHECK(launch_pyramid(P, dImages, w, h, stride, frameStride, st, &e->launches));
     if (timed) ORB_CUDA(cudaEventRecord(e->ev[1], st));
+    if (pe) ORB_CUDA(cudaEventRecord(pe[1], st));
     ORB_CHECK(launch_fast(P, st, &e->launches));
+    if (pe) ORB_CUDA(cudaEventRecord(pe[2], st));
     ORB_CHECK(launch_octree(P, e->otSmem, e->otKeyCap, e->otNodeCap, e->otCellCap, st, &e->launches));
     if (timed) ORB_CUDA(cudaEventRecord(e->ev[2], st));
+    if (pe) ORB_CUDA(cudaEventRecord(pe[3], st));
     ORB_CHECK(launch_blur(P, e->dTiles.as<BlurTile>(), (int)e->tiles.size(), st, &e->launches));
+    if (pe) ORB_CUDA(cudaEventRecord(pe[4], st));
     ORB_CHECK(launch_brief(P, std::min(capacity, e->kpCapacity), dKps, dDesc, dCount, st, &e->launches));
     if (timed) ORB_CUDA(cudaEventRecord(e->ev[3], st));
+    if (pe) ORB_CUDA(cudaEventRecord(pe[5], st));
     return ORB_OK;
 }
 
@@ -315,6 +336,7 @@ int orbx_destroy(orbx_handle e) {
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < 4; ++i)
         if (e->ev[i]) cudaEventDestroy(e->ev[i]);
+    for (cudaEvent_t ev : e->profEvents) cudaEventDestroy(ev);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
     return ORB_OK;
@@ -482,6 +504,31 @@ int orbx_debug_blurred(orbx_handle e, int frame, int level, uint8_t* out) {
     ORB_CUDA(cudaStreamSynchronize(e->stream));
     ORB_CUDA(cudaMemcpy2D(out, L.w, e->P.blur + (size_t)frame * e->P.blurFrameBytes + L.blurOff, L.bpitch, L.w, L.h,
                           cudaMemcpyDeviceToHost));
+    return ORB_OK;
+}
+
+int orbx_set_profiling(orbx_handle e, int on) {
+    if (!e) return fail(ORB_ERR_INVALID, "orbx_set_profiling: null handle");
+    e->profiling = on != 0;
+    e->profCalls = 0;
+    return ORB_OK;
+}
+
+int orbx_kernel_times(orbx_handle e, double* ms5, int* nCalls) {
+    ORBX_ENTER(e);
+    if (!ms5 || !nCalls) return fail(ORB_ERR_INVALID, "orbx_kernel_times: null argument");
+    for (int k = 0; k < 5; ++k) ms5[k] = 0;
+    for (int c = 0; c < e->profCalls; ++c) {
+        cudaEvent_t* pe = &e->profEvents[6 * c];
+        ORB_CUDA(cudaEventSynchronize(pe[5]));
+        for (int k = 0; k < 5; ++k) {
+            float ms = 0;
+            ORB_CUDA(cudaEventElapsedTime(&ms, pe[k], pe[k + 1]));
+            ms5[k] += ms;
+        }
+    }
+    *nCalls = e->profCalls;
+    e->profCalls = 0;
     return ORB_OK;
 }
 

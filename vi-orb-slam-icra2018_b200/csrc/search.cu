@@ -1,0 +1,850 @@
+// Windowed and vocabulary-gated searches of ORBmatcher on flat arrays, plus the Frame grid they read.
+//
+//   Frame::AssignFeaturesToGrid / PosInGrid / GetFeaturesInArea     Frame.cc:574-589, 726-736, 671-724
+//   ORBmatcher::SearchForInitialization                             ORBmatcher.cc:405-520
+//   ORBmatcher::SearchByProjection(Frame&, const Frame&, th, mono)  ORBmatcher.cc:1341-1498
+//   ORBmatcher::SearchByProjection(Frame&, vector<MapPoint*>&, th)  ORBmatcher.cc:45-129
+//   ORBmatcher::SearchForTriangulation (+CheckDistEpipolarLine)     ORBmatcher.cc:657-823, 140-157
+//
+// The reference loops are "parallel distances, sequential bookkeeping": a later query sees what earlier queries
+// matched (vMatchedDistance / mvpMapPoints).  They are split accordingly:
+//   phase 1 (one warp per query, whole GPU): enumerate the grid candidates in the reference's order (cell column,
+//            cell row, bucket order), apply the static filters, compute the 256-bit Hamming distances;
+//   phase 2 (one warp per search): replay the queries in order over the stored (index, distance) lists with the
+//            dynamic skip rules; lanes split a query's candidates and merge (distance, order) keys by shuffle.
+// SearchForTriangulation never sets vbMatched2 (ORBmatcher.cc:725), so its queries are independent: one thread each.
+#include <vector>
+
+#include "matcher.h"
+
+namespace orbb {
+
+struct FrameDev {
+    int n;
+    const orb_keypoint* keys;
+    const uint4* desc;
+    const int* cellStart;   // [64*48 + 1], cell id = ix*48 + iy
+    const int* cellIdx;
+    float minX, minY, maxX, maxY, invW, invH;
+};
+
+struct AreaQuery {       // one GetFeaturesInArea call + the static per-candidate stereo filter
+    float x, y, r;
+    int minLevel, maxLevel;
+    int active;
+    float stereoCenter, stereoTol;   // candidate with uRight > 0 is dropped if |stereoCenter - uRight| > stereoTol
+};
+
+constexpr int kCells = kGridCols * kGridRows;
+
+// ------------------------------------------------------------------------------------------------ grid build
+__global__ void grid_count_kernel(FrameDev f, int* cellOf, int* counts) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= f.n) return;
+    const int px = (int)roundf(__fmul_rn(__fsub_rn(f.keys[i].x, f.minX), f.invW));   // PosInGrid, Frame.cc:728-729
+    const int py = (int)roundf(__fmul_rn(__fsub_rn(f.keys[i].y, f.minY), f.invH));
+    int c = -1;
+    if (px >= 0 && px < kGridCols && py >= 0 && py < kGridRows) {
+        c = px * kGridRows + py;
+        atomicAdd(&counts[c], 1);
+    }
+    cellOf[i] = c;
+}
+
+// exclusive scan of n ints by one block of 1024 threads (n is a few thousand)
+__global__ void __launch_bounds__(1024) scan_kernel(const int* in, int* out, int n) {
+    __shared__ int warpSums[32];
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int v = i < n ? in[i] : 0;
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((threadIdx.x & 31) >= o) incl += t;
+        }
+        if ((threadIdx.x & 31) == 31) warpSums[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        int wbase = 0;
+        for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) wbase += warpSums[w];
+        const int c = carry;
+        if (i < n) out[i] = c + wbase + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = c + wbase + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[n] = carry;
+}
+
+__global__ void grid_fill_kernel(int n, const int* cellOf, const int* cellStart, int* cursor, int* cellIdx) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int c = cellOf[i];
+    if (c >= 0) cellIdx[cellStart[c] + atomicAdd(&cursor[c], 1)] = i;
+}
+
+// buckets were filled in arbitrary order; the reference pushes indices in ascending order (Frame.cc:581-588)
+__global__ void grid_sort_kernel(const int* cellStart, int* cellIdx) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= kCells) return;
+    const int a = cellStart[c], b = cellStart[c + 1];
+    for (int i = a + 1; i < b; ++i) {
+        const int v = cellIdx[i];
+        int j = i - 1;
+        while (j >= a && cellIdx[j] > v) { cellIdx[j + 1] = cellIdx[j]; --j; }
+        cellIdx[j + 1] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ candidate enumeration
+struct CellRange { int c0, c1, r0, r1; bool empty; };
+
+__device__ __forceinline__ CellRange cell_range(const FrameDev& f, float x, float y, float r) {   // Frame.cc:676-690
+    CellRange cr;
+    cr.empty = true;
+    cr.c0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(x, f.minX), r), f.invW)));
+    if (cr.c0 >= kGridCols) return cr;
+    cr.c1 = min(kGridCols - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(x, f.minX), r), f.invW)));
+    if (cr.c1 < 0) return cr;
+    cr.r0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(y, f.minY), r), f.invH)));
+    if (cr.r0 >= kGridRows) return cr;
+    cr.r1 = min(kGridRows - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(y, f.minY), r), f.invH)));
+    if (cr.r1 < 0) return cr;
+    cr.empty = false;
+    return cr;
+}
+
+// One warp walks the query's cells in reference order; `emit(idx, position)` is called by the lane that owns the
+// candidate, positions are the candidate's rank in the reference's vIndices. Returns the candidate count.
+template <class Emit>
+__device__ __forceinline__ int warp_enumerate(const FrameDev& f, const AreaQuery& q, const float* uRight, Emit emit) {
+    const int lane = threadIdx.x & 31;
+    const CellRange cr = cell_range(f, q.x, q.y, q.r);
+    if (cr.empty) return 0;
+    const bool checkLevels = (q.minLevel > 0) || (q.maxLevel >= 0);   // Frame.cc:692
+    int base = 0;
+    for (int ix = cr.c0; ix <= cr.c1; ++ix)
+        for (int iy = cr.r0; iy <= cr.r1; ++iy) {
+            const int c = ix * kGridRows + iy;
+            const int a = f.cellStart[c], b = f.cellStart[c + 1];
+            for (int k0 = a; k0 < b; k0 += 32) {
+                const int k = k0 + lane;
+                bool ok = false;
+                int idx = -1;
+                if (k < b) {
+                    idx = f.cellIdx[k];
+                    const orb_keypoint kp = f.keys[idx];
+                    ok = true;
+                    if (checkLevels) {
+                        if (kp.octave < q.minLevel) ok = false;
+                        if (q.maxLevel >= 0 && kp.octave > q.maxLevel) ok = false;
+                    }
+                    const float dx = __fsub_rn(kp.x, q.x), dy = __fsub_rn(kp.y, q.y);
+                    if (!(fabsf(dx) < q.r && fabsf(dy) < q.r)) ok = false;
+                    if (ok && uRight) {
+                        const float ur = uRight[idx];
+                        if (ur > 0 && fabsf(__fsub_rn(q.stereoCenter, ur)) > q.stereoTol) ok = false;
+                    }
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, ok);
+                if (ok) emit(idx, base + __popc(m & ((1u << lane) - 1u)));
+                base += __popc(m);
+            }
+        }
+    return base;
+}
+
+// count (cand == nullptr) or fill the per-query candidate lists: (train index, distance) in reference order.
+// stereoInFill: the stereo filter is static, so it is applied here; the dynamic filters wait for phase 2.
+__global__ void __launch_bounds__(256)
+candidates_kernel(FrameDev f, const AreaQuery* __restrict__ queries, const uint4* __restrict__ qdesc, int nq,
+                  const float* __restrict__ uRight, int* __restrict__ counts, const int* __restrict__ offsets,
+                  int2* __restrict__ cand) {
+    const int qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (qi >= nq) return;
+    const AreaQuery q = queries[qi];
+    int n = 0;
+    if (q.active) {
+        if (!cand) {
+            n = warp_enumerate(f, q, uRight, [](int, int) {});
+        } else {
+            const uint4 qa = qdesc[2 * qi], qb = qdesc[2 * qi + 1];
+            int2* out = cand + offsets[qi];
+            n = warp_enumerate(f, q, uRight, [&](int idx, int pos) {
+                out[pos] = make_int2(idx, hamming256(qa, qb, f.desc[2 * idx], f.desc[2 * idx + 1]));
+            });
+        }
+    }
+    if (!cand && (threadIdx.x & 31) == 0) counts[qi] = n;
+}
+
+// GetFeaturesInArea as an API of its own (tests, adapter)
+__global__ void __launch_bounds__(256)
+area_kernel(FrameDev f, const float* __restrict__ xyr, int nq, int minLevel, int maxLevel, int* __restrict__ idxOut,
+            int cap, int* __restrict__ countOut) {
+    const int qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (qi >= nq) return;
+    AreaQuery q;
+    q.x = xyr[3 * qi]; q.y = xyr[3 * qi + 1]; q.r = xyr[3 * qi + 2];
+    q.minLevel = minLevel; q.maxLevel = maxLevel; q.active = 1; q.stereoCenter = 0; q.stereoTol = 0;
+    int* out = idxOut + (size_t)qi * cap;
+    const int n = warp_enumerate(f, q, nullptr, [&](int idx, int pos) { if (pos < cap) out[pos] = idx; });
+    if ((threadIdx.x & 31) == 0) countOut[qi] = n;
+}
+
+// ------------------------------------------------------------------------------------------------ query builders
+__global__ void init_queries_kernel(FrameDev f1, const float* __restrict__ prevXY, int window, AreaQuery* __restrict__ q) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= f1.n) return;
+    AreaQuery a;
+    const int level1 = f1.keys[i].octave;
+    a.x = prevXY[2 * i]; a.y = prevXY[2 * i + 1]; a.r = (float)window;
+    a.minLevel = level1; a.maxLevel = level1;
+    a.active = level1 > 0 ? 0 : 1;                        // ORBmatcher.cc:421-423
+    a.stereoCenter = 0; a.stereoTol = 0;
+    q[i] = a;
+}
+
+__global__ void proj_queries_kernel(FrameDev cur, const orbm_proj_query* __restrict__ pq, int nq,
+                                    const float* __restrict__ sf, float th, int mode, float mbf, AreaQuery* __restrict__ q) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    const orbm_proj_query p = pq[i];
+    AreaQuery a;
+    a.x = p.u; a.y = p.v;
+    a.active = p.valid != 0;
+    if (p.u < cur.minX || p.u > cur.maxX) a.active = 0;   // ORBmatcher.cc:1390-1393
+    if (p.v < cur.minY || p.v > cur.maxY) a.active = 0;
+    const int o = p.octave;
+    a.r = __fmul_rn(th, sf[o]);                           // :1398
+    if (mode == 1) { a.minLevel = o; a.maxLevel = -1; }   // forward  (:1409)
+    else if (mode == 2) { a.minLevel = 0; a.maxLevel = o; }   // backward (:1411)
+    else { a.minLevel = o - 1; a.maxLevel = o + 1; }      // :1413
+    a.stereoCenter = __fsub_rn(p.u, __fmul_rn(mbf, p.invz));   // :1435
+    a.stereoTol = a.r;
+    q[i] = a;
+}
+
+__global__ void point_queries_kernel(const orbm_point_query* __restrict__ pq, int nq, const float* __restrict__ sf, float th,
+                                     AreaQuery* __restrict__ q) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    const orbm_point_query p = pq[i];
+    AreaQuery a;
+    float r = ((double)p.view_cos > 0.998) ? 2.5f : 4.0f;   // RadiusByViewingCos, ORBmatcher.cc:131-137
+    if (th != 1.0f) r = __fmul_rn(r, th);                    // bFactor (:49, 65-66)
+    a.x = p.proj_x; a.y = p.proj_y;
+    a.r = __fmul_rn(r, sf[p.level]);
+    a.minLevel = p.level - 1; a.maxLevel = p.level;          // :69
+    a.active = p.in_view != 0;
+    a.stereoCenter = p.proj_xr; a.stereoTol = a.r;           // :94-99
+    q[i] = a;
+}
+
+// ------------------------------------------------------------------------------------------------ phase 2: replays
+constexpr int kOrdShift = 22;
+constexpr int kOrdMask = (1 << kOrdShift) - 1;
+constexpr int kNone = 0x7fffffff;
+
+__device__ __forceinline__ void warp_min2(int& best, int& second) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const int ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int os = __shfl_xor_sync(0xffffffffu, second, o);
+        second = min(min(second, os), max(best, ob));
+        best = min(best, ob);
+    }
+}
+
+// rotation-histogram tail shared by the searches: pushes are (bin, value) pairs in push order
+__device__ void prune_pushes(const int* pushBin, const int* pushVal, int nPush, int* hist, int* target, bool guardMatched,
+                             int* nmatches) {
+    const int lane = threadIdx.x & 31;
+    __shared__ int keep[3];
+    __syncwarp();
+    if (lane == 0) three_maxima(hist, keep[0], keep[1], keep[2]);
+    __syncwarp();
+    int removed = 0;
+    if (lane == 0) {   // sequential: the same value can be pushed twice and every push decrements (ORBmatcher.cc:1483-1491)
+        for (int k = 0; k < nPush; ++k) {
+            const int b = pushBin[k];
+            if (b == keep[0] || b == keep[1] || b == keep[2]) continue;
+            const int v = pushVal[k];
+            if (guardMatched) {
+                if (target[v] >= 0) { target[v] = -1; ++removed; }
+            } else {
+                target[v] = -1;
+                ++removed;
+            }
+        }
+        *nmatches -= removed;
+    }
+    __syncwarp();
+}
+
+// SearchForInitialization replay (ORBmatcher.cc:417-517). One warp.
+__global__ void __launch_bounds__(32)
+init_replay_kernel(FrameDev f1, FrameDev f2, const AreaQuery* __restrict__ q, const int* __restrict__ offsets,
+                   const int2* __restrict__ cand, float ratio, int checkOri, float* prevXY, int* m12, int* m21,
+                   int* matchedDist, int* pushBin, int* pushVal, int* nmatchesOut) {
+    __shared__ int hist[kHistoLength];
+    __shared__ int nmatches;
+    const int lane = threadIdx.x;
+    if (lane < kHistoLength) hist[lane] = 0;
+    if (lane == 0) nmatches = 0;
+    for (int i = lane; i < f1.n; i += 32) m12[i] = -1;
+    for (int i = lane; i < f2.n; i += 32) { m21[i] = -1; matchedDist[i] = INT_MAX; }
+    __syncwarp();
+    int nPush = 0;
+    for (int i1 = 0; i1 < f1.n; ++i1) {
+        if (!q[i1].active) continue;
+        const int a = offsets[i1], b = offsets[i1 + 1];
+        if (a == b) continue;
+        int best = kNone, second = kNone;
+        for (int k = a + lane; k < b; k += 32) {
+            const int2 c = cand[k];
+            if (matchedDist[c.x] <= c.y) continue;                     // :444
+            const int key = (c.y << kOrdShift) | (k - a);
+            second = min(second, max(key, best));
+            best = min(best, key);
+        }
+        warp_min2(best, second);
+        const int bd = best == kNone ? INT_MAX : best >> kOrdShift;
+        const int sd = second == kNone ? INT_MAX : second >> kOrdShift;
+        if (bd <= kThLow && (float)bd < __fmul_rn((float)sd, ratio)) {   // :459-461
+            if (lane == 0) {
+                const int i2 = cand[a + (best & kOrdMask)].x;
+                if (m21[i2] >= 0) { m12[m21[i2]] = -1; --nmatches; }
+                m12[i1] = i2; m21[i2] = i1; matchedDist[i2] = bd; ++nmatches;
+                if (checkOri) {
+                    const int bin = rotation_bin(f1.keys[i1].angle, f2.keys[i2].angle);
+                    hist[bin] += 1;
+                    pushBin[nPush] = bin; pushVal[nPush] = i1;
+                }
+            }
+            if (checkOri) ++nPush;
+            __syncwarp();
+        }
+    }
+    __threadfence_block();
+    if (checkOri) prune_pushes(pushBin, pushVal, nPush, hist, m12, true, &nmatches);
+    __syncwarp();
+    for (int i1 = lane; i1 < f1.n; i1 += 32)
+        if (m12[i1] >= 0) {                                             // :515-517
+            prevXY[2 * i1] = f2.keys[m12[i1]].x;
+            prevXY[2 * i1 + 1] = f2.keys[m12[i1]].y;
+        }
+    if (lane == 0) *nmatchesOut = nmatches;
+}
+
+// SearchByProjection(Frame, Frame) replay (ORBmatcher.cc:1363-1495). One warp.
+__global__ void __launch_bounds__(32)
+proj_replay_kernel(FrameDev cur, const AreaQuery* __restrict__ q, const orbm_proj_query* __restrict__ pq, int nq,
+                   const int* __restrict__ offsets, const int2* __restrict__ cand, int checkOri, unsigned char* occ,
+                   int* curMatch, int* pushBin, int* pushVal, int* nmatchesOut) {
+    __shared__ int hist[kHistoLength];
+    __shared__ int nmatches;
+    const int lane = threadIdx.x;
+    if (lane < kHistoLength) hist[lane] = 0;
+    if (lane == 0) nmatches = 0;
+    for (int i = lane; i < cur.n; i += 32) curMatch[i] = -1;
+    __syncwarp();
+    int nPush = 0;
+    for (int i = 0; i < nq; ++i) {
+        if (!q[i].active) continue;
+        const int a = offsets[i], b = offsets[i + 1];
+        if (a == b) continue;
+        int best = kNone;
+        for (int k = a + lane; k < b; k += 32) {
+            const int2 c = cand[k];
+            if (occ[c.x]) continue;                                     // :1428-1430
+            best = min(best, (c.y << kOrdShift) | (k - a));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+        const int bd = best == kNone ? 256 : best >> kOrdShift;
+        if (bd <= kThHigh) {                                            // :1453
+            if (lane == 0) {
+                const int i2 = cand[a + (best & kOrdMask)].x;
+                curMatch[i2] = i;
+                occ[i2] = pq[i].obs_positive ? 1 : 0;
+                ++nmatches;
+                if (checkOri) {
+                    const int bin = rotation_bin(pq[i].angle, cur.keys[i2].angle);
+                    hist[bin] += 1;
+                    pushBin[nPush] = bin; pushVal[nPush] = i2;
+                }
+            }
+            if (checkOri) ++nPush;
+            __syncwarp();
+        }
+    }
+    __threadfence_block();
+    if (checkOri) prune_pushes(pushBin, pushVal, nPush, hist, curMatch, false, &nmatches);
+    __syncwarp();
+    if (lane == 0) *nmatchesOut = nmatches;
+}
+
+// SearchByProjection(Frame, MapPoints) replay (ORBmatcher.cc:51-126). One warp.
+__global__ void __launch_bounds__(32)
+point_replay_kernel(FrameDev f, const AreaQuery* __restrict__ q, const orbm_point_query* __restrict__ pq, int nq,
+                    const int* __restrict__ offsets, const int2* __restrict__ cand, float ratio, unsigned char* occ,
+                    int* match, int* nmatchesOut) {
+    const int lane = threadIdx.x;
+    for (int i = lane; i < f.n; i += 32) match[i] = -1;
+    __syncwarp();
+    int nmatches = 0;
+    for (int i = 0; i < nq; ++i) {
+        if (!q[i].active) continue;
+        const int a = offsets[i], b = offsets[i + 1];
+        if (a == b) continue;
+        int best = kNone, second = kNone;
+        for (int k = a + lane; k < b; k += 32) {
+            const int2 c = cand[k];
+            if (occ[c.x]) continue;                                     // :84-86
+            const int key = (c.y << kOrdShift) | (k - a);
+            second = min(second, max(key, best));
+            best = min(best, key);
+        }
+        warp_min2(best, second);
+        const int bd = best == kNone ? 256 : best >> kOrdShift;
+        if (bd <= kThHigh) {                                            // :115
+            const int bi = cand[a + (best & kOrdMask)].x;
+            const int bestLevel = f.keys[bi].octave;
+            int sd = 256, secondLevel = -1;
+            if (second != kNone) {
+                sd = second >> kOrdShift;
+                secondLevel = f.keys[cand[a + (second & kOrdMask)].x].octave;
+            }
+            if (bestLevel == secondLevel && (float)bd > __fmul_rn(ratio, (float)sd)) continue;   // :118-119
+            if (lane == 0) {
+                match[bi] = i;
+                occ[bi] = pq[i].obs_positive ? 1 : 0;
+            }
+            ++nmatches;
+            __syncwarp();
+        }
+    }
+    if (lane == 0) *nmatchesOut = nmatches;
+}
+
+// ------------------------------------------------------------------------------------------------ triangulation
+struct TriParams {
+    FrameDev k1, k2;
+    int nNodes1, nNodes2, nEntries1;
+    const int *nodeId1, *start1, *idx1, *nodeId2, *start2, *idx2;
+    const unsigned char *has1, *has2;
+    const float *uR1, *uR2;
+    float F[9];
+    float ex, ey;
+    const float *sf2, *sigma2;
+    int onlyStereo, checkOri;
+};
+
+__device__ __forceinline__ bool epipolar_ok(const orb_keypoint& k1, const orb_keypoint& k2, const float* F, const float* sigma2) {
+    // l = x1' F12 (ORBmatcher.cc:143-145), all float32, left to right, no contraction
+    const float a = __fadd_rn(__fadd_rn(__fmul_rn(k1.x, F[0]), __fmul_rn(k1.y, F[3])), F[6]);
+    const float b = __fadd_rn(__fadd_rn(__fmul_rn(k1.x, F[1]), __fmul_rn(k1.y, F[4])), F[7]);
+    const float c = __fadd_rn(__fadd_rn(__fmul_rn(k1.x, F[2]), __fmul_rn(k1.y, F[5])), F[8]);
+    const float num = __fadd_rn(__fadd_rn(__fmul_rn(a, k2.x), __fmul_rn(b, k2.y)), c);
+    const float den = __fadd_rn(__fmul_rn(a, a), __fmul_rn(b, b));
+    if (den == 0) return false;
+    const float dsqr = __fdiv_rn(__fmul_rn(num, num), den);
+    return (double)dsqr < __dmul_rn(3.84, (double)sigma2[k2.octave]);   // :156, compared in double
+}
+
+// one thread per feature-vector entry of KF1: node lookup by binary search replaces the map merge-walk (:691-789)
+__global__ void tri_match_kernel(TriParams P, const int* __restrict__ entryNode, int* __restrict__ m12, int* hist) {
+    const int p1 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p1 >= P.nEntries1) return;
+    const int node = P.nodeId1[entryNode[p1]];
+    int lo = 0, hi = P.nNodes2 - 1, b = -1;
+    while (lo <= hi) {
+        const int mid = (lo + hi) >> 1, v = P.nodeId2[mid];
+        if (v == node) { b = mid; break; }
+        if (v < node) lo = mid + 1; else hi = mid - 1;
+    }
+    if (b < 0) return;
+    const int idx1 = P.idx1[p1];
+    if (P.has1[idx1]) return;
+    const bool stereo1 = P.uR1 ? (P.uR1[idx1] >= 0) : false;
+    if (P.onlyStereo && !stereo1) return;
+    const orb_keypoint kp1 = P.k1.keys[idx1];
+    const uint4 da = P.k1.desc[2 * idx1], db = P.k1.desc[2 * idx1 + 1];
+    int best = kThLow, bestIdx = -1;
+    for (int p2 = P.start2[b]; p2 < P.start2[b + 1]; ++p2) {
+        const int idx2 = P.idx2[p2];
+        if (P.has2[idx2]) continue;
+        const bool stereo2 = P.uR2 ? (P.uR2[idx2] >= 0) : false;
+        if (P.onlyStereo && !stereo2) continue;
+        const int dist = hamming256(da, db, P.k2.desc[2 * idx2], P.k2.desc[2 * idx2 + 1]);
+        if (dist > kThLow || dist > best) continue;                    // :738 (ties replace)
+        const orb_keypoint kp2 = P.k2.keys[idx2];
+        if (!stereo1 && !stereo2) {
+            const float dex = __fsub_rn(P.ex, kp2.x), dey = __fsub_rn(P.ey, kp2.y);
+            if (__fadd_rn(__fmul_rn(dex, dex), __fmul_rn(dey, dey)) < __fmul_rn(100.f, P.sf2[kp2.octave])) continue;   // :747
+        }
+        if (epipolar_ok(kp1, kp2, P.F, P.sigma2)) { bestIdx = idx2; best = dist; }
+    }
+    if (bestIdx >= 0) {
+        m12[idx1] = bestIdx;
+        if (P.checkOri) atomicAdd(&hist[rotation_bin(kp1.angle, P.k2.keys[bestIdx].angle)], 1);
+    }
+}
+
+__global__ void tri_entry_node_kernel(int nNodes, const int* start, int* entryNode) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= nNodes) return;
+    for (int p = start[a]; p < start[a + 1]; ++p) entryNode[p] = a;
+}
+
+__global__ void __launch_bounds__(256) tri_finish_kernel(FrameDev k1, FrameDev k2, int checkOri, int* m12, int* hist, int* nmatchesOut) {
+    __shared__ int keep[3];
+    __shared__ int total;
+    if (threadIdx.x == 0) {
+        total = 0;
+        if (checkOri) three_maxima(hist, keep[0], keep[1], keep[2]);
+    }
+    __syncthreads();
+    int mine = 0;
+    for (int i = threadIdx.x; i < k1.n; i += blockDim.x) {
+        const int m = m12[i];
+        if (m < 0) continue;
+        if (checkOri) {
+            const int bin = rotation_bin(k1.keys[i].angle, k2.keys[m].angle);
+            if (bin != keep[0] && bin != keep[1] && bin != keep[2]) { m12[i] = -1; continue; }
+        }
+        ++mine;
+    }
+    atomicAdd(&total, mine);
+    __syncthreads();
+    if (threadIdx.x == 0) *nmatchesOut = total;
+}
+
+__global__ void fill_int_kernel(int* p, int n, int v) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+}  // namespace orbb
+
+// =================================================================================================== host side
+using namespace orbb;
+
+struct orbm_frame_s {
+    orbm_matcher* m = nullptr;
+    int n = 0;
+    DevBuf keys, desc, cellStart, cellIdx;
+    float minX = 0, minY = 0, maxX = 0, maxY = 0, invW = 0, invH = 0;
+    FrameDev dev() const {
+        FrameDev f;
+        f.n = n; f.keys = keys.as<orb_keypoint>(); f.desc = desc.as<uint4>();
+        f.cellStart = cellStart.as<int>(); f.cellIdx = cellIdx.as<int>();
+        f.minX = minX; f.minY = minY; f.maxX = maxX; f.maxY = maxY; f.invW = invW; f.invH = invH;
+        return f;
+    }
+};
+
+#define ORBM_ENTER(h)                                                                                     \
+    if (!(h)) return fail(ORB_ERR_INVALID, "%s: null matcher handle", __func__);                          \
+    DeviceGuard guard__((h)->device);                                                                     \
+    if (!guard__.ok) return fail(ORB_ERR_CUDA, "%s: cannot select device %d", __func__, (h)->device);     \
+    (h)->launches = 0;
+
+namespace {
+
+// phase 1 for nq queries already built in h->ws0 (AreaQuery[nq]); leaves offsets in ws1 and candidates in ws2
+int run_candidates(orbm_matcher* h, const FrameDev& f, const uint4* dQdesc, int nq, const float* dURight, int* totalOut) {
+    cudaStream_t st = h->stream;
+    ORB_CHECK(h->out4.reserve((size_t)(nq + 1) * 4));
+    ORB_CHECK(h->ws1.reserve((size_t)(nq + 2) * 4));
+    int* counts = h->out4.as<int>();
+    int* offsets = h->ws1.as<int>();
+    const int wpb = 8, blocks = ceil_div(nq, wpb);
+    candidates_kernel<<<blocks, wpb * 32, 0, st>>>(f, h->ws0.as<AreaQuery>(), dQdesc, nq, dURight, counts, nullptr, nullptr);
+    scan_kernel<<<1, 1024, 0, st>>>(counts, offsets, nq);
+    int total = 0;
+    ORB_CUDA(cudaMemcpyAsync(&total, offsets + nq, 4, cudaMemcpyDeviceToHost, st));
+    ORB_CUDA(cudaStreamSynchronize(st));
+    ORB_CHECK(h->ws2.reserve((size_t)(total + 1) * sizeof(int2)));
+    candidates_kernel<<<blocks, wpb * 32, 0, st>>>(f, h->ws0.as<AreaQuery>(), dQdesc, nq, dURight, nullptr, offsets, h->ws2.as<int2>());
+    h->launches += 3;
+    ORB_CUDA(cudaGetLastError());
+    *totalOut = total;
+    return ORB_OK;
+}
+
+int upload(DevBuf& b, const void* src, size_t bytes, cudaStream_t st) {
+    ORB_CHECK(b.reserve(bytes + 16));
+    if (bytes) ORB_CUDA(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, st));
+    return ORB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int orbm_frame_create(orbm_handle h, const orb_keypoint* keys, const uint8_t* desc, int n, float minX, float minY,
+                      float maxX, float maxY, orbm_frame* out) {
+    ORBM_ENTER(h);
+    if (!out) return fail(ORB_ERR_INVALID, "orbm_frame_create: null out");
+    *out = nullptr;
+    if (n < 0 || (n > 0 && (!keys || !desc)) || !(maxX > minX) || !(maxY > minY))
+        return fail(ORB_ERR_INVALID, "orbm_frame_create: bad arguments");
+    if (n > kOrdMask) return fail(ORB_ERR_INVALID, "orbm_frame_create: more than %d keypoints", kOrdMask);
+    orbm_frame_s* f = new orbm_frame_s;
+    f->m = h;
+    f->n = n;
+    f->minX = minX; f->minY = minY; f->maxX = maxX; f->maxY = maxY;
+    f->invW = (float)kGridCols / (maxX - minX);   // Frame.cc:93-94
+    f->invH = (float)kGridRows / (maxY - minY);
+    cudaStream_t st = h->stream;
+    int status = ORB_OK;
+    auto body = [&]() -> int {
+        ORB_CHECK(upload(f->keys, keys, (size_t)n * sizeof(orb_keypoint), st));
+        ORB_CHECK(upload(f->desc, desc, (size_t)n * 32, st));
+        ORB_CHECK(f->cellStart.reserve((kCells + 1) * 4));
+        ORB_CHECK(f->cellIdx.reserve((size_t)(n + 1) * 4));
+        ORB_CHECK(h->ws0.reserve((size_t)(n + 1) * 4));            // cellOf
+        ORB_CHECK(h->ws1.reserve((size_t)(kCells + 1) * 4 * 2));   // counts, cursor
+        int* counts = h->ws1.as<int>();
+        int* cursor = counts + kCells + 1;
+        ORB_CUDA(cudaMemsetAsync(counts, 0, (size_t)(kCells + 1) * 4 * 2, st));
+        const FrameDev fd = f->dev();
+        if (n > 0) grid_count_kernel<<<ceil_div(n, 256), 256, 0, st>>>(fd, h->ws0.as<int>(), counts);
+        scan_kernel<<<1, 1024, 0, st>>>(counts, f->cellStart.as<int>(), kCells);
+        if (n > 0) grid_fill_kernel<<<ceil_div(n, 256), 256, 0, st>>>(n, h->ws0.as<int>(), f->cellStart.as<int>(), cursor, f->cellIdx.as<int>());
+        grid_sort_kernel<<<ceil_div(kCells, 256), 256, 0, st>>>(f->cellStart.as<int>(), f->cellIdx.as<int>());
+        h->launches += 4;
+        ORB_CUDA(cudaGetLastError());
+        ORB_CUDA(cudaStreamSynchronize(st));
+        return ORB_OK;
+    };
+    status = body();
+    if (status != ORB_OK) {
+        orbm_frame_destroy(f);
+        return status;
+    }
+    *out = f;
+    return ORB_OK;
+}
+
+int orbm_frame_destroy(orbm_frame f) {
+    if (!f) return ORB_OK;
+    DeviceGuard g(f->m->device);
+    f->keys.release(); f->desc.release(); f->cellStart.release(); f->cellIdx.release();
+    delete f;
+    return ORB_OK;
+}
+
+int orbm_frame_grid(orbm_frame f, int* cellStart, int* cellIdx) {
+    if (!f || !cellStart || !cellIdx) return fail(ORB_ERR_INVALID, "orbm_frame_grid: null argument");
+    DeviceGuard g(f->m->device);
+    ORB_CUDA(cudaMemcpy(cellStart, f->cellStart.p, (kCells + 1) * 4, cudaMemcpyDeviceToHost));
+    const int total = cellStart[kCells];
+    if (total > 0) ORB_CUDA(cudaMemcpy(cellIdx, f->cellIdx.p, (size_t)total * 4, cudaMemcpyDeviceToHost));
+    return ORB_OK;
+}
+
+int orbm_features_in_area(orbm_frame f, const float* xyr, int nq, int minLevel, int maxLevel, int* idxOut, int cap, int* countOut) {
+    if (!f) return fail(ORB_ERR_INVALID, "orbm_features_in_area: null frame");
+    orbm_matcher* h = f->m;
+    ORBM_ENTER(h);
+    if (nq < 0 || cap < 1 || (nq > 0 && (!xyr || !idxOut || !countOut))) return fail(ORB_ERR_INVALID, "orbm_features_in_area: bad arguments");
+    if (nq == 0) return ORB_OK;
+    cudaStream_t st = h->stream;
+    ORB_CHECK(upload(h->in0, xyr, (size_t)nq * 12, st));
+    ORB_CHECK(h->out0.reserve((size_t)nq * cap * 4));
+    ORB_CHECK(h->out1.reserve((size_t)nq * 4));
+    area_kernel<<<ceil_div(nq, 8), 256, 0, st>>>(f->dev(), h->in0.as<float>(), nq, minLevel, maxLevel, h->out0.as<int>(), cap, h->out1.as<int>());
+    h->launches += 1;
+    ORB_CUDA(cudaGetLastError());
+    ORB_CUDA(cudaMemcpyAsync(idxOut, h->out0.p, (size_t)nq * cap * 4, cudaMemcpyDeviceToHost, st));
+    ORB_CUDA(cudaMemcpyAsync(countOut, h->out1.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
+    ORB_CUDA(cudaStreamSynchronize(st));
+    return ORB_OK;
+}
+
+int orbm_search_for_initialization(orbm_handle h, orbm_frame f1, orbm_frame f2, float* prevXY, int* matches12,
+                                   int windowSize, float ratio, int checkOri, int* nmatches) {
+    ORBM_ENTER(h);
+    if (!f1 || !f2 || !prevXY || !matches12 || !nmatches) return fail(ORB_ERR_INVALID, "orbm_search_for_initialization: null argument");
+    *nmatches = 0;
+    const int n1 = f1->n, n2 = f2->n;
+    if (n1 == 0) return ORB_OK;
+    cudaStream_t st = h->stream;
+    ORB_CHECK(upload(h->in0, prevXY, (size_t)n1 * 8, st));
+    ORB_CHECK(h->ws0.reserve((size_t)n1 * sizeof(AreaQuery)));
+    const FrameDev d1 = f1->dev(), d2 = f2->dev();
+    init_queries_kernel<<<ceil_div(n1, 256), 256, 0, st>>>(d1, h->in0.as<float>(), windowSize, h->ws0.as<AreaQuery>());
+    h->launches += 1;
+    int total = 0;
+    ORB_CHECK(run_candidates(h, d2, d1.desc, n1, nullptr, &total));
+    ORB_CHECK(h->out0.reserve((size_t)(n1 + 1) * 4));          // m12
+    ORB_CHECK(h->out1.reserve((size_t)(n2 + 1) * 4 * 2));      // m21, matchedDist
+    ORB_CHECK(h->out2.reserve((size_t)(n1 + 1) * 4 * 2));      // pushBin, pushVal
+    ORB_CHECK(h->out3.reserve(16));
+    int* m21 = h->out1.as<int>();
+    int* pushBin = h->out2.as<int>();
+    init_replay_kernel<<<1, 32, 0, st>>>(d1, d2, h->ws0.as<AreaQuery>(), h->ws1.as<int>(), h->ws2.as<int2>(), ratio, checkOri,
+                                         h->in0.as<float>(), h->out0.as<int>(), m21, m21 + n2 + 1, pushBin, pushBin + n1 + 1,
+                                         h->out3.as<int>());
+    h->launches += 1;
+    ORB_CUDA(cudaGetLastError());
+    ORB_CUDA(cudaMemcpyAsync(matches12, h->out0.p, (size_t)n1 * 4, cudaMemcpyDeviceToHost, st));
+    ORB_CUDA(cudaMemcpyAsync(prevXY, h->in0.p, (size_t)n1 * 8, cudaMemcpyDeviceToHost, st));
+    ORB_CUDA(cudaMemcpyAsync(nmatches, h->out3.p, 4, cudaMemcpyDeviceToHost, st));
+    ORB_CUDA(cudaStreamSynchronize(st));
+    return ORB_OK;
+}
+
+int orbm_search_by_projection(orbm_handle h, orbm_frame cur, const float* sf, int nlevels, const float* uRight, float mbf,
+                              const orbm_proj_query* queries, const uint8_t* qdesc, int nq, float th, int mode,
+                              const uint8_t* occupied, int* curMatch, int checkOri, int* nmatches) {
+    ORBM_ENTER(h);
+    if (!cur || !sf || nlevels < 1 || !curMatch || !nmatches || nq < 0 || (nq > 0 && (!queries || !qdesc)))
+        return fail(ORB_ERR_INVALID, "orbm_search_by_projection: bad arguments");
+    for (int i = 0; i < nq; ++i)
+        if (queries[i].valid && (queries[i].octave < 0 || queries[i].octave >= nlevels))
+            return fail(ORB_ERR_INVALID, "orbm_search_by_projection: query %d has octave %d outside 0..%d", i, queries[i].octave, nlevels - 1);
+    *nmatches = 0;
+    const int n = cur->n;
+    for (int i = 0; i < n; ++i) curMatch[i] = -1;
+    if (nq == 0 || n == 0) return ORB_OK;
+    cudaStream_t st = h->stream;
+    ORB_CHECK(upload(h->in0, queries, (size_t)nq * sizeof(orbm_proj_query), st));
+    ORB_CHECK(upload(h->in1, qdesc, (size_t)nq * 32, st));
+    ORB_CHECK(upload(h->in2, sf, (size_t)nlevels * 4, st));
+    if (uRight) ORB_CHECK(upload(h->in3, uRight, (size_t)n * 4, st));
+    ORB_CHECK(h->in4.reserve((size_t)n + 16));
+    if (occupied) ORB_CUDA(cudaMemcpyAsync(h->in4.p, occupied, (size_t)n, cudaMemcpyHostToDevice, st));
+    else ORB_CUDA(cudaMemsetAsync(h->in4.p, 0, (size_t)n, st));
+    ORB_CHECK(h->ws0.reserve((size_t)nq * sizeof(AreaQuery)));
+    const FrameDev d = cur->dev();
+    proj_queries_kernel<<<ceil_div(nq, 256), 256, 0, st>>>(d, h->in0.as<orbm_proj_query>(), nq, h->in2.as<float>(), th, mode, mbf,
+                                                           h->ws0.as<AreaQuery>());
+    h->launches += 1;
+    int total = 0;
+    ORB_CHECK(run_candidates(h, d, h->in1.as<uint4>(), nq, uRight ? h->in3.as<float>() : nullptr, &total));
+    ORB_CHECK(h->out0.reserve((size_t)(n + 1) * 4));
+    ORB_CHECK(h->out2.reserve((size_t)(nq + 1) * 4 * 2));
+    ORB_CHECK(h->out3.reserve(16));
+    int* pushBin = h->out2.as<int>();
+    proj_replay_kernel<<<1, 32, 0, st>>>(d, h->ws0.as<AreaQuery>(), h->in0.as<orbm_proj_query>(), nq, h->ws1.as<int>(),
+                                         h->ws2.as<int2>(), checkOri, h->in4.as<unsigned char>(), h->out0.as<int>(), pushBin,
+                                         pushBin + nq + 1, h->out3.as<int>());
+    h->launches += 1;
+    ORB_CUDA(cudaGetLastError());
+    ORB_CUDA(cudaMemcpyAsync(curMatch, h->out0.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    ORB_CUDA(cudaMemcpyAsync(nmatches, h->out3.p, 4, cudaMemcpyDeviceToHost, st));
+    ORB_CUDA(cudaStreamSynchronize(st));
+    return ORB_OK;
+}
+
+int orbm_search_by_projection_points(orbm_handle h, orbm_frame f, const float* sf, int nlevels, const float* uRight,
+                                     const orbm_point_query* queries, const uint8_t* qdesc, int nq, float th, float ratio,
+                                     const uint8_t* occupied, int* match, int* nmatches) {
+    ORBM_ENTER(h);
+    if (!f || !sf || nlevels < 1 || !match || !nmatches || nq < 0 || (nq > 0 && (!queries || !qdesc)))
+        return fail(ORB_ERR_INVALID, "orbm_search_by_projection_points: bad arguments");
+    for (int i = 0; i < nq; ++i)
+        if (queries[i].in_view && (queries[i].level < 0 || queries[i].level >= nlevels))
+            return fail(ORB_ERR_INVALID, "orbm_search_by_projection_points: query %d has level %d outside 0..%d", i, queries[i].level, nlevels - 1);
+    *nmatches = 0;
+    const int n = f->n;
+    for (int i = 0; i < n; ++i) match[i] = -1;
+    if (nq == 0 || n == 0) return ORB_OK;
+    cudaStream_t st = h->stream;
+    ORB_CHECK(upload(h->in0, queries, (size_t)nq * sizeof(orbm_point_query), st));
+    ORB_CHECK(upload(h->in1, qdesc, (size_t)nq * 32, st));
+    ORB_CHECK(upload(h->in2, sf, (size_t)nlevels * 4, st));
+    if (uRight) ORB_CHECK(upload(h->in3, uRight, (size_t)n * 4, st));
+    ORB_CHECK(h->in4.reserve((size_t)n + 16));
+    if (occupied) ORB_CUDA(cudaMemcpyAsync(h->in4.p, occupied, (size_t)n, cudaMemcpyHostToDevice, st));
+    else ORB_CUDA(cudaMemsetAsync(h->in4.p, 0, (size_t)n, st));
+    ORB_CHECK(h->ws0.reserve((size_t)nq * sizeof(AreaQuery)));
+    const FrameDev d = f->dev();
+    point_queries_kernel<<<ceil_div(nq, 256), 256, 0, st>>>(h->in0.as<orbm_point_query>(), nq, h->in2.as<float>(), th, h->ws0.as<AreaQuery>());
+    h->launches += 1;
+    int total = 0;
+    ORB_CHECK(run_candidates(h, d, h->in1.as<uint4>(), nq, uRight ? h->in3.as<float>() : nullptr, &total));
+    ORB_CHECK(h->out0.reserve((size_t)(n + 1) * 4));
+    ORB_CHECK(h->out3.reserve(16));
+    point_replay_kernel<<<1, 32, 0, st>>>(d, h->ws0.as<AreaQuery>(), h->in0.as<orbm_point_query>(), nq, h->ws1.as<int>(),
+                                          h->ws2.as<int2>(), ratio, h->in4.as<unsigned char>(), h->out0.as<int>(), h->out3.as<int>());
+    h->launches += 1;
+    ORB_CUDA(cudaGetLastError());
+    ORB_CUDA(cudaMemcpyAsync(match, h->out0.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    ORB_CUDA(cudaMemcpyAsync(nmatches, h->out3.p, 4, cudaMemcpyDeviceToHost, st));
+    ORB_CUDA(cudaStreamSynchronize(st));
+    return ORB_OK;
+}
+
+int orbm_search_for_triangulation(orbm_handle h, orbm_frame k1, orbm_frame k2, int nNodes1, const int* nodeId1,
+                                  const int* start1, const int* idx1, int nNodes2, const int* nodeId2, const int* start2,
+                                  const int* idx2, const uint8_t* has1, const uint8_t* has2, const float* uR1, const float* uR2,
+                                  const float* f12, float ex, float ey, const float* sf2, const float* sigma2, int nlevels,
+                                  int onlyStereo, int checkOri, int* matches12, int* nmatches) {
+    ORBM_ENTER(h);
+    if (!k1 || !k2 || !f12 || !sf2 || !sigma2 || !matches12 || !nmatches || nNodes1 < 0 || nNodes2 < 0 || nlevels < 1 ||
+        (nNodes1 > 0 && (!nodeId1 || !start1 || !idx1)) || (nNodes2 > 0 && (!nodeId2 || !start2 || !idx2)) || !has1 || !has2)
+        return fail(ORB_ERR_INVALID, "orbm_search_for_triangulation: bad arguments");
+    *nmatches = 0;
+    const int n1 = k1->n, n2 = k2->n;
+    for (int i = 0; i < n1; ++i) matches12[i] = -1;
+    if (nNodes1 == 0 || nNodes2 == 0 || n1 == 0 || n2 == 0) return ORB_OK;
+    const int e1 = start1[nNodes1], e2 = start2[nNodes2];
+    for (int a = 1; a < nNodes1; ++a)
+        if (nodeId1[a] <= nodeId1[a - 1]) return fail(ORB_ERR_INVALID, "orbm_search_for_triangulation: node ids of KF1 not ascending");
+    for (int a = 1; a < nNodes2; ++a)
+        if (nodeId2[a] <= nodeId2[a - 1]) return fail(ORB_ERR_INVALID, "orbm_search_for_triangulation: node ids of KF2 not ascending");
+    cudaStream_t st = h->stream;
+    // one staging buffer: ints first, then floats, then bytes
+    std::vector<int> ints;
+    auto putInts = [&](const int* p, int n) { size_t o = ints.size(); ints.insert(ints.end(), p, p + n); return o; };
+    const size_t oId1 = putInts(nodeId1, nNodes1), oS1 = putInts(start1, nNodes1 + 1), oI1 = putInts(idx1, e1);
+    const size_t oId2 = putInts(nodeId2, nNodes2), oS2 = putInts(start2, nNodes2 + 1), oI2 = putInts(idx2, e2);
+    ORB_CHECK(upload(h->in0, ints.data(), ints.size() * 4, st));
+    std::vector<float> fl;
+    fl.insert(fl.end(), sf2, sf2 + nlevels);
+    fl.insert(fl.end(), sigma2, sigma2 + nlevels);
+    const size_t oU1 = fl.size();
+    if (uR1) fl.insert(fl.end(), uR1, uR1 + n1);
+    const size_t oU2 = fl.size();
+    if (uR2) fl.insert(fl.end(), uR2, uR2 + n2);
+    ORB_CHECK(upload(h->in1, fl.data(), fl.size() * 4, st));
+    ORB_CHECK(upload(h->in2, has1, (size_t)n1, st));
+    ORB_CHECK(upload(h->in3, has2, (size_t)n2, st));
+    ORB_CHECK(h->ws0.reserve((size_t)(e1 + 1) * 4));              // entryNode
+    ORB_CHECK(h->out0.reserve((size_t)(n1 + 1) * 4));             // m12
+    ORB_CHECK(h->out1.reserve((kHistoLength + 2) * 4));           // hist, nmatches
+    TriParams P;
+    P.k1 = k1->dev(); P.k2 = k2->dev();
+    P.nNodes1 = nNodes1; P.nNodes2 = nNodes2; P.nEntries1 = e1;
+    const int* di = h->in0.as<int>();
+    P.nodeId1 = di + oId1; P.start1 = di + oS1; P.idx1 = di + oI1;
+    P.nodeId2 = di + oId2; P.start2 = di + oS2; P.idx2 = di + oI2;
+    P.has1 = h->in2.as<unsigned char>(); P.has2 = h->in3.as<unsigned char>();
+    const float* df = h->in1.as<float>();
+    P.sf2 = df; P.sigma2 = df + nlevels;
+    P.uR1 = uR1 ? df + oU1 : nullptr; P.uR2 = uR2 ? df + oU2 : nullptr;
+    for (int i = 0; i < 9; ++i) P.F[i] = f12[i];
+    P.ex = ex; P.ey = ey; P.onlyStereo = onlyStereo; P.checkOri = checkOri;
+    int* hist = h->out1.as<int>();
+    ORB_CUDA(cudaMemsetAsync(hist, 0, (kHistoLength + 2) * 4, st));
+    fill_int_kernel<<<ceil_div(n1, 256), 256, 0, st>>>(h->out0.as<int>(), n1, -1);
+    tri_entry_node_kernel<<<ceil_div(nNodes1, 128), 128, 0, st>>>(nNodes1, P.start1, h->ws0.as<int>());
+    if (e1 > 0) tri_match_kernel<<<ceil_div(e1, 128), 128, 0, st>>>(P, h->ws0.as<int>(), h->out0.as<int>(), hist);
+    tri_finish_kernel<<<1, 256, 0, st>>>(P.k1, P.k2, checkOri, h->out0.as<int>(), hist, hist + kHistoLength);
+    h->launches += 4;
+    ORB_CUDA(cudaGetLastError());
+    ORB_CUDA(cudaMemcpyAsync(matches12, h->out0.p, (size_t)n1 * 4, cudaMemcpyDeviceToHost, st));
+    ORB_CUDA(cudaMemcpyAsync(nmatches, hist + kHistoLength, 4, cudaMemcpyDeviceToHost, st));
+    ORB_CUDA(cudaStreamSynchronize(st));
+    return ORB_OK;
+}
+
+}  // extern "C"

@@ -169,6 +169,16 @@ class Extractor:
         _check(self.L.orbx_last_launch_count(self.h, C.byref(n)))
         return n.value
 
+    def set_profiling(self, on):
+        _check(self.L.orbx_set_profiling(self.h, int(on)))
+
+    def kernel_times(self):
+        """(ms summed per kernel group [pyramid, fast, quadtree, blur, brief], number of calls) since last query"""
+        ms = np.zeros(5, np.float64)
+        n = C.c_int()
+        _check(self.L.orbx_kernel_times(self.h, _p(ms), C.byref(n)))
+        return ms, n.value
+
 
 class Frame:
     """Device-resident Frame/KeyFrame arrays + the 64x48 grid (Frame.cc:574-589)."""

@@ -22,6 +22,8 @@ SIGNATURES = {
     "orbx_debug_candidates": (i32, [vp, i32, i32, vp, i32, vp]),
     "orbx_debug_blurred": (i32, [vp, i32, i32, vp]),
     "orbx_last_launch_count": (i32, [vp, vp]),
+    "orbx_set_profiling": (i32, [vp, i32]),
+    "orbx_kernel_times": (i32, [vp, vp, vp]),
     # matcher
     "orbm_create": (i32, [i32, vp]),
     "orbm_destroy": (i32, [vp]),
