@@ -1,0 +1,97 @@
+"""The oracle's OpenCV primitive models against the installed OpenCV (cv2 4.13.0), bit for bit.
+These models carry all the arithmetic the reference delegates to OpenCV, so this is what pins them."""
+import numpy as np
+import pytest
+
+from orbb200.synth import synth_frame
+
+cv2 = pytest.importorskip("cv2")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _single_thread():
+    cv2.setNumThreads(1)
+
+
+@pytest.mark.parametrize("w,h", [(752, 480), (1241, 376), (640, 480), (333, 251)])
+def test_resize_chain(oracle, w, h):
+    cur = synth_frame(1, w, h)
+    for l in range(1, 8):
+        dw, dh = int(round(w / 1.2 ** l)), int(round(h / 1.2 ** l))
+        ref = cv2.resize(cur, (dw, dh), interpolation=cv2.INTER_LINEAR)
+        assert np.array_equal(oracle.resize(cur, dw, dh), ref), (w, h, l)
+        cur = ref
+
+
+def test_resize_adversarial(oracle):
+    rng = np.random.default_rng(0)
+    for _ in range(40):
+        sw, sh = rng.integers(8, 200, 2)
+        dw, dh = max(2, int(sw / rng.uniform(1.0, 1.5))), max(2, int(sh / rng.uniform(1.0, 1.5)))
+        img = rng.choice([0, 1, 127, 128, 254, 255], (sh, sw)).astype(np.uint8)
+        assert np.array_equal(oracle.resize(img, dw, dh), cv2.resize(img, (dw, dh), interpolation=cv2.INTER_LINEAR))
+
+
+def test_border_and_blur(oracle):
+    for seed, (w, h) in enumerate([(752, 480), (210, 134), (62, 62), (9, 8)]):
+        img = synth_frame(seed, max(w, 64), max(h, 64))[:h, :w].copy()
+        if min(w, h) > 19:
+            assert np.array_equal(oracle.border(img), cv2.copyMakeBorder(img, 19, 19, 19, 19, cv2.BORDER_REFLECT_101))
+        assert np.array_equal(oracle.blur(img), cv2.GaussianBlur(img, (7, 7), 2, 2, borderType=cv2.BORDER_REFLECT_101))
+    rng = np.random.default_rng(1)
+    ext = rng.choice([0, 255], (90, 120)).astype(np.uint8)   # saturating pattern: rounding of the single >>16
+    assert np.array_equal(oracle.blur(ext), cv2.GaussianBlur(ext, (7, 7), 2, 2, borderType=cv2.BORDER_REFLECT_101))
+
+
+def _cv_fast(img, th):
+    det = cv2.FastFeatureDetector_create(th, True, cv2.FAST_FEATURE_DETECTOR_TYPE_9_16)
+    kp = det.detect(img, None)
+    return np.array([(k.pt[0], k.pt[1], k.response, k.size, k.angle, k.octave, k.class_id) for k in kp]).reshape(-1, 7)
+
+
+def _oracle_fast(oracle, img, th):
+    k = oracle.fast(img, th)
+    return np.stack([k["x"], k["y"], k["response"], k["size"], k["angle"], k["octave"], k["class_id"]], 1).astype(np.float64)
+
+
+@pytest.mark.parametrize("th", [20, 7, 1, 100])
+def test_fast_full_image(oracle, th):
+    for seed, noise in ((0, False), (3, True)):
+        img = synth_frame(seed, 400, 300, noise_only=noise)
+        a, b = _cv_fast(img, th), _oracle_fast(oracle, img, th)
+        assert a.shape == b.shape and np.array_equal(a, b)   # same set, same order, same responses
+
+
+def test_fast_cell_rois(oracle):
+    """What the extractor really calls: FAST on ~36x36 views of a larger image, some thinner than 7 px."""
+    img = synth_frame(0)
+    rng = np.random.default_rng(0)
+    for _ in range(300):
+        x, y = rng.integers(0, 700), rng.integers(0, 440)
+        w, h = rng.integers(7, 40), rng.integers(1, 40)
+        roi = img[y:y + h, x:x + w]
+        for th in (20, 7):
+            a, b = _cv_fast(roi, th), _oracle_fast(oracle, roi, th)
+            assert a.shape == b.shape and np.array_equal(a, b)
+
+
+def test_fast_equal_neighbours_suppress_each_other(oracle):
+    """Two adjacent pixels with equal maximal score: strict '>' drops both, so a cell can be empty at threshold 20 and
+    trigger the 7 fallback (ORBextractor.cc:811-818)."""
+    img = np.full((24, 24), 50, np.uint8)
+    img[10:13, 10:14] = 200                      # a 4x3 bright blob: symmetric corners with equal scores
+    for th in (20, 7):
+        a, b = _cv_fast(img, th), _oracle_fast(oracle, img, th)
+        assert a.shape == b.shape and np.array_equal(a, b)
+
+
+def test_fast_atan2(oracle):
+    rng = np.random.default_rng(0)
+    y = rng.normal(0, 1000, 20000).astype(np.float32)
+    x = rng.normal(0, 1000, 20000).astype(np.float32)
+    y[:10] = 0; x[5:15] = 0; y[20:30] = x[20:30]; y[30:40] = -x[30:40]
+    y[40:1000] = np.rint(y[40:1000]); x[40:1000] = np.rint(x[40:1000])     # integer moments, as IC_Angle produces
+    ref = np.array([cv2.fastAtan2(float(a), float(b)) for a, b in zip(y, x)], np.float32)
+    got = oracle.atan2(y, x)
+    assert np.array_equal(ref.view(np.uint32), got.view(np.uint32))
+    assert oracle.atan2(np.zeros(1, np.float32), np.zeros(1, np.float32))[0] == 0.0

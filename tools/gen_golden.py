@@ -1,0 +1,99 @@
+#!/usr/bin/env python3
+"""Generates tests/golden/*.npz (run in the build container, where /root/reference is mounted).
+
+Extractor vectors come from oracle/_ref/orb_ref = the reference's OWN src/ORBextractor.cc compiled in place against the
+OpenCV stand-in (oracle/ref_shim), i.e. they are outputs of the reference itself, not of our restatement.
+ORBmatcher.cc cannot be compiled here (it needs Frame.h -> Eigen/DBoW2/g2o), so the matcher vectors are produced by
+oracle/match_oracle.cpp and are marked `pinned_by: oracle` -- parity for the matcher is unpinned.
+"""
+import hashlib
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "vi-orb-slam-icra2018_b200"))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from orbb200.synth import synth_frame, shifted_pair  # noqa: E402
+from oracle_py import Oracle  # noqa: E402
+import ref_runner  # noqa: E402
+from datagen import planted_descriptors  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    assert ref_runner.ref_binary("orb_ref"), "build oracle/_ref first (make -C oracle/ref_shim)"
+    # ---- extractor: reference outputs
+    cases = [("euroc_s0", 0, 752, 480, 1000, False), ("small_s5", 5, 400, 300, 1500, False),
+             ("qvga_noise", 9, 320, 240, 500, True), ("kitti_s2", 2, 1241, 376, 2000, False)]
+    for name, seed, w, h, nf, noise in cases:
+        img = synth_frame(seed, w, h, noise_only=noise)
+        r = ref_runner.ref_extract([img], nfeatures=nf, dump_levels=True)[0]
+        small = w * h <= 400 * 300
+        np.savez_compressed(os.path.join(OUT, "extract_%s.npz" % name),
+                            seed=seed, w=w, h=h, nfeatures=nf, noise=noise, image_sha256=sha(img),
+                            image=img if small else np.zeros(0, np.uint8),
+                            kps=r["kps"], desc=r["desc"],
+                            level_sha256=np.array([sha(l) for l in r["levels"]]),
+                            level_shapes=np.array([l.shape for l in r["levels"]]), pinned_by="reference (oracle/_ref)")
+        print(name, len(r["kps"]))
+    # ---- quadtree KATs: reference DistributeOctTree on hand-made key sets
+    o = Oracle()
+    rng = np.random.default_rng(4)
+    kats = {}
+
+    def keys(xy, resp):
+        k = np.zeros(len(xy), ref_runner.KP_DTYPE)
+        k["x"], k["y"], k["response"] = xy[:, 0], xy[:, 1], resp
+        k["size"], k["angle"], k["class_id"] = 7, -1, -1
+        return k
+
+    W, H = 720, 448
+    kats["ties"] = (keys(np.stack([np.repeat(np.arange(8) * 90 + 3, 8) + np.tile(np.arange(8), 8) * 2.0,
+                                   np.tile(np.arange(8) * 50 + 3.0, 8)], 1), np.full(64, 30.0)), 40)
+    kats["equal_response"] = (keys(rng.integers(3, [W - 3, H - 3], (3000, 2)).astype(np.float64), np.full(3000, 25.0)), 217)
+    kats["stop_mid_round"] = (keys(rng.integers(3, [W - 3, H - 3], (5000, 2)).astype(np.float64), rng.integers(7, 120, 5000)), 217)
+    kats["single_key_roots"] = (keys(np.array([[10.0, 10.0], [600.0, 300.0]]), [20, 40]), 100)
+    kats["one_root_empty"] = (keys(np.stack([rng.integers(3, 300, 500), rng.integers(3, H - 3, 500)], 1).astype(np.float64),
+                                   rng.integers(7, 200, 500)), 60)
+    kats["fewer_keys_than_n"] = (keys(rng.integers(3, [W - 3, H - 3], (90, 2)).astype(np.float64), rng.integers(7, 90, 90)), 217)
+    kats["clustered"] = (keys(np.clip(rng.normal([360, 224], [25, 18], (4000, 2)), 3, [W - 4, H - 4]).round(),
+                              rng.integers(7, 250, 4000)), 151)
+    kats["n_zero"] = (keys(rng.integers(3, [W - 3, H - 3], (300, 2)).astype(np.float64), rng.integers(7, 90, 300)), 0)
+    save = {}
+    for name, (k, n) in kats.items():
+        out = ref_runner.ref_distribute(k, 16, 16 + W, 16, 16 + H, n)
+        assert out.tobytes() == o.distribute(k, 16, 16 + W, 16, 16 + H, n).tobytes(), name
+        save[name + "_in"], save[name + "_out"], save[name + "_n"] = k, out, n
+        print("octree", name, len(k), "->", len(out))
+    np.savez_compressed(os.path.join(OUT, "octree_kats.npz"), win=np.array([16, 16 + W, 16, 16 + H]),
+                        pinned_by="reference (oracle/_ref)", **save)
+    # ---- matcher vectors (oracle-generated)
+    a, b = shifted_pair(3, 400, 300)
+    oe = o.extractor(800)
+    ka, da = oe.extract(a)
+    kb, db = oe.extract(b)
+    bounds = (0.0, 0.0, 400.0, 300.0)
+    f1, f2 = o.frame(ka, da, bounds), o.frame(kb, db, bounds)
+    prev = np.stack([ka["x"], ka["y"]], 1).astype(np.float32)
+    n, m12, p = f1.search_init(f2, prev, 100, 0.9, True)
+    q, qa, t, ta = planted_descriptors(np.random.default_rng(1), 300, 280)
+    bn, best, second, idx, bm12 = o.bruteforce(q, qa, t, ta, 0.9, True)
+    gs, gi = f2.grid()
+    np.savez_compressed(os.path.join(OUT, "matcher_vectors.npz"), ka=ka, da=da, kb=kb, db=db, bounds=np.array(bounds),
+                        init_n=n, init_m12=m12, init_prev=p, grid_start=gs, grid_idx=gi,
+                        bf_q=q, bf_qa=qa, bf_t=t, bf_ta=ta, bf_n=bn, bf_best=best, bf_second=second, bf_idx=idx, bf_m12=bm12,
+                        pinned_by="oracle (ORBmatcher.cc cannot be compiled here)")
+    print("matcher vectors: init", n, "bruteforce", bn)
+
+
+if __name__ == "__main__":
+    main()

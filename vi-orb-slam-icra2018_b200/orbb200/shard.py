@@ -1,0 +1,88 @@
+"""Multi-GPU plumbing (one process per GPU, torch.distributed): who owns which frames / keyframes, and the one
+exchange step of the path -- the all-gather of the keyframe descriptor table for all-pairs matching.
+
+Frame batches and frame pairs are independent units: ranks take contiguous blocks and nothing crosses NVLink.
+All-pairs keyframe matching has exactly one exchange: every rank contributes the descriptors of its own keyframe block
+and needs everybody else's.  The gather is started first, and the rank matches its query block against its OWN block
+(already local) while the gather is in flight; the remaining column blocks follow once it has landed.
+"""
+import numpy as np
+
+
+def block_range(n, rank, world):
+    """Contiguous block [begin, end) of n units owned by `rank` (sizes differ by at most one)."""
+    base, rem = divmod(n, world)
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+def column_schedule(n_kf, rank, world):
+    """Order in which a rank visits the db keyframe blocks: its own block first (no communication needed), then the
+    others in ring order so that ranks do not all hammer the same source at once."""
+    order = [(rank + k) % world for k in range(world)]
+    return [block_range(n_kf, r, world) for r in order]
+
+
+def all_gather_table(local_desc, local_angles, n_kf, dist, async_op=True):
+    """All-gather the descriptor table. local_desc: (n_local, n_desc, 32) uint8 tensor, local_angles: (n_local, n_desc)
+    float32, on this rank's device (or CPU for gloo).  Returns (table, angles, work_handles); wait on the handles before
+    reading rows outside this rank's block.  Blocks may differ in size by one keyframe, so the gather is done on padded
+    blocks and compacted (the padding rows are never read)."""
+    import torch
+    world, rank = dist.get_world_size(), dist.get_rank()
+    sizes = [block_range(n_kf, r, world) for r in range(world)]
+    max_local = max(e - b for b, e in sizes)
+    n_desc = local_desc.shape[1]
+    pad_d = torch.zeros((max_local, n_desc, 32), dtype=torch.uint8, device=local_desc.device)
+    pad_a = torch.zeros((max_local, n_desc), dtype=torch.float32, device=local_desc.device)
+    pad_d[: local_desc.shape[0]] = local_desc
+    pad_a[: local_angles.shape[0]] = local_angles
+    gd = torch.empty((world * max_local, n_desc, 32), dtype=torch.uint8, device=local_desc.device)
+    ga = torch.empty((world * max_local, n_desc), dtype=torch.float32, device=local_desc.device)
+    # the own block is valid immediately: copy it in place so that matching against it can start before the gather ends
+    gd[rank * max_local: rank * max_local + local_desc.shape[0]] = local_desc
+    ga[rank * max_local: rank * max_local + local_angles.shape[0]] = local_angles
+    works = [dist.all_gather_into_tensor(gd, pad_d, async_op=async_op),
+             dist.all_gather_into_tensor(ga, pad_a, async_op=async_op)]
+    return gd, ga, [w for w in works if w is not None], max_local, sizes
+
+
+def allpairs_sharded(matcher, local_desc, local_angles, n_kf, dist, ratio=0.75, check_ori=True, compute=None, stream=None):
+    """Config 5: this rank's (n_local x n_kf) tile of the keyframe match-count matrix.
+
+    compute(table, angles, q_begin, q_end, db_begin, db_end, counts) defaults to the CUDA all-pairs kernel through the C ABI;
+    the gloo tests inject a host stand-in to exercise the plumbing without a GPU.
+    """
+    import torch
+    world, rank = dist.get_world_size(), dist.get_rank()
+    gd, ga, works, max_local, sizes = all_gather_table(local_desc, local_angles, n_kf, dist)
+    qb, qe = sizes[rank]
+    counts = torch.full((qe - qb, n_kf), -1, dtype=torch.int32, device=local_desc.device)
+    padded_rows = world * max_local
+
+    if compute is None:
+        if stream is None:   # enqueue on torch's current stream so that work.wait() orders the gather before the kernels
+            stream = torch.cuda.current_stream(local_desc.device).cuda_stream
+
+        def compute(table, angles, q0, q1, d0, d1, out):
+            # `out` has one column per row of the padded table; only [d0, d1) is written by this call
+            matcher.allpairs_device(table, angles, q0, q1, d0, d1, ratio, check_ori, out, stream=stream)
+
+    # rows of the padded table: rank r's keyframes start at r*max_local
+    padded_counts = torch.full((qe - qb, padded_rows), -1, dtype=torch.int32, device=local_desc.device)
+    first = True
+    for (b, e) in column_schedule(n_kf, rank, world):
+        r = next(i for i, s in enumerate(sizes) if s == (b, e))
+        if not first:
+            for w in works:
+                w.wait()
+            works = []
+        compute(gd, ga, rank * max_local, rank * max_local + (qe - qb), r * max_local, r * max_local + (e - b), padded_counts)
+        first = False
+    for w in works:
+        w.wait()
+    if local_desc.is_cuda:
+        torch.cuda.current_stream(local_desc.device).synchronize()
+    for r, (b, e) in enumerate(sizes):
+        counts[:, b:e] = padded_counts[:, r * max_local: r * max_local + (e - b)]
+    return counts
