@@ -1,0 +1,39 @@
+// Compiles the C++ adapter (reference class names and method names) against liborbb200.so and runs it once.
+// argv[1] = raw 8-bit image file, argv[2] = width, argv[3] = height. Prints "n_keypoints checksum n_matches".
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "ORBextractor.h"
+#include "ORBmatcher.h"
+
+int main(int argc, char** argv) {
+    if (argc < 4) return 2;
+    const int w = atoi(argv[2]), h = atoi(argv[3]);
+    std::vector<unsigned char> img((size_t)w * h);
+    FILE* f = fopen(argv[1], "rb");
+    if (!f || fread(img.data(), 1, img.size(), f) != img.size()) return 2;
+    fclose(f);
+    try {
+        ORB_SLAM2::ORBextractor extractor(1000, 1.2f, 8, 20, 7);
+        std::vector<orb_keypoint> keys;
+        std::vector<unsigned char> desc;
+        extractor(img.data(), w, h, w, keys, desc);
+        unsigned long long sum = 0;
+        for (size_t i = 0; i < desc.size(); ++i) sum = sum * 131 + desc[i];
+        ORB_SLAM2::ORBmatcher matcher(0.9f, true);
+        ORB_SLAM2::FrameView F1(matcher.handle(), keys.data(), desc.data(), (int)keys.size(), 0, 0, (float)w, (float)h);
+        ORB_SLAM2::FrameView F2(matcher.handle(), keys.data(), desc.data(), (int)keys.size(), 0, 0, (float)w, (float)h);
+        std::vector<float> prev(keys.size() * 2);
+        for (size_t i = 0; i < keys.size(); ++i) { prev[2 * i] = keys[i].x; prev[2 * i + 1] = keys[i].y; }
+        std::vector<int> m12;
+        const int n = matcher.SearchForInitialization(F1, F2, prev, m12, 100);
+        printf("%zu %llu %d %d %.3f\n", keys.size(), sum, n, extractor.GetLevels(), extractor.GetScaleFactors()[7]);
+        const int d = matcher.DescriptorDistance(desc.data(), desc.data() + 32);
+        printf("%d\n", d);
+    } catch (const std::exception& e) {
+        fprintf(stderr, "%s\n", e.what());
+        return 1;
+    }
+    return 0;
+}

@@ -1,0 +1,36 @@
+"""The C++ adapter (reference class and method names over the C ABI) compiled with g++ and run on the GPU."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import orbb200
+from orbb200.synth import synth_frame
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_adapter_matches_c_abi(tmp_path, matcher):
+    pkg = os.path.join(ROOT, "vi-orb-slam-icra2018_b200")
+    exe = str(tmp_path / "adapter_smoke")
+    subprocess.check_call(["g++", "-std=c++11", "-O1", "-I", os.path.join(pkg, "adapter"), "-o", exe,
+                           os.path.join(ROOT, "tests", "adapter_smoke.cpp"), "-L", pkg, "-lorbb200", "-Wl,-rpath," + pkg])
+    img = synth_frame(0)
+    raw = tmp_path / "img.raw"
+    img.tofile(raw)
+    out = subprocess.run([exe, str(raw), "752", "480"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    n_kp, checksum, n_match, levels, sf7 = out.stdout.split("\n")[0].split()
+    ex = orbb200.Extractor(1000)
+    kps, desc = ex(img)
+    s = 0
+    for b in desc.reshape(-1).tolist():
+        s = (s * 131 + b) & 0xFFFFFFFFFFFFFFFF
+    assert int(n_kp) == len(kps) and int(checksum) == s and int(levels) == 8
+    f = matcher.frame(kps, desc, (0, 0, 752, 480))
+    n, m12, _ = matcher.search_for_initialization(f, f, np.stack([kps["x"], kps["y"]], 1), 100, 0.9, True)
+    assert int(n_match) == n
+    assert int(out.stdout.split("\n")[1]) == int(matcher.distance(desc[0], desc[1])[0])
+    ex.close()

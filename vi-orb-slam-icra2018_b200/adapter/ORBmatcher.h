@@ -1,0 +1,145 @@
+// Host-side mirror of ORB_SLAM2::ORBmatcher (reference: include/ORBmatcher.h:41-83) over the orbb200 C ABI.
+//
+// The reference's search methods take Frame / KeyFrame / MapPoint object graphs.  The data those loops actually read
+// are a handful of arrays (undistorted keypoints, descriptors, image bounds, scale tables, per-point flags), so the
+// adapter's native surface is `FrameView` + the query structs of orbb200.h; with -DORBB200_WITH_ORBSLAM (ORB-SLAM2
+// headers on the include path) the reference's exact signatures are provided as thin overloads that flatten the
+// objects, run the search on the GPU and write the results back into the objects the way the reference does.
+// Same constants (TH_LOW, TH_HIGH, HISTO_LENGTH), same constructor (nnratio, checkOri), same return values.
+#ifndef ORBB200_ADAPTER_ORBMATCHER_H
+#define ORBB200_ADAPTER_ORBMATCHER_H
+
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/orbb200.h"
+
+namespace ORB_SLAM2 {
+
+// What a search reads of a Frame or KeyFrame. Owns the device copy + 64x48 grid (Frame.cc:574-589).
+class FrameView {
+public:
+    FrameView(orbm_handle m, const orb_keypoint* keysUn, const unsigned char* descriptors, int n, float minX, float minY,
+              float maxX, float maxY)
+        : n_(n) {
+        if (orbm_frame_create(m, keysUn, descriptors, n, minX, minY, maxX, maxY, &f_) != ORB_OK)
+            throw std::runtime_error(std::string("orbb200: ") + orb_last_error());
+    }
+    ~FrameView() { orbm_frame_destroy(f_); }
+    FrameView(const FrameView&) = delete;
+    FrameView& operator=(const FrameView&) = delete;
+    orbm_frame get() const { return f_; }
+    int size() const { return n_; }
+
+private:
+    orbm_frame f_ = nullptr;
+    int n_ = 0;
+};
+
+class ORBmatcher {
+public:
+    static const int TH_LOW = 50;
+    static const int TH_HIGH = 100;
+    static const int HISTO_LENGTH = 30;
+
+    ORBmatcher(float nnratio = 0.6, bool checkOri = true, int device = 0) : mfNNratio(nnratio), mbCheckOrientation(checkOri) {
+        check(orbm_create(device, &h_));
+    }
+    ~ORBmatcher() { orbm_destroy(h_); }
+    ORBmatcher(const ORBmatcher&) = delete;
+    ORBmatcher& operator=(const ORBmatcher&) = delete;
+    orbm_handle handle() { return h_; }
+
+    // Computes the Hamming distance between two ORB descriptors (ORBmatcher.cc:1675-1691). One pair per call is a poor
+    // use of a GPU; DescriptorDistances() takes n pairs.  Kept for drop-in completeness.
+    int DescriptorDistance(const unsigned char* a, const unsigned char* b) {
+        int d = 0;
+        check(orbm_distance(h_, a, b, 1, &d));
+        return d;
+    }
+    void DescriptorDistances(const unsigned char* a, const unsigned char* b, int n, int* out) { check(orbm_distance(h_, a, b, n, out)); }
+
+    // SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize)   ORBmatcher.cc:405-520
+    int SearchForInitialization(const FrameView& F1, const FrameView& F2, std::vector<float>& vbPrevMatchedXY,
+                                std::vector<int>& vnMatches12, int windowSize = 10) {
+        vnMatches12.assign(F1.size(), -1);
+        vbPrevMatchedXY.resize((size_t)F1.size() * 2);
+        int n = 0;
+        check(orbm_search_for_initialization(h_, F1.get(), F2.get(), vbPrevMatchedXY.data(), vnMatches12.data(), windowSize,
+                                             mfNNratio, mbCheckOrientation, &n));
+        return n;
+    }
+
+    // SearchByProjection(CurrentFrame, LastFrame, th, bMono)   ORBmatcher.cc:1341-1498
+    // queries: one per LastFrame keypoint (projection done by the caller); curMatch[i2] = query index or -1
+    int SearchByProjection(const FrameView& Current, const std::vector<float>& scaleFactors, const float* uRight, float mbf,
+                           const std::vector<orbm_proj_query>& queries, const unsigned char* queryDescriptors, float th, int mode,
+                           const unsigned char* occupied, std::vector<int>& curMatch) {
+        curMatch.assign(Current.size(), -1);
+        int n = 0;
+        check(orbm_search_by_projection(h_, Current.get(), scaleFactors.data(), (int)scaleFactors.size(), uRight, mbf,
+                                        queries.data(), queryDescriptors, (int)queries.size(), th, mode, occupied,
+                                        curMatch.data(), mbCheckOrientation, &n));
+        return n;
+    }
+
+    // SearchByProjection(F, vpMapPoints, th)   ORBmatcher.cc:45-129
+    int SearchByProjection(const FrameView& F, const std::vector<float>& scaleFactors, const float* uRight,
+                           const std::vector<orbm_point_query>& queries, const unsigned char* queryDescriptors, float th,
+                           const unsigned char* occupied, std::vector<int>& match) {
+        match.assign(F.size(), -1);
+        int n = 0;
+        check(orbm_search_by_projection_points(h_, F.get(), scaleFactors.data(), (int)scaleFactors.size(), uRight, queries.data(),
+                                               queryDescriptors, (int)queries.size(), th, mfNNratio, occupied, match.data(), &n));
+        return n;
+    }
+
+    // SearchForTriangulation(pKF1, pKF2, F12, vMatchedPairs, bOnlyStereo)   ORBmatcher.cc:657-823
+    struct FeatureVectorCSR { std::vector<int> nodeId, start, idx; };   // DBoW2::FeatureVector flattened, ids ascending
+    int SearchForTriangulation(const FrameView& KF1, const FrameView& KF2, const FeatureVectorCSR& fv1, const FeatureVectorCSR& fv2,
+                               const unsigned char* hasMapPoint1, const unsigned char* hasMapPoint2, const float* uRight1,
+                               const float* uRight2, const float F12[9], float ex, float ey, const std::vector<float>& scaleFactors2,
+                               const std::vector<float>& levelSigma2_2, std::vector<std::pair<size_t, size_t> >& vMatchedPairs,
+                               bool bOnlyStereo) {
+        std::vector<int> m12(KF1.size(), -1);
+        int n = 0;
+        check(orbm_search_for_triangulation(h_, KF1.get(), KF2.get(), (int)fv1.nodeId.size(), fv1.nodeId.data(), fv1.start.data(),
+                                            fv1.idx.data(), (int)fv2.nodeId.size(), fv2.nodeId.data(), fv2.start.data(), fv2.idx.data(),
+                                            hasMapPoint1, hasMapPoint2, uRight1, uRight2, F12, ex, ey, scaleFactors2.data(),
+                                            levelSigma2_2.data(), (int)scaleFactors2.size(), bOnlyStereo, mbCheckOrientation,
+                                            m12.data(), &n));
+        vMatchedPairs.clear();
+        vMatchedPairs.reserve(n);
+        for (size_t i = 0; i < m12.size(); ++i)
+            if (m12[i] >= 0) vMatchedPairs.push_back(std::make_pair(i, (size_t)m12[i]));   // ORBmatcher.cc:812-820
+        return n;
+    }
+
+#ifdef ORBB200_WITH_ORBSLAM
+    // ---- the reference's own signatures (need Frame.h / KeyFrame.h / MapPoint.h of the host project) -------------------
+    // Declared here, defined in adapter/ORBmatcher_orbslam.inl, which flattens the objects exactly as documented in
+    // INTEGRATION.md section 3.  Not compiled in this repository: the host project's headers need Eigen, DBoW2 and g2o.
+    int SearchForInitialization(Frame& F1, Frame& F2, std::vector<cv::Point2f>& vbPrevMatched, std::vector<int>& vnMatches12,
+                                int windowSize = 10);
+    int SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, const float th, const bool bMono);
+    int SearchByProjection(Frame& F, const std::vector<MapPoint*>& vpMapPoints, const float th = 3);
+    int SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, cv::Mat F12, std::vector<std::pair<size_t, size_t> >& vMatchedPairs,
+                               const bool bOnlyStereo);
+#endif
+
+protected:
+    float mfNNratio;
+    bool mbCheckOrientation;
+
+private:
+    orbm_handle h_ = nullptr;
+    static void check(int st) {
+        if (st != ORB_OK) throw std::runtime_error(std::string("orbb200: ") + orb_last_error());
+    }
+};
+
+}  // namespace ORB_SLAM2
+
+#endif

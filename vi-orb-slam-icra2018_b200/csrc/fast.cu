@@ -11,52 +11,55 @@
 //     non-corners count as 0;
 //   * threshold fallback: the cell is re-run at minThFAST only if NOTHING survives NMS at iniThFAST (:811-818);
 //   * emission order inside a cell is row-major (y, x); cells are consumed in (row, col) order by the quadtree kernel.
-// Stages: tile (+3 halo) -> shared memory with aligned 32-bit loads; cheap necessary test on all pixels (of each
-// opposing circle pair one must be brighter / darker) with survivors compacted into a queue; exact packed-16-bit
-// sliding-window score on the queue only; NMS + ordered compaction with a block scan.
+//
+// Instruction budget is what bounds this kernel (ncu: issue-bound, DRAM < 2%), so the stages are shaped for dense
+// lanes and packed arithmetic:
+//   0. tile (+halo) -> shared memory, widened to 16 bits per pixel so that two horizontally adjacent pixels are one
+//      ready-made 16x2 operand;
+//   A. necessary test on EVERY pixel, 4 pixels per thread, no divergence: of each opposing circle pair (k, k+8) one
+//      pixel lies on any 9-arc, so min_j max(p_j, p_j+8) > v+t (or max_j min(..) < v-t) must hold.  All in DPX 16x2
+//      min/max (VIMNMX); neighbours at odd offsets come from 16-bit funnel shifts.  Survivors are queued;
+//   B. exact score on the queue only (dense lanes again): both polarities in one 16x2 register, sliding-window minimum
+//      with 3-input min/max;
+//   C. NMS on the queue entries, survivors set bits in two row-major bitmaps (>= iniTh, >= minTh);
+//   D. one warp prefix-sums the popcounts of the chosen bitmap; E. survivors store themselves at their rank.
 #include "extractor.h"
 
 namespace orbb {
 
 constexpr int FAST_THREADS = 128;
-constexpr int TILE_PITCH = 72;                    // bytes; 3 (alignment shift) + 66 + slack, multiple of 4
+constexpr int TPX = 72;                           // tile pitch in pixels (16-bit each); interior x=0 sits at column 4
 constexpr int TILE_ROWS = kCellMax + 6;
-constexpr int SC_PITCH = 64;                      // score map pitch, interior + 1-px zero ring (<= 62)
+constexpr int SC_PITCH = 64;                      // score map pitch (bytes), interior + 1-px zero ring (<= 62)
 constexpr int SC_ROWS = kCellMax + 2;
+constexpr int BM_WORDS = (kCellMax * kCellMax + 31) / 32;   // 113
 
-// offsets of the 16 circle pixels in the shared tile, OpenCV order (dx,dy) = (0,3)(1,3)(2,2)(3,1)(3,0)(3,-1)(2,-2)(1,-3)
-// (0,-3)(-1,-3)(-2,-2)(-3,-1)(-3,0)(-3,1)(-2,2)(-1,3)
-#define CIRCLE_OFFSET(k)                                                                                           \
-    ((k) == 0 ? 3 * TILE_PITCH : (k) == 1 ? 3 * TILE_PITCH + 1 : (k) == 2 ? 2 * TILE_PITCH + 2 : (k) == 3 ? TILE_PITCH + 3 \
-     : (k) == 4 ? 3 : (k) == 5 ? -TILE_PITCH + 3 : (k) == 6 ? -2 * TILE_PITCH + 2 : (k) == 7 ? -3 * TILE_PITCH + 1       \
-     : (k) == 8 ? -3 * TILE_PITCH : (k) == 9 ? -3 * TILE_PITCH - 1 : (k) == 10 ? -2 * TILE_PITCH - 2                   \
-     : (k) == 11 ? -TILE_PITCH - 3 : (k) == 12 ? -3 : (k) == 13 ? TILE_PITCH - 3 : (k) == 14 ? 2 * TILE_PITCH - 2       \
-                                                                                           : 3 * TILE_PITCH - 1)
+// circle offsets in tile pixels, OpenCV order (dx,dy) = (0,3)(1,3)(2,2)(3,1)(3,0)(3,-1)(2,-2)(1,-3)(0,-3)(-1,-3)(-2,-2)
+// (-3,-1)(-3,0)(-3,1)(-2,2)(-1,3)
+#define CIRCLE_OFFSET(k)                                                                                   \
+    ((k) == 0 ? 3 * TPX : (k) == 1 ? 3 * TPX + 1 : (k) == 2 ? 2 * TPX + 2 : (k) == 3 ? TPX + 3             \
+     : (k) == 4 ? 3 : (k) == 5 ? -TPX + 3 : (k) == 6 ? -2 * TPX + 2 : (k) == 7 ? -3 * TPX + 1              \
+     : (k) == 8 ? -3 * TPX : (k) == 9 ? -3 * TPX - 1 : (k) == 10 ? -2 * TPX - 2 : (k) == 11 ? -TPX - 3     \
+     : (k) == 12 ? -3 : (k) == 13 ? TPX - 3 : (k) == 14 ? 2 * TPX - 2 : 3 * TPX - 1)
 
-// Necessary condition for S >= t: every opposing pair (k, k+8) holds a pixel of the arc, so all 8 pairs need a
-// brighter (> v+t) member, or all 8 a darker (< v-t) one.
-__device__ __forceinline__ bool maybe_corner(const unsigned char* c, int t) {
-    const int v = c[0];
-    const int hi = v + t, lo = v - t;
-    int bright = 1, dark = 1;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const int a = c[CIRCLE_OFFSET(k)], b = c[CIRCLE_OFFSET(k + 8)];
-        bright &= (a > hi) | (b > hi);
-        dark &= (a < lo) | (b < lo);
-        if (k == 1 && !(bright | dark)) return false;   // two pairs read: most flat pixels leave here
-    }
-    return (bright | dark) != 0;
-}
+struct FastShared {
+    unsigned int tile[TILE_ROWS * TPX / 2];                 // 16-bit pixels, two per word
+    unsigned int score[SC_ROWS * SC_PITCH / 4];             // uint8 scores with a zero ring
+    unsigned short queue[kCellMax * kCellMax];              // x | y<<6 | alive<<12 | max<<13 | ini<<14
+    unsigned int bmMin[BM_WORDS + 1], bmIni[BM_WORDS + 1];  // survivors at minTh / iniTh, bit = y*cw + x
+    int prefix[BM_WORDS + 1];
+    int queueLen;
+    int anyIni;
+};
 
 // Exact threshold-free score. Both polarities ride in one register: low half p_k - v, high half v - p_k.
-__device__ __forceinline__ int fast_score(const unsigned char* c) {
+__device__ __forceinline__ int fast_score(const unsigned short* c) {
     const int v = c[0];
     unsigned int d[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
         const int diff = (int)c[CIRCLE_OFFSET(k)] - v;
-        d[k] = ((unsigned int)diff & 0xffffu) | ((unsigned int)(-diff) << 16);
+        d[k] = __byte_perm((unsigned int)diff, (unsigned int)(-diff), 0x5410);
     }
     unsigned int m3[16];
 #pragma unroll
@@ -72,105 +75,187 @@ __device__ __forceinline__ int fast_score(const unsigned char* c) {
     return max(lo, hi) - 1;
 }
 
-struct FastShared {
-    unsigned int tile[TILE_ROWS * TILE_PITCH / 4];          // pixels; reused as per-pixel NMS flags afterwards
-    unsigned int score[SC_ROWS * SC_PITCH / 4];             // uint8 scores with a zero ring
-    unsigned short queue[kCellMax * kCellMax];              // pixels that passed the necessary test
-    int warpSums[FAST_THREADS / 32];
-    int queueLen;
-};
+// one opposing circle pair for two pixel pairs: running min of the pair maxima and max of the pair minima
+__device__ __forceinline__ void pair_step(unsigned int a, unsigned int b, unsigned int& minOfMax, unsigned int& maxOfMin) {
+    minOfMax = __vminu2(minOfMax, __vmaxu2(a, b));   // DPX VIMNMX.U16x2
+    maxOfMin = __vmaxu2(maxOfMin, __vminu2(a, b));
+}
 
-__global__ void __launch_bounds__(FAST_THREADS) fast_cells_kernel(const __grid_constant__ ExtractParams P) {
-    __shared__ FastShared S;
+__global__ void __launch_bounds__(FAST_THREADS, 8) fast_cells_kernel(const __grid_constant__ ExtractParams P) {
+    __shared__ __align__(16) FastShared S;
     const Cell cell = P.cells[blockIdx.x];
     const LevelGeom& L = P.lv[cell.level];
     const int frame = blockIdx.y, tid = threadIdx.x;
-    const int cw = cell.cw, ch = cell.ch, npix = cw * ch;
+    const int cw = cell.cw, ch = cell.ch;
     const unsigned char* level0 = P.pyr + (size_t)frame * P.pyrFrameBytes + L.pyrOff + (size_t)kEdge * L.pitch + kPadLeft;
 
-    // ---- stage the (cw+6) x (ch+6) tile with aligned 32-bit loads
-    const int tx0 = cell.x0 - 3, ty0 = cell.y0 - 3;
-    const int shift = (tx0 + kPadLeft) & 3;
-    const int wordsPerRow = (shift + cw + 6 + 3) >> 2;
-    const unsigned char* src = level0 + (long long)ty0 * L.pitch + (tx0 - shift);
-    for (int i = tid; i < (ch + 6) * wordsPerRow; i += FAST_THREADS) {
-        const int r = i / wordsPerRow, wI = i - r * wordsPerRow;
-        S.tile[r * (TILE_PITCH / 4) + wI] = __ldg(reinterpret_cast<const unsigned int*>(src + (size_t)r * L.pitch) + wI);
-    }
-    for (int i = tid; i < SC_ROWS * SC_PITCH / 4; i += FAST_THREADS) S.score[i] = 0;
-    if (tid == 0) S.queueLen = 0;
-    __syncthreads();
-
-    const unsigned char* tile = reinterpret_cast<const unsigned char*>(S.tile);
-    unsigned char* score = reinterpret_cast<unsigned char*>(S.score);
-
-    // ---- necessary test on every interior pixel, survivors queued
-    for (int p = tid; p < npix; p += FAST_THREADS) {
-        const int y = p / cw, x = p - y * cw;
-        if (maybe_corner(tile + (y + 3) * TILE_PITCH + shift + x + 3, P.minTh)) S.queue[atomicAdd(&S.queueLen, 1)] = (unsigned short)p;
-    }
-    __syncthreads();
-    // ---- exact score for the queue
-    const int qn = S.queueLen;
-    for (int q = tid; q < qn; q += FAST_THREADS) {
-        const int p = S.queue[q];
-        const int y = p / cw, x = p - y * cw;
-        const int s = fast_score(tile + (y + 3) * TILE_PITCH + shift + x + 3);
-        if (s >= P.minTh) score[(y + 1) * SC_PITCH + x + 1] = (unsigned char)s;
+    // ---- 0. stage level pixels [x0-4, x0+cw+4) x [y0-3, y0+ch+3) as 16-bit values; aligned 32-bit global loads,
+    //         funnel shift to the tile's alignment, widen, one 64-bit shared store per 4 pixels
+    {
+        const int tx0 = cell.x0 - 4, ty0 = cell.y0 - 3;
+        const int shift8 = ((tx0 + kPadLeft) & 3) * 8;
+        const int quads = (cw + 8 + 3) >> 2;                 // 4-pixel groups per tile row (<= 17)
+        const unsigned char* src = level0 + (long long)ty0 * L.pitch + (tx0 - (shift8 >> 3));
+        uint2* tile64 = reinterpret_cast<uint2*>(S.tile);
+        for (int i = tid; i < (ch + 6) * quads; i += FAST_THREADS) {
+            const int r = i / quads, q = i - r * quads;
+            const unsigned int* g = reinterpret_cast<const unsigned int*>(src + (size_t)r * L.pitch) + q;
+            const unsigned int w0 = __ldg(g), w1 = shift8 ? __ldg(g + 1) : 0u;
+            const unsigned int px = __funnelshift_r(w0, w1, shift8);
+            tile64[r * (TPX / 4) + q] = make_uint2(__byte_perm(px, 0, 0x4140), __byte_perm(px, 0, 0x4342));
+        }
+        for (int i = tid; i < SC_ROWS * SC_PITCH / 4; i += FAST_THREADS) S.score[i] = 0;
+        for (int i = tid; i < BM_WORDS + 1; i += FAST_THREADS) { S.bmMin[i] = 0; S.bmIni[i] = 0; }
+        if (tid == 0) { S.queueLen = 0; S.anyIni = 0; }
     }
     __syncthreads();
 
-    // ---- per-cell NMS; each thread owns a contiguous run of the row-major pixel order
-    unsigned char* flags = reinterpret_cast<unsigned char*>(S.tile);
-    const int per = (npix + FAST_THREADS - 1) / FAST_THREADS;
-    const int p0 = min(tid * per, npix), p1 = min(p0 + per, npix);
-    int nIni = 0, nMin = 0;
-    for (int p = p0; p < p1; ++p) {
-        const int y = p / cw, x = p - y * cw;
-        const unsigned char* sc = score + (y + 1) * SC_PITCH + x + 1;
-        const int s = sc[0];
-        unsigned char f = 0;
-        if (s > 0) {
-            const int m = max(max(max(sc[-SC_PITCH - 1], sc[-SC_PITCH]), max(sc[-SC_PITCH + 1], sc[-1])),
-                              max(max(sc[1], sc[SC_PITCH - 1]), max(sc[SC_PITCH], sc[SC_PITCH + 1])));
-            if (s > m) {
-                f = s >= P.iniTh ? 2 : 1;
-                ++nMin;
-                nIni += f == 2;
+    // ---- A. necessary test, 4 pixels (two 16x2 pairs) per thread
+    {
+        const int groups = (cw + 3) >> 2;
+        const unsigned int T1 = (unsigned int)(P.minTh + 1) * 0x00010001u;
+        const uint2* tile64 = reinterpret_cast<const uint2*>(S.tile);
+        for (int i = tid; i < groups * ch; i += FAST_THREADS) {
+            const int y = i / groups, g = i - y * groups;
+            const uint2* row = tile64 + (y + 3) * (TPX / 4) + g;   // row[0] = pixels x0-4..x0-1, row[1] = x0..x0+3, row[2] = x0+4..
+            // A = pixels (x0, x0+1), B = (x0+2, x0+3); "min of pair maxima" must exceed v+t, "max of pair minima" stay below v-t
+            unsigned int mmA = 0xffffffffu, mmB = 0xffffffffu, nnA = 0u, nnB = 0u;
+            {   // rows +-3: dx = 0, +1, -1  -> circle points 0/8, 1/9, 15/7
+                const uint2* up = row - 3 * (TPX / 4);
+                const uint2* dn = row + 3 * (TPX / 4);
+                const unsigned int u1 = up[0].y, u4 = up[2].x, d1 = dn[0].y, d4 = dn[2].x;
+                const uint2 uc = up[1], dc = dn[1];
+                pair_step(dc.x, uc.x, mmA, nnA);                                   // k=0 (0,3) with k=8 (0,-3)
+                pair_step(dc.y, uc.y, mmB, nnB);
+                const unsigned int uf12 = __funnelshift_r(u1, uc.x, 16), uf23 = __funnelshift_r(uc.x, uc.y, 16),
+                                   uf34 = __funnelshift_r(uc.y, u4, 16);
+                const unsigned int df12 = __funnelshift_r(d1, dc.x, 16), df23 = __funnelshift_r(dc.x, dc.y, 16),
+                                   df34 = __funnelshift_r(dc.y, d4, 16);
+                pair_step(df23, uf12, mmA, nnA);                                   // k=1 (1,3) with k=9 (-1,-3)
+                pair_step(df34, uf23, mmB, nnB);
+                pair_step(uf23, df12, mmA, nnA);                                   // k=7 (1,-3) with k=15 (-1,3)
+                pair_step(uf34, df23, mmB, nnB);
+            }
+            {   // rows +-2: dx = +-2 -> circle points 2/10, 6/14; no shifts
+                const uint2* up = row - 2 * (TPX / 4);
+                const uint2* dn = row + 2 * (TPX / 4);
+                const unsigned int u1 = up[0].y, u4 = up[2].x, d1 = dn[0].y, d4 = dn[2].x;
+                const uint2 uc = up[1], dc = dn[1];
+                pair_step(dc.y, u1, mmA, nnA);                                     // k=2 (2,2) with k=10 (-2,-2)
+                pair_step(d4, uc.x, mmB, nnB);
+                pair_step(uc.y, d1, mmA, nnA);                                     // k=6 (2,-2) with k=14 (-2,2)
+                pair_step(u4, dc.x, mmB, nnB);
+            }
+            unsigned int cA, cB;
+            {   // rows +-1 and 0: dx = +-3 -> circle points 3/11, 5/13, 4/12
+                const uint2* up = row - (TPX / 4);
+                const uint2* dn = row + (TPX / 4);
+                const uint2 ul = up[0], uc = up[1], ur = up[2], dl = dn[0], dc = dn[1], dr = dn[2];
+                const uint2 ml = row[0], mc = row[1], mr = row[2];
+                cA = mc.x; cB = mc.y;
+                // +3: A' = (x0+3, x0+4), B' = (x0+5, x0+6);  -3: A' = (x0-3, x0-2), B' = (x0-1, x0)
+                const unsigned int uPA = __funnelshift_r(uc.y, ur.x, 16), uPB = __funnelshift_r(ur.x, ur.y, 16);
+                const unsigned int uMA = __funnelshift_r(ul.x, ul.y, 16), uMB = __funnelshift_r(ul.y, uc.x, 16);
+                const unsigned int dPA = __funnelshift_r(dc.y, dr.x, 16), dPB = __funnelshift_r(dr.x, dr.y, 16);
+                const unsigned int dMA = __funnelshift_r(dl.x, dl.y, 16), dMB = __funnelshift_r(dl.y, dc.x, 16);
+                const unsigned int mPA = __funnelshift_r(mc.y, mr.x, 16), mPB = __funnelshift_r(mr.x, mr.y, 16);
+                const unsigned int mMA = __funnelshift_r(ml.x, ml.y, 16), mMB = __funnelshift_r(ml.y, mc.x, 16);
+                pair_step(dPA, uMA, mmA, nnA);                                     // k=3 (3,1) with k=11 (-3,-1)
+                pair_step(dPB, uMB, mmB, nnB);
+                pair_step(uPA, dMA, mmA, nnA);                                     // k=5 (3,-1) with k=13 (-3,1)
+                pair_step(uPB, dMB, mmB, nnB);
+                pair_step(mPA, mMA, mmA, nnA);                                     // k=4 (3,0) with k=12 (-3,0)
+                pair_step(mPB, mMB, mmB, nnB);
+            }
+            // bright possible: mm >= v + t + 1 ; dark possible: v >= nn + t + 1   (per 16-bit half, values < 1024)
+            bool bAh, bAl, bBh, bBl, dAh, dAl, dBh, dBl;
+            __vibmax_u16x2(mmA, cA + T1, &bAh, &bAl);
+            __vibmax_u16x2(mmB, cB + T1, &bBh, &bBl);
+            __vibmax_u16x2(cA, nnA + T1, &dAh, &dAl);
+            __vibmax_u16x2(cB, nnB + T1, &dBh, &dBl);
+            const int x0 = 4 * g;
+            unsigned int flags = ((bAl | dAl) ? 1u : 0u) | ((bAh | dAh) ? 2u : 0u) | ((bBl | dBl) ? 4u : 0u) | ((bBh | dBh) ? 8u : 0u);
+            flags &= (1u << min(4, cw - x0)) - 1u;
+            if (flags) {
+                int pos = atomicAdd(&S.queueLen, __popc(flags));
+                const unsigned int base = (unsigned int)x0 | ((unsigned int)y << 6);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (flags & (1u << k)) S.queue[pos++] = (unsigned short)(base + k);
             }
         }
-        flags[p] = f;
     }
-    const int anyIni = __syncthreads_or(nIni > 0);   // also orders the flag writes
-    const int need = anyIni ? 2 : 1;
-    int mine = anyIni ? nIni : nMin;
-
-    // ---- ordered compaction: exclusive block scan of the per-thread counts
-    int incl = mine;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int n = __shfl_up_sync(0xffffffffu, incl, o);
-        if ((tid & 31) >= o) incl += n;
-    }
-    if ((tid & 31) == 31) S.warpSums[tid >> 5] = incl;
     __syncthreads();
-    int base = 0, total = 0;
-#pragma unroll
-    for (int wI = 0; wI < FAST_THREADS / 32; ++wI) {
-        const int s = S.warpSums[wI];
-        if (wI < (tid >> 5)) base += s;
-        total += s;
-    }
-    int pos = base + incl - mine;
-    unsigned int* slot = P.slots + (size_t)frame * P.slotFrameEntries + cell.slot;
-    for (int p = p0; p < p1; ++p) {
-        if (flags[p] >= need) {
-            const int y = p / cw, x = p - y * cw;
-            const unsigned int s = score[(y + 1) * SC_PITCH + x + 1];
-            slot[pos++] = ((unsigned int)(cell.x0 + x - 16) << 20) | ((unsigned int)(cell.y0 + y - 16) << 8) | s;
+
+    // ---- B. exact score for the queue
+    const int qn = S.queueLen;
+    const unsigned short* tile16 = reinterpret_cast<const unsigned short*>(S.tile);
+    unsigned char* score = reinterpret_cast<unsigned char*>(S.score);
+    for (int q = tid; q < qn; q += FAST_THREADS) {
+        const unsigned int e = S.queue[q];
+        const int x = e & 63, y = (e >> 6) & 63;
+        const int s = fast_score(tile16 + (y + 3) * TPX + x + 4);
+        if (s >= P.minTh) {
+            score[(y + 1) * SC_PITCH + x + 1] = (unsigned char)s;
+            S.queue[q] = (unsigned short)(e | 0x1000u | (s >= P.iniTh ? 0x4000u : 0u));
         }
     }
-    if (tid == 0) P.cellCount[(size_t)frame * P.nCellsTotal + blockIdx.x] = total;
+    __syncthreads();
+
+    // ---- C. per-cell NMS on the corners
+    for (int q = tid; q < qn; q += FAST_THREADS) {
+        const unsigned int e = S.queue[q];
+        if (!(e & 0x1000u)) continue;
+        const int x = e & 63, y = (e >> 6) & 63;
+        const unsigned char* sc = score + (y + 1) * SC_PITCH + x + 1;
+        const int s = sc[0];
+        const int m = max(max(max(sc[-SC_PITCH - 1], sc[-SC_PITCH]), max(sc[-SC_PITCH + 1], sc[-1])),
+                          max(max(sc[1], sc[SC_PITCH - 1]), max(sc[SC_PITCH], sc[SC_PITCH + 1])));
+        if (s > m) {
+            const int bit = y * cw + x;
+            atomicOr(&S.bmMin[bit >> 5], 1u << (bit & 31));
+            if (e & 0x4000u) {
+                atomicOr(&S.bmIni[bit >> 5], 1u << (bit & 31));
+                S.anyIni = 1;
+            }
+            S.queue[q] = (unsigned short)(e | 0x2000u);
+        }
+    }
+    __syncthreads();
+
+    // ---- D. rank table of the chosen threshold's survivors (row-major order == bit order)
+    const bool useIni = S.anyIni != 0;
+    const unsigned int* bm = useIni ? S.bmIni : S.bmMin;
+    if (tid < 32) {
+        int carry = 0;
+        for (int base = 0; base < BM_WORDS + 1; base += 32) {
+            const int w = base + tid;
+            const int c = w < BM_WORDS + 1 ? __popc(bm[w]) : 0;
+            int incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (tid >= o) incl += t;
+            }
+            if (w < BM_WORDS + 1) S.prefix[w] = carry + incl - c;
+            carry += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (tid == 0) P.cellCount[(size_t)frame * P.nCellsTotal + blockIdx.x] = carry;
+    }
+    __syncthreads();
+
+    // ---- E. survivors store themselves at their rank
+    unsigned int* slot = P.slots + (size_t)frame * P.slotFrameEntries + cell.slot;
+    const unsigned int need = useIni ? 0x6000u : 0x2000u;
+    for (int q = tid; q < qn; q += FAST_THREADS) {
+        const unsigned int e = S.queue[q];
+        if ((e & need) != need) continue;
+        const int x = e & 63, y = (e >> 6) & 63;
+        const int bit = y * cw + x;
+        const int rank = S.prefix[bit >> 5] + __popc(bm[bit >> 5] & ((1u << (bit & 31)) - 1u));
+        const unsigned int s = score[(y + 1) * SC_PITCH + x + 1];
+        slot[rank] = ((unsigned int)(cell.x0 + x - 16) << 20) | ((unsigned int)(cell.y0 + y - 16) << 8) | s;
+    }
 }
 
 int launch_fast(const ExtractParams& P, cudaStream_t st, int* launches) {

@@ -23,7 +23,7 @@
 
 namespace orbb {
 
-constexpr int OT_THREADS = 512;
+constexpr int OT_THREADS = 256;
 constexpr int OT_WARPS = OT_THREADS / 32;
 
 struct OtLayout {   // byte offsets into dynamic shared memory
@@ -120,7 +120,7 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
     return a;
 }
 
-__global__ void __launch_bounds__(OT_THREADS)
+__global__ void __launch_bounds__(OT_THREADS, 4)
 octree_kernel(const __grid_constant__ ExtractParams P, int nodeCap, int cellCap, int keyCap) {
     extern __shared__ __align__(16) unsigned char sm[];
     __shared__ int scanTmp[OT_WARPS + 1];
@@ -355,10 +355,13 @@ octree_kernel(const __grid_constant__ ExtractParams P, int nodeCap, int cellCap,
 }
 
 int octree_smem_plan(int nodeCap, int cellCap, int* smemBytes, int* keyCapSmem) {
-    const int budget = 200 * 1024;
+    // Occupancy matters more than capacity: the kernel is latency-bound (scans, barriers, shared atomics), so aim for
+    // 4 CTAs per SM (~55 KB each). Levels with more candidates than fit spill their key list to global memory.
+    const int hardBudget = 200 * 1024;
     const OtLayout fixed = ot_layout(nodeCap, cellCap, 0);
-    if (fixed.total > budget - 6 * 1024)
+    if (fixed.total > hardBudget - 6 * 1024)
         return fail(ORB_ERR_INVALID, "quadtree tables (%d B for %d nodes, %d cells) exceed shared memory", fixed.total, nodeCap, cellCap);
+    const int budget = fixed.total + 24 * 1024 < 55 * 1024 ? 55 * 1024 : (fixed.total + 24 * 1024 < hardBudget ? fixed.total + 24 * 1024 : hardBudget);
     int keyCap = ((budget - fixed.total - 64) / 6) & ~7;
     *keyCapSmem = keyCap;
     *smemBytes = ot_layout(nodeCap, cellCap, keyCap).total;
