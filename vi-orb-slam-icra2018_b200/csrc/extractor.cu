@@ -38,6 +38,8 @@ void resize_axis_table(int ssize, int dsize, int* ofs, short2* coef) {
 struct orbx_extractor {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t streamIn = nullptr, streamOut = nullptr;   // H2D / D2H of the host entry points, overlapped with compute
+    std::vector<cudaEvent_t> pipeEvents;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     // ctor state
     int nfeatures = 0, nlevels = 0, iniTh = 0, minTh = 0;
@@ -209,11 +211,20 @@ int configure(orbx_extractor* e, int w, int h, int nFrames) {
 
 // enqueue one batch (device pointers), no synchronisation
 int enqueue(orbx_extractor* e, const uint8_t* dImages, int nFrames, int w, int h, int stride, size_t frameStride,
-            orb_keypoint* dKps, uint8_t* dDesc, int capacity, int* dCount, cudaStream_t st, bool timed) {
-    ORB_CHECK(configure(e, w, h, nFrames));
+            orb_keypoint* dKps, uint8_t* dDesc, int capacity, int* dCount, cudaStream_t st, bool timed, int frameBase = 0) {
+    ORB_CHECK(configure(e, w, h, frameBase + nFrames));
     ExtractParams P = e->P;
     P.nFrames = nFrames;
     P.outCapacity = capacity;
+    if (frameBase) {   // this call works in arena slots [frameBase, frameBase + nFrames)
+        P.pyr += (size_t)frameBase * P.pyrFrameBytes;
+        P.blur += (size_t)frameBase * P.blurFrameBytes;
+        P.slots += (size_t)frameBase * P.slotFrameEntries;
+        P.cellCount += (size_t)frameBase * P.nCellsTotal;
+        P.sel += (size_t)frameBase * P.selPerFrame;
+        P.selCount += (size_t)frameBase * P.nLevels;
+        P.keyWs += (size_t)frameBase * P.keyWsFrameEntries;
+    }
     e->lastCapacity = capacity;
     e->timed = timed;
     cudaEvent_t* pe = nullptr;
@@ -312,6 +323,8 @@ int orbx_create(int nfeatures, float scaleFactor, int nlevels, int iniTh, int mi
         }
     }
     cudaError_t ce = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
+    if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&e->streamIn, cudaStreamNonBlocking);
+    if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&e->streamOut, cudaStreamNonBlocking);
     for (int i = 0; i < 4 && ce == cudaSuccess; ++i) ce = cudaEventCreate(&e->ev[i]);
     if (ce != cudaSuccess) {
         delete e;
@@ -337,6 +350,9 @@ int orbx_destroy(orbx_handle e) {
     for (int i = 0; i < 4; ++i)
         if (e->ev[i]) cudaEventDestroy(e->ev[i]);
     for (cudaEvent_t ev : e->profEvents) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : e->pipeEvents) cudaEventDestroy(ev);
+    if (e->streamIn) cudaStreamDestroy(e->streamIn);
+    if (e->streamOut) cudaStreamDestroy(e->streamOut);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
     return ORB_OK;
@@ -378,43 +394,64 @@ int orbx_extract_batch(orbx_handle e, const uint8_t* images, int nFrames, int w,
     }
     if (!kps || !desc || stride < w || capacity < 1) return fail(ORB_ERR_INVALID, "orbx_extract_batch: bad arguments");
     e->launches = 0;
-    const int chunk = std::min(e->maxBatch, 65535);
+    // The arena holds `super` frames; inside it the batch is cut into pipeline chunks so that the H2D copy of chunk k+1
+    // and the D2H copy of chunk k-1 overlap the kernels of chunk k (three streams, events between them).
+    const int super = std::min(e->maxBatch, 65535);
     const size_t imgBytes = (size_t)stride * h;
-    ORB_CHECK(configure(e, w, h, std::min(nFrames, chunk)));
-    ORB_CHECK(e->dImages.reserve((size_t)chunk * imgBytes));
-    ORB_CHECK(e->dKps.reserve((size_t)chunk * capacity * sizeof(orb_keypoint)));
-    ORB_CHECK(e->dDesc.reserve((size_t)chunk * capacity * 32));
-    ORB_CHECK(e->dCount.reserve((size_t)chunk * 4));
-    cudaStream_t st = e->stream;
+    ORB_CHECK(configure(e, w, h, std::min(nFrames, super)));
+    ORB_CHECK(e->dImages.reserve((size_t)super * imgBytes));
+    ORB_CHECK(e->dKps.reserve((size_t)super * capacity * sizeof(orb_keypoint)));
+    ORB_CHECK(e->dDesc.reserve((size_t)super * capacity * 32));
+    ORB_CHECK(e->dCount.reserve((size_t)super * 4));
+    const int pipeChunk = std::max(1, std::min(128, (std::min(nFrames, super) + 7) / 8));
+    const int maxChunks = (super + pipeChunk - 1) / pipeChunk;
+    while ((int)e->pipeEvents.size() < 2 * maxChunks) {
+        cudaEvent_t ev;
+        ORB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        e->pipeEvents.push_back(ev);
+    }
     int status = ORB_OK;
-    for (int f0 = 0; f0 < nFrames; f0 += chunk) {
-        const int nf = std::min(chunk, nFrames - f0);
-        if (frameStride == imgBytes) {
-            ORB_CUDA(cudaMemcpyAsync(e->dImages.p, images + (size_t)f0 * frameStride, (size_t)nf * imgBytes, cudaMemcpyHostToDevice, st));
-        } else {
-            for (int f = 0; f < nf; ++f)
-                ORB_CUDA(cudaMemcpyAsync(e->dImages.as<uint8_t>() + (size_t)f * imgBytes, images + (size_t)(f0 + f) * frameStride,
-                                         imgBytes, cudaMemcpyHostToDevice, st));
+    for (int s0 = 0; s0 < nFrames; s0 += super) {
+        const int ns = std::min(super, nFrames - s0);
+        int k = 0;
+        for (int f0 = 0; f0 < ns; f0 += pipeChunk, ++k) {
+            const int nf = std::min(pipeChunk, ns - f0);
+            uint8_t* dImg = e->dImages.as<uint8_t>() + (size_t)f0 * imgBytes;
+            const uint8_t* src = images + (size_t)(s0 + f0) * frameStride;
+            if (frameStride == imgBytes) {
+                ORB_CUDA(cudaMemcpyAsync(dImg, src, (size_t)nf * imgBytes, cudaMemcpyHostToDevice, e->streamIn));
+            } else {
+                ORB_CUDA(cudaMemcpy2DAsync(dImg, imgBytes, src, frameStride, imgBytes, nf, cudaMemcpyHostToDevice, e->streamIn));
+            }
+            ORB_CUDA(cudaEventRecord(e->pipeEvents[2 * k], e->streamIn));
+            ORB_CUDA(cudaStreamWaitEvent(e->stream, e->pipeEvents[2 * k], 0));
+            orb_keypoint* dK = e->dKps.as<orb_keypoint>() + (size_t)f0 * capacity;
+            uint8_t* dD = e->dDesc.as<uint8_t>() + (size_t)f0 * capacity * 32;
+            int* dN = e->dCount.as<int>() + f0;
+            ORB_CHECK(enqueue(e, dImg, nf, w, h, stride, imgBytes, dK, dD, capacity, dN, e->stream, s0 == 0 && f0 == 0, f0));
+            ORB_CUDA(cudaEventRecord(e->pipeEvents[2 * k + 1], e->stream));
+            ORB_CUDA(cudaStreamWaitEvent(e->streamOut, e->pipeEvents[2 * k + 1], 0));
+            const size_t o = (size_t)(s0 + f0);
+            ORB_CUDA(cudaMemcpyAsync(nOut + o, dN, (size_t)nf * 4, cudaMemcpyDeviceToHost, e->streamOut));
+            ORB_CUDA(cudaMemcpyAsync(kps + o * capacity, dK, (size_t)nf * capacity * sizeof(orb_keypoint), cudaMemcpyDeviceToHost, e->streamOut));
+            ORB_CUDA(cudaMemcpyAsync(desc + o * capacity * 32, dD, (size_t)nf * capacity * 32, cudaMemcpyDeviceToHost, e->streamOut));
         }
-        ORB_CHECK(enqueue(e, e->dImages.as<uint8_t>(), nf, w, h, stride, imgBytes, e->dKps.as<orb_keypoint>(),
-                          e->dDesc.as<uint8_t>(), capacity, e->dCount.as<int>(), st, f0 == 0));
-        ORB_CUDA(cudaMemcpyAsync(nOut + f0, e->dCount.p, (size_t)nf * 4, cudaMemcpyDeviceToHost, st));
-        ORB_CUDA(cudaMemcpyAsync(kps + (size_t)f0 * capacity, e->dKps.p, (size_t)nf * capacity * sizeof(orb_keypoint),
-                                 cudaMemcpyDeviceToHost, st));
-        ORB_CUDA(cudaMemcpyAsync(desc + (size_t)f0 * capacity * 32, e->dDesc.p, (size_t)nf * capacity * 32, cudaMemcpyDeviceToHost, st));
-        ORB_CUDA(cudaStreamSynchronize(st));
-        if (f0 == 0) {
+        // the next super-chunk reuses the arena and the staging buffers: drain everything first
+        ORB_CUDA(cudaStreamSynchronize(e->streamOut));
+        ORB_CUDA(cudaStreamSynchronize(e->stream));
+        if (s0 == 0) {
             float ms;
             for (int i = 0; i < 3; ++i)
                 if (cudaEventElapsedTime(&ms, e->ev[i], e->ev[i + 1]) == cudaSuccess) e->stageMs[i] = ms;
         }
-        for (int f = 0; f < nf; ++f)
-            if (nOut[f0 + f] > capacity) {
-                status = fail(ORB_ERR_CAPACITY, "frame %d has %d keypoints, capacity %d (see orbx_keypoint_capacity)", f0 + f,
-                              nOut[f0 + f], capacity);
-                nOut[f0 + f] = capacity;
+        for (int f = 0; f < ns; ++f)
+            if (nOut[s0 + f] > capacity) {
+                status = fail(ORB_ERR_CAPACITY, "frame %d has %d keypoints, capacity %d (see orbx_keypoint_capacity)", s0 + f,
+                              nOut[s0 + f], capacity);
+                nOut[s0 + f] = capacity;
             }
     }
+    e->lastFrames = std::max(e->lastFrames, 1);
     return status;
 }
 
