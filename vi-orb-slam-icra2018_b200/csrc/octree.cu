@@ -329,15 +329,19 @@ octree_kernel(const __grid_constant__ ExtractParams P, int nodeCap, int cellCap,
         const int u = lane - kHalfPatch;
         int m10 = 0, m01 = 0;
         if (lane < kPatch) {
+            // all 31 row loads are issued before the first use (the loop is latency-bound otherwise)
             const int au = u < 0 ? -u : u;
-#pragma unroll 1
+            int val[kPatch];
+#pragma unroll
+            for (int v = -kHalfPatch; v <= kHalfPatch; ++v)
+                val[v + kHalfPatch] = (au <= P.umax[v < 0 ? -v : v]) ? (int)c[v * L.pitch + u] : 0;
+            int rowSum = 0;
+#pragma unroll
             for (int v = -kHalfPatch; v <= kHalfPatch; ++v) {
-                if (au <= P.umax[v < 0 ? -v : v]) {
-                    const int val = c[v * L.pitch + u];
-                    m10 += u * val;
-                    m01 += v * val;
-                }
+                rowSum += val[v + kHalfPatch];
+                m01 += v * val[v + kHalfPatch];
             }
+            m10 = u * rowSum;
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {

@@ -7,10 +7,19 @@
 // the host with the exact float recipe, see extractor.cu), horizontal sums kept at 19 bits, vertical pass
 // (((b0*(T0>>4))>>16) + ((b1*(T1>>4))>>16) + 2) >> 2.  The kernels write the 19-px reflect-101 frame in the same pass
 // by evaluating the reflected interior coordinate, so the border costs no extra launch and no read-after-write.
-// Each thread produces 4 horizontally adjacent bytes and stores one 32-bit word (rows are 16-byte aligned).
+//
+// Shape (the first version was issue-bound at ~45 instructions per pixel): a thread owns 4 horizontally adjacent output
+// bytes (one aligned 32-bit store) and walks down 8 output rows, so the per-column table entries, byte offsets and
+// funnel-shift amounts are loop invariants.  Per source row it loads three aligned words, funnel-shifts each pixel's
+// two source bytes into place and forms the horizontal sum with ONE IDP.2A (16-bit coefficient pair x two bytes).
+// Reading S[x+1] / row y+1 one past the level is harmless: the table's coefficient there is 0 and the source level
+// has its own frame.  Threads that touch the left/right frame take the per-pixel reflected path.
 #include "extractor.h"
 
 namespace orbb {
+
+constexpr int PY_ROWS = 16;   // output rows per thread
+constexpr int PY_TY = 4;      // row bands per CTA
 
 __device__ __forceinline__ int reflect101(int i, int n) {
     if (i < 0) i = -i;
@@ -18,64 +27,132 @@ __device__ __forceinline__ int reflect101(int i, int n) {
     return i;
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(32 * PY_TY)
 pyramid_level0_kernel(const unsigned char* __restrict__ images, int w, int h, int stride, size_t frameStride,
                       unsigned char* __restrict__ pyr, long long pyrFrameBytes, long long pyrOff, int pitch) {
-    const int bx = (blockIdx.x * 64 + threadIdx.x) * 4;
-    const int by = blockIdx.y * 4 + threadIdx.y;
-    if (bx >= pitch || by >= h + 2 * kEdge) return;
-    const unsigned char* src = images + (size_t)blockIdx.z * frameStride + (size_t)reflect101(by - kEdge, h) * stride;
-    unsigned int word = 0;
+    const int bx = (blockIdx.x * 32 + threadIdx.x) * 4;
+    if (bx >= pitch) return;
+    const int lx0 = bx - kPadLeft;
+    const unsigned char* img = images + (size_t)blockIdx.z * frameStride;
+    unsigned char* dst = pyr + (size_t)blockIdx.z * pyrFrameBytes + pyrOff + bx;
+    const bool wordCopy = lx0 >= 0 && lx0 + 3 < w && (((size_t)img | (size_t)stride) & 3) == 0;
+    const int by0 = (blockIdx.y * PY_TY + threadIdx.y) * PY_ROWS;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int lx = bx + k - kPadLeft;
-        unsigned int v = 0;
-        if (lx >= -kEdge && lx < w + kEdge) v = __ldg(src + reflect101(lx, w));
-        word |= v << (8 * k);
+    for (int r = 0; r < PY_ROWS; ++r) {
+        const int by = by0 + r;
+        if (by >= h + 2 * kEdge) break;
+        const unsigned char* src = img + (size_t)reflect101(by - kEdge, h) * stride;
+        unsigned int word;
+        if (wordCopy) {
+            word = __ldg(reinterpret_cast<const unsigned int*>(src + lx0));
+        } else {
+            word = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int lx = lx0 + k;
+                unsigned int v = 0;
+                if (lx >= -kEdge && lx < w + kEdge) v = __ldg(src + reflect101(lx, w));
+                word |= v << (8 * k);
+            }
+        }
+        *reinterpret_cast<unsigned int*>(dst + (size_t)by * pitch) = word;
     }
-    unsigned char* dst = pyr + (size_t)blockIdx.z * pyrFrameBytes + pyrOff + (size_t)by * pitch + bx;
-    *reinterpret_cast<unsigned int*>(dst) = word;
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(32 * PY_TY)
 pyramid_resize_kernel(unsigned char* __restrict__ pyr, long long pyrFrameBytes, long long srcOff, int srcPitch, int sw,
                       int sh, long long dstOff, int dstPitch, int dw, int dh, const int* __restrict__ xofs,
-                      const short2* __restrict__ xcoef, const int* __restrict__ yofs, const short2* __restrict__ ycoef) {
-    const int bx = (blockIdx.x * 64 + threadIdx.x) * 4;
-    const int by = blockIdx.y * 4 + threadIdx.y;
-    if (bx >= dstPitch || by >= dh + 2 * kEdge) return;
+                      const unsigned int* __restrict__ xcoef, const int* __restrict__ yofs, const short2* __restrict__ ycoef) {
+    const int bx = (blockIdx.x * 32 + threadIdx.x) * 4;
+    if (bx >= dstPitch) return;
+    const int lx0 = bx - kPadLeft;
     unsigned char* frame = pyr + (size_t)blockIdx.z * pyrFrameBytes;
-    const int dy = reflect101(by - kEdge, dh);
-    const int sy0 = __ldg(yofs + dy);
-    const int sy1 = min(sy0 + 1, sh - 1);
-    const short2 b = __ldg(ycoef + dy);
-    const unsigned char* r0 = frame + srcOff + (size_t)(sy0 + kEdge) * srcPitch + kPadLeft;
-    const unsigned char* r1 = frame + srcOff + (size_t)(sy1 + kEdge) * srcPitch + kPadLeft;
-    unsigned int word = 0;
+    const unsigned char* src0 = frame + srcOff + (size_t)kEdge * srcPitch + kPadLeft;   // source level pixel (0,0)
+    unsigned char* dst = frame + dstOff + bx;
+
+    // per-column invariants
+    unsigned int cf[4];
+    int shiftBits[4], rel[4];
+    bool hiWin[4];
+    int base = 0;
+    bool fast = lx0 >= 0 && lx0 + 3 < dw;
+    if (fast) {
+        const int o0 = __ldg(xofs + lx0);
+        base = o0 & ~3;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int lx = bx + k - kPadLeft;
-        unsigned int v = 0;
-        if (lx >= -kEdge && lx < dw + kEdge) {
-            const int dx = reflect101(lx, dw);
-            const int x0 = __ldg(xofs + dx);
-            const int x1 = min(x0 + 1, sw - 1);
-            const short2 a = __ldg(xcoef + dx);
-            const int t0 = (int)r0[x0] * a.x + (int)r0[x1] * a.y;
-            const int t1 = (int)r1[x0] * a.x + (int)r1[x1] * a.y;
-            v = (unsigned int)(((((int)b.x * (t0 >> 4)) >> 16) + (((int)b.y * (t1 >> 4)) >> 16) + 2) >> 2);
+        for (int k = 0; k < 4; ++k) {
+            rel[k] = __ldg(xofs + lx0 + k) - base;
+            cf[k] = __ldg(xcoef + lx0 + k);           // a0 | a1 << 16
+            hiWin[k] = rel[k] >= 4;
+            shiftBits[k] = (rel[k] & 3) * 8;
         }
-        word |= (v & 0xffu) << (8 * k);
+        fast = rel[3] <= 7;                           // both source bytes of every pixel inside the 12-byte window
     }
-    *reinterpret_cast<unsigned int*>(frame + dstOff + (size_t)by * dstPitch + bx) = word;
+    const int by0 = (blockIdx.y * PY_TY + threadIdx.y) * PY_ROWS;
+    const int rowsTotal = dh + 2 * kEdge;
+    if (fast) {
+        // the common case; kept in its own loop so that nothing of the per-pixel border path is hoisted into it
+#pragma unroll 2
+        for (int r = 0; r < PY_ROWS; ++r) {
+            const int by = by0 + r;
+            if (by >= rowsTotal) break;
+            const int dy = reflect101(by - kEdge, dh);
+            const int sy0 = __ldg(yofs + dy);
+            const short2 b = __ldg(ycoef + dy);
+            const unsigned int* p0 = reinterpret_cast<const unsigned int*>(src0 + (size_t)sy0 * srcPitch + base);
+            const unsigned int* p1 = reinterpret_cast<const unsigned int*>(reinterpret_cast<const unsigned char*>(p0) + srcPitch);
+            const unsigned int a0 = __ldg(p0), a1 = __ldg(p0 + 1), a2 = __ldg(p0 + 2);
+            const unsigned int c0 = __ldg(p1), c1 = __ldg(p1 + 1), c2 = __ldg(p1 + 2);
+            unsigned int word = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const unsigned int v0 = __funnelshift_r(hiWin[k] ? a1 : a0, hiWin[k] ? a2 : a1, shiftBits[k]);
+                const unsigned int v1 = __funnelshift_r(hiWin[k] ? c1 : c0, hiWin[k] ? c2 : c1, shiftBits[k]);
+                const int t0 = (int)__dp2a_lo(cf[k], v0, 0u);     // S[x0]*a0 + S[x0+1]*a1
+                const int t1 = (int)__dp2a_lo(cf[k], v1, 0u);
+                const unsigned int v = (unsigned int)(((((int)b.x * (t0 >> 4)) >> 16) + (((int)b.y * (t1 >> 4)) >> 16) + 2) >> 2);
+                word |= (v & 0xffu) << (8 * k);
+            }
+            *reinterpret_cast<unsigned int*>(dst + (size_t)by * dstPitch) = word;
+        }
+        return;
+    }
+    // threads that touch the left/right frame (or an unusual scale factor): per-pixel reflected coordinates
+#pragma unroll 1
+    for (int r = 0; r < PY_ROWS; ++r) {
+        const int by = by0 + r;
+        if (by >= rowsTotal) break;
+        const int dy = reflect101(by - kEdge, dh);
+        const int sy0 = __ldg(yofs + dy);
+        const short2 b = __ldg(ycoef + dy);
+        const unsigned char* r0 = src0 + (size_t)sy0 * srcPitch;
+        const unsigned char* r1 = r0 + srcPitch;      // row sh is the source's own frame when sy0 == sh-1 (b.y == 0 there)
+        unsigned int word = 0;
+#pragma unroll 1
+        for (int k = 0; k < 4; ++k) {
+            const int lx = lx0 + k;
+            unsigned int v = 0;
+            if (lx >= -kEdge && lx < dw + kEdge) {
+                const int dx = reflect101(lx, dw);
+                const int x0 = __ldg(xofs + dx);
+                const unsigned int a = __ldg(xcoef + dx);
+                const int ax = (int)(a & 0xffffu), ay = (int)(a >> 16);
+                const int t0 = (int)r0[x0] * ax + (int)r0[x0 + 1] * ay;
+                const int t1 = (int)r1[x0] * ax + (int)r1[x0 + 1] * ay;
+                v = (unsigned int)(((((int)b.x * (t0 >> 4)) >> 16) + (((int)b.y * (t1 >> 4)) >> 16) + 2) >> 2);
+            }
+            word |= (v & 0xffu) << (8 * k);
+        }
+        *reinterpret_cast<unsigned int*>(dst + (size_t)by * dstPitch) = word;
+    }
 }
 
 int launch_pyramid(const ExtractParams& P, const unsigned char* dImages, int width, int height, int stride,
                    size_t frameStride, cudaStream_t st, int* launches) {
-    const dim3 block(64, 4);
+    const dim3 block(32, PY_TY);
     {
         const LevelGeom& L = P.lv[0];
-        dim3 grid(ceil_div(L.pitch, 256), ceil_div(L.h + 2 * kEdge, 4), P.nFrames);
+        dim3 grid(ceil_div(L.pitch, 128), ceil_div(L.h + 2 * kEdge, PY_TY * PY_ROWS), P.nFrames);
         pyramid_level0_kernel<<<grid, block, 0, st>>>(dImages, width, height, stride, frameStride, P.pyr, P.pyrFrameBytes,
                                                       L.pyrOff, L.pitch);
         ++*launches;
@@ -83,9 +160,10 @@ int launch_pyramid(const ExtractParams& P, const unsigned char* dImages, int wid
     for (int l = 1; l < P.nLevels; ++l) {
         const LevelGeom& S = P.lv[l - 1];
         const LevelGeom& D = P.lv[l];
-        dim3 grid(ceil_div(D.pitch, 256), ceil_div(D.h + 2 * kEdge, 4), P.nFrames);
+        dim3 grid(ceil_div(D.pitch, 128), ceil_div(D.h + 2 * kEdge, PY_TY * PY_ROWS), P.nFrames);
         pyramid_resize_kernel<<<grid, block, 0, st>>>(P.pyr, P.pyrFrameBytes, S.pyrOff, S.pitch, S.w, S.h, D.pyrOff,
-                                                      D.pitch, D.w, D.h, P.tabOfs + D.xTab, P.tabCoef + D.xTab,
+                                                      D.pitch, D.w, D.h, P.tabOfs + D.xTab,
+                                                      reinterpret_cast<const unsigned int*>(P.tabCoef + D.xTab),
                                                       P.tabOfs + D.yTab, P.tabCoef + D.yTab);
         ++*launches;
     }
