@@ -39,6 +39,7 @@ struct orbx_extractor {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t streamIn = nullptr, streamOut = nullptr;   // H2D / D2H of the host entry points, overlapped with compute
+    cudaStream_t stream2 = nullptr;                          // second compute stream: odd pipeline chunks, fills kernel tails
     std::vector<cudaEvent_t> pipeEvents;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     // ctor state
@@ -325,6 +326,7 @@ int orbx_create(int nfeatures, float scaleFactor, int nlevels, int iniTh, int mi
     cudaError_t ce = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
     if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&e->streamIn, cudaStreamNonBlocking);
     if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&e->streamOut, cudaStreamNonBlocking);
+    if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking);
     for (int i = 0; i < 4 && ce == cudaSuccess; ++i) ce = cudaEventCreate(&e->ev[i]);
     if (ce != cudaSuccess) {
         delete e;
@@ -353,6 +355,7 @@ int orbx_destroy(orbx_handle e) {
     for (cudaEvent_t ev : e->pipeEvents) cudaEventDestroy(ev);
     if (e->streamIn) cudaStreamDestroy(e->streamIn);
     if (e->streamOut) cudaStreamDestroy(e->streamOut);
+    if (e->stream2) cudaStreamDestroy(e->stream2);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
     return ORB_OK;
@@ -424,12 +427,13 @@ int orbx_extract_batch(orbx_handle e, const uint8_t* images, int nFrames, int w,
                 ORB_CUDA(cudaMemcpy2DAsync(dImg, imgBytes, src, frameStride, imgBytes, nf, cudaMemcpyHostToDevice, e->streamIn));
             }
             ORB_CUDA(cudaEventRecord(e->pipeEvents[2 * k], e->streamIn));
-            ORB_CUDA(cudaStreamWaitEvent(e->stream, e->pipeEvents[2 * k], 0));
+            cudaStream_t cs = (k & 1) ? e->stream2 : e->stream;   // chunks own disjoint arena slots, so they may overlap
+            ORB_CUDA(cudaStreamWaitEvent(cs, e->pipeEvents[2 * k], 0));
             orb_keypoint* dK = e->dKps.as<orb_keypoint>() + (size_t)f0 * capacity;
             uint8_t* dD = e->dDesc.as<uint8_t>() + (size_t)f0 * capacity * 32;
             int* dN = e->dCount.as<int>() + f0;
-            ORB_CHECK(enqueue(e, dImg, nf, w, h, stride, imgBytes, dK, dD, capacity, dN, e->stream, s0 == 0 && f0 == 0, f0));
-            ORB_CUDA(cudaEventRecord(e->pipeEvents[2 * k + 1], e->stream));
+            ORB_CHECK(enqueue(e, dImg, nf, w, h, stride, imgBytes, dK, dD, capacity, dN, cs, s0 == 0 && f0 == 0, f0));
+            ORB_CUDA(cudaEventRecord(e->pipeEvents[2 * k + 1], cs));
             ORB_CUDA(cudaStreamWaitEvent(e->streamOut, e->pipeEvents[2 * k + 1], 0));
             const size_t o = (size_t)(s0 + f0);
             ORB_CUDA(cudaMemcpyAsync(nOut + o, dN, (size_t)nf * 4, cudaMemcpyDeviceToHost, e->streamOut));
@@ -439,6 +443,7 @@ int orbx_extract_batch(orbx_handle e, const uint8_t* images, int nFrames, int w,
         // the next super-chunk reuses the arena and the staging buffers: drain everything first
         ORB_CUDA(cudaStreamSynchronize(e->streamOut));
         ORB_CUDA(cudaStreamSynchronize(e->stream));
+        ORB_CUDA(cudaStreamSynchronize(e->stream2));
         if (s0 == 0) {
             float ms;
             for (int i = 0; i < 3; ++i)

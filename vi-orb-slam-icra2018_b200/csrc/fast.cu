@@ -43,12 +43,13 @@ constexpr int BM_WORDS = (kCellMax * kCellMax + 31) / 32;   // 113
      : (k) == 12 ? -3 : (k) == 13 ? TPX - 3 : (k) == 14 ? 2 * TPX - 2 : 3 * TPX - 1)
 
 struct FastShared {
-    unsigned int tile[TILE_ROWS * TPX / 2];                 // 16-bit pixels, two per word
+    unsigned int tile[TILE_ROWS * TPX / 2];                 // 16-bit pixels, two per word; reused as survivor list after B
     unsigned int score[SC_ROWS * SC_PITCH / 4];             // uint8 scores with a zero ring
-    unsigned short queue[kCellMax * kCellMax];              // x | y<<6 | alive<<12 | max<<13 | ini<<14
+    unsigned short queue[kCellMax * kCellMax];              // pixels that pass the necessary test: x | y<<6
+    unsigned short alive[kCellMax * kCellMax];              // corners (S >= minTh): x | y<<6 | ini<<14
     unsigned int bmMin[BM_WORDS + 1], bmIni[BM_WORDS + 1];  // survivors at minTh / iniTh, bit = y*cw + x
     int prefix[BM_WORDS + 1];
-    int queueLen;
+    int queueLen, aliveLen, survLen;
     int anyIni;
 };
 
@@ -75,17 +76,19 @@ __device__ __forceinline__ int fast_score(const unsigned short* c) {
     return max(lo, hi) - 1;
 }
 
-// one opposing circle pair for two pixel pairs: running min of the pair maxima and max of the pair minima
-__device__ __forceinline__ void pair_step(unsigned int a, unsigned int b, unsigned int& minOfMax, unsigned int& maxOfMin) {
-    minOfMax = __vminu2(minOfMax, __vmaxu2(a, b));   // DPX VIMNMX.U16x2
-    maxOfMin = __vmaxu2(maxOfMin, __vminu2(a, b));
+// per-half test of the necessary condition: bright possible (mm >= v+t+1) or dark possible (v >= nn+t+1); 2 result bits
+__device__ __forceinline__ unsigned int pass_bits(unsigned int mm, unsigned int nn, unsigned int c, unsigned int T1) {
+    bool bh, bl, dh, dl;
+    __vibmax_u16x2(mm, c + T1, &bh, &bl);
+    __vibmax_u16x2(c, nn + T1, &dh, &dl);
+    return ((bl | dl) ? 1u : 0u) | ((bh | dh) ? 2u : 0u);
 }
 
-__global__ void __launch_bounds__(FAST_THREADS, 8) fast_cells_kernel(const __grid_constant__ ExtractParams P) {
+__global__ void __launch_bounds__(FAST_THREADS, 7) fast_cells_kernel(const __grid_constant__ ExtractParams P) {
     __shared__ __align__(16) FastShared S;
     const Cell cell = P.cells[blockIdx.x];
     const LevelGeom& L = P.lv[cell.level];
-    const int frame = blockIdx.y, tid = threadIdx.x;
+    const int frame = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
     const int cw = cell.cw, ch = cell.ch;
     const unsigned char* level0 = P.pyr + (size_t)frame * P.pyrFrameBytes + L.pyrOff + (size_t)kEdge * L.pitch + kPadLeft;
 
@@ -95,58 +98,39 @@ __global__ void __launch_bounds__(FAST_THREADS, 8) fast_cells_kernel(const __gri
         const int tx0 = cell.x0 - 4, ty0 = cell.y0 - 3;
         const int shift8 = ((tx0 + kPadLeft) & 3) * 8;
         const int quads = (cw + 8 + 3) >> 2;                 // 4-pixel groups per tile row (<= 17)
+        const unsigned int rq = (65536u + quads - 1) / quads;   // i / quads == (i * rq) >> 16 for i * quads < 65536
         const unsigned char* src = level0 + (long long)ty0 * L.pitch + (tx0 - (shift8 >> 3));
         uint2* tile64 = reinterpret_cast<uint2*>(S.tile);
         for (int i = tid; i < (ch + 6) * quads; i += FAST_THREADS) {
-            const int r = i / quads, q = i - r * quads;
+            const int r = (int)(((unsigned int)i * rq) >> 16), q = i - r * quads;
             const unsigned int* g = reinterpret_cast<const unsigned int*>(src + (size_t)r * L.pitch) + q;
-            const unsigned int w0 = __ldg(g), w1 = shift8 ? __ldg(g + 1) : 0u;
+            const unsigned int w0 = __ldg(g), w1 = __ldg(g + 1);
             const unsigned int px = __funnelshift_r(w0, w1, shift8);
             tile64[r * (TPX / 4) + q] = make_uint2(__byte_perm(px, 0, 0x4140), __byte_perm(px, 0, 0x4342));
         }
-        for (int i = tid; i < SC_ROWS * SC_PITCH / 4; i += FAST_THREADS) S.score[i] = 0;
-        for (int i = tid; i < BM_WORDS + 1; i += FAST_THREADS) { S.bmMin[i] = 0; S.bmIni[i] = 0; }
-        if (tid == 0) { S.queueLen = 0; S.anyIni = 0; }
+        uint4* sc4 = reinterpret_cast<uint4*>(S.score);
+        for (int i = tid; i < (ch + 2) * (SC_PITCH / 16); i += FAST_THREADS) sc4[i] = make_uint4(0, 0, 0, 0);
+        for (int i = tid; i < ((cw * ch + 31) >> 5) + 1; i += FAST_THREADS) { S.bmMin[i] = 0; S.bmIni[i] = 0; }
+        if (tid == 0) { S.queueLen = 0; S.aliveLen = 0; S.survLen = 0; S.anyIni = 0; }
     }
     __syncthreads();
 
-    // ---- A. necessary test, 4 pixels (two 16x2 pairs) per thread
+    // ---- A. necessary test, 4 pixels (two 16x2 pairs) per thread; warp-uniform loop so that a warp whose 128 pixels
+    //         all fail after the three middle-row pairs skips the other five
     {
-        const int groups = (cw + 3) >> 2;
+        const int groups = (cw + 3) >> 2, total = groups * ch;
+        const unsigned int rg = (65536u + groups - 1) / groups;
         const unsigned int T1 = (unsigned int)(P.minTh + 1) * 0x00010001u;
         const uint2* tile64 = reinterpret_cast<const uint2*>(S.tile);
-        for (int i = tid; i < groups * ch; i += FAST_THREADS) {
-            const int y = i / groups, g = i - y * groups;
+        for (int i0 = tid - lane; i0 < total; i0 += FAST_THREADS) {
+            const int i = min(i0 + lane, total - 1);
+            const bool valid = i0 + lane < total;
+            const int y = (int)(((unsigned int)i * rg) >> 16), g = i - y * groups;
             const uint2* row = tile64 + (y + 3) * (TPX / 4) + g;   // row[0] = pixels x0-4..x0-1, row[1] = x0..x0+3, row[2] = x0+4..
-            // A = pixels (x0, x0+1), B = (x0+2, x0+3); "min of pair maxima" must exceed v+t, "max of pair minima" stay below v-t
-            unsigned int mmA = 0xffffffffu, mmB = 0xffffffffu, nnA = 0u, nnB = 0u;
-            {   // rows +-3: dx = 0, +1, -1  -> circle points 0/8, 1/9, 15/7
-                const uint2* up = row - 3 * (TPX / 4);
-                const uint2* dn = row + 3 * (TPX / 4);
-                const unsigned int u1 = up[0].y, u4 = up[2].x, d1 = dn[0].y, d4 = dn[2].x;
-                const uint2 uc = up[1], dc = dn[1];
-                pair_step(dc.x, uc.x, mmA, nnA);                                   // k=0 (0,3) with k=8 (0,-3)
-                pair_step(dc.y, uc.y, mmB, nnB);
-                const unsigned int uf12 = __funnelshift_r(u1, uc.x, 16), uf23 = __funnelshift_r(uc.x, uc.y, 16),
-                                   uf34 = __funnelshift_r(uc.y, u4, 16);
-                const unsigned int df12 = __funnelshift_r(d1, dc.x, 16), df23 = __funnelshift_r(dc.x, dc.y, 16),
-                                   df34 = __funnelshift_r(dc.y, d4, 16);
-                pair_step(df23, uf12, mmA, nnA);                                   // k=1 (1,3) with k=9 (-1,-3)
-                pair_step(df34, uf23, mmB, nnB);
-                pair_step(uf23, df12, mmA, nnA);                                   // k=7 (1,-3) with k=15 (-1,3)
-                pair_step(uf34, df23, mmB, nnB);
-            }
-            {   // rows +-2: dx = +-2 -> circle points 2/10, 6/14; no shifts
-                const uint2* up = row - 2 * (TPX / 4);
-                const uint2* dn = row + 2 * (TPX / 4);
-                const unsigned int u1 = up[0].y, u4 = up[2].x, d1 = dn[0].y, d4 = dn[2].x;
-                const uint2 uc = up[1], dc = dn[1];
-                pair_step(dc.y, u1, mmA, nnA);                                     // k=2 (2,2) with k=10 (-2,-2)
-                pair_step(d4, uc.x, mmB, nnB);
-                pair_step(uc.y, d1, mmA, nnA);                                     // k=6 (2,-2) with k=14 (-2,2)
-                pair_step(u4, dc.x, mmB, nnB);
-            }
-            unsigned int cA, cB;
+            // A = pixels (x0, x0+1), B = (x0+2, x0+3). M = pair maxima, m = pair minima of the opposing circle points
+            unsigned int MA[8], MB[8], mA[8], mB[8], cA, cB;
+#define PAIR(j, aA, bA, aB, bB)                                                            \
+    MA[j] = __vmaxu2(aA, bA); mA[j] = __vminu2(aA, bA); MB[j] = __vmaxu2(aB, bB); mB[j] = __vminu2(aB, bB);
             {   // rows +-1 and 0: dx = +-3 -> circle points 3/11, 5/13, 4/12
                 const uint2* up = row - (TPX / 4);
                 const uint2* dn = row + (TPX / 4);
@@ -160,23 +144,44 @@ __global__ void __launch_bounds__(FAST_THREADS, 8) fast_cells_kernel(const __gri
                 const unsigned int dMA = __funnelshift_r(dl.x, dl.y, 16), dMB = __funnelshift_r(dl.y, dc.x, 16);
                 const unsigned int mPA = __funnelshift_r(mc.y, mr.x, 16), mPB = __funnelshift_r(mr.x, mr.y, 16);
                 const unsigned int mMA = __funnelshift_r(ml.x, ml.y, 16), mMB = __funnelshift_r(ml.y, mc.x, 16);
-                pair_step(dPA, uMA, mmA, nnA);                                     // k=3 (3,1) with k=11 (-3,-1)
-                pair_step(dPB, uMB, mmB, nnB);
-                pair_step(uPA, dMA, mmA, nnA);                                     // k=5 (3,-1) with k=13 (-3,1)
-                pair_step(uPB, dMB, mmB, nnB);
-                pair_step(mPA, mMA, mmA, nnA);                                     // k=4 (3,0) with k=12 (-3,0)
-                pair_step(mPB, mMB, mmB, nnB);
+                PAIR(0, dPA, uMA, dPB, uMB)                                        // k=3 (3,1) with k=11 (-3,-1)
+                PAIR(1, uPA, dMA, uPB, dMB)                                        // k=5 (3,-1) with k=13 (-3,1)
+                PAIR(2, mPA, mMA, mPB, mMB)                                        // k=4 (3,0) with k=12 (-3,0)
             }
-            // bright possible: mm >= v + t + 1 ; dark possible: v >= nn + t + 1   (per 16-bit half, values < 1024)
-            bool bAh, bAl, bBh, bBl, dAh, dAl, dBh, dBl;
-            __vibmax_u16x2(mmA, cA + T1, &bAh, &bAl);
-            __vibmax_u16x2(mmB, cB + T1, &bBh, &bBl);
-            __vibmax_u16x2(cA, nnA + T1, &dAh, &dAl);
-            __vibmax_u16x2(cB, nnB + T1, &dBh, &dBl);
+            unsigned int mmA = __vimin3_u16x2(MA[0], MA[1], MA[2]), mmB = __vimin3_u16x2(MB[0], MB[1], MB[2]);
+            unsigned int nnA = __vimax3_u16x2(mA[0], mA[1], mA[2]), nnB = __vimax3_u16x2(mB[0], mB[1], mB[2]);
+            unsigned int flags = pass_bits(mmA, nnA, cA, T1) | (pass_bits(mmB, nnB, cB, T1) << 2);
+            if (!__any_sync(0xffffffffu, valid && flags)) continue;
+            {   // rows +-3: dx = 0, +1, -1  -> circle points 0/8, 1/9, 15/7
+                const uint2* up = row - 3 * (TPX / 4);
+                const uint2* dn = row + 3 * (TPX / 4);
+                const unsigned int u1 = up[0].y, u4 = up[2].x, d1 = dn[0].y, d4 = dn[2].x;
+                const uint2 uc = up[1], dc = dn[1];
+                const unsigned int uf12 = __funnelshift_r(u1, uc.x, 16), uf23 = __funnelshift_r(uc.x, uc.y, 16),
+                                   uf34 = __funnelshift_r(uc.y, u4, 16);
+                const unsigned int df12 = __funnelshift_r(d1, dc.x, 16), df23 = __funnelshift_r(dc.x, dc.y, 16),
+                                   df34 = __funnelshift_r(dc.y, d4, 16);
+                PAIR(3, dc.x, uc.x, dc.y, uc.y)                                    // k=0 (0,3) with k=8 (0,-3)
+                PAIR(4, df23, uf12, df34, uf23)                                    // k=1 (1,3) with k=9 (-1,-3)
+                PAIR(5, uf23, df12, uf34, df23)                                    // k=7 (1,-3) with k=15 (-1,3)
+            }
+            {   // rows +-2: dx = +-2 -> circle points 2/10, 6/14; no shifts
+                const uint2* up = row - 2 * (TPX / 4);
+                const uint2* dn = row + 2 * (TPX / 4);
+                const unsigned int u1 = up[0].y, u4 = up[2].x, d1 = dn[0].y, d4 = dn[2].x;
+                const uint2 uc = up[1], dc = dn[1];
+                PAIR(6, dc.y, u1, d4, uc.x)                                        // k=2 (2,2) with k=10 (-2,-2)
+                PAIR(7, uc.y, d1, u4, dc.x)                                        // k=6 (2,-2) with k=14 (-2,2)
+            }
+#undef PAIR
+            mmA = __vimin3_u16x2(mmA, __vimin3_u16x2(MA[3], MA[4], MA[5]), __vminu2(MA[6], MA[7]));
+            mmB = __vimin3_u16x2(mmB, __vimin3_u16x2(MB[3], MB[4], MB[5]), __vminu2(MB[6], MB[7]));
+            nnA = __vimax3_u16x2(nnA, __vimax3_u16x2(mA[3], mA[4], mA[5]), __vmaxu2(mA[6], mA[7]));
+            nnB = __vimax3_u16x2(nnB, __vimax3_u16x2(mB[3], mB[4], mB[5]), __vmaxu2(mB[6], mB[7]));
             const int x0 = 4 * g;
-            unsigned int flags = ((bAl | dAl) ? 1u : 0u) | ((bAh | dAh) ? 2u : 0u) | ((bBl | dBl) ? 4u : 0u) | ((bBh | dBh) ? 8u : 0u);
+            flags = pass_bits(mmA, nnA, cA, T1) | (pass_bits(mmB, nnB, cB, T1) << 2);
             flags &= (1u << min(4, cw - x0)) - 1u;
-            if (flags) {
+            if (valid && flags) {
                 int pos = atomicAdd(&S.queueLen, __popc(flags));
                 const unsigned int base = (unsigned int)x0 | ((unsigned int)y << 6);
 #pragma unroll
@@ -187,7 +192,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 8) fast_cells_kernel(const __gri
     }
     __syncthreads();
 
-    // ---- B. exact score for the queue
+    // ---- B. exact score for the queue; corners go to the dense `alive` list
     const int qn = S.queueLen;
     const unsigned short* tile16 = reinterpret_cast<const unsigned short*>(S.tile);
     unsigned char* score = reinterpret_cast<unsigned char*>(S.score);
@@ -197,15 +202,16 @@ __global__ void __launch_bounds__(FAST_THREADS, 8) fast_cells_kernel(const __gri
         const int s = fast_score(tile16 + (y + 3) * TPX + x + 4);
         if (s >= P.minTh) {
             score[(y + 1) * SC_PITCH + x + 1] = (unsigned char)s;
-            S.queue[q] = (unsigned short)(e | 0x1000u | (s >= P.iniTh ? 0x4000u : 0u));
+            S.alive[atomicAdd(&S.aliveLen, 1)] = (unsigned short)(e | (s >= P.iniTh ? 0x4000u : 0u));
         }
     }
     __syncthreads();
 
-    // ---- C. per-cell NMS on the corners
-    for (int q = tid; q < qn; q += FAST_THREADS) {
-        const unsigned int e = S.queue[q];
-        if (!(e & 0x1000u)) continue;
+    // ---- C. per-cell NMS on the corners; survivors are listed (in the tile, no longer needed) and set bitmap bits
+    const int an = S.aliveLen;
+    unsigned short* surv = reinterpret_cast<unsigned short*>(S.tile);
+    for (int q = tid; q < an; q += FAST_THREADS) {
+        const unsigned int e = S.alive[q];
         const int x = e & 63, y = (e >> 6) & 63;
         const unsigned char* sc = score + (y + 1) * SC_PITCH + x + 1;
         const int s = sc[0];
@@ -218,7 +224,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 8) fast_cells_kernel(const __gri
                 atomicOr(&S.bmIni[bit >> 5], 1u << (bit & 31));
                 S.anyIni = 1;
             }
-            S.queue[q] = (unsigned short)(e | 0x2000u);
+            surv[atomicAdd(&S.survLen, 1)] = (unsigned short)e;
         }
     }
     __syncthreads();
@@ -226,30 +232,31 @@ __global__ void __launch_bounds__(FAST_THREADS, 8) fast_cells_kernel(const __gri
     // ---- D. rank table of the chosen threshold's survivors (row-major order == bit order)
     const bool useIni = S.anyIni != 0;
     const unsigned int* bm = useIni ? S.bmIni : S.bmMin;
+    const int bmWords = ((cw * ch + 31) >> 5) + 1;
     if (tid < 32) {
         int carry = 0;
-        for (int base = 0; base < BM_WORDS + 1; base += 32) {
+        for (int base = 0; base < bmWords; base += 32) {
             const int w = base + tid;
-            const int c = w < BM_WORDS + 1 ? __popc(bm[w]) : 0;
+            const int c = w < bmWords ? __popc(bm[w]) : 0;
             int incl = c;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const int t = __shfl_up_sync(0xffffffffu, incl, o);
                 if (tid >= o) incl += t;
             }
-            if (w < BM_WORDS + 1) S.prefix[w] = carry + incl - c;
+            if (w < bmWords) S.prefix[w] = carry + incl - c;
             carry += __shfl_sync(0xffffffffu, incl, 31);
         }
         if (tid == 0) P.cellCount[(size_t)frame * P.nCellsTotal + blockIdx.x] = carry;
     }
     __syncthreads();
 
-    // ---- E. survivors store themselves at their rank
+    // ---- E. survivors of the chosen threshold store themselves at their rank
     unsigned int* slot = P.slots + (size_t)frame * P.slotFrameEntries + cell.slot;
-    const unsigned int need = useIni ? 0x6000u : 0x2000u;
-    for (int q = tid; q < qn; q += FAST_THREADS) {
-        const unsigned int e = S.queue[q];
-        if ((e & need) != need) continue;
+    const int sn = S.survLen;
+    for (int q = tid; q < sn; q += FAST_THREADS) {
+        const unsigned int e = surv[q];
+        if (useIni && !(e & 0x4000u)) continue;
         const int x = e & 63, y = (e >> 6) & 63;
         const int bit = y * cw + x;
         const int rank = S.prefix[bit >> 5] + __popc(bm[bit >> 5] & ((1u << (bit & 31)) - 1u));
