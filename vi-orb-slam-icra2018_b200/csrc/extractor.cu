@@ -184,6 +184,9 @@ int configure(orbx_extractor* e, int w, int h, int nFrames) {
     P.iniTh = e->iniTh;
     P.minTh = e->minTh;
     P.nCellsTotal = (int)cells.size();
+    P.maxCellW = 1;
+    P.maxCellH = 1;
+    for (const Cell& c : cells) { P.maxCellW = std::max(P.maxCellW, (int)c.cw); P.maxCellH = std::max(P.maxCellH, (int)c.ch); }
     P.selPerFrame = selOff;
     P.pyrFrameBytes = pyrOff;
     P.blurFrameBytes = blurOff;

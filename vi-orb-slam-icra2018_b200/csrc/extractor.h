@@ -60,6 +60,7 @@ struct ExtractParams {
     int nCellsTotal;
     int selPerFrame;         // entries
     int outCapacity;         // caller's per-frame output capacity
+    int maxCellW, maxCellH;  // largest FAST cell interior of this image size (sizes the FAST kernel's shared memory)
     long long pyrFrameBytes, blurFrameBytes, slotFrameEntries, keyWsFrameEntries;
     unsigned char* pyr;
     unsigned char* blur;

@@ -42,16 +42,26 @@ constexpr int BM_WORDS = (kCellMax * kCellMax + 31) / 32;   // 113
      : (k) == 8 ? -3 * TPX : (k) == 9 ? -3 * TPX - 1 : (k) == 10 ? -2 * TPX - 2 : (k) == 11 ? -TPX - 3     \
      : (k) == 12 ? -3 : (k) == 13 ? TPX - 3 : (k) == 14 ? 2 * TPX - 2 : 3 * TPX - 1)
 
-struct FastShared {
-    unsigned int tile[TILE_ROWS * TPX / 2];                 // 16-bit pixels, two per word; reused as survivor list after B
-    unsigned int score[SC_ROWS * SC_PITCH / 4];             // uint8 scores with a zero ring
-    unsigned short queue[kCellMax * kCellMax];              // pixels that pass the necessary test: x | y<<6
-    unsigned short alive[kCellMax * kCellMax];              // corners (S >= minTh): x | y<<6 | ini<<14
-    unsigned int bmMin[BM_WORDS + 1], bmIni[BM_WORDS + 1];  // survivors at minTh / iniTh, bit = y*cw + x
-    int prefix[BM_WORDS + 1];
-    int queueLen, aliveLen, survLen;
-    int anyIni;
+// Dynamic shared memory, sized by the largest cell of the current image size (typical 36x34 cells: 13 KB, so the SM holds
+// enough CTAs to hide the barriers between the phases; the 60x60 worst case needs 29 KB).
+struct FastLayout {
+    int tile, score, queue, alive, bmMin, bmIni, total, bmWords;
 };
+__host__ __device__ inline FastLayout fast_layout(int maxW, int maxH) {
+    FastLayout f;
+    const int npix = maxW * maxH;
+    int p = 0;
+    auto take = [&](int bytes) { int r = p; p += (bytes + 15) & ~15; return r; };
+    f.tile = take((maxH + 6) * TPX * 2);          // 16-bit pixels; reused as the survivor list after phase B
+    f.score = take((maxH + 2) * SC_PITCH);        // uint8 scores with a zero ring
+    f.queue = take(npix * 2);                     // pixels that pass the necessary test: x | y<<6
+    f.alive = take(npix * 2);                     // corners (S >= minTh): x | y<<6 | ini<<14
+    f.bmWords = ((npix + 31) >> 5) + 1;
+    f.bmMin = take(f.bmWords * 4);                // survivors at minTh / iniTh, bit = y*cw + x
+    f.bmIni = take(f.bmWords * 4);
+    f.total = p;
+    return f;
+}
 
 // Exact threshold-free score. Both polarities ride in one register: low half p_k - v, high half v - p_k.
 __device__ __forceinline__ int fast_score(const unsigned short* c) {
@@ -84,8 +94,16 @@ __device__ __forceinline__ unsigned int pass_bits(unsigned int mm, unsigned int 
     return ((bl | dl) ? 1u : 0u) | ((bh | dh) ? 2u : 0u);
 }
 
-__global__ void __launch_bounds__(FAST_THREADS, 7) fast_cells_kernel(const __grid_constant__ ExtractParams P) {
-    __shared__ __align__(16) FastShared S;
+__global__ void __launch_bounds__(FAST_THREADS, 10) fast_cells_kernel(const __grid_constant__ ExtractParams P) {
+    extern __shared__ __align__(16) unsigned char fsm[];
+    __shared__ int sQueueLen, sAliveLen, sSurvLen, sIniLen;
+    const FastLayout lay = fast_layout(P.maxCellW, P.maxCellH);
+    unsigned int* sTile = reinterpret_cast<unsigned int*>(fsm + lay.tile);
+    unsigned int* sScore = reinterpret_cast<unsigned int*>(fsm + lay.score);
+    unsigned short* sQueue = reinterpret_cast<unsigned short*>(fsm + lay.queue);
+    unsigned short* sAlive = reinterpret_cast<unsigned short*>(fsm + lay.alive);
+    unsigned int* sBmMin = reinterpret_cast<unsigned int*>(fsm + lay.bmMin);
+    unsigned int* sBmIni = reinterpret_cast<unsigned int*>(fsm + lay.bmIni);
     const Cell cell = P.cells[blockIdx.x];
     const LevelGeom& L = P.lv[cell.level];
     const int frame = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
@@ -100,7 +118,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 7) fast_cells_kernel(const __gri
         const int quads = (cw + 8 + 3) >> 2;                 // 4-pixel groups per tile row (<= 17)
         const unsigned int rq = (65536u + quads - 1) / quads;   // i / quads == (i * rq) >> 16 for i * quads < 65536
         const unsigned char* src = level0 + (long long)ty0 * L.pitch + (tx0 - (shift8 >> 3));
-        uint2* tile64 = reinterpret_cast<uint2*>(S.tile);
+        uint2* tile64 = reinterpret_cast<uint2*>(sTile);
         for (int i = tid; i < (ch + 6) * quads; i += FAST_THREADS) {
             const int r = (int)(((unsigned int)i * rq) >> 16), q = i - r * quads;
             const unsigned int* g = reinterpret_cast<const unsigned int*>(src + (size_t)r * L.pitch) + q;
@@ -108,10 +126,10 @@ __global__ void __launch_bounds__(FAST_THREADS, 7) fast_cells_kernel(const __gri
             const unsigned int px = __funnelshift_r(w0, w1, shift8);
             tile64[r * (TPX / 4) + q] = make_uint2(__byte_perm(px, 0, 0x4140), __byte_perm(px, 0, 0x4342));
         }
-        uint4* sc4 = reinterpret_cast<uint4*>(S.score);
+        uint4* sc4 = reinterpret_cast<uint4*>(sScore);
         for (int i = tid; i < (ch + 2) * (SC_PITCH / 16); i += FAST_THREADS) sc4[i] = make_uint4(0, 0, 0, 0);
-        for (int i = tid; i < ((cw * ch + 31) >> 5) + 1; i += FAST_THREADS) { S.bmMin[i] = 0; S.bmIni[i] = 0; }
-        if (tid == 0) { S.queueLen = 0; S.aliveLen = 0; S.survLen = 0; S.anyIni = 0; }
+        for (int i = tid; i < ((cw * ch + 31) >> 5) + 1; i += FAST_THREADS) { sBmMin[i] = 0; sBmIni[i] = 0; }
+        if (tid == 0) { sQueueLen = 0; sAliveLen = 0; sSurvLen = 0; sIniLen = 0; }
     }
     __syncthreads();
 
@@ -121,7 +139,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 7) fast_cells_kernel(const __gri
         const int groups = (cw + 3) >> 2, total = groups * ch;
         const unsigned int rg = (65536u + groups - 1) / groups;
         const unsigned int T1 = (unsigned int)(P.minTh + 1) * 0x00010001u;
-        const uint2* tile64 = reinterpret_cast<const uint2*>(S.tile);
+        const uint2* tile64 = reinterpret_cast<const uint2*>(sTile);
         for (int i0 = tid - lane; i0 < total; i0 += FAST_THREADS) {
             const int i = min(i0 + lane, total - 1);
             const bool valid = i0 + lane < total;
@@ -182,36 +200,36 @@ __global__ void __launch_bounds__(FAST_THREADS, 7) fast_cells_kernel(const __gri
             flags = pass_bits(mmA, nnA, cA, T1) | (pass_bits(mmB, nnB, cB, T1) << 2);
             flags &= (1u << min(4, cw - x0)) - 1u;
             if (valid && flags) {
-                int pos = atomicAdd(&S.queueLen, __popc(flags));
+                int pos = atomicAdd(&sQueueLen, __popc(flags));
                 const unsigned int base = (unsigned int)x0 | ((unsigned int)y << 6);
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                    if (flags & (1u << k)) S.queue[pos++] = (unsigned short)(base + k);
+                    if (flags & (1u << k)) sQueue[pos++] = (unsigned short)(base + k);
             }
         }
     }
     __syncthreads();
 
     // ---- B. exact score for the queue; corners go to the dense `alive` list
-    const int qn = S.queueLen;
-    const unsigned short* tile16 = reinterpret_cast<const unsigned short*>(S.tile);
-    unsigned char* score = reinterpret_cast<unsigned char*>(S.score);
+    const int qn = sQueueLen;
+    const unsigned short* tile16 = reinterpret_cast<const unsigned short*>(sTile);
+    unsigned char* score = reinterpret_cast<unsigned char*>(sScore);
     for (int q = tid; q < qn; q += FAST_THREADS) {
-        const unsigned int e = S.queue[q];
+        const unsigned int e = sQueue[q];
         const int x = e & 63, y = (e >> 6) & 63;
         const int s = fast_score(tile16 + (y + 3) * TPX + x + 4);
         if (s >= P.minTh) {
             score[(y + 1) * SC_PITCH + x + 1] = (unsigned char)s;
-            S.alive[atomicAdd(&S.aliveLen, 1)] = (unsigned short)(e | (s >= P.iniTh ? 0x4000u : 0u));
+            sAlive[atomicAdd(&sAliveLen, 1)] = (unsigned short)(e | (s >= P.iniTh ? 0x4000u : 0u));
         }
     }
     __syncthreads();
 
     // ---- C. per-cell NMS on the corners; survivors are listed (in the tile, no longer needed) and set bitmap bits
-    const int an = S.aliveLen;
-    unsigned short* surv = reinterpret_cast<unsigned short*>(S.tile);
+    const int an = sAliveLen;
+    unsigned short* surv = reinterpret_cast<unsigned short*>(sTile);
     for (int q = tid; q < an; q += FAST_THREADS) {
-        const unsigned int e = S.alive[q];
+        const unsigned int e = sAlive[q];
         const int x = e & 63, y = (e >> 6) & 63;
         const unsigned char* sc = score + (y + 1) * SC_PITCH + x + 1;
         const int s = sc[0];
@@ -219,47 +237,30 @@ __global__ void __launch_bounds__(FAST_THREADS, 7) fast_cells_kernel(const __gri
                           max(max(sc[1], sc[SC_PITCH - 1]), max(sc[SC_PITCH], sc[SC_PITCH + 1])));
         if (s > m) {
             const int bit = y * cw + x;
-            atomicOr(&S.bmMin[bit >> 5], 1u << (bit & 31));
+            atomicOr(&sBmMin[bit >> 5], 1u << (bit & 31));
             if (e & 0x4000u) {
-                atomicOr(&S.bmIni[bit >> 5], 1u << (bit & 31));
-                S.anyIni = 1;
+                atomicOr(&sBmIni[bit >> 5], 1u << (bit & 31));
+                atomicAdd(&sIniLen, 1);
             }
-            surv[atomicAdd(&S.survLen, 1)] = (unsigned short)e;
+            surv[atomicAdd(&sSurvLen, 1)] = (unsigned short)e;
         }
     }
     __syncthreads();
 
-    // ---- D. rank table of the chosen threshold's survivors (row-major order == bit order)
-    const bool useIni = S.anyIni != 0;
-    const unsigned int* bm = useIni ? S.bmIni : S.bmMin;
-    const int bmWords = ((cw * ch + 31) >> 5) + 1;
-    if (tid < 32) {
-        int carry = 0;
-        for (int base = 0; base < bmWords; base += 32) {
-            const int w = base + tid;
-            const int c = w < bmWords ? __popc(bm[w]) : 0;
-            int incl = c;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, incl, o);
-                if (tid >= o) incl += t;
-            }
-            if (w < bmWords) S.prefix[w] = carry + incl - c;
-            carry += __shfl_sync(0xffffffffu, incl, 31);
-        }
-        if (tid == 0) P.cellCount[(size_t)frame * P.nCellsTotal + blockIdx.x] = carry;
-    }
-    __syncthreads();
-
-    // ---- E. survivors of the chosen threshold store themselves at their rank
+    // ---- D. survivors of the chosen threshold store themselves at their row-major rank = number of set bits below
+    //         their own in the bitmap (a few dozen POPCs each; there are only ~15 survivors per cell)
+    const int nIni = sIniLen, sn = sSurvLen;
+    const bool useIni = nIni > 0;
+    const unsigned int* bm = useIni ? sBmIni : sBmMin;
+    if (tid == 0) P.cellCount[(size_t)frame * P.nCellsTotal + blockIdx.x] = useIni ? nIni : sn;
     unsigned int* slot = P.slots + (size_t)frame * P.slotFrameEntries + cell.slot;
-    const int sn = S.survLen;
     for (int q = tid; q < sn; q += FAST_THREADS) {
         const unsigned int e = surv[q];
         if (useIni && !(e & 0x4000u)) continue;
         const int x = e & 63, y = (e >> 6) & 63;
         const int bit = y * cw + x;
-        const int rank = S.prefix[bit >> 5] + __popc(bm[bit >> 5] & ((1u << (bit & 31)) - 1u));
+        int rank = __popc(bm[bit >> 5] & ((1u << (bit & 31)) - 1u));
+        for (int w = 0; w < (bit >> 5); ++w) rank += __popc(bm[w]);
         const unsigned int s = score[(y + 1) * SC_PITCH + x + 1];
         slot[rank] = ((unsigned int)(cell.x0 + x - 16) << 20) | ((unsigned int)(cell.y0 + y - 16) << 8) | s;
     }
@@ -268,7 +269,8 @@ __global__ void __launch_bounds__(FAST_THREADS, 7) fast_cells_kernel(const __gri
 int launch_fast(const ExtractParams& P, cudaStream_t st, int* launches) {
     if (P.nCellsTotal == 0) return ORB_OK;
     dim3 grid(P.nCellsTotal, P.nFrames);
-    fast_cells_kernel<<<grid, FAST_THREADS, 0, st>>>(P);
+    const int smem = fast_layout(P.maxCellW, P.maxCellH).total;
+    fast_cells_kernel<<<grid, FAST_THREADS, smem, st>>>(P);
     ++*launches;
     ORB_CUDA(cudaGetLastError());
     return ORB_OK;
