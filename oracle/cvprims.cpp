@@ -154,21 +154,25 @@ void fast9_16(const uint8_t* img, int w, int h, int stride, int threshold, bool 
 // exact integer accumulation, one rounding (v + 2^15) >> 16, reflect-101 borders.
 // ---------------------------------------------------------------------------------------------
 void gaussian_blur_7x7_s2(const uint8_t* src, int w, int h, int sstride, uint8_t* dst, int dstride) {
-    static const int K[7] = {18, 34, 48, 56, 48, 34, 18};
-    std::vector<uint16_t> tmp((size_t)w * h);
+    // two separable passes over contiguous rows (plain loops the compiler can vectorise); same arithmetic as above
+    const int pw = w + 6;
+    std::vector<uint8_t> padded(pw);
+    std::vector<uint16_t> tmp((size_t)w * (h + 6));
+    auto hrow = [&](int sy, uint16_t* out) {
+        const uint8_t* s = src + (size_t)sy * sstride;
+        for (int x = 0; x < 3; ++x) padded[x] = s[reflect101(x - 3, w)];
+        std::memcpy(&padded[3], s, w);
+        for (int x = 0; x < 3; ++x) padded[w + 3 + x] = s[reflect101(w + x, w)];
+        const uint8_t* p = padded.data();
+        for (int x = 0; x < w; ++x)
+            out[x] = (uint16_t)(18 * (p[x] + p[x + 6]) + 34 * (p[x + 1] + p[x + 5]) + 48 * (p[x + 2] + p[x + 4]) + 56 * p[x + 3]);
+    };
+    for (int y = -3; y < h + 3; ++y) hrow(reflect101(y, h), &tmp[(size_t)(y + 3) * w]);
     for (int y = 0; y < h; ++y) {
-        const uint8_t* s = src + (size_t)y * sstride;
-        for (int x = 0; x < w; ++x) {
-            int acc = 0;
-            for (int k = 0; k < 7; ++k) acc += K[k] * s[reflect101(x + k - 3, w)];
-            tmp[(size_t)y * w + x] = (uint16_t)acc;  // <= 255*256
-        }
-    }
-    for (int y = 0; y < h; ++y) {
+        const uint16_t *r0 = &tmp[(size_t)y * w], *r1 = r0 + w, *r2 = r1 + w, *r3 = r2 + w, *r4 = r3 + w, *r5 = r4 + w, *r6 = r5 + w;
         uint8_t* d = dst + (size_t)y * dstride;
         for (int x = 0; x < w; ++x) {
-            uint32_t acc = 0;
-            for (int k = 0; k < 7; ++k) acc += (uint32_t)K[k] * tmp[(size_t)reflect101(y + k - 3, h) * w + x];
+            const uint32_t acc = 18u * ((uint32_t)r0[x] + r6[x]) + 34u * ((uint32_t)r1[x] + r5[x]) + 48u * ((uint32_t)r2[x] + r4[x]) + 56u * r3[x];
             d[x] = (uint8_t)((acc + 32768u) >> 16);
         }
     }

@@ -86,6 +86,7 @@ def test_allpairs_counts(matcher, oracle):
     d_ang = torch.from_numpy(ang).cuda()
     for ratio, ori in ((0.75, True), (0.9, False)):
         counts = torch.full((nkf, nkf), -7, dtype=torch.int32, device="cuda")
+        torch.cuda.synchronize()      # the matcher enqueues on its own stream
         matcher.allpairs_device(d_table, d_ang, 0, nkf, 0, nkf, ratio, ori, counts)
         matcher.synchronize()
         torch.cuda.synchronize()
@@ -96,6 +97,7 @@ def test_allpairs_counts(matcher, oracle):
         assert ref.max() > 100
     # sub-ranges (what a rank computes in the sharded run) agree with the full matrix
     part = torch.full((4, nkf), -7, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
     matcher.allpairs_device(d_table, d_ang, 4, 8, 0, nkf, 0.9, False, part)
     matcher.synchronize()
     assert np.array_equal(part.cpu().numpy(), ref[4:8])
