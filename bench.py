@@ -58,6 +58,13 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.rows, self.p = index, [], None
+        self.t0 = self.t1 = None
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def start(self):
         try:
@@ -69,17 +76,20 @@ class ClockSampler:
 
     def _read(self):
         for line in self.p.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
     def stop(self):
         if self.p:
             self.p.terminate()
-        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
-        mx = max([int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()] or [0])
+        # samples taken while the timed region ran (nvidia-smi reports ~100 ms late: widen the window a little)
+        inside = [r for t, r in self.rows if self.t0 is None or (self.t0 <= t <= (self.t1 or t) + 0.15)]
+        rows = inside or [r for _, r in self.rows]
+        sm = sorted(int(float(r[0])) for r in rows if r and r[0].replace(".", "").isdigit())
+        mx = max([int(float(r[1])) for r in rows if len(r) > 1 and r[1].replace(".", "").isdigit()] or [0])
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].startswith("Active")})
+        reasons = sorted({names[i] for r in rows if len(r) >= 7 for i in range(4) if r[3 + i].startswith("Active")})
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": reasons,
-                "samples": len(sm)}
+                "samples": len(sm), "samples_in_timed_region": len(inside)}
 
 
 def cpu_reference(frames, procs, seconds_budget, native=True):
@@ -110,6 +120,53 @@ def cpu_reference(frames, procs, seconds_budget, native=True):
     dt = time.perf_counter() - t0
     return {"value": n / dt, "unit": "frames/s", "cores": 1, "kind": "port",
             "sample": "%d extractions of synthetic 752x480 frames through oracle/liborb_oracle.so" % n}
+
+
+def single_frame_latency(device, iters=30):
+    """configs[0]: one 752x480 frame, ORBextractor(2000, ...) as the initialiser uses (Tracking.cc:822) + SearchForInitialization
+    against the same scene shifted by (+7,+3); configs[1]: one 1241x376 frame, 2000 features + SearchByProjection(th=15).
+    Host buffers in, host buffers out, median of `iters` calls in milliseconds."""
+    import numpy as np
+    import orbb200
+    from orbb200.synth import shifted_pair
+
+    def med(fn):
+        for _ in range(3):
+            fn()
+        ts = []
+        for _ in range(iters):
+            t0 = time.perf_counter()
+            fn()
+            ts.append((time.perf_counter() - t0) * 1e3)
+        return float(np.median(ts))
+
+    out = {}
+    m = orbb200.Matcher(device)
+    sf = np.array([1.2 ** i for i in range(8)], np.float32)
+    for name, (w, h) in (("euroc_752x480", (752, 480)), ("kitti_1241x376", (1241, 376))):
+        a, b = shifted_pair(3, w, h)
+        ex = orbb200.Extractor(2000, SCALE, NLEVELS, INI_TH, MIN_TH, max_width=w, max_height=h, max_batch=1, device=device)
+        out["extract_%s_2000kp" % name] = med(lambda: ex(a))
+        ka, da = ex(a)
+        kb, db = ex(b)
+        st = ex.stage_times()
+        out["extract_%s_stage_ms" % name] = [float(x) for x in st]
+        bounds = (0.0, 0.0, float(w), float(h))
+        out["frame_grid_%s" % name] = med(lambda: m.frame(kb, db, bounds).close())
+        f1, f2 = m.frame(ka, da, bounds), m.frame(kb, db, bounds)
+        if name.startswith("euroc"):
+            prev = np.stack([ka["x"], ka["y"]], 1).astype(np.float32)
+            out["search_for_initialization"] = med(lambda: m.search_for_initialization(f1, f2, prev, 100, 0.9, True))
+            out["search_for_initialization_matches"] = int(m.search_for_initialization(f1, f2, prev, 100, 0.9, True)[0])
+        else:
+            q = np.zeros(len(ka), orbb200.PROJ_QUERY_DTYPE)
+            q["u"], q["v"], q["invz"], q["octave"], q["valid"], q["obs_positive"], q["angle"] = \
+                ka["x"] - 7, ka["y"] - 3, 0.1, ka["octave"], 1, 1, ka["angle"]
+            out["search_by_projection_th15"] = med(lambda: m.search_by_projection(f2, sf, q, da, 15.0, 0, None, None, 0.0, True))
+            out["search_by_projection_matches"] = int(m.search_by_projection(f2, sf, q, da, 15.0, 0, None, None, 0.0, True)[0])
+        f1.close(); f2.close(); ex.close()
+    m.close()
+    return out
 
 
 def run_reference(args):
@@ -148,6 +205,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--no-hamming", action="store_true")
+    ap.add_argument("--no-latency", action="store_true", help="skip the single-frame latency leg")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -169,6 +227,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     B, K, Wm = args.frames, args.steps, max(args.warmup, 3)
+    sampler = ClockSampler(local)
+    sampler.start()      # nvidia-smi takes ~1 s to produce its first line: start it before the inputs are generated
 
     def barrier():
         torch.cuda.synchronize()
@@ -205,9 +265,8 @@ def main():
     nkp = float(d_n.float().mean().item())
 
     # ---- timed region: K steps, kernels bracketed by events on the launching stream
-    sampler = ClockSampler(local)
     barrier()
-    sampler.start()
+    sampler.mark_begin()
     ex.set_profiling(True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
@@ -215,6 +274,7 @@ def main():
         step()
     e1.record(stream)
     stream.synchronize()
+    sampler.mark_end()
     barrier()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     kernel_ms, ncalls = ex.kernel_times()
@@ -259,6 +319,12 @@ def main():
         # the quadtree kernel moves almost no bytes (latency-bound list surgery): its roofline entry is the time share
         dom_bw = "fast" if dom == "quadtree" else dom
         ach = alg[dom_bw] * B / (per_kernel[dom_bw] * 1e-3) / 1e9
+        traffic = None
+        try:   # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture, per frame (profiles/)
+            tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            traffic = tr[dom_bw]["dram_bytes_per_frame"] * B
+        except Exception:
+            pass
         line = {
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -272,7 +338,7 @@ def main():
                     "d2h_bytes_per_step": B * (cap * 60 + 4), "steps": e2e_steps},
             "gpu_launches": launches_per_step * K,
             "roofline": {"bound": "hbm", "kernel": dom_bw, "achieved": ach, "peak": hbm, "unit": "GB/s",
-                         "frac": ach / hbm, "traffic": None,
+                         "frac": ach / hbm, "traffic": traffic,
                          "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                          "algorithmic_bytes_per_launch": alg[dom_bw] * B, "launch_ms": per_kernel[dom_bw],
                          "dominant_by_time": dom},
@@ -323,6 +389,10 @@ def main():
                                             "peak_source": "orbm_popc_peak microbenchmark in this run"},
                                "gpu_launches": 2 * K, "matches_per_pair": float(nm.float().mean().item())}
         m.close()
+
+    # ---- single-frame latency of configs[0] / configs[1] through the host C ABI (what a live SLAM loop sees)
+    if rank == 0 and world == 1 and not args.no_latency:
+        line["latency_ms"] = single_frame_latency(local)
 
     # ---- CPU baseline beside it (rank 0, N=1 only): bounded sample, single thread
     if rank == 0 and world == 1 and not args.no_cpu:

@@ -148,6 +148,15 @@ int orbm_search_by_projection(orbm_handle h, orbm_frame cur, const float* scale_
                               const uint8_t* query_desc, int nq, float th, int mode, const uint8_t* occupied,
                               int* cur_match, int check_orientation, int* nmatches);
 
+/* The same search with the acceptance threshold as a parameter: SearchByProjection(Frame&, KeyFrame*, sAlreadyFound, th,
+ * ORBdist) used by relocalisation (ORBmatcher.cc:1500-1627; ORBdist = 100 or 64, Tracking.cc:2677, 2691).  There the host
+ * predicts the level (query.octave = nPredictedLevel), mode is 0, and every assigned keypoint counts as occupied
+ * (obs_positive = 1, occupied[i2] = CurrentFrame.mvpMapPoints[i2] != NULL).                                          */
+int orbm_search_by_projection_ex(orbm_handle h, orbm_frame cur, const float* scale_factors, int nlevels,
+                                 const float* u_right, float mbf, const orbm_proj_query* queries,
+                                 const uint8_t* query_desc, int nq, float th, int mode, int max_distance,
+                                 const uint8_t* occupied, int* cur_match, int check_orientation, int* nmatches);
+
 typedef struct {
     float proj_x, proj_y, proj_xr;
     float view_cos;

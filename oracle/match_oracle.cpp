@@ -151,7 +151,7 @@ int search_for_initialization(const FrameArrays& F1, const FrameArrays& F2, floa
 // ORBmatcher.cc:1341-1498 (projection itself, :1376-1388, stays with the caller)
 int search_by_projection_frame(const FrameArrays& cur, const float* sf, const float* uRight, float mbf,
                                const ProjQuery* q, const uint8_t* qdesc, int nq, float th, int mode,
-                               const uint8_t* curOccupied, int* curMatch, bool checkOri) {
+                               const uint8_t* curOccupied, int* curMatch, bool checkOri, int maxDist) {
     int nmatches = 0;
     std::vector<uint8_t> occ(curOccupied, curOccupied + cur.n);
     std::fill(curMatch, curMatch + cur.n, -1);
@@ -180,7 +180,7 @@ int search_by_projection_frame(const FrameArrays& cur, const float* sf, const fl
             const int dist = descriptor_distance(d, cur.desc + (size_t)i2 * 32);
             if (dist < best) { best = dist; bestIdx = i2; }
         }
-        if (best <= TH_HIGH) {
+        if (best <= maxDist) {   // TH_HIGH (:1453); ORBdist in the relocalisation overload (:1583)
             curMatch[bestIdx] = i;
             occ[bestIdx] = q[i].obsPositive ? 1 : 0;
             ++nmatches;

@@ -59,7 +59,7 @@ struct ProjQuery {          // one LastFrame keypoint with a map point (ORBmatch
 // curMatch[i2] (out)   : index of the query assigned to keypoint i2, or -1
 int search_by_projection_frame(const FrameArrays& cur, const float* scaleFactors, const float* uRight /* may be null */,
                                float mbf, const ProjQuery* q, const uint8_t* qdesc, int nq, float th, int mode,
-                               const uint8_t* curOccupied, int* curMatch, bool checkOri);
+                               const uint8_t* curOccupied, int* curMatch, bool checkOri, int maxDist = TH_HIGH);
 
 struct MapPointQuery {      // ORBmatcher.cc:45-129
     float projX, projY, projXR;

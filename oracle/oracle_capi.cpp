@@ -154,6 +154,12 @@ int orbo_search_projection(void* cur, const float* sf, const float* uRight, floa
     return search_by_projection_frame(((OrboFrame*)cur)->fa, sf, uRight, mbf, q, qdesc, nq, th, mode, occupied,
                                       curMatch, checkOri != 0);
 }
+int orbo_search_projection_ex(void* cur, const float* sf, const float* uRight, float mbf, const ProjQuery* q,
+                              const uint8_t* qdesc, int nq, float th, int mode, int maxDist, const uint8_t* occupied,
+                              int* curMatch, int checkOri) {
+    return search_by_projection_frame(((OrboFrame*)cur)->fa, sf, uRight, mbf, q, qdesc, nq, th, mode, occupied,
+                                      curMatch, checkOri != 0, maxDist);
+}
 int orbo_search_points(void* F, const float* sf, const float* uRight, const MapPointQuery* q, const uint8_t* qdesc,
                        int nq, float th, float ratio, const uint8_t* occupied, int* match) {
     return search_by_projection_points(((OrboFrame*)F)->fa, sf, uRight, q, qdesc, nq, th, ratio, occupied, match);

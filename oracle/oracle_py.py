@@ -68,6 +68,8 @@ class Oracle:
         L.orbo_search_init.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int]
         L.orbo_search_projection.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p,
                                              C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        L.orbo_search_projection_ex.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p,
+                                                C.c_int, C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
         L.orbo_search_points.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                          C.c_float, C.c_float, C.c_void_p, C.c_void_p]
         L.orbo_search_triangulation.argtypes = ([C.c_void_p, C.c_void_p] + [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p] * 2
@@ -296,15 +298,15 @@ class OracleFrame:
         return n, m12, prev
 
     def search_projection(self, scale_factors, queries, qdesc, th, mode=0, occupied=None, u_right=None, mbf=0.0,
-                          check_ori=True):
+                          check_ori=True, max_distance=100):
         sf = np.ascontiguousarray(scale_factors, np.float32)
         q = np.ascontiguousarray(queries, PROJ_QUERY_DTYPE)
         qd = np.ascontiguousarray(qdesc, np.uint8)
         occ = np.zeros(self.n, np.uint8) if occupied is None else np.ascontiguousarray(occupied, np.uint8)
         ur = None if u_right is None else np.ascontiguousarray(u_right, np.float32)
         match = np.empty(self.n, np.int32)
-        n = self.lib.orbo_search_projection(self.h, _p(sf), _p(ur), mbf, _p(q), _p(qd), len(q), th, mode, _p(occ),
-                                            _p(match), int(check_ori))
+        n = self.lib.orbo_search_projection_ex(self.h, _p(sf), _p(ur), mbf, _p(q), _p(qd), len(q), th, mode, max_distance,
+                                               _p(occ), _p(match), int(check_ori))
         return n, match
 
     def search_points(self, scale_factors, queries, qdesc, th, ratio, occupied=None, u_right=None):

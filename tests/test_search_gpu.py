@@ -103,6 +103,27 @@ def test_search_by_projection(matcher, oracle, pair, name, th, mode, stereo, ori
         assert n > 100
 
 
+def test_search_by_projection_relocalisation_threshold(matcher, oracle, pair):
+    """SearchByProjection(Frame, KeyFrame, sAlreadyFound, th, ORBdist) (ORBmatcher.cc:1500-1627): predicted levels come
+    from the host, any assigned keypoint is occupied, acceptance threshold ORBdist = 64 (Tracking.cc:2691)."""
+    ka, da, kb, db, bounds = pair["euroc"]
+    rng = np.random.default_rng(64)
+    g, o = _frames(matcher, oracle, kb, db, bounds)
+    q = _proj_queries(rng, ka)
+    q["octave"] = np.clip(ka["octave"] + rng.integers(-1, 2, len(ka)), 0, 7)    # PredictScale on the host
+    q["obs_positive"] = 1
+    occ = (rng.random(len(kb)) < 0.2).astype(np.uint8)
+    oq = q.view(np.dtype([(a, b) for a, b in zip(("u", "v", "invz", "octave", "valid", "obsPositive", "angle"),
+                                                   ("<f4", "<f4", "<f4", "<i4", "<i4", "<i4", "<f4"))]))
+    res = {}
+    for dist in (100, 64, 30):
+        n, match = matcher.search_by_projection(g, SF, q, da, 10.0, 0, occ, None, 0.0, True, max_distance=dist)
+        rn, rmatch = o.search_projection(SF, oq, da, 10.0, 0, occ, None, 0.0, True, max_distance=dist)
+        assert n == rn and np.array_equal(match, rmatch)
+        res[dist] = n
+    assert res[100] >= res[64] >= res[30] and res[64] > 50
+
+
 @pytest.mark.parametrize("name,th,ratio", [("euroc", 1.0, 0.8), ("kitti", 3.0, 0.8), ("euroc", 5.0, 0.6)])
 def test_search_by_projection_points(matcher, oracle, pair, name, th, ratio):
     ka, da, kb, db, bounds = pair[name]

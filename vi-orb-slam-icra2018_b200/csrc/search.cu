@@ -285,11 +285,52 @@ __device__ void prune_pushes(const int* pushBin, const int* pushVal, int nPush, 
     __syncwarp();
 }
 
-// SearchForInitialization replay (ORBmatcher.cc:417-517). One warp.
+// Ordered walk over the queries by ONE warp.  The order-dependent state (what earlier queries matched) lives in shared
+// memory; the per-query metadata is fetched 32 queries at a time and the first 32 candidates of the NEXT query are
+// loaded while the current one is reduced, so the dependent chain per query is shared-memory lookups and shuffles
+// rather than global-memory round trips.  skip(c) -> candidate c is ignored; accept(i, a, best, second) is warp-uniform.
+template <class Skip, class Accept>
+__device__ __forceinline__ void replay_queries(const AreaQuery* __restrict__ q, const int* __restrict__ offsets,
+                                               const int2* __restrict__ cand, int nq, Skip skip, Accept accept) {
+    const int lane = threadIdx.x & 31;
+    for (int i0 = 0; i0 < nq; i0 += 32) {
+        const int qi = i0 + lane;
+        int act = 0, a = 0, b = 0;
+        if (qi < nq) { act = q[qi].active; a = offsets[qi]; b = offsets[qi + 1]; }
+        int na = __shfl_sync(0xffffffffu, a, 0), nb = __shfl_sync(0xffffffffu, b, 0), nact = __shfl_sync(0xffffffffu, act, 0);
+        int2 pre = (nact && na + lane < nb) ? cand[na + lane] : make_int2(-1, 0);
+        const int m = min(32, nq - i0);
+        for (int j = 0; j < m; ++j) {
+            const int ca = na, cb = nb, cact = nact;
+            const int2 cur = pre;
+            if (j + 1 < m) {
+                na = __shfl_sync(0xffffffffu, a, j + 1); nb = __shfl_sync(0xffffffffu, b, j + 1); nact = __shfl_sync(0xffffffffu, act, j + 1);
+                pre = (nact && na + lane < nb) ? cand[na + lane] : make_int2(-1, 0);
+            }
+            if (!cact || ca == cb) continue;
+            int best = kNone, second = kNone;
+            if (cur.x >= 0 && !skip(cur)) best = (cur.y << kOrdShift) | lane;
+            for (int k = ca + 32 + lane; k < cb; k += 32) {
+                const int2 c = cand[k];
+                if (skip(c)) continue;
+                const int key = (c.y << kOrdShift) | (k - ca);
+                second = min(second, max(key, best));
+                best = min(best, key);
+            }
+            warp_min2(best, second);
+            accept(i0 + j, ca, best, second);
+        }
+    }
+}
+
+// SearchForInitialization replay (ORBmatcher.cc:417-517). One warp; m21 / vMatchedDistance in shared memory.
 __global__ void __launch_bounds__(32)
 init_replay_kernel(FrameDev f1, FrameDev f2, const AreaQuery* __restrict__ q, const int* __restrict__ offsets,
-                   const int2* __restrict__ cand, float ratio, int checkOri, float* prevXY, int* m12, int* m21,
-                   int* matchedDist, int* pushBin, int* pushVal, int* nmatchesOut) {
+                   const int2* __restrict__ cand, float ratio, int checkOri, float* prevXY, int* m12, int* pushBin,
+                   int* pushVal, int* nmatchesOut) {
+    extern __shared__ int dyn[];
+    int* m21 = dyn;
+    int* matchedDist = dyn + f2.n;
     __shared__ int hist[kHistoLength];
     __shared__ int nmatches;
     const int lane = threadIdx.x;
@@ -299,36 +340,26 @@ init_replay_kernel(FrameDev f1, FrameDev f2, const AreaQuery* __restrict__ q, co
     for (int i = lane; i < f2.n; i += 32) { m21[i] = -1; matchedDist[i] = INT_MAX; }
     __syncwarp();
     int nPush = 0;
-    for (int i1 = 0; i1 < f1.n; ++i1) {
-        if (!q[i1].active) continue;
-        const int a = offsets[i1], b = offsets[i1 + 1];
-        if (a == b) continue;
-        int best = kNone, second = kNone;
-        for (int k = a + lane; k < b; k += 32) {
-            const int2 c = cand[k];
-            if (matchedDist[c.x] <= c.y) continue;                     // :444
-            const int key = (c.y << kOrdShift) | (k - a);
-            second = min(second, max(key, best));
-            best = min(best, key);
-        }
-        warp_min2(best, second);
-        const int bd = best == kNone ? INT_MAX : best >> kOrdShift;
-        const int sd = second == kNone ? INT_MAX : second >> kOrdShift;
-        if (bd <= kThLow && (float)bd < __fmul_rn((float)sd, ratio)) {   // :459-461
-            if (lane == 0) {
-                const int i2 = cand[a + (best & kOrdMask)].x;
-                if (m21[i2] >= 0) { m12[m21[i2]] = -1; --nmatches; }
-                m12[i1] = i2; m21[i2] = i1; matchedDist[i2] = bd; ++nmatches;
-                if (checkOri) {
-                    const int bin = rotation_bin(f1.keys[i1].angle, f2.keys[i2].angle);
-                    hist[bin] += 1;
-                    pushBin[nPush] = bin; pushVal[nPush] = i1;
+    replay_queries(q, offsets, cand, f1.n,
+        [&](const int2& c) { return matchedDist[c.x] <= c.y; },                               // :444
+        [&](int i1, int a, int best, int second) {
+            const int bd = best == kNone ? INT_MAX : best >> kOrdShift;
+            const int sd = second == kNone ? INT_MAX : second >> kOrdShift;
+            if (bd <= kThLow && (float)bd < __fmul_rn((float)sd, ratio)) {                    // :459-461
+                if (lane == 0) {
+                    const int i2 = cand[a + (best & kOrdMask)].x;
+                    if (m21[i2] >= 0) { m12[m21[i2]] = -1; --nmatches; }
+                    m12[i1] = i2; m21[i2] = i1; matchedDist[i2] = bd; ++nmatches;
+                    if (checkOri) {
+                        const int bin = rotation_bin(f1.keys[i1].angle, f2.keys[i2].angle);
+                        hist[bin] += 1;
+                        pushBin[nPush] = bin; pushVal[nPush] = i1;
+                    }
                 }
+                if (checkOri) ++nPush;
+                __syncwarp();
             }
-            if (checkOri) ++nPush;
-            __syncwarp();
-        }
-    }
+        });
     __threadfence_block();
     if (checkOri) prune_pushes(pushBin, pushVal, nPush, hist, m12, true, &nmatches);
     __syncwarp();
@@ -340,48 +371,42 @@ init_replay_kernel(FrameDev f1, FrameDev f2, const AreaQuery* __restrict__ q, co
     if (lane == 0) *nmatchesOut = nmatches;
 }
 
-// SearchByProjection(Frame, Frame) replay (ORBmatcher.cc:1363-1495). One warp.
+// SearchByProjection(Frame, Frame) replay (ORBmatcher.cc:1363-1495), also the relocalisation overload (:1500-1627, where
+// the acceptance threshold is ORBdist instead of TH_HIGH). One warp; occupancy flags in shared memory.
 __global__ void __launch_bounds__(32)
 proj_replay_kernel(FrameDev cur, const AreaQuery* __restrict__ q, const orbm_proj_query* __restrict__ pq, int nq,
-                   const int* __restrict__ offsets, const int2* __restrict__ cand, int checkOri, unsigned char* occ,
-                   int* curMatch, int* pushBin, int* pushVal, int* nmatchesOut) {
+                   const int* __restrict__ offsets, const int2* __restrict__ cand, int checkOri, int maxDist,
+                   const unsigned char* __restrict__ occIn, int* curMatch, int* pushBin, int* pushVal, int* nmatchesOut) {
+    extern __shared__ int dyn[];
+    unsigned char* occ = reinterpret_cast<unsigned char*>(dyn);
     __shared__ int hist[kHistoLength];
     __shared__ int nmatches;
     const int lane = threadIdx.x;
     if (lane < kHistoLength) hist[lane] = 0;
     if (lane == 0) nmatches = 0;
-    for (int i = lane; i < cur.n; i += 32) curMatch[i] = -1;
+    for (int i = lane; i < cur.n; i += 32) { curMatch[i] = -1; occ[i] = occIn[i]; }
     __syncwarp();
     int nPush = 0;
-    for (int i = 0; i < nq; ++i) {
-        if (!q[i].active) continue;
-        const int a = offsets[i], b = offsets[i + 1];
-        if (a == b) continue;
-        int best = kNone;
-        for (int k = a + lane; k < b; k += 32) {
-            const int2 c = cand[k];
-            if (occ[c.x]) continue;                                     // :1428-1430
-            best = min(best, (c.y << kOrdShift) | (k - a));
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
-        const int bd = best == kNone ? 256 : best >> kOrdShift;
-        if (bd <= kThHigh) {                                            // :1453
-            if (lane == 0) {
-                const int i2 = cand[a + (best & kOrdMask)].x;
-                curMatch[i2] = i;
-                occ[i2] = pq[i].obs_positive ? 1 : 0;
-                ++nmatches;
-                if (checkOri) {
-                    const int bin = rotation_bin(pq[i].angle, cur.keys[i2].angle);
-                    hist[bin] += 1;
-                    pushBin[nPush] = bin; pushVal[nPush] = i2;
+    replay_queries(q, offsets, cand, nq,
+        [&](const int2& c) { return occ[c.x] != 0; },                                         // :1428-1430
+        [&](int i, int a, int best, int) {
+            const int bd = best == kNone ? 256 : best >> kOrdShift;
+            if (bd <= maxDist) {                                                              // :1453 / :1583
+                if (lane == 0) {
+                    const int i2 = cand[a + (best & kOrdMask)].x;
+                    curMatch[i2] = i;
+                    occ[i2] = pq[i].obs_positive ? 1 : 0;
+                    ++nmatches;
+                    if (checkOri) {
+                        const int bin = rotation_bin(pq[i].angle, cur.keys[i2].angle);
+                        hist[bin] += 1;
+                        pushBin[nPush] = bin; pushVal[nPush] = i2;
+                    }
                 }
+                if (checkOri) ++nPush;
+                __syncwarp();
             }
-            if (checkOri) ++nPush;
-            __syncwarp();
-        }
-    }
+        });
     __threadfence_block();
     if (checkOri) prune_pushes(pushBin, pushVal, nPush, hist, curMatch, false, &nmatches);
     __syncwarp();
@@ -391,27 +416,19 @@ proj_replay_kernel(FrameDev cur, const AreaQuery* __restrict__ q, const orbm_pro
 // SearchByProjection(Frame, MapPoints) replay (ORBmatcher.cc:51-126). One warp.
 __global__ void __launch_bounds__(32)
 point_replay_kernel(FrameDev f, const AreaQuery* __restrict__ q, const orbm_point_query* __restrict__ pq, int nq,
-                    const int* __restrict__ offsets, const int2* __restrict__ cand, float ratio, unsigned char* occ,
-                    int* match, int* nmatchesOut) {
+                    const int* __restrict__ offsets, const int2* __restrict__ cand, float ratio,
+                    const unsigned char* __restrict__ occIn, int* match, int* nmatchesOut) {
+    extern __shared__ int dyn[];
+    unsigned char* occ = reinterpret_cast<unsigned char*>(dyn);
     const int lane = threadIdx.x;
-    for (int i = lane; i < f.n; i += 32) match[i] = -1;
+    for (int i = lane; i < f.n; i += 32) { match[i] = -1; occ[i] = occIn[i]; }
     __syncwarp();
     int nmatches = 0;
-    for (int i = 0; i < nq; ++i) {
-        if (!q[i].active) continue;
-        const int a = offsets[i], b = offsets[i + 1];
-        if (a == b) continue;
-        int best = kNone, second = kNone;
-        for (int k = a + lane; k < b; k += 32) {
-            const int2 c = cand[k];
-            if (occ[c.x]) continue;                                     // :84-86
-            const int key = (c.y << kOrdShift) | (k - a);
-            second = min(second, max(key, best));
-            best = min(best, key);
-        }
-        warp_min2(best, second);
-        const int bd = best == kNone ? 256 : best >> kOrdShift;
-        if (bd <= kThHigh) {                                            // :115
+    replay_queries(q, offsets, cand, nq,
+        [&](const int2& c) { return occ[c.x] != 0; },                                         // :84-86
+        [&](int i, int a, int best, int second) {
+            const int bd = best == kNone ? 256 : best >> kOrdShift;
+            if (bd > kThHigh) return;                                                         // :115
             const int bi = cand[a + (best & kOrdMask)].x;
             const int bestLevel = f.keys[bi].octave;
             int sd = 256, secondLevel = -1;
@@ -419,15 +436,14 @@ point_replay_kernel(FrameDev f, const AreaQuery* __restrict__ q, const orbm_poin
                 sd = second >> kOrdShift;
                 secondLevel = f.keys[cand[a + (second & kOrdMask)].x].octave;
             }
-            if (bestLevel == secondLevel && (float)bd > __fmul_rn(ratio, (float)sd)) continue;   // :118-119
+            if (bestLevel == secondLevel && (float)bd > __fmul_rn(ratio, (float)sd)) return;  // :118-119
             if (lane == 0) {
                 match[bi] = i;
                 occ[bi] = pq[i].obs_positive ? 1 : 0;
             }
             ++nmatches;
             __syncwarp();
-        }
-    }
+        });
     if (lane == 0) *nmatchesOut = nmatches;
 }
 
@@ -555,6 +571,8 @@ struct orbm_frame_s {
     (h)->launches = 0;
 
 namespace {
+
+constexpr size_t kReplaySmemMax = 160 * 1024;   // shared-memory state of the one-warp replays (20k keypoints for init)
 
 // phase 1 for nq queries already built in h->ws0 (AreaQuery[nq]); leaves offsets in ws1 and candidates in ws2
 int run_candidates(orbm_matcher* h, const FrameDev& f, const uint4* dQdesc, int nq, const float* dURight, int* totalOut) {
@@ -684,14 +702,14 @@ int orbm_search_for_initialization(orbm_handle h, orbm_frame f1, orbm_frame f2, 
     int total = 0;
     ORB_CHECK(run_candidates(h, d2, d1.desc, n1, nullptr, &total));
     ORB_CHECK(h->out0.reserve((size_t)(n1 + 1) * 4));          // m12
-    ORB_CHECK(h->out1.reserve((size_t)(n2 + 1) * 4 * 2));      // m21, matchedDist
     ORB_CHECK(h->out2.reserve((size_t)(n1 + 1) * 4 * 2));      // pushBin, pushVal
     ORB_CHECK(h->out3.reserve(16));
-    int* m21 = h->out1.as<int>();
     int* pushBin = h->out2.as<int>();
-    init_replay_kernel<<<1, 32, 0, st>>>(d1, d2, h->ws0.as<AreaQuery>(), h->ws1.as<int>(), h->ws2.as<int2>(), ratio, checkOri,
-                                         h->in0.as<float>(), h->out0.as<int>(), m21, m21 + n2 + 1, pushBin, pushBin + n1 + 1,
-                                         h->out3.as<int>());
+    const size_t replaySmem = (size_t)std::max(n2, 1) * 8;       // m21 + vMatchedDistance
+    if (replaySmem > kReplaySmemMax) return fail(ORB_ERR_CAPACITY, "orbm_search_for_initialization: %d keypoints exceed the replay state (%d)", n2, (int)(kReplaySmemMax / 8));
+    ORB_CUDA(cudaFuncSetAttribute(init_replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kReplaySmemMax));
+    init_replay_kernel<<<1, 32, replaySmem, st>>>(d1, d2, h->ws0.as<AreaQuery>(), h->ws1.as<int>(), h->ws2.as<int2>(), ratio, checkOri,
+                                                  h->in0.as<float>(), h->out0.as<int>(), pushBin, pushBin + n1 + 1, h->out3.as<int>());
     h->launches += 1;
     ORB_CUDA(cudaGetLastError());
     ORB_CUDA(cudaMemcpyAsync(matches12, h->out0.p, (size_t)n1 * 4, cudaMemcpyDeviceToHost, st));
@@ -704,6 +722,13 @@ int orbm_search_for_initialization(orbm_handle h, orbm_frame f1, orbm_frame f2, 
 int orbm_search_by_projection(orbm_handle h, orbm_frame cur, const float* sf, int nlevels, const float* uRight, float mbf,
                               const orbm_proj_query* queries, const uint8_t* qdesc, int nq, float th, int mode,
                               const uint8_t* occupied, int* curMatch, int checkOri, int* nmatches) {
+    return orbm_search_by_projection_ex(h, cur, sf, nlevels, uRight, mbf, queries, qdesc, nq, th, mode, kThHigh, occupied,
+                                        curMatch, checkOri, nmatches);
+}
+
+int orbm_search_by_projection_ex(orbm_handle h, orbm_frame cur, const float* sf, int nlevels, const float* uRight, float mbf,
+                                 const orbm_proj_query* queries, const uint8_t* qdesc, int nq, float th, int mode, int maxDist,
+                                 const uint8_t* occupied, int* curMatch, int checkOri, int* nmatches) {
     ORBM_ENTER(h);
     if (!cur || !sf || nlevels < 1 || !curMatch || !nmatches || nq < 0 || (nq > 0 && (!queries || !qdesc)))
         return fail(ORB_ERR_INVALID, "orbm_search_by_projection: bad arguments");
@@ -733,9 +758,11 @@ int orbm_search_by_projection(orbm_handle h, orbm_frame cur, const float* sf, in
     ORB_CHECK(h->out2.reserve((size_t)(nq + 1) * 4 * 2));
     ORB_CHECK(h->out3.reserve(16));
     int* pushBin = h->out2.as<int>();
-    proj_replay_kernel<<<1, 32, 0, st>>>(d, h->ws0.as<AreaQuery>(), h->in0.as<orbm_proj_query>(), nq, h->ws1.as<int>(),
-                                         h->ws2.as<int2>(), checkOri, h->in4.as<unsigned char>(), h->out0.as<int>(), pushBin,
-                                         pushBin + nq + 1, h->out3.as<int>());
+    if ((size_t)n + 16 > kReplaySmemMax) return fail(ORB_ERR_CAPACITY, "orbm_search_by_projection: %d keypoints exceed the replay state", n);
+    ORB_CUDA(cudaFuncSetAttribute(proj_replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kReplaySmemMax));
+    proj_replay_kernel<<<1, 32, (size_t)n + 16, st>>>(d, h->ws0.as<AreaQuery>(), h->in0.as<orbm_proj_query>(), nq, h->ws1.as<int>(),
+                                                      h->ws2.as<int2>(), checkOri, maxDist, h->in4.as<unsigned char>(), h->out0.as<int>(),
+                                                      pushBin, pushBin + nq + 1, h->out3.as<int>());
     h->launches += 1;
     ORB_CUDA(cudaGetLastError());
     ORB_CUDA(cudaMemcpyAsync(curMatch, h->out0.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
@@ -773,8 +800,11 @@ int orbm_search_by_projection_points(orbm_handle h, orbm_frame f, const float* s
     ORB_CHECK(run_candidates(h, d, h->in1.as<uint4>(), nq, uRight ? h->in3.as<float>() : nullptr, &total));
     ORB_CHECK(h->out0.reserve((size_t)(n + 1) * 4));
     ORB_CHECK(h->out3.reserve(16));
-    point_replay_kernel<<<1, 32, 0, st>>>(d, h->ws0.as<AreaQuery>(), h->in0.as<orbm_point_query>(), nq, h->ws1.as<int>(),
-                                          h->ws2.as<int2>(), ratio, h->in4.as<unsigned char>(), h->out0.as<int>(), h->out3.as<int>());
+    if ((size_t)n + 16 > kReplaySmemMax) return fail(ORB_ERR_CAPACITY, "orbm_search_by_projection_points: %d keypoints exceed the replay state", n);
+    ORB_CUDA(cudaFuncSetAttribute(point_replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kReplaySmemMax));
+    point_replay_kernel<<<1, 32, (size_t)n + 16, st>>>(d, h->ws0.as<AreaQuery>(), h->in0.as<orbm_point_query>(), nq, h->ws1.as<int>(),
+                                                       h->ws2.as<int2>(), ratio, h->in4.as<unsigned char>(), h->out0.as<int>(),
+                                                       h->out3.as<int>());
     h->launches += 1;
     ORB_CUDA(cudaGetLastError());
     ORB_CUDA(cudaMemcpyAsync(match, h->out0.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));

@@ -294,7 +294,7 @@ class Matcher:
         return n.value, m12, prev
 
     def search_by_projection(self, cur, scale_factors, queries, qdesc, th, mode=0, occupied=None, u_right=None,
-                             mbf=0.0, check_ori=True):
+                             mbf=0.0, check_ori=True, max_distance=100):
         sf = np.ascontiguousarray(scale_factors, np.float32)
         q = np.ascontiguousarray(queries, PROJ_QUERY_DTYPE)
         qd = np.ascontiguousarray(qdesc, np.uint8)
@@ -302,9 +302,9 @@ class Matcher:
         ur = None if u_right is None else np.ascontiguousarray(u_right, np.float32)
         match = np.empty(cur.n, np.int32)
         n = C.c_int()
-        _check(self.L.orbm_search_by_projection(self.h, cur.f, _p(sf), len(sf), _p(ur), C.c_float(mbf), _p(q), _p(qd),
-                                                len(q), C.c_float(th), mode, _p(occ), _p(match), int(check_ori),
-                                                C.byref(n)))
+        _check(self.L.orbm_search_by_projection_ex(self.h, cur.f, _p(sf), len(sf), _p(ur), C.c_float(mbf), _p(q), _p(qd),
+                                                   len(q), C.c_float(th), mode, max_distance, _p(occ), _p(match),
+                                                   int(check_ori), C.byref(n)))
         return n.value, match
 
     def search_by_projection_points(self, f, scale_factors, queries, qdesc, th, ratio, occupied=None, u_right=None):
