@@ -60,6 +60,29 @@ def test_extract_matches_oracle(oracle, seed, w, h, nf, noise):
     ex.close()
 
 
+@pytest.mark.parametrize("nf,scale,nlevels,ini,mn,w,h", [
+    (300, 1.5, 4, 12, 5, 640, 480),      # other constructor arguments than the shipped YAMLs
+    (1200, 1.2, 8, 12, 7, 752, 480),     # EuRoC stereo / KITTI04-12 settings (iniThFAST 12)
+    (500, 2.0, 3, 20, 7, 800, 600),      # scale 2: the resize window is wider than the fast path assumes
+    (400, 1.2, 1, 20, 7, 320, 240),      # a single level
+    (1000, 1.1, 12, 30, 10, 752, 480),   # many shallow levels
+])
+def test_other_constructor_arguments(oracle, nf, scale, nlevels, ini, mn, w, h):
+    img = synth_frame(11, w, h)
+    ex = orbb200.Extractor(nf, scale, nlevels, ini, mn, max_width=w, max_height=h)
+    oe = oracle.extractor(nf, scale, nlevels, ini, mn)
+    kps, desc = ex(img)
+    rk, rd = oe.extract(img)
+    t, rt = ex.tables(), oe.tables()
+    for k in rt:
+        assert np.array_equal(t[k], rt[k]), k
+    for l in range(nlevels):
+        assert np.array_equal(ex.level(l), oe.level_padded(l)), "pyramid level %d" % l
+    assert kps.tobytes() == rk.tobytes()
+    assert np.array_equal(desc, rd)
+    ex.close()
+
+
 def test_batch_equals_single_and_oracle(oracle):
     frames = np.stack([synth_frame(100 + i, 752, 480) for i in range(5)] + [synth_frame(200, 752, 480, noise_only=True)])
     ex = orbb200.Extractor(1000, max_width=752, max_height=480, max_batch=4)   # 6 frames -> chunks of 4 + 2

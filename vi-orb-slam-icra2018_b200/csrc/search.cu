@@ -174,7 +174,7 @@ candidates_kernel(FrameDev f, const AreaQuery* __restrict__ queries, const uint4
             const uint4 qa = qdesc[2 * qi], qb = qdesc[2 * qi + 1];
             int2* out = cand + offsets[qi];
             n = warp_enumerate(f, q, uRight, [&](int idx, int pos) {
-                out[pos] = make_int2(idx, hamming256(qa, qb, f.desc[2 * idx], f.desc[2 * idx + 1]));
+                out[pos] = make_int2(idx | (f.keys[idx].octave << 24), hamming256(qa, qb, f.desc[2 * idx], f.desc[2 * idx + 1]));
             });
         }
     }
@@ -259,44 +259,55 @@ __device__ __forceinline__ void warp_min2(int& best, int& second) {
     }
 }
 
-// rotation-histogram tail shared by the searches: pushes are (bin, value) pairs in push order
-__device__ void prune_pushes(const int* pushBin, const int* pushVal, int nPush, int* hist, int* target, bool guardMatched,
-                             int* nmatches) {
+constexpr int kCandIdxMask = 0x00ffffff;   // candidate.x = keypoint index | octave << 24
+
+// Rotation-histogram tail shared by the searches (e.g. ORBmatcher.cc:473-512).  Pushes were recorded in order as
+// (angle source A, angle source B, value to clear); bins are computed here, in parallel, because only their COUNTS
+// matter until the end.  guardMatched: SearchForInitialization decrements only for still-matched entries (:503-507);
+// the projection searches decrement per push, duplicates included (:1483-1491).
+template <class AngleA, class AngleB>
+__device__ void histogram_prune(const int* pushA, const int* pushB, const int* pushVal, int nPush, int* hist, int* target,
+                                bool guardMatched, int* nmatches, AngleA angleA, AngleB angleB) {
     const int lane = threadIdx.x & 31;
     __shared__ int keep[3];
+    __shared__ int removed;
+    if (lane == 0) removed = 0;
+    __syncwarp();
+    for (int k = lane; k < nPush; k += 32) atomicAdd(&hist[rotation_bin(angleA(pushA[k]), angleB(pushB[k]))], 1);
     __syncwarp();
     if (lane == 0) three_maxima(hist, keep[0], keep[1], keep[2]);
     __syncwarp();
-    int removed = 0;
-    if (lane == 0) {   // sequential: the same value can be pushed twice and every push decrements (ORBmatcher.cc:1483-1491)
-        for (int k = 0; k < nPush; ++k) {
-            const int b = pushBin[k];
-            if (b == keep[0] || b == keep[1] || b == keep[2]) continue;
-            const int v = pushVal[k];
-            if (guardMatched) {
-                if (target[v] >= 0) { target[v] = -1; ++removed; }
-            } else {
-                target[v] = -1;
-                ++removed;
-            }
+    for (int k = lane; k < nPush; k += 32) {
+        const int b = rotation_bin(angleA(pushA[k]), angleB(pushB[k]));
+        if (b == keep[0] || b == keep[1] || b == keep[2]) continue;
+        const int v = pushVal[k];
+        if (guardMatched) {
+            if (target[v] >= 0) { target[v] = -1; atomicAdd(&removed, 1); }   // each value is pushed at most once here
+        } else {
+            target[v] = -1;
+            atomicAdd(&removed, 1);
         }
-        *nmatches -= removed;
     }
+    __syncwarp();
+    if (lane == 0) *nmatches -= removed;
     __syncwarp();
 }
 
 // Ordered walk over the queries by ONE warp.  The order-dependent state (what earlier queries matched) lives in shared
-// memory; the per-query metadata is fetched 32 queries at a time and the first 32 candidates of the NEXT query are
-// loaded while the current one is reduced, so the dependent chain per query is shared-memory lookups and shuffles
-// rather than global-memory round trips.  skip(c) -> candidate c is ignored; accept(i, a, best, second) is warp-uniform.
-template <class Skip, class Accept>
+// memory; per-query metadata is fetched 32 queries at a time and the first 32 candidates of the NEXT query are loaded
+// while the current one is reduced; the winning candidates travel by shuffle.  The dependent chain per query is
+// therefore shared-memory lookups and shuffles only -- no global-memory round trip.
+//   meta(qi)                      -> small per-query integer needed by accept (fetched with the batch)
+//   skip(c)                       -> candidate c is ignored (dynamic state)
+//   accept(i, metaVal, best, second, bestX, secondX) is warp-uniform; bestX/secondX = candidate.x of the winners
+template <class Meta, class Skip, class Accept>
 __device__ __forceinline__ void replay_queries(const AreaQuery* __restrict__ q, const int* __restrict__ offsets,
-                                               const int2* __restrict__ cand, int nq, Skip skip, Accept accept) {
+                                               const int2* __restrict__ cand, int nq, Meta meta, Skip skip, Accept accept) {
     const int lane = threadIdx.x & 31;
     for (int i0 = 0; i0 < nq; i0 += 32) {
         const int qi = i0 + lane;
-        int act = 0, a = 0, b = 0;
-        if (qi < nq) { act = q[qi].active; a = offsets[qi]; b = offsets[qi + 1]; }
+        int act = 0, a = 0, b = 0, mv = 0;
+        if (qi < nq) { act = q[qi].active; a = offsets[qi]; b = offsets[qi + 1]; mv = meta(qi); }
         int na = __shfl_sync(0xffffffffu, a, 0), nb = __shfl_sync(0xffffffffu, b, 0), nact = __shfl_sync(0xffffffffu, act, 0);
         int2 pre = (nact && na + lane < nb) ? cand[na + lane] : make_int2(-1, 0);
         const int m = min(32, nq - i0);
@@ -308,17 +319,27 @@ __device__ __forceinline__ void replay_queries(const AreaQuery* __restrict__ q, 
                 pre = (nact && na + lane < nb) ? cand[na + lane] : make_int2(-1, 0);
             }
             if (!cact || ca == cb) continue;
-            int best = kNone, second = kNone;
-            if (cur.x >= 0 && !skip(cur)) best = (cur.y << kOrdShift) | lane;
+            int bk = kNone, sk = kNone, bx = -1, sx = -1;   // this lane's best / second key and their candidate.x
+            if (cur.x >= 0 && !skip(cur)) { bk = (cur.y << kOrdShift) | lane; bx = cur.x; }
             for (int k = ca + 32 + lane; k < cb; k += 32) {
                 const int2 c = cand[k];
                 if (skip(c)) continue;
                 const int key = (c.y << kOrdShift) | (k - ca);
-                second = min(second, max(key, best));
-                best = min(best, key);
+                if (key < bk) { sk = bk; sx = bx; bk = key; bx = c.x; }
+                else if (key < sk) { sk = key; sx = c.x; }
             }
-            warp_min2(best, second);
-            accept(i0 + j, ca, best, second);
+            int gb = bk, gs = sk;
+            warp_min2(gb, gs);
+            // keys are unique (they carry the candidate's position), so exactly one lane owns each winner
+            int bestX = -1, secondX = -1;
+            if (gb != kNone) bestX = __shfl_sync(0xffffffffu, bx, __ffs(__ballot_sync(0xffffffffu, bk == gb)) - 1);
+            if (gs != kNone) {
+                const unsigned m1 = __ballot_sync(0xffffffffu, bk == gs), m2 = __ballot_sync(0xffffffffu, sk == gs);
+                const int fromBest = __shfl_sync(0xffffffffu, bx, m1 ? __ffs(m1) - 1 : 0);
+                const int fromSecond = __shfl_sync(0xffffffffu, sx, m2 ? __ffs(m2) - 1 : 0);
+                secondX = m1 ? fromBest : fromSecond;
+            }
+            accept(i0 + j, __shfl_sync(0xffffffffu, mv, j), gb, gs, bestX, secondX);
         }
     }
 }
@@ -326,8 +347,8 @@ __device__ __forceinline__ void replay_queries(const AreaQuery* __restrict__ q, 
 // SearchForInitialization replay (ORBmatcher.cc:417-517). One warp; m21 / vMatchedDistance in shared memory.
 __global__ void __launch_bounds__(32)
 init_replay_kernel(FrameDev f1, FrameDev f2, const AreaQuery* __restrict__ q, const int* __restrict__ offsets,
-                   const int2* __restrict__ cand, float ratio, int checkOri, float* prevXY, int* m12, int* pushBin,
-                   int* pushVal, int* nmatchesOut) {
+                   const int2* __restrict__ cand, float ratio, int checkOri, float* prevXY, int* m12, int* pushA,
+                   int* pushB, int* nmatchesOut) {
     extern __shared__ int dyn[];
     int* m21 = dyn;
     int* matchedDist = dyn + f2.n;
@@ -340,28 +361,27 @@ init_replay_kernel(FrameDev f1, FrameDev f2, const AreaQuery* __restrict__ q, co
     for (int i = lane; i < f2.n; i += 32) { m21[i] = -1; matchedDist[i] = INT_MAX; }
     __syncwarp();
     int nPush = 0;
-    replay_queries(q, offsets, cand, f1.n,
-        [&](const int2& c) { return matchedDist[c.x] <= c.y; },                               // :444
-        [&](int i1, int a, int best, int second) {
+    replay_queries(q, offsets, cand, f1.n, [](int) { return 0; },
+        [&](const int2& c) { return matchedDist[c.x & kCandIdxMask] <= c.y; },               // :444
+        [&](int i1, int, int best, int second, int bestX, int) {
             const int bd = best == kNone ? INT_MAX : best >> kOrdShift;
             const int sd = second == kNone ? INT_MAX : second >> kOrdShift;
             if (bd <= kThLow && (float)bd < __fmul_rn((float)sd, ratio)) {                    // :459-461
                 if (lane == 0) {
-                    const int i2 = cand[a + (best & kOrdMask)].x;
-                    if (m21[i2] >= 0) { m12[m21[i2]] = -1; --nmatches; }
+                    const int i2 = bestX & kCandIdxMask;
+                    if (m21[i2] >= 0) { m12[m21[i2]] = -1; --nmatches; }                      // :463-467
                     m12[i1] = i2; m21[i2] = i1; matchedDist[i2] = bd; ++nmatches;
-                    if (checkOri) {
-                        const int bin = rotation_bin(f1.keys[i1].angle, f2.keys[i2].angle);
-                        hist[bin] += 1;
-                        pushBin[nPush] = bin; pushVal[nPush] = i1;
-                    }
+                    if (checkOri) { pushA[nPush] = i1; pushB[nPush] = i2; }
                 }
                 if (checkOri) ++nPush;
                 __syncwarp();
             }
         });
     __threadfence_block();
-    if (checkOri) prune_pushes(pushBin, pushVal, nPush, hist, m12, true, &nmatches);
+    __syncwarp();
+    if (checkOri)
+        histogram_prune(pushA, pushB, pushA, nPush, hist, m12, true, &nmatches,
+                        [&](int i1) { return f1.keys[i1].angle; }, [&](int i2) { return f2.keys[i2].angle; });
     __syncwarp();
     for (int i1 = lane; i1 < f1.n; i1 += 32)
         if (m12[i1] >= 0) {                                             // :515-517
@@ -376,7 +396,7 @@ init_replay_kernel(FrameDev f1, FrameDev f2, const AreaQuery* __restrict__ q, co
 __global__ void __launch_bounds__(32)
 proj_replay_kernel(FrameDev cur, const AreaQuery* __restrict__ q, const orbm_proj_query* __restrict__ pq, int nq,
                    const int* __restrict__ offsets, const int2* __restrict__ cand, int checkOri, int maxDist,
-                   const unsigned char* __restrict__ occIn, int* curMatch, int* pushBin, int* pushVal, int* nmatchesOut) {
+                   const unsigned char* __restrict__ occIn, int* curMatch, int* pushA, int* pushB, int* nmatchesOut) {
     extern __shared__ int dyn[];
     unsigned char* occ = reinterpret_cast<unsigned char*>(dyn);
     __shared__ int hist[kHistoLength];
@@ -387,28 +407,27 @@ proj_replay_kernel(FrameDev cur, const AreaQuery* __restrict__ q, const orbm_pro
     for (int i = lane; i < cur.n; i += 32) { curMatch[i] = -1; occ[i] = occIn[i]; }
     __syncwarp();
     int nPush = 0;
-    replay_queries(q, offsets, cand, nq,
-        [&](const int2& c) { return occ[c.x] != 0; },                                         // :1428-1430
-        [&](int i, int a, int best, int) {
+    replay_queries(q, offsets, cand, nq, [&](int qi) { return pq[qi].obs_positive; },
+        [&](const int2& c) { return occ[c.x & kCandIdxMask] != 0; },                          // :1428-1430
+        [&](int i, int obs, int best, int, int bestX, int) {
             const int bd = best == kNone ? 256 : best >> kOrdShift;
             if (bd <= maxDist) {                                                              // :1453 / :1583
                 if (lane == 0) {
-                    const int i2 = cand[a + (best & kOrdMask)].x;
+                    const int i2 = bestX & kCandIdxMask;
                     curMatch[i2] = i;
-                    occ[i2] = pq[i].obs_positive ? 1 : 0;
+                    occ[i2] = obs ? 1 : 0;
                     ++nmatches;
-                    if (checkOri) {
-                        const int bin = rotation_bin(pq[i].angle, cur.keys[i2].angle);
-                        hist[bin] += 1;
-                        pushBin[nPush] = bin; pushVal[nPush] = i2;
-                    }
+                    if (checkOri) { pushA[nPush] = i; pushB[nPush] = i2; }
                 }
                 if (checkOri) ++nPush;
                 __syncwarp();
             }
         });
     __threadfence_block();
-    if (checkOri) prune_pushes(pushBin, pushVal, nPush, hist, curMatch, false, &nmatches);
+    __syncwarp();
+    if (checkOri)
+        histogram_prune(pushA, pushB, pushB, nPush, hist, curMatch, false, &nmatches,
+                        [&](int i) { return pq[i].angle; }, [&](int i2) { return cur.keys[i2].angle; });
     __syncwarp();
     if (lane == 0) *nmatchesOut = nmatches;
 }
@@ -424,22 +443,19 @@ point_replay_kernel(FrameDev f, const AreaQuery* __restrict__ q, const orbm_poin
     for (int i = lane; i < f.n; i += 32) { match[i] = -1; occ[i] = occIn[i]; }
     __syncwarp();
     int nmatches = 0;
-    replay_queries(q, offsets, cand, nq,
-        [&](const int2& c) { return occ[c.x] != 0; },                                         // :84-86
-        [&](int i, int a, int best, int second) {
+    replay_queries(q, offsets, cand, nq, [&](int qi) { return pq[qi].obs_positive; },
+        [&](const int2& c) { return occ[c.x & kCandIdxMask] != 0; },                          // :84-86
+        [&](int i, int obs, int best, int second, int bestX, int secondX) {
             const int bd = best == kNone ? 256 : best >> kOrdShift;
             if (bd > kThHigh) return;                                                         // :115
-            const int bi = cand[a + (best & kOrdMask)].x;
-            const int bestLevel = f.keys[bi].octave;
+            const int bestLevel = bestX >> 24;
             int sd = 256, secondLevel = -1;
-            if (second != kNone) {
-                sd = second >> kOrdShift;
-                secondLevel = f.keys[cand[a + (second & kOrdMask)].x].octave;
-            }
+            if (second != kNone) { sd = second >> kOrdShift; secondLevel = secondX >> 24; }
             if (bestLevel == secondLevel && (float)bd > __fmul_rn(ratio, (float)sd)) return;  // :118-119
             if (lane == 0) {
+                const int bi = bestX & kCandIdxMask;
                 match[bi] = i;
-                occ[bi] = pq[i].obs_positive ? 1 : 0;
+                occ[bi] = obs ? 1 : 0;
             }
             ++nmatches;
             __syncwarp();
