@@ -247,6 +247,7 @@ allpairs_kernel(const uint4* __restrict__ table, const float* __restrict__ angle
                         const int sd = sk == kNoKey ? 256 : (sk >> kKeyShift);
                         if (bd < kThLow && (float)bd < __fmul_rn(ratio, (float)sd)) {
                             const int i2 = bk & kKeyIdxMask;
+                            __syncwarp();   // all lanes are done reading matched2 for this query
                             if (lane == 0) {
                                 S.matched2[i2] = 1;
                                 if (checkOri) S.hist[rotation_bin(a1[i1], a2[i2])] += 1;

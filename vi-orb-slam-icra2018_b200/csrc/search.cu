@@ -367,6 +367,7 @@ init_replay_kernel(FrameDev f1, FrameDev f2, const AreaQuery* __restrict__ q, co
             const int bd = best == kNone ? INT_MAX : best >> kOrdShift;
             const int sd = second == kNone ? INT_MAX : second >> kOrdShift;
             if (bd <= kThLow && (float)bd < __fmul_rn((float)sd, ratio)) {                    // :459-461
+                __syncwarp();   // every lane has finished reading the state it is about to change
                 if (lane == 0) {
                     const int i2 = bestX & kCandIdxMask;
                     if (m21[i2] >= 0) { m12[m21[i2]] = -1; --nmatches; }                      // :463-467
@@ -412,6 +413,7 @@ proj_replay_kernel(FrameDev cur, const AreaQuery* __restrict__ q, const orbm_pro
         [&](int i, int obs, int best, int, int bestX, int) {
             const int bd = best == kNone ? 256 : best >> kOrdShift;
             if (bd <= maxDist) {                                                              // :1453 / :1583
+                __syncwarp();
                 if (lane == 0) {
                     const int i2 = bestX & kCandIdxMask;
                     curMatch[i2] = i;
@@ -452,6 +454,7 @@ point_replay_kernel(FrameDev f, const AreaQuery* __restrict__ q, const orbm_poin
             int sd = 256, secondLevel = -1;
             if (second != kNone) { sd = second >> kOrdShift; secondLevel = secondX >> 24; }
             if (bestLevel == secondLevel && (float)bd > __fmul_rn(ratio, (float)sd)) return;  // :118-119
+            __syncwarp();
             if (lane == 0) {
                 const int bi = bestX & kCandIdxMask;
                 match[bi] = i;
