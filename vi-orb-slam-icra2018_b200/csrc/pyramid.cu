@@ -92,6 +92,18 @@ pyramid_resize_kernel(unsigned char* __restrict__ pyr, long long pyrFrameBytes, 
     const int rowsTotal = dh + 2 * kEdge;
     if (fast) {
         // the common case; kept in its own loop so that nothing of the per-pixel border path is hoisted into it
+        // Consecutive output rows usually step one source row (scale 1.2: five times out of six), so the lower source
+        // row's horizontal sums become the next output row's upper ones: kept in registers, chosen by a warp-uniform test.
+        int keptRow = -0x40000000, kept[4] = {0, 0, 0, 0};
+        auto hsum = [&](const unsigned char* row, int (&t)[4]) {
+            const unsigned int* p = reinterpret_cast<const unsigned int*>(row + base);
+            const unsigned int w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const unsigned int v = __funnelshift_r(hiWin[k] ? w1 : w0, hiWin[k] ? w2 : w1, shiftBits[k]);
+                t[k] = (int)__dp2a_lo(cf[k], v, 0u);              // S[x0]*a0 + S[x0+1]*a1
+            }
+        };
 #pragma unroll 2
         for (int r = 0; r < PY_ROWS; ++r) {
             const int by = by0 + r;
@@ -99,18 +111,21 @@ pyramid_resize_kernel(unsigned char* __restrict__ pyr, long long pyrFrameBytes, 
             const int dy = reflect101(by - kEdge, dh);
             const int sy0 = __ldg(yofs + dy);
             const short2 b = __ldg(ycoef + dy);
-            const unsigned int* p0 = reinterpret_cast<const unsigned int*>(src0 + (size_t)sy0 * srcPitch + base);
-            const unsigned int* p1 = reinterpret_cast<const unsigned int*>(reinterpret_cast<const unsigned char*>(p0) + srcPitch);
-            const unsigned int a0 = __ldg(p0), a1 = __ldg(p0 + 1), a2 = __ldg(p0 + 2);
-            const unsigned int c0 = __ldg(p1), c1 = __ldg(p1 + 1), c2 = __ldg(p1 + 2);
+            const unsigned char* r0 = src0 + (size_t)sy0 * srcPitch;
+            int t0[4], t1[4];
+            if (sy0 == keptRow) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) t0[k] = kept[k];
+            } else {
+                hsum(r0, t0);
+            }
+            hsum(r0 + srcPitch, t1);
+            keptRow = sy0 + 1;
             unsigned int word = 0;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const unsigned int v0 = __funnelshift_r(hiWin[k] ? a1 : a0, hiWin[k] ? a2 : a1, shiftBits[k]);
-                const unsigned int v1 = __funnelshift_r(hiWin[k] ? c1 : c0, hiWin[k] ? c2 : c1, shiftBits[k]);
-                const int t0 = (int)__dp2a_lo(cf[k], v0, 0u);     // S[x0]*a0 + S[x0+1]*a1
-                const int t1 = (int)__dp2a_lo(cf[k], v1, 0u);
-                const unsigned int v = (unsigned int)(((((int)b.x * (t0 >> 4)) >> 16) + (((int)b.y * (t1 >> 4)) >> 16) + 2) >> 2);
+                kept[k] = t1[k];
+                const unsigned int v = (unsigned int)(((((int)b.x * (t0[k] >> 4)) >> 16) + (((int)b.y * (t1[k] >> 4)) >> 16) + 2) >> 2);
                 word |= (v & 0xffu) << (8 * k);
             }
             *reinterpret_cast<unsigned int*>(dst + (size_t)by * dstPitch) = word;
