@@ -183,6 +183,17 @@ int orbm_search_for_triangulation(orbm_handle h, orbm_frame kf1, orbm_frame kf2,
                                   const float* scale_factors2, const float* level_sigma2_2, int nlevels,
                                   int only_stereo, int check_orientation, int* matches12, int* nmatches);
 
+/* SearchByBoW, both overloads: (KeyFrame*, Frame&, vpMapPointMatches) ORBmatcher.cc:159-288 with strict_low = 0
+ * (accept best <= TH_LOW, valid2 = NULL) and (KeyFrame*, KeyFrame*, vpMatches12) ORBmatcher.cc:522-655 with strict_low = 1
+ * (accept best < TH_LOW).  valid1 / valid2: the keypoint's map point exists and is not bad.  Feature vectors as in
+ * orbm_search_for_triangulation.  matches12[n1] / matches21[n2]: partner index or -1 (the Frame overload's
+ * vpMapPointMatches[i2] is pKF's map point at matches21[i2]).                                                       */
+int orbm_search_by_bow(orbm_handle h, orbm_frame kf1, orbm_frame f2,
+                       int n_nodes1, const int* node_id1, const int* node_start1, const int* node_idx1,
+                       int n_nodes2, const int* node_id2, const int* node_start2, const int* node_idx2,
+                       const uint8_t* valid1, const uint8_t* valid2, float nnratio, int check_orientation,
+                       int strict_low, int* matches12, int* matches21, int* nmatches);
+
 /* Brute-force matching of n_pairs independent (query set, train set) pairs: every query against every train
  * descriptor, best / second-best / index with the reference's strict '<' (first wins), acceptance
  * best <= TH_LOW && best < (float)second * nnratio, rotation-histogram pruning (ORBmatcher.cc:432-461, 473-512).

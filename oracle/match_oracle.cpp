@@ -293,6 +293,46 @@ int search_for_triangulation(const FrameArrays& K1, const FrameArrays& K2, const
     return nmatches;
 }
 
+// ORBmatcher.cc:159-288 and 522-655
+int search_by_bow(const FrameArrays& K1, const FrameArrays& K2, const FeatVec& fv1, const FeatVec& fv2,
+                  const uint8_t* valid1, const uint8_t* valid2, float nnratio, bool checkOri, bool strictLow, int* m12,
+                  int* m21) {
+    int nmatches = 0;
+    std::fill(m12, m12 + K1.n, -1);
+    std::fill(m21, m21 + K2.n, -1);
+    RotHist hist;
+    int a = 0, b = 0;
+    while (a < fv1.nNodes && b < fv2.nNodes) {
+        if (fv1.nodeId[a] < fv2.nodeId[b]) { ++a; continue; }
+        if (fv1.nodeId[a] > fv2.nodeId[b]) { ++b; continue; }
+        for (int p1 = fv1.start[a]; p1 < fv1.start[a + 1]; ++p1) {
+            const int idx1 = fv1.idx[p1];
+            if (valid1 && !valid1[idx1]) continue;
+            const uint8_t* d1 = K1.desc + (size_t)idx1 * 32;
+            int best = 256, second = 256, bestIdx = -1;
+            for (int p2 = fv2.start[b]; p2 < fv2.start[b + 1]; ++p2) {
+                const int idx2 = fv2.idx[p2];
+                if (m21[idx2] >= 0) continue;                    // vbMatched2 / vpMapPointMatches[realIdxF]
+                if (valid2 && !valid2[idx2]) continue;
+                const int dist = descriptor_distance(d1, K2.desc + (size_t)idx2 * 32);
+                if (dist < best) { second = best; best = dist; bestIdx = idx2; }
+                else if (dist < second) second = dist;
+            }
+            const bool low = strictLow ? best < TH_LOW : best <= TH_LOW;
+            if (low && (float)best < nnratio * (float)second) {
+                m12[idx1] = bestIdx;
+                m21[bestIdx] = idx1;
+                ++nmatches;
+                if (checkOri) hist.add(K1.keysUn[idx1].angle, K2.keysUn[bestIdx].angle, idx1);
+            }
+        }
+        ++a; ++b;
+    }
+    if (checkOri)
+        hist.pruneMinor([&](int i1) { m21[m12[i1]] = -1; m12[i1] = -1; --nmatches; });
+    return nmatches;
+}
+
 int bruteforce_match(const uint8_t* q, const float* qAngle, int nq, const uint8_t* t, const float* tAngle, int nt,
                      float nnratio, bool checkOri, int* bestDist, int* secondDist, int* bestIdx, int* m12) {
     int nmatches = 0;

@@ -80,6 +80,15 @@ int search_for_triangulation(const FrameArrays& K1, const FrameArrays& K2, const
                              const float* uRight2, const EpiParams& ep, bool onlyStereo, bool checkOri,
                              int* matches12 /* n1, out */);
 
+// SearchByBoW, both overloads (ORBmatcher.cc:159-288 KeyFrame->Frame, 522-655 KeyFrame->KeyFrame): brute force inside
+// shared vocabulary nodes, one-to-one through the "already matched" flags of the second frame.
+//   strictLow = false : accept best <= TH_LOW (KF->Frame, :227);  true : best < TH_LOW (KF->KF, :598)
+//   valid1 / valid2   : keypoint has a usable map point (KF->Frame has no test on the frame side: pass null)
+// matches12[i1] = i2 or -1, matches21[i2] = i1 or -1 (the Frame overload reports per frame keypoint, the KF one per idx1).
+int search_by_bow(const FrameArrays& K1, const FrameArrays& K2, const FeatVec& fv1, const FeatVec& fv2,
+                  const uint8_t* valid1, const uint8_t* valid2, float nnratio, bool checkOri, bool strictLow,
+                  int* matches12, int* matches21);
+
 // Brute force, every query against every train descriptor (no window, no one-to-one constraint):
 // best / second / index with strict '<' (first wins), accept best<=TH_LOW && best < (float)second*ratio,
 // then the rotation-histogram pruning.  (SearchForInitialization's inner loop + accept rule, ORBmatcher.cc:432-461)

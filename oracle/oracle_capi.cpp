@@ -176,6 +176,13 @@ int orbo_search_triangulation(void* k1, void* k2, int nNodes1, const int* nodeId
     return search_for_triangulation(((OrboFrame*)k1)->fa, ((OrboFrame*)k2)->fa, a, b, has1, has2, uR1, uR2, ep,
                                     onlyStereo != 0, checkOri != 0, m12);
 }
+int orbo_search_bow(void* k1, void* k2, int nNodes1, const int* nodeId1, const int* start1, const int* idx1, int nNodes2,
+                    const int* nodeId2, const int* start2, const int* idx2, const uint8_t* valid1, const uint8_t* valid2,
+                    float ratio, int checkOri, int strictLow, int* m12, int* m21) {
+    FeatVec a{nNodes1, nodeId1, start1, idx1}, b{nNodes2, nodeId2, start2, idx2};
+    return search_by_bow(((OrboFrame*)k1)->fa, ((OrboFrame*)k2)->fa, a, b, valid1, valid2, ratio, checkOri != 0,
+                         strictLow != 0, m12, m21);
+}
 int orbo_bruteforce(const uint8_t* q, const float* qa, int nq, const uint8_t* t, const float* ta, int nt, float ratio,
                     int checkOri, int* best, int* second, int* idx, int* m12) {
     return bruteforce_match(q, qa, nq, t, ta, nt, ratio, checkOri != 0, best, second, idx, m12);

@@ -337,3 +337,19 @@ class OracleFrame:
                                                _p(s2), _p(i2), _p(has1), _p(has2), _p(ur1), _p(ur2), _p(F12), ex, ey,
                                                _p(sf2), _p(sg2), int(only_stereo), int(check_ori), _p(m12))
         return n, m12
+
+    def search_bow(self, other, fv1, fv2, valid1=None, valid2=None, ratio=0.7, check_ori=True, strict_low=False):
+        """SearchByBoW (ORBmatcher.cc:159-288 strict_low=False, 522-655 strict_low=True) -> (n, matches12, matches21)"""
+        def fv(v):
+            return [np.ascontiguousarray(a, np.int32) for a in v]
+        n1, s1, i1 = fv(fv1)
+        n2, s2, i2 = fv(fv2)
+        v1 = None if valid1 is None else np.ascontiguousarray(valid1, np.uint8)
+        v2 = None if valid2 is None else np.ascontiguousarray(valid2, np.uint8)
+        m12 = np.empty(self.n, np.int32)
+        m21 = np.empty(other.n, np.int32)
+        self.lib.orbo_search_bow.argtypes = ([C.c_void_p, C.c_void_p] + [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p] * 2
+                                             + [C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_void_p])
+        n = self.lib.orbo_search_bow(self.h, other.h, len(n1), _p(n1), _p(s1), _p(i1), len(n2), _p(n2), _p(s2), _p(i2),
+                                     _p(v1), _p(v2), ratio, int(check_ori), int(strict_low), _p(m12), _p(m21))
+        return n, m12, m21

@@ -199,3 +199,25 @@ def test_search_edge_cases(matcher, oracle, pair):
         matcher.search_by_projection(g2, SF, q, da[:4], 15.0)
     with pytest.raises(orbb200.OrbError):
         matcher.frame(ka, da, (0.0, 0.0, 0.0, 480.0))   # empty bounds
+
+
+@pytest.mark.parametrize("name,strict,ratio,ori,use_valid2", [("euroc", False, 0.7, True, False),   # KeyFrame -> Frame
+                                                              ("kitti", True, 0.75, True, True),     # KeyFrame -> KeyFrame
+                                                              ("euroc", True, 0.9, False, True)])
+def test_search_by_bow(matcher, oracle, pair, name, strict, ratio, ori, use_valid2):
+    """SearchByBoW (ORBmatcher.cc:159-288, 522-655): brute force inside shared vocabulary nodes, one-to-one."""
+    ka, da, kb, db, bounds = pair[name]
+    rng = np.random.default_rng(17 + strict)
+    g1, o1 = _frames(matcher, oracle, ka, da, bounds)
+    g2, o2 = _frames(matcher, oracle, kb, db, bounds)
+    fv1 = _feature_vector(ka, 0, 0, cell=64)
+    fv2 = _feature_vector(kb, 7, 3, cell=64)
+    valid1 = (rng.random(len(ka)) < 0.7).astype(np.uint8)
+    valid2 = (rng.random(len(kb)) < 0.8).astype(np.uint8) if use_valid2 else None
+    n, m12, m21 = matcher.search_by_bow(g1, g2, fv1, fv2, valid1, valid2, ratio, ori, strict)
+    rn, rm12, rm21 = o1.search_bow(o2, fv1, fv2, valid1, valid2, ratio, ori, strict)
+    assert n == rn and np.array_equal(m12, rm12) and np.array_equal(m21, rm21)
+    assert n > 50
+    # one-to-one and mutually consistent
+    i1 = np.nonzero(m12 >= 0)[0]
+    assert len(i1) == n and len(set(m12[i1].tolist())) == n and np.array_equal(m21[m12[i1]], i1)

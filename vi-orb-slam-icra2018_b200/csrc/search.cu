@@ -564,6 +564,104 @@ __global__ void fill_int_kernel(int* p, int n, int v) {
     if (i < n) p[i] = v;
 }
 
+// ------------------------------------------------------------------------------------------------ SearchByBoW
+// Both overloads (ORBmatcher.cc:159-288 KeyFrame->Frame, 522-655 KeyFrame->KeyFrame): queries are the feature-vector
+// entries of frame 1 in map order (node id ascending, list order inside a node), candidates the entries of the same
+// node in frame 2.  Phase 1 (one warp per entry): node lookup, static validity, distances.  Phase 2: the ordered
+// one-warp replay with the "already matched" flags of frame 2 in shared memory.
+struct BowParams {
+    FrameDev k1, k2;
+    int nNodes2, nEntries1;
+    const int *nodeId1, *idx1, *nodeId2, *start2, *idx2;
+    const unsigned char *valid1, *valid2;   // may be null: everything valid
+};
+
+__global__ void __launch_bounds__(256)
+bow_candidates_kernel(BowParams P, const int* __restrict__ entryNode, AreaQuery* __restrict__ q, int* __restrict__ counts,
+                      const int* __restrict__ offsets, int2* __restrict__ cand) {
+    const int p1 = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (p1 >= P.nEntries1) return;
+    const int lane = threadIdx.x & 31;
+    const int node = P.nodeId1[entryNode[p1]];
+    int lo = 0, hi = P.nNodes2 - 1, b = -1;
+    while (lo <= hi) {
+        const int mid = (lo + hi) >> 1, v = P.nodeId2[mid];
+        if (v == node) { b = mid; break; }
+        if (v < node) lo = mid + 1; else hi = mid - 1;
+    }
+    const int idx1 = P.idx1[p1];
+    const bool active = b >= 0 && (!P.valid1 || P.valid1[idx1]);
+    int n = 0;
+    if (active) {
+        const uint4 qa = P.k1.desc[2 * idx1], qb = P.k1.desc[2 * idx1 + 1];
+        int2* out = cand ? cand + offsets[p1] : nullptr;
+        for (int k0 = P.start2[b]; k0 < P.start2[b + 1]; k0 += 32) {
+            const int k = k0 + lane;
+            int idx2 = -1;
+            bool ok = false;
+            if (k < P.start2[b + 1]) {
+                idx2 = P.idx2[k];
+                ok = !P.valid2 || P.valid2[idx2];
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, ok);
+            if (ok && out)
+                out[n + __popc(m & ((1u << lane) - 1u))] =
+                    make_int2(idx2 | (P.k2.keys[idx2].octave << 24), hamming256(qa, qb, P.k2.desc[2 * idx2], P.k2.desc[2 * idx2 + 1]));
+            n += __popc(m);
+        }
+    }
+    if (!cand && lane == 0) {
+        counts[p1] = n;
+        q[p1].active = active ? 1 : 0;
+    }
+}
+
+__global__ void __launch_bounds__(32)
+bow_replay_kernel(FrameDev k1, FrameDev k2, const AreaQuery* __restrict__ q, const int* __restrict__ idx1OfEntry, int nq,
+                  const int* __restrict__ offsets, const int2* __restrict__ cand, float ratio, int checkOri, int strictLow,
+                  int* m12, int* m21, int* pushA, int* pushB, int* nmatchesOut) {
+    extern __shared__ int dyn[];
+    unsigned char* matched2 = reinterpret_cast<unsigned char*>(dyn);
+    __shared__ int hist[kHistoLength];
+    __shared__ int nmatches;
+    const int lane = threadIdx.x;
+    if (lane < kHistoLength) hist[lane] = 0;
+    if (lane == 0) nmatches = 0;
+    for (int i = lane; i < k1.n; i += 32) m12[i] = -1;
+    for (int i = lane; i < k2.n; i += 32) { m21[i] = -1; matched2[i] = 0; }
+    __syncwarp();
+    int nPush = 0;
+    replay_queries(q, offsets, cand, nq, [&](int p1) { return idx1OfEntry[p1]; },
+        [&](const int2& c) { return matched2[c.x & kCandIdxMask] != 0; },                     // :203-204 / :576
+        [&](int, int idx1, int best, int second, int bestX, int) {
+            const int bd = best == kNone ? 256 : best >> kOrdShift;
+            const int sd = second == kNone ? 256 : second >> kOrdShift;
+            const bool low = strictLow ? bd < kThLow : bd <= kThLow;                          // :598 / :227
+            if (low && (float)bd < __fmul_rn(ratio, (float)sd)) {                             // :229 / :600
+                __syncwarp();
+                if (lane == 0) {
+                    const int i2 = bestX & kCandIdxMask;
+                    m12[idx1] = i2; m21[i2] = idx1; matched2[i2] = 1; ++nmatches;
+                    if (checkOri) { pushA[nPush] = idx1; pushB[nPush] = i2; }
+                }
+                if (checkOri) ++nPush;
+                __syncwarp();
+            }
+        });
+    __threadfence_block();
+    __syncwarp();
+    if (checkOri) {
+        histogram_prune(pushA, pushB, pushA, nPush, hist, m12, false, &nmatches,
+                        [&](int i1) { return k1.keys[i1].angle; }, [&](int i2) { return k2.keys[i2].angle; });
+        __threadfence_block();
+        __syncwarp();
+        for (int k = lane; k < nPush; k += 32)
+            if (m12[pushA[k]] < 0) m21[pushB[k]] = -1;
+    }
+    __syncwarp();
+    if (lane == 0) *nmatchesOut = nmatches;
+}
+
 }  // namespace orbb
 
 // =================================================================================================== host side
@@ -892,6 +990,74 @@ int orbm_search_for_triangulation(orbm_handle h, orbm_frame k1, orbm_frame k2, i
     ORB_CUDA(cudaGetLastError());
     ORB_CUDA(cudaMemcpyAsync(matches12, h->out0.p, (size_t)n1 * 4, cudaMemcpyDeviceToHost, st));
     ORB_CUDA(cudaMemcpyAsync(nmatches, hist + kHistoLength, 4, cudaMemcpyDeviceToHost, st));
+    ORB_CUDA(cudaStreamSynchronize(st));
+    return ORB_OK;
+}
+
+int orbm_search_by_bow(orbm_handle h, orbm_frame k1, orbm_frame k2, int nNodes1, const int* nodeId1, const int* start1,
+                       const int* idx1, int nNodes2, const int* nodeId2, const int* start2, const int* idx2,
+                       const uint8_t* valid1, const uint8_t* valid2, float ratio, int checkOri, int strictLow,
+                       int* matches12, int* matches21, int* nmatches) {
+    ORBM_ENTER(h);
+    if (!k1 || !k2 || !matches12 || !matches21 || !nmatches || nNodes1 < 0 || nNodes2 < 0 ||
+        (nNodes1 > 0 && (!nodeId1 || !start1 || !idx1)) || (nNodes2 > 0 && (!nodeId2 || !start2 || !idx2)))
+        return fail(ORB_ERR_INVALID, "orbm_search_by_bow: bad arguments");
+    *nmatches = 0;
+    const int n1 = k1->n, n2 = k2->n;
+    for (int i = 0; i < n1; ++i) matches12[i] = -1;
+    for (int i = 0; i < n2; ++i) matches21[i] = -1;
+    if (nNodes1 == 0 || nNodes2 == 0 || n1 == 0 || n2 == 0) return ORB_OK;
+    const int e1 = start1[nNodes1], e2 = start2[nNodes2];
+    for (int a = 1; a < nNodes1; ++a)
+        if (nodeId1[a] <= nodeId1[a - 1]) return fail(ORB_ERR_INVALID, "orbm_search_by_bow: node ids of frame 1 not ascending");
+    for (int a = 1; a < nNodes2; ++a)
+        if (nodeId2[a] <= nodeId2[a - 1]) return fail(ORB_ERR_INVALID, "orbm_search_by_bow: node ids of frame 2 not ascending");
+    if (e1 == 0 || e2 == 0) return ORB_OK;
+    if ((size_t)n2 + 16 > kReplaySmemMax) return fail(ORB_ERR_CAPACITY, "orbm_search_by_bow: %d keypoints exceed the replay state", n2);
+    cudaStream_t st = h->stream;
+    std::vector<int> ints;
+    auto putInts = [&](const int* p, int n) { size_t o = ints.size(); ints.insert(ints.end(), p, p + n); return o; };
+    const size_t oId1 = putInts(nodeId1, nNodes1), oS1 = putInts(start1, nNodes1 + 1), oI1 = putInts(idx1, e1);
+    const size_t oId2 = putInts(nodeId2, nNodes2), oS2 = putInts(start2, nNodes2 + 1), oI2 = putInts(idx2, e2);
+    ORB_CHECK(upload(h->in0, ints.data(), ints.size() * 4, st));
+    if (valid1) ORB_CHECK(upload(h->in2, valid1, (size_t)n1, st));
+    if (valid2) ORB_CHECK(upload(h->in3, valid2, (size_t)n2, st));
+    ORB_CHECK(h->in5.reserve((size_t)(e1 + 1) * 4));                     // entry -> node position
+    ORB_CHECK(h->ws0.reserve((size_t)e1 * sizeof(AreaQuery)));
+    ORB_CHECK(h->out4.reserve((size_t)(e1 + 1) * 4));
+    ORB_CHECK(h->ws1.reserve((size_t)(e1 + 2) * 4));
+    const int* di = h->in0.as<int>();
+    BowParams P;
+    P.k1 = k1->dev(); P.k2 = k2->dev();
+    P.nNodes2 = nNodes2; P.nEntries1 = e1;
+    P.nodeId1 = di + oId1; P.idx1 = di + oI1; P.nodeId2 = di + oId2; P.start2 = di + oS2; P.idx2 = di + oI2;
+    P.valid1 = valid1 ? h->in2.as<unsigned char>() : nullptr;
+    P.valid2 = valid2 ? h->in3.as<unsigned char>() : nullptr;
+    int* counts = h->out4.as<int>();
+    int* offsets = h->ws1.as<int>();
+    tri_entry_node_kernel<<<ceil_div(nNodes1, 128), 128, 0, st>>>(nNodes1, di + oS1, h->in5.as<int>());
+    const int wpb = 8, blocks = ceil_div(e1, wpb);
+    bow_candidates_kernel<<<blocks, wpb * 32, 0, st>>>(P, h->in5.as<int>(), h->ws0.as<AreaQuery>(), counts, nullptr, nullptr);
+    scan_kernel<<<1, 1024, 0, st>>>(counts, offsets, e1);
+    int total = 0;
+    ORB_CUDA(cudaMemcpyAsync(&total, offsets + e1, 4, cudaMemcpyDeviceToHost, st));
+    ORB_CUDA(cudaStreamSynchronize(st));
+    ORB_CHECK(h->ws2.reserve((size_t)(total + 1) * sizeof(int2)));
+    bow_candidates_kernel<<<blocks, wpb * 32, 0, st>>>(P, h->in5.as<int>(), h->ws0.as<AreaQuery>(), counts, offsets, h->ws2.as<int2>());
+    ORB_CHECK(h->out0.reserve((size_t)(n1 + 1) * 4));
+    ORB_CHECK(h->out1.reserve((size_t)(n2 + 1) * 4));
+    ORB_CHECK(h->out2.reserve((size_t)(e1 + 1) * 4 * 2));
+    ORB_CHECK(h->out3.reserve(16));
+    int* pushA = h->out2.as<int>();
+    ORB_CUDA(cudaFuncSetAttribute(bow_replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kReplaySmemMax));
+    bow_replay_kernel<<<1, 32, (size_t)n2 + 16, st>>>(P.k1, P.k2, h->ws0.as<AreaQuery>(), P.idx1, e1, offsets, h->ws2.as<int2>(), ratio,
+                                                      checkOri, strictLow, h->out0.as<int>(), h->out1.as<int>(), pushA,
+                                                      pushA + e1 + 1, h->out3.as<int>());
+    h->launches += 5;
+    ORB_CUDA(cudaGetLastError());
+    ORB_CUDA(cudaMemcpyAsync(matches12, h->out0.p, (size_t)n1 * 4, cudaMemcpyDeviceToHost, st));
+    ORB_CUDA(cudaMemcpyAsync(matches21, h->out1.p, (size_t)n2 * 4, cudaMemcpyDeviceToHost, st));
+    ORB_CUDA(cudaMemcpyAsync(nmatches, h->out3.p, 4, cudaMemcpyDeviceToHost, st));
     ORB_CUDA(cudaStreamSynchronize(st));
     return ORB_OK;
 }

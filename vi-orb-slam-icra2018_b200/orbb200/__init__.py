@@ -340,3 +340,19 @@ class Matcher:
                                                     _p(F12), C.c_float(ex), C.c_float(ey), _p(sf2), _p(sg2), len(sf2),
                                                     int(only_stereo), int(check_ori), _p(m12), C.byref(n)))
         return n.value, m12
+
+    def search_by_bow(self, k1, k2, fv1, fv2, valid1=None, valid2=None, ratio=0.7, check_ori=True, strict_low=False):
+        """SearchByBoW (ORBmatcher.cc:159-288 strict_low=False; 522-655 strict_low=True) -> (n, matches12, matches21)"""
+        def fv(v):
+            return [np.ascontiguousarray(a, np.int32) for a in v]
+        n1, s1, i1 = fv(fv1)
+        n2, s2, i2 = fv(fv2)
+        v1 = None if valid1 is None else np.ascontiguousarray(valid1, np.uint8)
+        v2 = None if valid2 is None else np.ascontiguousarray(valid2, np.uint8)
+        m12 = np.empty(k1.n, np.int32)
+        m21 = np.empty(k2.n, np.int32)
+        n = C.c_int()
+        _check(self.L.orbm_search_by_bow(self.h, k1.f, k2.f, len(n1), _p(n1), _p(s1), _p(i1), len(n2), _p(n2), _p(s2),
+                                         _p(i2), _p(v1), _p(v2), C.c_float(ratio), int(check_ori), int(strict_low),
+                                         _p(m12), _p(m21), C.byref(n)))
+        return n.value, m12, m21
