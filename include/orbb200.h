@@ -194,6 +194,22 @@ int orbm_search_by_bow(orbm_handle h, orbm_frame kf1, orbm_frame f2,
                        const uint8_t* valid1, const uint8_t* valid2, float nnratio, int check_orientation,
                        int strict_low, int* matches12, int* matches21, int* nmatches);
 
+/* The independent projected search inside Fuse (ORBmatcher.cc:892-944, chi2_filter = 1), Fuse with a Sim3 (:1051-1075) and
+ * both directions of SearchBySim3 (:1191-1215, :1271-1295) (chi2_filter = 0): per query KeyFrame::GetFeaturesInArea(u, v,
+ * radius), candidates with octave in [level-1, level], optionally the reprojection chi-square test against
+ * inv_level_sigma2 (5.99 mono / 7.8 when u_right[idx] >= 0), then the closest descriptor (strict '<', first wins).
+ * best_idx[q] = keypoint index or -1, best_dist[q] = distance or 256.  What happens to a hit (Replace / AddObservation /
+ * mutual-agreement check) is pointer-graph work and stays with the caller.                                            */
+typedef struct {
+    float u, v, radius;    /* projection and search radius th * mvScaleFactors[level] */
+    float ur;              /* u - bf/z, only read by the stereo chi-square test */
+    int32_t level;         /* nPredictedLevel */
+    int32_t valid;         /* the point passed the caller's visibility tests */
+} orbm_best_query;
+int orbm_search_projected_best(orbm_handle h, orbm_frame kf, const orbm_best_query* queries, const uint8_t* query_desc,
+                               int nq, int chi2_filter, const float* u_right, const float* inv_level_sigma2, int nlevels,
+                               int* best_idx, int* best_dist);
+
 /* Brute-force matching of n_pairs independent (query set, train set) pairs: every query against every train
  * descriptor, best / second-best / index with the reference's strict '<' (first wins), acceptance
  * best <= TH_LOW && best < (float)second * nnratio, rotation-histogram pruning (ORBmatcher.cc:432-461, 473-512).

@@ -166,6 +166,7 @@ int search_by_projection_frame(const FrameArrays& cur, const float* sf, const fl
         const float radius = th * sf[oct];
         if (mode == 1) cur.featuresInArea(u, v, radius, oct, -1, cand);
         else if (mode == 2) cur.featuresInArea(u, v, radius, 0, oct, cand);
+        else if (mode == 3) cur.featuresInArea(u, v, radius, oct - 1, oct, cand);   // SearchByProjection(KF, Scw, ..): :362-381
         else cur.featuresInArea(u, v, radius, oct - 1, oct + 1, cand);
         if (cand.empty()) continue;
         const uint8_t* d = qdesc + (size_t)i * 32;
@@ -331,6 +332,36 @@ int search_by_bow(const FrameArrays& K1, const FrameArrays& K2, const FeatVec& f
     if (checkOri)
         hist.pruneMinor([&](int i1) { m21[m12[i1]] = -1; m12[i1] = -1; --nmatches; });
     return nmatches;
+}
+
+// ORBmatcher.cc:892-944 (chi2Filter), 1051-1075, 1191-1215, 1271-1295
+void search_projected_best(const FrameArrays& K, const BestQuery* q, const uint8_t* qdesc, int nq, bool chi2Filter,
+                           const float* uRight, const float* invSigma2, int* bestIdx, int* bestDist) {
+    std::vector<int> cand;
+    for (int i = 0; i < nq; ++i) {
+        bestIdx[i] = -1;
+        bestDist[i] = 256;
+        if (!q[i].valid) continue;
+        K.featuresInArea(q[i].u, q[i].v, q[i].radius, -1, -1, cand);     // KeyFrame overload: no level filter
+        const uint8_t* d = qdesc + (size_t)i * 32;
+        for (int idx : cand) {
+            const KeyPoint& kp = K.keysUn[idx];
+            if (kp.octave < q[i].level - 1 || kp.octave > q[i].level) continue;
+            if (chi2Filter) {
+                const float ex = q[i].u - kp.x, ey = q[i].v - kp.y;
+                if (uRight && uRight[idx] >= 0) {
+                    const float er = q[i].ur - uRight[idx];
+                    const float e2 = ex * ex + ey * ey + er * er;
+                    if (e2 * invSigma2[kp.octave] > 7.8) continue;
+                } else {
+                    const float e2 = ex * ex + ey * ey;
+                    if (e2 * invSigma2[kp.octave] > 5.99) continue;
+                }
+            }
+            const int dist = descriptor_distance(d, K.desc + (size_t)idx * 32);
+            if (dist < bestDist[i]) { bestDist[i] = dist; bestIdx[i] = idx; }
+        }
+    }
 }
 
 int bruteforce_match(const uint8_t* q, const float* qAngle, int nq, const uint8_t* t, const float* tAngle, int nt,

@@ -89,6 +89,13 @@ int search_by_bow(const FrameArrays& K1, const FrameArrays& K2, const FeatVec& f
                   const uint8_t* valid1, const uint8_t* valid2, float nnratio, bool checkOri, bool strictLow,
                   int* matches12, int* matches21);
 
+// The independent projected search shared by Fuse (ORBmatcher.cc:892-944), Fuse with Sim3 (:1051-1075) and both directions
+// of SearchBySim3 (:1191-1215, :1271-1295): KeyFrame::GetFeaturesInArea(u, v, radius), keep candidates whose octave is in
+// [level-1, level], optionally Fuse's reprojection chi-square test, strict '<' on the Hamming distance (first wins).
+struct BestQuery { float u, v, radius, ur; int32_t level, valid; };
+void search_projected_best(const FrameArrays& K, const BestQuery* q, const uint8_t* qdesc, int nq, bool chi2Filter,
+                           const float* uRight, const float* invLevelSigma2, int* bestIdx, int* bestDist);
+
 // Brute force, every query against every train descriptor (no window, no one-to-one constraint):
 // best / second / index with strict '<' (first wins), accept best<=TH_LOW && best < (float)second*ratio,
 // then the rotation-histogram pruning.  (SearchForInitialization's inner loop + accept rule, ORBmatcher.cc:432-461)

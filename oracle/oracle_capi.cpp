@@ -183,6 +183,10 @@ int orbo_search_bow(void* k1, void* k2, int nNodes1, const int* nodeId1, const i
     return search_by_bow(((OrboFrame*)k1)->fa, ((OrboFrame*)k2)->fa, a, b, valid1, valid2, ratio, checkOri != 0,
                          strictLow != 0, m12, m21);
 }
+void orbo_search_best(void* k, const BestQuery* q, const uint8_t* qdesc, int nq, int chi2, const float* uRight,
+                      const float* invSigma2, int* bestIdx, int* bestDist) {
+    search_projected_best(((OrboFrame*)k)->fa, q, qdesc, nq, chi2 != 0, uRight, invSigma2, bestIdx, bestDist);
+}
 int orbo_bruteforce(const uint8_t* q, const float* qa, int nq, const uint8_t* t, const float* ta, int nt, float ratio,
                     int checkOri, int* best, int* second, int* idx, int* m12) {
     return bruteforce_match(q, qa, nq, t, ta, nt, ratio, checkOri != 0, best, second, idx, m12);

@@ -353,3 +353,18 @@ class OracleFrame:
         n = self.lib.orbo_search_bow(self.h, other.h, len(n1), _p(n1), _p(s1), _p(i1), len(n2), _p(n2), _p(s2), _p(i2),
                                      _p(v1), _p(v2), ratio, int(check_ori), int(strict_low), _p(m12), _p(m21))
         return n, m12, m21
+
+    def search_best(self, queries, qdesc, chi2=False, u_right=None, inv_sigma2=None):
+        """Independent projected search of Fuse / SearchBySim3 -> (best_idx, best_dist)"""
+        q = np.ascontiguousarray(queries, BEST_QUERY_DTYPE)
+        qd = np.ascontiguousarray(qdesc, np.uint8)
+        ur = None if u_right is None else np.ascontiguousarray(u_right, np.float32)
+        s2 = None if inv_sigma2 is None else np.ascontiguousarray(inv_sigma2, np.float32)
+        bi = np.empty(len(q), np.int32); bd = np.empty(len(q), np.int32)
+        self.lib.orbo_search_best.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                              C.c_void_p, C.c_void_p]
+        self.lib.orbo_search_best(self.h, _p(q), _p(qd), len(q), int(chi2), _p(ur), _p(s2), _p(bi), _p(bd))
+        return bi, bd
+
+
+BEST_QUERY_DTYPE = np.dtype([("u", "<f4"), ("v", "<f4"), ("radius", "<f4"), ("ur", "<f4"), ("level", "<i4"), ("valid", "<i4")])

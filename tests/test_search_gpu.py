@@ -221,3 +221,40 @@ def test_search_by_bow(matcher, oracle, pair, name, strict, ratio, ori, use_vali
     # one-to-one and mutually consistent
     i1 = np.nonzero(m12 >= 0)[0]
     assert len(i1) == n and len(set(m12[i1].tolist())) == n and np.array_equal(m21[m12[i1]], i1)
+
+
+@pytest.mark.parametrize("name,chi2,stereo", [("euroc", False, False), ("kitti", True, False), ("euroc", True, True)])
+def test_search_projected_best(matcher, oracle, pair, name, chi2, stereo):
+    """The independent projected search of Fuse / SearchBySim3 (ORBmatcher.cc:892-944, 1051-1075, 1191-1215, 1271-1295)."""
+    ka, da, kb, db, bounds = pair[name]
+    rng = np.random.default_rng(31 + chi2 + 2 * stereo)
+    g, o = _frames(matcher, oracle, kb, db, bounds)
+    q = np.zeros(len(ka), orbb200.BEST_QUERY_DTYPE)
+    q["u"] = ka["x"] - 7 + rng.normal(0, 1.5, len(ka))
+    q["v"] = ka["y"] - 3 + rng.normal(0, 1.5, len(ka))
+    q["level"] = np.clip(ka["octave"] + rng.integers(0, 2, len(ka)), 0, 7)
+    q["radius"] = 3.0 * SF[q["level"]]
+    q["ur"] = q["u"] - 4.0
+    q["valid"] = rng.random(len(ka)) < 0.9
+    ur = np.where(rng.random(len(kb)) < 0.5, kb["x"] - 4 + rng.normal(0, 2, len(kb)), -1).astype(np.float32) if stereo else None
+    inv_s2 = (1.0 / (SF * SF)).astype(np.float32)
+    bi, bd = matcher.search_projected_best(g, q, da, chi2, ur, inv_s2 if chi2 else None)
+    ri, rd = o.search_best(q, da, chi2, ur, inv_s2 if chi2 else None)
+    assert np.array_equal(bi, ri) and np.array_equal(bd, rd)
+    assert (bi >= 0).sum() > 200 and (bd[bi >= 0] < 256).all() and (bd[bi < 0] == 256).all()
+
+
+def test_search_by_projection_keyframe_sim3_window(matcher, oracle, pair):
+    """SearchByProjection(KeyFrame*, Scw, vpPoints, vpMatched, th) (ORBmatcher.cc:290-403): octave window [level-1, level],
+    occupied = vpMatched[idx] != NULL, acceptance TH_LOW, no orientation check -> mode 3 of the projection search."""
+    ka, da, kb, db, bounds = pair["euroc"]
+    rng = np.random.default_rng(290)
+    g, o = _frames(matcher, oracle, kb, db, bounds)
+    q = _proj_queries(rng, ka)
+    q["obs_positive"] = 1
+    occ = (rng.random(len(kb)) < 0.3).astype(np.uint8)
+    oq = q.view(np.dtype([(a, b) for a, b in zip(("u", "v", "invz", "octave", "valid", "obsPositive", "angle"),
+                                                   ("<f4", "<f4", "<f4", "<i4", "<i4", "<i4", "<f4"))]))
+    n, match = matcher.search_by_projection(g, SF, q, da, 10.0, 3, occ, None, 0.0, False, max_distance=50)
+    rn, rmatch = o.search_projection(SF, oq, da, 10.0, 3, occ, None, 0.0, False, max_distance=50)
+    assert n == rn and np.array_equal(match, rmatch) and n > 50

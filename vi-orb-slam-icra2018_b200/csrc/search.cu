@@ -222,6 +222,7 @@ __global__ void proj_queries_kernel(FrameDev cur, const orbm_proj_query* __restr
     a.r = __fmul_rn(th, sf[o]);                           // :1398
     if (mode == 1) { a.minLevel = o; a.maxLevel = -1; }   // forward  (:1409)
     else if (mode == 2) { a.minLevel = 0; a.maxLevel = o; }   // backward (:1411)
+    else if (mode == 3) { a.minLevel = o - 1; a.maxLevel = o; }   // SearchByProjection(KF, Scw, ...) (:369-371)
     else { a.minLevel = o - 1; a.maxLevel = o + 1; }      // :1413
     a.stereoCenter = __fsub_rn(p.u, __fmul_rn(mbf, p.invz));   // :1435
     a.stereoTol = a.r;
@@ -562,6 +563,52 @@ __global__ void __launch_bounds__(256) tri_finish_kernel(FrameDev k1, FrameDev k
 __global__ void fill_int_kernel(int* p, int n, int v) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
+}
+
+// ------------------------------------------------------------------------------------------------ projected best match
+// The independent search shared by Fuse (ORBmatcher.cc:892-944), Fuse with Sim3 (:1051-1075) and both directions of
+// SearchBySim3 (:1191-1215, :1271-1295): no query sees another's result, so one warp per query, whole GPU.
+__global__ void __launch_bounds__(256)
+projected_best_kernel(FrameDev f, const orbm_best_query* __restrict__ queries, const uint4* __restrict__ qdesc, int nq,
+                      int chi2Filter, const float* __restrict__ uRight, const float* __restrict__ invSigma2,
+                      int* __restrict__ bestIdx, int* __restrict__ bestDist) {
+    const int qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (qi >= nq) return;
+    const int lane = threadIdx.x & 31;
+    const orbm_best_query bq = queries[qi];
+    int best = kNone, bx = -1;
+    if (bq.valid) {
+        AreaQuery a;
+        a.x = bq.u; a.y = bq.v; a.r = bq.radius;
+        a.minLevel = bq.level - 1; a.maxLevel = bq.level;   // the in-loop octave test of the reference (:908-911)
+        a.active = 1; a.stereoCenter = 0; a.stereoTol = 0;
+        const uint4 qa = qdesc[2 * qi], qb = qdesc[2 * qi + 1];
+        warp_enumerate(f, a, nullptr, [&](int idx, int pos) {
+            if (chi2Filter) {                                // :914-938
+                const orb_keypoint kp = f.keys[idx];
+                const float ex = __fsub_rn(bq.u, kp.x), ey = __fsub_rn(bq.v, kp.y);
+                float e2 = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
+                double limit = 5.99;
+                if (uRight && uRight[idx] >= 0) {
+                    const float er = __fsub_rn(bq.ur, uRight[idx]);
+                    e2 = __fadd_rn(e2, __fmul_rn(er, er));
+                    limit = 7.8;
+                }
+                if ((double)__fmul_rn(e2, invSigma2[kp.octave]) > limit) return;
+            }
+            const int key = (hamming256(qa, qb, f.desc[2 * idx], f.desc[2 * idx + 1]) << kOrdShift) | pos;
+            if (key < best) { best = key; bx = idx; }
+        });
+    }
+    int g = best;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) g = min(g, __shfl_xor_sync(0xffffffffu, g, o));
+    const unsigned owner = __ballot_sync(0xffffffffu, best == g && g != kNone);
+    const int idx = owner ? __shfl_sync(0xffffffffu, bx, __ffs(owner) - 1) : -1;
+    if (lane == 0) {
+        bestIdx[qi] = idx;
+        bestDist[qi] = g == kNone ? 256 : g >> kOrdShift;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ SearchByBoW
@@ -1058,6 +1105,36 @@ int orbm_search_by_bow(orbm_handle h, orbm_frame k1, orbm_frame k2, int nNodes1,
     ORB_CUDA(cudaMemcpyAsync(matches12, h->out0.p, (size_t)n1 * 4, cudaMemcpyDeviceToHost, st));
     ORB_CUDA(cudaMemcpyAsync(matches21, h->out1.p, (size_t)n2 * 4, cudaMemcpyDeviceToHost, st));
     ORB_CUDA(cudaMemcpyAsync(nmatches, h->out3.p, 4, cudaMemcpyDeviceToHost, st));
+    ORB_CUDA(cudaStreamSynchronize(st));
+    return ORB_OK;
+}
+
+int orbm_search_projected_best(orbm_handle h, orbm_frame kf, const orbm_best_query* queries, const uint8_t* qdesc, int nq,
+                               int chi2Filter, const float* uRight, const float* invSigma2, int nlevels, int* bestIdx,
+                               int* bestDist) {
+    ORBM_ENTER(h);
+    if (!kf || nq < 0 || (nq > 0 && (!queries || !qdesc || !bestIdx || !bestDist)) || (chi2Filter && (!invSigma2 || nlevels < 1)))
+        return fail(ORB_ERR_INVALID, "orbm_search_projected_best: bad arguments");
+    if (nq == 0) return ORB_OK;
+    const int n = kf->n;
+    if (n == 0) {
+        for (int i = 0; i < nq; ++i) { bestIdx[i] = -1; bestDist[i] = 256; }
+        return ORB_OK;
+    }
+    cudaStream_t st = h->stream;
+    ORB_CHECK(upload(h->in0, queries, (size_t)nq * sizeof(orbm_best_query), st));
+    ORB_CHECK(upload(h->in1, qdesc, (size_t)nq * 32, st));
+    if (chi2Filter) ORB_CHECK(upload(h->in2, invSigma2, (size_t)nlevels * 4, st));
+    if (chi2Filter && uRight) ORB_CHECK(upload(h->in3, uRight, (size_t)n * 4, st));
+    ORB_CHECK(h->out0.reserve((size_t)nq * 4));
+    ORB_CHECK(h->out1.reserve((size_t)nq * 4));
+    projected_best_kernel<<<ceil_div(nq, 8), 256, 0, st>>>(kf->dev(), h->in0.as<orbm_best_query>(), h->in1.as<uint4>(), nq, chi2Filter,
+                                                           (chi2Filter && uRight) ? h->in3.as<float>() : nullptr,
+                                                           chi2Filter ? h->in2.as<float>() : nullptr, h->out0.as<int>(), h->out1.as<int>());
+    h->launches += 1;
+    ORB_CUDA(cudaGetLastError());
+    ORB_CUDA(cudaMemcpyAsync(bestIdx, h->out0.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
+    ORB_CUDA(cudaMemcpyAsync(bestDist, h->out1.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
     ORB_CUDA(cudaStreamSynchronize(st));
     return ORB_OK;
 }

@@ -356,3 +356,18 @@ class Matcher:
                                          _p(i2), _p(v1), _p(v2), C.c_float(ratio), int(check_ori), int(strict_low),
                                          _p(m12), _p(m21), C.byref(n)))
         return n.value, m12, m21
+
+    def search_projected_best(self, kf, queries, qdesc, chi2=False, u_right=None, inv_sigma2=None):
+        """Projected search of Fuse / SearchBySim3 (ORBmatcher.cc:892-944, 1051-1075, 1191-1215) -> (best_idx, best_dist)"""
+        q = np.ascontiguousarray(queries, BEST_QUERY_DTYPE)
+        qd = np.ascontiguousarray(qdesc, np.uint8)
+        ur = None if u_right is None else np.ascontiguousarray(u_right, np.float32)
+        s2 = None if inv_sigma2 is None else np.ascontiguousarray(inv_sigma2, np.float32)
+        bi = np.empty(len(q), np.int32)
+        bd = np.empty(len(q), np.int32)
+        _check(self.L.orbm_search_projected_best(self.h, kf.f, _p(q), _p(qd), len(q), int(chi2), _p(ur), _p(s2),
+                                                 0 if s2 is None else len(s2), _p(bi), _p(bd)))
+        return bi, bd
+
+
+BEST_QUERY_DTYPE = np.dtype([("u", "<f4"), ("v", "<f4"), ("radius", "<f4"), ("ur", "<f4"), ("level", "<i4"), ("valid", "<i4")])

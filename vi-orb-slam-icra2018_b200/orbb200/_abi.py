@@ -41,7 +41,8 @@ SIGNATURES = {
     "orbm_search_for_triangulation": (i32, [vp, vp, vp, i32, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, f32, f32,
                                             vp, vp, i32, i32, i32, vp, vp]),
     "orbm_search_by_bow": (i32, [vp, vp, vp, i32, vp, vp, vp, i32, vp, vp, vp, vp, vp, f32, i32, i32, vp, vp, vp]),
-    "orbm_bruteforce": (i32, [vp, vp, vp, i32, vp, vp, i32, i32, f32, i32, vp, vp, vp, vp, vp]),
+    "orbm_search_projected_best": (i32, [vp, vp, vp, vp, i32, i32, vp, vp, i32, vp, vp]),
+    "orbm_bruteforce":(i32, [vp, vp, vp, i32, vp, vp, i32, i32, f32, i32, vp, vp, vp, vp, vp]),
     "orbm_bruteforce_device": (i32, [vp, vp, vp, i32, vp, vp, i32, i32, f32, i32, vp, vp, vp, vp, vp, vp]),
     "orbm_allpairs_device": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, f32, i32, vp, vp]),
     "orbm_popc_peak": (i32, [vp, vp]),
