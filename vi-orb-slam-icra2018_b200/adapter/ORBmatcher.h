@@ -117,6 +117,46 @@ public:
         return n;
     }
 
+    // SearchByBoW(pKF, F, vpMapPointMatches) ORBmatcher.cc:159-288 (strictLow = false) and
+    // SearchByBoW(pKF1, pKF2, vpMatches12)   ORBmatcher.cc:522-655 (strictLow = true).
+    // matches12[i1] = i2, matches21[i2] = i1 (or -1); the Frame overload's vpMapPointMatches[i2] is pKF's point at matches21[i2].
+    int SearchByBoW(const FrameView& KF1, const FrameView& F2, const FeatureVectorCSR& fv1, const FeatureVectorCSR& fv2,
+                    const unsigned char* valid1, const unsigned char* valid2, bool strictLow, std::vector<int>& matches12,
+                    std::vector<int>& matches21) {
+        matches12.assign(KF1.size(), -1);
+        matches21.assign(F2.size(), -1);
+        int n = 0;
+        check(orbm_search_by_bow(h_, KF1.get(), F2.get(), (int)fv1.nodeId.size(), fv1.nodeId.data(), fv1.start.data(), fv1.idx.data(),
+                                 (int)fv2.nodeId.size(), fv2.nodeId.data(), fv2.start.data(), fv2.idx.data(), valid1, valid2,
+                                 mfNNratio, mbCheckOrientation, strictLow, matches12.data(), matches21.data(), &n));
+        return n;
+    }
+
+    // SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist) ORBmatcher.cc:1500-1627 (mode 0, maxDistance = ORBdist)
+    // and SearchByProjection(pKF, Scw, vpPoints, vpMatched, th) ORBmatcher.cc:290-403 (mode 3, maxDistance = TH_LOW, no
+    // orientation check: construct the matcher with checkOri = false): the caller predicts the level into query.octave.
+    int SearchByProjection(const FrameView& Current, const std::vector<float>& scaleFactors, const std::vector<orbm_proj_query>& queries,
+                           const unsigned char* queryDescriptors, float th, int mode, int maxDistance, const unsigned char* occupied,
+                           std::vector<int>& curMatch) {
+        curMatch.assign(Current.size(), -1);
+        int n = 0;
+        check(orbm_search_by_projection_ex(h_, Current.get(), scaleFactors.data(), (int)scaleFactors.size(), nullptr, 0.f,
+                                           queries.data(), queryDescriptors, (int)queries.size(), th, mode, maxDistance, occupied,
+                                           curMatch.data(), mbCheckOrientation, &n));
+        return n;
+    }
+
+    // The search inside Fuse (ORBmatcher.cc:892-944, chi2 = true; :1051-1075) and SearchBySim3 (:1191-1215, :1271-1295):
+    // closest descriptor per projected point; Replace / AddObservation / the mutual-agreement test stay with the caller.
+    void ProjectedBest(const FrameView& KF, const std::vector<orbm_best_query>& queries, const unsigned char* queryDescriptors,
+                       bool chi2, const float* uRight, const std::vector<float>& invLevelSigma2, std::vector<int>& bestIdx,
+                       std::vector<int>& bestDist) {
+        bestIdx.assign(queries.size(), -1);
+        bestDist.assign(queries.size(), 256);
+        check(orbm_search_projected_best(h_, KF.get(), queries.data(), queryDescriptors, (int)queries.size(), chi2, uRight,
+                                         invLevelSigma2.data(), (int)invLevelSigma2.size(), bestIdx.data(), bestDist.data()));
+    }
+
 #ifdef ORBB200_WITH_ORBSLAM
     // ---- the reference's own signatures (need Frame.h / KeyFrame.h / MapPoint.h of the host project) -------------------
     // Declared here, defined in adapter/ORBmatcher_orbslam.inl, which flattens the objects exactly as documented in

@@ -5,6 +5,7 @@
 // host code here only derives sizes and tables (the same float expressions as the reference, compiled without FMA
 // contraction) and enqueues 12 launches per batch on one stream.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -409,8 +410,9 @@ int orbx_extract_batch(orbx_handle e, const uint8_t* images, int nFrames, int w,
     ORB_CHECK(e->dKps.reserve((size_t)super * capacity * sizeof(orb_keypoint)));
     ORB_CHECK(e->dDesc.reserve((size_t)super * capacity * 32));
     ORB_CHECK(e->dCount.reserve((size_t)super * 4));
-    const int pipeChunk = std::max(1, std::min(128, (std::min(nFrames, super) + 7) / 8));
-    const int maxChunks = (super + pipeChunk - 1) / pipeChunk;
+    int pipeChunk = std::max(1, std::min(192, (std::min(nFrames, super) + 5) / 6));
+    if (const char* envChunk = getenv("ORBB_PIPE_CHUNK")) pipeChunk = std::max(1, std::min(atoi(envChunk), super));   // tuning knob
+    const int maxChunks = (super + pipeChunk - 1) / pipeChunk + 2;
     while ((int)e->pipeEvents.size() < 2 * maxChunks) {
         cudaEvent_t ev;
         ORB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -420,8 +422,9 @@ int orbx_extract_batch(orbx_handle e, const uint8_t* images, int nFrames, int w,
     for (int s0 = 0; s0 < nFrames; s0 += super) {
         const int ns = std::min(super, nFrames - s0);
         int k = 0;
-        for (int f0 = 0; f0 < ns; f0 += pipeChunk, ++k) {
-            const int nf = std::min(pipeChunk, ns - f0);
+        // short first chunks: the pipeline fills after a quarter-size copy instead of a full one
+        for (int f0 = 0, nf = 0; f0 < ns; f0 += nf, ++k) {
+            nf = std::min(k == 0 ? std::max(1, pipeChunk / 4) : (k == 1 ? std::max(1, pipeChunk / 2) : pipeChunk), ns - f0);
             uint8_t* dImg = e->dImages.as<uint8_t>() + (size_t)f0 * imgBytes;
             const uint8_t* src = images + (size_t)(s0 + f0) * frameStride;
             if (frameStride == imgBytes) {
