@@ -120,8 +120,8 @@ int configure(orbx_extractor* e, int w, int h, int nFrames) {
                 c.y0 = (short)(kEdge + i * hCell);
                 c.cw = (short)std::min(wCell, (L.w - kEdge) - c.x0);
                 c.ch = (short)std::min(hCell, (L.h - kEdge) - c.y0);
-                c.pad = 0;
                 if (c.cw <= 0 || c.ch <= 0) continue;   // the reference skips it or FAST sees a ROI thinner than 7 px
+                fast_cell_setup(c, L.pyrOff, L.pitch);
                 c.slot = (int)slotOff;
                 slotOff += L.slotCap;
                 cells.push_back(c);
@@ -183,11 +183,12 @@ int configure(orbx_extractor* e, int w, int h, int nFrames) {
     std::memset(&P, 0, sizeof P);
     P.nLevels = nl;
     P.iniTh = e->iniTh;
-    P.minTh = e->minTh;
+    P.minTh = std::min(e->minTh, e->iniTh);   // a second pass at a threshold >= the first cannot find anything new
     P.nCellsTotal = (int)cells.size();
     P.maxCellW = 1;
     P.maxCellH = 1;
     for (const Cell& c : cells) { P.maxCellW = std::max(P.maxCellW, (int)c.cw); P.maxCellH = std::max(P.maxCellH, (int)c.ch); }
+    P.fast = fast_layout(P.maxCellW, P.maxCellH);
     P.selPerFrame = selOff;
     P.pyrFrameBytes = pyrOff;
     P.blurFrameBytes = blurOff;

@@ -41,12 +41,29 @@ struct LevelGeom {
     float patchSize;     // (float)(int)(31*scale)
 };
 
-struct Cell {            // one FAST cell with a non-empty interior
+struct alignas(16) Cell {    // one FAST cell with a non-empty interior; 32 bytes = two 128-bit loads
     short level;
     short x0, y0;        // interior origin in level coordinates (first pixel that can be a keypoint)
     short cw, ch;        // interior size
-    short pad;
+    unsigned short pitch;    // padded row pitch of the level (bytes)
     int slot;            // entry offset of its slot inside one frame's slot block
+    // precomputed for the FAST kernel so that its prologue has no divisions and no level-table reads
+    int tileOff;         // byte offset inside one frame's pyramid block of the aligned word that holds pixel (x0-4, y0-3)
+    unsigned char shift8;    // funnel shift (bits) that brings that pixel to byte 0
+    unsigned char quads;     // 4-pixel groups per staged tile row, ceil((cw+8)/4)
+    unsigned char rowsStage; // tile rows staged per pass of the CTA = threads / quads
+    unsigned char groups;    // 4-pixel groups per interior row, ceil(cw/4)
+    unsigned char rowsTest;  // interior rows tested per pass = threads / groups
+    unsigned char pad;
+    unsigned short rq, rg;   // ceil(32768/quads), ceil(32768/groups): t / n == (t * r) >> 15 for t < threads
+    unsigned short pad2;
+};
+static_assert(sizeof(Cell) == 32, "Cell is read as two uint4");
+
+struct FastLayout {      // byte offsets inside the FAST kernel's dynamic shared memory (host-computed, see fast.cu)
+    int tile, score, bitmap, queue, alive, total;
+    int zeroVec;         // uint4 count of [score, queue): score map + bitmap start as zero
+    int qCap;            // queue capacity in entries
 };
 
 struct SelKey {          // quadtree survivor in level coordinates
@@ -61,6 +78,7 @@ struct ExtractParams {
     int selPerFrame;         // entries
     int outCapacity;         // caller's per-frame output capacity
     int maxCellW, maxCellH;  // largest FAST cell interior of this image size (sizes the FAST kernel's shared memory)
+    FastLayout fast;
     long long pyrFrameBytes, blurFrameBytes, slotFrameEntries, keyWsFrameEntries;
     unsigned char* pyr;
     unsigned char* blur;
@@ -82,6 +100,8 @@ struct BlurTile { short level, tx, ty, pad; };
 int launch_pyramid(const ExtractParams& P, const unsigned char* dImages, int width, int height, int stride,
                    size_t frameStride, cudaStream_t st, int* launches);
 int launch_fast(const ExtractParams& P, cudaStream_t st, int* launches);
+FastLayout fast_layout(int maxCellW, int maxCellH);
+void fast_cell_setup(Cell& c, long long levelPyrOff, int pitch);
 int launch_octree(const ExtractParams& P, int smemBytes, int keyCapSmem, int nodeCap, int cellCap, cudaStream_t st,
                   int* launches);
 int launch_blur(const ExtractParams& P, const BlurTile* dTiles, int nTiles, cudaStream_t st, int* launches);
