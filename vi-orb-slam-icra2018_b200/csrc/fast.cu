@@ -53,9 +53,8 @@ FastLayout fast_layout(int maxW, int maxH) {
     f.tile = take((maxH + 6) * TPX * 2);          // 16-bit pixels
     f.score = take((maxH + 2) * SC_PITCH);        // uint8 scores with a zero ring
     f.bitmap = take((((npix + 31) >> 5) + 1) * 4);    // NMS survivors, bit = y*cw + x
-    f.queue = take(npix * 2);                     // x | y<<6: front = may be a corner at iniTh, back = only at minTh;
-                                                  // the front is reused as the survivor list once it has been scored
-    f.alive = take(npix * 2);                     // corners (S >= minTh): x | y<<6 | (S >= iniTh)<<14
+    f.queue = take(npix * 2);                     // x | y<<6: front = may be a corner at iniTh, back = only at minTh
+    f.alive = take(((maxW + 1) / 2) * ((maxH + 1) / 2) * 2);   // NMS survivors (no two are 8-adjacent)
     f.total = p;
     f.zeroVec = (f.queue - f.score) / 16;
     f.qCap = npix;
@@ -103,12 +102,13 @@ __device__ __forceinline__ int fast_score(const unsigned short* c) {
     return max(lo, hi) - 1;
 }
 
-// per-half test of the necessary condition: bright possible (mm >= v+t+1) or dark possible (v >= nn+t+1); 2 result bits
-__device__ __forceinline__ unsigned int pass_bits(unsigned int mm, unsigned int nn, unsigned int c, unsigned int T1) {
-    bool bh, bl, dh, dl;
-    __vibmax_u16x2(mm, c + T1, &bh, &bl);
-    __vibmax_u16x2(c, nn + T1, &dh, &dl);
-    return ((bl | dl) ? 1u : 0u) | ((bh | dh) ? 2u : 0u);
+// Necessary condition per 16-bit half, branch- and predicate-free: with K = 0x0200 - (t+1) in both halves,
+// bit 9 of (mm - c + K) is set iff mm >= c + t + 1 (bright arc possible) and bit 9 of (c - nn + K) iff c >= nn + t + 1
+// (dark arc possible). All halves hold 8-bit values, so every half stays in [1, 0x2fe]: no borrow crosses the halves and
+// each expression is a single three-input add.
+constexpr unsigned int PASS_MASK = 0x02000200u;
+__device__ __forceinline__ unsigned int pass_word(unsigned int mm, unsigned int nn, unsigned int c, unsigned int K) {
+    return ((mm - c + K) | (c - nn + K)) & PASS_MASK;
 }
 
 struct FastShared {
@@ -116,46 +116,46 @@ struct FastShared {
     unsigned char* score;
     unsigned int* bitmap;
     unsigned short* queue;
-    unsigned short* alive;
+    unsigned short* surv;
 };
 
-// B: exact score of queue entries [first, first + n * step) (step = +1 walks the front, -1 the back)
-__device__ __forceinline__ void score_queue(const FastShared& S, int first, int step, int n, int tid, int minTh, int iniTh,
-                                            int* aliveLen) {
+// B: exact score of queue entries first, first + step, ... (step = +1 walks the front, -1 the back); corners (S >= minTh)
+//    enter the score map
+__device__ __forceinline__ void score_queue(const FastShared& S, int first, int step, int n, int tid, int minTh) {
     const unsigned short* tile16 = reinterpret_cast<const unsigned short*>(S.tile);
+#pragma unroll 1
     for (int q = tid; q < n; q += FAST_THREADS) {
         const unsigned int e = S.queue[first + q * step];
-        const int x = e & 63, y = (e >> 6) & 63;
+        const int x = e & 63, y = e >> 6;
         const int s = fast_score(tile16 + (y + 3) * TPX + x + 4);
-        if (s >= minTh) {
-            S.score[(y + 1) * SC_PITCH + x + 1] = (unsigned char)s;
-            S.alive[atomicAdd(aliveLen, 1)] = (unsigned short)(e | (s >= iniTh ? 0x4000u : 0u));
-        }
+        if (s >= minTh) S.score[(y + 1) * SC_PITCH + x + 1] = (unsigned char)s;
     }
 }
 
-// C: per-cell NMS over the corners whose ini flag equals `wantIni`; survivors are listed and set their bitmap bit
-__device__ __forceinline__ void nms_alive(const FastShared& S, unsigned short* surv, int an, int tid, int cw, unsigned int wantIni,
+// C: per-cell NMS over the queue entries whose score lies in [lo, hi); survivors are listed and set their bitmap bit
+__device__ __forceinline__ void nms_queue(const FastShared& S, int first, int step, int n, int tid, int cw, int lo, int hi,
                                           int* survLen) {
-    for (int q = tid; q < an; q += FAST_THREADS) {
-        const unsigned int e = S.alive[q];
-        if ((e & 0x4000u) != wantIni) continue;
-        const int x = e & 63, y = (e >> 6) & 63;
+#pragma unroll 1
+    for (int q = tid; q < n; q += FAST_THREADS) {
+        const unsigned int e = S.queue[first + q * step];
+        const int x = e & 63, y = e >> 6;
         const unsigned char* sc = S.score + (y + 1) * SC_PITCH + x + 1;
         const int s = sc[0];
+        if (s < lo || s >= hi) continue;
         const int m = max(max(max(sc[-SC_PITCH - 1], sc[-SC_PITCH]), max(sc[-SC_PITCH + 1], sc[-1])),
                           max(max(sc[1], sc[SC_PITCH - 1]), max(sc[SC_PITCH], sc[SC_PITCH + 1])));
         if (s > m) {
             const int bit = y * cw + x;
             atomicOr(&S.bitmap[bit >> 5], 1u << (bit & 31));
-            surv[atomicAdd(survLen, 1)] = (unsigned short)e;
+            S.surv[atomicAdd(survLen, 1)] = (unsigned short)e;
         }
     }
 }
 
 __global__ void __launch_bounds__(FAST_THREADS, 10) fast_cells_kernel(const __grid_constant__ ExtractParams P) {
     extern __shared__ __align__(16) unsigned char fsm[];
-    __shared__ int sFrontLen, sBackLen, sAliveLen, sSurvLen;
+    __shared__ unsigned int sQueueLens;   // front length | back length << 16
+    __shared__ int sSurvLen;
     const int frame = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
     const uint4* cellWords = reinterpret_cast<const uint4*>(P.cells + blockIdx.x);
     const uint4 cw0 = __ldg(cellWords), cw1 = __ldg(cellWords + 1);
@@ -164,13 +164,14 @@ __global__ void __launch_bounds__(FAST_THREADS, 10) fast_cells_kernel(const __gr
     S.score = fsm + P.fast.score;
     S.bitmap = reinterpret_cast<unsigned int*>(fsm + P.fast.bitmap);
     S.queue = reinterpret_cast<unsigned short*>(fsm + P.fast.queue);
-    S.alive = reinterpret_cast<unsigned short*>(fsm + P.fast.alive);
+    S.surv = reinterpret_cast<unsigned short*>(fsm + P.fast.alive);
 
     // score map and bitmap start as zero (independent of the cell: overlaps the cell-table load)
     {
         uint4* z = reinterpret_cast<uint4*>(S.score);
+#pragma unroll 1
         for (int i = tid; i < P.fast.zeroVec; i += FAST_THREADS) z[i] = make_uint4(0, 0, 0, 0);
-        if (tid == 0) { sFrontLen = 0; sBackLen = 0; sAliveLen = 0; sSurvLen = 0; }
+        if (tid == 0) { sQueueLens = 0; sSurvLen = 0; }
     }
     // unpack the cell record (layout of struct Cell)
     const int cellX0 = (int)(short)(cw0.x >> 16), cellY0 = (int)(short)(cw0.y & 0xffffu);
@@ -189,27 +190,41 @@ __global__ void __launch_bounds__(FAST_THREADS, 10) fast_cells_kernel(const __gr
             const unsigned int* g =
                 reinterpret_cast<const unsigned int*>(P.pyr + (size_t)frame * P.pyrFrameBytes + tileOff + (size_t)r0 * pitch) + q;
             uint2* t = reinterpret_cast<uint2*>(S.tile) + r0 * (TPX / 4) + q;
-            const int gStep = rowsStage * (pitch >> 2), tStep = rowsStage * (TPX / 4);
-            for (int r = r0; r < ch + 6; r += rowsStage, g += gStep, t += tStep) {
-                const unsigned int w0 = __ldg(g), w1 = __ldg(g + 1);
-                const unsigned int px = __funnelshift_r(w0, w1, shift8);
-                *t = make_uint2(__byte_perm(px, 0, 0x4140), __byte_perm(px, 0, 0x4342));
+            const int gStep = rowsStage * (pitch >> 2), tStep = rowsStage * (TPX / 4), rows = ch + 6;
+            // four rows per trip, all eight loads issued before the first use (one DRAM/L2 round trip per trip)
+#pragma unroll 1
+            for (int r = r0; r < rows; r += 4 * rowsStage, g += 4 * gStep, t += 4 * tStep) {
+                unsigned int w0[4], w1[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (r + j * rowsStage < rows) { w0[j] = __ldg(g + j * gStep); w1[j] = __ldg(g + j * gStep + 1); }
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (r + j * rowsStage < rows) {
+                        const unsigned int px = __funnelshift_r(w0[j], w1[j], shift8);
+                        t[j * tStep] = make_uint2(__byte_perm(px, 0, 0x4140), __byte_perm(px, 0, 0x4342));
+                    }
             }
         }
     }
     __syncthreads();
 
+    const int qLastAll = P.fast.qCap - 1;
     // ---- A. necessary test, 4 pixels (two 16x2 pairs) per thread; warp-uniform loop so that a warp whose 128 pixels
     //         all fail after the three middle-row pairs skips the other five
     {
-        const unsigned int Tmin = (unsigned int)(P.minTh + 1) * 0x00010001u, Tini = (unsigned int)(P.iniTh + 1) * 0x00010001u;
+        const unsigned int Kmin = PASS_MASK - (unsigned int)(P.minTh + 1) * 0x00010001u,
+                           Kini = PASS_MASK - (unsigned int)(P.iniTh + 1) * 0x00010001u;
         const int y0 = (int)(((unsigned int)tid * rg) >> 15), g = tid - y0 * groups;
         const int yLane0 = __shfl_sync(0xffffffffu, y0, 0);   // rows advance in lockstep: the warp's first lane leaves last
         const uint2* row = reinterpret_cast<const uint2*>(S.tile) + (y0 + 3) * (TPX / 4) + g;
         const int x0 = 4 * g;
-        const unsigned int colMask = (1u << min(4, cw - x0)) - 1u;
+        // pixels x0, x0+1 answer in bits 9 / 25 of the A word, x0+2, x0+3 in those of the B word
+        const unsigned int colA = (x0 < cw ? 0x200u : 0u) | (x0 + 1 < cw ? 0x02000000u : 0u),
+                           colB = (x0 + 2 < cw ? 0x200u : 0u) | (x0 + 3 < cw ? 0x02000000u : 0u);
         const unsigned int base = (unsigned int)x0 | ((unsigned int)y0 << 6);
         const int qLast = P.fast.qCap - 1;
+#pragma unroll 1
         for (int k = 0; yLane0 + k < ch; k += rowsTest, row += rowsTest * (TPX / 4)) {
             const bool valid = (y0 < rowsTest) && (y0 + k < ch);
             const uint2* rowC = valid ? row : reinterpret_cast<const uint2*>(S.tile) + 3 * (TPX / 4);
@@ -237,8 +252,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 10) fast_cells_kernel(const __gr
             }
             unsigned int mmA = __vimin3_u16x2(MA[0], MA[1], MA[2]), mmB = __vimin3_u16x2(MB[0], MB[1], MB[2]);
             unsigned int nnA = __vimax3_u16x2(mA[0], mA[1], mA[2]), nnB = __vimax3_u16x2(mB[0], mB[1], mB[2]);
-            unsigned int flags = pass_bits(mmA, nnA, cA, Tmin) | (pass_bits(mmB, nnB, cB, Tmin) << 2);
-            if (!__any_sync(0xffffffffu, valid && flags)) continue;
+            if (!__any_sync(0xffffffffu, valid && (pass_word(mmA, nnA, cA, Kmin) | pass_word(mmB, nnB, cB, Kmin)))) continue;
             {   // rows +-3: dx = 0, +1, -1  -> circle points 0/8, 1/9, 15/7
                 const uint2* up = rowC - 3 * (TPX / 4);
                 const uint2* dn = rowC + 3 * (TPX / 4);
@@ -265,42 +279,49 @@ __global__ void __launch_bounds__(FAST_THREADS, 10) fast_cells_kernel(const __gr
             mmB = __vimin3_u16x2(mmB, __vimin3_u16x2(MB[3], MB[4], MB[5]), __vminu2(MB[6], MB[7]));
             nnA = __vimax3_u16x2(nnA, __vimax3_u16x2(mA[3], mA[4], mA[5]), __vmaxu2(mA[6], mA[7]));
             nnB = __vimax3_u16x2(nnB, __vimax3_u16x2(mB[3], mB[4], mB[5]), __vmaxu2(mB[6], mB[7]));
-            flags = (pass_bits(mmA, nnA, cA, Tmin) | (pass_bits(mmB, nnB, cB, Tmin) << 2)) & colMask;
-            if (valid && flags) {
-                const unsigned int front = (pass_bits(mmA, nnA, cA, Tini) | (pass_bits(mmB, nnB, cB, Tini) << 2)) & flags;
-                const unsigned int back = flags & ~front;
-                const unsigned int e = base + ((unsigned int)k << 6);
-                if (front) {
-                    int pos = atomicAdd(&sFrontLen, __popc(front));
+            const unsigned int passA = valid ? pass_word(mmA, nnA, cA, Kmin) & colA : 0u,
+                               passB = valid ? pass_word(mmB, nnB, cB, Kmin) & colB : 0u;
+            const unsigned int frontA = pass_word(mmA, nnA, cA, Kini) & passA, frontB = pass_word(mmB, nnB, cB, Kini) & passB;
+            const unsigned int backA = passA ^ frontA, backB = passB ^ frontB;
+            // queue slots: warp scan of (front count | back count << 16), one shared atomic per warp
+            const unsigned int mine = (unsigned int)(__popc(frontA) + __popc(frontB)) | ((unsigned int)(__popc(backA) + __popc(backB)) << 16);
+            unsigned int incl = mine;
 #pragma unroll
-                    for (int b = 0; b < 4; ++b)
-                        if (front & (1u << b)) S.queue[pos++] = (unsigned short)(e + b);
-                }
-                if (back) {
-                    int pos = qLast - atomicAdd(&sBackLen, __popc(back));
-#pragma unroll
-                    for (int b = 0; b < 4; ++b)
-                        if (back & (1u << b)) S.queue[pos--] = (unsigned short)(e + b);
-                }
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned int up = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += up;
             }
+            unsigned int start = 0;
+            if (lane == 31 && incl) start = atomicAdd(&sQueueLens, incl);
+            start = __shfl_sync(0xffffffffu, start, 31) + incl - mine;
+            const unsigned int e = base + ((unsigned int)k << 6);
+            int pf = (int)(start & 0xffffu), pb = qLast - (int)(start >> 16);
+            if (frontA & 0x200u) S.queue[pf++] = (unsigned short)e;
+            if (frontA & 0x02000000u) S.queue[pf++] = (unsigned short)(e + 1);
+            if (frontB & 0x200u) S.queue[pf++] = (unsigned short)(e + 2);
+            if (frontB & 0x02000000u) S.queue[pf] = (unsigned short)(e + 3);
+            if (backA & 0x200u) S.queue[pb--] = (unsigned short)e;
+            if (backA & 0x02000000u) S.queue[pb--] = (unsigned short)(e + 1);
+            if (backB & 0x200u) S.queue[pb--] = (unsigned short)(e + 2);
+            if (backB & 0x02000000u) S.queue[pb] = (unsigned short)(e + 3);
         }
     }
     __syncthreads();
 
     // ---- B, C at iniThFAST
-    score_queue(S, 0, 1, sFrontLen, tid, P.minTh, P.iniTh, &sAliveLen);
+    const int nFront = (int)(sQueueLens & 0xffffu), nBack = (int)(sQueueLens >> 16);
+    score_queue(S, 0, 1, nFront, tid, P.minTh);
     __syncthreads();
-    unsigned short* surv = S.queue;   // the front queue has been consumed
-    const int an = sAliveLen;
-    nms_alive(S, surv, an, tid, cw, 0x4000u, &sSurvLen);
+    nms_queue(S, 0, 1, nFront, tid, cw, P.iniTh, 256, &sSurvLen);
     __syncthreads();
     int sn = sSurvLen;
     if (sn == 0) {
-        // ---- B', C': the reference's second cv::FAST call at minThFAST (:811-818). The back queue is still intact
-        //      (nothing was listed as a survivor), corners found so far keep their scores.
-        score_queue(S, P.fast.qCap - 1, -1, sBackLen, tid, P.minTh, P.iniTh, &sAliveLen);
+        // ---- B', C': the reference's second cv::FAST call at minThFAST (:811-818). Corners found so far keep their
+        //      scores; those >= iniThFAST have just lost their NMS and would lose it again.
+        score_queue(S, qLastAll, -1, nBack, tid, P.minTh);
         __syncthreads();
-        nms_alive(S, surv, sAliveLen, tid, cw, 0u, &sSurvLen);
+        nms_queue(S, 0, 1, nFront, tid, cw, P.minTh, P.iniTh, &sSurvLen);
+        nms_queue(S, qLastAll, -1, nBack, tid, cw, P.minTh, P.iniTh, &sSurvLen);
         __syncthreads();
         sn = sSurvLen;
     }
@@ -310,8 +331,8 @@ __global__ void __launch_bounds__(FAST_THREADS, 10) fast_cells_kernel(const __gr
     if (tid == 0) P.cellCount[(size_t)frame * P.nCellsTotal + blockIdx.x] = sn;
     unsigned int* slot = P.slots + (size_t)frame * P.slotFrameEntries + cellSlot;
     for (int q = tid; q < sn; q += FAST_THREADS) {
-        const unsigned int e = surv[q];
-        const int x = e & 63, y = (e >> 6) & 63;
+        const unsigned int e = S.surv[q];
+        const int x = e & 63, y = e >> 6;
         const int bit = y * cw + x;
         int rank = __popc(S.bitmap[bit >> 5] & ((1u << (bit & 31)) - 1u));
         for (int w = 0; w < (bit >> 5); ++w) rank += __popc(S.bitmap[w]);
