@@ -8,18 +8,25 @@
 // (((b0*(T0>>4))>>16) + ((b1*(T1>>4))>>16) + 2) >> 2.  The kernels write the 19-px reflect-101 frame in the same pass
 // by evaluating the reflected interior coordinate, so the border costs no extra launch and no read-after-write.
 //
-// Shape (the first version was issue-bound at ~45 instructions per pixel): a thread owns 4 horizontally adjacent output
-// bytes (one aligned 32-bit store) and walks down 8 output rows, so the per-column table entries, byte offsets and
-// funnel-shift amounts are loop invariants.  Per source row it loads three aligned words, funnel-shifts each pixel's
-// two source bytes into place and forms the horizontal sum with ONE IDP.2A (16-bit coefficient pair x two bytes).
+// Shape (instruction-bound kernel; every lane does the same thing):
+//   * work item = 4 horizontally adjacent output bytes (one aligned 32-bit store) x 16 output rows; items are numbered
+//     row-band-major and laid over the threads linearly, so warps are full whatever the level's width;
+//   * a work item resolves its four destination columns ONCE: reflected column -> source offset + coefficient pair.
+//     Interior, mirrored (left/right frame) and straddling groups all read their source bytes from one 8-byte window
+//     that starts at the group's smallest source offset, so they share a single code path: per source row three aligned
+//     32-bit loads, two funnel shifts that bring the window to byte 0, two byte permutes with per-item selectors and
+//     four IDP.2A (16-bit coefficient pair x two bytes) give the four horizontal sums;
+//   * consecutive output rows usually step one source row (scale 1.2: five times out of six), so the lower row's sums
+//     are kept for the next output row;
+//   * the vertical pass is two multiply-high per pixel: hi32((T & ~15) * (b << 12)) == (b * (T >> 4)) >> 16.
 // Reading S[x+1] / row y+1 one past the level is harmless: the table's coefficient there is 0 and the source level
-// has its own frame.  Threads that touch the left/right frame take the per-pixel reflected path.
+// has its own frame.
 #include "extractor.h"
 
 namespace orbb {
 
-constexpr int PY_ROWS = 16;   // output rows per thread
-constexpr int PY_TY = 4;      // row bands per CTA
+constexpr int PY_ROWS = 16;       // output rows per work item
+constexpr int PY_THREADS = 128;
 
 __device__ __forceinline__ int reflect101(int i, int n) {
     if (i < 0) i = -i;
@@ -27,83 +34,99 @@ __device__ __forceinline__ int reflect101(int i, int n) {
     return i;
 }
 
-__global__ void __launch_bounds__(32 * PY_TY)
+// destination column of output byte bx + k: reflect-101 inside the 19-px frame; the unused alignment bytes beyond the
+// frame get a clamped (deterministic, never used) column
+__device__ __forceinline__ int frame_column(int lx, int w) { return min(max(reflect101(lx, w), 0), w - 1); }
+
+__global__ void __launch_bounds__(PY_THREADS)
 pyramid_level0_kernel(const unsigned char* __restrict__ images, int w, int h, int stride, size_t frameStride,
-                      unsigned char* __restrict__ pyr, long long pyrFrameBytes, long long pyrOff, int pitch) {
-    const int bx = (blockIdx.x * 32 + threadIdx.x) * 4;
-    if (bx >= pitch) return;
-    const int lx0 = bx - kPadLeft;
-    const unsigned char* img = images + (size_t)blockIdx.z * frameStride;
-    unsigned char* dst = pyr + (size_t)blockIdx.z * pyrFrameBytes + pyrOff + bx;
-    const bool wordCopy = lx0 >= 0 && lx0 + 3 < w && (((size_t)img | (size_t)stride) & 3) == 0;
-    const int by0 = (blockIdx.y * PY_TY + threadIdx.y) * PY_ROWS;
+                      unsigned char* __restrict__ pyr, long long pyrFrameBytes, long long pyrOff, int pitch, int groups,
+                      int nItems, int wordLoads) {
+    const int item = blockIdx.x * PY_THREADS + threadIdx.x;
+    if (item >= nItems) return;
+    const int band = item / groups, g = item - band * groups;
+    const int bx = 4 * g, lx0 = bx - kPadLeft;
+    const unsigned char* img = images + (size_t)blockIdx.y * frameStride;
+    unsigned char* dst = pyr + (size_t)blockIdx.y * pyrFrameBytes + pyrOff + bx;
+    int col[4], cmin = 0x7fffffff;
 #pragma unroll
+    for (int k = 0; k < 4; ++k) { col[k] = frame_column(lx0 + k, w); cmin = min(cmin, col[k]); }
+    const int base = cmin & ~3;
+    unsigned int sel = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) sel |= (unsigned int)(col[k] - base) << (4 * k);   // the columns span <= 4 bytes: index <= 6
+    const int by0 = band * PY_ROWS, rowsTotal = h + 2 * kEdge;
+    if (wordLoads) {
+        // image rows are 4-byte aligned: two aligned words hold the four (possibly mirrored) source bytes
+        const bool second = base + 4 < ((w + 3) & ~3);   // stay inside the row's last word
+#pragma unroll 4
+        for (int r = 0; r < PY_ROWS; ++r) {
+            const int by = by0 + r;
+            if (by >= rowsTotal) break;
+            const unsigned int* src = reinterpret_cast<const unsigned int*>(img + (size_t)reflect101(by - kEdge, h) * stride + base);
+            const unsigned int w0 = __ldg(src), w1 = second ? __ldg(src + 1) : 0u;
+            *reinterpret_cast<unsigned int*>(dst + (size_t)by * pitch) = __byte_perm(w0, w1, sel);
+        }
+        return;
+    }
+#pragma unroll 1
     for (int r = 0; r < PY_ROWS; ++r) {
         const int by = by0 + r;
-        if (by >= h + 2 * kEdge) break;
+        if (by >= rowsTotal) break;
         const unsigned char* src = img + (size_t)reflect101(by - kEdge, h) * stride;
-        unsigned int word;
-        if (wordCopy) {
-            word = __ldg(reinterpret_cast<const unsigned int*>(src + lx0));
-        } else {
-            word = 0;
+        unsigned int word = 0;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int lx = lx0 + k;
-                unsigned int v = 0;
-                if (lx >= -kEdge && lx < w + kEdge) v = __ldg(src + reflect101(lx, w));
-                word |= v << (8 * k);
-            }
-        }
+        for (int k = 0; k < 4; ++k) word |= (unsigned int)__ldg(src + col[k]) << (8 * k);
         *reinterpret_cast<unsigned int*>(dst + (size_t)by * pitch) = word;
     }
 }
 
-__global__ void __launch_bounds__(32 * PY_TY)
-pyramid_resize_kernel(unsigned char* __restrict__ pyr, long long pyrFrameBytes, long long srcOff, int srcPitch, int sw,
-                      int sh, long long dstOff, int dstPitch, int dw, int dh, const int* __restrict__ xofs,
+__global__ void __launch_bounds__(PY_THREADS)
+pyramid_resize_kernel(unsigned char* __restrict__ pyr, long long pyrFrameBytes, long long srcOff, int srcPitch,
+                      long long dstOff, int dstPitch, int dw, int dh, int groups, int nItems, const int* __restrict__ xofs,
                       const unsigned int* __restrict__ xcoef, const int* __restrict__ yofs, const short2* __restrict__ ycoef) {
-    const int bx = (blockIdx.x * 32 + threadIdx.x) * 4;
-    if (bx >= dstPitch) return;
-    const int lx0 = bx - kPadLeft;
-    unsigned char* frame = pyr + (size_t)blockIdx.z * pyrFrameBytes;
+    const int item = blockIdx.x * PY_THREADS + threadIdx.x;
+    if (item >= nItems) return;
+    const int band = item / groups, g = item - band * groups;
+    const int bx = 4 * g, lx0 = bx - kPadLeft;
+    unsigned char* frame = pyr + (size_t)blockIdx.y * pyrFrameBytes;
     const unsigned char* src0 = frame + srcOff + (size_t)kEdge * srcPitch + kPadLeft;   // source level pixel (0,0)
     unsigned char* dst = frame + dstOff + bx;
 
-    // per-column invariants
+    // per-item column invariants
     unsigned int cf[4];
-    int shiftBits[4], rel[4];
-    bool hiWin[4];
-    int base = 0;
-    bool fast = lx0 >= 0 && lx0 + 3 < dw;
-    if (fast) {
-        const int o0 = __ldg(xofs + lx0);
-        base = o0 & ~3;
+    int ofs[4], omin = 0x7fffffff, omax = 0;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            rel[k] = __ldg(xofs + lx0 + k) - base;
-            cf[k] = __ldg(xcoef + lx0 + k);           // a0 | a1 << 16
-            hiWin[k] = rel[k] >= 4;
-            shiftBits[k] = (rel[k] & 3) * 8;
-        }
-        fast = rel[3] <= 7;                           // both source bytes of every pixel inside the 12-byte window
+    for (int k = 0; k < 4; ++k) {
+        const int dx = frame_column(lx0 + k, dw);
+        ofs[k] = __ldg(xofs + dx);
+        cf[k] = __ldg(xcoef + dx);                    // a0 | a1 << 16
+        omin = min(omin, ofs[k]);
+        omax = max(omax, ofs[k]);
     }
-    const int by0 = (blockIdx.y * PY_TY + threadIdx.y) * PY_ROWS;
-    const int rowsTotal = dh + 2 * kEdge;
-    if (fast) {
-        // the common case; kept in its own loop so that nothing of the per-pixel border path is hoisted into it
-        // Consecutive output rows usually step one source row (scale 1.2: five times out of six), so the lower source
-        // row's horizontal sums become the next output row's upper ones: kept in registers, chosen by a warp-uniform test.
-        int keptRow = -0x40000000, kept[4] = {0, 0, 0, 0};
-        auto hsum = [&](const unsigned char* row, int (&t)[4]) {
+    const int by0 = band * PY_ROWS, rowsTotal = dh + 2 * kEdge;
+    if (omax - omin <= 6) {
+        // the 8 bytes from omin hold S[x0], S[x0+1] of all four pixels (any scale factor up to 2)
+        const int base = omin & ~3, shift = (omin & 3) * 8;
+        unsigned int sel01, sel23;
+        {
+            const unsigned int i0 = ofs[0] - omin, i1 = ofs[1] - omin, i2 = ofs[2] - omin, i3 = ofs[3] - omin;
+            sel01 = i0 | ((i0 + 1) << 4) | (i1 << 8) | ((i1 + 1) << 12);
+            sel23 = i2 | ((i2 + 1) << 4) | (i3 << 8) | ((i3 + 1) << 12);
+        }
+        // horizontal sums of one source row, low 4 bits dropped (the vertical pass uses T >> 4 only)
+        auto hsum = [&](const unsigned char* row, unsigned int (&t)[4]) {
             const unsigned int* p = reinterpret_cast<const unsigned int*>(row + base);
             const unsigned int w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const unsigned int v = __funnelshift_r(hiWin[k] ? w1 : w0, hiWin[k] ? w2 : w1, shiftBits[k]);
-                t[k] = (int)__dp2a_lo(cf[k], v, 0u);              // S[x0]*a0 + S[x0+1]*a1
-            }
+            const unsigned int X = __funnelshift_r(w0, w1, shift), Y = __funnelshift_r(w1, w2, shift);
+            const unsigned int v01 = __byte_perm(X, Y, sel01), v23 = __byte_perm(X, Y, sel23);
+            t[0] = __dp2a_lo(cf[0], v01, 0u) & ~15u;          // S[x0]*a0 + S[x0+1]*a1
+            t[1] = __dp2a_hi(cf[1], v01, 0u) & ~15u;
+            t[2] = __dp2a_lo(cf[2], v23, 0u) & ~15u;
+            t[3] = __dp2a_hi(cf[3], v23, 0u) & ~15u;
         };
+        int keptRow = -0x40000000;
+        unsigned int kept[4] = {0, 0, 0, 0};
 #pragma unroll 2
         for (int r = 0; r < PY_ROWS; ++r) {
             const int by = by0 + r;
@@ -111,8 +134,9 @@ pyramid_resize_kernel(unsigned char* __restrict__ pyr, long long pyrFrameBytes, 
             const int dy = reflect101(by - kEdge, dh);
             const int sy0 = __ldg(yofs + dy);
             const short2 b = __ldg(ycoef + dy);
+            const unsigned int B0 = (unsigned int)b.x << 12, B1 = (unsigned int)b.y << 12;
             const unsigned char* r0 = src0 + (size_t)sy0 * srcPitch;
-            int t0[4], t1[4];
+            unsigned int t0[4], t1[4];
             if (sy0 == keptRow) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) t0[k] = kept[k];
@@ -121,18 +145,18 @@ pyramid_resize_kernel(unsigned char* __restrict__ pyr, long long pyrFrameBytes, 
             }
             hsum(r0 + srcPitch, t1);
             keptRow = sy0 + 1;
-            unsigned int word = 0;
+            unsigned int s[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 kept[k] = t1[k];
-                const unsigned int v = (unsigned int)(((((int)b.x * (t0[k] >> 4)) >> 16) + (((int)b.y * (t1[k] >> 4)) >> 16) + 2) >> 2);
-                word |= (v & 0xffu) << (8 * k);
+                s[k] = __umulhi(t0[k], B0) + __umulhi(t1[k], B1) + 2u;    // <= 1023
             }
-            *reinterpret_cast<unsigned int*>(dst + (size_t)by * dstPitch) = word;
+            const unsigned int q01 = __byte_perm(s[0], s[1], 0x5410) >> 2, q23 = __byte_perm(s[2], s[3], 0x5410) >> 2;
+            *reinterpret_cast<unsigned int*>(dst + (size_t)by * dstPitch) = __byte_perm(q01, q23, 0x6420);
         }
         return;
     }
-    // threads that touch the left/right frame (or an unusual scale factor): per-pixel reflected coordinates
+    // unusual scale factors (> 2): per-pixel path
 #pragma unroll 1
     for (int r = 0; r < PY_ROWS; ++r) {
         const int by = by0 + r;
@@ -143,19 +167,12 @@ pyramid_resize_kernel(unsigned char* __restrict__ pyr, long long pyrFrameBytes, 
         const unsigned char* r0 = src0 + (size_t)sy0 * srcPitch;
         const unsigned char* r1 = r0 + srcPitch;      // row sh is the source's own frame when sy0 == sh-1 (b.y == 0 there)
         unsigned int word = 0;
-#pragma unroll 1
+#pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const int lx = lx0 + k;
-            unsigned int v = 0;
-            if (lx >= -kEdge && lx < dw + kEdge) {
-                const int dx = reflect101(lx, dw);
-                const int x0 = __ldg(xofs + dx);
-                const unsigned int a = __ldg(xcoef + dx);
-                const int ax = (int)(a & 0xffffu), ay = (int)(a >> 16);
-                const int t0 = (int)r0[x0] * ax + (int)r0[x0 + 1] * ay;
-                const int t1 = (int)r1[x0] * ax + (int)r1[x0 + 1] * ay;
-                v = (unsigned int)(((((int)b.x * (t0 >> 4)) >> 16) + (((int)b.y * (t1 >> 4)) >> 16) + 2) >> 2);
-            }
+            const int ax = (int)(cf[k] & 0xffffu), ay = (int)(cf[k] >> 16);
+            const int t0 = (int)r0[ofs[k]] * ax + (int)r0[ofs[k] + 1] * ay;
+            const int t1 = (int)r1[ofs[k]] * ax + (int)r1[ofs[k] + 1] * ay;
+            const unsigned int v = (unsigned int)(((((int)b.x * (t0 >> 4)) >> 16) + (((int)b.y * (t1 >> 4)) >> 16) + 2) >> 2);
             word |= (v & 0xffu) << (8 * k);
         }
         *reinterpret_cast<unsigned int*>(dst + (size_t)by * dstPitch) = word;
@@ -164,22 +181,24 @@ pyramid_resize_kernel(unsigned char* __restrict__ pyr, long long pyrFrameBytes, 
 
 int launch_pyramid(const ExtractParams& P, const unsigned char* dImages, int width, int height, int stride,
                    size_t frameStride, cudaStream_t st, int* launches) {
-    const dim3 block(32, PY_TY);
     {
         const LevelGeom& L = P.lv[0];
-        dim3 grid(ceil_div(L.pitch, 128), ceil_div(L.h + 2 * kEdge, PY_TY * PY_ROWS), P.nFrames);
-        pyramid_level0_kernel<<<grid, block, 0, st>>>(dImages, width, height, stride, frameStride, P.pyr, P.pyrFrameBytes,
-                                                      L.pyrOff, L.pitch);
+        const int groups = L.pitch / 4, nItems = groups * ceil_div(L.h + 2 * kEdge, PY_ROWS);
+        const int wordLoads = ((((size_t)dImages) | (size_t)stride | frameStride) & 3) == 0 ? 1 : 0;
+        dim3 grid(ceil_div(nItems, PY_THREADS), P.nFrames);
+        pyramid_level0_kernel<<<grid, PY_THREADS, 0, st>>>(dImages, width, height, stride, frameStride, P.pyr, P.pyrFrameBytes,
+                                                           L.pyrOff, L.pitch, groups, nItems, wordLoads);
         ++*launches;
     }
     for (int l = 1; l < P.nLevels; ++l) {
         const LevelGeom& S = P.lv[l - 1];
         const LevelGeom& D = P.lv[l];
-        dim3 grid(ceil_div(D.pitch, 128), ceil_div(D.h + 2 * kEdge, PY_TY * PY_ROWS), P.nFrames);
-        pyramid_resize_kernel<<<grid, block, 0, st>>>(P.pyr, P.pyrFrameBytes, S.pyrOff, S.pitch, S.w, S.h, D.pyrOff,
-                                                      D.pitch, D.w, D.h, P.tabOfs + D.xTab,
-                                                      reinterpret_cast<const unsigned int*>(P.tabCoef + D.xTab),
-                                                      P.tabOfs + D.yTab, P.tabCoef + D.yTab);
+        const int groups = D.pitch / 4, nItems = groups * ceil_div(D.h + 2 * kEdge, PY_ROWS);
+        dim3 grid(ceil_div(nItems, PY_THREADS), P.nFrames);
+        pyramid_resize_kernel<<<grid, PY_THREADS, 0, st>>>(P.pyr, P.pyrFrameBytes, S.pyrOff, S.pitch, D.pyrOff, D.pitch, D.w,
+                                                           D.h, groups, nItems, P.tabOfs + D.xTab,
+                                                           reinterpret_cast<const unsigned int*>(P.tabCoef + D.xTab),
+                                                           P.tabOfs + D.yTab, P.tabCoef + D.yTab);
         ++*launches;
     }
     ORB_CUDA(cudaGetLastError());
