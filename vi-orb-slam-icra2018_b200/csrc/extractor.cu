@@ -81,8 +81,6 @@ int configure(orbx_extractor* e, int w, int h, int nFrames) {
     int tabOff = 0, selOff = 0, cellBase = 0;
     std::vector<Cell> cells;
     std::vector<BlurTile> tiles;
-    int tw, th;
-    blur_tile_dims(&tw, &th);
     int nodeCap = 8, cellCap = 1;
     for (int l = 0; l < nl; ++l) {
         LevelGeom& L = lv[l];
@@ -145,8 +143,7 @@ int configure(orbx_extractor* e, int w, int h, int nFrames) {
         keyOff += L.keyWsCap + (L.keyWsCap + 1) / 2 + 2;
         L.scale = e->scale[l];
         L.patchSize = (float)(int)((float)kPatch * e->scale[l]);   // :837, 848
-        for (int ty = 0; ty < ceil_div(L.h, th); ++ty)
-            for (int tx = 0; tx < ceil_div(L.w, tw); ++tx) tiles.push_back(BlurTile{(short)l, (short)tx, (short)ty, 0});
+        for (int c = 0; c < blur_cta_count(L.w, L.h); ++c) tiles.push_back(BlurTile{l, c});
     }
     if (nodeCap > 65535) return fail(ORB_ERR_INVALID, "nfeatures too large for the quadtree kernel");
     ORB_CHECK(octree_smem_plan(nodeCap, cellCap, &e->otSmem, &e->otKeyCap));

@@ -94,7 +94,7 @@ struct ExtractParams {
     LevelGeom lv[kMaxLevels];
 };
 
-struct BlurTile { short level, tx, ty, pad; };
+struct BlurTile { int level, cta; };   // one CTA of the blur kernel: level and CTA index inside the level
 
 // launchers (each returns orb_status and bumps *launches)
 int launch_pyramid(const ExtractParams& P, const unsigned char* dImages, int width, int height, int stride,
@@ -108,7 +108,7 @@ int launch_blur(const ExtractParams& P, const BlurTile* dTiles, int nTiles, cuda
 int launch_brief(const ExtractParams& P, int maxKeypoints, orb_keypoint* dKps, unsigned char* dDesc, int* dCount,
                  cudaStream_t st, int* launches);
 int octree_smem_plan(int nodeCap, int cellCap, int* smemBytes, int* keyCapSmem);
-int blur_tile_dims(int* tw, int* th);
+int blur_cta_count(int w, int h);
 int upload_brief_pattern();
 
 }  // namespace orbb
