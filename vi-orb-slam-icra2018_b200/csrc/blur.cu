@@ -48,34 +48,46 @@ __global__ void __launch_bounds__(BL_THREADS) blur_kernel(const __grid_constant_
     unsigned char* out = P.blur + (size_t)frame * P.blurFrameBytes + L.blurOff + (size_t)y0 * bpitch + x0;
     const int rowsOut = min(BL_ROWS, L.h - y0);
 
-    // horizontal sums of one input row for the item's four pixels
-    auto hrow = [&](int j, unsigned int (&h)[4]) {
+    // the three aligned words of input row j that hold the item's pixels and their 3-px neighbourhood
+    auto load_row = [&](int j, unsigned int (&w)[3]) {
         const unsigned int* p = reinterpret_cast<const unsigned int*>(col + (size_t)min(y0 - 3 + j + kEdge, lastRow) * pitch);
-        const unsigned int wl = __ldg(p), wc = __ldg(p + 1), wr = __ldg(p + 2);
-        h[0] = __dp4a(__funnelshift_r(wl, wc, 8), TAP_H_LO, __dp4a(__funnelshift_r(wc, wr, 8), TAP_H_HI, 0u));
-        h[1] = __dp4a(__funnelshift_r(wl, wc, 16), TAP_H_LO, __dp4a(__funnelshift_r(wc, wr, 16), TAP_H_HI, 0u));
-        h[2] = __dp4a(__funnelshift_r(wl, wc, 24), TAP_H_LO, __dp4a(__funnelshift_r(wc, wr, 24), TAP_H_HI, 0u));
-        h[3] = __dp4a(wc, TAP_H_LO, __dp4a(wr, TAP_H_HI, 0u));
+        w[0] = __ldg(p); w[1] = __ldg(p + 1); w[2] = __ldg(p + 2);
     };
-    // row pair i = input rows 2i, 2i+1 packed per pixel (even row in the low half)
-    auto load_pair = [&](int i, unsigned int (&pr)[4]) {
+    // horizontal sums of one input row for the item's four pixels
+    auto hrow = [&](const unsigned int (&w)[3], unsigned int (&h)[4]) {
+        h[0] = __dp4a(__funnelshift_r(w[0], w[1], 8), TAP_H_LO, __dp4a(__funnelshift_r(w[1], w[2], 8), TAP_H_HI, 0u));
+        h[1] = __dp4a(__funnelshift_r(w[0], w[1], 16), TAP_H_LO, __dp4a(__funnelshift_r(w[1], w[2], 16), TAP_H_HI, 0u));
+        h[2] = __dp4a(__funnelshift_r(w[0], w[1], 24), TAP_H_LO, __dp4a(__funnelshift_r(w[1], w[2], 24), TAP_H_HI, 0u));
+        h[3] = __dp4a(w[1], TAP_H_LO, __dp4a(w[2], TAP_H_HI, 0u));
+    };
+    // row pair = input rows 2i, 2i+1 packed per pixel (even row in the low half)
+    auto make_pair = [&](const unsigned int (&we)[3], const unsigned int (&wo)[3], unsigned int (&pr)[4]) {
         unsigned int he[4], ho[4];
-        hrow(2 * i, he);
-        hrow(2 * i + 1, ho);
+        hrow(we, he);
+        hrow(wo, ho);
 #pragma unroll
         for (int k = 0; k < 4; ++k) pr[k] = __byte_perm(he[k], ho[k], 0x5410);
     };
 
     unsigned int p0[4], p1[4], p2[4], p3[4];
-    load_pair(0, p0);
-    load_pair(1, p1);
-    load_pair(2, p2);
-    // pair i completes output rows 2i-6 (input rows 2i-6 .. 2i) and 2i-5 (input rows 2i-5 .. 2i+1)
+    unsigned int we[3], wo[3];
+    {
+        unsigned int a0[3], a1[3], a2[3], a3[3], a4[3], a5[3];
+        load_row(0, a0); load_row(1, a1); load_row(2, a2); load_row(3, a3); load_row(4, a4); load_row(5, a5);
+        load_row(6, we); load_row(7, wo);
+        make_pair(a0, a1, p0);
+        make_pair(a2, a3, p1);
+        make_pair(a4, a5, p2);
+    }
+    // pair i completes output rows 2i-6 (input rows 2i-6 .. 2i) and 2i-5 (input rows 2i-5 .. 2i+1); the words of pair i+1
+    // are requested before pair i is consumed
 #pragma unroll 4
     for (int i = 3; i < BL_ROWS / 2 + 3; ++i) {
         const int o = 2 * i - 6;
         if (o >= rowsOut) break;
-        load_pair(i, p3);
+        make_pair(we, wo, p3);
+        load_row(2 * i + 2, we);
+        load_row(2 * i + 3, wo);
         unsigned int ve[4], vo[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {

@@ -335,6 +335,7 @@ int orbx_create(int nfeatures, float scaleFactor, int nlevels, int iniTh, int mi
         return fail(ORB_ERR_CUDA, "orbx_create: %s", cudaGetErrorString(ce));
     }
     int st = upload_brief_pattern();
+    if (st == ORB_OK) st = upload_orientation_table(e->umax);
     if (st == ORB_OK && maxW > 0 && maxH > 0) st = configure(e, maxW, maxH, maxBatch);
     if (st != ORB_OK) {
         orbx_destroy(e);

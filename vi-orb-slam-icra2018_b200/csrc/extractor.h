@@ -110,5 +110,6 @@ int launch_brief(const ExtractParams& P, int maxKeypoints, orb_keypoint* dKps, u
 int octree_smem_plan(int nodeCap, int cellCap, int* smemBytes, int* keyCapSmem);
 int blur_cta_count(int w, int h);
 int upload_brief_pattern();
+int upload_orientation_table(const int* umax);
 
 }  // namespace orbb

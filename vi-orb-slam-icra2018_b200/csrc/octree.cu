@@ -15,8 +15,8 @@
 //      node sits nearer the list front, so ties on size resolve toward the smaller list index.
 // Candidate keys come from the per-cell FAST slots in (cell row, cell col, y, x) order and live in shared memory
 // (global spill space if a level has more candidates than fit).  The selected keys get their orientation from the
-// unblurred level in the same kernel: one warp per keypoint, integer moments, float32 fastAtan2 with the reference's
-// operation order (no FMA).
+// unblurred level in the same kernel: one warp per keypoint, integer moments by dot products of aligned pixel words
+// with tabulated coordinate bytes, float32 fastAtan2 with the reference's operation order (no FMA).
 #include <cfloat>
 
 #include "extractor.h"
@@ -98,6 +98,42 @@ __device__ int block_scan_exclusive(int* a, int n, int* tmp) {
     }
     __syncthreads();
     return total;
+}
+
+// IC_Angle (ORBextractor.cc:79-106) as dot products.  The 31 rows of the circular patch are read as aligned 32-bit words
+// (9 per row); for each of the four alignments of the patch's left edge and each (row, word) item the table holds the
+// signed u and v coordinates of the word's four bytes (0 outside the circle), the row and the word's byte offset, so
+//   m10 += dp4a(u bytes, pixels),  m01 += dp4a(v bytes, pixels).
+// 279 items are dealt to the 32 lanes of a warp, 9 each (the last 9 table slots are zero).
+constexpr int kOriItems = 9 * 32;
+__device__ int4 gOriTable[4 * kOriItems];
+
+int upload_orientation_table(const int* umax) {
+    static int4 host[4 * kOriItems];
+    for (int a = 0; a < 4; ++a)
+        for (int t = 0; t < kOriItems; ++t) {
+            int4 e = make_int4(0, 0, 0, 0);
+            if (t < 9 * kPatch) {
+                const int v = t / 9 - kHalfPatch, j = t % 9;
+                unsigned int uc = 0, vc = 0;
+                for (int b = 0; b < 4; ++b) {
+                    const int u = 4 * j + b - a - kHalfPatch;
+                    if (u < -kHalfPatch || u > kHalfPatch || (u < 0 ? -u : u) > umax[v < 0 ? -v : v]) continue;
+                    uc |= (unsigned int)(u & 0xff) << (8 * b);
+                    vc |= (unsigned int)(v & 0xff) << (8 * b);
+                }
+                e = make_int4((int)uc, (int)vc, v, 4 * j);
+            }
+            host[a * kOriItems + t] = e;
+        }
+    ORB_CUDA(cudaMemcpyToSymbol(gOriTable, host, sizeof host));
+    return ORB_OK;
+}
+
+__device__ __forceinline__ int dp4a_su(int coef, unsigned int pixels, int acc) {   // signed bytes x unsigned bytes
+    int d;
+    asm("dp4a.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(coef), "r"(pixels), "r"(acc));
+    return d;
 }
 
 // cv::fastAtan2 (degrees), float32 with the reference operation order, every op rounded (no contraction)
@@ -325,23 +361,20 @@ octree_kernel(const __grid_constant__ ExtractParams P, int nodeCap, int cellCap,
     for (int s = warp; s < nOut; s += OT_WARPS) {
         const unsigned int key = kv[t1[s]];
         const int x = key_x(key) + 16, y = key_y(key) + 16;   // + minBorderX/Y (:843-844)
-        const unsigned char* c = level0 + (size_t)y * L.pitch + x;
-        const int u = lane - kHalfPatch;
+        const int al = (x - kHalfPatch) & 3;          // the level's pixel (0, y) is 4-byte aligned
+        const unsigned char* c0 = level0 + (size_t)y * L.pitch + (x - kHalfPatch - al);
+        const int4* tab = gOriTable + al * kOriItems + lane;
+        int4 e[9];
+        unsigned int w[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) e[i] = __ldg(tab + 32 * i);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) w[i] = __ldg(reinterpret_cast<const unsigned int*>(c0 + e[i].z * L.pitch + e[i].w));
         int m10 = 0, m01 = 0;
-        if (lane < kPatch) {
-            // all 31 row loads are issued before the first use (the loop is latency-bound otherwise)
-            const int au = u < 0 ? -u : u;
-            int val[kPatch];
 #pragma unroll
-            for (int v = -kHalfPatch; v <= kHalfPatch; ++v)
-                val[v + kHalfPatch] = (au <= P.umax[v < 0 ? -v : v]) ? (int)c[v * L.pitch + u] : 0;
-            int rowSum = 0;
-#pragma unroll
-            for (int v = -kHalfPatch; v <= kHalfPatch; ++v) {
-                rowSum += val[v + kHalfPatch];
-                m01 += v * val[v + kHalfPatch];
-            }
-            m10 = u * rowSum;
+        for (int i = 0; i < 9; ++i) {
+            m10 = dp4a_su(e[i].x, w[i], m10);
+            m01 = dp4a_su(e[i].y, w[i], m01);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
