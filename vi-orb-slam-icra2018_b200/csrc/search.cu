@@ -250,16 +250,6 @@ constexpr int kOrdShift = 22;
 constexpr int kOrdMask = (1 << kOrdShift) - 1;
 constexpr int kNone = 0x7fffffff;
 
-__device__ __forceinline__ void warp_min2(int& best, int& second) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const int ob = __shfl_xor_sync(0xffffffffu, best, o);
-        const int os = __shfl_xor_sync(0xffffffffu, second, o);
-        second = min(min(second, os), max(best, ob));
-        best = min(best, ob);
-    }
-}
-
 constexpr int kCandIdxMask = 0x00ffffff;   // candidate.x = keypoint index | octave << 24
 
 // Rotation-histogram tail shared by the searches (e.g. ORBmatcher.cc:473-512).  Pushes were recorded in order as
@@ -294,177 +284,235 @@ __device__ void histogram_prune(const int* pushA, const int* pushB, const int* p
     __syncwarp();
 }
 
-// Ordered walk over the queries by ONE warp.  The order-dependent state (what earlier queries matched) lives in shared
-// memory; per-query metadata is fetched 32 queries at a time and the first 32 candidates of the NEXT query are loaded
-// while the current one is reduced; the winning candidates travel by shuffle.  The dependent chain per query is
-// therefore shared-memory lookups and shuffles only -- no global-memory round trip.
-//   meta(qi)                      -> small per-query integer needed by accept (fetched with the batch)
-//   skip(c)                       -> candidate c is ignored (dynamic state)
-//   accept(i, metaVal, best, second, bestX, secondX) is warp-uniform; bestX/secondX = candidate.x of the winners
-template <class Meta, class Skip, class Accept>
+// Ordered walk over the queries by ONE CTA.  The order-dependent state (what earlier queries matched) lives in shared
+// memory and is indexed by TARGET keypoint; a query reads it only at its own candidates and changes it only at the
+// candidate it accepts.  That makes the sequential loop speculatable:
+//   round: the next 16 unresolved queries are evaluated at once, one warp each (candidates spread over the lanes, best /
+//          second by two warp reductions -- keys carry the candidate's position, hence the owning lane), all against
+//          the state left by the committed queries.  Every tentative acceptor stamps its target with its rank in the
+//          round (shared atomicMin).  State changes only ever REMOVE candidates, so a query's outcome can change only
+//          if its best or second-best target goes: it is DIRTY if one of the two carries a smaller stamp than its own
+//          rank.  The clean prefix of the round commits -- its results are the sequential ones -- and the next round
+//          starts at the first dirty query.  The first query of a round is never dirty, so a round
+//          retires at least one query and, with conflicts as rare as they are between 2000 keypoints, nearly all 16.
+// Queries and their candidate lists (contiguous in the CSR) are staged in shared memory a chunk at a time with coalesced
+// loads, so the per-round chain is shared-memory lookups, warp reductions and three barriers -- no global round trip.
+//   meta(qi)                       small per-query integer needed by decide / commit (staged with the chunk)
+//   skip(c)                        candidate c is ignored (dynamic state)
+//   decide(qi, meta, best, second, bestX, secondX) -> accept?   pure; bestX/secondX = candidate.x of the winners
+//   commit(qi, meta, best, bestX, pushPos) -> change of the match count; run by ONE thread per accepted query
+constexpr int RP_WARPS = 16;                 // queries in flight per round
+constexpr int RP_THREADS = RP_WARPS * 32;
+constexpr int kChunkQueries = 256;           // queries staged per chunk
+constexpr int kStageCand = 6144;             // candidates staged per chunk (48 KB)
+constexpr int kReplayFixedInts = kStageCand * 2 + kChunkQueries * 4;   // staging area at the start of dynamic smem
+
+template <class Meta, class Skip, class Decide, class Commit>
 __device__ __forceinline__ void replay_queries(const AreaQuery* __restrict__ q, const int* __restrict__ offsets,
-                                               const int2* __restrict__ cand, int nq, Meta meta, Skip skip, Accept accept) {
-    const int lane = threadIdx.x & 31;
-    for (int i0 = 0; i0 < nq; i0 += 32) {
-        const int qi = i0 + lane;
-        int act = 0, a = 0, b = 0, mv = 0;
-        if (qi < nq) { act = q[qi].active; a = offsets[qi]; b = offsets[qi + 1]; mv = meta(qi); }
-        int na = __shfl_sync(0xffffffffu, a, 0), nb = __shfl_sync(0xffffffffu, b, 0), nact = __shfl_sync(0xffffffffu, act, 0);
-        int2 pre = (nact && na + lane < nb) ? cand[na + lane] : make_int2(-1, 0);
-        const int m = min(32, nq - i0);
-        for (int j = 0; j < m; ++j) {
-            const int ca = na, cb = nb, cact = nact;
-            const int2 cur = pre;
-            if (j + 1 < m) {
-                na = __shfl_sync(0xffffffffu, a, j + 1); nb = __shfl_sync(0xffffffffu, b, j + 1); nact = __shfl_sync(0xffffffffu, act, j + 1);
-                pre = (nact && na + lane < nb) ? cand[na + lane] : make_int2(-1, 0);
+                                               const int2* __restrict__ cand, int nq, int* stamp, int nTargets, int& nPush,
+                                               int* nMatchesShared, Meta meta, Skip skip, Decide decide, Commit commit) {
+    extern __shared__ int dyn[];
+    int2* stage = reinterpret_cast<int2*>(dyn);
+    int4* qmeta = reinterpret_cast<int4*>(dyn + kStageCand * 2);   // candidate range [x, y), active, meta
+    __shared__ int sOk[RP_WARPS], sDirty[RP_WARPS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < nTargets; i += RP_THREADS) stamp[i] = INT_MAX;
+    int base = 0, chunkBegin = 0, chunkEnd = 0, stageA = 0;
+    bool staged = true;
+    while (base < nq) {
+        if (base == chunkEnd) {
+            // stage the next chunk: as many queries (<= 256) as have their candidates fit the buffer
+            __syncthreads();   // the previous chunk has been consumed
+            const int first = offsets[base];
+            const int qi = base + tid;
+            int a = 0, b = 0;
+            bool fits = false;
+            if (tid < kChunkQueries && qi < nq) { a = offsets[qi]; b = offsets[qi + 1]; fits = b - first <= kStageCand; }
+            const int cnt = __syncthreads_count(fits);     // offsets are monotone: the fitting queries are a prefix
+            staged = cnt > 0;
+            chunkBegin = base;
+            chunkEnd = base + max(cnt, 1);
+            stageA = first;
+            if (tid < chunkEnd - base) qmeta[tid] = make_int4(a, b, q[qi].active, meta(qi));
+            if (staged) {
+                const int total = offsets[chunkEnd] - first;
+#pragma unroll 4
+                for (int k = tid; k < total; k += RP_THREADS) stage[k] = cand[first + k];
             }
-            if (!cact || ca == cb) continue;
+            __syncthreads();
+        }
+        const int2* src = staged ? stage - stageA : cand;
+        const int nr = min(RP_WARPS, chunkEnd - base);
+
+        // A. speculative evaluation, one warp per query
+        bool ok = false;
+        int gb = kNone, bestX = -1, target = -1, target2 = -1;
+        int4 mq = make_int4(0, 0, 0, 0);
+        if (warp < nr) mq = qmeta[base - chunkBegin + warp];
+        if (warp < nr && mq.z && mq.x < mq.y) {
             int bk = kNone, sk = kNone, bx = -1, sx = -1;   // this lane's best / second key and their candidate.x
-            if (cur.x >= 0 && !skip(cur)) { bk = (cur.y << kOrdShift) | lane; bx = cur.x; }
-            for (int k = ca + 32 + lane; k < cb; k += 32) {
-                const int2 c = cand[k];
+            for (int k = mq.x + lane; k < mq.y; k += 32) {
+                const int2 c = src[k];
                 if (skip(c)) continue;
-                const int key = (c.y << kOrdShift) | (k - ca);
+                const int key = (c.y << kOrdShift) | (k - mq.x);
                 if (key < bk) { sk = bk; sx = bx; bk = key; bx = c.x; }
                 else if (key < sk) { sk = key; sx = c.x; }
             }
-            int gb = bk, gs = sk;
-            warp_min2(gb, gs);
-            // keys are unique (they carry the candidate's position), so exactly one lane owns each winner
-            int bestX = -1, secondX = -1;
-            if (gb != kNone) bestX = __shfl_sync(0xffffffffu, bx, __ffs(__ballot_sync(0xffffffffu, bk == gb)) - 1);
-            if (gs != kNone) {
-                const unsigned m1 = __ballot_sync(0xffffffffu, bk == gs), m2 = __ballot_sync(0xffffffffu, sk == gs);
-                const int fromBest = __shfl_sync(0xffffffffu, bx, m1 ? __ffs(m1) - 1 : 0);
-                const int fromSecond = __shfl_sync(0xffffffffu, sx, m2 ? __ffs(m2) - 1 : 0);
-                secondX = m1 ? fromBest : fromSecond;
+            // keys are unique and carry the candidate's position, whose low five bits are the owning lane
+            gb = __reduce_min_sync(0xffffffffu, bk);
+            if (gb != kNone) {
+                const int gs = __reduce_min_sync(0xffffffffu, bk == gb ? sk : bk);
+                bestX = __shfl_sync(0xffffffffu, bx, gb & 31);
+                const int secondX = __shfl_sync(0xffffffffu, bk == gs ? bx : sx, gs & 31);   // meaningful iff gs != kNone
+                target = bestX & kCandIdxMask;
+                if (gs != kNone) target2 = secondX & kCandIdxMask;
+                ok = decide(base + warp, mq.w, gb, gs, bestX, secondX);
+                if (ok && lane == 0) atomicMin(&stamp[target], warp);
             }
-            accept(i0 + j, __shfl_sync(0xffffffffu, mv, j), gb, gs, bestX, secondX);
         }
+        if (lane == 0) sOk[warp] = ok;
+        __syncthreads();
+
+        // B. state only ever REMOVES candidates (occupied / matched flags are set, matched distances shrink), so a
+        //    query's outcome can change only if an earlier query of the round takes its best or its second-best target
+        if (lane == 0)
+            sDirty[warp] = (target >= 0 && stamp[target] < warp) || (target2 >= 0 && stamp[target2] < warp);
+        __syncthreads();
+
+        // C. commit the clean prefix
+        const unsigned dirtyMask = __ballot_sync(0xffffffffu, lane < nr && sDirty[lane]);
+        const int f = dirtyMask ? __ffs(dirtyMask) - 1 : nr;
+        const unsigned okPrefix = __ballot_sync(0xffffffffu, lane < f && sOk[lane]);
+        if (ok && lane == 0) {
+            if (warp < f) {
+                const int delta = commit(base + warp, mq.w, gb, bestX, nPush + __popc(okPrefix & ((1u << warp) - 1u)));
+                if (delta) atomicAdd(nMatchesShared, delta);
+            }
+            stamp[target] = INT_MAX;
+        }
+        nPush += __popc(okPrefix);
+        base += f;
+        __syncthreads();
     }
 }
 
-// SearchForInitialization replay (ORBmatcher.cc:417-517). One warp; m21 / vMatchedDistance in shared memory.
-__global__ void __launch_bounds__(32)
+// SearchForInitialization replay (ORBmatcher.cc:417-517). m21 / vMatchedDistance in shared memory.
+__global__ void __launch_bounds__(RP_THREADS)
 init_replay_kernel(FrameDev f1, FrameDev f2, const AreaQuery* __restrict__ q, const int* __restrict__ offsets,
                    const int2* __restrict__ cand, float ratio, int checkOri, float* prevXY, int* m12, int* pushA,
                    int* pushB, int* nmatchesOut) {
     extern __shared__ int dyn[];
-    int* m21 = dyn;
-    int* matchedDist = dyn + f2.n;
+    int* m21 = dyn + kReplayFixedInts;
+    int* matchedDist = m21 + f2.n;
+    int* stamp = m21 + 2 * f2.n;
     __shared__ int hist[kHistoLength];
     __shared__ int nmatches;
-    const int lane = threadIdx.x;
-    if (lane < kHistoLength) hist[lane] = 0;
-    if (lane == 0) nmatches = 0;
-    for (int i = lane; i < f1.n; i += 32) m12[i] = -1;
-    for (int i = lane; i < f2.n; i += 32) { m21[i] = -1; matchedDist[i] = INT_MAX; }
-    __syncwarp();
+    const int tid = threadIdx.x;
+    if (tid < kHistoLength) hist[tid] = 0;
+    if (tid == 0) nmatches = 0;
+    for (int i = tid; i < f1.n; i += RP_THREADS) m12[i] = -1;
+    for (int i = tid; i < f2.n; i += RP_THREADS) { m21[i] = -1; matchedDist[i] = INT_MAX; }
     int nPush = 0;
-    replay_queries(q, offsets, cand, f1.n, [](int) { return 0; },
+    replay_queries(q, offsets, cand, f1.n, stamp, f2.n, nPush, &nmatches, [](int) { return 0; },
         [&](const int2& c) { return matchedDist[c.x & kCandIdxMask] <= c.y; },               // :444
-        [&](int i1, int, int best, int second, int bestX, int) {
-            const int bd = best == kNone ? INT_MAX : best >> kOrdShift;
+        [&](int, int, int best, int second, int, int) {
+            const int bd = best >> kOrdShift;
             const int sd = second == kNone ? INT_MAX : second >> kOrdShift;
-            if (bd <= kThLow && (float)bd < __fmul_rn((float)sd, ratio)) {                    // :459-461
-                __syncwarp();   // every lane has finished reading the state it is about to change
-                if (lane == 0) {
-                    const int i2 = bestX & kCandIdxMask;
-                    if (m21[i2] >= 0) { m12[m21[i2]] = -1; --nmatches; }                      // :463-467
-                    m12[i1] = i2; m21[i2] = i1; matchedDist[i2] = bd; ++nmatches;
-                    if (checkOri) { pushA[nPush] = i1; pushB[nPush] = i2; }
-                }
-                if (checkOri) ++nPush;
-                __syncwarp();
-            }
+            return bd <= kThLow && (float)bd < __fmul_rn((float)sd, ratio);                   // :459-461
+        },
+        [&](int i1, int, int best, int bestX, int pos) {
+            const int i2 = bestX & kCandIdxMask;
+            int delta = 1;
+            if (m21[i2] >= 0) { m12[m21[i2]] = -1; delta = 0; }                               // :463-467
+            m12[i1] = i2; m21[i2] = i1; matchedDist[i2] = best >> kOrdShift;
+            if (checkOri) { pushA[pos] = i1; pushB[pos] = i2; }
+            return delta;
         });
     __threadfence_block();
-    __syncwarp();
-    if (checkOri)
-        histogram_prune(pushA, pushB, pushA, nPush, hist, m12, true, &nmatches,
-                        [&](int i1) { return f1.keys[i1].angle; }, [&](int i2) { return f2.keys[i2].angle; });
-    __syncwarp();
-    for (int i1 = lane; i1 < f1.n; i1 += 32)
+    __syncthreads();
+    if (tid < 32) {
+        if (checkOri)
+            histogram_prune(pushA, pushB, pushA, nPush, hist, m12, true, &nmatches,
+                            [&](int i1) { return f1.keys[i1].angle; }, [&](int i2) { return f2.keys[i2].angle; });
+        __syncwarp();
+        if (tid == 0) *nmatchesOut = nmatches;
+    }
+    __syncthreads();
+    for (int i1 = tid; i1 < f1.n; i1 += RP_THREADS)
         if (m12[i1] >= 0) {                                             // :515-517
             prevXY[2 * i1] = f2.keys[m12[i1]].x;
             prevXY[2 * i1 + 1] = f2.keys[m12[i1]].y;
         }
-    if (lane == 0) *nmatchesOut = nmatches;
 }
 
 // SearchByProjection(Frame, Frame) replay (ORBmatcher.cc:1363-1495), also the relocalisation overload (:1500-1627, where
-// the acceptance threshold is ORBdist instead of TH_HIGH). One warp; occupancy flags in shared memory.
-__global__ void __launch_bounds__(32)
+// the acceptance threshold is ORBdist instead of TH_HIGH). Occupancy flags in shared memory.
+__global__ void __launch_bounds__(RP_THREADS)
 proj_replay_kernel(FrameDev cur, const AreaQuery* __restrict__ q, const orbm_proj_query* __restrict__ pq, int nq,
                    const int* __restrict__ offsets, const int2* __restrict__ cand, int checkOri, int maxDist,
                    const unsigned char* __restrict__ occIn, int* curMatch, int* pushA, int* pushB, int* nmatchesOut) {
     extern __shared__ int dyn[];
-    unsigned char* occ = reinterpret_cast<unsigned char*>(dyn);
+    int* stamp = dyn + kReplayFixedInts;
+    unsigned char* occ = reinterpret_cast<unsigned char*>(stamp + cur.n);
     __shared__ int hist[kHistoLength];
     __shared__ int nmatches;
-    const int lane = threadIdx.x;
-    if (lane < kHistoLength) hist[lane] = 0;
-    if (lane == 0) nmatches = 0;
-    for (int i = lane; i < cur.n; i += 32) { curMatch[i] = -1; occ[i] = occIn[i]; }
-    __syncwarp();
+    const int tid = threadIdx.x;
+    if (tid < kHistoLength) hist[tid] = 0;
+    if (tid == 0) nmatches = 0;
+    for (int i = tid; i < cur.n; i += RP_THREADS) { curMatch[i] = -1; occ[i] = occIn[i]; }
     int nPush = 0;
-    replay_queries(q, offsets, cand, nq, [&](int qi) { return pq[qi].obs_positive; },
+    replay_queries(q, offsets, cand, nq, stamp, cur.n, nPush, &nmatches, [&](int qi) { return pq[qi].obs_positive; },
         [&](const int2& c) { return occ[c.x & kCandIdxMask] != 0; },                          // :1428-1430
-        [&](int i, int obs, int best, int, int bestX, int) {
-            const int bd = best == kNone ? 256 : best >> kOrdShift;
-            if (bd <= maxDist) {                                                              // :1453 / :1583
-                __syncwarp();
-                if (lane == 0) {
-                    const int i2 = bestX & kCandIdxMask;
-                    curMatch[i2] = i;
-                    occ[i2] = obs ? 1 : 0;
-                    ++nmatches;
-                    if (checkOri) { pushA[nPush] = i; pushB[nPush] = i2; }
-                }
-                if (checkOri) ++nPush;
-                __syncwarp();
-            }
+        [&](int, int, int best, int, int, int) { return (best >> kOrdShift) <= maxDist; },    // :1453 / :1583
+        [&](int i, int obs, int, int bestX, int pos) {
+            const int i2 = bestX & kCandIdxMask;
+            curMatch[i2] = i;
+            occ[i2] = obs ? 1 : 0;
+            if (checkOri) { pushA[pos] = i; pushB[pos] = i2; }
+            return 1;
         });
     __threadfence_block();
-    __syncwarp();
-    if (checkOri)
-        histogram_prune(pushA, pushB, pushB, nPush, hist, curMatch, false, &nmatches,
-                        [&](int i) { return pq[i].angle; }, [&](int i2) { return cur.keys[i2].angle; });
-    __syncwarp();
-    if (lane == 0) *nmatchesOut = nmatches;
+    __syncthreads();
+    if (tid < 32) {
+        if (checkOri)
+            histogram_prune(pushA, pushB, pushB, nPush, hist, curMatch, false, &nmatches,
+                            [&](int i) { return pq[i].angle; }, [&](int i2) { return cur.keys[i2].angle; });
+        __syncwarp();
+        if (tid == 0) *nmatchesOut = nmatches;
+    }
 }
 
-// SearchByProjection(Frame, MapPoints) replay (ORBmatcher.cc:51-126). One warp.
-__global__ void __launch_bounds__(32)
+// SearchByProjection(Frame, MapPoints) replay (ORBmatcher.cc:51-126).
+__global__ void __launch_bounds__(RP_THREADS)
 point_replay_kernel(FrameDev f, const AreaQuery* __restrict__ q, const orbm_point_query* __restrict__ pq, int nq,
                     const int* __restrict__ offsets, const int2* __restrict__ cand, float ratio,
                     const unsigned char* __restrict__ occIn, int* match, int* nmatchesOut) {
     extern __shared__ int dyn[];
-    unsigned char* occ = reinterpret_cast<unsigned char*>(dyn);
-    const int lane = threadIdx.x;
-    for (int i = lane; i < f.n; i += 32) { match[i] = -1; occ[i] = occIn[i]; }
-    __syncwarp();
-    int nmatches = 0;
-    replay_queries(q, offsets, cand, nq, [&](int qi) { return pq[qi].obs_positive; },
+    int* stamp = dyn + kReplayFixedInts;
+    unsigned char* occ = reinterpret_cast<unsigned char*>(stamp + f.n);
+    __shared__ int nmatches;
+    const int tid = threadIdx.x;
+    if (tid == 0) nmatches = 0;
+    for (int i = tid; i < f.n; i += RP_THREADS) { match[i] = -1; occ[i] = occIn[i]; }
+    int nPush = 0;
+    replay_queries(q, offsets, cand, nq, stamp, f.n, nPush, &nmatches, [&](int qi) { return pq[qi].obs_positive; },
         [&](const int2& c) { return occ[c.x & kCandIdxMask] != 0; },                          // :84-86
-        [&](int i, int obs, int best, int second, int bestX, int secondX) {
-            const int bd = best == kNone ? 256 : best >> kOrdShift;
-            if (bd > kThHigh) return;                                                         // :115
+        [&](int, int, int best, int second, int bestX, int secondX) {
+            const int bd = best >> kOrdShift;
+            if (bd > kThHigh) return false;                                                   // :115
             const int bestLevel = bestX >> 24;
             int sd = 256, secondLevel = -1;
             if (second != kNone) { sd = second >> kOrdShift; secondLevel = secondX >> 24; }
-            if (bestLevel == secondLevel && (float)bd > __fmul_rn(ratio, (float)sd)) return;  // :118-119
-            __syncwarp();
-            if (lane == 0) {
-                const int bi = bestX & kCandIdxMask;
-                match[bi] = i;
-                occ[bi] = obs ? 1 : 0;
-            }
-            ++nmatches;
-            __syncwarp();
+            return !(bestLevel == secondLevel && (float)bd > __fmul_rn(ratio, (float)sd));    // :118-119
+        },
+        [&](int i, int obs, int, int bestX, int) {
+            const int bi = bestX & kCandIdxMask;
+            match[bi] = i;
+            occ[bi] = obs ? 1 : 0;
+            return 1;
         });
-    if (lane == 0) *nmatchesOut = nmatches;
+    __syncthreads();
+    if (tid == 0) *nmatchesOut = nmatches;
 }
 
 // ------------------------------------------------------------------------------------------------ triangulation
@@ -663,50 +711,50 @@ bow_candidates_kernel(BowParams P, const int* __restrict__ entryNode, AreaQuery*
     }
 }
 
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(RP_THREADS)
 bow_replay_kernel(FrameDev k1, FrameDev k2, const AreaQuery* __restrict__ q, const int* __restrict__ idx1OfEntry, int nq,
                   const int* __restrict__ offsets, const int2* __restrict__ cand, float ratio, int checkOri, int strictLow,
                   int* m12, int* m21, int* pushA, int* pushB, int* nmatchesOut) {
     extern __shared__ int dyn[];
-    unsigned char* matched2 = reinterpret_cast<unsigned char*>(dyn);
+    int* stamp = dyn + kReplayFixedInts;
+    unsigned char* matched2 = reinterpret_cast<unsigned char*>(stamp + k2.n);
     __shared__ int hist[kHistoLength];
     __shared__ int nmatches;
-    const int lane = threadIdx.x;
-    if (lane < kHistoLength) hist[lane] = 0;
-    if (lane == 0) nmatches = 0;
-    for (int i = lane; i < k1.n; i += 32) m12[i] = -1;
-    for (int i = lane; i < k2.n; i += 32) { m21[i] = -1; matched2[i] = 0; }
-    __syncwarp();
+    const int tid = threadIdx.x;
+    if (tid < kHistoLength) hist[tid] = 0;
+    if (tid == 0) nmatches = 0;
+    for (int i = tid; i < k1.n; i += RP_THREADS) m12[i] = -1;
+    for (int i = tid; i < k2.n; i += RP_THREADS) { m21[i] = -1; matched2[i] = 0; }
     int nPush = 0;
-    replay_queries(q, offsets, cand, nq, [&](int p1) { return idx1OfEntry[p1]; },
+    replay_queries(q, offsets, cand, nq, stamp, k2.n, nPush, &nmatches, [&](int p1) { return idx1OfEntry[p1]; },
         [&](const int2& c) { return matched2[c.x & kCandIdxMask] != 0; },                     // :203-204 / :576
-        [&](int, int idx1, int best, int second, int bestX, int) {
-            const int bd = best == kNone ? 256 : best >> kOrdShift;
+        [&](int, int, int best, int second, int, int) {
+            const int bd = best >> kOrdShift;
             const int sd = second == kNone ? 256 : second >> kOrdShift;
             const bool low = strictLow ? bd < kThLow : bd <= kThLow;                          // :598 / :227
-            if (low && (float)bd < __fmul_rn(ratio, (float)sd)) {                             // :229 / :600
-                __syncwarp();
-                if (lane == 0) {
-                    const int i2 = bestX & kCandIdxMask;
-                    m12[idx1] = i2; m21[i2] = idx1; matched2[i2] = 1; ++nmatches;
-                    if (checkOri) { pushA[nPush] = idx1; pushB[nPush] = i2; }
-                }
-                if (checkOri) ++nPush;
-                __syncwarp();
-            }
+            return low && (float)bd < __fmul_rn(ratio, (float)sd);                            // :229 / :600
+        },
+        [&](int, int idx1, int, int bestX, int pos) {
+            const int i2 = bestX & kCandIdxMask;
+            m12[idx1] = i2; m21[i2] = idx1; matched2[i2] = 1;
+            if (checkOri) { pushA[pos] = idx1; pushB[pos] = i2; }
+            return 1;
         });
     __threadfence_block();
-    __syncwarp();
-    if (checkOri) {
-        histogram_prune(pushA, pushB, pushA, nPush, hist, m12, false, &nmatches,
-                        [&](int i1) { return k1.keys[i1].angle; }, [&](int i2) { return k2.keys[i2].angle; });
-        __threadfence_block();
+    __syncthreads();
+    if (tid < 32) {
+        const int lane = tid;
+        if (checkOri) {
+            histogram_prune(pushA, pushB, pushA, nPush, hist, m12, false, &nmatches,
+                            [&](int i1) { return k1.keys[i1].angle; }, [&](int i2) { return k2.keys[i2].angle; });
+            __threadfence_block();
+            __syncwarp();
+            for (int k = lane; k < nPush; k += 32)
+                if (m12[pushA[k]] < 0) m21[pushB[k]] = -1;
+        }
         __syncwarp();
-        for (int k = lane; k < nPush; k += 32)
-            if (m12[pushA[k]] < 0) m21[pushB[k]] = -1;
+        if (lane == 0) *nmatchesOut = nmatches;
     }
-    __syncwarp();
-    if (lane == 0) *nmatchesOut = nmatches;
 }
 
 }  // namespace orbb
@@ -736,6 +784,7 @@ struct orbm_frame_s {
 
 namespace {
 
+constexpr size_t kReplayFixed = (size_t)kReplayFixedInts * 4;   // candidate / query staging of replay_queries
 constexpr size_t kReplaySmemMax = 160 * 1024;   // shared-memory state of the one-warp replays (20k keypoints for init)
 
 // phase 1 for nq queries already built in h->ws0 (AreaQuery[nq]); leaves offsets in ws1 and candidates in ws2
@@ -869,10 +918,10 @@ int orbm_search_for_initialization(orbm_handle h, orbm_frame f1, orbm_frame f2, 
     ORB_CHECK(h->out2.reserve((size_t)(n1 + 1) * 4 * 2));      // pushBin, pushVal
     ORB_CHECK(h->out3.reserve(16));
     int* pushBin = h->out2.as<int>();
-    const size_t replaySmem = (size_t)std::max(n2, 1) * 8;       // m21 + vMatchedDistance
-    if (replaySmem > kReplaySmemMax) return fail(ORB_ERR_CAPACITY, "orbm_search_for_initialization: %d keypoints exceed the replay state (%d)", n2, (int)(kReplaySmemMax / 8));
-    ORB_CUDA(cudaFuncSetAttribute(init_replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kReplaySmemMax));
-    init_replay_kernel<<<1, 32, replaySmem, st>>>(d1, d2, h->ws0.as<AreaQuery>(), h->ws1.as<int>(), h->ws2.as<int2>(), ratio, checkOri,
+    const size_t replaySmem = (size_t)std::max(n2, 1) * 12 + 16;  // m21 + vMatchedDistance + stamps
+    if (replaySmem > kReplaySmemMax) return fail(ORB_ERR_CAPACITY, "orbm_search_for_initialization: %d keypoints exceed the replay state (%d)", n2, (int)(kReplaySmemMax / 12));
+    ORB_CUDA(cudaFuncSetAttribute(init_replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kReplayFixed + kReplaySmemMax)));
+    init_replay_kernel<<<1, RP_THREADS, kReplayFixed + replaySmem, st>>>(d1, d2, h->ws0.as<AreaQuery>(), h->ws1.as<int>(), h->ws2.as<int2>(), ratio, checkOri,
                                                   h->in0.as<float>(), h->out0.as<int>(), pushBin, pushBin + n1 + 1, h->out3.as<int>());
     h->launches += 1;
     ORB_CUDA(cudaGetLastError());
@@ -922,9 +971,9 @@ int orbm_search_by_projection_ex(orbm_handle h, orbm_frame cur, const float* sf,
     ORB_CHECK(h->out2.reserve((size_t)(nq + 1) * 4 * 2));
     ORB_CHECK(h->out3.reserve(16));
     int* pushBin = h->out2.as<int>();
-    if ((size_t)n + 16 > kReplaySmemMax) return fail(ORB_ERR_CAPACITY, "orbm_search_by_projection: %d keypoints exceed the replay state", n);
-    ORB_CUDA(cudaFuncSetAttribute(proj_replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kReplaySmemMax));
-    proj_replay_kernel<<<1, 32, (size_t)n + 16, st>>>(d, h->ws0.as<AreaQuery>(), h->in0.as<orbm_proj_query>(), nq, h->ws1.as<int>(),
+    if (5 * (size_t)n + 32 > kReplaySmemMax) return fail(ORB_ERR_CAPACITY, "orbm_search_by_projection: %d keypoints exceed the replay state", n);
+    ORB_CUDA(cudaFuncSetAttribute(proj_replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kReplayFixed + kReplaySmemMax)));
+    proj_replay_kernel<<<1, RP_THREADS, kReplayFixed + 5 * (size_t)n + 32, st>>>(d, h->ws0.as<AreaQuery>(), h->in0.as<orbm_proj_query>(), nq, h->ws1.as<int>(),
                                                       h->ws2.as<int2>(), checkOri, maxDist, h->in4.as<unsigned char>(), h->out0.as<int>(),
                                                       pushBin, pushBin + nq + 1, h->out3.as<int>());
     h->launches += 1;
@@ -964,9 +1013,9 @@ int orbm_search_by_projection_points(orbm_handle h, orbm_frame f, const float* s
     ORB_CHECK(run_candidates(h, d, h->in1.as<uint4>(), nq, uRight ? h->in3.as<float>() : nullptr, &total));
     ORB_CHECK(h->out0.reserve((size_t)(n + 1) * 4));
     ORB_CHECK(h->out3.reserve(16));
-    if ((size_t)n + 16 > kReplaySmemMax) return fail(ORB_ERR_CAPACITY, "orbm_search_by_projection_points: %d keypoints exceed the replay state", n);
-    ORB_CUDA(cudaFuncSetAttribute(point_replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kReplaySmemMax));
-    point_replay_kernel<<<1, 32, (size_t)n + 16, st>>>(d, h->ws0.as<AreaQuery>(), h->in0.as<orbm_point_query>(), nq, h->ws1.as<int>(),
+    if (5 * (size_t)n + 32 > kReplaySmemMax) return fail(ORB_ERR_CAPACITY, "orbm_search_by_projection_points: %d keypoints exceed the replay state", n);
+    ORB_CUDA(cudaFuncSetAttribute(point_replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kReplayFixed + kReplaySmemMax)));
+    point_replay_kernel<<<1, RP_THREADS, kReplayFixed + 5 * (size_t)n + 32, st>>>(d, h->ws0.as<AreaQuery>(), h->in0.as<orbm_point_query>(), nq, h->ws1.as<int>(),
                                                        h->ws2.as<int2>(), ratio, h->in4.as<unsigned char>(), h->out0.as<int>(),
                                                        h->out3.as<int>());
     h->launches += 1;
@@ -1060,7 +1109,7 @@ int orbm_search_by_bow(orbm_handle h, orbm_frame k1, orbm_frame k2, int nNodes1,
     for (int a = 1; a < nNodes2; ++a)
         if (nodeId2[a] <= nodeId2[a - 1]) return fail(ORB_ERR_INVALID, "orbm_search_by_bow: node ids of frame 2 not ascending");
     if (e1 == 0 || e2 == 0) return ORB_OK;
-    if ((size_t)n2 + 16 > kReplaySmemMax) return fail(ORB_ERR_CAPACITY, "orbm_search_by_bow: %d keypoints exceed the replay state", n2);
+    if (5 * (size_t)n2 + 32 > kReplaySmemMax) return fail(ORB_ERR_CAPACITY, "orbm_search_by_bow: %d keypoints exceed the replay state", n2);
     cudaStream_t st = h->stream;
     std::vector<int> ints;
     auto putInts = [&](const int* p, int n) { size_t o = ints.size(); ints.insert(ints.end(), p, p + n); return o; };
@@ -1096,8 +1145,8 @@ int orbm_search_by_bow(orbm_handle h, orbm_frame k1, orbm_frame k2, int nNodes1,
     ORB_CHECK(h->out2.reserve((size_t)(e1 + 1) * 4 * 2));
     ORB_CHECK(h->out3.reserve(16));
     int* pushA = h->out2.as<int>();
-    ORB_CUDA(cudaFuncSetAttribute(bow_replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kReplaySmemMax));
-    bow_replay_kernel<<<1, 32, (size_t)n2 + 16, st>>>(P.k1, P.k2, h->ws0.as<AreaQuery>(), P.idx1, e1, offsets, h->ws2.as<int2>(), ratio,
+    ORB_CUDA(cudaFuncSetAttribute(bow_replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kReplayFixed + kReplaySmemMax)));
+    bow_replay_kernel<<<1, RP_THREADS, kReplayFixed + 5 * (size_t)n2 + 32, st>>>(P.k1, P.k2, h->ws0.as<AreaQuery>(), P.idx1, e1, offsets, h->ws2.as<int2>(), ratio,
                                                       checkOri, strictLow, h->out0.as<int>(), h->out1.as<int>(), pushA,
                                                       pushA + e1 + 1, h->out3.as<int>());
     h->launches += 5;
