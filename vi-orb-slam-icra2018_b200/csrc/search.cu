@@ -126,10 +126,18 @@ __device__ __forceinline__ int warp_enumerate(const FrameDev& f, const AreaQuery
     if (cr.empty) return 0;
     const bool checkLevels = (q.minLevel > 0) || (q.maxLevel >= 0);   // Frame.cc:692
     int base = 0;
-    for (int ix = cr.c0; ix <= cr.c1; ++ix)
-        for (int iy = cr.r0; iy <= cr.r1; ++iy) {
-            const int c = ix * kGridRows + iy;
-            const int a = f.cellStart[c], b = f.cellStart[c + 1];
+    // cell id = ix * rows + iy and bucket members are stored cell after cell, so the cells (ix, r0..r1) of one grid
+    // column are ONE contiguous run of cellIdx, already in the reference's (iy, bucket) order. The runs' bounds are
+    // fetched 32 columns at a time.
+    for (int ix0 = cr.c0; ix0 <= cr.c1; ix0 += 32) {
+        int ra = 0, rb = 0;
+        if (ix0 + lane <= cr.c1) {
+            ra = f.cellStart[(ix0 + lane) * kGridRows + cr.r0];
+            rb = f.cellStart[(ix0 + lane) * kGridRows + cr.r1 + 1];
+        }
+        const int ncol = min(32, cr.c1 - ix0 + 1);
+        for (int j = 0; j < ncol; ++j) {
+            const int a = __shfl_sync(0xffffffffu, ra, j), b = __shfl_sync(0xffffffffu, rb, j);
             for (int k0 = a; k0 < b; k0 += 32) {
                 const int k = k0 + lane;
                 bool ok = false;
@@ -154,6 +162,7 @@ __device__ __forceinline__ int warp_enumerate(const FrameDev& f, const AreaQuery
                 base += __popc(m);
             }
         }
+    }
     return base;
 }
 
@@ -300,6 +309,7 @@ __device__ void histogram_prune(const int* pushA, const int* pushB, const int* p
 //   meta(qi)                       small per-query integer needed by decide / commit (staged with the chunk)
 //   skip(c)                        candidate c is ignored (dynamic state)
 //   decide(qi, meta, best, second, bestX, secondX) -> accept?   pure; bestX/secondX = candidate.x of the winners
+//                                  (kUsesSecond = false promises that it ignores second / secondX)
 //   commit(qi, meta, best, bestX, pushPos) -> change of the match count; run by ONE thread per accepted query
 constexpr int RP_WARPS = 16;                 // queries in flight per round
 constexpr int RP_THREADS = RP_WARPS * 32;
@@ -307,7 +317,7 @@ constexpr int kChunkQueries = 256;           // queries staged per chunk
 constexpr int kStageCand = 6144;             // candidates staged per chunk (48 KB)
 constexpr int kReplayFixedInts = kStageCand * 2 + kChunkQueries * 4;   // staging area at the start of dynamic smem
 
-template <class Meta, class Skip, class Decide, class Commit>
+template <bool kUsesSecond, class Meta, class Skip, class Decide, class Commit>
 __device__ __forceinline__ void replay_queries(const AreaQuery* __restrict__ q, const int* __restrict__ offsets,
                                                const int2* __restrict__ cand, int nq, int* stamp, int nTargets, int& nPush,
                                                int* nMatchesShared, Meta meta, Skip skip, Decide decide, Commit commit) {
@@ -365,7 +375,7 @@ __device__ __forceinline__ void replay_queries(const AreaQuery* __restrict__ q, 
                 bestX = __shfl_sync(0xffffffffu, bx, gb & 31);
                 const int secondX = __shfl_sync(0xffffffffu, bk == gs ? bx : sx, gs & 31);   // meaningful iff gs != kNone
                 target = bestX & kCandIdxMask;
-                if (gs != kNone) target2 = secondX & kCandIdxMask;
+                if (kUsesSecond && gs != kNone) target2 = secondX & kCandIdxMask;
                 ok = decide(base + warp, mq.w, gb, gs, bestX, secondX);
                 if (ok && lane == 0) atomicMin(&stamp[target], warp);
             }
@@ -413,7 +423,7 @@ init_replay_kernel(FrameDev f1, FrameDev f2, const AreaQuery* __restrict__ q, co
     for (int i = tid; i < f1.n; i += RP_THREADS) m12[i] = -1;
     for (int i = tid; i < f2.n; i += RP_THREADS) { m21[i] = -1; matchedDist[i] = INT_MAX; }
     int nPush = 0;
-    replay_queries(q, offsets, cand, f1.n, stamp, f2.n, nPush, &nmatches, [](int) { return 0; },
+    replay_queries<true>(q, offsets, cand, f1.n, stamp, f2.n, nPush, &nmatches, [](int) { return 0; },
         [&](const int2& c) { return matchedDist[c.x & kCandIdxMask] <= c.y; },               // :444
         [&](int, int, int best, int second, int, int) {
             const int bd = best >> kOrdShift;
@@ -461,7 +471,7 @@ proj_replay_kernel(FrameDev cur, const AreaQuery* __restrict__ q, const orbm_pro
     if (tid == 0) nmatches = 0;
     for (int i = tid; i < cur.n; i += RP_THREADS) { curMatch[i] = -1; occ[i] = occIn[i]; }
     int nPush = 0;
-    replay_queries(q, offsets, cand, nq, stamp, cur.n, nPush, &nmatches, [&](int qi) { return pq[qi].obs_positive; },
+    replay_queries<false>(q, offsets, cand, nq, stamp, cur.n, nPush, &nmatches, [&](int qi) { return pq[qi].obs_positive; },
         [&](const int2& c) { return occ[c.x & kCandIdxMask] != 0; },                          // :1428-1430
         [&](int, int, int best, int, int, int) { return (best >> kOrdShift) <= maxDist; },    // :1453 / :1583
         [&](int i, int obs, int, int bestX, int pos) {
@@ -495,7 +505,7 @@ point_replay_kernel(FrameDev f, const AreaQuery* __restrict__ q, const orbm_poin
     if (tid == 0) nmatches = 0;
     for (int i = tid; i < f.n; i += RP_THREADS) { match[i] = -1; occ[i] = occIn[i]; }
     int nPush = 0;
-    replay_queries(q, offsets, cand, nq, stamp, f.n, nPush, &nmatches, [&](int qi) { return pq[qi].obs_positive; },
+    replay_queries<true>(q, offsets, cand, nq, stamp, f.n, nPush, &nmatches, [&](int qi) { return pq[qi].obs_positive; },
         [&](const int2& c) { return occ[c.x & kCandIdxMask] != 0; },                          // :84-86
         [&](int, int, int best, int second, int bestX, int secondX) {
             const int bd = best >> kOrdShift;
@@ -726,7 +736,7 @@ bow_replay_kernel(FrameDev k1, FrameDev k2, const AreaQuery* __restrict__ q, con
     for (int i = tid; i < k1.n; i += RP_THREADS) m12[i] = -1;
     for (int i = tid; i < k2.n; i += RP_THREADS) { m21[i] = -1; matched2[i] = 0; }
     int nPush = 0;
-    replay_queries(q, offsets, cand, nq, stamp, k2.n, nPush, &nmatches, [&](int p1) { return idx1OfEntry[p1]; },
+    replay_queries<true>(q, offsets, cand, nq, stamp, k2.n, nPush, &nmatches, [&](int p1) { return idx1OfEntry[p1]; },
         [&](const int2& c) { return matched2[c.x & kCandIdxMask] != 0; },                     // :203-204 / :576
         [&](int, int, int best, int second, int, int) {
             const int bd = best >> kOrdShift;
