@@ -161,7 +161,7 @@ def single_frame_latency(device, iters=30):
         else:
             q = np.zeros(len(ka), orbb200.PROJ_QUERY_DTYPE)
             q["u"], q["v"], q["invz"], q["octave"], q["valid"], q["obs_positive"], q["angle"] = \
-                ka["x"] - 7, ka["y"] - 3, 0.1, ka["octave"], 1, 1, ka["angle"]
+                ka["x"] + 7, ka["y"] + 3, 0.1, ka["octave"], 1, 1, ka["angle"]
             out["search_by_projection_th15"] = med(lambda: m.search_by_projection(f2, sf, q, da, 15.0, 0, None, None, 0.0, True))
             out["search_by_projection_matches"] = int(m.search_by_projection(f2, sf, q, da, 15.0, 0, None, None, 0.0, True)[0])
         f1.close(); f2.close(); ex.close()

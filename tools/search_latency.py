@@ -16,7 +16,7 @@ for name, (w, h) in (("euroc", (752, 480)), ("kitti", (1241, 376))):
     f1, f2 = m.frame(ka, da, bounds), m.frame(kb, db, bounds)
     prev = np.stack([ka["x"], ka["y"]], 1).astype(np.float32)
     q = np.zeros(len(ka), orbb200.PROJ_QUERY_DTYPE)
-    q["u"], q["v"], q["invz"], q["octave"], q["valid"], q["obs_positive"], q["angle"] = ka["x"] - 7, ka["y"] - 3, 0.1, ka["octave"], 1, 1, ka["angle"]
+    q["u"], q["v"], q["invz"], q["octave"], q["valid"], q["obs_positive"], q["angle"] = ka["x"] + 7, ka["y"] + 3, 0.1, ka["octave"], 1, 1, ka["angle"]
     for it in range(3):
         t0 = time.perf_counter(); m.search_for_initialization(f1, f2, prev, 100, 0.9, True); t1 = time.perf_counter()
         m.search_by_projection(f2, sf, q, da, 15.0, 0, None, None, 0.0, True); t2 = time.perf_counter()

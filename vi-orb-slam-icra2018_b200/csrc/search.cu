@@ -268,16 +268,16 @@ constexpr int kCandIdxMask = 0x00ffffff;   // candidate.x = keypoint index | oct
 template <class AngleA, class AngleB>
 __device__ void histogram_prune(const int* pushA, const int* pushB, const int* pushVal, int nPush, int* hist, int* target,
                                 bool guardMatched, int* nmatches, AngleA angleA, AngleB angleB) {
-    const int lane = threadIdx.x & 31;
+    // whole CTA; the caller has synchronised after the last push
+    const int tid = threadIdx.x, nthr = blockDim.x;
     __shared__ int keep[3];
     __shared__ int removed;
-    if (lane == 0) removed = 0;
-    __syncwarp();
-    for (int k = lane; k < nPush; k += 32) atomicAdd(&hist[rotation_bin(angleA(pushA[k]), angleB(pushB[k]))], 1);
-    __syncwarp();
-    if (lane == 0) three_maxima(hist, keep[0], keep[1], keep[2]);
-    __syncwarp();
-    for (int k = lane; k < nPush; k += 32) {
+    if (tid == 0) removed = 0;
+    for (int k = tid; k < nPush; k += nthr) atomicAdd(&hist[rotation_bin(angleA(pushA[k]), angleB(pushB[k]))], 1);
+    __syncthreads();
+    if (tid == 0) three_maxima(hist, keep[0], keep[1], keep[2]);
+    __syncthreads();
+    for (int k = tid; k < nPush; k += nthr) {
         const int b = rotation_bin(angleA(pushA[k]), angleB(pushB[k]));
         if (b == keep[0] || b == keep[1] || b == keep[2]) continue;
         const int v = pushVal[k];
@@ -288,9 +288,9 @@ __device__ void histogram_prune(const int* pushA, const int* pushB, const int* p
             atomicAdd(&removed, 1);
         }
     }
-    __syncwarp();
-    if (lane == 0) *nmatches -= removed;
-    __syncwarp();
+    __syncthreads();
+    if (tid == 0) *nmatches -= removed;
+    __syncthreads();
 }
 
 // Ordered walk over the queries by ONE CTA.  The order-dependent state (what earlier queries matched) lives in shared
@@ -324,36 +324,20 @@ __device__ __forceinline__ void replay_queries(const AreaQuery* __restrict__ q, 
     extern __shared__ int dyn[];
     int2* stage = reinterpret_cast<int2*>(dyn);
     int4* qmeta = reinterpret_cast<int4*>(dyn + kStageCand * 2);   // candidate range [x, y), active, meta
-    __shared__ int sOk[RP_WARPS], sDirty[RP_WARPS];
+    __shared__ int4 sRound[32];   // per query of the round: accepted?, best target, second-best target
+    __shared__ int sVerdict[2];   // retired queries, mask of the committing ones
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < nTargets; i += RP_THREADS) stamp[i] = INT_MAX;
-    int base = 0, chunkBegin = 0, chunkEnd = 0, stageA = 0;
+    // two stamp arrays, used by alternate rounds: a round's stamps are cleared during the next round, when nobody reads them
+    for (int i = tid; i < 2 * nTargets; i += RP_THREADS) stamp[i] = INT_MAX;
+    int base = 0, chunkBegin = 0, chunkEnd = 0, stageA = 0, parity = 0, prevTarget = -1, myMatches = 0;
+    if (tid < 32) sRound[tid] = make_int4(0, -1, -1, 0);
     bool staged = true;
-    while (base < nq) {
-        if (base == chunkEnd) {
-            // stage the next chunk: as many queries (<= 256) as have their candidates fit the buffer
-            __syncthreads();   // the previous chunk has been consumed
-            const int first = offsets[base];
-            const int qi = base + tid;
-            int a = 0, b = 0;
-            bool fits = false;
-            if (tid < kChunkQueries && qi < nq) { a = offsets[qi]; b = offsets[qi + 1]; fits = b - first <= kStageCand; }
-            const int cnt = __syncthreads_count(fits);     // offsets are monotone: the fitting queries are a prefix
-            staged = cnt > 0;
-            chunkBegin = base;
-            chunkEnd = base + max(cnt, 1);
-            stageA = first;
-            if (tid < chunkEnd - base) qmeta[tid] = make_int4(a, b, q[qi].active, meta(qi));
-            if (staged) {
-                const int total = offsets[chunkEnd] - first;
-#pragma unroll 4
-                for (int k = tid; k < total; k += RP_THREADS) stage[k] = cand[first + k];
-            }
-            __syncthreads();
-        }
-        const int2* src = staged ? stage - stageA : cand;
-        const int nr = min(RP_WARPS, chunkEnd - base);
 
+    // one round over queries [base, base + nr); `src[k]` is candidate k of the CSR. Returns the number of queries retired.
+    auto round = [&](const int2* src, int nr) {
+        int* S = stamp + parity * nTargets;
+        if (lane == 0 && prevTarget >= 0) stamp[(parity ^ 1) * nTargets + prevTarget] = INT_MAX;
+        prevTarget = -1;
         // A. speculative evaluation, one warp per query
         bool ok = false;
         int gb = kNone, bestX = -1, target = -1, target2 = -1;
@@ -377,33 +361,62 @@ __device__ __forceinline__ void replay_queries(const AreaQuery* __restrict__ q, 
                 target = bestX & kCandIdxMask;
                 if (kUsesSecond && gs != kNone) target2 = secondX & kCandIdxMask;
                 ok = decide(base + warp, mq.w, gb, gs, bestX, secondX);
-                if (ok && lane == 0) atomicMin(&stamp[target], warp);
+                if (ok && lane == 0) { atomicMin(&S[target], warp); prevTarget = target; }
             }
         }
-        if (lane == 0) sOk[warp] = ok;
+        if (lane == 0) sRound[warp] = make_int4(ok, target, target2, 0);
         __syncthreads();
 
         // B. state only ever REMOVES candidates (occupied / matched flags are set, matched distances shrink), so a
-        //    query's outcome can change only if an earlier query of the round takes its best or its second-best target
-        if (lane == 0)
-            sDirty[warp] = (target >= 0 && stamp[target] < warp) || (target2 >= 0 && stamp[target2] < warp);
+        //    query's outcome can change only if an earlier query of the round takes its best or its second-best target.
+        //    Warp 0 works this out for the whole round (lane = query).
+        if (warp == 0) {
+            const int4 r = sRound[lane];
+            const bool in = lane < nr;
+            const int s1 = S[max(r.y, 0)], s2 = S[max(r.z, 0)];
+            const bool dirty = in && ((r.y >= 0 && s1 < lane) || (r.z >= 0 && s2 < lane));
+            const unsigned dirtyMask = __ballot_sync(0xffffffffu, dirty);
+            const int f = dirtyMask ? __ffs(dirtyMask) - 1 : nr;
+            const unsigned okPrefix = __ballot_sync(0xffffffffu, lane < f && r.x);
+            if (lane == 0) { sVerdict[0] = f; sVerdict[1] = (int)okPrefix; }
+        }
         __syncthreads();
 
         // C. commit the clean prefix
-        const unsigned dirtyMask = __ballot_sync(0xffffffffu, lane < nr && sDirty[lane]);
-        const int f = dirtyMask ? __ffs(dirtyMask) - 1 : nr;
-        const unsigned okPrefix = __ballot_sync(0xffffffffu, lane < f && sOk[lane]);
-        if (ok && lane == 0) {
-            if (warp < f) {
-                const int delta = commit(base + warp, mq.w, gb, bestX, nPush + __popc(okPrefix & ((1u << warp) - 1u)));
-                if (delta) atomicAdd(nMatchesShared, delta);
-            }
-            stamp[target] = INT_MAX;
-        }
+        const int f = sVerdict[0];
+        const unsigned okPrefix = (unsigned)sVerdict[1];
+        if (ok && lane == 0 && warp < f) myMatches += commit(base + warp, mq.w, gb, bestX, nPush + __popc(okPrefix & ((1u << warp) - 1u)));
         nPush += __popc(okPrefix);
-        base += f;
+        parity ^= 1;
         __syncthreads();
+        return f;
+    };
+
+    while (base < nq) {
+        if (base == chunkEnd) {
+            // stage the next chunk: as many queries (<= 256) as have their candidates fit the buffer
+            const int first = offsets[base];
+            const int qi = base + tid;
+            int a = 0, b = 0;
+            bool fits = false;
+            if (tid < kChunkQueries && qi < nq) { a = offsets[qi]; b = offsets[qi + 1]; fits = b - first <= kStageCand; }
+            const int cnt = __syncthreads_count(fits);     // offsets are monotone: the fitting queries are a prefix
+            staged = cnt > 0;
+            chunkBegin = base;
+            chunkEnd = base + max(cnt, 1);
+            stageA = first;
+            if (tid < chunkEnd - base) qmeta[tid] = make_int4(a, b, q[qi].active, meta(qi));
+            if (staged) {
+                const int total = offsets[chunkEnd] - first;
+#pragma unroll 4
+                for (int k = tid; k < total; k += RP_THREADS) stage[k] = cand[first + k];
+            }
+            __syncthreads();
+        }
+        const int nr = min(RP_WARPS, chunkEnd - base);
+        base += staged ? round(stage - stageA, nr) : round(cand, nr);
     }
+    if (myMatches) atomicAdd(nMatchesShared, myMatches);
 }
 
 // SearchForInitialization replay (ORBmatcher.cc:417-517). m21 / vMatchedDistance in shared memory.
@@ -414,7 +427,7 @@ init_replay_kernel(FrameDev f1, FrameDev f2, const AreaQuery* __restrict__ q, co
     extern __shared__ int dyn[];
     int* m21 = dyn + kReplayFixedInts;
     int* matchedDist = m21 + f2.n;
-    int* stamp = m21 + 2 * f2.n;
+    int* stamp = m21 + 2 * f2.n;   // 2 * f2.n entries
     __shared__ int hist[kHistoLength];
     __shared__ int nmatches;
     const int tid = threadIdx.x;
@@ -440,14 +453,10 @@ init_replay_kernel(FrameDev f1, FrameDev f2, const AreaQuery* __restrict__ q, co
         });
     __threadfence_block();
     __syncthreads();
-    if (tid < 32) {
-        if (checkOri)
-            histogram_prune(pushA, pushB, pushA, nPush, hist, m12, true, &nmatches,
-                            [&](int i1) { return f1.keys[i1].angle; }, [&](int i2) { return f2.keys[i2].angle; });
-        __syncwarp();
-        if (tid == 0) *nmatchesOut = nmatches;
-    }
-    __syncthreads();
+    if (checkOri)
+        histogram_prune(pushA, pushB, pushA, nPush, hist, m12, true, &nmatches,
+                        [&](int i1) { return f1.keys[i1].angle; }, [&](int i2) { return f2.keys[i2].angle; });
+    if (tid == 0) *nmatchesOut = nmatches;
     for (int i1 = tid; i1 < f1.n; i1 += RP_THREADS)
         if (m12[i1] >= 0) {                                             // :515-517
             prevXY[2 * i1] = f2.keys[m12[i1]].x;
@@ -463,7 +472,7 @@ proj_replay_kernel(FrameDev cur, const AreaQuery* __restrict__ q, const orbm_pro
                    const unsigned char* __restrict__ occIn, int* curMatch, int* pushA, int* pushB, int* nmatchesOut) {
     extern __shared__ int dyn[];
     int* stamp = dyn + kReplayFixedInts;
-    unsigned char* occ = reinterpret_cast<unsigned char*>(stamp + cur.n);
+    unsigned char* occ = reinterpret_cast<unsigned char*>(stamp + 2 * cur.n);
     __shared__ int hist[kHistoLength];
     __shared__ int nmatches;
     const int tid = threadIdx.x;
@@ -483,13 +492,10 @@ proj_replay_kernel(FrameDev cur, const AreaQuery* __restrict__ q, const orbm_pro
         });
     __threadfence_block();
     __syncthreads();
-    if (tid < 32) {
-        if (checkOri)
-            histogram_prune(pushA, pushB, pushB, nPush, hist, curMatch, false, &nmatches,
-                            [&](int i) { return pq[i].angle; }, [&](int i2) { return cur.keys[i2].angle; });
-        __syncwarp();
-        if (tid == 0) *nmatchesOut = nmatches;
-    }
+    if (checkOri)
+        histogram_prune(pushA, pushB, pushB, nPush, hist, curMatch, false, &nmatches,
+                        [&](int i) { return pq[i].angle; }, [&](int i2) { return cur.keys[i2].angle; });
+    if (tid == 0) *nmatchesOut = nmatches;
 }
 
 // SearchByProjection(Frame, MapPoints) replay (ORBmatcher.cc:51-126).
@@ -499,7 +505,7 @@ point_replay_kernel(FrameDev f, const AreaQuery* __restrict__ q, const orbm_poin
                     const unsigned char* __restrict__ occIn, int* match, int* nmatchesOut) {
     extern __shared__ int dyn[];
     int* stamp = dyn + kReplayFixedInts;
-    unsigned char* occ = reinterpret_cast<unsigned char*>(stamp + f.n);
+    unsigned char* occ = reinterpret_cast<unsigned char*>(stamp + 2 * f.n);
     __shared__ int nmatches;
     const int tid = threadIdx.x;
     if (tid == 0) nmatches = 0;
@@ -727,7 +733,7 @@ bow_replay_kernel(FrameDev k1, FrameDev k2, const AreaQuery* __restrict__ q, con
                   int* m12, int* m21, int* pushA, int* pushB, int* nmatchesOut) {
     extern __shared__ int dyn[];
     int* stamp = dyn + kReplayFixedInts;
-    unsigned char* matched2 = reinterpret_cast<unsigned char*>(stamp + k2.n);
+    unsigned char* matched2 = reinterpret_cast<unsigned char*>(stamp + 2 * k2.n);
     __shared__ int hist[kHistoLength];
     __shared__ int nmatches;
     const int tid = threadIdx.x;
@@ -752,19 +758,15 @@ bow_replay_kernel(FrameDev k1, FrameDev k2, const AreaQuery* __restrict__ q, con
         });
     __threadfence_block();
     __syncthreads();
-    if (tid < 32) {
-        const int lane = tid;
-        if (checkOri) {
-            histogram_prune(pushA, pushB, pushA, nPush, hist, m12, false, &nmatches,
-                            [&](int i1) { return k1.keys[i1].angle; }, [&](int i2) { return k2.keys[i2].angle; });
-            __threadfence_block();
-            __syncwarp();
-            for (int k = lane; k < nPush; k += 32)
-                if (m12[pushA[k]] < 0) m21[pushB[k]] = -1;
-        }
-        __syncwarp();
-        if (lane == 0) *nmatchesOut = nmatches;
+    if (checkOri) {
+        histogram_prune(pushA, pushB, pushA, nPush, hist, m12, false, &nmatches,
+                        [&](int i1) { return k1.keys[i1].angle; }, [&](int i2) { return k2.keys[i2].angle; });
+        __threadfence_block();
+        __syncthreads();
+        for (int k = tid; k < nPush; k += RP_THREADS)
+            if (m12[pushA[k]] < 0) m21[pushB[k]] = -1;
     }
+    if (tid == 0) *nmatchesOut = nmatches;
 }
 
 }  // namespace orbb
@@ -795,7 +797,7 @@ struct orbm_frame_s {
 namespace {
 
 constexpr size_t kReplayFixed = (size_t)kReplayFixedInts * 4;   // candidate / query staging of replay_queries
-constexpr size_t kReplaySmemMax = 160 * 1024;   // shared-memory state of the one-warp replays (20k keypoints for init)
+constexpr size_t kReplaySmemMax = 160 * 1024;   // shared-memory state of the replays (10k keypoints for init, 18k for the others)
 
 // phase 1 for nq queries already built in h->ws0 (AreaQuery[nq]); leaves offsets in ws1 and candidates in ws2
 int run_candidates(orbm_matcher* h, const FrameDev& f, const uint4* dQdesc, int nq, const float* dURight, int* totalOut) {
@@ -928,8 +930,8 @@ int orbm_search_for_initialization(orbm_handle h, orbm_frame f1, orbm_frame f2, 
     ORB_CHECK(h->out2.reserve((size_t)(n1 + 1) * 4 * 2));      // pushBin, pushVal
     ORB_CHECK(h->out3.reserve(16));
     int* pushBin = h->out2.as<int>();
-    const size_t replaySmem = (size_t)std::max(n2, 1) * 12 + 16;  // m21 + vMatchedDistance + stamps
-    if (replaySmem > kReplaySmemMax) return fail(ORB_ERR_CAPACITY, "orbm_search_for_initialization: %d keypoints exceed the replay state (%d)", n2, (int)(kReplaySmemMax / 12));
+    const size_t replaySmem = (size_t)std::max(n2, 1) * 16 + 16;  // m21 + vMatchedDistance + two stamp arrays
+    if (replaySmem > kReplaySmemMax) return fail(ORB_ERR_CAPACITY, "orbm_search_for_initialization: %d keypoints exceed the replay state (%d)", n2, (int)(kReplaySmemMax / 16));
     ORB_CUDA(cudaFuncSetAttribute(init_replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kReplayFixed + kReplaySmemMax)));
     init_replay_kernel<<<1, RP_THREADS, kReplayFixed + replaySmem, st>>>(d1, d2, h->ws0.as<AreaQuery>(), h->ws1.as<int>(), h->ws2.as<int2>(), ratio, checkOri,
                                                   h->in0.as<float>(), h->out0.as<int>(), pushBin, pushBin + n1 + 1, h->out3.as<int>());
@@ -981,9 +983,9 @@ int orbm_search_by_projection_ex(orbm_handle h, orbm_frame cur, const float* sf,
     ORB_CHECK(h->out2.reserve((size_t)(nq + 1) * 4 * 2));
     ORB_CHECK(h->out3.reserve(16));
     int* pushBin = h->out2.as<int>();
-    if (5 * (size_t)n + 32 > kReplaySmemMax) return fail(ORB_ERR_CAPACITY, "orbm_search_by_projection: %d keypoints exceed the replay state", n);
+    if (9 * (size_t)n + 32 > kReplaySmemMax) return fail(ORB_ERR_CAPACITY, "orbm_search_by_projection: %d keypoints exceed the replay state", n);
     ORB_CUDA(cudaFuncSetAttribute(proj_replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kReplayFixed + kReplaySmemMax)));
-    proj_replay_kernel<<<1, RP_THREADS, kReplayFixed + 5 * (size_t)n + 32, st>>>(d, h->ws0.as<AreaQuery>(), h->in0.as<orbm_proj_query>(), nq, h->ws1.as<int>(),
+    proj_replay_kernel<<<1, RP_THREADS, kReplayFixed + 9 * (size_t)n + 32, st>>>(d, h->ws0.as<AreaQuery>(), h->in0.as<orbm_proj_query>(), nq, h->ws1.as<int>(),
                                                       h->ws2.as<int2>(), checkOri, maxDist, h->in4.as<unsigned char>(), h->out0.as<int>(),
                                                       pushBin, pushBin + nq + 1, h->out3.as<int>());
     h->launches += 1;
@@ -1023,9 +1025,9 @@ int orbm_search_by_projection_points(orbm_handle h, orbm_frame f, const float* s
     ORB_CHECK(run_candidates(h, d, h->in1.as<uint4>(), nq, uRight ? h->in3.as<float>() : nullptr, &total));
     ORB_CHECK(h->out0.reserve((size_t)(n + 1) * 4));
     ORB_CHECK(h->out3.reserve(16));
-    if (5 * (size_t)n + 32 > kReplaySmemMax) return fail(ORB_ERR_CAPACITY, "orbm_search_by_projection_points: %d keypoints exceed the replay state", n);
+    if (9 * (size_t)n + 32 > kReplaySmemMax) return fail(ORB_ERR_CAPACITY, "orbm_search_by_projection_points: %d keypoints exceed the replay state", n);
     ORB_CUDA(cudaFuncSetAttribute(point_replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kReplayFixed + kReplaySmemMax)));
-    point_replay_kernel<<<1, RP_THREADS, kReplayFixed + 5 * (size_t)n + 32, st>>>(d, h->ws0.as<AreaQuery>(), h->in0.as<orbm_point_query>(), nq, h->ws1.as<int>(),
+    point_replay_kernel<<<1, RP_THREADS, kReplayFixed + 9 * (size_t)n + 32, st>>>(d, h->ws0.as<AreaQuery>(), h->in0.as<orbm_point_query>(), nq, h->ws1.as<int>(),
                                                        h->ws2.as<int2>(), ratio, h->in4.as<unsigned char>(), h->out0.as<int>(),
                                                        h->out3.as<int>());
     h->launches += 1;
@@ -1119,7 +1121,7 @@ int orbm_search_by_bow(orbm_handle h, orbm_frame k1, orbm_frame k2, int nNodes1,
     for (int a = 1; a < nNodes2; ++a)
         if (nodeId2[a] <= nodeId2[a - 1]) return fail(ORB_ERR_INVALID, "orbm_search_by_bow: node ids of frame 2 not ascending");
     if (e1 == 0 || e2 == 0) return ORB_OK;
-    if (5 * (size_t)n2 + 32 > kReplaySmemMax) return fail(ORB_ERR_CAPACITY, "orbm_search_by_bow: %d keypoints exceed the replay state", n2);
+    if (9 * (size_t)n2 + 32 > kReplaySmemMax) return fail(ORB_ERR_CAPACITY, "orbm_search_by_bow: %d keypoints exceed the replay state", n2);
     cudaStream_t st = h->stream;
     std::vector<int> ints;
     auto putInts = [&](const int* p, int n) { size_t o = ints.size(); ints.insert(ints.end(), p, p + n); return o; };
@@ -1156,7 +1158,7 @@ int orbm_search_by_bow(orbm_handle h, orbm_frame k1, orbm_frame k2, int nNodes1,
     ORB_CHECK(h->out3.reserve(16));
     int* pushA = h->out2.as<int>();
     ORB_CUDA(cudaFuncSetAttribute(bow_replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kReplayFixed + kReplaySmemMax)));
-    bow_replay_kernel<<<1, RP_THREADS, kReplayFixed + 5 * (size_t)n2 + 32, st>>>(P.k1, P.k2, h->ws0.as<AreaQuery>(), P.idx1, e1, offsets, h->ws2.as<int2>(), ratio,
+    bow_replay_kernel<<<1, RP_THREADS, kReplayFixed + 9 * (size_t)n2 + 32, st>>>(P.k1, P.k2, h->ws0.as<AreaQuery>(), P.idx1, e1, offsets, h->ws2.as<int2>(), ratio,
                                                       checkOri, strictLow, h->out0.as<int>(), h->out1.as<int>(), pushA,
                                                       pushA + e1 + 1, h->out3.as<int>());
     h->launches += 5;
