@@ -145,3 +145,37 @@ def test_device_resident_batch(oracle):
         _assert_same_keypoints(k, rk)
         assert np.array_equal(d_desc[i, :n[i]].cpu().numpy(), rd)
     ex.close()
+
+
+def test_full_size_batch_is_periodic(oracle):
+    """BASELINE.json config 3 at full size: 4096 EuRoC frames in one device-resident call. The arena then spans more
+    than 4 GB per buffer, so every frame offset must be 64-bit. Property: the batch repeats 8 distinct frames, hence
+    the outputs must repeat with period 8, and the first period must equal the oracle."""
+    torch = pytest.importorskip("torch")
+    if torch.cuda.mem_get_info()[0] < 60e9:
+        pytest.skip("needs ~35 GB of device memory")
+    base = np.stack([synth_frame(400 + i, 752, 480) for i in range(8)])
+    nF = 4096
+    ex = orbb200.Extractor(1000, max_width=752, max_height=480, max_batch=nF)
+    d_img = torch.from_numpy(base).cuda().repeat(nF // 8, 1, 1).contiguous()
+    cap = ex.capacity
+    d_kps = torch.zeros((nF, cap, 7), dtype=torch.int32, device="cuda")
+    d_desc = torch.zeros((nF, cap, 32), dtype=torch.uint8, device="cuda")
+    d_n = torch.zeros(nF, dtype=torch.int32, device="cuda")
+    ex.extract_batch_device(d_img, d_kps, d_desc, d_n)
+    ex.synchronize()
+    n = d_n.view(nF // 8, 8)
+    assert bool((n == n[0:1]).all())
+    k = d_kps.view(nF // 8, 8, cap, 7)
+    d = d_desc.view(nF // 8, 8, cap, 32)
+    valid = (torch.arange(cap, device="cuda")[None, :] < n[0][:, None])           # (8, cap)
+    assert bool(((k == k[0:1]) | ~valid[None, :, :, None]).all())
+    assert bool(((d == d[0:1]) | ~valid[None, :, :, None]).all())
+    oe = oracle.extractor(1000)
+    n0 = n[0].cpu().numpy()
+    for i in (0, 7):
+        rk, rd = oe.extract(base[i])
+        got = d_kps[nF - 8 + i, :n0[i]].cpu().numpy().copy().view(orbb200.KP_DTYPE).reshape(-1)   # from the LAST period
+        _assert_same_keypoints(got, rk)
+        assert np.array_equal(d_desc[nF - 8 + i, :n0[i]].cpu().numpy(), rd)
+    ex.close()
