@@ -152,7 +152,7 @@ __device__ __forceinline__ void nms_queue(const FastShared& S, int first, int st
     }
 }
 
-__global__ void __launch_bounds__(FAST_THREADS, 10) fast_cells_kernel(const __grid_constant__ ExtractParams P) {
+__global__ void __launch_bounds__(FAST_THREADS, 12) fast_cells_kernel(const __grid_constant__ ExtractParams P) {
     extern __shared__ __align__(16) unsigned char fsm[];
     __shared__ unsigned int sQueueLens;   // front length | back length << 16
     __shared__ int sSurvLen;
@@ -229,10 +229,9 @@ __global__ void __launch_bounds__(FAST_THREADS, 10) fast_cells_kernel(const __gr
             const bool valid = (y0 < rowsTest) && (y0 + k < ch);
             const uint2* rowC = valid ? row : reinterpret_cast<const uint2*>(S.tile) + 3 * (TPX / 4);
             // rowC[0] = pixels x0-4..x0-1, rowC[1] = x0..x0+3, rowC[2] = x0+4..
-            // A = pixels (x0, x0+1), B = (x0+2, x0+3). M = pair maxima, m = pair minima of the opposing circle points
-            unsigned int MA[8], MB[8], mA[8], mB[8], cA, cB;
-#define PAIR(j, aA, bA, aB, bB)                                                            \
-    MA[j] = __vmaxu2(aA, bA); mA[j] = __vminu2(aA, bA); MB[j] = __vmaxu2(aB, bB); mB[j] = __vminu2(aB, bB);
+            // A = pixels (x0, x0+1), B = (x0+2, x0+3). mm = running minimum of the pair maxima, nn = running maximum of
+            // the pair minima of opposing circle points (folded in as they are formed: few live registers)
+            unsigned int mmA, mmB, nnA, nnB, cA, cB;
             {   // rows +-1 and 0: dx = +-3 -> circle points 3/11, 5/13, 4/12
                 const uint2* up = rowC - (TPX / 4);
                 const uint2* dn = rowC + (TPX / 4);
@@ -246,12 +245,12 @@ __global__ void __launch_bounds__(FAST_THREADS, 10) fast_cells_kernel(const __gr
                 const unsigned int dMA = __funnelshift_r(dl.x, dl.y, 16), dMB = __funnelshift_r(dl.y, dc.x, 16);
                 const unsigned int mPA = __funnelshift_r(mc.y, mr.x, 16), mPB = __funnelshift_r(mr.x, mr.y, 16);
                 const unsigned int mMA = __funnelshift_r(ml.x, ml.y, 16), mMB = __funnelshift_r(ml.y, mc.x, 16);
-                PAIR(0, dPA, uMA, dPB, uMB)                                        // k=3 (3,1) with k=11 (-3,-1)
-                PAIR(1, uPA, dMA, uPB, dMB)                                        // k=5 (3,-1) with k=13 (-3,1)
-                PAIR(2, mPA, mMA, mPB, mMB)                                        // k=4 (3,0) with k=12 (-3,0)
+                // k=3 (3,1) with k=11 (-3,-1); k=5 (3,-1) with k=13 (-3,1); k=4 (3,0) with k=12 (-3,0)
+                mmA = __vimin3_u16x2(__vmaxu2(dPA, uMA), __vmaxu2(uPA, dMA), __vmaxu2(mPA, mMA));
+                nnA = __vimax3_u16x2(__vminu2(dPA, uMA), __vminu2(uPA, dMA), __vminu2(mPA, mMA));
+                mmB = __vimin3_u16x2(__vmaxu2(dPB, uMB), __vmaxu2(uPB, dMB), __vmaxu2(mPB, mMB));
+                nnB = __vimax3_u16x2(__vminu2(dPB, uMB), __vminu2(uPB, dMB), __vminu2(mPB, mMB));
             }
-            unsigned int mmA = __vimin3_u16x2(MA[0], MA[1], MA[2]), mmB = __vimin3_u16x2(MB[0], MB[1], MB[2]);
-            unsigned int nnA = __vimax3_u16x2(mA[0], mA[1], mA[2]), nnB = __vimax3_u16x2(mB[0], mB[1], mB[2]);
             if (!__any_sync(0xffffffffu, valid && (pass_word(mmA, nnA, cA, Kmin) | pass_word(mmB, nnB, cB, Kmin)))) continue;
             {   // rows +-3: dx = 0, +1, -1  -> circle points 0/8, 1/9, 15/7
                 const uint2* up = rowC - 3 * (TPX / 4);
@@ -262,23 +261,30 @@ __global__ void __launch_bounds__(FAST_THREADS, 10) fast_cells_kernel(const __gr
                                    uf34 = __funnelshift_r(uc.y, u4, 16);
                 const unsigned int df12 = __funnelshift_r(d1, dc.x, 16), df23 = __funnelshift_r(dc.x, dc.y, 16),
                                    df34 = __funnelshift_r(dc.y, d4, 16);
-                PAIR(3, dc.x, uc.x, dc.y, uc.y)                                    // k=0 (0,3) with k=8 (0,-3)
-                PAIR(4, df23, uf12, df34, uf23)                                    // k=1 (1,3) with k=9 (-1,-3)
-                PAIR(5, uf23, df12, uf34, df23)                                    // k=7 (1,-3) with k=15 (-1,3)
+                // k=0 (0,3) with k=8 (0,-3); k=1 (1,3) with k=9 (-1,-3)
+                mmA = __vimin3_u16x2(mmA, __vmaxu2(dc.x, uc.x), __vmaxu2(df23, uf12));
+                nnA = __vimax3_u16x2(nnA, __vminu2(dc.x, uc.x), __vminu2(df23, uf12));
+                mmB = __vimin3_u16x2(mmB, __vmaxu2(dc.y, uc.y), __vmaxu2(df34, uf23));
+                nnB = __vimax3_u16x2(nnB, __vminu2(dc.y, uc.y), __vminu2(df34, uf23));
+                // k=7 (1,-3) with k=15 (-1,3) is folded in below with k=2/10
+                const unsigned int pA7 = __vmaxu2(uf23, df12), qA7 = __vminu2(uf23, df12);
+                const unsigned int pB7 = __vmaxu2(uf34, df23), qB7 = __vminu2(uf34, df23);
+                // rows +-2: dx = +-2 -> circle points 2/10, 6/14; no shifts
+                const uint2* up2 = rowC - 2 * (TPX / 4);
+                const uint2* dn2 = rowC + 2 * (TPX / 4);
+                const unsigned int v1 = up2[0].y, v4 = up2[2].x, e1 = dn2[0].y, e4 = dn2[2].x;
+                const uint2 vc = up2[1], ec = dn2[1];
+                // k=2 (2,2) with k=10 (-2,-2)
+                mmA = __vimin3_u16x2(mmA, pA7, __vmaxu2(ec.y, v1));
+                nnA = __vimax3_u16x2(nnA, qA7, __vminu2(ec.y, v1));
+                mmB = __vimin3_u16x2(mmB, pB7, __vmaxu2(e4, vc.x));
+                nnB = __vimax3_u16x2(nnB, qB7, __vminu2(e4, vc.x));
+                // k=6 (2,-2) with k=14 (-2,2)
+                mmA = __vminu2(mmA, __vmaxu2(vc.y, e1));
+                nnA = __vmaxu2(nnA, __vminu2(vc.y, e1));
+                mmB = __vminu2(mmB, __vmaxu2(v4, ec.x));
+                nnB = __vmaxu2(nnB, __vminu2(v4, ec.x));
             }
-            {   // rows +-2: dx = +-2 -> circle points 2/10, 6/14; no shifts
-                const uint2* up = rowC - 2 * (TPX / 4);
-                const uint2* dn = rowC + 2 * (TPX / 4);
-                const unsigned int u1 = up[0].y, u4 = up[2].x, d1 = dn[0].y, d4 = dn[2].x;
-                const uint2 uc = up[1], dc = dn[1];
-                PAIR(6, dc.y, u1, d4, uc.x)                                        // k=2 (2,2) with k=10 (-2,-2)
-                PAIR(7, uc.y, d1, u4, dc.x)                                        // k=6 (2,-2) with k=14 (-2,2)
-            }
-#undef PAIR
-            mmA = __vimin3_u16x2(mmA, __vimin3_u16x2(MA[3], MA[4], MA[5]), __vminu2(MA[6], MA[7]));
-            mmB = __vimin3_u16x2(mmB, __vimin3_u16x2(MB[3], MB[4], MB[5]), __vminu2(MB[6], MB[7]));
-            nnA = __vimax3_u16x2(nnA, __vimax3_u16x2(mA[3], mA[4], mA[5]), __vmaxu2(mA[6], mA[7]));
-            nnB = __vimax3_u16x2(nnB, __vimax3_u16x2(mB[3], mB[4], mB[5]), __vmaxu2(mB[6], mB[7]));
             const unsigned int passA = valid ? pass_word(mmA, nnA, cA, Kmin) & colA : 0u,
                                passB = valid ? pass_word(mmB, nnB, cB, Kmin) & colB : 0u;
             const unsigned int frontA = pass_word(mmA, nnA, cA, Kini) & passA, frontB = pass_word(mmB, nnB, cB, Kini) & passB;
