@@ -20,10 +20,10 @@ sf = np.array([1.2 ** i for i in range(8)], np.float32)
 prev = np.stack([ka["x"], ka["y"]], 1).astype(np.float32)
 n_init = m.search_for_initialization(f1, f2, prev, 100, 0.9, True)[0]
 q = np.zeros(len(ka), orbb200.PROJ_QUERY_DTYPE)
-q["u"], q["v"], q["invz"], q["octave"], q["valid"], q["obs_positive"], q["angle"] = ka["x"] - 7, ka["y"] - 3, 0.1, ka["octave"], 1, 1, ka["angle"]
+q["u"], q["v"], q["invz"], q["octave"], q["valid"], q["obs_positive"], q["angle"] = ka["x"] + 7, ka["y"] + 3, 0.1, ka["octave"], 1, 1, ka["angle"]
 n_proj = m.search_by_projection(f2, sf, q, da, 15.0)[0]
 pq = np.zeros(len(ka), orbb200.POINT_QUERY_DTYPE)
-pq["proj_x"], pq["proj_y"], pq["view_cos"], pq["level"], pq["in_view"], pq["obs_positive"] = ka["x"] - 7, ka["y"] - 3, 1.0, ka["octave"], 1, 1
+pq["proj_x"], pq["proj_y"], pq["view_cos"], pq["level"], pq["in_view"], pq["obs_positive"] = ka["x"] + 7, ka["y"] + 3, 1.0, ka["octave"], 1, 1
 n_pts = m.search_by_projection_points(f2, sf, pq, da, 3.0, 0.8)[0]
 node = lambda k, dx, dy: ((k["y"] + dy) // 48).astype(np.int64) * 100 + ((k["x"] + dx) // 48).astype(np.int64)
 def fv(k, dx, dy):
@@ -33,6 +33,11 @@ def fv(k, dx, dy):
     return ids.astype(np.int32), np.array(start, np.int32), np.array(idx, np.int32)
 F12 = np.array([[0, 0, -3.0], [0, 0, 7.0], [3.0, -7.0, 0]], np.float32) * 1e-2
 n_tri = m.search_for_triangulation(f1, f2, fv(ka, 0, 0), fv(kb, 7, 3), F12, 3000.0, 200.0, sf, sf * sf, check_ori=True)[0]
+n_bow = m.search_by_bow(f1, f2, fv(ka, 0, 0), fv(kb, -7, -3), ratio=0.75, check_ori=True, strict_low=True)[0]
+n_proj_kf = m.search_by_projection(f2, sf, q, da, 10.0, mode=3, check_ori=False, max_distance=50)[0] if "max_distance" in m.search_by_projection.__code__.co_varnames else -1
+bq = np.zeros(len(ka), orbb200.BEST_QUERY_DTYPE)
+bq["u"], bq["v"], bq["radius"], bq["ur"], bq["level"], bq["valid"] = ka["x"] + 7, ka["y"] + 3, 12.0, -1.0, ka["octave"], 1
+best_idx, best_dist = m.search_projected_best(f2, bq, da, chi2=True, inv_sigma2=1.0 / (sf * sf))
 rng = np.random.default_rng(0)
 qd, qa, td, ta = planted_descriptors(rng, 300, 270)
 n_bf = int(m.bruteforce(qd, qa, td, ta, 0.9, True)["nmatches"])
@@ -45,4 +50,4 @@ cnt = torch.zeros((3, 3), dtype=torch.int32, device="cuda")
 torch.cuda.synchronize()
 m.allpairs_device(tab, ang, 0, 3, 0, 3, 0.75, True, cnt)
 m.synchronize()
-print("ok", len(ka), len(kn), n_init, n_proj, n_pts, n_tri, n_bf, int(d.sum()), cnt.cpu().numpy().tolist())
+print("ok", len(ka), len(kn), n_init, n_proj, n_pts, n_tri, n_bow, n_proj_kf, int((best_idx >= 0).sum()), n_bf, int(d.sum()), cnt.cpu().numpy().tolist())
