@@ -1,6 +1,5 @@
-// Quadtree keypoint selection + orientation (north-star kernels 3 and 4):
+// Quadtree keypoint selection (north-star kernel 3):
 //   ORBextractor::DistributeOctTree  ORBextractor.cc:541-765   (ExtractorNode::DivideNode :483-539)
-//   IC_Angle / computeOrientation    ORBextractor.cc:79-106, 474-481
 //
 // One CTA per (frame, level).  The reference manipulates a std::list sequentially; the same result is obtained in
 // level-synchronous rounds because of three facts (checked against a literal list simulation, tests/test_octree*):
@@ -14,11 +13,8 @@
 //      ADDRESS ORDER IS DEFINED AS CREATION ORDER (the reference leaves it to the allocator, :686); a later-created
 //      node sits nearer the list front, so ties on size resolve toward the smaller list index.
 // Candidate keys come from the per-cell FAST slots in (cell row, cell col, y, x) order and live in shared memory
-// (global spill space if a level has more candidates than fit).  The selected keys get their orientation from the
-// unblurred level in the same kernel: one warp per keypoint, integer moments by dot products of aligned pixel words
-// with tabulated coordinate bytes, float32 fastAtan2 with the reference's operation order (no FMA).
-#include <cfloat>
-
+// (global spill space if a level has more candidates than fit).  The selected keys get their orientation in the
+// descriptor kernel (brief.cu), which has a warp per keypoint anyway.
 #include "extractor.h"
 
 namespace orbb {
@@ -98,62 +94,6 @@ __device__ int block_scan_exclusive(int* a, int n, int* tmp) {
     }
     __syncthreads();
     return total;
-}
-
-// IC_Angle (ORBextractor.cc:79-106) as dot products.  The 31 rows of the circular patch are read as aligned 32-bit words
-// (9 per row); for each of the four alignments of the patch's left edge and each (row, word) item the table holds the
-// signed u and v coordinates of the word's four bytes (0 outside the circle), the row and the word's byte offset, so
-//   m10 += dp4a(u bytes, pixels),  m01 += dp4a(v bytes, pixels).
-// 279 items are dealt to the 32 lanes of a warp, 9 each (the last 9 table slots are zero).
-constexpr int kOriItems = 9 * 32;
-__device__ int4 gOriTable[4 * kOriItems];
-
-int upload_orientation_table(const int* umax) {
-    static int4 host[4 * kOriItems];
-    for (int a = 0; a < 4; ++a)
-        for (int t = 0; t < kOriItems; ++t) {
-            int4 e = make_int4(0, 0, 0, 0);
-            if (t < 9 * kPatch) {
-                const int v = t / 9 - kHalfPatch, j = t % 9;
-                unsigned int uc = 0, vc = 0;
-                for (int b = 0; b < 4; ++b) {
-                    const int u = 4 * j + b - a - kHalfPatch;
-                    if (u < -kHalfPatch || u > kHalfPatch || (u < 0 ? -u : u) > umax[v < 0 ? -v : v]) continue;
-                    uc |= (unsigned int)(u & 0xff) << (8 * b);
-                    vc |= (unsigned int)(v & 0xff) << (8 * b);
-                }
-                e = make_int4((int)uc, (int)vc, v, 4 * j);
-            }
-            host[a * kOriItems + t] = e;
-        }
-    ORB_CUDA(cudaMemcpyToSymbol(gOriTable, host, sizeof host));
-    return ORB_OK;
-}
-
-__device__ __forceinline__ int dp4a_su(int coef, unsigned int pixels, int acc) {   // signed bytes x unsigned bytes
-    int d;
-    asm("dp4a.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(coef), "r"(pixels), "r"(acc));
-    return d;
-}
-
-// cv::fastAtan2 (degrees), float32 with the reference operation order, every op rounded (no contraction)
-__device__ __forceinline__ float fast_atan2_deg(float y, float x) {
-    const float P1 = 57.283626556396484f, P3 = -18.66744613647461f, P5 = 8.914000511169434f, P7 = -2.539724588394165f;
-    const float eps = (float)DBL_EPSILON;
-    const float ax = fabsf(x), ay = fabsf(y);
-    float a, c, c2;
-    if (ax >= ay) {
-        c = __fdiv_rn(ay, __fadd_rn(ax, eps));
-        c2 = __fmul_rn(c, c);
-        a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(P7, c2), P5), c2), P3), c2), P1), c);
-    } else {
-        c = __fdiv_rn(ax, __fadd_rn(ay, eps));
-        c2 = __fmul_rn(c, c);
-        a = __fsub_rn(90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(P7, c2), P5), c2), P3), c2), P1), c));
-    }
-    if (x < 0) a = __fsub_rn(180.f, a);
-    if (y < 0) a = __fsub_rn(360.f, a);
-    return a;
 }
 
 __global__ void __launch_bounds__(OT_THREADS, 4)
@@ -354,39 +294,16 @@ octree_kernel(const __grid_constant__ ExtractParams P, int nodeCap, int cellCap,
         if (key_s(kv[k]) == t0[kn[k]]) atomicMin(&t1[kn[k]], k);
     __syncthreads();
 
-    // ---- 5. emit in list order with orientation (IC_Angle on the unblurred level)
+    // ---- 5. emit in list order; the orientation is computed where the descriptor is (brief.cu)
     const int nOut = min(S, L.selCap);
-    const unsigned char* level0 = P.pyr + (size_t)frame * P.pyrFrameBytes + L.pyrOff + (size_t)kEdge * L.pitch + kPadLeft;
     SelKey* out = P.sel + (size_t)frame * P.selPerFrame + L.selBase;
-    for (int s = warp; s < nOut; s += OT_WARPS) {
+    for (int s = tid; s < nOut; s += OT_THREADS) {
         const unsigned int key = kv[t1[s]];
-        const int x = key_x(key) + 16, y = key_y(key) + 16;   // + minBorderX/Y (:843-844)
-        const int al = (x - kHalfPatch) & 3;          // the level's pixel (0, y) is 4-byte aligned
-        const unsigned char* c0 = level0 + (size_t)y * L.pitch + (x - kHalfPatch - al);
-        const int4* tab = gOriTable + al * kOriItems + lane;
-        int4 e[9];
-        unsigned int w[9];
-#pragma unroll
-        for (int i = 0; i < 9; ++i) e[i] = __ldg(tab + 32 * i);
-#pragma unroll
-        for (int i = 0; i < 9; ++i) w[i] = __ldg(reinterpret_cast<const unsigned int*>(c0 + e[i].z * L.pitch + e[i].w));
-        int m10 = 0, m01 = 0;
-#pragma unroll
-        for (int i = 0; i < 9; ++i) {
-            m10 = dp4a_su(e[i].x, w[i], m10);
-            m01 = dp4a_su(e[i].y, w[i], m01);
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            m10 += __shfl_xor_sync(0xffffffffu, m10, o);
-            m01 += __shfl_xor_sync(0xffffffffu, m01, o);
-        }
-        if (lane == 0) {
-            SelKey k;
-            k.x = (float)x; k.y = (float)y; k.response = (float)key_s(key);
-            k.angle = fast_atan2_deg((float)m01, (float)m10);
-            out[s] = k;
-        }
+        SelKey k;
+        k.x = (float)(key_x(key) + 16); k.y = (float)(key_y(key) + 16);   // + minBorderX/Y (:843-844)
+        k.response = (float)key_s(key);
+        k.angle = 0.f;
+        out[s] = k;
     }
     if (tid == 0) *selCountOut = nOut;
 }
