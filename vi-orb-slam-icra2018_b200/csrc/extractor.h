@@ -53,10 +53,9 @@ struct alignas(16) Cell {    // one FAST cell with a non-empty interior; 32 byte
     unsigned char quads;     // 4-pixel groups per staged tile row, ceil((cw+8)/4)
     unsigned char rowsStage; // tile rows staged per pass of the CTA = threads / quads
     unsigned char groups;    // 4-pixel groups per interior row, ceil(cw/4)
-    unsigned char rowsTest;  // interior rows tested per pass = threads / groups
-    unsigned char pad;
-    unsigned short rq, rg;   // ceil(32768/quads), ceil(32768/groups): t / n == (t * r) >> 15 for t < threads
-    unsigned short pad2;
+    unsigned char pad, pad1;
+    unsigned short rq;       // ceil(2^15 / quads):  t / quads == (t * rq) >> 15 for t < threads
+    unsigned int rch;        // ceil(2^20 / ch):     i / ch == (i * rch) >> 20 for i < groups * ch
 };
 static_assert(sizeof(Cell) == 32, "Cell is read as two uint4");
 

@@ -32,7 +32,9 @@
 namespace orbb {
 
 constexpr int FAST_THREADS = 128;
-constexpr int TPX = 72;                           // tile pitch in pixels (16-bit each); interior x=0 sits at column 4
+constexpr int TPX = 76;                           // tile pitch in pixels (16-bit each); interior x=0 sits at column 4.
+                                                  // 19 eight-byte words per row: ODD, so the 16 lanes of a half warp that
+                                                  // walk down a column of 4-pixel groups hit 16 different bank pairs
 constexpr int SC_PITCH = 64;                      // score map pitch (bytes), interior + 1-px zero ring (<= 62)
 
 // circle offsets in tile pixels, OpenCV order (dx,dy) = (0,3)(1,3)(2,2)(3,1)(3,0)(3,-1)(2,-2)(1,-3)(0,-3)(-1,-3)(-2,-2)
@@ -72,11 +74,10 @@ void fast_cell_setup(Cell& c, long long levelPyrOff, int pitch) {
     c.quads = (unsigned char)((c.cw + 8 + 3) >> 2);
     c.groups = (unsigned char)((c.cw + 3) >> 2);
     c.rowsStage = (unsigned char)(FAST_THREADS / c.quads);
-    c.rowsTest = (unsigned char)(FAST_THREADS / c.groups);
     c.rq = (unsigned short)((32768 + c.quads - 1) / c.quads);
-    c.rg = (unsigned short)((32768 + c.groups - 1) / c.groups);
+    c.rch = ((1u << 20) + c.ch - 1) / c.ch;
     c.pad = 0;
-    c.pad2 = 0;
+    c.pad1 = 0;
 }
 
 // Exact threshold-free score. Both polarities ride in one register: low half p_k - v, high half v - p_k.
@@ -179,8 +180,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 12) fast_cells_kernel(const __gr
     const int cellSlot = (int)cw0.w, tileOff = (int)cw1.x;
     const int shift8 = (int)(cw1.y & 0xffu), quads = (int)((cw1.y >> 8) & 0xffu), rowsStage = (int)((cw1.y >> 16) & 0xffu),
               groups = (int)(cw1.y >> 24);
-    const int rowsTest = (int)(cw1.z & 0xffu);
-    const unsigned int rq = cw1.z >> 16, rg = cw1.w & 0xffffu;
+    const unsigned int rq = cw1.z >> 16, rch = cw1.w;
 
     // ---- 0. stage level pixels [x0-4, x0+cw+4) x [y0-3, y0+ch+3) as 16-bit values; aligned 32-bit global loads,
     //         funnel shift to the tile's alignment, widen, one 64-bit shared store per 4 pixels
@@ -215,19 +215,20 @@ __global__ void __launch_bounds__(FAST_THREADS, 12) fast_cells_kernel(const __gr
     {
         const unsigned int Kmin = PASS_MASK - (unsigned int)(P.minTh + 1) * 0x00010001u,
                            Kini = PASS_MASK - (unsigned int)(P.iniTh + 1) * 0x00010001u;
-        const int y0 = (int)(((unsigned int)tid * rg) >> 15), g = tid - y0 * groups;
-        const int yLane0 = __shfl_sync(0xffffffffu, y0, 0);   // rows advance in lockstep: the warp's first lane leaves last
-        const uint2* row = reinterpret_cast<const uint2*>(S.tile) + (y0 + 3) * (TPX / 4) + g;
-        const int x0 = 4 * g;
-        // pixels x0, x0+1 answer in bits 9 / 25 of the A word, x0+2, x0+3 in those of the B word
-        const unsigned int colA = (x0 < cw ? 0x200u : 0u) | (x0 + 1 < cw ? 0x02000000u : 0u),
-                           colB = (x0 + 2 < cw ? 0x200u : 0u) | (x0 + 3 < cw ? 0x02000000u : 0u);
-        const unsigned int base = (unsigned int)x0 | ((unsigned int)y0 << 6);
+        // work item i = g * ch + y: the lanes of a warp walk DOWN a column of 4-pixel groups (conflict-free shared loads,
+        // see TPX); i / ch by multiply-shift (exact for i < 2^20 / ch)
+        const int total = groups * ch;
         const int qLast = P.fast.qCap - 1;
 #pragma unroll 1
-        for (int k = 0; yLane0 + k < ch; k += rowsTest, row += rowsTest * (TPX / 4)) {
-            const bool valid = (y0 < rowsTest) && (y0 + k < ch);
-            const uint2* rowC = valid ? row : reinterpret_cast<const uint2*>(S.tile) + 3 * (TPX / 4);
+        for (int i0 = tid - lane; i0 < total; i0 += FAST_THREADS) {
+            const int i = min(i0 + lane, total - 1);
+            const bool valid = i0 + lane < total;
+            const int g = (int)(((unsigned int)i * rch) >> 20), y = i - g * ch;   // i * rch < 900 * 2^20
+            const int x0 = 4 * g;
+            // pixels x0, x0+1 answer in bits 9 / 25 of the A word, x0+2, x0+3 in those of the B word
+            const unsigned int colA = (x0 < cw ? 0x200u : 0u) | (x0 + 1 < cw ? 0x02000000u : 0u),
+                               colB = (x0 + 2 < cw ? 0x200u : 0u) | (x0 + 3 < cw ? 0x02000000u : 0u);
+            const uint2* rowC = reinterpret_cast<const uint2*>(S.tile) + (y + 3) * (TPX / 4) + g;
             // rowC[0] = pixels x0-4..x0-1, rowC[1] = x0..x0+3, rowC[2] = x0+4..
             // A = pixels (x0, x0+1), B = (x0+2, x0+3). mm = running minimum of the pair maxima, nn = running maximum of
             // the pair minima of opposing circle points (folded in as they are formed: few live registers)
@@ -300,7 +301,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 12) fast_cells_kernel(const __gr
             unsigned int start = 0;
             if (lane == 31 && incl) start = atomicAdd(&sQueueLens, incl);
             start = __shfl_sync(0xffffffffu, start, 31) + incl - mine;
-            const unsigned int e = base + ((unsigned int)k << 6);
+            const unsigned int e = (unsigned int)x0 | ((unsigned int)y << 6);
             int pf = (int)(start & 0xffffu), pb = qLast - (int)(start >> 16);
             if (frontA & 0x200u) S.queue[pf++] = (unsigned short)e;
             if (frontA & 0x02000000u) S.queue[pf++] = (unsigned short)(e + 1);
