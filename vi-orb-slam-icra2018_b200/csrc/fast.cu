@@ -35,7 +35,8 @@ constexpr int FAST_THREADS = 128;
 constexpr int TPX = 76;                           // tile pitch in pixels (16-bit each); interior x=0 sits at column 4.
                                                   // 19 eight-byte words per row: ODD, so the 16 lanes of a half warp that
                                                   // walk down a column of 4-pixel groups hit 16 different bank pairs
-constexpr int SC_PITCH = 64;                      // score map pitch (bytes), interior + 1-px zero ring (<= 62)
+constexpr int SC_PITCH = 68;                      // score map pitch (bytes), interior + 1-px zero ring (<= 62); 17 words:
+                                                  // odd, so vertically adjacent corners fall into different banks
 
 // circle offsets in tile pixels, OpenCV order (dx,dy) = (0,3)(1,3)(2,2)(3,1)(3,0)(3,-1)(2,-2)(1,-3)(0,-3)(-1,-3)(-2,-2)
 // (-3,-1)(-3,0)(-3,1)(-2,2)(-1,3)
