@@ -55,7 +55,7 @@ struct alignas(16) Cell {    // one FAST cell with a non-empty interior; 32 byte
     unsigned char groups;    // 4-pixel groups per interior row, ceil(cw/4)
     unsigned char pad, pad1;
     unsigned short rq;       // ceil(2^15 / quads):  t / quads == (t * rq) >> 15 for t < threads
-    unsigned int rch;        // ceil(2^20 / ch):     i / ch == (i * rch) >> 20 for i < groups * ch
+    unsigned int rci;        // ceil(2^20 / n), n = 2 * ceil(ch / 2) items per pair of group columns: i / n == (i * rci) >> 20
 };
 static_assert(sizeof(Cell) == 32, "Cell is read as two uint4");
 

@@ -32,9 +32,9 @@
 namespace orbb {
 
 constexpr int FAST_THREADS = 128;
-constexpr int TPX = 76;                           // tile pitch in pixels (16-bit each); interior x=0 sits at column 4.
-                                                  // 19 eight-byte words per row: ODD, so the 16 lanes of a half warp that
-                                                  // walk down a column of 4-pixel groups hit 16 different bank pairs
+constexpr int TPX = 68;                           // tile pitch in pixels (16-bit each); interior x=0 sits at column 4.
+                                                  // 17 eight-byte words per row: with items two rows apart, 2 * 17 = 2 (mod
+                                                  // 16), so 8 row pairs x 2 adjacent groups cover all 16 bank pairs
 constexpr int SC_PITCH = 68;                      // score map pitch (bytes), interior + 1-px zero ring (<= 62); 17 words:
                                                   // odd, so vertically adjacent corners fall into different banks
 
@@ -76,7 +76,7 @@ void fast_cell_setup(Cell& c, long long levelPyrOff, int pitch) {
     c.groups = (unsigned char)((c.cw + 3) >> 2);
     c.rowsStage = (unsigned char)(FAST_THREADS / c.quads);
     c.rq = (unsigned short)((32768 + c.quads - 1) / c.quads);
-    c.rch = ((1u << 20) + c.ch - 1) / c.ch;
+    { const unsigned int colItems = 2u * ((c.ch + 1) >> 1); c.rci = ((1u << 20) + colItems - 1) / colItems; }
     c.pad = 0;
     c.pad1 = 0;
 }
@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 12) fast_cells_kernel(const __gr
     const int cellSlot = (int)cw0.w, tileOff = (int)cw1.x;
     const int shift8 = (int)(cw1.y & 0xffu), quads = (int)((cw1.y >> 8) & 0xffu), rowsStage = (int)((cw1.y >> 16) & 0xffu),
               groups = (int)(cw1.y >> 24);
-    const unsigned int rq = cw1.z >> 16, rch = cw1.w;
+    const unsigned int rq = cw1.z >> 16, rci = cw1.w;
 
     // ---- 0. stage level pixels [x0-4, x0+cw+4) x [y0-3, y0+ch+3) as 16-bit values; aligned 32-bit global loads,
     //         funnel shift to the tile's alignment, widen, one 64-bit shared store per 4 pixels
@@ -211,88 +211,126 @@ __global__ void __launch_bounds__(FAST_THREADS, 12) fast_cells_kernel(const __gr
     __syncthreads();
 
     const int qLastAll = P.fast.qCap - 1;
-    // ---- A. necessary test, 4 pixels (two 16x2 pairs) per thread; warp-uniform loop so that a warp whose 128 pixels
-    //         all fail after the three middle-row pairs skips the other five
+    // ---- A. necessary test on every pixel. A work item is a 4-pixel group on TWO vertically adjacent rows (y, y+1): the
+    //         two rows share six of the eight tile rows they read, which is what matters here -- the kernel is bound by
+    //         shared-memory wavefronts. Items are laid out so that 16 consecutive lanes (8 row pairs x 2 adjacent groups)
+    //         hit 16 different 8-byte bank pairs (see TPX). A warp whose items all fail after the middle rows skips the rest.
     {
         const unsigned int Kmin = PASS_MASK - (unsigned int)(P.minTh + 1) * 0x00010001u,
                            Kini = PASS_MASK - (unsigned int)(P.iniTh + 1) * 0x00010001u;
-        // work item i = g * ch + y: the lanes of a warp walk DOWN a column of 4-pixel groups (conflict-free shared loads,
-        // see TPX); i / ch by multiply-shift (exact for i < 2^20 / ch)
-        const int total = groups * ch;
+        constexpr int PW = TPX / 4;                       // tile pitch in uint2
+        const int colItems = 2 * ((ch + 1) >> 1);         // items per pair of group columns: (row pair, left/right group)
+        const int total = colItems * ((groups + 1) >> 1);
         const int qLast = P.fast.qCap - 1;
+        // pair maxima / minima of opposing circle points folded into running registers
+        auto acc2 = [](unsigned int& mm, unsigned int& nn, unsigned int a1, unsigned int b1, unsigned int a2, unsigned int b2) {
+            mm = __vimin3_u16x2(mm, __vmaxu2(a1, b1), __vmaxu2(a2, b2));
+            nn = __vimax3_u16x2(nn, __vminu2(a1, b1), __vminu2(a2, b2));
+        };
+        auto acc1 = [](unsigned int& mm, unsigned int& nn, unsigned int a, unsigned int b) {
+            mm = __vminu2(mm, __vmaxu2(a, b));
+            nn = __vmaxu2(nn, __vminu2(a, b));
+        };
 #pragma unroll 1
         for (int i0 = tid - lane; i0 < total; i0 += FAST_THREADS) {
             const int i = min(i0 + lane, total - 1);
-            const bool valid = i0 + lane < total;
-            const int g = (int)(((unsigned int)i * rch) >> 20), y = i - g * ch;   // i * rch < 900 * 2^20
-            const int x0 = 4 * g;
+            const int cp = (int)(((unsigned int)i * rci) >> 20), rem = i - cp * colItems;   // i * rci < 512 * 2^20
+            const int gRaw = 2 * cp + (rem & 1), y = rem & ~1;
+            const bool valid = (i0 + lane < total) && gRaw < groups;
+            const int g = min(gRaw, groups - 1), x0 = 4 * g;
             // pixels x0, x0+1 answer in bits 9 / 25 of the A word, x0+2, x0+3 in those of the B word
             const unsigned int colA = (x0 < cw ? 0x200u : 0u) | (x0 + 1 < cw ? 0x02000000u : 0u),
                                colB = (x0 + 2 < cw ? 0x200u : 0u) | (x0 + 3 < cw ? 0x02000000u : 0u);
-            const uint2* rowC = reinterpret_cast<const uint2*>(S.tile) + (y + 3) * (TPX / 4) + g;
-            // rowC[0] = pixels x0-4..x0-1, rowC[1] = x0..x0+3, rowC[2] = x0+4..
-            // A = pixels (x0, x0+1), B = (x0+2, x0+3). mm = running minimum of the pair maxima, nn = running maximum of
-            // the pair minima of opposing circle points (folded in as they are formed: few live registers)
-            unsigned int mmA, mmB, nnA, nnB, cA, cB;
-            {   // rows +-1 and 0: dx = +-3 -> circle points 3/11, 5/13, 4/12
-                const uint2* up = rowC - (TPX / 4);
-                const uint2* dn = rowC + (TPX / 4);
-                const uint2 ul = up[0], uc = up[1], ur = up[2], dl = dn[0], dc = dn[1], dr = dn[2];
-                const uint2 ml = rowC[0], mc = rowC[1], mr = rowC[2];
-                cA = mc.x; cB = mc.y;
-                // +3: A' = (x0+3, x0+4), B' = (x0+5, x0+6);  -3: A' = (x0-3, x0-2), B' = (x0-1, x0)
-                const unsigned int uPA = __funnelshift_r(uc.y, ur.x, 16), uPB = __funnelshift_r(ur.x, ur.y, 16);
-                const unsigned int uMA = __funnelshift_r(ul.x, ul.y, 16), uMB = __funnelshift_r(ul.y, uc.x, 16);
-                const unsigned int dPA = __funnelshift_r(dc.y, dr.x, 16), dPB = __funnelshift_r(dr.x, dr.y, 16);
-                const unsigned int dMA = __funnelshift_r(dl.x, dl.y, 16), dMB = __funnelshift_r(dl.y, dc.x, 16);
-                const unsigned int mPA = __funnelshift_r(mc.y, mr.x, 16), mPB = __funnelshift_r(mr.x, mr.y, 16);
-                const unsigned int mMA = __funnelshift_r(ml.x, ml.y, 16), mMB = __funnelshift_r(ml.y, mc.x, 16);
-                // k=3 (3,1) with k=11 (-3,-1); k=5 (3,-1) with k=13 (-3,1); k=4 (3,0) with k=12 (-3,0)
-                mmA = __vimin3_u16x2(__vmaxu2(dPA, uMA), __vmaxu2(uPA, dMA), __vmaxu2(mPA, mMA));
-                nnA = __vimax3_u16x2(__vminu2(dPA, uMA), __vminu2(uPA, dMA), __vminu2(mPA, mMA));
-                mmB = __vimin3_u16x2(__vmaxu2(dPB, uMB), __vmaxu2(uPB, dMB), __vmaxu2(mPB, mMB));
-                nnB = __vimax3_u16x2(__vminu2(dPB, uMB), __vminu2(uPB, dMB), __vminu2(mPB, mMB));
+            const uint2* rowC = reinterpret_cast<const uint2*>(S.tile) + (y + 3) * PW + g;   // tile row of pixel row y
+            // rowC[0] = pixels x0-4..x0-1, rowC[1] = x0..x0+3, rowC[2] = x0+4..   (A = pixels x0, x0+1; B = x0+2, x0+3)
+            // Row r relative to y is "up/mid/down k" for pixel row 0 (= y) and/or pixel row 1 (= y+1).
+            unsigned int mm0A, nn0A, mm0B, nn0B, mm1A, nn1A, mm1B, nn1B, c0A, c0B, c1A, c1B;
+            unsigned int m1w1, m1cx, m1cy, m1w4;          // row -1 raw words (pixel row 1's "up 2")
+            unsigned int p2w1, p2cx, p2cy, p2w4;          // row +2 raw words (pixel row 0's "down 2")
+            {
+                // rows -1..+2: the +-3 shifted pairs. +3: A' = (x0+3, x0+4), B' = (x0+5, x0+6); -3: A' = (x0-3, x0-2), B' = (x0-1, x0)
+                uint2 l = rowC[-PW], c = rowC[-PW + 1], r = rowC[-PW + 2];
+                const unsigned int am1PA = __funnelshift_r(c.y, r.x, 16), am1PB = __funnelshift_r(r.x, r.y, 16),
+                                   am1MA = __funnelshift_r(l.x, l.y, 16), am1MB = __funnelshift_r(l.y, c.x, 16);
+                m1w1 = l.y; m1cx = c.x; m1cy = c.y; m1w4 = r.x;
+                l = rowC[0]; c = rowC[1]; r = rowC[2];
+                const unsigned int a0PA = __funnelshift_r(c.y, r.x, 16), a0PB = __funnelshift_r(r.x, r.y, 16),
+                                   a0MA = __funnelshift_r(l.x, l.y, 16), a0MB = __funnelshift_r(l.y, c.x, 16);
+                c0A = c.x; c0B = c.y;
+                // pixel row 0: k=4 (3,0) with k=12 (-3,0)
+                mm0A = __vmaxu2(a0PA, a0MA); nn0A = __vminu2(a0PA, a0MA);
+                mm0B = __vmaxu2(a0PB, a0MB); nn0B = __vminu2(a0PB, a0MB);
+                l = rowC[PW]; c = rowC[PW + 1]; r = rowC[PW + 2];
+                const unsigned int a1PA = __funnelshift_r(c.y, r.x, 16), a1PB = __funnelshift_r(r.x, r.y, 16),
+                                   a1MA = __funnelshift_r(l.x, l.y, 16), a1MB = __funnelshift_r(l.y, c.x, 16);
+                c1A = c.x; c1B = c.y;
+                // pixel row 0: k=3 (3,1) with k=11 (-3,-1); k=5 (3,-1) with k=13 (-3,1)
+                acc2(mm0A, nn0A, a1PA, am1MA, am1PA, a1MA);
+                acc2(mm0B, nn0B, a1PB, am1MB, am1PB, a1MB);
+                // pixel row 1: k=4 with k=12
+                mm1A = __vmaxu2(a1PA, a1MA); nn1A = __vminu2(a1PA, a1MA);
+                mm1B = __vmaxu2(a1PB, a1MB); nn1B = __vminu2(a1PB, a1MB);
+                l = rowC[2 * PW]; c = rowC[2 * PW + 1]; r = rowC[2 * PW + 2];
+                const unsigned int a2PA = __funnelshift_r(c.y, r.x, 16), a2PB = __funnelshift_r(r.x, r.y, 16),
+                                   a2MA = __funnelshift_r(l.x, l.y, 16), a2MB = __funnelshift_r(l.y, c.x, 16);
+                p2w1 = l.y; p2cx = c.x; p2cy = c.y; p2w4 = r.x;
+                // pixel row 1: k=3 with k=11; k=5 with k=13
+                acc2(mm1A, nn1A, a2PA, a0MA, a0PA, a2MA);
+                acc2(mm1B, nn1B, a2PB, a0MB, a0PB, a2MB);
             }
-            if (!__any_sync(0xffffffffu, valid && (pass_word(mmA, nnA, cA, Kmin) | pass_word(mmB, nnB, cB, Kmin)))) continue;
-            {   // rows +-3: dx = 0, +1, -1  -> circle points 0/8, 1/9, 15/7
-                const uint2* up = rowC - 3 * (TPX / 4);
-                const uint2* dn = rowC + 3 * (TPX / 4);
-                const unsigned int u1 = up[0].y, u4 = up[2].x, d1 = dn[0].y, d4 = dn[2].x;
-                const uint2 uc = up[1], dc = dn[1];
-                const unsigned int uf12 = __funnelshift_r(u1, uc.x, 16), uf23 = __funnelshift_r(uc.x, uc.y, 16),
-                                   uf34 = __funnelshift_r(uc.y, u4, 16);
-                const unsigned int df12 = __funnelshift_r(d1, dc.x, 16), df23 = __funnelshift_r(dc.x, dc.y, 16),
-                                   df34 = __funnelshift_r(dc.y, d4, 16);
-                // k=0 (0,3) with k=8 (0,-3); k=1 (1,3) with k=9 (-1,-3)
-                mmA = __vimin3_u16x2(mmA, __vmaxu2(dc.x, uc.x), __vmaxu2(df23, uf12));
-                nnA = __vimax3_u16x2(nnA, __vminu2(dc.x, uc.x), __vminu2(df23, uf12));
-                mmB = __vimin3_u16x2(mmB, __vmaxu2(dc.y, uc.y), __vmaxu2(df34, uf23));
-                nnB = __vimax3_u16x2(nnB, __vminu2(dc.y, uc.y), __vminu2(df34, uf23));
-                // k=7 (1,-3) with k=15 (-1,3) is folded in below with k=2/10
-                const unsigned int pA7 = __vmaxu2(uf23, df12), qA7 = __vminu2(uf23, df12);
-                const unsigned int pB7 = __vmaxu2(uf34, df23), qB7 = __vminu2(uf34, df23);
-                // rows +-2: dx = +-2 -> circle points 2/10, 6/14; no shifts
-                const uint2* up2 = rowC - 2 * (TPX / 4);
-                const uint2* dn2 = rowC + 2 * (TPX / 4);
-                const unsigned int v1 = up2[0].y, v4 = up2[2].x, e1 = dn2[0].y, e4 = dn2[2].x;
-                const uint2 vc = up2[1], ec = dn2[1];
-                // k=2 (2,2) with k=10 (-2,-2)
-                mmA = __vimin3_u16x2(mmA, pA7, __vmaxu2(ec.y, v1));
-                nnA = __vimax3_u16x2(nnA, qA7, __vminu2(ec.y, v1));
-                mmB = __vimin3_u16x2(mmB, pB7, __vmaxu2(e4, vc.x));
-                nnB = __vimax3_u16x2(nnB, qB7, __vminu2(e4, vc.x));
-                // k=6 (2,-2) with k=14 (-2,2)
-                mmA = __vminu2(mmA, __vmaxu2(vc.y, e1));
-                nnA = __vmaxu2(nnA, __vminu2(vc.y, e1));
-                mmB = __vminu2(mmB, __vmaxu2(v4, ec.x));
-                nnB = __vmaxu2(nnB, __vminu2(v4, ec.x));
+            if (!__any_sync(0xffffffffu, valid && (pass_word(mm0A, nn0A, c0A, Kmin) | pass_word(mm0B, nn0B, c0B, Kmin) |
+                                                   pass_word(mm1A, nn1A, c1A, Kmin) | pass_word(mm1B, nn1B, c1B, Kmin))))
+                continue;
+            unsigned int u3f12, u3f23, u3f34, u3cx, u3cy;   // row -2 as pixel row 1's "up 3"
+            {
+                // row -2: pixel row 0's "up 2" (dx = +-2, no shifts) against row +2
+                const unsigned int w1 = rowC[-2 * PW].y, w4 = rowC[-2 * PW + 2].x;
+                const uint2 c = rowC[-2 * PW + 1];
+                acc2(mm0A, nn0A, p2cy, w1, c.y, p2w1);     // k=2 (2,2) with k=10 (-2,-2); k=6 (2,-2) with k=14 (-2,2)
+                acc2(mm0B, nn0B, p2w4, c.x, w4, p2cx);
+                u3f12 = __funnelshift_r(w1, c.x, 16); u3f23 = __funnelshift_r(c.x, c.y, 16); u3f34 = __funnelshift_r(c.y, w4, 16);
+                u3cx = c.x; u3cy = c.y;
             }
-            const unsigned int passA = valid ? pass_word(mmA, nnA, cA, Kmin) & colA : 0u,
-                               passB = valid ? pass_word(mmB, nnB, cB, Kmin) & colB : 0u;
-            const unsigned int frontA = pass_word(mmA, nnA, cA, Kini) & passA, frontB = pass_word(mmB, nnB, cB, Kini) & passB;
-            const unsigned int backA = passA ^ frontA, backB = passB ^ frontB;
+            {
+                // row +3: pixel row 1's "down 2" against row -1; pixel row 0's "down 3" against row -3
+                const unsigned int w1 = rowC[3 * PW].y, w4 = rowC[3 * PW + 2].x;
+                const uint2 c = rowC[3 * PW + 1];
+                acc2(mm1A, nn1A, c.y, m1w1, m1cy, w1);
+                acc2(mm1B, nn1B, w4, m1cx, m1w4, c.x);
+                const unsigned int df12 = __funnelshift_r(w1, c.x, 16), df23 = __funnelshift_r(c.x, c.y, 16),
+                                   df34 = __funnelshift_r(c.y, w4, 16);
+                const unsigned int v1 = rowC[-3 * PW].y, v4 = rowC[-3 * PW + 2].x;
+                const uint2 uc = rowC[-3 * PW + 1];
+                const unsigned int uf12 = __funnelshift_r(v1, uc.x, 16), uf23 = __funnelshift_r(uc.x, uc.y, 16),
+                                   uf34 = __funnelshift_r(uc.y, v4, 16);
+                // k=0 (0,3) with k=8 (0,-3); k=1 (1,3) with k=9 (-1,-3); k=7 (1,-3) with k=15 (-1,3)
+                acc2(mm0A, nn0A, c.x, uc.x, df23, uf12);
+                acc2(mm0B, nn0B, c.y, uc.y, df34, uf23);
+                acc1(mm0A, nn0A, uf23, df12);
+                acc1(mm0B, nn0B, uf34, df23);
+            }
+            {
+                // row +4: pixel row 1's "down 3" against row -2
+                const unsigned int w1 = rowC[4 * PW].y, w4 = rowC[4 * PW + 2].x;
+                const uint2 c = rowC[4 * PW + 1];
+                const unsigned int df12 = __funnelshift_r(w1, c.x, 16), df23 = __funnelshift_r(c.x, c.y, 16),
+                                   df34 = __funnelshift_r(c.y, w4, 16);
+                acc2(mm1A, nn1A, c.x, u3cx, df23, u3f12);
+                acc2(mm1B, nn1B, c.y, u3cy, df34, u3f23);
+                acc1(mm1A, nn1A, u3f23, df12);
+                acc1(mm1B, nn1B, u3f34, df23);
+            }
+            const bool valid1 = valid && y + 1 < ch;
+            const unsigned int pass0A = valid ? pass_word(mm0A, nn0A, c0A, Kmin) & colA : 0u,
+                               pass0B = valid ? pass_word(mm0B, nn0B, c0B, Kmin) & colB : 0u,
+                               pass1A = valid1 ? pass_word(mm1A, nn1A, c1A, Kmin) & colA : 0u,
+                               pass1B = valid1 ? pass_word(mm1B, nn1B, c1B, Kmin) & colB : 0u;
+            const unsigned int front0A = pass_word(mm0A, nn0A, c0A, Kini) & pass0A, front0B = pass_word(mm0B, nn0B, c0B, Kini) & pass0B,
+                               front1A = pass_word(mm1A, nn1A, c1A, Kini) & pass1A, front1B = pass_word(mm1B, nn1B, c1B, Kini) & pass1B;
+            const unsigned int back0A = pass0A ^ front0A, back0B = pass0B ^ front0B, back1A = pass1A ^ front1A, back1B = pass1B ^ front1B;
             // queue slots: warp scan of (front count | back count << 16), one shared atomic per warp
-            const unsigned int mine = (unsigned int)(__popc(frontA) + __popc(frontB)) | ((unsigned int)(__popc(backA) + __popc(backB)) << 16);
+            const unsigned int mine = (unsigned int)(__popc(front0A | (front0B << 1)) + __popc(front1A | (front1B << 1))) |
+                                      ((unsigned int)(__popc(back0A | (back0B << 1)) + __popc(back1A | (back1B << 1))) << 16);
             unsigned int incl = mine;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
@@ -302,16 +340,24 @@ __global__ void __launch_bounds__(FAST_THREADS, 12) fast_cells_kernel(const __gr
             unsigned int start = 0;
             if (lane == 31 && incl) start = atomicAdd(&sQueueLens, incl);
             start = __shfl_sync(0xffffffffu, start, 31) + incl - mine;
-            const unsigned int e = (unsigned int)x0 | ((unsigned int)y << 6);
+            const unsigned int e0 = (unsigned int)x0 | ((unsigned int)y << 6), e1 = e0 + 64u;
             int pf = (int)(start & 0xffffu), pb = qLast - (int)(start >> 16);
-            if (frontA & 0x200u) S.queue[pf++] = (unsigned short)e;
-            if (frontA & 0x02000000u) S.queue[pf++] = (unsigned short)(e + 1);
-            if (frontB & 0x200u) S.queue[pf++] = (unsigned short)(e + 2);
-            if (frontB & 0x02000000u) S.queue[pf] = (unsigned short)(e + 3);
-            if (backA & 0x200u) S.queue[pb--] = (unsigned short)e;
-            if (backA & 0x02000000u) S.queue[pb--] = (unsigned short)(e + 1);
-            if (backB & 0x200u) S.queue[pb--] = (unsigned short)(e + 2);
-            if (backB & 0x02000000u) S.queue[pb] = (unsigned short)(e + 3);
+            if (front0A & 0x200u) S.queue[pf++] = (unsigned short)e0;
+            if (front0A & 0x02000000u) S.queue[pf++] = (unsigned short)(e0 + 1);
+            if (front0B & 0x200u) S.queue[pf++] = (unsigned short)(e0 + 2);
+            if (front0B & 0x02000000u) S.queue[pf++] = (unsigned short)(e0 + 3);
+            if (front1A & 0x200u) S.queue[pf++] = (unsigned short)e1;
+            if (front1A & 0x02000000u) S.queue[pf++] = (unsigned short)(e1 + 1);
+            if (front1B & 0x200u) S.queue[pf++] = (unsigned short)(e1 + 2);
+            if (front1B & 0x02000000u) S.queue[pf] = (unsigned short)(e1 + 3);
+            if (back0A & 0x200u) S.queue[pb--] = (unsigned short)e0;
+            if (back0A & 0x02000000u) S.queue[pb--] = (unsigned short)(e0 + 1);
+            if (back0B & 0x200u) S.queue[pb--] = (unsigned short)(e0 + 2);
+            if (back0B & 0x02000000u) S.queue[pb--] = (unsigned short)(e0 + 3);
+            if (back1A & 0x200u) S.queue[pb--] = (unsigned short)e1;
+            if (back1A & 0x02000000u) S.queue[pb--] = (unsigned short)(e1 + 1);
+            if (back1B & 0x200u) S.queue[pb--] = (unsigned short)(e1 + 2);
+            if (back1B & 0x02000000u) S.queue[pb] = (unsigned short)(e1 + 3);
         }
     }
     __syncthreads();
