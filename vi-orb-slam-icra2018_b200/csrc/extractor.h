@@ -60,8 +60,8 @@ struct alignas(16) Cell {    // one FAST cell with a non-empty interior; 32 byte
 static_assert(sizeof(Cell) == 32, "Cell is read as two uint4");
 
 struct FastLayout {      // byte offsets inside the FAST kernel's dynamic shared memory (host-computed, see fast.cu)
-    int tile, score, bitmap, queue, alive, total;
-    int zeroVec;         // uint4 count of [score, queue): score map + bitmap start as zero
+    int tile, score, queue, alive, total;
+    int zeroVec;         // uint4 count of [score, queue): the score map starts as zero
     int qCap;            // queue capacity in entries
 };
 

@@ -24,9 +24,9 @@
 //      only be corners at minThFAST from the back;
 //   B. exact score on the front queue only (dense lanes again): both polarities in one 16x2 register, sliding-window
 //      minimum with 3-input min/max;
-//   C. NMS on the corners with S >= iniThFAST; survivors set bits in a row-major bitmap;
+//   C. NMS on the corners with S >= iniThFAST; survivors are listed;
 //   B', C'. only if nothing survived: the back queue is scored too and NMS runs at minThFAST;
-//   D. survivors store themselves at their row-major rank (bitmap popcounts).
+//   D. survivors store themselves at their row-major rank (count of smaller keys in the list).
 #include "extractor.h"
 
 namespace orbb {
@@ -55,7 +55,6 @@ FastLayout fast_layout(int maxW, int maxH) {
     auto take = [&](int bytes) { int r = p; p += (bytes + 15) & ~15; return r; };
     f.tile = take((maxH + 6) * TPX * 2);          // 16-bit pixels
     f.score = take((maxH + 2) * SC_PITCH);        // uint8 scores with a zero ring
-    f.bitmap = take((((npix + 31) >> 5) + 1) * 4);    // NMS survivors, bit = y*cw + x
     f.queue = take(npix * 2);                     // x | y<<6: front = may be a corner at iniTh, back = only at minTh
     f.alive = take(((maxW + 1) / 2) * ((maxH + 1) / 2) * 2);   // NMS survivors (no two are 8-adjacent)
     f.total = p;
@@ -116,7 +115,6 @@ __device__ __forceinline__ unsigned int pass_word(unsigned int mm, unsigned int 
 struct FastShared {
     unsigned int* tile;
     unsigned char* score;
-    unsigned int* bitmap;
     unsigned short* queue;
     unsigned short* surv;
 };
@@ -134,7 +132,7 @@ __device__ __forceinline__ void score_queue(const FastShared& S, int first, int 
     }
 }
 
-// C: per-cell NMS over the queue entries whose score lies in [lo, hi); survivors are listed and set their bitmap bit
+// C: per-cell NMS over the queue entries whose score lies in [lo, hi); survivors are listed
 __device__ __forceinline__ void nms_queue(const FastShared& S, int first, int step, int n, int tid, int cw, int lo, int hi,
                                           int* survLen) {
 #pragma unroll 1
@@ -146,11 +144,7 @@ __device__ __forceinline__ void nms_queue(const FastShared& S, int first, int st
         if (s < lo || s >= hi) continue;
         const int m = max(max(max(sc[-SC_PITCH - 1], sc[-SC_PITCH]), max(sc[-SC_PITCH + 1], sc[-1])),
                           max(max(sc[1], sc[SC_PITCH - 1]), max(sc[SC_PITCH], sc[SC_PITCH + 1])));
-        if (s > m) {
-            const int bit = y * cw + x;
-            atomicOr(&S.bitmap[bit >> 5], 1u << (bit & 31));
-            S.surv[atomicAdd(survLen, 1)] = (unsigned short)e;
-        }
+        if (s > m) S.surv[atomicAdd(survLen, 1)] = (unsigned short)e;
     }
 }
 
@@ -164,11 +158,10 @@ __global__ void __launch_bounds__(FAST_THREADS, 12) fast_cells_kernel(const __gr
     FastShared S;
     S.tile = reinterpret_cast<unsigned int*>(fsm + P.fast.tile);
     S.score = fsm + P.fast.score;
-    S.bitmap = reinterpret_cast<unsigned int*>(fsm + P.fast.bitmap);
     S.queue = reinterpret_cast<unsigned short*>(fsm + P.fast.queue);
     S.surv = reinterpret_cast<unsigned short*>(fsm + P.fast.alive);
 
-    // score map and bitmap start as zero (independent of the cell: overlaps the cell-table load)
+    // the score map starts as zero (independent of the cell: overlaps the cell-table load)
     {
         uint4* z = reinterpret_cast<uint4*>(S.score);
 #pragma unroll 1
@@ -380,16 +373,15 @@ __global__ void __launch_bounds__(FAST_THREADS, 12) fast_cells_kernel(const __gr
         sn = sSurvLen;
     }
 
-    // ---- D. survivors store themselves at their row-major rank = number of set bits below their own in the bitmap
-    //         (a few dozen POPCs each; there are only ~15 survivors per cell)
+    // ---- D. survivors store themselves at their row-major rank = number of survivors with a smaller (y, x) key
+    //         (there are only ~15 survivors per cell; the list reads are warp-wide broadcasts)
     if (tid == 0) P.cellCount[(size_t)frame * P.nCellsTotal + blockIdx.x] = sn;
     unsigned int* slot = P.slots + (size_t)frame * P.slotFrameEntries + cellSlot;
     for (int q = tid; q < sn; q += FAST_THREADS) {
         const unsigned int e = S.surv[q];
         const int x = e & 63, y = e >> 6;
-        const int bit = y * cw + x;
-        int rank = __popc(S.bitmap[bit >> 5] & ((1u << (bit & 31)) - 1u));
-        for (int w = 0; w < (bit >> 5); ++w) rank += __popc(S.bitmap[w]);
+        int rank = 0;                                   // entries are x | y << 6: numeric order == (y, x) order
+        for (int j = 0; j < sn; ++j) rank += S.surv[j] < e;
         const unsigned int s = S.score[(y + 1) * SC_PITCH + x + 1];
         slot[rank] = ((unsigned int)(cellX0 + x - 16) << 20) | ((unsigned int)(cellY0 + y - 16) << 8) | s;
     }
