@@ -22,7 +22,12 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__warp_issue_stalled_no_instruction_per_warp_active.pct", "smsp__warp_issue_stalled_dispatch_stall_per_warp_active.pct",
         "smsp__warp_issue_stalled_membar_per_warp_active.pct", "smsp__warp_issue_stalled_sleeping_per_warp_active.pct",
         "smsp__inst_executed_op_shared_atom.sum", "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
-        "sm__inst_executed_pipe_uniform.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active"]
+        "sm__inst_executed_pipe_uniform.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+        "smsp__pcsamp_warps_issue_stalled_long_scoreboard", "smsp__pcsamp_warps_issue_stalled_barrier",
+        "smsp__pcsamp_warps_issue_stalled_short_scoreboard", "smsp__pcsamp_warps_issue_stalled_mio_throttle",
+        "smsp__pcsamp_warps_issue_stalled_math_pipe_throttle", "smsp__pcsamp_warps_issue_stalled_not_selected",
+        "smsp__pcsamp_warps_issue_stalled_wait", "smsp__pcsamp_sample_buffer_full"]
 
 
 def raw(rep):
@@ -50,7 +55,7 @@ def main():
             if k in d:
                 lines.append("%-75s %s %s" % (k, d[k][0], d[k][1]))
         extra = [k for k in d if ("stalled" in k and "per_warp_active" in k and k not in KEYS)]
-        with open(os.path.join("profiles", "%s_ncu_%s.txt" % (rnd, base.replace("prof_", ""))), "w") as f:
+        with open(os.path.join("profiles", "%s_ncu_%s.txt" % (rnd, base.replace("prof_", "").replace("final_", ""))), "w") as f:
             f.write("\n".join(lines) + "\n")
         print("\n".join(lines[:1] + [l for l in lines[3:]]))
         print()
