@@ -1,0 +1,122 @@
+"""TEST INFRASTRUCTURE ONLY -- ctypes front end of oracle/_ref/libmatch_ref.so: the reference's own ORBmatcher.cc
+(compiled in place against oracle/ref_shim/matcher) behind the same flat-array calls as oracle_py.OracleFrame, so a test
+hands identical inputs to the oracle restatement and to the reference's code."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from oracle_py import KP_DTYPE, MP_QUERY_DTYPE, PROJ_QUERY_DTYPE
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "_ref", "libmatch_ref.so")
+
+
+def build():
+    """Needs /root/reference (absent on the GPU box, where the prebuilt file is used)."""
+    subprocess.check_call(["make", "-s", "-f", os.path.join(HERE, "ref_shim", "Makefile"), LIB])
+    return LIB
+
+
+def available():
+    return os.path.exists(LIB)
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+vp, i32, f32 = C.c_void_p, C.c_int, C.c_float
+
+
+class RefMatcher:
+    def __init__(self):
+        self.lib = L = C.CDLL(LIB)
+        L.refm_distance.argtypes = [vp, vp]
+        L.refm_frame_create.restype = vp
+        L.refm_frame_create.argtypes = [vp, vp, i32, f32, f32, f32, f32]
+        L.refm_frame_destroy.argtypes = [vp]
+        L.refm_search_init.argtypes = [vp, vp, vp, vp, i32, f32, i32]
+        L.refm_search_projection.argtypes = [vp, vp, i32, vp, f32, vp, vp, i32, f32, i32, vp, vp, i32]
+        L.refm_search_points.argtypes = [vp, vp, i32, vp, vp, vp, i32, f32, f32, vp, vp]
+        L.refm_search_triangulation.argtypes = ([vp, vp] + [i32, vp, vp, vp] * 2 + [vp] * 5 + [f32, f32, vp, vp, i32, i32, i32, vp])
+        L.refm_search_bow.argtypes = ([vp, vp] + [i32, vp, vp, vp] * 2 + [vp, vp, f32, i32, i32, vp, vp])
+
+    def distance(self, a, b):
+        a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)
+        return self.lib.refm_distance(_p(a), _p(b))
+
+    def frame(self, keys_un, desc, bounds):
+        return RefFrame(self, keys_un, desc, bounds)
+
+
+class RefFrame:
+    def __init__(self, ref, keys_un, desc, bounds):
+        self.lib = ref.lib
+        self.keys = np.ascontiguousarray(keys_un, KP_DTYPE)
+        self.desc = np.ascontiguousarray(desc, np.uint8)
+        self.n = len(self.keys)
+        self.h = C.c_void_p(self.lib.refm_frame_create(_p(self.keys), _p(self.desc), self.n, *[float(b) for b in bounds]))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.refm_frame_destroy(self.h)
+            self.h = None
+
+    def search_init(self, other, prev_xy, window=100, ratio=0.9, check_ori=True):
+        prev = np.ascontiguousarray(prev_xy, np.float32).copy()
+        m12 = np.empty(self.n, np.int32)
+        n = self.lib.refm_search_init(self.h, other.h, _p(prev), _p(m12), window, ratio, int(check_ori))
+        return n, m12, prev
+
+    def search_projection(self, scale_factors, queries, qdesc, th, mode=0, occupied=None, u_right=None, mbf=0.0, check_ori=True):
+        """queries must carry invz == 1 (identity camera at unit depth, see match_ref.cpp)."""
+        sf = np.ascontiguousarray(scale_factors, np.float32)
+        q = np.ascontiguousarray(queries, PROJ_QUERY_DTYPE)
+        qd = np.ascontiguousarray(qdesc, np.uint8)
+        occ = np.zeros(self.n, np.uint8) if occupied is None else np.ascontiguousarray(occupied, np.uint8)
+        ur = None if u_right is None else np.ascontiguousarray(u_right, np.float32)
+        match = np.empty(self.n, np.int32)
+        n = self.lib.refm_search_projection(self.h, _p(sf), len(sf), _p(ur), mbf, _p(q), _p(qd), len(q), th, mode, _p(occ),
+                                            _p(match), int(check_ori))
+        assert n != -2, "refm_search_projection needs invz == 1"
+        return n, match
+
+    def search_points(self, scale_factors, queries, qdesc, th, ratio, occupied=None, u_right=None):
+        sf = np.ascontiguousarray(scale_factors, np.float32)
+        q = np.ascontiguousarray(queries, MP_QUERY_DTYPE)
+        qd = np.ascontiguousarray(qdesc, np.uint8)
+        occ = np.zeros(self.n, np.uint8) if occupied is None else np.ascontiguousarray(occupied, np.uint8)
+        ur = None if u_right is None else np.ascontiguousarray(u_right, np.float32)
+        match = np.empty(self.n, np.int32)
+        n = self.lib.refm_search_points(self.h, _p(sf), len(sf), _p(ur), _p(q), _p(qd), len(q), th, ratio, _p(occ), _p(match))
+        return n, match
+
+    def search_triangulation(self, other, fv1, fv2, F12, ex, ey, sf2, sigma2_2, has1=None, has2=None, ur1=None, ur2=None,
+                             only_stereo=False, check_ori=False):
+        n1, s1, i1 = [np.ascontiguousarray(a, np.int32) for a in fv1]
+        n2, s2, i2 = [np.ascontiguousarray(a, np.int32) for a in fv2]
+        has1 = np.zeros(self.n, np.uint8) if has1 is None else np.ascontiguousarray(has1, np.uint8)
+        has2 = np.zeros(other.n, np.uint8) if has2 is None else np.ascontiguousarray(has2, np.uint8)
+        ur1 = None if ur1 is None else np.ascontiguousarray(ur1, np.float32)
+        ur2 = None if ur2 is None else np.ascontiguousarray(ur2, np.float32)
+        F12 = np.ascontiguousarray(F12, np.float32)
+        sf2 = np.ascontiguousarray(sf2, np.float32)
+        sg2 = np.ascontiguousarray(sigma2_2, np.float32)
+        m12 = np.empty(self.n, np.int32)
+        n = self.lib.refm_search_triangulation(self.h, other.h, len(n1), _p(n1), _p(s1), _p(i1), len(n2), _p(n2), _p(s2),
+                                               _p(i2), _p(has1), _p(has2), _p(ur1), _p(ur2), _p(F12), ex, ey, _p(sf2),
+                                               _p(sg2), len(sf2), int(only_stereo), int(check_ori), _p(m12))
+        return n, m12
+
+    def search_bow(self, other, fv1, fv2, valid1=None, valid2=None, ratio=0.7, check_ori=True, strict_low=False):
+        n1, s1, i1 = [np.ascontiguousarray(a, np.int32) for a in fv1]
+        n2, s2, i2 = [np.ascontiguousarray(a, np.int32) for a in fv2]
+        v1 = None if valid1 is None else np.ascontiguousarray(valid1, np.uint8)
+        v2 = None if valid2 is None else np.ascontiguousarray(valid2, np.uint8)
+        m12 = np.empty(self.n, np.int32)
+        m21 = np.empty(other.n, np.int32)
+        n = self.lib.refm_search_bow(self.h, other.h, len(n1), _p(n1), _p(s1), _p(i1), len(n2), _p(n2), _p(s2), _p(i2),
+                                     _p(v1), _p(v2), ratio, int(check_ori), int(strict_low), _p(m12), _p(m21))
+        return n, m12, m21

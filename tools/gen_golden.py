@@ -3,8 +3,9 @@
 
 Extractor vectors come from oracle/_ref/orb_ref = the reference's OWN src/ORBextractor.cc compiled in place against the
 OpenCV stand-in (oracle/ref_shim), i.e. they are outputs of the reference itself, not of our restatement.
-ORBmatcher.cc cannot be compiled here (it needs Frame.h -> Eigen/DBoW2/g2o), so the matcher vectors are produced by
-oracle/match_oracle.cpp and are marked `pinned_by: oracle` -- parity for the matcher is unpinned.
+Matcher vectors: matcher_ref_vectors.npz holds outputs of oracle/_ref/libmatch_ref.so = the reference's OWN
+src/ORBmatcher.cc compiled in place against the stand-ins of oracle/ref_shim/matcher (seeded cases of
+tests/matcher_cases.py); matcher_vectors.npz (grid CSR, brute force) is produced by oracle/match_oracle.cpp and says so.
 """
 import hashlib
 import os
@@ -93,6 +94,22 @@ def main():
                         bf_q=q, bf_qa=qa, bf_t=t, bf_ta=ta, bf_n=bn, bf_best=best, bf_second=second, bf_idx=idx, bf_m12=bm12,
                         pinned_by="oracle (ORBmatcher.cc cannot be compiled here)")
     print("matcher vectors: init", n, "bruteforce", bn)
+    # ---- matcher vectors from the reference's own ORBmatcher.cc
+    import ref_matcher
+    from matcher_cases import CASES, run_case
+    if not ref_matcher.available():
+        ref_matcher.build()
+    rm = ref_matcher.RefMatcher()
+    r1, r2 = rm.frame(ka, da, bounds), rm.frame(kb, db, bounds)
+    save = {}
+    for c in CASES:
+        out = run_case(c, r1, r2, ka, da, kb, db)
+        for j, a in enumerate(out):
+            save["%s__%d" % (c, j)] = np.asarray(a)
+        print("reference", c, int(out[0]))
+    np.savez_compressed(os.path.join(OUT, "matcher_ref_vectors.npz"), cases=np.array(CASES),
+                        pinned_by="reference (oracle/_ref/libmatch_ref.so = /root/reference/src/ORBmatcher.cc compiled in place)",
+                        **save)
 
 
 if __name__ == "__main__":
