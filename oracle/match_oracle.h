@@ -11,6 +11,8 @@
 //   ORBmatcher::SearchForTriangulation                   ORBmatcher.cc:657-823 (+140-157)
 //   ORBmatcher::SearchByBoW(KF,KF) inner loop            ORBmatcher.cc:566-618 (brute-force / all-pairs)
 // The object graphs (Frame, KeyFrame, MapPoint) are flattened to the arrays the loops actually read.
+// Pinned: tests/test_matcher_ref.py runs every search here against the reference's own ORBmatcher.cc compiled in place
+// (oracle/_ref/libmatch_ref.so) on identical inputs; the grid lookup is pinned by known-answer tests only.
 #pragma once
 #include <cstdint>
 #include <vector>

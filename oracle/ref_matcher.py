@@ -42,6 +42,10 @@ class RefMatcher:
         L.refm_search_points.argtypes = [vp, vp, i32, vp, vp, vp, i32, f32, f32, vp, vp]
         L.refm_search_triangulation.argtypes = ([vp, vp] + [i32, vp, vp, vp] * 2 + [vp] * 5 + [f32, f32, vp, vp, i32, i32, i32, vp])
         L.refm_search_bow.argtypes = ([vp, vp] + [i32, vp, vp, vp] * 2 + [vp, vp, f32, i32, i32, vp, vp])
+        L.refm_search_projection_kf.argtypes = [vp, vp, i32, vp, vp, i32, f32, i32, vp, vp, i32]
+        L.refm_search_projection_sim3.argtypes = [vp, vp, i32, vp, vp, i32, i32, vp, vp]
+        L.refm_fuse.argtypes = [vp, vp, vp, i32, vp, f32, vp, vp, i32, f32, i32, vp]
+        L.refm_search_sim3.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, f32, vp]
 
     def distance(self, a, b):
         a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)
@@ -120,3 +124,50 @@ class RefFrame:
         n = self.lib.refm_search_bow(self.h, other.h, len(n1), _p(n1), _p(s1), _p(i1), len(n2), _p(n2), _p(s2), _p(i2),
                                      _p(v1), _p(v2), ratio, int(check_ori), int(strict_low), _p(m12), _p(m21))
         return n, m12, m21
+
+    # ---- the overloads whose GPU entry points are orbm_search_by_projection_ex / orbm_search_projected_best
+    def search_projection_kf(self, scale_factors, queries, qdesc, th, orb_dist, occupied=None, check_ori=True):
+        """SearchByProjection(Frame, KeyFrame, sAlreadyFound, th, ORBdist), ORBmatcher.cc:1500"""
+        sf = np.ascontiguousarray(scale_factors, np.float32)
+        q = np.ascontiguousarray(queries, PROJ_QUERY_DTYPE)
+        qd = np.ascontiguousarray(qdesc, np.uint8)
+        occ = np.zeros(self.n, np.uint8) if occupied is None else np.ascontiguousarray(occupied, np.uint8)
+        match = np.empty(self.n, np.int32)
+        n = self.lib.refm_search_projection_kf(self.h, _p(sf), len(sf), _p(q), _p(qd), len(q), th, orb_dist, _p(occ), _p(match),
+                                               int(check_ori))
+        assert n != -2
+        return n, match
+
+    def search_projection_sim3(self, scale_factors, queries, qdesc, th, occupied=None):
+        """SearchByProjection(KeyFrame, Scw, vpPoints, vpMatched, th), ORBmatcher.cc:290"""
+        sf = np.ascontiguousarray(scale_factors, np.float32)
+        q = np.ascontiguousarray(queries, PROJ_QUERY_DTYPE)
+        qd = np.ascontiguousarray(qdesc, np.uint8)
+        occ = np.zeros(self.n, np.uint8) if occupied is None else np.ascontiguousarray(occupied, np.uint8)
+        match = np.empty(self.n, np.int32)
+        n = self.lib.refm_search_projection_sim3(self.h, _p(sf), len(sf), _p(q), _p(qd), len(q), int(th), _p(occ), _p(match))
+        assert n != -2
+        return n, match
+
+    def fuse(self, scale_factors, inv_sigma2, queries, qdesc, th, u_right=None, bf=0.0, scw=False):
+        """Fuse (ORBmatcher.cc:825 / :977 with scw=True) -> (nFused, keypoint index each point was fused into or -1)"""
+        from oracle_py import BEST_QUERY_DTYPE
+        sf = np.ascontiguousarray(scale_factors, np.float32)
+        s2 = np.ascontiguousarray(inv_sigma2, np.float32)
+        q = np.ascontiguousarray(queries, BEST_QUERY_DTYPE)
+        qd = np.ascontiguousarray(qdesc, np.uint8)
+        ur = None if u_right is None else np.ascontiguousarray(u_right, np.float32)
+        fused = np.empty(len(q), np.int32)
+        n = self.lib.refm_fuse(self.h, _p(sf), _p(s2), len(sf), _p(ur), bf, _p(q), _p(qd), len(q), th, int(scw), _p(fused))
+        return n, fused
+
+    def search_sim3(self, other, sf1, sf2, uv1, level1, has1, uv2, level2, has2, th):
+        """SearchBySim3 (ORBmatcher.cc:1102) with identity Sim3 and poses -> (nFound, matches12)"""
+        sf1 = np.ascontiguousarray(sf1, np.float32); sf2 = np.ascontiguousarray(sf2, np.float32)
+        uv1 = np.ascontiguousarray(uv1, np.float32); uv2 = np.ascontiguousarray(uv2, np.float32)
+        level1 = np.ascontiguousarray(level1, np.int32); level2 = np.ascontiguousarray(level2, np.int32)
+        has1 = np.ascontiguousarray(has1, np.uint8); has2 = np.ascontiguousarray(has2, np.uint8)
+        m12 = np.empty(self.n, np.int32)
+        n = self.lib.refm_search_sim3(self.h, other.h, _p(sf1), _p(sf2), len(sf1), _p(uv1), _p(level1), _p(has1), _p(uv2),
+                                      _p(level2), _p(has2), th, _p(m12))
+        return n, m12

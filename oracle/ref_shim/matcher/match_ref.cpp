@@ -219,4 +219,127 @@ int refm_search_bow(void* k1, void* k2, int nNodes1, const int* nodeId1, const i
     return n;
 }
 
+// ORBmatcher::SearchByProjection(Frame&, KeyFrame*, const set<MapPoint*>&, th, ORBdist)  (ORBmatcher.cc:1500, relocalisation).
+// q[i].octave is the level the reference predicts with MapPoint::PredictScale; q[i].valid = 0 covers NULL / bad / already found.
+int refm_search_projection_kf(void* cur, const float* sf, int nLevels, const orbo::ProjQuery* q, const uint8_t* qdesc, int nq,
+                              float th, int orbDist, const uint8_t* occupied, int* curMatch, int checkOri) {
+    Frame C;
+    fill(C, (RefFrame*)cur);
+    C.mvScaleFactors.assign(sf, sf + nLevels);
+    MapPoint taken;
+    C.mvpMapPoints.assign(C.N, (MapPoint*)NULL);
+    for (int i = 0; i < C.N; ++i)
+        if (occupied && occupied[i]) C.mvpMapPoints[i] = &taken;
+    KeyFrame K;
+    std::vector<MapPoint> mp(nq);
+    K.N = nq;
+    K.mvKeysUn.resize(nq);
+    K.mvpMapPoints.assign(nq, (MapPoint*)NULL);
+    for (int i = 0; i < nq; ++i) {
+        if (q[i].valid && q[i].invz != 1.f) return -2;
+        mp[i].worldPos = vec3(q[i].u, q[i].v, 1.f);
+        mp[i].descriptor = row32(qdesc + (size_t)i * 32);
+        mp[i].predictedLevel = q[i].octave;
+        K.mvKeysUn[i].angle = q[i].angle;
+        if (q[i].valid) K.mvpMapPoints[i] = &mp[i];
+    }
+    std::set<MapPoint*> none;
+    ORBmatcher m(0.9f, checkOri != 0);
+    const int n = m.SearchByProjection(C, &K, none, th, orbDist);
+    for (int i = 0; i < C.N; ++i) curMatch[i] = index_of(C.mvpMapPoints[i], mp);
+    return n;
+}
+
+// ORBmatcher::SearchByProjection(KeyFrame*, cv::Mat Scw, vpPoints, vpMatched, th)  (ORBmatcher.cc:290, loop closing)
+int refm_search_projection_sim3(void* kf, const float* sf, int nLevels, const orbo::ProjQuery* q, const uint8_t* qdesc, int nq,
+                                int th, const uint8_t* occupied, int* match) {
+    KeyFrame K;
+    fill(K, (RefFrame*)kf);
+    K.mvScaleFactors.assign(sf, sf + nLevels);
+    MapPoint taken;
+    std::vector<MapPoint*> vpMatched(K.N, (MapPoint*)NULL);
+    for (int i = 0; i < K.N; ++i)
+        if (occupied && occupied[i]) vpMatched[i] = &taken;
+    std::vector<MapPoint> mp(nq);
+    std::vector<MapPoint*> vp(nq);
+    for (int i = 0; i < nq; ++i) {
+        if (q[i].valid && q[i].invz != 1.f) return -2;
+        mp[i].worldPos = vec3(q[i].u, q[i].v, 1.f);
+        mp[i].normal = mp[i].worldPos;                       // passes the viewing-angle test (:352-355)
+        mp[i].descriptor = row32(qdesc + (size_t)i * 32);
+        mp[i].predictedLevel = q[i].octave;
+        mp[i].bad = !q[i].valid;
+        vp[i] = &mp[i];
+    }
+    ORBmatcher m(0.75f, true);
+    const int n = m.SearchByProjection(&K, cv::Mat::eye(4, 4, CV_32F), vp, vpMatched, th);
+    for (int i = 0; i < K.N; ++i) match[i] = index_of(vpMatched[i], mp);
+    return n;
+}
+
+// ORBmatcher::Fuse(KeyFrame*, const vector<MapPoint*>&, th) (ORBmatcher.cc:825; scw = 0) and
+// ORBmatcher::Fuse(KeyFrame*, cv::Mat Scw, vpPoints, th, vpReplacePoint) (ORBmatcher.cc:977; scw = 1).
+// The keyframe holds no map points, so every accepted point ends in AddObservation(pKF, bestIdx): fusedIdx[i] = bestIdx or -1.
+int refm_fuse(void* kf, const float* sf, const float* invSigma2, int nLevels, const float* uRight, float bf,
+              const orbo::BestQuery* q, const uint8_t* qdesc, int nq, float th, int scw, int* fusedIdx) {
+    KeyFrame K;
+    fill(K, (RefFrame*)kf);
+    K.mvScaleFactors.assign(sf, sf + nLevels);
+    K.mvInvLevelSigma2.assign(invSigma2, invSigma2 + nLevels);
+    if (uRight) K.mvuRight.assign(uRight, uRight + K.N);
+    K.mbf = bf;
+    K.mvpMapPoints.assign(K.N, (MapPoint*)NULL);
+    std::vector<MapPoint> mp(nq);
+    std::vector<MapPoint*> vp(nq);
+    for (int i = 0; i < nq; ++i) {
+        mp[i].worldPos = vec3(q[i].u, q[i].v, 1.f);
+        mp[i].normal = mp[i].worldPos;
+        mp[i].descriptor = row32(qdesc + (size_t)i * 32);
+        mp[i].predictedLevel = q[i].level;
+        mp[i].bad = !q[i].valid;
+        vp[i] = &mp[i];
+    }
+    ORBmatcher m(0.6f, true);
+    int n;
+    if (!scw) {
+        n = m.Fuse(&K, vp, th);
+    } else {
+        std::vector<MapPoint*> repl(nq, (MapPoint*)NULL);
+        n = m.Fuse(&K, cv::Mat::eye(4, 4, CV_32F), vp, th, repl);
+    }
+    for (int i = 0; i < nq; ++i) fusedIdx[i] = mp[i].added.empty() ? -1 : (int)mp[i].added[0].second;
+    return n;
+}
+
+// ORBmatcher::SearchBySim3  (ORBmatcher.cc:1102) with s12 = 1, R12 = I, t12 = 0 and identity keyframe poses: map point i of a
+// keyframe sits at (u, v, 1), i.e. projects to (u, v) in the other one.  level = what PredictScale returns for it.
+int refm_search_sim3(void* k1, void* k2, const float* sf1, const float* sf2, int nLevels, const float* uv1, const int* level1,
+                     const uint8_t* has1, const float* uv2, const int* level2, const uint8_t* has2, float th, int* m12) {
+    KeyFrame K1, K2;
+    fill(K1, (RefFrame*)k1);
+    fill(K2, (RefFrame*)k2);
+    K1.mvScaleFactors.assign(sf1, sf1 + nLevels);
+    K2.mvScaleFactors.assign(sf2, sf2 + nLevels);
+    std::vector<MapPoint> mp1(K1.N), mp2(K2.N);
+    K1.mvpMapPoints.assign(K1.N, (MapPoint*)NULL);
+    K2.mvpMapPoints.assign(K2.N, (MapPoint*)NULL);
+    for (int i = 0; i < K1.N; ++i) {
+        mp1[i].worldPos = vec3(uv1[2 * i], uv1[2 * i + 1], 1.f);
+        mp1[i].predictedLevel = level1[i];
+        mp1[i].descriptor = row32(K1.mDescriptors.ptr<uchar>(i));
+        if (has1[i]) K1.mvpMapPoints[i] = &mp1[i];
+    }
+    for (int i = 0; i < K2.N; ++i) {
+        mp2[i].worldPos = vec3(uv2[2 * i], uv2[2 * i + 1], 1.f);
+        mp2[i].predictedLevel = level2[i];
+        mp2[i].descriptor = row32(K2.mDescriptors.ptr<uchar>(i));
+        if (has2[i]) K2.mvpMapPoints[i] = &mp2[i];
+    }
+    std::vector<MapPoint*> v12(K1.N, (MapPoint*)NULL);
+    ORBmatcher m(0.75f, true);
+    const int n = m.SearchBySim3(&K1, &K2, v12, 1.f, cv::Mat::eye(3, 3, CV_32F), cv::Mat(3, 1, CV_32F), th);
+    for (int i = 0; i < K1.N; ++i) m12[i] = index_of(v12[i], mp2);
+    return n;
+}
+
 }  // extern "C"

@@ -26,7 +26,10 @@ def feature_vector(keys, dx, dy, cell=48):
 
 
 CASES = ["init_w100", "init_w30_noori", "init_ratio06", "proj_window", "proj_forward_stereo", "proj_backward_stereo",
-         "points_th1", "points_th3", "tri_mono", "tri_only_stereo", "bow_kf_frame", "bow_kf_kf", "bow_kf_kf_noori"]
+         "points_th1", "points_th3", "tri_mono", "tri_only_stereo", "bow_kf_frame", "bow_kf_kf", "bow_kf_kf_noori",
+         "reloc_orbdist64", "reloc_orbdist100_noori", "loop_window", "fuse_mono", "fuse_stereo", "fuse_scw", "sim3"]
+BEST = np.dtype([("u", "<f4"), ("v", "<f4"), ("radius", "<f4"), ("ur", "<f4"), ("level", "<i4"), ("valid", "<i4")])
+TH_LOW, TH_HIGH = 50, 100
 
 
 def run_case(name, f1, f2, ka, da, kb, db, shift=(7.0, 3.0)):
@@ -89,6 +92,70 @@ def run_case(name, f1, f2, ka, da, kb, db, shift=(7.0, 3.0)):
         valid1 = (rng.random(n1) < 0.7).astype(np.uint8)
         valid2 = (rng.random(n2) < 0.8).astype(np.uint8) if use_valid2 else None
         return f1.search_bow(f2, fv1, fv2, valid1, valid2, ratio, ori, strict)
+    if name.startswith("reloc") or name == "loop_window":
+        # SearchByProjection(Frame, KeyFrame, sAlreadyFound, th, ORBdist) (:1500) and SearchByProjection(KF, Scw, ...) (:290):
+        # the level is the one MapPoint::PredictScale returns; an assigned keypoint is simply taken afterwards
+        q = np.zeros(n1, PROJ)
+        q["u"] = ka["x"] + dx + rng.normal(0, 1.5, n1)
+        q["v"] = ka["y"] + dy + rng.normal(0, 1.5, n1)
+        q["invz"] = 1.0
+        q["octave"] = np.clip(ka["octave"] + rng.integers(-1, 2, n1), 0, 7)
+        q["valid"] = rng.random(n1) < 0.8
+        q["obsPositive"] = 1
+        q["angle"] = ka["angle"]
+        occ = (rng.random(n2) < 0.1).astype(np.uint8)
+        if name == "loop_window":
+            if hasattr(f2, "search_projection_sim3"):
+                return f2.search_projection_sim3(SF, q, da, 10, occ)
+            return f2.search_projection(SF, q, da, 10.0, 3, occ, None, 0.0, False, TH_LOW)
+        th, orb_dist, ori = {"reloc_orbdist64": (10.0, 64, True), "reloc_orbdist100_noori": (3.0, 100, False)}[name]
+        if hasattr(f2, "search_projection_kf"):
+            return f2.search_projection_kf(SF, q, da, th, orb_dist, occ, ori)
+        return f2.search_projection(SF, q, da, th, 0, occ, None, 0.0, ori, orb_dist)
+    if name.startswith("fuse"):
+        # Fuse (:825 with the chi-square gate, :977 without): the keyframe has no map points, so "fused into keypoint k"
+        # is all the reference does with a hit; the GPU / oracle side returns the closest keypoint and its distance
+        chi2, stereo, th = {"fuse_mono": (True, False, 3.0), "fuse_stereo": (True, True, 3.0), "fuse_scw": (False, False, 4.0)}[name]
+        bf = 40.0 if stereo else 0.0
+        q = np.zeros(n1, BEST)
+        q["u"] = (ka["x"] + dx + rng.normal(0, 1.0, n1)).astype(np.float32)
+        q["v"] = (ka["y"] + dy + rng.normal(0, 1.0, n1)).astype(np.float32)
+        q["level"] = np.clip(ka["octave"] + rng.integers(0, 2, n1), 0, 7)
+        q["radius"] = np.float32(th) * SF[q["level"]]
+        q["ur"] = q["u"] - np.float32(bf)
+        q["valid"] = rng.random(n1) < 0.85
+        inv_s2 = (1.0 / (SF * SF)).astype(np.float32)
+        ur = np.where(rng.random(n2) < 0.5, kb["x"] - bf + rng.normal(0, 1.0, n2), -1).astype(np.float32) if stereo else None
+        if hasattr(f2, "fuse"):
+            return f2.fuse(SF, inv_s2, q, da, th, ur, bf, not chi2)
+        bi, bd = f2.search_best(q, da, chi2, ur, inv_s2)
+        fused = np.where(bd <= TH_LOW, bi, -1).astype(np.int32)
+        return int((fused >= 0).sum()), fused
+    if name == "sim3":
+        # SearchBySim3 (:1102) with the identity Sim3: the points of each keyframe project into the other one at (u, v)
+        th = 7.5
+        uv1 = np.stack([ka["x"] + dx + rng.normal(0, 1.0, n1), ka["y"] + dy + rng.normal(0, 1.0, n1)], 1).astype(np.float32)
+        uv2 = np.stack([kb["x"] - dx + rng.normal(0, 1.0, n2), kb["y"] - dy + rng.normal(0, 1.0, n2)], 1).astype(np.float32)
+        l1 = np.clip(ka["octave"] + rng.integers(0, 2, n1), 0, 7).astype(np.int32)
+        l2 = np.clip(kb["octave"] + rng.integers(0, 2, n2), 0, 7).astype(np.int32)
+        has1 = (rng.random(n1) < 0.8).astype(np.uint8)
+        has2 = (rng.random(n2) < 0.8).astype(np.uint8)
+        if hasattr(f1, "search_sim3"):
+            return f1.search_sim3(f2, SF, SF, uv1, l1, has1, uv2, l2, has2, th)
+
+        def direction(frame, uv, lev, has, qdesc):
+            q = np.zeros(len(uv), BEST)
+            q["u"], q["v"], q["level"], q["valid"] = uv[:, 0], uv[:, 1], lev, has
+            q["radius"] = np.float32(th) * SF[lev]
+            bi, bd = frame.search_best(q, qdesc, False, None, None)
+            return np.where((bd <= TH_HIGH) & (has != 0), bi, -1)
+        v1 = direction(f2, uv1, l1, has1, da)        # points of keyframe 1 searched in keyframe 2 (:1141-1219)
+        v2 = direction(f1, uv2, l2, has2, db)        # and the other way round (:1222-1299)
+        m12 = np.full(n1, -1, np.int32)
+        for i1 in range(n1):                           # mutual agreement (:1302-1318)
+            if v1[i1] >= 0 and v2[v1[i1]] == i1:
+                m12[i1] = v1[i1]
+        return int((m12 >= 0).sum()), m12
     raise KeyError(name)
 
 
@@ -111,10 +178,15 @@ class GpuFrame:
     def search_init(self, other, prev_xy, window=100, ratio=0.9, check_ori=True):
         return self.m.search_for_initialization(self.f, other.f, prev_xy, window, ratio, check_ori)
 
-    def search_projection(self, sf, q, qdesc, th, mode=0, occupied=None, u_right=None, mbf=0.0, check_ori=True):
+    def search_projection(self, sf, q, qdesc, th, mode=0, occupied=None, u_right=None, mbf=0.0, check_ori=True,
+                          max_distance=100):
         import orbb200
         return self.m.search_by_projection(self.f, sf, q.view(orbb200.PROJ_QUERY_DTYPE), qdesc, th, mode, occupied, u_right,
-                                           mbf, check_ori)
+                                           mbf, check_ori, max_distance)
+
+    def search_best(self, q, qdesc, chi2=False, u_right=None, inv_sigma2=None):
+        import orbb200
+        return self.m.search_projected_best(self.f, q.view(orbb200.BEST_QUERY_DTYPE), qdesc, chi2, u_right, inv_sigma2)
 
     def search_points(self, sf, q, qdesc, th, ratio, occupied=None, u_right=None):
         import orbb200

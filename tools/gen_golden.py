@@ -92,7 +92,7 @@ def main():
     np.savez_compressed(os.path.join(OUT, "matcher_vectors.npz"), ka=ka, da=da, kb=kb, db=db, bounds=np.array(bounds),
                         init_n=n, init_m12=m12, init_prev=p, grid_start=gs, grid_idx=gi,
                         bf_q=q, bf_qa=qa, bf_t=t, bf_ta=ta, bf_n=bn, bf_best=best, bf_second=second, bf_idx=idx, bf_m12=bm12,
-                        pinned_by="oracle (ORBmatcher.cc cannot be compiled here)")
+                        pinned_by="oracle (grid CSR and brute force; the search loops are in matcher_ref_vectors.npz)")
     print("matcher vectors: init", n, "bruteforce", bn)
     # ---- matcher vectors from the reference's own ORBmatcher.cc
     import ref_matcher
