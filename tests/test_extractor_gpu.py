@@ -83,6 +83,34 @@ def test_other_constructor_arguments(oracle, nf, scale, nlevels, ini, mn, w, h):
     ex.close()
 
 
+def test_size_sweep(oracle):
+    """Odd image sizes and aspect ratios: FAST cells of every width modulo 4 and height parity, level widths that are
+    not multiples of 4 or 16 (pyramid / blur column groups that straddle the border), tall and wide images, a contrast
+    so low that most cells fall back to minThFAST, and a cell size near the 60-px maximum."""
+    rng = np.random.default_rng(2024)
+    sizes = [(97, 131), (131, 97), (255, 257), (331, 203), (402, 119), (260, 402), (513, 383), (640, 367), (89, 89),
+             (178, 119)]   # 178x119 -> 59-px cells on level 0
+    for i, (w, h) in enumerate(sizes):
+        img = synth_frame(700 + i, w, h)
+        if i % 3 == 1:
+            img = (img.astype(np.int32) // 6 + 100).astype(np.uint8)      # low contrast: threshold fallback everywhere
+        nf = int(rng.integers(50, 600))
+        nlev = min(8, int(np.log(min(w, h) / 63.0) / np.log(1.2)) + 1)    # the top level must stay >= 62 px
+        ex = orbb200.Extractor(nf, 1.2, nlev, 20, 7, max_width=w, max_height=h)
+        oe = oracle.extractor(nf, 1.2, nlev, 20, 7)
+        kps, desc = ex(img)
+        rk, rd = oe.extract(img)
+        for l in range(nlev):
+            assert np.array_equal(ex.level(l), oe.level_padded(l)), (w, h, "pyramid level %d" % l)
+            rb = oe.level_blurred(l)
+            if rb is not None:
+                assert np.array_equal(ex.blurred(l), rb), (w, h, "blur level %d" % l)
+            assert ex.candidates(l).tobytes() == oe.level_candidates(l).tobytes(), (w, h, "FAST candidates level %d" % l)
+        assert kps.tobytes() == rk.tobytes(), (w, h)
+        assert np.array_equal(desc, rd), (w, h)
+        ex.close()
+
+
 def test_batch_equals_single_and_oracle(oracle):
     frames = np.stack([synth_frame(100 + i, 752, 480) for i in range(5)] + [synth_frame(200, 752, 480, noise_only=True)])
     ex = orbb200.Extractor(1000, max_width=752, max_height=480, max_batch=4)   # 6 frames -> chunks of 4 + 2
