@@ -122,6 +122,63 @@ def cpu_reference(frames, procs, seconds_budget, native=True):
             "sample": "%d extractions of synthetic 752x480 frames through oracle/liborb_oracle.so" % n}
 
 
+def cpu_matcher_reference():
+    """CPU side of the matcher numbers (part of the cpu_baseline leg): the reference's own ORBmatcher.cc
+    (oracle/_ref/libmatch_ref.so, built with the parity flags -O2) on the inputs of the latency leg, one core, search call
+    only; plus the oracle's brute-force loop (ORBmatcher.cc:432-461 restated) on one 2000x2000 pair."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    from orbb200.synth import shifted_pair
+    from oracle_py import Oracle
+    out = {"cores": 1}
+    o = Oracle()
+    rng = np.random.default_rng(7)
+    q = rng.integers(0, 256, (2000, 32), dtype=np.uint8)
+    t = rng.integers(0, 256, (2000, 32), dtype=np.uint8)
+    qa = (rng.random(2000) * 360).astype(np.float32)
+    ta = (rng.random(2000) * 360).astype(np.float32)
+    t0 = time.perf_counter()
+    reps = 0
+    while time.perf_counter() - t0 < 1.5:
+        o.bruteforce(q, qa, t, ta, 0.9, True)
+        reps += 1
+    out["bruteforce_compares_per_s"] = reps * 2000 * 2000 / (time.perf_counter() - t0)
+    out["bruteforce_kind"] = "port (oracle/match_oracle.cpp, SWAR popcount as ORBmatcher.cc:1675-1691)"
+    try:
+        import ref_matcher
+        if ref_matcher.available():
+            rm = ref_matcher.RefMatcher()
+            rm.lib.refm_last_search_ms.restype = __import__("ctypes").c_double
+            sf = np.array([1.2 ** i for i in range(8)], np.float32)
+            for name, (w, h) in (("euroc_752x480", (752, 480)), ("kitti_1241x376", (1241, 376))):
+                a, b = shifted_pair(3, w, h)
+                oe = o.extractor(2000, SCALE, NLEVELS, INI_TH, MIN_TH)
+                ka, da = oe.extract(a)
+                kb, db = oe.extract(b)
+                bounds = (0.0, 0.0, float(w), float(h))
+                f1, f2 = rm.frame(ka, da, bounds), rm.frame(kb, db, bounds)
+                ts = []
+                if name.startswith("euroc"):
+                    prev = np.stack([ka["x"], ka["y"]], 1).astype(np.float32)
+                    for _ in range(7):
+                        f1.search_init(f2, prev, 100, 0.9, True)
+                        ts.append(rm.lib.refm_last_search_ms())
+                    out["search_for_initialization_ms"] = float(np.median(ts))
+                else:
+                    from oracle_py import PROJ_QUERY_DTYPE
+                    pq = np.zeros(len(ka), PROJ_QUERY_DTYPE)
+                    pq["u"], pq["v"], pq["invz"], pq["octave"], pq["valid"], pq["obsPositive"], pq["angle"] = \
+                        ka["x"] + 7, ka["y"] + 3, 1.0, ka["octave"], 1, 1, ka["angle"]
+                    for _ in range(7):
+                        f2.search_projection(sf, pq, da, 15.0, 0, None, None, 0.0, True)
+                        ts.append(rm.lib.refm_last_search_ms())
+                    out["search_by_projection_th15_ms"] = float(np.median(ts))
+            out["search_kind"] = "reference (ORBmatcher.cc compiled in place, -O2; time of the search call alone)"
+    except Exception as ex:  # the .so may be missing on a box that never saw /root/reference
+        out["search_kind"] = "unavailable: %s" % ex
+    return out
+
+
 def single_frame_latency(device, iters=30):
     """configs[0]: one 752x480 frame, ORBextractor(2000, ...) as the initialiser uses (Tracking.cc:822) + SearchForInitialization
     against the same scene shifted by (+7,+3); configs[1]: one 1241x376 frame, 2000 features + SearchByProjection(th=15).
@@ -398,6 +455,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu:
         frames = [h_images[i].numpy().copy() for i in range(4)]
         line["cpu_baseline"] = cpu_reference(frames, 1, seconds_budget=12.0)
+        line["cpu_baseline"]["matcher"] = cpu_matcher_reference()
     if rank == 0:
         print(json.dumps(line))
     ex.close()

@@ -5,6 +5,8 @@
 // identical outputs.  The searches whose inputs the C ABI takes as already-projected coordinates are driven with an
 // identity camera (R = I, t = 0, fx = fy = 1, cx = cy = 0, depth 1), for which the reference's own projection arithmetic
 // returns the given coordinates bit for bit.
+#include <chrono>
+
 #include "slam_shim.hpp"
 
 using namespace std;   // the reference's headers lean on a using-directive leaked by the headers replaced here
@@ -14,6 +16,13 @@ using namespace std;   // the reference's headers lean on a using-directive leak
 using namespace ORB_SLAM2;
 
 namespace {
+
+// wall time of the reference's search call alone (the stand-in objects are built outside of it)
+double g_last_search_ms = 0;
+struct SearchTimer {
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    ~SearchTimer() { g_last_search_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
+};
 
 struct RefFrame {
     std::vector<cv::KeyPoint> keys;
@@ -62,6 +71,7 @@ void* refm_frame_create(const cv::KeyPoint* keysUn, const uint8_t* desc, int n, 
     return f;
 }
 void refm_frame_destroy(void* f) { delete (RefFrame*)f; }
+double refm_last_search_ms() { return g_last_search_ms; }
 
 // ORBmatcher::SearchForInitialization  (ORBmatcher.cc:405)
 int refm_search_init(void* f1, void* f2, float* prevXY, int* m12, int window, float ratio, int checkOri) {
@@ -72,7 +82,8 @@ int refm_search_init(void* f1, void* f2, float* prevXY, int* m12, int window, fl
     for (int i = 0; i < F1.N; ++i) prev[i] = cv::Point2f(prevXY[2 * i], prevXY[2 * i + 1]);
     std::vector<int> v12;
     ORBmatcher m(ratio, checkOri != 0);
-    const int n = m.SearchForInitialization(F1, F2, prev, v12, window);
+    int n;
+    { SearchTimer timer; n = m.SearchForInitialization(F1, F2, prev, v12, window); }
     for (int i = 0; i < F1.N; ++i) { m12[i] = v12[i]; prevXY[2 * i] = prev[i].x; prevXY[2 * i + 1] = prev[i].y; }
     return n;
 }
@@ -111,7 +122,8 @@ int refm_search_projection(void* cur, const float* sf, int nLevels, const float*
     // tlc = Rlw * twc + tlw decides forward / backward against CurrentFrame.mb (:1361-1364)
     L.mTcw.at<float>(2, 3) = mode == 1 ? 2.f : mode == 2 ? -2.f : 0.f;
     ORBmatcher m(0.9f, checkOri != 0);
-    const int n = m.SearchByProjection(C, L, th, false);
+    int n;
+    { SearchTimer timer; n = m.SearchByProjection(C, L, th, false); }
     for (int i = 0; i < C.N; ++i) curMatch[i] = index_of(C.mvpMapPoints[i], mp);
     return n;
 }
@@ -140,7 +152,8 @@ int refm_search_points(void* Fp, const float* sf, int nLevels, const float* uRig
         vp[i] = &mp[i];
     }
     ORBmatcher m(ratio, true);
-    const int n = m.SearchByProjection(F, vp, th);
+    int n;
+    { SearchTimer timer; n = m.SearchByProjection(F, vp, th); }
     for (int i = 0; i < F.N; ++i) match[i] = index_of(F.mvpMapPoints[i], mp);
     return n;
 }
@@ -169,7 +182,8 @@ int refm_search_triangulation(void* k1, void* k2, int nNodes1, const int* nodeId
     for (int i = 0; i < 9; ++i) F.at<float>(i / 3, i % 3) = F12[i];
     std::vector<std::pair<size_t, size_t> > pairs;
     ORBmatcher m(0.6f, checkOri != 0);
-    const int n = m.SearchForTriangulation(&K1, &K2, F, pairs, onlyStereo != 0);
+    int n;
+    { SearchTimer timer; n = m.SearchForTriangulation(&K1, &K2, F, pairs, onlyStereo != 0); }
     for (int i = 0; i < K1.N; ++i) m12[i] = -1;
     for (size_t i = 0; i < pairs.size(); ++i) m12[pairs[i].first] = (int)pairs[i].second;
     return n;
@@ -194,7 +208,7 @@ int refm_search_bow(void* k1, void* k2, int nNodes1, const int* nodeId1, const i
         fill(F2, (RefFrame*)k2);
         set_featvec(F2.mFeatVec, nNodes2, nodeId2, start2, idx2);
         std::vector<MapPoint*> found;
-        n = m.SearchByBoW(&K1, F2, found);
+        { SearchTimer timer; n = m.SearchByBoW(&K1, F2, found); }
         for (int i = 0; i < K1.N; ++i) m12[i] = -1;
         for (int i2 = 0; i2 < F2.N; ++i2) {
             m21[i2] = index_of(found[i2], mp1);
@@ -209,7 +223,7 @@ int refm_search_bow(void* k1, void* k2, int nNodes1, const int* nodeId1, const i
         for (int i = 0; i < K2.N; ++i)
             if (!valid2 || valid2[i]) K2.mvpMapPoints[i] = &mp2[i];
         std::vector<MapPoint*> found;
-        n = m.SearchByBoW(&K1, &K2, found);
+        { SearchTimer timer; n = m.SearchByBoW(&K1, &K2, found); }
         for (int i = 0; i < K2.N; ++i) m21[i] = -1;
         for (int i1 = 0; i1 < K1.N; ++i1) {
             m12[i1] = index_of(found[i1], mp2);
@@ -245,7 +259,8 @@ int refm_search_projection_kf(void* cur, const float* sf, int nLevels, const orb
     }
     std::set<MapPoint*> none;
     ORBmatcher m(0.9f, checkOri != 0);
-    const int n = m.SearchByProjection(C, &K, none, th, orbDist);
+    int n;
+    { SearchTimer timer; n = m.SearchByProjection(C, &K, none, th, orbDist); }
     for (int i = 0; i < C.N; ++i) curMatch[i] = index_of(C.mvpMapPoints[i], mp);
     return n;
 }
@@ -272,7 +287,8 @@ int refm_search_projection_sim3(void* kf, const float* sf, int nLevels, const or
         vp[i] = &mp[i];
     }
     ORBmatcher m(0.75f, true);
-    const int n = m.SearchByProjection(&K, cv::Mat::eye(4, 4, CV_32F), vp, vpMatched, th);
+    int n;
+    { SearchTimer timer; n = m.SearchByProjection(&K, cv::Mat::eye(4, 4, CV_32F), vp, vpMatched, th); }
     for (int i = 0; i < K.N; ++i) match[i] = index_of(vpMatched[i], mp);
     return n;
 }
@@ -302,10 +318,10 @@ int refm_fuse(void* kf, const float* sf, const float* invSigma2, int nLevels, co
     ORBmatcher m(0.6f, true);
     int n;
     if (!scw) {
-        n = m.Fuse(&K, vp, th);
+        { SearchTimer timer; n = m.Fuse(&K, vp, th); }
     } else {
         std::vector<MapPoint*> repl(nq, (MapPoint*)NULL);
-        n = m.Fuse(&K, cv::Mat::eye(4, 4, CV_32F), vp, th, repl);
+        { SearchTimer timer; n = m.Fuse(&K, cv::Mat::eye(4, 4, CV_32F), vp, th, repl); }
     }
     for (int i = 0; i < nq; ++i) fusedIdx[i] = mp[i].added.empty() ? -1 : (int)mp[i].added[0].second;
     return n;
@@ -337,7 +353,8 @@ int refm_search_sim3(void* k1, void* k2, const float* sf1, const float* sf2, int
     }
     std::vector<MapPoint*> v12(K1.N, (MapPoint*)NULL);
     ORBmatcher m(0.75f, true);
-    const int n = m.SearchBySim3(&K1, &K2, v12, 1.f, cv::Mat::eye(3, 3, CV_32F), cv::Mat(3, 1, CV_32F), th);
+    int n;
+    { SearchTimer timer; n = m.SearchBySim3(&K1, &K2, v12, 1.f, cv::Mat::eye(3, 3, CV_32F), cv::Mat(3, 1, CV_32F), th); }
     for (int i = 0; i < K1.N; ++i) m12[i] = index_of(v12[i], mp2);
     return n;
 }
