@@ -359,6 +359,16 @@ def main():
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = world * B * e2e_steps / e2e_s
+    # what the link alone gives: the same pinned input copied with nothing else running (context for the e2e number)
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    d_images.copy_(h_images, non_blocking=True)
+    torch.cuda.synchronize()
+    c0.record()
+    for _ in range(3):
+        d_images.copy_(h_images, non_blocking=True)
+    c1.record()
+    torch.cuda.synchronize()
+    h2d_gbs = 3 * B * W * H / (c0.elapsed_time(c1) * 1e-3) / 1e9
     e2e_launches = ex.launch_count() * e2e_steps
 
     line = None
@@ -392,7 +402,8 @@ def main():
                        "keypoints_per_frame": nkp},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": B * W * H,
-                    "d2h_bytes_per_step": B * (cap * 60 + 4), "steps": e2e_steps},
+                    "d2h_bytes_per_step": B * (cap * 60 + 4), "steps": e2e_steps,
+                    "h2d_gbs_in_e2e": e2e_value / world * W * H / 1e9, "h2d_gbs_link_alone": h2d_gbs},
             "gpu_launches": launches_per_step * K,
             "roofline": {"bound": "hbm", "kernel": dom_bw, "achieved": ach, "peak": hbm, "unit": "GB/s",
                          "frac": ach / hbm, "traffic": traffic,
