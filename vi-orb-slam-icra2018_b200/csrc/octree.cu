@@ -101,7 +101,7 @@ octree_kernel(const __grid_constant__ ExtractParams P, int nodeCap, int cellCap,
     extern __shared__ __align__(16) unsigned char sm[];
     __shared__ int scanTmp[OT_WARPS + 1];
     __shared__ int ctl[8];   // 0: nToExpand, 1: cut, 2: scratch
-    const int level = blockIdx.x, frame = blockIdx.y;
+    const int frame = blockIdx.x, level = blockIdx.y;   // level-major dispatch: the long level-0 CTAs of all frames start first
     const LevelGeom& L = P.lv[level];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int* selCountOut = P.selCount + (size_t)frame * P.nLevels + level;
@@ -326,7 +326,7 @@ int launch_octree(const ExtractParams& P, int smemBytes, int keyCapSmem, int nod
                   int* launches) {
     // per device and cheap; set every time so that handles on different GPUs of one process all get it
     ORB_CUDA(cudaFuncSetAttribute(octree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smemBytes));
-    dim3 grid(P.nLevels, P.nFrames);
+    dim3 grid(P.nFrames, P.nLevels);
     octree_kernel<<<grid, OT_THREADS, smemBytes, st>>>(P, nodeCap, cellCap, keyCapSmem);
     ++*launches;
     ORB_CUDA(cudaGetLastError());
