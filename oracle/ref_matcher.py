@@ -11,6 +11,7 @@ from oracle_py import KP_DTYPE, MP_QUERY_DTYPE, PROJ_QUERY_DTYPE
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "_ref", "libmatch_ref.so")
+ADAPTER_LIB = os.path.join(HERE, "_ref", "libmatch_adapter.so")   # same entry points (adpm_*), ORBmatcher = the CUDA adapter
 
 
 def build():
@@ -23,6 +24,10 @@ def available():
     return os.path.exists(LIB)
 
 
+def adapter_available():
+    return os.path.exists(ADAPTER_LIB)
+
+
 def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
@@ -30,9 +35,20 @@ def _p(a):
 vp, i32, f32 = C.c_void_p, C.c_int, C.c_float
 
 
+class _Prefixed:
+    """lib.refm_x -> getattr(lib, prefix + x): the two libraries export the same functions under different prefixes."""
+
+    def __init__(self, lib, prefix):
+        object.__setattr__(self, "_lib", lib)
+        object.__setattr__(self, "_prefix", prefix)
+
+    def __getattr__(self, name):
+        return getattr(self._lib, self._prefix + name[len("refm_"):] if name.startswith("refm_") else name)
+
+
 class RefMatcher:
-    def __init__(self):
-        self.lib = L = C.CDLL(LIB)
+    def __init__(self, adapter=False):
+        self.lib = L = _Prefixed(C.CDLL(ADAPTER_LIB if adapter else LIB), "adpm_" if adapter else "refm_")
         L.refm_distance.argtypes = [vp, vp]
         L.refm_frame_create.restype = vp
         L.refm_frame_create.argtypes = [vp, vp, i32, f32, f32, f32, f32]

@@ -49,6 +49,8 @@ public:
     int type() const { return type_; }
     template <class T> T* ptr(int r = 0) { return reinterpret_cast<T*>(buf_->data() + off_ + (size_t)r * step_); }
     template <class T> const T* ptr(int r = 0) const { return reinterpret_cast<const T*>(buf_->data() + off_ + (size_t)r * step_); }
+    uchar* ptr(int r = 0) { return ptr<uchar>(r); }
+    const uchar* ptr(int r = 0) const { return ptr<uchar>(r); }
     template <class T> T& at(int r, int c) { return ptr<T>(r)[c]; }
     template <class T> const T& at(int r, int c) const { return ptr<T>(r)[c]; }
     template <class T> T& at(int i) { return rows == 1 ? ptr<T>(0)[i] : ptr<T>(i)[0]; }

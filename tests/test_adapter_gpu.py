@@ -34,3 +34,29 @@ def test_adapter_matches_c_abi(tmp_path, matcher):
     assert int(n_match) == n
     assert int(out.stdout.split("\n")[1]) == int(matcher.distance(desc[0], desc[1])[0])
     ex.close()
+
+
+def test_reference_signatures_on_object_graphs():
+    """The adapter's reference-signature overloads (adapter/ORBmatcher.h + ORBmatcher_orbslam.inl: what a maintainer
+    compiles instead of ORBmatcher.cc) run on Frame / KeyFrame / MapPoint object graphs -- the stand-ins of
+    oracle/ref_shim/matcher, prebuilt into oracle/_ref/libmatch_adapter.so where /root/reference is mounted -- and must
+    reproduce what the reference's OWN ORBmatcher.cc produced on the same graphs (tests/golden/matcher_ref_vectors.npz,
+    and the live libmatch_ref.so when it is there): every search, match for match."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_matcher
+    from matcher_cases import run_case, same
+    if not ref_matcher.adapter_available():
+        pytest.skip("oracle/_ref/libmatch_adapter.so is built only where /root/reference is mounted (DBoW2's FeatureVector)")
+    gold = os.path.join(ROOT, "tests", "golden")
+    g = np.load(os.path.join(gold, "matcher_vectors.npz"))
+    r = np.load(os.path.join(gold, "matcher_ref_vectors.npz"))
+    ka, da, kb, db, bounds = g["ka"], g["da"], g["kb"], g["db"], g["bounds"]
+    ad = ref_matcher.RefMatcher(adapter=True)
+    a1, a2 = ad.frame(ka, da, bounds), ad.frame(kb, db, bounds)
+    live = ref_matcher.RefMatcher() if ref_matcher.available() else None
+    for c in [str(x) for x in r["cases"]]:
+        got = run_case(c, a1, a2, ka, da, kb, db)
+        same(got, [r["%s__%d" % (c, j)] for j in range(len(got))])
+        if live:
+            same(got, run_case(c, live.frame(ka, da, bounds), live.frame(kb, db, bounds), ka, da, kb, db))

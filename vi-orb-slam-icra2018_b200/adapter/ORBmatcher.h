@@ -9,6 +9,7 @@
 #ifndef ORBB200_ADAPTER_ORBMATCHER_H
 #define ORBB200_ADAPTER_ORBMATCHER_H
 
+#include <set>
 #include <stdexcept>
 #include <string>
 #include <utility>
@@ -30,6 +31,7 @@ public:
     ~FrameView() { orbm_frame_destroy(f_); }
     FrameView(const FrameView&) = delete;
     FrameView& operator=(const FrameView&) = delete;
+    FrameView(FrameView&& o) : f_(o.f_), n_(o.n_) { o.f_ = nullptr; }
     orbm_frame get() const { return f_; }
     int size() const { return n_; }
 
@@ -167,6 +169,17 @@ public:
     int SearchByProjection(Frame& F, const std::vector<MapPoint*>& vpMapPoints, const float th = 3);
     int SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, cv::Mat F12, std::vector<std::pair<size_t, size_t> >& vMatchedPairs,
                                const bool bOnlyStereo);
+    int SearchByBoW(KeyFrame* pKF, Frame& F, std::vector<MapPoint*>& vpMapPointMatches);
+    int SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<MapPoint*>& vpMatches12);
+    int SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, const std::set<MapPoint*>& sAlreadyFound, const float th,
+                           const int ORBdist);
+    int SearchByProjection(KeyFrame* pKF, cv::Mat Scw, const std::vector<MapPoint*>& vpPoints, std::vector<MapPoint*>& vpMatched,
+                           int th);
+    int Fuse(KeyFrame* pKF, const std::vector<MapPoint*>& vpMapPoints, const float th = 3.0);
+    int Fuse(KeyFrame* pKF, cv::Mat Scw, const std::vector<MapPoint*>& vpPoints, float th, std::vector<MapPoint*>& vpReplacePoint);
+    int SearchBySim3(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<MapPoint*>& vpMatches12, const float& s12, const cv::Mat& R12,
+                     const cv::Mat& t12, const float th);
+    static int DescriptorDistance(const cv::Mat& a, const cv::Mat& b);
 #endif
 
 protected:

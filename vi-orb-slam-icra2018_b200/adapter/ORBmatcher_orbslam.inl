@@ -1,8 +1,10 @@
 // Definitions of the reference-signature overloads of ORB_SLAM2::ORBmatcher (declared in adapter/ORBmatcher.h under
 // ORBB200_WITH_ORBSLAM).  Include this file from ONE translation unit of the host project after Frame.h, KeyFrame.h and
-// MapPoint.h.  It is NOT compiled in this repository (those headers need OpenCV, Eigen, DBoW2 and g2o, none of which is
-// installed here); each function states which reference lines it stands in for, and INTEGRATION.md section 3 lists what
-// is read from and written back to the objects.  Everything between "flatten" and "write back" runs on the GPU.
+// MapPoint.h.  The host project's own headers need OpenCV, Eigen, DBoW2 and g2o, none of which is installed here; in this
+// repository the file is compiled and run against the stand-ins of oracle/ref_shim/matcher (test infrastructure) and
+// compared with the reference's own ORBmatcher.cc on the same object graphs (tests/test_adapter_gpu.py).  Each function
+// states which reference lines it stands in for; INTEGRATION.md section 3 lists what is read from and written back to the
+// objects.  Everything between "flatten" and "write back" runs on the GPU.
 #ifdef ORBB200_WITH_ORBSLAM
 
 namespace ORB_SLAM2 {
@@ -24,7 +26,51 @@ template <class F> inline FrameView view_of(orbm_handle h, const F& f) {
                      f.mnMaxX, f.mnMaxY);
 }
 
+inline ORBmatcher::FeatureVectorCSR flatten(const DBoW2::FeatureVector& fv) {
+    ORBmatcher::FeatureVectorCSR c;
+    c.start.push_back(0);
+    for (DBoW2::FeatureVector::const_iterator it = fv.begin(); it != fv.end(); ++it) {   // std::map: ascending node ids
+        c.nodeId.push_back((int)it->first);
+        for (size_t k = 0; k < it->second.size(); ++k) c.idx.push_back((int)it->second[k]);
+        c.start.push_back((int)c.idx.size());
+    }
+    return c;
+}
+
+// A map point carried into a keyframe's image the way Fuse / SearchBySim3 / SearchByProjection(KF, Scw) do it on the
+// host (e.g. ORBmatcher.cc:853-890): p = R*X + t, positive depth, u = fx*(x/z) + cx, inside the image, distance inside the
+// point's scale-invariance range, optionally the 60-degree viewing-angle gate.  `floatReciprocal` keeps the one spelling
+// difference between the overloads (1/z in float at :861 and :331, 1.0/z in double elsewhere).
+struct Projected { bool ok; float u, v, invz, dist; };
+template <class KF>
+inline Projected project_into(MapPoint* pMP, const cv::Mat& X, const cv::Mat& p3Dc, const cv::Mat& PO, KF* kf, bool angleGate,
+                              bool floatReciprocal) {
+    Projected r = {false, 0.f, 0.f, 0.f, 0.f};
+    if (p3Dc.at<float>(2) < 0.0f) return r;
+    const float invz = floatReciprocal ? 1 / p3Dc.at<float>(2) : (float)(1.0 / p3Dc.at<float>(2));
+    const float x = p3Dc.at<float>(0) * invz, y = p3Dc.at<float>(1) * invz;
+    r.u = kf->fx * x + kf->cx;
+    r.v = kf->fy * y + kf->cy;
+    r.invz = invz;
+    if (!kf->IsInImage(r.u, r.v)) return r;
+    r.dist = cv::norm(PO);
+    if (r.dist < pMP->GetMinDistanceInvariance() || r.dist > pMP->GetMaxDistanceInvariance()) return r;
+    if (angleGate && PO.dot(pMP->GetNormal()) < 0.5 * r.dist) return r;
+    (void)X;
+    r.ok = true;
+    return r;
+}
+
 }  // namespace orbb_detail
+
+// ORBmatcher.cc:1675-1691. One pair is host work; batches go through DescriptorDistances().
+inline int ORBmatcher::DescriptorDistance(const cv::Mat& a, const cv::Mat& b) {
+    const unsigned int* pa = a.ptr<unsigned int>();
+    const unsigned int* pb = b.ptr<unsigned int>();
+    int dist = 0;
+    for (int i = 0; i < 8; ++i) dist += __builtin_popcount(pa[i] ^ pb[i]);
+    return dist;
+}
 
 // ORBmatcher.cc:405-520
 inline int ORBmatcher::SearchForInitialization(Frame& F1, Frame& F2, std::vector<cv::Point2f>& vbPrevMatched,
@@ -114,17 +160,7 @@ inline int ORBmatcher::SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, cv
     const float invz = 1.0f / C2.at<float>(2);
     const float ex = pKF2->fx * C2.at<float>(0) * invz + pKF2->cx;   // :668-670
     const float ey = pKF2->fy * C2.at<float>(1) * invz + pKF2->cy;
-    auto flatten = [](const DBoW2::FeatureVector& fv) {
-        FeatureVectorCSR c;
-        c.start.push_back(0);
-        for (DBoW2::FeatureVector::const_iterator it = fv.begin(); it != fv.end(); ++it) {   // std::map: ascending node ids
-            c.nodeId.push_back((int)it->first);
-            for (size_t k = 0; k < it->second.size(); ++k) c.idx.push_back((int)it->second[k]);
-            c.start.push_back((int)c.idx.size());
-        }
-        return c;
-    };
-    const FeatureVectorCSR fv1 = flatten(pKF1->mFeatVec), fv2 = flatten(pKF2->mFeatVec);
+    const FeatureVectorCSR fv1 = orbb_detail::flatten(pKF1->mFeatVec), fv2 = orbb_detail::flatten(pKF2->mFeatVec);
     std::vector<unsigned char> has1(pKF1->N), has2(pKF2->N);
     for (int i = 0; i < pKF1->N; ++i) has1[i] = pKF1->GetMapPoint(i) != NULL;
     for (int i = 0; i < pKF2->N; ++i) has2[i] = pKF2->GetMapPoint(i) != NULL;
@@ -134,6 +170,264 @@ inline int ORBmatcher::SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, cv
     FrameView v1 = orbb_detail::view_of(h_, *pKF1), v2 = orbb_detail::view_of(h_, *pKF2);
     return SearchForTriangulation(v1, v2, fv1, fv2, has1.data(), has2.data(), pKF1->mvuRight.data(), pKF2->mvuRight.data(), f12,
                                   ex, ey, pKF2->mvScaleFactors, pKF2->mvLevelSigma2, vMatchedPairs, bOnlyStereo);
+}
+
+
+// ORBmatcher.cc:159-288
+inline int ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, std::vector<MapPoint*>& vpMapPointMatches) {
+    const std::vector<MapPoint*> vpMapPointsKF = pKF->GetMapPointMatches();
+    vpMapPointMatches = std::vector<MapPoint*>(F.N, static_cast<MapPoint*>(NULL));
+    std::vector<unsigned char> valid1(vpMapPointsKF.size());
+    for (size_t i = 0; i < vpMapPointsKF.size(); ++i) valid1[i] = vpMapPointsKF[i] && !vpMapPointsKF[i]->isBad();
+    FrameView v1 = orbb_detail::view_of(h_, *pKF), v2 = orbb_detail::view_of(h_, F);
+    std::vector<int> m12, m21;
+    const int n = SearchByBoW(v1, v2, orbb_detail::flatten(pKF->mFeatVec), orbb_detail::flatten(F.mFeatVec), valid1.data(), NULL,
+                              false, m12, m21);
+    for (int i2 = 0; i2 < F.N; ++i2)
+        if (m21[i2] >= 0) vpMapPointMatches[i2] = vpMapPointsKF[m21[i2]];   // :229-233
+    return n;
+}
+
+// ORBmatcher.cc:522-655
+inline int ORBmatcher::SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<MapPoint*>& vpMatches12) {
+    const std::vector<MapPoint*> vp1 = pKF1->GetMapPointMatches(), vp2 = pKF2->GetMapPointMatches();
+    vpMatches12 = std::vector<MapPoint*>(vp1.size(), static_cast<MapPoint*>(NULL));
+    std::vector<unsigned char> valid1(vp1.size()), valid2(vp2.size());
+    for (size_t i = 0; i < vp1.size(); ++i) valid1[i] = vp1[i] && !vp1[i]->isBad();
+    for (size_t i = 0; i < vp2.size(); ++i) valid2[i] = vp2[i] && !vp2[i]->isBad();
+    FrameView v1 = orbb_detail::view_of(h_, *pKF1), v2 = orbb_detail::view_of(h_, *pKF2);
+    std::vector<int> m12, m21;
+    const int n = SearchByBoW(v1, v2, orbb_detail::flatten(pKF1->mFeatVec), orbb_detail::flatten(pKF2->mFeatVec), valid1.data(),
+                              valid2.data(), true, m12, m21);
+    for (size_t i1 = 0; i1 < vp1.size(); ++i1)
+        if (m12[i1] >= 0) vpMatches12[i1] = vp2[m12[i1]];   // :600-604
+    return n;
+}
+
+// ORBmatcher.cc:1500-1627 (relocalisation). The level comes from MapPoint::PredictScale, the acceptance bound is ORBdist.
+inline int ORBmatcher::SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, const std::set<MapPoint*>& sAlreadyFound,
+                                          const float th, const int ORBdist) {
+    const cv::Mat Rcw = CurrentFrame.mTcw.rowRange(0, 3).colRange(0, 3);
+    const cv::Mat tcw = CurrentFrame.mTcw.rowRange(0, 3).col(3);
+    const cv::Mat Ow = -Rcw.t() * tcw;
+    const std::vector<MapPoint*> vpMPs = pKF->GetMapPointMatches();
+    std::vector<orbm_proj_query> q(vpMPs.size());
+    std::vector<unsigned char> qdesc(vpMPs.size() * 32, 0);
+    for (size_t i = 0; i < vpMPs.size(); ++i) {
+        orbm_proj_query& a = q[i];
+        a = orbm_proj_query();
+        MapPoint* pMP = vpMPs[i];
+        if (!pMP || pMP->isBad() || sAlreadyFound.count(pMP)) continue;
+        cv::Mat x3Dw = pMP->GetWorldPos();
+        cv::Mat x3Dc = Rcw * x3Dw + tcw;
+        const float xc = x3Dc.at<float>(0), yc = x3Dc.at<float>(1);
+        const float invzc = 1.0 / x3Dc.at<float>(2);
+        a.u = CurrentFrame.fx * xc * invzc + CurrentFrame.cx;     // the image-bounds test (:1535-1538) runs with the query
+        a.v = CurrentFrame.fy * yc * invzc + CurrentFrame.cy;
+        cv::Mat PO = x3Dw - Ow;
+        const float dist3D = cv::norm(PO);
+        if (dist3D < pMP->GetMinDistanceInvariance() || dist3D > pMP->GetMaxDistanceInvariance()) continue;
+        a.invz = 1.f;                                             // no stereo test in this overload
+        a.octave = pMP->PredictScale(dist3D, &CurrentFrame);
+        a.valid = 1;
+        a.obs_positive = 1;                                       // any assigned keypoint is taken afterwards (:1566)
+        a.angle = pKF->mvKeysUn[i].angle;
+        std::memcpy(&qdesc[i * 32], pMP->GetDescriptor().ptr(0), 32);
+    }
+    std::vector<unsigned char> occupied(CurrentFrame.N, 0);
+    for (int i = 0; i < CurrentFrame.N; ++i) occupied[i] = CurrentFrame.mvpMapPoints[i] != NULL;
+    FrameView cur = orbb_detail::view_of(h_, CurrentFrame);
+    std::vector<int> curMatch;
+    const int n = SearchByProjection(cur, CurrentFrame.mvScaleFactors, q, qdesc.data(), th, 0, ORBdist, occupied.data(), curMatch);
+    for (int i2 = 0; i2 < CurrentFrame.N; ++i2)
+        if (curMatch[i2] >= 0) CurrentFrame.mvpMapPoints[i2] = vpMPs[curMatch[i2]];   // :1585
+    return n;
+}
+
+// ORBmatcher.cc:290-403 (loop closing): levels [predicted-1, predicted], bound TH_LOW, no orientation check.
+inline int ORBmatcher::SearchByProjection(KeyFrame* pKF, cv::Mat Scw, const std::vector<MapPoint*>& vpPoints,
+                                          std::vector<MapPoint*>& vpMatched, int th) {
+    cv::Mat sRcw = Scw.rowRange(0, 3).colRange(0, 3);
+    const float scw = sqrt(sRcw.row(0).dot(sRcw.row(0)));
+    cv::Mat Rcw = sRcw / scw;
+    cv::Mat tcw = Scw.rowRange(0, 3).col(3) / scw;
+    cv::Mat Ow = -Rcw.t() * tcw;
+    std::set<MapPoint*> found(vpMatched.begin(), vpMatched.end());
+    found.erase(static_cast<MapPoint*>(NULL));
+    std::vector<orbm_proj_query> q(vpPoints.size());
+    std::vector<unsigned char> qdesc(vpPoints.size() * 32, 0);
+    for (size_t i = 0; i < vpPoints.size(); ++i) {
+        orbm_proj_query& a = q[i];
+        a = orbm_proj_query();
+        MapPoint* pMP = vpPoints[i];
+        if (pMP->isBad() || found.count(pMP)) continue;
+        cv::Mat p3Dw = pMP->GetWorldPos();
+        cv::Mat p3Dc = Rcw * p3Dw + tcw;
+        const orbb_detail::Projected pr = orbb_detail::project_into(pMP, p3Dw, p3Dc, p3Dw - Ow, pKF, true, true);
+        if (!pr.ok) continue;
+        a.u = pr.u; a.v = pr.v; a.invz = 1.f;
+        a.octave = pMP->PredictScale(pr.dist, pKF);
+        a.valid = 1;
+        a.obs_positive = 1;
+        std::memcpy(&qdesc[i * 32], pMP->GetDescriptor().ptr(0), 32);
+    }
+    std::vector<unsigned char> occupied(pKF->N, 0);
+    for (int i = 0; i < pKF->N; ++i) occupied[i] = vpMatched[i] != NULL;
+    FrameView kf = orbb_detail::view_of(h_, *pKF);
+    std::vector<int> match(pKF->N, -1);
+    int n = 0;
+    check(orbm_search_by_projection_ex(h_, kf.get(), pKF->mvScaleFactors.data(), (int)pKF->mvScaleFactors.size(), NULL, 0.f,
+                                       q.data(), qdesc.data(), (int)q.size(), (float)th, 3, TH_LOW, occupied.data(), match.data(),
+                                       0, &n));
+    for (int i = 0; i < pKF->N; ++i)
+        if (match[i] >= 0) vpMatched[i] = vpPoints[match[i]];   // :394-398
+    return n;
+}
+
+// ORBmatcher.cc:825-975. The projected search runs on the GPU; what a hit does to the map stays here, in point order.
+inline int ORBmatcher::Fuse(KeyFrame* pKF, const std::vector<MapPoint*>& vpMapPoints, const float th) {
+    cv::Mat Rcw = pKF->GetRotation(), tcw = pKF->GetTranslation(), Ow = pKF->GetCameraCenter();
+    std::vector<orbm_best_query> q(vpMapPoints.size());
+    std::vector<unsigned char> qdesc(vpMapPoints.size() * 32, 0);
+    for (size_t i = 0; i < vpMapPoints.size(); ++i) {
+        orbm_best_query& a = q[i];
+        a = orbm_best_query();
+        MapPoint* pMP = vpMapPoints[i];
+        if (!pMP || pMP->isBad() || pMP->IsInKeyFrame(pKF)) continue;
+        cv::Mat p3Dw = pMP->GetWorldPos();
+        const orbb_detail::Projected pr = orbb_detail::project_into(pMP, p3Dw, Rcw * p3Dw + tcw, p3Dw - Ow, pKF, true, true);
+        if (!pr.ok) continue;
+        a.u = pr.u; a.v = pr.v;
+        a.ur = pr.u - pKF->mbf * pr.invz;
+        a.level = pMP->PredictScale(pr.dist, pKF);
+        a.radius = th * pKF->mvScaleFactors[a.level];
+        a.valid = 1;
+        std::memcpy(&qdesc[i * 32], pMP->GetDescriptor().ptr(0), 32);
+    }
+    FrameView kf = orbb_detail::view_of(h_, *pKF);
+    std::vector<int> bestIdx, bestDist;
+    ProjectedBest(kf, q, qdesc.data(), true, pKF->mvuRight.data(), pKF->mvInvLevelSigma2, bestIdx, bestDist);
+    int nFused = 0;
+    for (size_t i = 0; i < vpMapPoints.size(); ++i) {
+        if (!q[i].valid || bestIdx[i] < 0 || bestDist[i] > TH_LOW) continue;
+        MapPoint* pMP = vpMapPoints[i];
+        MapPoint* pMPinKF = pKF->GetMapPoint(bestIdx[i]);
+        if (pMPinKF) {                                            // :949-958
+            if (!pMPinKF->isBad()) {
+                if (pMPinKF->Observations() > pMP->Observations()) pMP->Replace(pMPinKF);
+                else pMPinKF->Replace(pMP);
+            }
+        } else {
+            pMP->AddObservation(pKF, bestIdx[i]);
+            pKF->AddMapPoint(pMP, bestIdx[i]);
+        }
+        ++nFused;
+    }
+    return nFused;
+}
+
+// ORBmatcher.cc:977-1099
+inline int ORBmatcher::Fuse(KeyFrame* pKF, cv::Mat Scw, const std::vector<MapPoint*>& vpPoints, float th,
+                            std::vector<MapPoint*>& vpReplacePoint) {
+    cv::Mat sRcw = Scw.rowRange(0, 3).colRange(0, 3);
+    const float scw = sqrt(sRcw.row(0).dot(sRcw.row(0)));
+    cv::Mat Rcw = sRcw / scw;
+    cv::Mat tcw = Scw.rowRange(0, 3).col(3) / scw;
+    cv::Mat Ow = -Rcw.t() * tcw;
+    const std::set<MapPoint*> found = pKF->GetMapPoints();
+    std::vector<orbm_best_query> q(vpPoints.size());
+    std::vector<unsigned char> qdesc(vpPoints.size() * 32, 0);
+    for (size_t i = 0; i < vpPoints.size(); ++i) {
+        orbm_best_query& a = q[i];
+        a = orbm_best_query();
+        MapPoint* pMP = vpPoints[i];
+        if (pMP->isBad() || found.count(pMP)) continue;
+        cv::Mat p3Dw = pMP->GetWorldPos();
+        const orbb_detail::Projected pr = orbb_detail::project_into(pMP, p3Dw, Rcw * p3Dw + tcw, p3Dw - Ow, pKF, true, false);
+        if (!pr.ok) continue;
+        a.u = pr.u; a.v = pr.v; a.ur = -1.f;
+        a.level = pMP->PredictScale(pr.dist, pKF);
+        a.radius = th * pKF->mvScaleFactors[a.level];
+        a.valid = 1;
+        std::memcpy(&qdesc[i * 32], pMP->GetDescriptor().ptr(0), 32);
+    }
+    FrameView kf = orbb_detail::view_of(h_, *pKF);
+    std::vector<int> bestIdx, bestDist;
+    ProjectedBest(kf, q, qdesc.data(), false, NULL, pKF->mvInvLevelSigma2, bestIdx, bestDist);
+    int nFused = 0;
+    for (size_t i = 0; i < vpPoints.size(); ++i) {
+        if (!q[i].valid || bestIdx[i] < 0 || bestDist[i] > TH_LOW) continue;
+        MapPoint* pMPinKF = pKF->GetMapPoint(bestIdx[i]);
+        if (pMPinKF) {                                            // :1082-1086
+            if (!pMPinKF->isBad()) vpReplacePoint[i] = pMPinKF;
+        } else {
+            vpPoints[i]->AddObservation(pKF, bestIdx[i]);
+            pKF->AddMapPoint(vpPoints[i], bestIdx[i]);
+        }
+        ++nFused;
+    }
+    return nFused;
+}
+
+// ORBmatcher.cc:1102-1321: two projected searches (GPU) and the mutual-agreement pass (host).
+inline int ORBmatcher::SearchBySim3(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<MapPoint*>& vpMatches12, const float& s12,
+                                    const cv::Mat& R12, const cv::Mat& t12, const float th) {
+    cv::Mat R1w = pKF1->GetRotation(), t1w = pKF1->GetTranslation();
+    cv::Mat R2w = pKF2->GetRotation(), t2w = pKF2->GetTranslation();
+    cv::Mat sR12 = s12 * R12;
+    cv::Mat sR21 = (1.0 / s12) * R12.t();
+    cv::Mat t21 = -sR21 * t12;
+    const std::vector<MapPoint*> vp1 = pKF1->GetMapPointMatches(), vp2 = pKF2->GetMapPointMatches();
+    const int N1 = (int)vp1.size(), N2 = (int)vp2.size();
+    std::vector<bool> done1(N1, false), done2(N2, false);
+    for (int i = 0; i < N1; ++i) {
+        MapPoint* pMP = vpMatches12[i];
+        if (!pMP) continue;
+        done1[i] = true;
+        const int idx2 = pMP->GetIndexInKeyFrame(pKF2);
+        if (idx2 >= 0 && idx2 < N2) done2[idx2] = true;
+    }
+    // points of `from` carried into `into`: camera coordinates there are A * (Rw * X + tw) + b
+    struct Side {
+        static void queries(const std::vector<MapPoint*>& vp, const std::vector<bool>& done, const cv::Mat& Rw, const cv::Mat& tw,
+                            const cv::Mat& A, const cv::Mat& b, KeyFrame* into, float th, std::vector<orbm_best_query>& q,
+                            std::vector<unsigned char>& qdesc) {
+            q.assign(vp.size(), orbm_best_query());
+            qdesc.assign(vp.size() * 32, 0);
+            for (size_t i = 0; i < vp.size(); ++i) {
+                MapPoint* pMP = vp[i];
+                if (!pMP || done[i] || pMP->isBad()) continue;
+                cv::Mat p3Dw = pMP->GetWorldPos();
+                cv::Mat pOther = A * (Rw * p3Dw + tw) + b;
+                const orbb_detail::Projected pr = orbb_detail::project_into(pMP, p3Dw, pOther, pOther, into, false, false);
+                if (!pr.ok) continue;
+                orbm_best_query& a = q[i];
+                a.u = pr.u; a.v = pr.v; a.ur = -1.f;
+                a.level = pMP->PredictScale(pr.dist, into);
+                a.radius = th * into->mvScaleFactors[a.level];
+                a.valid = 1;
+                std::memcpy(&qdesc[i * 32], pMP->GetDescriptor().ptr(0), 32);
+            }
+        }
+    };
+    std::vector<orbm_best_query> q1, q2;
+    std::vector<unsigned char> d1, d2;
+    Side::queries(vp1, done1, R1w, t1w, sR21, t21, pKF2, th, q1, d1);   // :1141-1219
+    Side::queries(vp2, done2, R2w, t2w, sR12, t12, pKF1, th, q2, d2);   // :1222-1299
+    FrameView v1 = orbb_detail::view_of(h_, *pKF1), v2 = orbb_detail::view_of(h_, *pKF2);
+    std::vector<int> b1, dist1, b2, dist2;
+    ProjectedBest(v2, q1, d1.data(), false, NULL, pKF2->mvInvLevelSigma2, b1, dist1);
+    ProjectedBest(v1, q2, d2.data(), false, NULL, pKF1->mvInvLevelSigma2, b2, dist2);
+    int nFound = 0;
+    for (int i1 = 0; i1 < N1; ++i1) {                              // :1302-1318
+        if (!q1[i1].valid || b1[i1] < 0 || dist1[i1] > TH_HIGH) continue;
+        const int idx2 = b1[i1];
+        if (q2[idx2].valid && b2[idx2] == i1 && dist2[idx2] <= TH_HIGH) {
+            vpMatches12[i1] = vp2[idx2];
+            ++nFound;
+        }
+    }
+    return nFound;
 }
 
 }  // namespace ORB_SLAM2
