@@ -18,6 +18,7 @@ typedef unsigned char uchar;
 
 #define CV_8U 0
 #define CV_8UC1 0
+#define CV_Assert(expr) assert(expr)
 #define CV_PI 3.1415926535897932384626433832795
 
 inline int cvRound(double v) { return orbo::cv_round_d(v); }

@@ -60,3 +60,27 @@ def test_reference_signatures_on_object_graphs():
         same(got, [r["%s__%d" % (c, j)] for j in range(len(got))])
         if live:
             same(got, run_case(c, live.frame(ka, da, bounds), live.frame(kb, db, bounds), ka, da, kb, db))
+
+
+def test_extractor_opencv_signature(tmp_path):
+    """adapter/ORBextractor.h with -DORBB200_WITH_OPENCV, compiled against the OpenCV stand-in the reference's own
+    ORBextractor.cc is built against (oracle/ref_shim/include): operator()(InputArray, InputArray, vector<KeyPoint>&,
+    OutputArray) and the public mvImagePyramid member behave like the reference's (Frame.cc:591-597, 817)."""
+    pkg = os.path.join(ROOT, "vi-orb-slam-icra2018_b200")
+    exe = str(tmp_path / "adapter_opencv_sig")
+    subprocess.check_call(["g++", "-std=c++11", "-O1", "-I", os.path.join(ROOT, "oracle", "ref_shim", "include"),
+                           "-I", os.path.join(pkg, "adapter"), "-o", exe, os.path.join(ROOT, "tests", "adapter_opencv_sig.cpp"),
+                           os.path.join(ROOT, "oracle", "cvprims.cpp"), "-L", pkg, "-lorbb200", "-Wl,-rpath," + pkg])
+    img = synth_frame(0)
+    raw = tmp_path / "img.raw"
+    img.tofile(raw)
+    out = subprocess.run([exe, str(raw), "752", "480"], capture_output=True, text=True)
+    assert out.returncode == 0, (out.returncode, out.stderr)
+    n_kp, checksum, levels = out.stdout.split()
+    ex = orbb200.Extractor(1000)
+    kps, desc = ex(img)
+    s = 0
+    for b in desc.reshape(-1).tolist():
+        s = (s * 131 + b) & 0xFFFFFFFFFFFFFFFF
+    assert int(n_kp) == len(kps) and int(checksum) == s and int(levels) == 8
+    ex.close()
