@@ -40,7 +40,6 @@ struct orbx_extractor {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t streamIn = nullptr, streamOut = nullptr;   // H2D / D2H of the host entry points, overlapped with compute
-    cudaStream_t stream2 = nullptr;                          // second compute stream: odd pipeline chunks, fills kernel tails
     std::vector<cudaEvent_t> pipeEvents;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     // ctor state
@@ -201,7 +200,6 @@ int configure(orbx_extractor* e, int w, int h, int nFrames) {
     P.cells = e->dCells.as<Cell>();
     P.tabOfs = e->dTabOfs.as<int>();
     P.tabCoef = e->dTabCoef.as<short2>();
-    std::memcpy(P.umax, e->umax, sizeof P.umax);
     for (int l = 0; l < nl; ++l) P.lv[l] = lv[l];
     e->cells.swap(cells);
     e->tiles.swap(tiles);
@@ -328,7 +326,6 @@ int orbx_create(int nfeatures, float scaleFactor, int nlevels, int iniTh, int mi
     cudaError_t ce = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
     if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&e->streamIn, cudaStreamNonBlocking);
     if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&e->streamOut, cudaStreamNonBlocking);
-    if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking);
     for (int i = 0; i < 4 && ce == cudaSuccess; ++i) ce = cudaEventCreate(&e->ev[i]);
     if (ce != cudaSuccess) {
         delete e;
@@ -358,7 +355,6 @@ int orbx_destroy(orbx_handle e) {
     for (cudaEvent_t ev : e->pipeEvents) cudaEventDestroy(ev);
     if (e->streamIn) cudaStreamDestroy(e->streamIn);
     if (e->streamOut) cudaStreamDestroy(e->streamOut);
-    if (e->stream2) cudaStreamDestroy(e->stream2);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
     return ORB_OK;
@@ -472,7 +468,6 @@ int orbx_extract_batch(orbx_handle e, const uint8_t* images, int nFrames, int w,
         // the next super-chunk reuses the arena and the staging buffers: drain everything first
         ORB_CUDA(cudaStreamSynchronize(e->streamOut));
         ORB_CUDA(cudaStreamSynchronize(e->stream));
-        ORB_CUDA(cudaStreamSynchronize(e->stream2));
         if (trace && s0 == 0) {
             for (int c = 0; c < k; ++c) {
                 float a = 0, b = 0, d = 0;

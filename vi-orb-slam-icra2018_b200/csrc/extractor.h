@@ -89,7 +89,6 @@ struct ExtractParams {
     const Cell* cells;
     const int* tabOfs;       // resize tables: source index per destination index
     const short2* tabCoef;   // 11-bit coefficient pairs
-    int umax[16];
     LevelGeom lv[kMaxLevels];
 };
 
