@@ -411,6 +411,11 @@ def main():
                          "algorithmic_bytes_per_launch": alg[dom_bw] * B, "launch_ms": per_kernel[dom_bw],
                          "dominant_by_time": dom},
             "kernels_ms_per_step": per_kernel,
+            # every stage against the HBM roofline (north star: pyramid, blur and extraction as fractions of HBM GB/s)
+            "stage_rooflines": {n: {"algorithmic_bytes_per_frame": alg[n], "ms_per_step": per_kernel[n],
+                                    "achieved_gbs": alg[n] * B / (per_kernel[n] * 1e-3) / 1e9,
+                                    "frac_of_hbm": alg[n] * B / (per_kernel[n] * 1e-3) / 1e9 / hbm}
+                                for n in names if alg[n] > 0},
             "extract_roofline": {"algorithmic_bytes_per_frame": alg["total"],
                                  "achieved_gbs": alg["total"] * value / world / 1e9,
                                  "frac_of_hbm": alg["total"] * value / world / 1e9 / hbm},
