@@ -123,6 +123,28 @@ int orbm_distance(orbm_handle h, const uint8_t* a, const uint8_t* b, int n, int*
 int orbm_frame_create(orbm_handle h, const orb_keypoint* keys_un, const uint8_t* descriptors, int n,
                       float min_x, float min_y, float max_x, float max_y, orbm_frame* out);
 int orbm_frame_destroy(orbm_frame f);
+
+/* mK and mDistCoef as Frame holds them (CV_32F; Tracking.cc reads Camera.fx .. Camera.k3 from the settings file). */
+typedef struct {
+    float fx, fy, cx, cy;
+    float k1, k2, p1, p2, k3;   /* k3 = 0 for the four-coefficient model */
+} orb_camera;
+/* cv::undistortPoints(mat, mat, mK, mDistCoef, cv::Mat(), mK) on n (x, y) pairs, bit for bit as the installed OpenCV
+ * computes it (five iterations in double, one rounding to float): what Frame::UndistortKeyPoints (Frame.cc:748-778) and
+ * Frame::ComputeImageBounds (Frame.cc:780-808) call.  cam == NULL or k1 == 0 copies the input (Frame.cc:750-754).  */
+int orbm_undistort_points(orbm_handle h, const orb_camera* cam, const float* xy, int n, float* xy_out);
+/* Frame::ComputeImageBounds: bounds[4] = mnMinX, mnMinY, mnMaxX, mnMaxY of a width x height image. */
+int orbm_image_bounds(orbm_handle h, const orb_camera* cam, int width, int height, float* bounds);
+/* The Frame constructor's work after ExtractORB (Frame.cc:75-109: UndistortKeyPoints, AssignFeaturesToGrid) for
+ * keypoints and descriptors that are still where orbx_extract_batch_device left them: d_keys / d_descriptors / d_count
+ * are DEVICE pointers of one frame (capacity entries), producer_stream is the stream that extraction was enqueued on.
+ * The frame keeps its own undistorted copy; only the 4-byte count crosses PCIe (N is host state of a Frame).      */
+int orbm_frame_create_device(orbm_handle h, const orb_keypoint* d_keys, const uint8_t* d_descriptors, const int* d_count,
+                             int capacity, const orb_camera* cam, float min_x, float min_y, float max_x, float max_y,
+                             void* producer_stream, orbm_frame* out);
+/* N, and mvKeysUn / mDescriptors copied back to the host (either pointer may be NULL) */
+int orbm_frame_size(orbm_frame f, int* n);
+int orbm_frame_download(orbm_frame f, orb_keypoint* keys_un, uint8_t* descriptors);
 /* mGrid as CSR: cell id = ix*48+iy; cell_start[3073], cell_idx[n] */
 int orbm_frame_grid(orbm_frame f, int* cell_start, int* cell_idx);
 /* Frame::GetFeaturesInArea (Frame.cc:671-724) for nq queries (x,y,r triples); min_level = max_level = -1 gives the

@@ -201,4 +201,39 @@ float fast_atan2(float y, float x) {
     return a;
 }
 
+// ---------------------------------------------------------------------------------------------
+// cv::undistortPoints(src, dst, K, distCoeffs, noArray(), K) for CV_32FC2 points, as Frame::UndistortKeyPoints and
+// Frame::ComputeImageBounds call it (Frame.cc:748-808): K and the coefficients are CV_32F and are widened to double,
+// five fixed-point iterations (TermCriteria(MAX_ITER, 5, 0.01)), rational model with k4..k6 = 0, tangential p1/p2,
+// no thin-prism / tilt terms, then P = K applied in double and one rounding to float.  The zero-valued terms that
+// OpenCV's general formula still evaluates are kept where they could change a rounding (they cannot: x + 0 is exact).
+// ---------------------------------------------------------------------------------------------
+void undistort_points(const float* xy, int n, float fxF, float fyF, float cxF, float cyF, const float* dist, int nDist,
+                      float* out) {
+    double k[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // k1 k2 p1 p2 k3 k4 k5 k6
+    for (int i = 0; i < nDist && i < 8; ++i) k[i] = (double)dist[i];
+    const double fx = fxF, fy = fyF, cx = cxF, cy = cyF;
+    const double ifx = 1. / fx, ify = 1. / fy;
+    for (int i = 0; i < n; ++i) {
+        const double u = xy[2 * i], v = xy[2 * i + 1];
+        double x = (u - cx) * ifx, y = (v - cy) * ify;
+        const double x0 = x, y0 = y;
+        for (int j = 0; j < 5; ++j) {
+            const double r2 = x * x + y * y;
+            const double icdist = (1 + ((k[7] * r2 + k[6]) * r2 + k[5]) * r2) / (1 + ((k[4] * r2 + k[1]) * r2 + k[0]) * r2);
+            if (icdist < 0) {   // OpenCV's regression_14583 guard
+                x = (u - cx) * ifx;
+                y = (v - cy) * ify;
+                break;
+            }
+            const double deltaX = 2 * k[2] * x * y + k[3] * (r2 + 2 * x * x);
+            const double deltaY = k[2] * (r2 + 2 * y * y) + 2 * k[3] * x * y;
+            x = (x0 - deltaX) * icdist;
+            y = (y0 - deltaY) * icdist;
+        }
+        out[2 * i] = (float)(fx * x + cx);
+        out[2 * i + 1] = (float)(fy * y + cy);
+    }
+}
+
 }  // namespace orbo

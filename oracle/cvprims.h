@@ -11,6 +11,8 @@
 //   cv::GaussianBlur(7x7, sigma 2)      :1104
 //   cv::fastAtan2                       :105
 //   cvRound                             :83, 117, 121-122, 444, 462, 1133
+// and, for the Frame post-processing either side of the path (/root/reference/src/Frame.cc):
+//   cv::undistortPoints                 :767, :793
 #pragma once
 #include <cstdint>
 #include <vector>
@@ -54,5 +56,10 @@ void gaussian_blur_7x7_s2(const uint8_t* src, int w, int h, int sstride,
 
 // cv::fastAtan2(y, x): degrees in [0, 360)
 float fast_atan2(float y, float x);
+
+// cv::undistortPoints(pts, pts, K, D, noArray(), K) for CV_32FC2 points and CV_32F K / D (Frame.cc:748-808);
+// dist = k1 k2 p1 p2 [k3], nDist = 4 or 5
+void undistort_points(const float* xy, int n, float fx, float fy, float cx, float cy, const float* dist, int nDist,
+                      float* out);
 
 }  // namespace orbo

@@ -19,6 +19,9 @@ void orbo_resize_table(int ssize, int dsize, int* ofs, int16_t* coef) { resize_a
 void orbo_border(const uint8_t* s, int w, int h, int ss, uint8_t* d, int ds, int b) {
     copy_make_border_reflect101(s, w, h, ss, d, ds, b);
 }
+void orbo_undistort(const float* xy, int n, const float* k4, const float* dist, int nDist, float* out) {
+    undistort_points(xy, n, k4[0], k4[1], k4[2], k4[3], dist, nDist, out);
+}
 int orbo_fast(const uint8_t* img, int w, int h, int stride, int th, KeyPoint* out, int cap) {
     std::vector<KeyPoint> v;
     fast9_16(img, w, h, stride, th, true, v);

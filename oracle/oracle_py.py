@@ -49,6 +49,7 @@ class Oracle:
         L.orbo_level_candidates.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         L.orbo_level_selected.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         L.orbo_stage_ms.argtypes = [C.c_void_p, C.c_void_p]
+        L.orbo_undistort.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.orbo_atan2.restype = C.c_float
         L.orbo_atan2.argtypes = [C.c_float, C.c_float]
         L.orbo_cosf.restype = C.c_float
@@ -117,6 +118,15 @@ class Oracle:
         dst = np.empty((h, w), np.uint8)
         self.lib.orbo_blur(_p(src), w, h, src.strides[0], _p(dst), w)
         return dst
+
+    def undistort(self, xy, K4, dist):
+        """cv::undistortPoints(pts, pts, K, D, noArray(), K); K4 = (fx, fy, cx, cy), dist = k1 k2 p1 p2 [k3]"""
+        xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
+        K4 = np.ascontiguousarray(K4, np.float32)
+        dist = np.ascontiguousarray(dist, np.float32).ravel()
+        out = np.empty_like(xy)
+        self.lib.orbo_undistort(_p(xy), len(xy), _p(K4), _p(dist), dist.size, _p(out))
+        return out
 
     def atan2(self, y, x):
         y = np.ascontiguousarray(y, np.float32)

@@ -95,3 +95,27 @@ def test_fast_atan2(oracle):
     got = oracle.atan2(y, x)
     assert np.array_equal(ref.view(np.uint32), got.view(np.uint32))
     assert oracle.atan2(np.zeros(1, np.float32), np.zeros(1, np.float32))[0] == 0.0
+
+
+# Cameras of the reference's own settings files: Examples/Monocular/EuRoC.yaml:8-16, TUM1.yaml (5 coefficients), plus a
+# strong barrel/pincushion pair so that the five iterations do not converge early.
+CAMERAS = [
+    ((458.654, 457.296, 367.215, 248.375), (-0.28340811, 0.07395907, 0.00019359, 1.76187114e-05), (752, 480)),
+    ((517.306408, 516.469215, 318.643040, 255.313989), (0.262383, -0.953104, -0.005358, 0.002628, 1.163314), (640, 480)),
+    ((300.0, 310.0, 320.0, 240.0), (-0.45, 0.21, 0.003, -0.002), (640, 480)),
+    ((700.0, 705.0, 600.0, 180.0), (0.12, 0.05, -0.001, 0.0007, -0.01), (1241, 376)),
+]
+
+
+@pytest.mark.parametrize("K4,dist,size", CAMERAS)
+def test_undistort_points(oracle, K4, dist, size):
+    """cv::undistortPoints as Frame::UndistortKeyPoints / ComputeImageBounds call it (Frame.cc:767, :793)"""
+    rng = np.random.default_rng(7)
+    w, h = size
+    pts = (rng.random((50000, 2)) * [w, h]).astype(np.float32)
+    pts = np.concatenate([pts, np.array([[0, 0], [w, 0], [0, h], [w, h], [K4[2], K4[3]]], np.float32)])
+    K = np.array([[K4[0], 0, K4[2]], [0, K4[1], K4[3]], [0, 0, 1]], np.float32)
+    D = np.array(dist, np.float32).reshape(-1, 1)
+    ref = cv2.undistortPoints(pts.reshape(-1, 1, 2), K, D, None, K).reshape(-1, 2)
+    got = oracle.undistort(pts, K4, dist)
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))

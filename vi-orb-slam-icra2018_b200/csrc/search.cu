@@ -13,6 +13,7 @@
 //   phase 2 (one warp per search): replay the queries in order over the stored (index, distance) lists with the
 //            dynamic skip rules; lanes split a query's candidates and merge (distance, order) keys by shuffle.
 // SearchForTriangulation never sets vbMatched2 (ORBmatcher.cc:725), so its queries are independent: one thread each.
+#include <cstring>
 #include <vector>
 
 #include "matcher.h"
@@ -97,6 +98,71 @@ __global__ void grid_sort_kernel(const int* cellStart, int* cellIdx) {
         while (j >= a && cellIdx[j] > v) { cellIdx[j + 1] = cellIdx[j]; --j; }
         cellIdx[j + 1] = v;
     }
+}
+
+// ------------------------------------------------------------------------------------------------ Frame post-extraction
+// cv::undistortPoints(mat, mat, mK, mDistCoef, cv::Mat(), mK) on CV_32FC2 points, as Frame::UndistortKeyPoints and
+// Frame::ComputeImageBounds call it (Frame.cc:767, :793).  OpenCV widens K and the coefficients to double, normalises,
+// runs five fixed-point iterations of the Brown model (TermCriteria(MAX_ITER, 5, 0.01)), applies P = K in double and
+// rounds once to float.  Every double operation below is a separately rounded IEEE operation in OpenCV's order
+// (its build has no FMA contraction); terms that are identically zero there (k4..k6, thin prism, tilt, R = I) are dropped.
+struct CamDev {
+    double fx, fy, cx, cy, ifx, ify;
+    double k1, k2, p1, p2, k3;
+    int distorted;   // mDistCoef.at<float>(0) != 0.0 (Frame.cc:750): otherwise mvKeysUn = mvKeys
+};
+
+__device__ __forceinline__ float2 undistort_point(const CamDev& c, float uf, float vf) {
+    const double u = (double)uf, v = (double)vf;
+    double x = __dmul_rn(__dsub_rn(u, c.cx), c.ifx), y = __dmul_rn(__dsub_rn(v, c.cy), c.ify);
+    const double x0 = x, y0 = y;
+    const double p1x2 = __dmul_rn(2.0, c.p1), p2x2 = __dmul_rn(2.0, c.p2);
+    for (int j = 0; j < 5; ++j) {
+        const double r2 = __dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y));
+        const double den = __dadd_rn(1.0, __dmul_rn(__dadd_rn(__dmul_rn(__dadd_rn(__dmul_rn(c.k3, r2), c.k2), r2), c.k1), r2));
+        const double icdist = __ddiv_rn(1.0, den);
+        if (icdist < 0) {   // OpenCV's guard against a sign flip of the radial factor: keep the normalised input
+            x = x0;
+            y = y0;
+            break;
+        }
+        const double deltaX = __dadd_rn(__dmul_rn(__dmul_rn(p1x2, x), y), __dmul_rn(c.p2, __dadd_rn(r2, __dmul_rn(__dmul_rn(2.0, x), x))));
+        const double deltaY = __dadd_rn(__dmul_rn(c.p1, __dadd_rn(r2, __dmul_rn(__dmul_rn(2.0, y), y))), __dmul_rn(__dmul_rn(p2x2, x), y));
+        x = __dmul_rn(__dsub_rn(x0, deltaX), icdist);
+        y = __dmul_rn(__dsub_rn(y0, deltaY), icdist);
+    }
+    return make_float2((float)__dadd_rn(__dmul_rn(c.fx, x), c.cx), (float)__dadd_rn(__dmul_rn(c.fy, y), c.cy));
+}
+
+__global__ void undistort_kernel(CamDev c, const float2* __restrict__ in, int n, float2* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = c.distorted ? undistort_point(c, in[i].x, in[i].y) : in[i];
+}
+
+// Frame::Frame after ExtractORB, for keypoints that never left the device: mvKeysUn (UndistortKeyPoints, Frame.cc:748-778),
+// a private copy of the descriptors, and the first pass of AssignFeaturesToGrid (PosInGrid, Frame.cc:726-736).
+__global__ void frame_import_kernel(CamDev c, const orb_keypoint* __restrict__ srcKeys, const uint4* __restrict__ srcDesc,
+                                    int n, orb_keypoint* __restrict__ keys, uint4* __restrict__ desc, float minX, float minY,
+                                    float invW, float invH, int* __restrict__ cellOf, int* __restrict__ counts) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    orb_keypoint kp = srcKeys[i];
+    if (c.distorted) {
+        const float2 p = undistort_point(c, kp.x, kp.y);
+        kp.x = p.x;
+        kp.y = p.y;
+    }
+    keys[i] = kp;
+    desc[2 * i] = srcDesc[2 * i];
+    desc[2 * i + 1] = srcDesc[2 * i + 1];
+    const int px = (int)roundf(__fmul_rn(__fsub_rn(kp.x, minX), invW));
+    const int py = (int)roundf(__fmul_rn(__fsub_rn(kp.y, minY), invH));
+    int cell = -1;
+    if (px >= 0 && px < kGridCols && py >= 0 && py < kGridRows) {
+        cell = px * kGridRows + py;
+        atomicAdd(&counts[cell], 1);
+    }
+    cellOf[i] = cell;
 }
 
 // ------------------------------------------------------------------------------------------------ candidate enumeration
@@ -826,6 +892,53 @@ int upload(DevBuf& b, const void* src, size_t bytes, cudaStream_t st) {
     return ORB_OK;
 }
 
+orbm_frame_s* new_frame(orbm_matcher* h, int n, float minX, float minY, float maxX, float maxY) {
+    orbm_frame_s* f = new orbm_frame_s;
+    f->m = h;
+    f->n = n;
+    f->minX = minX; f->minY = minY; f->maxX = maxX; f->maxY = maxY;
+    f->invW = (float)kGridCols / (maxX - minX);   // Frame.cc:93-94
+    f->invH = (float)kGridRows / (maxY - minY);
+    return f;
+}
+
+// AssignFeaturesToGrid (Frame.cc:574-589) in four launches: cell of every key + counts (the caller's kernel), exclusive
+// scan, bucket fill, per-bucket sort into the reference's push_back order.  cellOf lives in h->ws0.
+int grid_workspace(orbm_matcher* h, orbm_frame_s* f, int** counts, int** cursor, cudaStream_t st) {
+    ORB_CHECK(f->cellStart.reserve((kCells + 1) * 4));
+    ORB_CHECK(f->cellIdx.reserve((size_t)(f->n + 1) * 4));
+    ORB_CHECK(h->ws0.reserve((size_t)(f->n + 1) * 4));
+    ORB_CHECK(h->ws1.reserve((size_t)(kCells + 1) * 4 * 2));
+    *counts = h->ws1.as<int>();
+    *cursor = *counts + kCells + 1;
+    ORB_CUDA(cudaMemsetAsync(*counts, 0, (size_t)(kCells + 1) * 4 * 2, st));
+    return ORB_OK;
+}
+
+int finish_grid(orbm_matcher* h, orbm_frame_s* f, int* counts, int* cursor, cudaStream_t st) {
+    const int n = f->n;
+    scan_kernel<<<1, 1024, 0, st>>>(counts, f->cellStart.as<int>(), kCells);
+    if (n > 0) grid_fill_kernel<<<ceil_div(n, 256), 256, 0, st>>>(n, h->ws0.as<int>(), f->cellStart.as<int>(), cursor, f->cellIdx.as<int>());
+    grid_sort_kernel<<<ceil_div(kCells, 256), 256, 0, st>>>(f->cellStart.as<int>(), f->cellIdx.as<int>());
+    h->launches += 3;
+    ORB_CUDA(cudaGetLastError());
+    ORB_CUDA(cudaStreamSynchronize(st));
+    return ORB_OK;
+}
+
+// mK / mDistCoef (CV_32F, Tracking.cc reads fx fy cx cy k1 k2 p1 p2 [k3] from the settings file) widened to double
+int make_camera(const orb_camera* cam, CamDev* c, const char* who) {
+    std::memset(c, 0, sizeof *c);
+    if (!cam) return ORB_OK;
+    if (!(cam->fx != 0.0f) || !(cam->fy != 0.0f)) return fail(ORB_ERR_INVALID, "%s: focal length is zero", who);
+    c->fx = cam->fx; c->fy = cam->fy; c->cx = cam->cx; c->cy = cam->cy;
+    c->ifx = 1.0 / c->fx;
+    c->ify = 1.0 / c->fy;
+    c->k1 = cam->k1; c->k2 = cam->k2; c->p1 = cam->p1; c->p2 = cam->p2; c->k3 = cam->k3;
+    c->distorted = cam->k1 != 0.0f;
+    return ORB_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -838,40 +951,113 @@ int orbm_frame_create(orbm_handle h, const orb_keypoint* keys, const uint8_t* de
     if (n < 0 || (n > 0 && (!keys || !desc)) || !(maxX > minX) || !(maxY > minY))
         return fail(ORB_ERR_INVALID, "orbm_frame_create: bad arguments");
     if (n > kOrdMask) return fail(ORB_ERR_INVALID, "orbm_frame_create: more than %d keypoints", kOrdMask);
-    orbm_frame_s* f = new orbm_frame_s;
-    f->m = h;
-    f->n = n;
-    f->minX = minX; f->minY = minY; f->maxX = maxX; f->maxY = maxY;
-    f->invW = (float)kGridCols / (maxX - minX);   // Frame.cc:93-94
-    f->invH = (float)kGridRows / (maxY - minY);
+    orbm_frame_s* f = new_frame(h, n, minX, minY, maxX, maxY);
     cudaStream_t st = h->stream;
-    int status = ORB_OK;
     auto body = [&]() -> int {
         ORB_CHECK(upload(f->keys, keys, (size_t)n * sizeof(orb_keypoint), st));
         ORB_CHECK(upload(f->desc, desc, (size_t)n * 32, st));
-        ORB_CHECK(f->cellStart.reserve((kCells + 1) * 4));
-        ORB_CHECK(f->cellIdx.reserve((size_t)(n + 1) * 4));
-        ORB_CHECK(h->ws0.reserve((size_t)(n + 1) * 4));            // cellOf
-        ORB_CHECK(h->ws1.reserve((size_t)(kCells + 1) * 4 * 2));   // counts, cursor
-        int* counts = h->ws1.as<int>();
-        int* cursor = counts + kCells + 1;
-        ORB_CUDA(cudaMemsetAsync(counts, 0, (size_t)(kCells + 1) * 4 * 2, st));
-        const FrameDev fd = f->dev();
-        if (n > 0) grid_count_kernel<<<ceil_div(n, 256), 256, 0, st>>>(fd, h->ws0.as<int>(), counts);
-        scan_kernel<<<1, 1024, 0, st>>>(counts, f->cellStart.as<int>(), kCells);
-        if (n > 0) grid_fill_kernel<<<ceil_div(n, 256), 256, 0, st>>>(n, h->ws0.as<int>(), f->cellStart.as<int>(), cursor, f->cellIdx.as<int>());
-        grid_sort_kernel<<<ceil_div(kCells, 256), 256, 0, st>>>(f->cellStart.as<int>(), f->cellIdx.as<int>());
-        h->launches += 4;
-        ORB_CUDA(cudaGetLastError());
-        ORB_CUDA(cudaStreamSynchronize(st));
-        return ORB_OK;
+        int *counts, *cursor;
+        ORB_CHECK(grid_workspace(h, f, &counts, &cursor, st));
+        if (n > 0) grid_count_kernel<<<ceil_div(n, 256), 256, 0, st>>>(f->dev(), h->ws0.as<int>(), counts);
+        h->launches += 1;
+        return finish_grid(h, f, counts, cursor, st);
     };
-    status = body();
+    const int status = body();
     if (status != ORB_OK) {
         orbm_frame_destroy(f);
         return status;
     }
     *out = f;
+    return ORB_OK;
+}
+
+int orbm_frame_create_device(orbm_handle h, const orb_keypoint* dKeys, const uint8_t* dDesc, const int* dCount, int capacity,
+                             const orb_camera* cam, float minX, float minY, float maxX, float maxY, void* producerStream,
+                             orbm_frame* out) {
+    ORBM_ENTER(h);
+    if (!out) return fail(ORB_ERR_INVALID, "orbm_frame_create_device: null out");
+    *out = nullptr;
+    if (!dKeys || !dDesc || !dCount || capacity < 1 || !(maxX > minX) || !(maxY > minY))
+        return fail(ORB_ERR_INVALID, "orbm_frame_create_device: bad arguments");
+    if (((uintptr_t)dDesc & 15) != 0) return fail(ORB_ERR_INVALID, "orbm_frame_create_device: descriptors must be 16-byte aligned");
+    CamDev c;
+    ORB_CHECK(make_camera(cam, &c, "orbm_frame_create_device"));
+    // N = mvKeys.size() is host state of the Frame (it sizes mvpMapPoints, mvbOutlier): the one 4-byte read-back
+    int n = 0;
+    cudaStream_t ps = (cudaStream_t)producerStream;
+    ORB_CUDA(cudaMemcpyAsync(&n, dCount, 4, cudaMemcpyDeviceToHost, ps));
+    ORB_CUDA(cudaStreamSynchronize(ps));
+    if (n < 0) return fail(ORB_ERR_INVALID, "orbm_frame_create_device: negative keypoint count on the device");
+    if (n > capacity) return fail(ORB_ERR_CAPACITY, "orbm_frame_create_device: %d keypoints, capacity %d", n, capacity);
+    if (n > kOrdMask) return fail(ORB_ERR_INVALID, "orbm_frame_create_device: more than %d keypoints", kOrdMask);
+    orbm_frame_s* f = new_frame(h, n, minX, minY, maxX, maxY);
+    cudaStream_t st = h->stream;
+    auto body = [&]() -> int {
+        ORB_CHECK(f->keys.reserve((size_t)n * sizeof(orb_keypoint) + 16));
+        ORB_CHECK(f->desc.reserve((size_t)n * 32 + 16));
+        int *counts, *cursor;
+        ORB_CHECK(grid_workspace(h, f, &counts, &cursor, st));
+        if (n > 0)
+            frame_import_kernel<<<ceil_div(n, 128), 128, 0, st>>>(c, dKeys, (const uint4*)dDesc, n, f->keys.as<orb_keypoint>(),
+                                                                  f->desc.as<uint4>(), f->minX, f->minY, f->invW, f->invH,
+                                                                  h->ws0.as<int>(), counts);
+        h->launches += 1;
+        return finish_grid(h, f, counts, cursor, st);
+    };
+    const int status = body();
+    if (status != ORB_OK) {
+        orbm_frame_destroy(f);
+        return status;
+    }
+    *out = f;
+    return ORB_OK;
+}
+
+int orbm_frame_size(orbm_frame f, int* n) {
+    if (!f || !n) return fail(ORB_ERR_INVALID, "orbm_frame_size: null argument");
+    *n = f->n;
+    return ORB_OK;
+}
+
+int orbm_frame_download(orbm_frame f, orb_keypoint* keysUn, uint8_t* desc) {
+    if (!f) return fail(ORB_ERR_INVALID, "orbm_frame_download: null frame");
+    DeviceGuard g(f->m->device);
+    if (f->n == 0) return ORB_OK;
+    if (keysUn) ORB_CUDA(cudaMemcpy(keysUn, f->keys.p, (size_t)f->n * sizeof(orb_keypoint), cudaMemcpyDeviceToHost));
+    if (desc) ORB_CUDA(cudaMemcpy(desc, f->desc.p, (size_t)f->n * 32, cudaMemcpyDeviceToHost));
+    return ORB_OK;
+}
+
+int orbm_undistort_points(orbm_handle h, const orb_camera* cam, const float* xy, int n, float* xyOut) {
+    ORBM_ENTER(h);
+    if (n < 0 || (n > 0 && (!xy || !xyOut))) return fail(ORB_ERR_INVALID, "orbm_undistort_points: bad arguments");
+    CamDev c;
+    ORB_CHECK(make_camera(cam, &c, "orbm_undistort_points"));
+    if (n == 0) return ORB_OK;
+    cudaStream_t st = h->stream;
+    ORB_CHECK(upload(h->in0, xy, (size_t)n * 8, st));
+    ORB_CHECK(h->out0.reserve((size_t)n * 8));
+    undistort_kernel<<<ceil_div(n, 128), 128, 0, st>>>(c, h->in0.as<float2>(), n, h->out0.as<float2>());
+    h->launches += 1;
+    ORB_CUDA(cudaGetLastError());
+    ORB_CUDA(cudaMemcpyAsync(xyOut, h->out0.p, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    ORB_CUDA(cudaStreamSynchronize(st));
+    return ORB_OK;
+}
+
+int orbm_image_bounds(orbm_handle h, const orb_camera* cam, int width, int height, float* bounds) {
+    if (!bounds || width <= 0 || height <= 0) return fail(ORB_ERR_INVALID, "orbm_image_bounds: bad arguments");
+    if (!cam || cam->k1 == 0.0f) {   // Frame.cc:803-808
+        bounds[0] = 0.0f; bounds[1] = 0.0f; bounds[2] = (float)width; bounds[3] = (float)height;
+        return ORB_OK;
+    }
+    const float corners[8] = {0.0f, 0.0f, (float)width, 0.0f, 0.0f, (float)height, (float)width, (float)height};
+    float un[8];
+    ORB_CHECK(orbm_undistort_points(h, cam, corners, 4, un));
+    bounds[0] = fminf(un[0], un[4]);   // mnMinX = min(mat(0,0), mat(2,0))   Frame.cc:797-800
+    bounds[2] = fmaxf(un[2], un[6]);   // mnMaxX = max(mat(1,0), mat(3,0))
+    bounds[1] = fminf(un[1], un[3]);   // mnMinY = min(mat(0,1), mat(1,1))
+    bounds[3] = fmaxf(un[5], un[7]);   // mnMaxY = max(mat(2,1), mat(3,1))
     return ORB_OK;
 }
 

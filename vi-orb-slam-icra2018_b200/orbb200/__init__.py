@@ -20,7 +20,16 @@ PROJ_QUERY_DTYPE = np.dtype([("u", "<f4"), ("v", "<f4"), ("invz", "<f4"), ("octa
 POINT_QUERY_DTYPE = np.dtype([("proj_x", "<f4"), ("proj_y", "<f4"), ("proj_xr", "<f4"), ("view_cos", "<f4"),
                               ("level", "<i4"), ("in_view", "<i4"), ("obs_positive", "<i4")])
 
+CAMERA_DTYPE = np.dtype([(k, "<f4") for k in ("fx", "fy", "cx", "cy", "k1", "k2", "p1", "p2", "k3")])
+
 ORB_OK = 0
+
+
+def camera(fx, fy, cx, cy, k1=0.0, k2=0.0, p1=0.0, p2=0.0, k3=0.0):
+    """orb_camera: mK and mDistCoef of a Frame"""
+    c = np.zeros(1, CAMERA_DTYPE)
+    c[0] = (fx, fy, cx, cy, k1, k2, p1, p2, k3)
+    return c
 
 
 class OrbError(RuntimeError):
@@ -194,6 +203,29 @@ class Frame:
         _check(self.L.orbm_frame_create(matcher.h, _p(keys), _p(d), self.n, *[C.c_float(b) for b in bounds], C.byref(f)))
         self.f = f
 
+    @classmethod
+    def from_device(cls, matcher, d_keys, d_desc, d_count, capacity, bounds, cam=None, stream=None):
+        """Frame post-extraction on the device (orbm_frame_create_device): d_* are device pointers (ints) or torch
+        tensors of ONE frame as orbx_extract_batch_device wrote them."""
+        self = cls.__new__(cls)
+        self.m, self.L = matcher, matcher.L
+        f = C.c_void_p()
+        _check(self.L.orbm_frame_create_device(matcher.h, _dp(d_keys), _dp(d_desc), _dp(d_count), capacity, _p(cam),
+                                               *[C.c_float(b) for b in bounds], _dp(stream), C.byref(f)))
+        self.f = f
+        n = C.c_int()
+        _check(self.L.orbm_frame_size(self.f, C.byref(n)))
+        self.n = n.value
+        self.keys = self.desc = None
+        return self
+
+    def download(self):
+        """(mvKeysUn, mDescriptors) of the device-resident frame"""
+        keys = np.zeros(self.n, KP_DTYPE)
+        desc = np.zeros((self.n, 32), np.uint8)
+        _check(self.L.orbm_frame_download(self.f, _p(keys), _p(desc)))
+        return keys, desc
+
     def close(self):
         if getattr(self, "f", None):
             self.L.orbm_frame_destroy(self.f)
@@ -242,6 +274,19 @@ class Matcher:
 
     def frame(self, keys_un, desc, bounds):
         return Frame(self, keys_un, desc, bounds)
+
+    def undistort_points(self, cam, xy):
+        """cv::undistortPoints(pts, pts, mK, mDistCoef, Mat(), mK)  (Frame.cc:767)"""
+        xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
+        out = np.empty_like(xy)
+        _check(self.L.orbm_undistort_points(self.h, _p(cam), _p(xy), len(xy), _p(out)))
+        return out
+
+    def image_bounds(self, cam, width, height):
+        """Frame::ComputeImageBounds: (mnMinX, mnMinY, mnMaxX, mnMaxY)"""
+        b = np.empty(4, np.float32)
+        _check(self.L.orbm_image_bounds(self.h, _p(cam), width, height, _p(b)))
+        return b
 
     def distance(self, a, b):
         a = np.ascontiguousarray(a, np.uint8).reshape(-1, 32)

@@ -32,6 +32,11 @@ SIGNATURES = {
     "orbm_distance": (i32, [vp, vp, vp, i32, vp]),
     "orbm_frame_create": (i32, [vp, vp, vp, i32, f32, f32, f32, f32, vp]),
     "orbm_frame_destroy": (i32, [vp]),
+    "orbm_undistort_points": (i32, [vp, vp, vp, i32, vp]),
+    "orbm_image_bounds": (i32, [vp, vp, i32, i32, vp]),
+    "orbm_frame_create_device": (i32, [vp, vp, vp, vp, i32, vp, f32, f32, f32, f32, vp, vp]),
+    "orbm_frame_size": (i32, [vp, vp]),
+    "orbm_frame_download": (i32, [vp, vp, vp]),
     "orbm_frame_grid": (i32, [vp, vp, vp]),
     "orbm_features_in_area": (i32, [vp, vp, i32, i32, i32, vp, i32, vp]),
     "orbm_search_for_initialization": (i32, [vp, vp, vp, vp, vp, i32, f32, i32, vp]),
