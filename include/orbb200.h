@@ -93,6 +93,28 @@ int orbx_get_level(orbx_handle h, int frame, int level, uint8_t* out, int* w, in
  * host call measured with CUDA events on the handle's stream.                                                  */
 int orbx_stage_times(orbx_handle h, double* ms3);
 
+/* Frame::ComputeStereoMatches (Frame.cc:810-984), the one consumer of the padded mvImagePyramid: for every left keypoint
+ * the closest right descriptor on its row band, refined by the 11x11 SAD search and the parabola fit on the pyramid
+ * level of the left keypoint, then the 1.5*1.4*median SAD filter.  The pyramids are read in place from frame
+ * `left_frame` / `right_frame` of the LAST extract call of the two handles (same device, same image size and ctor
+ * arguments; the host call waits for the right handle's stream).  keys_* are mvKeys / mvKeysRight (not undistorted),
+ * mb = baseline in metres, mbf = baseline * fx.  u_right[n_left], depth[n_left]: mvuRight, mvDepth (-1 = no match).
+ * Where the reference has undefined behaviour the result is defined: a search window that leaves the level image is
+ * no match (cv::Mat::colRange would assert), and with no match at all the median filter is skipped.                */
+int orbx_compute_stereo_matches(orbx_handle left, int left_frame, orbx_handle right, int right_frame,
+                                const orb_keypoint* keys_left, const uint8_t* desc_left, int n_left,
+                                const orb_keypoint* keys_right, const uint8_t* desc_right, int n_right,
+                                float mb, float mbf, float* u_right, float* depth, int* n_matches);
+/* Device-resident variant: keypoints, descriptors and counts where orbx_extract_batch_device left them (d_n_* may be
+ * NULL: then cap_* is the count); outputs are device arrays of cap_left entries (d_sad: SAD of each kept match or -1),
+ * *d_kept the number of matches.  Enqueues on `stream` (NULL = the left handle's stream) without synchronising; the
+ * caller orders it after both extractions.                                                                         */
+int orbx_compute_stereo_matches_device(orbx_handle left, int left_frame, orbx_handle right, int right_frame,
+                                       const orb_keypoint* d_keys_left, const uint8_t* d_desc_left, const int* d_n_left,
+                                       int cap_left, const orb_keypoint* d_keys_right, const uint8_t* d_desc_right,
+                                       const int* d_n_right, int cap_right, float mb, float mbf, float* d_u_right,
+                                       float* d_depth, int* d_sad, int* d_kept, void* stream);
+
 /* Introspection for stage-by-stage parity tests (not part of the reference surface). */
 int orbx_debug_candidates(orbx_handle h, int frame, int level, orb_keypoint* out, int cap, int* n);
 int orbx_debug_blurred(orbx_handle h, int frame, int level, uint8_t* out /* w*h */);

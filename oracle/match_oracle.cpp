@@ -416,4 +416,113 @@ int kf_pair_match_count(const uint8_t* d1, const float* a1, int n1, const uint8_
     return nmatches;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Frame::ComputeStereoMatches, Frame.cc:810-984
+// ---------------------------------------------------------------------------------------------
+int compute_stereo_matches(const KeyPoint* keysL, const uint8_t* descL, int nL, const KeyPoint* keysR, const uint8_t* descR,
+                           int nR, const StereoLevel* levelsL, const StereoLevel* levelsR, int nLevels,
+                           const float* scaleFactors, const float* invScaleFactors, float mb, float mbf,
+                           float* uRight, float* depth, int* sad) {
+    (void)nLevels;
+    for (int i = 0; i < nL; ++i) { uRight[i] = -1.0f; depth[i] = -1.0f; sad[i] = -1; }   // :812-813
+    const int thOrbDist = (TH_HIGH + TH_LOW) / 2;                                        // :815
+    const int nRows = levelsL[0].rows;                                                   // :817
+    std::vector<std::vector<int>> rowIndices(nRows);                                     // :820-838
+    for (int iR = 0; iR < nR; ++iR) {
+        const float kpY = keysR[iR].y;
+        const float r = 2.0f * scaleFactors[keysR[iR].octave];
+        const int maxr = (int)std::ceil(kpY + r);
+        const int minr = (int)std::floor(kpY - r);
+        for (int yi = std::max(minr, 0); yi <= std::min(maxr, nRows - 1); ++yi) rowIndices[yi].push_back(iR);
+    }
+    const float minZ = mb, minD = 0, maxD = mbf / minZ;                                  // :841-843
+    std::vector<std::pair<int, int>> distIdx;
+    for (int iL = 0; iL < nL; ++iL) {
+        const KeyPoint& kpL = keysL[iL];
+        const int levelL = kpL.octave;
+        const float vL = kpL.y, uL = kpL.x;
+        const long row = (long)vL;                                                       // vRowIndices[vL], :856
+        if (row < 0 || row >= nRows) continue;
+        const std::vector<int>& cand = rowIndices[row];
+        if (cand.empty()) continue;
+        const float minU = uL - maxD, maxU = uL - minD;
+        if (maxU < 0) continue;
+        int bestDist = TH_HIGH;
+        int bestIdxR = 0;
+        const uint8_t* dL = descL + 32 * (size_t)iL;
+        for (int iR : cand) {                                                            // :873-895
+            const KeyPoint& kpR = keysR[iR];
+            if (kpR.octave < levelL - 1 || kpR.octave > levelL + 1) continue;
+            const float uR = kpR.x;
+            if (uR >= minU && uR <= maxU) {
+                const int dist = descriptor_distance(dL, descR + 32 * (size_t)iR);
+                if (dist < bestDist) { bestDist = dist; bestIdxR = iR; }
+            }
+        }
+        if (!(bestDist < thOrbDist)) continue;                                           // :898
+        const float uR0 = keysR[bestIdxR].x;
+        const float scaleFactor = invScaleFactors[kpL.octave];
+        const float scaleduL = std::round(kpL.x * scaleFactor);
+        const float scaledvL = std::round(kpL.y * scaleFactor);
+        const float scaleduR0 = std::round(uR0 * scaleFactor);
+        const int w = 5, L = 5;
+        const StereoLevel& PL = levelsL[kpL.octave];
+        const StereoLevel& PR = levelsR[kpL.octave];
+        // IL = level(rows v-w..v+w, cols u-w..u+w) as float minus its centre (:908-910); rowRange/colRange take ints
+        const int v0 = (int)(scaledvL - w), u0 = (int)(scaleduL - w);
+        // cv::Mat::rowRange / colRange assert that the window lies inside the level (the reference would throw): no match
+        if (u0 < 0 || u0 + 2 * w + 1 > PL.cols || v0 < 0 || v0 + 2 * w + 1 > PL.rows) continue;
+        if ((int)scaleduR0 - L - w < 0) continue;
+        float IL[11][11];
+        auto pixL = [&](int y, int x) { return (float)PL.padded[(size_t)(y + 19) * PL.stride + (x + 19)]; };
+        auto pixR = [&](int y, int x) { return (float)PR.padded[(size_t)(y + 19) * PR.stride + (x + 19)]; };
+        const float cL = pixL(v0 + w, u0 + w);
+        for (int y = 0; y < 11; ++y)
+            for (int x = 0; x < 11; ++x) IL[y][x] = pixL(v0 + y, u0 + x) - cL;
+        int bestSad = INT_MAX, bestincR = 0;
+        float dists[2 * 5 + 1];
+        const float iniu = scaleduR0 + L - w, endu = scaleduR0 + L + w + 1;              // :918-921
+        if (iniu < 0 || endu >= PR.cols) continue;
+        for (int incR = -L; incR <= +L; ++incR) {                                        // :923-937
+            const int ur0 = (int)(scaleduR0 + incR - w);
+            const float cR = pixR(v0 + w, ur0 + w);
+            double acc = 0;                                                              // cv::norm(NORM_L1) sums in double
+            for (int y = 0; y < 11; ++y)
+                for (int x = 0; x < 11; ++x) acc += (double)std::fabs(IL[y][x] - (pixR(v0 + y, ur0 + x) - cR));
+            const float dist = (float)acc;
+            if (dist < bestSad) { bestSad = (int)dist; bestincR = incR; }
+            dists[L + incR] = dist;
+        }
+        if (bestincR == -L || bestincR == L) continue;                                   // :939
+        const float dist1 = dists[L + bestincR - 1], dist2 = dists[L + bestincR], dist3 = dists[L + bestincR + 1];
+        const float deltaR = (dist1 - dist3) / (2.0f * (dist1 + dist3 - 2.0f * dist2));  // :947
+        if (deltaR < -1 || deltaR > 1) continue;
+        float bestuR = scaleFactors[kpL.octave] * ((float)scaleduR0 + (float)bestincR + deltaR);   // :953
+        float disparity = (uL - bestuR);
+        if (disparity >= minD && disparity < maxD) {
+            if (disparity <= 0) {
+                disparity = 0.01;
+                bestuR = uL - 0.01;                                                      // double arithmetic, then float
+            }
+            depth[iL] = mbf / disparity;
+            uRight[iL] = bestuR;
+            sad[iL] = bestSad;
+            distIdx.push_back(std::pair<int, int>(bestSad, iL));
+        }
+    }
+    if (distIdx.empty()) return 0;                                                       // (reference: undefined)
+    std::sort(distIdx.begin(), distIdx.end());                                           // :971-984
+    const float median = distIdx[distIdx.size() / 2].first;
+    const float thDist = 1.5f * 1.4f * median;
+    int kept = (int)distIdx.size();
+    for (int i = (int)distIdx.size() - 1; i >= 0; --i) {
+        if (distIdx[i].first < thDist) break;
+        uRight[distIdx[i].second] = -1;
+        depth[distIdx[i].second] = -1;
+        sad[distIdx[i].second] = -1;
+        --kept;
+    }
+    return kept;
+}
+
 }  // namespace orbo

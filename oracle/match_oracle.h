@@ -109,4 +109,20 @@ int bruteforce_match(const uint8_t* q, const float* qAngle, int nq, const uint8_
 int kf_pair_match_count(const uint8_t* d1, const float* a1, int n1, const uint8_t* d2, const float* a2, int n2,
                         float nnratio, bool checkOri, int* matches12 /* may be null */);
 
+// Frame::ComputeStereoMatches (Frame.cc:810-984): for every left keypoint the closest right descriptor among the right
+// keypoints whose row band covers the left keypoint's row (band = +-2*scale[octave]), octave within +-1, uR in
+// [uL - mbf/mb, uL]; accepted below (TH_HIGH+TH_LOW)/2; refined by an 11x11 centre-normalised SAD over 11 horizontal
+// shifts on the pyramid level of the left keypoint and a parabola through the three SADs around the best shift; finally
+// matches whose SAD is >= 1.5*1.4*median are withdrawn.  Levels are given as the padded buffers of mvImagePyramid
+// ((w+38) x (h+38), the level's pixel (0,0) at (19,19)), so that the shifted windows stay addressable.
+// Keys are mvKeys / mvKeysRight (NOT undistorted: stereo input is rectified).  Writes mvuRight / mvDepth (-1 = none) and
+// the SAD of each accepted match (-1 otherwise); returns the number of stereo matches kept.
+// Two deliberate definitions where the reference has undefined behaviour: a right keypoint's row band is clipped to
+// the image rows, and with no accepted match at all the median step is skipped (the reference indexes an empty vector).
+struct StereoLevel { const uint8_t* padded; int stride; int cols, rows; };
+int compute_stereo_matches(const KeyPoint* keysL, const uint8_t* descL, int nL, const KeyPoint* keysR, const uint8_t* descR,
+                           int nR, const StereoLevel* levelsL, const StereoLevel* levelsR, int nLevels,
+                           const float* scaleFactors, const float* invScaleFactors, float mb, float mbf,
+                           float* uRight, float* depth, int* sad);
+
 }  // namespace orbo

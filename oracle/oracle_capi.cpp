@@ -194,6 +194,17 @@ int orbo_bruteforce(const uint8_t* q, const float* qa, int nq, const uint8_t* t,
                     int checkOri, int* best, int* second, int* idx, int* m12) {
     return bruteforce_match(q, qa, nq, t, ta, nt, ratio, checkOri != 0, best, second, idx, m12);
 }
+int orbo_stereo(const KeyPoint* keysL, const uint8_t* descL, int nL, const KeyPoint* keysR, const uint8_t* descR, int nR,
+                const uint8_t* const* paddedL, const uint8_t* const* paddedR, const int* cols, const int* rows, int nLevels,
+                const float* sf, const float* isf, float mb, float mbf, float* uRight, float* depth, int* sad) {
+    std::vector<StereoLevel> L(nLevels), R(nLevels);
+    for (int l = 0; l < nLevels; ++l) {
+        L[l] = StereoLevel{paddedL[l], cols[l] + 38, cols[l], rows[l]};
+        R[l] = StereoLevel{paddedR[l], cols[l] + 38, cols[l], rows[l]};
+    }
+    return compute_stereo_matches(keysL, descL, nL, keysR, descR, nR, L.data(), R.data(), nLevels, sf, isf, mb, mbf, uRight,
+                                  depth, sad);
+}
 int orbo_kf_pair(const uint8_t* d1, const float* a1, int n1, const uint8_t* d2, const float* a2, int n2, float ratio,
                  int checkOri, int* m12) {
     return kf_pair_match_count(d1, a1, n1, d2, a2, n2, ratio, checkOri != 0, m12);

@@ -50,6 +50,9 @@ class Oracle:
         L.orbo_level_selected.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         L.orbo_stage_ms.argtypes = [C.c_void_p, C.c_void_p]
         L.orbo_undistort.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.orbo_stereo.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_float,
+                                  C.c_void_p, C.c_void_p, C.c_void_p]
         L.orbo_atan2.restype = C.c_float
         L.orbo_atan2.argtypes = [C.c_float, C.c_float]
         L.orbo_cosf.restype = C.c_float
@@ -185,6 +188,24 @@ class Oracle:
 
     def frame(self, keys_un, desc, bounds):
         return OracleFrame(self, keys_un, desc, bounds)
+
+    def stereo(self, keys_l, desc_l, keys_r, desc_r, levels_l, levels_r, scale, inv_scale, mb, mbf):
+        """Frame::ComputeStereoMatches; levels_* = lists of padded (h+38, w+38) uint8 arrays (mvImagePyramid).
+        Returns (mvuRight, mvDepth, sad, kept)."""
+        kl = np.ascontiguousarray(keys_l, KP_DTYPE); kr = np.ascontiguousarray(keys_r, KP_DTYPE)
+        dl = np.ascontiguousarray(desc_l, np.uint8); dr = np.ascontiguousarray(desc_r, np.uint8)
+        nl = len(levels_l)
+        la = [np.ascontiguousarray(a, np.uint8) for a in levels_l]
+        ra = [np.ascontiguousarray(a, np.uint8) for a in levels_r]
+        pl = (C.c_void_p * nl)(*[a.ctypes.data for a in la])
+        pr = (C.c_void_p * nl)(*[a.ctypes.data for a in ra])
+        cols = np.array([a.shape[1] - 38 for a in la], np.int32)
+        rows = np.array([a.shape[0] - 38 for a in la], np.int32)
+        sf = np.ascontiguousarray(scale, np.float32); isf = np.ascontiguousarray(inv_scale, np.float32)
+        ur = np.empty(len(kl), np.float32); depth = np.empty(len(kl), np.float32); sad = np.empty(len(kl), np.int32)
+        kept = self.lib.orbo_stereo(_p(kl), _p(dl), len(kl), _p(kr), _p(dr), len(kr), pl, pr, _p(cols), _p(rows), nl,
+                                    _p(sf), _p(isf), C.c_float(mb), C.c_float(mbf), _p(ur), _p(depth), _p(sad))
+        return ur, depth, sad, kept
 
     def bruteforce(self, q, qa, t, ta, ratio=0.9, check_ori=True):
         q = np.ascontiguousarray(q, np.uint8); t = np.ascontiguousarray(t, np.uint8)

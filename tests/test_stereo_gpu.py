@@ -1,0 +1,126 @@
+"""GPU parity of Frame::ComputeStereoMatches (Frame.cc:810-984) against the oracle
+restatement: mvuRight and mvDepth bit for bit (float32 with the reference's operation order), the same matches kept."""
+import numpy as np
+import pytest
+
+import orbb200
+from datagen import stereo_pair
+
+pytestmark = pytest.mark.gpu
+
+# EuRoC stereo rig of the reference's Examples/Stereo/EuRoC.yaml: Camera.bf = 47.90639384423901, fx = 435.2;
+# KITTI 00-02: bf = 386.1448, fx = 718.856
+RIGS = {"euroc": (752, 480, 1200, 47.90639384423901 / 435.2046959714599, 47.90639384423901),
+        "kitti": (1241, 376, 2000, 386.1448 / 718.856, 386.1448)}
+
+
+def _oracle_stereo(oracle, left, right, nfeat, mb, mbf):
+    el, er = oracle.extractor(nfeat), oracle.extractor(nfeat)
+    kl, dl = el.extract(left)
+    kr, dr = er.extract(right)
+    t = el.tables()
+    LL = [el.level_padded(i) for i in range(8)]
+    RR = [er.level_padded(i) for i in range(8)]
+    ur, depth, sad, kept = oracle.stereo(kl, dl, kr, dr, LL, RR, t["scale"], t["inv_scale"], mb, mbf)
+    return kl, dl, kr, dr, ur, depth, sad, kept
+
+
+@pytest.mark.parametrize("rig,seed", [("euroc", 1), ("euroc", 2), ("kitti", 3)])
+def test_compute_stereo_matches(oracle, rig, seed):
+    w, h, nfeat, mb, mbf = RIGS[rig]
+    left, right = stereo_pair(seed, w, h)
+    kl, dl, kr, dr, ur_ref, depth_ref, sad_ref, kept_ref = _oracle_stereo(oracle, left, right, nfeat, mb, mbf)
+    exl = orbb200.Extractor(nfeat, max_width=w, max_height=h)
+    exr = orbb200.Extractor(nfeat, max_width=w, max_height=h)
+    gkl, gdl = exl(left)
+    gkr, gdr = exr(right)
+    assert gkl.tobytes() == kl.tobytes() and gkr.tobytes() == kr.tobytes()
+    ur, depth, n = exl.stereo_matches(exr, gkl, gdl, gkr, gdr, mb, mbf)
+    assert n == kept_ref and kept_ref > 150
+    assert np.array_equal(ur.view(np.uint32), ur_ref.view(np.uint32))
+    assert np.array_equal(depth.view(np.uint32), depth_ref.view(np.uint32))
+    assert int((ur >= 0).sum()) == n
+    # the disparities are the planted ones (sub-pixel refined)
+    ok = ur >= 0
+    disp = kl["x"][ok] - ur[ok]
+    band = np.minimum((kl["y"][ok] * 4 // h).astype(int), 3)
+    for b, d in enumerate((6, 14, 27, 41)):
+        assert abs(np.median(disp[band == b]) - d) < 0.6
+    exl.close()
+    exr.close()
+
+
+def test_stereo_device_resident(oracle):
+    """the same through device pointers: extraction outputs are consumed where the extractors wrote them"""
+    torch = pytest.importorskip("torch")
+    w, h, nfeat, mb, mbf = RIGS["euroc"]
+    pairs = [stereo_pair(10 + i, w, h) for i in range(2)]
+    exl = orbb200.Extractor(nfeat, max_width=w, max_height=h, max_batch=2)
+    exr = orbb200.Extractor(nfeat, max_width=w, max_height=h, max_batch=2)
+    cap = exl.capacity
+    out = {}
+    for name, ex, imgs in (("l", exl, [p[0] for p in pairs]), ("r", exr, [p[1] for p in pairs])):
+        d_img = torch.from_numpy(np.stack(imgs)).cuda()
+        d_k = torch.zeros((2, cap, 7), dtype=torch.int32, device="cuda")
+        d_d = torch.zeros((2, cap, 32), dtype=torch.uint8, device="cuda")
+        d_n = torch.zeros(2, dtype=torch.int32, device="cuda")
+        ex.extract_batch_device(d_img, d_k, d_d, d_n)
+        out[name] = (d_img, d_k, d_d, d_n)
+    exl.synchronize()
+    exr.synchronize()
+    for f in range(2):
+        d_u = torch.zeros(cap, dtype=torch.float32, device="cuda")
+        d_z = torch.zeros(cap, dtype=torch.float32, device="cuda")
+        d_s = torch.zeros(cap, dtype=torch.int32, device="cuda")
+        d_kept = torch.zeros(1, dtype=torch.int32, device="cuda")
+        exl.stereo_matches_device(exr, f, f, out["l"][1][f], out["l"][2][f], out["l"][3][f:f + 1], out["r"][1][f],
+                                  out["r"][2][f], out["r"][3][f:f + 1], mb, mbf, d_u, d_z, d_s, d_kept)
+        exl.synchronize()
+        kl, dl, kr, dr, ur_ref, depth_ref, sad_ref, kept_ref = _oracle_stereo(oracle, pairs[f][0], pairs[f][1], nfeat, mb, mbf)
+        n = int(out["l"][3][f])
+        assert n == len(kl)
+        assert int(d_kept) == kept_ref
+        assert np.array_equal(d_u[:n].cpu().numpy().view(np.uint32), ur_ref.view(np.uint32))
+        assert np.array_equal(d_z[:n].cpu().numpy().view(np.uint32), depth_ref.view(np.uint32))
+        assert np.array_equal(d_s[:n].cpu().numpy(), sad_ref)
+    exl.close()
+    exr.close()
+
+
+def test_stereo_edge_cases(oracle):
+    w, h, nfeat, mb, mbf = RIGS["euroc"]
+    left, right = stereo_pair(4, w, h)
+    exl = orbb200.Extractor(nfeat, max_width=w, max_height=h)
+    exr = orbb200.Extractor(nfeat, max_width=w, max_height=h)
+    kl, dl = exl(left)
+    kr, dr = exr(right)
+    # no right keypoints, no left keypoints
+    ur, depth, n = exl.stereo_matches(exr, kl, dl, kr[:0], dr[:0], mb, mbf)
+    assert n == 0 and (ur == -1).all() and (depth == -1).all()
+    ur, depth, n = exl.stereo_matches(exr, kl[:0], dl[:0], kr, dr, mb, mbf)
+    assert n == 0 and len(ur) == 0
+    # zero disparity, and the top of the right image identical to the left: SAD 0 with a symmetric parabola gives a
+    # disparity of exactly 0 -> the reference's disparity<=0 branch (0.01 px, bestuR = uL - 0.01 in double)
+    l0, r0 = stereo_pair(4, w, h, disparities=(0, 0, 0, 0))
+    r0[:150] = l0[:150]
+    kl0, dl0 = exl(l0)
+    kr0, dr0 = exr(r0)
+    ur, depth, n = exl.stereo_matches(exr, kl0, dl0, kr0, dr0, mb, mbf)
+    el, er = oracle.extractor(nfeat), oracle.extractor(nfeat)
+    el.extract(l0)
+    er.extract(r0)
+    t = el.tables()
+    ur_ref, depth_ref, sad_ref, kept_ref = oracle.stereo(kl0, dl0, kr0, dr0, [el.level_padded(i) for i in range(8)],
+                                                         [er.level_padded(i) for i in range(8)], t["scale"],
+                                                         t["inv_scale"], mb, mbf)
+    assert n == kept_ref and n > 300
+    assert np.array_equal(ur.view(np.uint32), ur_ref.view(np.uint32))
+    assert np.array_equal(depth.view(np.uint32), depth_ref.view(np.uint32))
+    assert (depth_ref == np.float32(mbf) / np.float32(0.01)).any()
+    # mismatched extractors are refused
+    other = orbb200.Extractor(nfeat, max_width=640, max_height=480)
+    other(left[:480, :640].copy())
+    with pytest.raises(orbb200.OrbError):
+        exl.stereo_matches(other, kl, dl, kr, dr, mb, mbf)
+    for e in (exl, exr, other):
+        e.close()

@@ -59,6 +59,7 @@ struct orbx_extractor {
     // device memory
     DevBuf pyr, blur, slots, cellCount, sel, selCount, keyWs, dCells, dTiles, dTabOfs, dTabCoef;
     DevBuf dImages, dKps, dDesc, dCount;
+    DevBuf stKeysL, stDescL, stKeysR, stDescR, stOut;   // staging of orbx_compute_stereo_matches
     int lastFrames = 0, lastCapacity = 0;
     int launches = 0;
     double stageMs[3] = {0, 0, 0};
@@ -347,7 +348,8 @@ int orbx_destroy(orbx_handle e) {
     DeviceGuard g(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
     DevBuf* bufs[] = {&e->pyr, &e->blur, &e->slots, &e->cellCount, &e->sel, &e->selCount, &e->keyWs, &e->dCells,
-                      &e->dTiles, &e->dTabOfs, &e->dTabCoef, &e->dImages, &e->dKps, &e->dDesc, &e->dCount};
+                      &e->dTiles, &e->dTabOfs, &e->dTabCoef, &e->dImages, &e->dKps, &e->dDesc, &e->dCount,
+                      &e->stKeysL, &e->stDescL, &e->stKeysR, &e->stDescR, &e->stOut};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < 4; ++i)
         if (e->ev[i]) cudaEventDestroy(e->ev[i]);
@@ -497,6 +499,95 @@ int orbx_extract_batch(orbx_handle e, const uint8_t* images, int nFrames, int w,
 int orbx_extract(orbx_handle e, const uint8_t* image, int w, int h, int stride, orb_keypoint* kps, uint8_t* desc,
                  int capacity, int* nOut) {
     return orbx_extract_batch(e, image, 1, w, h, stride, (size_t)stride * (h > 0 ? h : 0), kps, desc, capacity, nOut);
+}
+
+// Frame::ComputeStereoMatches (Frame.cc:810-984): the pyramids are read where the two extractors' last calls left them
+static int stereo_params(orbx_extractor* l, int frameL, orbx_extractor* r, int frameR, float mb, float mbf, StereoParams* S,
+                         const char* who) {
+    if (l->device != r->device) return fail(ORB_ERR_INVALID, "%s: the two extractors live on different devices", who);
+    if (l->curW <= 0 || r->curW <= 0) return fail(ORB_ERR_INVALID, "%s: extract first (no pyramid yet)", who);
+    if (l->curW != r->curW || l->curH != r->curH || l->nlevels != r->nlevels || l->scaleFactor != r->scaleFactor)
+        return fail(ORB_ERR_INVALID, "%s: left and right extractor differ in image size, levels or scale factor", who);
+    if (frameL < 0 || frameL >= l->lastFrames || frameR < 0 || frameR >= r->lastFrames)
+        return fail(ORB_ERR_INVALID, "%s: frame index outside the last batch", who);
+    if (!(mb > 0.0f) || !(mbf > 0.0f)) return fail(ORB_ERR_INVALID, "%s: baseline mb and mbf must be positive", who);
+    const ExtractParams& P = l->P;
+    S->pyrL = P.pyr + (size_t)frameL * P.pyrFrameBytes;
+    S->pyrR = r->P.pyr + (size_t)frameR * r->P.pyrFrameBytes;
+    S->nLevels = l->nlevels;
+    S->nRows = P.lv[0].h;
+    S->maxD = mbf / mb;          // Frame.cc:841-843 (minZ = mb)
+    S->mbf = mbf;
+    for (int i = 0; i < l->nlevels; ++i) {
+        S->lvOff[i] = P.lv[i].pyrOff;
+        S->pitch[i] = P.lv[i].pitch;
+        S->cols[i] = P.lv[i].w;
+        S->rows[i] = P.lv[i].h;
+        S->scale[i] = l->scale[i];
+        S->invScale[i] = l->invScale[i];
+    }
+    return ORB_OK;
+}
+
+int orbx_compute_stereo_matches_device(orbx_handle left, int frameL, orbx_handle right, int frameR,
+                                       const orb_keypoint* dKeysL, const uint8_t* dDescL, const int* dNL, int capL,
+                                       const orb_keypoint* dKeysR, const uint8_t* dDescR, const int* dNR, int capR,
+                                       float mb, float mbf, float* dURight, float* dDepth, int* dSad, int* dKept,
+                                       void* stream) {
+    ORBX_ENTER(left);
+    if (!right) return fail(ORB_ERR_INVALID, "orbx_compute_stereo_matches_device: null right extractor");
+    if (!dKeysL || !dDescL || !dKeysR || !dDescR || !dURight || !dDepth || !dSad || !dKept || capL < 1 || capR < 1)
+        return fail(ORB_ERR_INVALID, "orbx_compute_stereo_matches_device: bad arguments");
+    if (capR > 65535) return fail(ORB_ERR_INVALID, "orbx_compute_stereo_matches_device: at most 65535 right keypoints");
+    StereoParams S;
+    ORB_CHECK(stereo_params(left, frameL, right, frameR, mb, mbf, &S, "orbx_compute_stereo_matches_device"));
+    left->launches = 0;
+    cudaStream_t st = stream ? (cudaStream_t)stream : left->stream;
+    return launch_stereo(S, dKeysL, dDescL, capL, dNL, dKeysR, dDescR, capR, dNR, dURight, dDepth, dSad, dKept, st,
+                         &left->launches);
+}
+
+int orbx_compute_stereo_matches(orbx_handle left, int frameL, orbx_handle right, int frameR, const orb_keypoint* keysL,
+                                const uint8_t* descL, int nL, const orb_keypoint* keysR, const uint8_t* descR, int nR,
+                                float mb, float mbf, float* uRight, float* depth, int* nMatches) {
+    ORBX_ENTER(left);
+    if (!right) return fail(ORB_ERR_INVALID, "orbx_compute_stereo_matches: null right extractor");
+    if (nL < 0 || nR < 0 || (nL > 0 && (!keysL || !descL || !uRight || !depth)) || (nR > 0 && (!keysR || !descR)))
+        return fail(ORB_ERR_INVALID, "orbx_compute_stereo_matches: bad arguments");
+    if (nR > 65535) return fail(ORB_ERR_INVALID, "orbx_compute_stereo_matches: at most 65535 right keypoints");
+    StereoParams S;
+    ORB_CHECK(stereo_params(left, frameL, right, frameR, mb, mbf, &S, "orbx_compute_stereo_matches"));
+    if (nMatches) *nMatches = 0;
+    if (nL == 0) return ORB_OK;
+    orbx_extractor* e = left;
+    e->launches = 0;
+    cudaStream_t st = e->stream;
+    ORB_CUDA(cudaStreamSynchronize(right->stream));     // the right pyramid must be complete
+    ORB_CHECK(e->stKeysL.reserve((size_t)nL * sizeof(orb_keypoint)));
+    ORB_CHECK(e->stDescL.reserve((size_t)nL * 32));
+    ORB_CHECK(e->stKeysR.reserve((size_t)(nR + 1) * sizeof(orb_keypoint)));
+    ORB_CHECK(e->stDescR.reserve((size_t)(nR + 1) * 32));
+    ORB_CHECK(e->stOut.reserve((size_t)nL * 12 + 16));
+    ORB_CUDA(cudaMemcpyAsync(e->stKeysL.p, keysL, (size_t)nL * sizeof(orb_keypoint), cudaMemcpyHostToDevice, st));
+    ORB_CUDA(cudaMemcpyAsync(e->stDescL.p, descL, (size_t)nL * 32, cudaMemcpyHostToDevice, st));
+    if (nR > 0) {
+        ORB_CUDA(cudaMemcpyAsync(e->stKeysR.p, keysR, (size_t)nR * sizeof(orb_keypoint), cudaMemcpyHostToDevice, st));
+        ORB_CUDA(cudaMemcpyAsync(e->stDescR.p, descR, (size_t)nR * 32, cudaMemcpyHostToDevice, st));
+    }
+    float* dU = e->stOut.as<float>();
+    float* dD = dU + nL;
+    int* dSad = (int*)(dD + nL);
+    int* dKept = dSad + nL;
+    ORB_CHECK(launch_stereo(S, e->stKeysL.as<orb_keypoint>(), e->stDescL.as<unsigned char>(), nL, nullptr,
+                            e->stKeysR.as<orb_keypoint>(), e->stDescR.as<unsigned char>(), nR, nullptr, dU, dD, dSad, dKept,
+                            st, &e->launches));
+    int kept = 0;
+    ORB_CUDA(cudaMemcpyAsync(uRight, dU, (size_t)nL * 4, cudaMemcpyDeviceToHost, st));
+    ORB_CUDA(cudaMemcpyAsync(depth, dD, (size_t)nL * 4, cudaMemcpyDeviceToHost, st));
+    ORB_CUDA(cudaMemcpyAsync(&kept, dKept, 4, cudaMemcpyDeviceToHost, st));
+    ORB_CUDA(cudaStreamSynchronize(st));
+    if (nMatches) *nMatches = kept;
+    return ORB_OK;
 }
 
 int orbx_synchronize(orbx_handle e) {

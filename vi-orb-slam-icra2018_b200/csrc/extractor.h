@@ -92,6 +92,16 @@ struct ExtractParams {
     LevelGeom lv[kMaxLevels];
 };
 
+struct StereoParams {    // Frame::ComputeStereoMatches: one frame's pyramid block of the left and of the right extractor
+    const unsigned char* pyrL;
+    const unsigned char* pyrR;
+    int nLevels, nRows;          // nRows = mvImagePyramid[0].rows
+    float maxD, mbf;             // maxD = mbf / mb
+    long long lvOff[kMaxLevels];
+    int pitch[kMaxLevels], cols[kMaxLevels], rows[kMaxLevels];
+    float scale[kMaxLevels], invScale[kMaxLevels];
+};
+
 struct BlurTile { int level, cta; };   // one CTA of the blur kernel: level and CTA index inside the level
 
 // launchers (each returns orb_status and bumps *launches)
@@ -105,6 +115,9 @@ int launch_octree(const ExtractParams& P, int smemBytes, int keyCapSmem, int nod
 int launch_blur(const ExtractParams& P, const BlurTile* dTiles, int nTiles, cudaStream_t st, int* launches);
 int launch_brief(const ExtractParams& P, int maxKeypoints, orb_keypoint* dKps, unsigned char* dDesc, int* dCount,
                  cudaStream_t st, int* launches);
+int launch_stereo(const StereoParams& P, const orb_keypoint* dKeysL, const unsigned char* dDescL, int nLmax, const int* dNL,
+                  const orb_keypoint* dKeysR, const unsigned char* dDescR, int nRmax, const int* dNR, float* dURight,
+                  float* dDepth, int* dSad, int* dKept, cudaStream_t st, int* launches);
 int octree_smem_plan(int nodeCap, int cellCap, int* smemBytes, int* keyCapSmem);
 int blur_cta_count(int w, int h);
 int upload_brief_pattern();

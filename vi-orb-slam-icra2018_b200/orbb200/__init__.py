@@ -134,6 +134,26 @@ class Extractor:
     def synchronize(self):
         _check(self.L.orbx_synchronize(self.h))
 
+    def stereo_matches(self, right, keys_l, desc_l, keys_r, desc_r, mb, mbf, frame_l=0, frame_r=0):
+        """Frame::ComputeStereoMatches on the pyramids of the last extract calls of self (left) and `right`:
+        returns (mvuRight, mvDepth, number of matches)."""
+        kl = np.ascontiguousarray(keys_l, KP_DTYPE); kr = np.ascontiguousarray(keys_r, KP_DTYPE)
+        dl = np.ascontiguousarray(desc_l, np.uint8); dr = np.ascontiguousarray(desc_r, np.uint8)
+        ur = np.empty(len(kl), np.float32)
+        depth = np.empty(len(kl), np.float32)
+        n = C.c_int()
+        _check(self.L.orbx_compute_stereo_matches(self.h, frame_l, right.h, frame_r, _p(kl), _p(dl), len(kl), _p(kr), _p(dr),
+                                                  len(kr), C.c_float(mb), C.c_float(mbf), _p(ur), _p(depth), C.byref(n)))
+        return ur, depth, n.value
+
+    def stereo_matches_device(self, right, frame_l, frame_r, d_keys_l, d_desc_l, d_n_l, d_keys_r, d_desc_r, d_n_r, mb, mbf,
+                              d_u_right, d_depth, d_sad, d_kept, stream=None):
+        """device-resident ComputeStereoMatches over one (left, right) frame of two extract_batch_device calls"""
+        _check(self.L.orbx_compute_stereo_matches_device(self.h, frame_l, right.h, frame_r, _dp(d_keys_l), _dp(d_desc_l),
+                                                         _dp(d_n_l), self.capacity, _dp(d_keys_r), _dp(d_desc_r),
+                                                         _dp(d_n_r), right.capacity, C.c_float(mb), C.c_float(mbf),
+                                                         _dp(d_u_right), _dp(d_depth), _dp(d_sad), _dp(d_kept), _dp(stream)))
+
     def tables(self):
         n = self.nlevels
         f = [np.empty(n, np.float32) for _ in range(4)]

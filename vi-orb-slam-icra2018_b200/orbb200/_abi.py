@@ -19,6 +19,9 @@ SIGNATURES = {
     "orbx_get_scale_tables": (i32, [vp, vp, vp, vp, vp, vp, vp]),
     "orbx_get_level": (i32, [vp, i32, i32, vp, vp, vp]),
     "orbx_stage_times": (i32, [vp, vp]),
+    "orbx_compute_stereo_matches": (i32, [vp, i32, vp, i32, vp, vp, i32, vp, vp, i32, f32, f32, vp, vp, vp]),
+    "orbx_compute_stereo_matches_device": (i32, [vp, i32, vp, i32, vp, vp, vp, i32, vp, vp, vp, i32, f32, f32, vp, vp,
+                                                 vp, vp, vp]),
     "orbx_debug_candidates": (i32, [vp, i32, i32, vp, i32, vp]),
     "orbx_debug_blurred": (i32, [vp, i32, i32, vp]),
     "orbx_last_launch_count": (i32, [vp, vp]),
