@@ -1,5 +1,7 @@
 """GPU parity of Frame::ComputeStereoMatches (Frame.cc:810-984) against the oracle
 restatement: mvuRight and mvDepth bit for bit (float32 with the reference's operation order), the same matches kept."""
+import os
+
 import numpy as np
 import pytest
 
@@ -8,10 +10,10 @@ from datagen import stereo_pair
 
 pytestmark = pytest.mark.gpu
 
-# EuRoC stereo rig of the reference's Examples/Stereo/EuRoC.yaml: Camera.bf = 47.90639384423901, fx = 435.2;
-# KITTI 00-02: bf = 386.1448, fx = 718.856
-RIGS = {"euroc": (752, 480, 1200, 47.90639384423901 / 435.2046959714599, 47.90639384423901),
-        "kitti": (1241, 376, 2000, 386.1448 / 718.856, 386.1448)}
+from stereo_cases import STEREO_CASES, images
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "stereo_ref_vectors.npz")
+RIGS = {"euroc": (752, 480, 1200, 47.90639384423901 / 435.2046959714599, 47.90639384423901)}
 
 
 def _oracle_stereo(oracle, left, right, nfeat, mb, mbf):
@@ -25,10 +27,11 @@ def _oracle_stereo(oracle, left, right, nfeat, mb, mbf):
     return kl, dl, kr, dr, ur, depth, sad, kept
 
 
-@pytest.mark.parametrize("rig,seed", [("euroc", 1), ("euroc", 2), ("kitti", 3)])
-def test_compute_stereo_matches(oracle, rig, seed):
-    w, h, nfeat, mb, mbf = RIGS[rig]
-    left, right = stereo_pair(seed, w, h)
+@pytest.mark.parametrize("name", sorted(STEREO_CASES))
+def test_compute_stereo_matches(oracle, name):
+    """extraction + stereo on the GPU == oracle == the reference's own Frame::ComputeStereoMatches (committed golden)"""
+    w, h, nfeat, mb, mbf, seed, disparities, same_rows = STEREO_CASES[name]
+    left, right = images(name)
     kl, dl, kr, dr, ur_ref, depth_ref, sad_ref, kept_ref = _oracle_stereo(oracle, left, right, nfeat, mb, mbf)
     exl = orbb200.Extractor(nfeat, max_width=w, max_height=h)
     exr = orbb200.Extractor(nfeat, max_width=w, max_height=h)
@@ -36,16 +39,24 @@ def test_compute_stereo_matches(oracle, rig, seed):
     gkr, gdr = exr(right)
     assert gkl.tobytes() == kl.tobytes() and gkr.tobytes() == kr.tobytes()
     ur, depth, n = exl.stereo_matches(exr, gkl, gdl, gkr, gdr, mb, mbf)
-    assert n == kept_ref and kept_ref > 150
+    assert exl.launch_count() == 2
+    assert n == kept_ref and kept_ref > 100
     assert np.array_equal(ur.view(np.uint32), ur_ref.view(np.uint32))
     assert np.array_equal(depth.view(np.uint32), depth_ref.view(np.uint32))
     assert int((ur >= 0).sum()) == n
-    # the disparities are the planted ones (sub-pixel refined)
-    ok = ur >= 0
-    disp = kl["x"][ok] - ur[ok]
-    band = np.minimum((kl["y"][ok] * 4 // h).astype(int), 3)
-    for b, d in enumerate((6, 14, 27, 41)):
-        assert abs(np.median(disp[band == b]) - d) < 0.6
+    g = np.load(GOLDEN)
+    assert n == int(g[name + "/kept"])
+    assert np.array_equal(ur.view(np.uint32), g[name + "/u_right"].view(np.uint32))
+    assert np.array_equal(depth.view(np.uint32), g[name + "/depth"].view(np.uint32))
+    if name == "euroc_zero":
+        assert (depth == np.float32(mbf) / np.float32(0.01)).any()     # the disparity <= 0 branch was taken
+    else:   # the disparities are the planted ones (sub-pixel refined) wherever mbf/mb admits them
+        ok = ur >= 0
+        disp = kl["x"][ok] - ur[ok]
+        band = np.minimum((kl["y"][ok] * 4 // h).astype(int), 3)
+        for b, d in enumerate(disparities):
+            if d < mbf / mb - 1 and (band == b).sum() > 10:
+                assert abs(np.median(disp[band == b]) - d) < 0.6
     exl.close()
     exr.close()
 
@@ -99,24 +110,6 @@ def test_stereo_edge_cases(oracle):
     assert n == 0 and (ur == -1).all() and (depth == -1).all()
     ur, depth, n = exl.stereo_matches(exr, kl[:0], dl[:0], kr, dr, mb, mbf)
     assert n == 0 and len(ur) == 0
-    # zero disparity, and the top of the right image identical to the left: SAD 0 with a symmetric parabola gives a
-    # disparity of exactly 0 -> the reference's disparity<=0 branch (0.01 px, bestuR = uL - 0.01 in double)
-    l0, r0 = stereo_pair(4, w, h, disparities=(0, 0, 0, 0))
-    r0[:150] = l0[:150]
-    kl0, dl0 = exl(l0)
-    kr0, dr0 = exr(r0)
-    ur, depth, n = exl.stereo_matches(exr, kl0, dl0, kr0, dr0, mb, mbf)
-    el, er = oracle.extractor(nfeat), oracle.extractor(nfeat)
-    el.extract(l0)
-    er.extract(r0)
-    t = el.tables()
-    ur_ref, depth_ref, sad_ref, kept_ref = oracle.stereo(kl0, dl0, kr0, dr0, [el.level_padded(i) for i in range(8)],
-                                                         [er.level_padded(i) for i in range(8)], t["scale"],
-                                                         t["inv_scale"], mb, mbf)
-    assert n == kept_ref and n > 300
-    assert np.array_equal(ur.view(np.uint32), ur_ref.view(np.uint32))
-    assert np.array_equal(depth.view(np.uint32), depth_ref.view(np.uint32))
-    assert (depth_ref == np.float32(mbf) / np.float32(0.01)).any()
     # mismatched extractors are refused
     other = orbb200.Extractor(nfeat, max_width=640, max_height=480)
     other(left[:480, :640].copy())

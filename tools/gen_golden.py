@@ -6,6 +6,8 @@ OpenCV stand-in (oracle/ref_shim), i.e. they are outputs of the reference itself
 Matcher vectors: matcher_ref_vectors.npz holds outputs of oracle/_ref/libmatch_ref.so = the reference's OWN
 src/ORBmatcher.cc compiled in place against the stand-ins of oracle/ref_shim/matcher (seeded cases of
 tests/matcher_cases.py); matcher_vectors.npz (grid CSR, brute force) is produced by oracle/match_oracle.cpp and says so.
+Stereo vectors: stereo_ref_vectors.npz holds outputs of oracle/_ref/libstereo_ref.so = the reference's OWN text of
+Frame::ComputeStereoMatches compiled in place (seeded cases of tests/stereo_cases.py; --stereo-only regenerates just these).
 """
 import hashlib
 import os
@@ -110,7 +112,34 @@ def main():
     np.savez_compressed(os.path.join(OUT, "matcher_ref_vectors.npz"), cases=np.array(CASES),
                         pinned_by="reference (oracle/_ref/libmatch_ref.so = /root/reference/src/ORBmatcher.cc compiled in place)",
                         **save)
+    stereo_golden()
+
+
+def stereo_golden():
+    """stereo_ref_vectors.npz: mvuRight / mvDepth of the reference's own Frame::ComputeStereoMatches text
+    (oracle/_ref/libstereo_ref.so) on the seeded cases of tests/stereo_cases.py"""
+    import ref_stereo
+    from stereo_cases import STEREO_CASES, images, oracle_inputs
+    if not ref_stereo.available():
+        ref_stereo.build()
+    o = Oracle()
+    save = {}
+    for name in sorted(STEREO_CASES):
+        left, right = images(name)
+        ur, depth, kept = ref_stereo.stereo(*oracle_inputs(o, name))
+        save[name + "/u_right"] = ur
+        save[name + "/depth"] = depth
+        save[name + "/kept"] = np.int32(kept)
+        save[name + "/left_sha256"] = sha(left)
+        save[name + "/right_sha256"] = sha(right)
+        print("reference stereo", name, kept, "of", len(ur))
+    np.savez_compressed(os.path.join(OUT, "stereo_ref_vectors.npz"),
+                        pinned_by="reference (oracle/_ref/libstereo_ref.so = Frame::ComputeStereoMatches of "
+                                  "/root/reference/src/Frame.cc compiled in place)", **save)
 
 
 if __name__ == "__main__":
-    main()
+    if "--stereo-only" in sys.argv:
+        stereo_golden()
+    else:
+        main()
