@@ -279,6 +279,14 @@ int orbm_allpairs_device(orbm_handle h, const uint8_t* d_table, const float* d_a
                          int q_begin, int q_end, int db_begin, int db_end, float nnratio, int check_orientation,
                          int* d_counts, void* stream);
 
+/* MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:257-322) for n_points map points in one call (LocalMapping runs it
+ * for every point a new keyframe touches): point p is observed by descriptors[start[p] .. start[p+1]) -- rows of 32 B in
+ * mObservations order, bad keyframes already dropped; start[0] = 0.  best[p] = index INSIDE the point's run of the
+ * descriptor whose median distance to all of the run (itself included, rank (size_t)(0.5*(N-1))) is smallest, the first
+ * such row winning; -1 for an empty run.  best_median (may be NULL) receives that median.                          */
+int orbm_distinctive_descriptors(orbm_handle h, const uint8_t* descriptors, const int* start, int n_points, int* best,
+                                 int* best_median);
+
 /* Measured POPC-pipe throughput of this GPU (the roofline denominator for matching): 32-bit POPC per second. */
 int orbm_popc_peak(orbm_handle h, double* popc_per_s);
 

@@ -417,6 +417,32 @@ int kf_pair_match_count(const uint8_t* d1, const float* a1, int n1, const uint8_
 }
 
 // ---------------------------------------------------------------------------------------------
+// MapPoint::ComputeDistinctiveDescriptors, MapPoint.cc:257-322
+// ---------------------------------------------------------------------------------------------
+int distinctive_descriptor(const uint8_t* desc, int n, int* bestMedian) {
+    if (bestMedian) *bestMedian = INT_MAX;
+    if (n <= 0) return -1;                                                    // :271-272, :285-286
+    std::vector<float> D((size_t)n * n);                                      // float Distances[N][N], :291
+    for (int i = 0; i < n; ++i) {
+        D[(size_t)i * n + i] = 0;
+        for (int j = i + 1; j < n; ++j) {
+            const int d = descriptor_distance(desc + 32 * (size_t)i, desc + 32 * (size_t)j);
+            D[(size_t)i * n + j] = (float)d;
+            D[(size_t)j * n + i] = (float)d;
+        }
+    }
+    int best = INT_MAX, bestIdx = 0;                                          // :305-318
+    for (int i = 0; i < n; ++i) {
+        std::vector<int> v(D.begin() + (size_t)i * n, D.begin() + (size_t)(i + 1) * n);
+        std::sort(v.begin(), v.end());
+        const int median = v[(size_t)(0.5 * (n - 1))];
+        if (median < best) { best = median; bestIdx = i; }
+    }
+    if (bestMedian) *bestMedian = best;
+    return bestIdx;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Frame::ComputeStereoMatches, Frame.cc:810-984
 // ---------------------------------------------------------------------------------------------
 int compute_stereo_matches(const KeyPoint* keysL, const uint8_t* descL, int nL, const KeyPoint* keysR, const uint8_t* descR,

@@ -109,6 +109,12 @@ int bruteforce_match(const uint8_t* q, const float* qAngle, int nq, const uint8_
 int kf_pair_match_count(const uint8_t* d1, const float* a1, int n1, const uint8_t* d2, const float* a2, int n2,
                         float nnratio, bool checkOri, int* matches12 /* may be null */);
 
+// MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:257-322): among the n descriptors observing one map point (in
+// mObservations order, bad keyframes removed) the one whose MEDIAN Hamming distance to all of them (its own 0 included,
+// median = sorted[(size_t)(0.5*(n-1))]) is smallest; the first such row wins.  Returns its index (-1 for n == 0) and
+// the median through *bestMedian.
+int distinctive_descriptor(const uint8_t* desc, int n, int* bestMedian);
+
 // Frame::ComputeStereoMatches (Frame.cc:810-984): for every left keypoint the closest right descriptor among the right
 // keypoints whose row band covers the left keypoint's row (band = +-2*scale[octave]), octave within +-1, uR in
 // [uL - mbf/mb, uL]; accepted below (TH_HIGH+TH_LOW)/2; refined by an 11x11 centre-normalised SAD over 11 horizontal

@@ -194,6 +194,10 @@ int orbo_bruteforce(const uint8_t* q, const float* qa, int nq, const uint8_t* t,
                     int checkOri, int* best, int* second, int* idx, int* m12) {
     return bruteforce_match(q, qa, nq, t, ta, nt, ratio, checkOri != 0, best, second, idx, m12);
 }
+void orbo_distinctive(const uint8_t* desc, const int* start, int nPoints, int* best, int* bestMedian) {
+    for (int p = 0; p < nPoints; ++p)
+        best[p] = distinctive_descriptor(desc + 32 * (size_t)start[p], start[p + 1] - start[p], bestMedian + p);
+}
 int orbo_stereo(const KeyPoint* keysL, const uint8_t* descL, int nL, const KeyPoint* keysR, const uint8_t* descR, int nR,
                 const uint8_t* const* paddedL, const uint8_t* const* paddedR, const int* cols, const int* rows, int nLevels,
                 const float* sf, const float* isf, float mb, float mbf, float* uRight, float* depth, int* sad) {

@@ -50,6 +50,7 @@ class Oracle:
         L.orbo_level_selected.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         L.orbo_stage_ms.argtypes = [C.c_void_p, C.c_void_p]
         L.orbo_undistort.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.orbo_distinctive.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.orbo_stereo.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_float,
                                   C.c_void_p, C.c_void_p, C.c_void_p]
@@ -188,6 +189,14 @@ class Oracle:
 
     def frame(self, keys_un, desc, bounds):
         return OracleFrame(self, keys_un, desc, bounds)
+
+    def distinctive(self, desc, start):
+        """MapPoint::ComputeDistinctiveDescriptors for len(start)-1 map points (CSR runs of `desc`): (best, median)"""
+        d = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        st = np.ascontiguousarray(start, np.int32)
+        best = np.empty(len(st) - 1, np.int32); med = np.empty(len(st) - 1, np.int32)
+        self.lib.orbo_distinctive(_p(d), _p(st), len(st) - 1, _p(best), _p(med))
+        return best, med
 
     def stereo(self, keys_l, desc_l, keys_r, desc_r, levels_l, levels_r, scale, inv_scale, mb, mbf):
         """Frame::ComputeStereoMatches; levels_* = lists of padded (h+38, w+38) uint8 arrays (mvImagePyramid).

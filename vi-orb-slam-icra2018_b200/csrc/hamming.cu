@@ -348,6 +348,72 @@ int launch_distance(const uint8_t* da, const uint8_t* db, int n, int* dOut, cuda
     return ORB_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ distinctive descriptor
+// MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:257-322) for a batch of map points.  The reference fills an N x N
+// float matrix, sorts every row and takes element (size_t)(0.5*(N-1)).  Distances are integers in [0, 256], so the median
+// of a row is read off a 257-bin histogram: CTA per map point, warp per row; lanes stride over the columns and count into
+// the warp's shared histogram, then a warp scan over the bins (9 per lane) finds the first bin whose cumulative count
+// exceeds the median rank.  (median, row) keys are min-reduced per CTA: the first row with the smallest median wins.
+constexpr int kDistWarps = 8;
+constexpr int kDistBins = 288;   // 257 bins padded to 9 per lane
+
+__global__ void __launch_bounds__(kDistWarps * 32)
+distinctive_kernel(const uint4* __restrict__ desc, const int* __restrict__ start, int nPoints, int* __restrict__ best,
+                   int* __restrict__ bestMedian) {
+    __shared__ int hist[kDistWarps][kDistBins];
+    __shared__ unsigned bestKey;
+    const int p = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int s0 = start[p], n = start[p + 1] - s0;
+    if (threadIdx.x == 0) bestKey = 0xffffffffu;
+    __syncthreads();
+    if (n > 0) {
+        const uint4* d = desc + 2 * (size_t)s0;
+        const int rank = (int)(0.5 * (double)(n - 1));          // vDists[0.5*(N-1)], :311
+        for (int i = warp; i < n; i += kDistWarps) {
+            for (int b = lane; b < kDistBins; b += 32) hist[warp][b] = 0;
+            __syncwarp();
+            const uint4 a0 = __ldg(&d[2 * i]), a1 = __ldg(&d[2 * i + 1]);
+            for (int j = lane; j < n; j += 32)
+                atomicAdd(&hist[warp][hamming256(a0, a1, __ldg(&d[2 * j]), __ldg(&d[2 * j + 1]))], 1);
+            __syncwarp();
+            int c[9], sum = 0;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) { c[k] = hist[warp][lane * 9 + k]; sum += c[k]; }
+            int incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            int before = incl - sum, median = 0x7fff;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {                       // first bin with cumulative count > rank
+                if (median == 0x7fff && before + c[k] > rank) median = lane * 9 + k;
+                before += c[k];
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) median = min(median, __shfl_xor_sync(0xffffffffu, median, o));
+            if (lane == 0) atomicMin(&bestKey, ((unsigned)median << 16) | (unsigned)i);
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        best[p] = n > 0 ? (int)(bestKey & 0xffffu) : -1;
+        if (bestMedian) bestMedian[p] = n > 0 ? (int)(bestKey >> 16) : 0x7fffffff;
+    }
+}
+
+int launch_distinctive(const uint8_t* dDesc, const int* dStart, int nPoints, int* dBest, int* dBestMedian, cudaStream_t st,
+                       int* launches) {
+    if (nPoints <= 0) return ORB_OK;
+    distinctive_kernel<<<nPoints, kDistWarps * 32, 0, st>>>((const uint4*)dDesc, dStart, nPoints, dBest, dBestMedian);
+    if (launches) *launches += 1;
+    ORB_CUDA(cudaGetLastError());
+    return ORB_OK;
+}
+
 int measure_popc_peak(cudaStream_t st, double* popcPerS) {
     unsigned* d = nullptr;
     ORB_CUDA(cudaMalloc(&d, 4));

@@ -10,6 +10,8 @@ int launch_bruteforce(const uint8_t* dq, const float* dqa, int nq, const uint8_t
 int launch_allpairs(const uint8_t* dTable, const float* dAngles, int nKf, int nDesc, int qBegin, int qEnd, int dbBegin,
                     int dbEnd, float ratio, int checkOri, int* dCounts, cudaStream_t st, int* launches);
 int launch_distance(const uint8_t* da, const uint8_t* db, int n, int* dOut, cudaStream_t st, int* launches);
+int launch_distinctive(const uint8_t* dDesc, const int* dStart, int nPoints, int* dBest, int* dBestMedian, cudaStream_t st,
+                       int* launches);
 int measure_popc_peak(cudaStream_t st, double* popcPerS);
 
 }  // namespace orbb

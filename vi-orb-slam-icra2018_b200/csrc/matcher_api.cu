@@ -144,6 +144,34 @@ int orbm_allpairs_device(orbm_handle h, const uint8_t* dTable, const float* dAng
                            &h->launches);
 }
 
+int orbm_distinctive_descriptors(orbm_handle h, const uint8_t* desc, const int* start, int nPoints, int* best,
+                                 int* bestMedian) {
+    ORBM_ENTER(h);
+    if (nPoints < 0 || (nPoints > 0 && (!start || !best))) return fail(ORB_ERR_INVALID, "orbm_distinctive_descriptors: bad arguments");
+    if (nPoints == 0) return ORB_OK;
+    if (start[0] != 0) return fail(ORB_ERR_INVALID, "orbm_distinctive_descriptors: start[0] must be 0");
+    for (int p = 0; p < nPoints; ++p) {
+        const int n = start[p + 1] - start[p];
+        if (n < 0 || n > 65535)
+            return fail(ORB_ERR_INVALID, "orbm_distinctive_descriptors: map point %d has %d observations (0..65535)", p, n);
+    }
+    const int total = start[nPoints];
+    if (total > 0 && !desc) return fail(ORB_ERR_INVALID, "orbm_distinctive_descriptors: null descriptors");
+    cudaStream_t st = h->stream;
+    ORB_CHECK(h->in0.reserve((size_t)total * 32 + 32));
+    ORB_CHECK(h->in1.reserve((size_t)(nPoints + 1) * 4));
+    ORB_CHECK(h->out0.reserve((size_t)nPoints * 4));
+    ORB_CHECK(h->out1.reserve((size_t)nPoints * 4));
+    if (total > 0) ORB_CUDA(cudaMemcpyAsync(h->in0.p, desc, (size_t)total * 32, cudaMemcpyHostToDevice, st));
+    ORB_CUDA(cudaMemcpyAsync(h->in1.p, start, (size_t)(nPoints + 1) * 4, cudaMemcpyHostToDevice, st));
+    ORB_CHECK(launch_distinctive(h->in0.as<uint8_t>(), h->in1.as<int>(), nPoints, h->out0.as<int>(), h->out1.as<int>(), st,
+                                 &h->launches));
+    ORB_CUDA(cudaMemcpyAsync(best, h->out0.p, (size_t)nPoints * 4, cudaMemcpyDeviceToHost, st));
+    if (bestMedian) ORB_CUDA(cudaMemcpyAsync(bestMedian, h->out1.p, (size_t)nPoints * 4, cudaMemcpyDeviceToHost, st));
+    ORB_CUDA(cudaStreamSynchronize(st));
+    return ORB_OK;
+}
+
 int orbm_popc_peak(orbm_handle h, double* popcPerS) {
     ORBM_ENTER(h);
     if (!popcPerS) return fail(ORB_ERR_INVALID, "orbm_popc_peak: null out");

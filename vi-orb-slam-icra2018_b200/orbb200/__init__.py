@@ -345,6 +345,15 @@ class Matcher:
         _check(self.L.orbm_allpairs_device(self.h, _dp(d_table), _dp(d_angles), n_kf, n_desc, q_begin, q_end, db_begin,
                                            db_end, C.c_float(ratio), int(check_ori), _dp(d_counts), _dp(stream)))
 
+    def distinctive_descriptors(self, desc, start):
+        """MapPoint::ComputeDistinctiveDescriptors for len(start)-1 map points: (best index inside each run, median)"""
+        d = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        st = np.ascontiguousarray(start, np.int32)
+        best = np.empty(len(st) - 1, np.int32)
+        med = np.empty(len(st) - 1, np.int32)
+        _check(self.L.orbm_distinctive_descriptors(self.h, _p(d), _p(st), len(st) - 1, _p(best), _p(med)))
+        return best, med
+
     def popc_peak(self):
         v = C.c_double()
         _check(self.L.orbm_popc_peak(self.h, C.byref(v)))

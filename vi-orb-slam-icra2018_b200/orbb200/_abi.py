@@ -53,6 +53,7 @@ SIGNATURES = {
     "orbm_bruteforce":(i32, [vp, vp, vp, i32, vp, vp, i32, i32, f32, i32, vp, vp, vp, vp, vp]),
     "orbm_bruteforce_device": (i32, [vp, vp, vp, i32, vp, vp, i32, i32, f32, i32, vp, vp, vp, vp, vp, vp]),
     "orbm_allpairs_device": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, f32, i32, vp, vp]),
+    "orbm_distinctive_descriptors": (i32, [vp, vp, vp, i32, vp, vp]),
     "orbm_popc_peak": (i32, [vp, vp]),
 }
 
