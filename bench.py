@@ -176,6 +176,37 @@ def cpu_matcher_reference():
             out["search_kind"] = "reference (ORBmatcher.cc compiled in place, -O2; time of the search call alone)"
     except Exception as ex:  # the .so may be missing on a box that never saw /root/reference
         out["search_kind"] = "unavailable: %s" % ex
+    try:   # CPU side of the section-8f rows: the reference's own ComputeStereoMatches text, the oracle's distinctive loop
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import ref_stereo
+        from datagen import stereo_pair
+        left, right = stereo_pair(1, 752, 480)
+        el, er = o.extractor(1200, SCALE, NLEVELS, INI_TH, MIN_TH), o.extractor(1200, SCALE, NLEVELS, INI_TH, MIN_TH)
+        kl, dl = el.extract(left)
+        kr, dr = er.extract(right)
+        tb = el.tables()
+        LL = [el.level_padded(i) for i in range(8)]
+        RR = [er.level_padded(i) for i in range(8)]
+        mb, mbf = 47.90639384423901 / 435.2046959714599, 47.90639384423901
+        fn = ref_stereo.stereo if ref_stereo.available() else (lambda *a: o.stereo(*a))
+        ts = []
+        for _ in range(7):
+            t0 = time.perf_counter()
+            fn(kl, dl, kr, dr, LL, RR, tb["scale"], tb["inv_scale"], mb, mbf)
+            ts.append((time.perf_counter() - t0) * 1e3)
+        out["stereo_matches_euroc_752x480_ms"] = float(np.median(ts))
+        out["stereo_kind"] = ("reference (Frame::ComputeStereoMatches compiled in place behind cv::Mat stand-ins, -O2)"
+                              if ref_stereo.available() else "port (oracle/match_oracle.cpp)")
+        rng = np.random.default_rng(3)
+        sizes = rng.integers(2, 41, 2000)
+        start = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+        desc = rng.integers(0, 256, (int(start[-1]), 32), dtype=np.uint8)
+        t0 = time.perf_counter()
+        o.distinctive(desc, start)
+        out["distinctive_descriptors_20000_points_ms"] = (time.perf_counter() - t0) * 1e3 * 10
+        out["distinctive_kind"] = "port (oracle/match_oracle.cpp), 2000 points timed and scaled x10"
+    except Exception as ex:
+        out["frame_side_kind"] = "unavailable: %s" % ex
     return out
 
 
@@ -222,7 +253,64 @@ def single_frame_latency(device, iters=30):
             out["search_by_projection_th15"] = med(lambda: m.search_by_projection(f2, sf, q, da, 15.0, 0, None, None, 0.0, True))
             out["search_by_projection_matches"] = int(m.search_by_projection(f2, sf, q, da, 15.0, 0, None, None, 0.0, True)[0])
         f1.close(); f2.close(); ex.close()
+    try:
+        out.update(frame_side_latency(device, m, med))
+    except Exception as exn:   # the widened rows (section 8f) must never cost the headline line
+        out["frame_side_error"] = repr(exn)
     m.close()
+    return out
+
+
+def frame_side_latency(device, m, med):
+    """SURVEY section 8f ranks 2-4, host to host unless stated: Frame post-extraction kept on the device
+    (orbm_frame_create_device: undistortion + grid, EuRoC camera of Examples/Monocular/EuRoC.yaml), ComputeStereoMatches on
+    an EuRoC-shaped rectified pair, ComputeDistinctiveDescriptors for a LocalMapping-sized batch of map points."""
+    import numpy as np
+    import torch
+    import orbb200
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from datagen import stereo_pair
+    out = {}
+    w, h = 752, 480
+    left, right = stereo_pair(1, w, h)
+    mb, mbf = 47.90639384423901 / 435.2046959714599, 47.90639384423901
+    exl = orbb200.Extractor(1200, SCALE, NLEVELS, INI_TH, MIN_TH, max_width=w, max_height=h, max_batch=1, device=device)
+    exr = orbb200.Extractor(1200, SCALE, NLEVELS, INI_TH, MIN_TH, max_width=w, max_height=h, max_batch=1, device=device)
+    kl, dl = exl(left)
+    kr, dr = exr(right)
+    out["stereo_matches_euroc_752x480"] = med(lambda: exl.stereo_matches(exr, kl, dl, kr, dr, mb, mbf))
+    out["stereo_matches_kept"] = int(exl.stereo_matches(exr, kl, dl, kr, dr, mb, mbf)[2])
+    out["stereo_frame_euroc_752x480"] = med(lambda: (exl(left), exr(right), exl.stereo_matches(exr, kl, dl, kr, dr, mb, mbf)))
+    # device-resident hand-over: keypoints stay where the extractor wrote them
+    cam = orbb200.camera(458.654, 457.296, 367.215, 248.375, -0.28340811, 0.07395907, 0.00019359, 1.76187114e-05)
+    cap = exl.capacity
+    with torch.cuda.device(device):
+        d_img = torch.from_numpy(left[None]).cuda()
+        d_k = torch.zeros((1, cap, 7), dtype=torch.int32, device="cuda")
+        d_d = torch.zeros((1, cap, 32), dtype=torch.uint8, device="cuda")
+        d_n = torch.zeros(1, dtype=torch.int32, device="cuda")
+    exl.extract_batch_device(d_img, d_k, d_d, d_n)
+    exl.synchronize()
+    bounds = m.image_bounds(cam, w, h)
+    out["frame_create_device_undistort_grid"] = med(
+        lambda: orbb200.Frame.from_device(m, d_k[0], d_d[0], d_n, cap, bounds, cam).close())
+    xy = np.stack([kl["x"], kl["y"]], 1)
+
+    def host_chain():
+        ku = kl.copy()
+        un = m.undistort_points(cam, xy)
+        ku["x"], ku["y"] = un[:, 0], un[:, 1]
+        m.frame(ku, dl, bounds).close()
+    out["frame_create_host_undistort_grid"] = med(host_chain)
+    # distinctive descriptors: 20 000 map points with 2..40 observations
+    rng = np.random.default_rng(3)
+    sizes = rng.integers(2, 41, 20000)
+    start = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    desc = rng.integers(0, 256, (int(start[-1]), 32), dtype=np.uint8)
+    out["distinctive_descriptors_20000_points"] = med(lambda: m.distinctive_descriptors(desc, start))
+    out["distinctive_descriptors_observations"] = int(start[-1])
+    exl.close()
+    exr.close()
     return out
 
 
