@@ -9,16 +9,16 @@
 // Here every left keypoint is independent until the median step, so: one warp per left keypoint; lanes stride over ALL
 // right keypoints and apply the row-band test directly (nR is one or two thousand: the row table would cost more than
 // the 12 bytes per test it saves); (distance, index) keys are min-reduced by shuffle; the same warp stages the two
-// patches in shared memory, lanes 0..10 each sum one shift in integers (the reference's float differences and its
-// double accumulation are exact on these integer-valued operands), lane 0 fits the parabola with separately rounded
-// float operations.  A second one-block kernel finds the median by counting ranks and withdraws the outliers.
+// patches in shared memory, the 11 shifts x 11 patch rows are summed by all lanes in integers (the reference's float
+// differences and its double accumulation are exact on these integer-valued operands), lane 0 fits the parabola with separately rounded
+// float operations.  A second one-block kernel finds the median by a two-pass radix select and withdraws the outliers.
 #include "extractor.h"
 
 namespace orbb {
 
 namespace {
 
-constexpr int kWarpsPerCta = 8;
+constexpr int kWarpsPerCta = 4;
 constexpr int kW = 5, kL = 5;                      // Frame.cc:907, :915
 constexpr int kPatchL = (2 * kW + 1) * (2 * kW + 1);                 // 121
 constexpr int kRowR = 2 * (kW + kL) + 1;                              // 21 columns cover every shifted window
@@ -34,6 +34,7 @@ stereo_match_kernel(StereoParams P, const orb_keypoint* __restrict__ keysL, cons
                     int* __restrict__ sad) {
     __shared__ short sL[kWarpsPerCta][kPatchL + 7];
     __shared__ short sR[kWarpsPerCta][kPatchR + 1];
+    __shared__ int sSad[kWarpsPerCta][2 * kL + 2];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int iL = blockIdx.x * kWarpsPerCta + warp;
     const int nL = dNL ? min(*dNL, nLmax) : nLmax;
@@ -83,17 +84,24 @@ stereo_match_kernel(StereoParams P, const orb_keypoint* __restrict__ keysL, cons
     for (int i = lane; i < kPatchL; i += 32) sL[warp][i] = baseL[(i / 11) * pitch + (i % 11)];
     for (int i = lane; i < kPatchR; i += 32) sR[warp][i] = baseR[(i / kRowR) * pitch + (i % kRowR)];
     __syncwarp();
-    int mySad = 0x7fffffff >> 4;
-    if (lane < 2 * kL + 1) {                                                    // shift incR = lane - L, :923-937
+    // 11 shifts x 11 patch rows = 121 row sums spread over the 32 lanes, added up per shift in shared memory
+    if (lane < 2 * kL + 1) sSad[warp][lane] = 0;
+    __syncwarp();
+    {
         const int cL = sL[warp][kW * 11 + kW];
-        const int cR = sR[warp][kW * kRowR + lane + kW];
-        int acc = 0;
-        for (int y = 0; y < 11; ++y)
+        for (int t = lane; t < (2 * kL + 1) * 11; t += 32) {
+            const int inc = t / 11, y = t - inc * 11;                           // shift incR = inc - L, :923-937
+            const int cR = sR[warp][kW * kRowR + inc + kW];
+            int acc = 0;
 #pragma unroll
             for (int x = 0; x < 11; ++x)
-                acc += abs((sL[warp][y * 11 + x] - cL) - (sR[warp][y * kRowR + lane + x] - cR));
-        mySad = acc;
+                acc += abs((sL[warp][y * 11 + x] - cL) - (sR[warp][y * kRowR + inc + x] - cR));
+            atomicAdd(&sSad[warp][inc], acc);
+        }
     }
+    __syncwarp();
+    int mySad = 0x7fffffff >> 4;
+    if (lane < 2 * kL + 1) mySad = sSad[warp][lane];
     unsigned sk = ((unsigned)mySad << 4) | (unsigned)(lane & 15);               // first minimum wins
     if (lane >= 2 * kL + 1) sk = 0xffffffffu;
 #pragma unroll
@@ -123,17 +131,45 @@ stereo_match_kernel(StereoParams P, const orb_keypoint* __restrict__ keysL, cons
 }
 
 // sort(vDistIdx); median = vDistIdx[size/2].first; thDist = 1.5f*1.4f*median; withdraw every match with SAD >= thDist
-// (Frame.cc:971-984).  Only the VALUE of the (size/2)-th smallest SAD matters: it is the SAD whose strict rank is
-// <= size/2 and whose inclusive rank is > size/2.
+// (Frame.cc:971-984).  Only the VALUE of the (size/2)-th smallest SAD matters, and a SAD is at most 121 * 510 < 2^16:
+// two-pass radix select over 256-bin shared histograms (high byte, then low byte inside the selected bin).
+__device__ __forceinline__ int select_bin(const int* hist, int rank, int* before) {   // warp 0: first bin with cum > rank
+    const int lane = threadIdx.x & 31;
+    int c[8], sum = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { c[k] = hist[lane * 8 + k]; sum += c[k]; }
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    int run = incl - sum, bin = 0x7fff, bef = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        if (bin == 0x7fff && run + c[k] > rank) { bin = lane * 8 + k; bef = run; }
+        run += c[k];
+    }
+    const int key = __reduce_min_sync(0xffffffffu, bin);
+    const int src = __ffs(__ballot_sync(0xffffffffu, bin == key)) - 1;
+    *before = __shfl_sync(0xffffffffu, bef, src);
+    return key;
+}
+
 __global__ void __launch_bounds__(1024)
 stereo_median_kernel(int nLmax, const int* __restrict__ dNL, float* __restrict__ uRight, float* __restrict__ depth,
                      int* __restrict__ sad, int* __restrict__ kept) {
-    __shared__ int sCount, sMedian, sKept;
+    __shared__ int hist[256];
+    __shared__ int sCount, sHigh, sRank, sMedian, sKept;
     const int nL = dNL ? min(*dNL, nLmax) : nLmax;
-    if (threadIdx.x == 0) { sCount = 0; sMedian = -1; sKept = 0; }
+    if (threadIdx.x < 256) hist[threadIdx.x] = 0;
+    if (threadIdx.x == 0) { sCount = 0; sKept = 0; }
     __syncthreads();
     int c = 0;
-    for (int i = threadIdx.x; i < nL; i += blockDim.x) c += sad[i] >= 0;
+    for (int i = threadIdx.x; i < nL; i += blockDim.x) {
+        const int s = sad[i];
+        if (s >= 0) { ++c; atomicAdd(&hist[min(s >> 8, 255)], 1); }
+    }
     if (c) atomicAdd(&sCount, c);
     __syncthreads();
     const int count = sCount;
@@ -141,17 +177,24 @@ stereo_median_kernel(int nLmax, const int* __restrict__ dNL, float* __restrict__
         if (threadIdx.x == 0) *kept = 0;
         return;
     }
-    const int k = count / 2;
+    if (threadIdx.x < 32) {
+        int before;
+        const int hi = select_bin(hist, count / 2, &before);
+        if (threadIdx.x == 0) { sHigh = hi; sRank = count / 2 - before; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 256) hist[threadIdx.x] = 0;
+    __syncthreads();
+    const int hi = sHigh;
     for (int i = threadIdx.x; i < nL; i += blockDim.x) {
         const int s = sad[i];
-        if (s < 0) continue;
-        int less = 0, leq = 0;
-        for (int j = 0; j < nL; ++j) {
-            const int t = __ldg(&sad[j]);
-            less += (t >= 0) & (t < s);
-            leq += (t >= 0) & (t <= s);
-        }
-        if (less <= k && k < leq) sMedian = s;
+        if (s >= 0 && min(s >> 8, 255) == hi) atomicAdd(&hist[s & 255], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        int before;
+        const int lo = select_bin(hist, sRank, &before);
+        if (threadIdx.x == 0) sMedian = (hi << 8) | lo;
     }
     __syncthreads();
     const float thDist = __fmul_rn(1.5f * 1.4f, (float)sMedian);
@@ -164,13 +207,11 @@ stereo_median_kernel(int nLmax, const int* __restrict__ dNL, float* __restrict__
         } else {
             uRight[i] = -1.0f;
             depth[i] = -1.0f;
+            sad[i] = -1;
         }
     }
     if (mine) atomicAdd(&sKept, mine);
     __syncthreads();
-    // the SADs of withdrawn matches are cleared last: every thread above compared against the unmodified list
-    for (int i = threadIdx.x; i < nL; i += blockDim.x)
-        if (sad[i] >= 0 && !((float)sad[i] < thDist)) sad[i] = -1;
     if (threadIdx.x == 0) *kept = sKept;
 }
 
