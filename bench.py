@@ -281,6 +281,14 @@ def frame_side_latency(device, m, med):
     out["stereo_matches_euroc_752x480"] = med(lambda: exl.stereo_matches(exr, kl, dl, kr, dr, mb, mbf))
     out["stereo_matches_kept"] = int(exl.stereo_matches(exr, kl, dl, kr, dr, mb, mbf)[2])
     out["stereo_frame_euroc_752x480"] = med(lambda: (exl(left), exr(right), exl.stereo_matches(exr, kl, dl, kr, dr, mb, mbf)))
+    ex2 = orbb200.Extractor(1200, SCALE, NLEVELS, INI_TH, MIN_TH, max_width=w, max_height=h, max_batch=2, device=device)
+    both = np.stack([left, right])
+
+    def one_handle():
+        (a, da), (b, db) = ex2.extract_batch(both)
+        ex2.stereo_matches(ex2, a, da, b, db, mb, mbf, frame_l=0, frame_r=1)
+    out["stereo_frame_one_batch_of_two"] = med(one_handle)
+    ex2.close()
     # device-resident hand-over: keypoints stay where the extractor wrote them
     cam = orbb200.camera(458.654, 457.296, 367.215, 248.375, -0.28340811, 0.07395907, 0.00019359, 1.76187114e-05)
     cap = exl.capacity

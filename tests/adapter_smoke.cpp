@@ -6,6 +6,7 @@
 
 #include "ORBextractor.h"
 #include "ORBmatcher.h"
+#include "Frame.h"
 
 int main(int argc, char** argv) {
     if (argc < 4) return 2;
@@ -31,6 +32,26 @@ int main(int argc, char** argv) {
         printf("%zu %llu %d %d %.3f\n", keys.size(), sum, n, extractor.GetLevels(), extractor.GetScaleFactors()[7]);
         const int d = matcher.DescriptorDistance(desc.data(), desc.data() + 32);
         printf("%d\n", d);
+        // Frame post-processing mirrors (adapter/Frame.h): third line = "kept minX maxY sum(mvKeysUn.x) best0 best1"
+        namespace fo = ORB_SLAM2::frame_ops;
+        ORB_SLAM2::ORBextractor right(1000, 1.2f, 8, 20, 7);
+        std::vector<orb_keypoint> keysR;
+        std::vector<unsigned char> descR;
+        right(img.data(), w, h, w, keysR, descR);          // right view = left view: zero disparity
+        std::vector<float> uRight, depth;
+        const int kept = fo::ComputeStereoMatches(extractor, right, keys, desc, keysR, descR, 0.11f, 47.9f, uRight, depth);
+        const orb_camera cam = fo::MakeCamera(458.654f, 457.296f, 367.215f, 248.375f, -0.28340811f, 0.07395907f, 0.00019359f, 1.76187114e-05f);
+        float minX, maxX, minY, maxY;
+        fo::ComputeImageBounds(matcher.handle(), cam, w, h, minX, maxX, minY, maxY);
+        std::vector<orb_keypoint> keysUn;
+        fo::UndistortKeyPoints(matcher.handle(), cam, keys, keysUn);
+        double sx = 0;
+        for (size_t i = 0; i < keysUn.size(); ++i) sx += keysUn[i].x;
+        std::vector<int> start(3), best;
+        start[0] = 0; start[1] = 5; start[2] = 12;
+        std::vector<unsigned char> obs(desc.begin(), desc.begin() + 12 * 32);
+        fo::ComputeDistinctiveDescriptors(matcher.handle(), obs, start, best);
+        printf("%d %.9g %.9g %.17g %d %d\n", kept, minX, maxY, sx, best[0], best[1]);
     } catch (const std::exception& e) {
         fprintf(stderr, "%s\n", e.what());
         return 1;

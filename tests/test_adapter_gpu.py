@@ -33,6 +33,20 @@ def test_adapter_matches_c_abi(tmp_path, matcher):
     n, m12, _ = matcher.search_for_initialization(f, f, np.stack([kps["x"], kps["y"]], 1), 100, 0.9, True)
     assert int(n_match) == n
     assert int(out.stdout.split("\n")[1]) == int(matcher.distance(desc[0], desc[1])[0])
+    # adapter/Frame.h: ComputeStereoMatches, ComputeImageBounds, UndistortKeyPoints, ComputeDistinctiveDescriptors
+    kept, min_x, max_y, sum_x, best0, best1 = out.stdout.split("\n")[2].split()
+    right = orbb200.Extractor(1000)
+    kr, dr = right(img)
+    ur, depth, n_st = ex.stereo_matches(right, kps, desc, kr, dr, np.float32(0.11), np.float32(47.9))
+    assert int(kept) == n_st
+    cam = orbb200.camera(458.654, 457.296, 367.215, 248.375, -0.28340811, 0.07395907, 0.00019359, 1.76187114e-05)
+    b = matcher.image_bounds(cam, 752, 480)
+    assert np.float32(min_x) == b[0] and np.float32(max_y) == b[3]
+    un = matcher.undistort_points(cam, np.stack([kps["x"], kps["y"]], 1))
+    assert float(sum_x) == float(np.cumsum(un[:, 0].astype(np.float64))[-1])
+    best, _ = matcher.distinctive_descriptors(desc[:12], [0, 5, 12])
+    assert [int(best0), int(best1)] == best.tolist()
+    right.close()
     ex.close()
 
 

@@ -98,6 +98,24 @@ def test_stereo_device_resident(oracle):
     exr.close()
 
 
+def test_stereo_pair_as_one_batch(oracle):
+    """left and right image as ONE batch of two on ONE handle (one launch set instead of two): frames 0 and 1 of the same
+    arena, same result as with two extractors"""
+    name = "euroc_s2"
+    w, h, nfeat, mb, mbf = STEREO_CASES[name][:5]
+    left, right = images(name)
+    ex = orbb200.Extractor(nfeat, max_width=w, max_height=h, max_batch=2)
+    (kl, dl), (kr, dr) = ex.extract_batch(np.stack([left, right]))
+    ur, depth, n = ex.stereo_matches(ex, kl, dl, kr, dr, mb, mbf, frame_l=0, frame_r=1)
+    g = np.load(GOLDEN)
+    assert n == int(g[name + "/kept"])
+    assert np.array_equal(ur.view(np.uint32), g[name + "/u_right"].view(np.uint32))
+    assert np.array_equal(depth.view(np.uint32), g[name + "/depth"].view(np.uint32))
+    with pytest.raises(orbb200.OrbError):
+        ex.stereo_matches(ex, kl, dl, kr, dr, mb, mbf, frame_l=0, frame_r=2)     # outside the last batch
+    ex.close()
+
+
 def test_stereo_edge_cases(oracle):
     w, h, nfeat, mb, mbf = RIGS["euroc"]
     left, right = stereo_pair(4, w, h)

@@ -1,0 +1,82 @@
+// Host-side mirror of the data-parallel member functions of ORB_SLAM2::Frame / MapPoint that sit either side of the
+// extractor and the matcher (reference: src/Frame.cc, src/MapPoint.cc), over the orbb200 C ABI:
+//
+//   Frame::UndistortKeyPoints()            Frame.cc:748-778   mvKeys -> mvKeysUn  (cv::undistortPoints, bit for bit)
+//   Frame::ComputeImageBounds(imLeft)      Frame.cc:780-808   mnMinX, mnMaxX, mnMinY, mnMaxY
+//   Frame::ComputeStereoMatches()          Frame.cc:810-984   mvuRight, mvDepth
+//   MapPoint::ComputeDistinctiveDescriptors()  MapPoint.cc:257-322  (batched over map points)
+//
+// The reference keeps these as member functions working on the object's own fields; here they are free functions named
+// alike that take exactly the fields the reference reads and write the fields it writes, so the bodies in Frame.cc /
+// MapPoint.cc become one call each.  Errors throw std::runtime_error with orb_last_error().
+#ifndef ORBB200_ADAPTER_FRAME_H
+#define ORBB200_ADAPTER_FRAME_H
+
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/orbb200.h"
+#include "ORBextractor.h"
+
+namespace ORB_SLAM2 {
+namespace frame_ops {
+
+inline void check(int st) {
+    if (st != ORB_OK) throw std::runtime_error(std::string("orbb200: ") + orb_last_error());
+}
+
+// mK = [fx 0 cx; 0 fy cy; 0 0 1] and mDistCoef = (k1 k2 p1 p2 [k3]) as Tracking.cc reads them from the settings file
+inline orb_camera MakeCamera(float fx, float fy, float cx, float cy, float k1, float k2, float p1, float p2, float k3 = 0.f) {
+    orb_camera c = {fx, fy, cx, cy, k1, k2, p1, p2, k3};
+    return c;
+}
+
+// Frame.cc:748-778.  mDistCoef.at<float>(0) == 0 copies mvKeys (Frame.cc:750-754).
+inline void UndistortKeyPoints(orbm_handle matcher, const orb_camera& cam, const std::vector<orb_keypoint>& mvKeys,
+                               std::vector<orb_keypoint>& mvKeysUn) {
+    const int N = (int)mvKeys.size();
+    std::vector<float> xy(2 * (size_t)N), un(2 * (size_t)N);
+    for (int i = 0; i < N; ++i) { xy[2 * i] = mvKeys[i].x; xy[2 * i + 1] = mvKeys[i].y; }
+    check(orbm_undistort_points(matcher, &cam, xy.data(), N, un.data()));
+    mvKeysUn = mvKeys;
+    for (int i = 0; i < N; ++i) { mvKeysUn[i].x = un[2 * i]; mvKeysUn[i].y = un[2 * i + 1]; }
+}
+
+// Frame.cc:780-808
+inline void ComputeImageBounds(orbm_handle matcher, const orb_camera& cam, int cols, int rows, float& mnMinX, float& mnMaxX,
+                               float& mnMinY, float& mnMaxY) {
+    float b[4];
+    check(orbm_image_bounds(matcher, &cam, cols, rows, b));
+    mnMinX = b[0]; mnMinY = b[1]; mnMaxX = b[2]; mnMaxY = b[3];
+}
+
+// Frame.cc:810-984: both extractors hold the pyramids of the stereo pair they just processed (Frame.cc:422-425)
+inline int ComputeStereoMatches(ORBextractor& left, ORBextractor& right, const std::vector<orb_keypoint>& mvKeys,
+                                const std::vector<unsigned char>& mDescriptors, const std::vector<orb_keypoint>& mvKeysRight,
+                                const std::vector<unsigned char>& mDescriptorsRight, float mb, float mbf,
+                                std::vector<float>& mvuRight, std::vector<float>& mvDepth) {
+    const int N = (int)mvKeys.size();
+    mvuRight.assign(N, -1.0f);
+    mvDepth.assign(N, -1.0f);
+    int kept = 0;
+    check(orbx_compute_stereo_matches(left.handle(), 0, right.handle(), 0, mvKeys.data(), mDescriptors.data(), N,
+                                      mvKeysRight.data(), mDescriptorsRight.data(), (int)mvKeysRight.size(), mb, mbf,
+                                      mvuRight.data(), mvDepth.data(), &kept));
+    return kept;
+}
+
+// MapPoint.cc:257-322 for many map points at once: descriptors of point p = rows start[p] .. start[p+1] of `descriptors`
+// (mObservations order, bad keyframes dropped).  best[p] = row inside the run to clone into mDescriptor, -1 = keep.
+inline void ComputeDistinctiveDescriptors(orbm_handle matcher, const std::vector<unsigned char>& descriptors,
+                                          const std::vector<int>& start, std::vector<int>& best) {
+    const int nPoints = start.empty() ? 0 : (int)start.size() - 1;
+    best.assign(nPoints, -1);
+    if (nPoints == 0) return;
+    check(orbm_distinctive_descriptors(matcher, descriptors.data(), start.data(), nPoints, best.data(), nullptr));
+}
+
+}  // namespace frame_ops
+}  // namespace ORB_SLAM2
+
+#endif
