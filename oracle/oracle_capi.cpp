@@ -5,6 +5,7 @@
 #include <cstring>
 
 #include "match_oracle.h"
+#include "bow_oracle.h"
 #include "orb_oracle.h"
 
 using namespace orbo;
@@ -193,6 +194,23 @@ void orbo_search_best(void* k, const BestQuery* q, const uint8_t* qdesc, int nq,
 int orbo_bruteforce(const uint8_t* q, const float* qa, int nq, const uint8_t* t, const float* ta, int nt, float ratio,
                     int checkOri, int* best, int* second, int* idx, int* m12) {
     return bruteforce_match(q, qa, nq, t, ta, nt, ratio, checkOri != 0, best, second, idx, m12);
+}
+// vocabulary-tree descent; the CSR outputs are written into caller arrays sized n (+1), the counts come back through nOut[3]
+void orbo_bow_transform(int nNodes, int L, const uint8_t* ndesc, const int* childStart, const int* children, const int* wordId,
+                        const double* weight, const uint8_t* desc, int n, int levelsup, int* pfWord, double* pfWeight,
+                        int* pfNode, int* bowWord, double* bowValue, int* fvNode, int* fvStart, int* fvIdx, int* nOut) {
+    VocabArrays V;
+    V.nNodes = nNodes; V.L = L; V.desc = ndesc; V.childStart = childStart; V.children = children; V.wordId = wordId;
+    V.weight = weight;
+    std::vector<int> bw, fn, fs, fi;
+    std::vector<double> bv;
+    bow_transform(V, desc, n, levelsup, bw, bv, fn, fs, fi, pfWord, pfWeight, pfNode);
+    std::copy(bw.begin(), bw.end(), bowWord);
+    std::copy(bv.begin(), bv.end(), bowValue);
+    std::copy(fn.begin(), fn.end(), fvNode);
+    std::copy(fs.begin(), fs.end(), fvStart);
+    std::copy(fi.begin(), fi.end(), fvIdx);
+    nOut[0] = (int)bw.size(); nOut[1] = (int)fn.size(); nOut[2] = (int)fi.size();
 }
 void orbo_distinctive(const uint8_t* desc, const int* start, int nPoints, int* best, int* bestMedian) {
     for (int p = 0; p < nPoints; ++p)

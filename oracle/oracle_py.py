@@ -190,6 +190,23 @@ class Oracle:
     def frame(self, keys_un, desc, bounds):
         return OracleFrame(self, keys_un, desc, bounds)
 
+    def bow_transform(self, voc, desc, levelsup=4, lib=None, fn="orbo_bow_transform"):
+        """TemplatedVocabulary::transform(features, v, fv, levelsup) on a flat vocabulary (tests/bow_cases.py::make_vocab).
+        Returns dict(word, weight, node per feature; bow_word, bow_value; fv_node, fv_start, fv_idx)."""
+        d = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        n = len(d)
+        f = getattr(lib or self.lib, fn)
+        f.restype = None
+        f.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 6 + [C.c_int, C.c_int] + [C.c_void_p] * 9
+        pw = np.empty(n, np.int32); pwt = np.empty(n, np.float64); pn = np.empty(n, np.int32)
+        bw = np.empty(n + 1, np.int32); bv = np.empty(n + 1, np.float64)
+        fn_ = np.empty(n + 1, np.int32); fs = np.empty(n + 2, np.int32); fi = np.empty(n + 1, np.int32)
+        cnt = np.zeros(3, np.int32)
+        f(voc["n_nodes"], voc["L"], _p(voc["desc"]), _p(voc["child_start"]), _p(voc["children"]), _p(voc["word_id"]),
+          _p(voc["weight"]), _p(d), n, levelsup, _p(pw), _p(pwt), _p(pn), _p(bw), _p(bv), _p(fn_), _p(fs), _p(fi), _p(cnt))
+        return dict(word=pw, weight=pwt, node=pn, bow_word=bw[:cnt[0]].copy(), bow_value=bv[:cnt[0]].copy(),
+                    fv_node=fn_[:cnt[1]].copy(), fv_start=fs[:cnt[1] + 1].copy(), fv_idx=fi[:cnt[2]].copy())
+
     def distinctive(self, desc, start):
         """MapPoint::ComputeDistinctiveDescriptors for len(start)-1 map points (CSR runs of `desc`): (best, median)"""
         d = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
