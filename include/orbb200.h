@@ -287,6 +287,29 @@ int orbm_allpairs_device(orbm_handle h, const uint8_t* d_table, const float* d_a
 int orbm_distinctive_descriptors(orbm_handle h, const uint8_t* descriptors, const int* start, int n_points, int* best,
                                  int* best_median);
 
+/* Frame::ComputeBoW / KeyFrame::ComputeBoW (Frame.cc:736-745: mpORBvocabulary->transform(vCurrentDesc, mBowVec, mFeatVec, 4)).
+ * The vocabulary is DBoW2's m_nodes as flat arrays (node 0 = root): node_desc[n_nodes][32], Node::children as CSR
+ * (child_start[n_nodes+1], children[] in vector order), Node::word_id and Node::weight (idf) per node, depth_l = m_L.
+ * Loading Vocabulary/ORBvoc.* into these arrays is file I/O and stays with the host project.                          */
+typedef struct orbm_vocabulary_s* orbm_vocabulary;
+int orbm_vocabulary_create(orbm_handle h, int n_nodes, int depth_l, const uint8_t* node_desc, const int* child_start,
+                           const int* children, const int* word_id, const double* weight, orbm_vocabulary* out);
+int orbm_vocabulary_destroy(orbm_vocabulary v);
+/* TemplatedVocabulary::transform(features, v, fv, levelsup) with TF_IDF weighting and L1 scoring (what ORBvoc uses;
+ * Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1166-1262, :1443-1485).  Per feature (any of them may be NULL): word_id[n],
+ * weight[n] (the word's idf; 0 = stopped word, left out of both vectors), node_id[n] (ancestor `levelsup` levels above
+ * the leaves; the root when the tree is shallower, and when a leaf sits above that level).  BowVector (all three or
+ * none): bow_word[<=n] ascending, bow_value L1-normalised, *n_words.  FeatureVector (all four or none) as the node-sorted
+ * CSR that orbm_search_by_bow / orbm_search_for_triangulation take: fv_node[<=n], fv_start[<=n+1], fv_idx[<=n], *n_nodes;
+ * feature indices ascend inside a node (this fork fills them from four racing threads, so its order there is timing-
+ * dependent; ascending is what its single-threaded variant produces).                                              */
+int orbm_bow_transform(orbm_handle h, orbm_vocabulary v, const uint8_t* descriptors, int n, int levelsup,
+                       int* word_id, double* weight, int* node_id, int* bow_word, double* bow_value, int* n_words,
+                       int* fv_node, int* fv_start, int* fv_idx, int* n_nodes);
+/* The descent alone on device-resident descriptors (e.g. where orbx_extract_batch_device left them); enqueues only. */
+int orbm_bow_transform_device(orbm_handle h, orbm_vocabulary v, const uint8_t* d_descriptors, int n, int levelsup,
+                              int* d_word_id, double* d_weight, int* d_node_id, void* stream);
+
 /* Measured POPC-pipe throughput of this GPU (the roofline denominator for matching): 32-bit POPC per second. */
 int orbm_popc_peak(orbm_handle h, double* popc_per_s);
 

@@ -354,6 +354,35 @@ class Matcher:
         _check(self.L.orbm_distinctive_descriptors(self.h, _p(d), _p(st), len(st) - 1, _p(best), _p(med)))
         return best, med
 
+    def vocabulary(self, voc):
+        """upload a flat DBoW2 tree (dict with n_nodes, L, desc, child_start, children, word_id, weight) -> handle"""
+        v = C.c_void_p()
+        keep = [np.ascontiguousarray(voc["desc"], np.uint8), np.ascontiguousarray(voc["child_start"], np.int32),
+                np.ascontiguousarray(voc["children"], np.int32), np.ascontiguousarray(voc["word_id"], np.int32),
+                np.ascontiguousarray(voc["weight"], np.float64)]
+        _check(self.L.orbm_vocabulary_create(self.h, int(voc["n_nodes"]), int(voc["L"]), *[_p(a) for a in keep], C.byref(v)))
+        return v
+
+    def vocabulary_destroy(self, v):
+        _check(self.L.orbm_vocabulary_destroy(v))
+
+    def bow_transform(self, v, desc, levelsup=4):
+        """TemplatedVocabulary::transform(features, BowVector, FeatureVector, levelsup): dict like the oracle's"""
+        d = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        n = len(d)
+        pw = np.empty(n, np.int32); pwt = np.empty(n, np.float64); pn = np.empty(n, np.int32)
+        bw = np.empty(n + 1, np.int32); bv = np.empty(n + 1, np.float64)
+        fn = np.empty(n + 1, np.int32); fs = np.empty(n + 2, np.int32); fi = np.empty(n + 1, np.int32)
+        nw, nn = C.c_int(), C.c_int()
+        _check(self.L.orbm_bow_transform(self.h, v, _p(d), n, levelsup, _p(pw), _p(pwt), _p(pn), _p(bw), _p(bv), C.byref(nw),
+                                         _p(fn), _p(fs), _p(fi), C.byref(nn)))
+        return dict(word=pw, weight=pwt, node=pn, bow_word=bw[:nw.value].copy(), bow_value=bv[:nw.value].copy(),
+                    fv_node=fn[:nn.value].copy(), fv_start=fs[:nn.value + 1].copy(), fv_idx=fi[:fs[nn.value]].copy())
+
+    def bow_transform_device(self, v, d_desc, n, levelsup, d_word, d_weight, d_node, stream=None):
+        _check(self.L.orbm_bow_transform_device(self.h, v, _dp(d_desc), n, levelsup, _dp(d_word), _dp(d_weight), _dp(d_node),
+                                                _dp(stream)))
+
     def popc_peak(self):
         v = C.c_double()
         _check(self.L.orbm_popc_peak(self.h, C.byref(v)))

@@ -54,6 +54,10 @@ SIGNATURES = {
     "orbm_bruteforce_device": (i32, [vp, vp, vp, i32, vp, vp, i32, i32, f32, i32, vp, vp, vp, vp, vp, vp]),
     "orbm_allpairs_device": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, f32, i32, vp, vp]),
     "orbm_distinctive_descriptors": (i32, [vp, vp, vp, i32, vp, vp]),
+    "orbm_vocabulary_create": (i32, [vp, i32, i32, vp, vp, vp, vp, vp, vp]),
+    "orbm_vocabulary_destroy": (i32, [vp]),
+    "orbm_bow_transform": (i32, [vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "orbm_bow_transform_device": (i32, [vp, vp, vp, i32, i32, vp, vp, vp, vp]),
     "orbm_popc_peak": (i32, [vp, vp]),
 }
 
