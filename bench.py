@@ -205,6 +205,18 @@ def cpu_matcher_reference():
         o.distinctive(desc, start)
         out["distinctive_descriptors_20000_points_ms"] = (time.perf_counter() - t0) * 1e3 * 10
         out["distinctive_kind"] = "port (oracle/match_oracle.cpp), 2000 points timed and scaled x10"
+        from bow_cases import make_vocab
+        import ref_bow
+        voc = make_vocab(seed=1, k=10, L=4)
+        kw = dict(lib=ref_bow.lib(), fn="ref_bow_transform") if ref_bow.available() else {}
+        ts = []
+        for _ in range(5):
+            t0 = time.perf_counter()
+            o.bow_transform(voc, dl, 4, **kw)
+            ts.append((time.perf_counter() - t0) * 1e3)
+        out["bow_transform_%d_features_k10_L4_ms" % len(dl)] = float(np.median(ts))
+        out["bow_kind"] = ("reference (DBoW2 transform / FORB::distance / BowVector.cpp / FeatureVector.cpp compiled in place, "
+                           "-O2, one thread)" if ref_bow.available() else "port (oracle/bow_oracle.cpp)")
     except Exception as ex:
         out["frame_side_kind"] = "unavailable: %s" % ex
     return out
@@ -317,6 +329,12 @@ def frame_side_latency(device, m, med):
     desc = rng.integers(0, 256, (int(start[-1]), 32), dtype=np.uint8)
     out["distinctive_descriptors_20000_points"] = med(lambda: m.distinctive_descriptors(desc, start))
     out["distinctive_descriptors_observations"] = int(start[-1])
+    # Frame::ComputeBoW: descent + BowVector / FeatureVector assembly, synthetic k=10 L=4 tree (ORBvoc itself is k=10 L=6)
+    from bow_cases import make_vocab
+    voc = make_vocab(seed=1, k=10, L=4)
+    v = m.vocabulary(voc)
+    out["bow_transform_%d_features_k10_L4" % len(dl)] = med(lambda: m.bow_transform(v, dl, 4))
+    m.vocabulary_destroy(v)
     exl.close()
     exr.close()
     return out

@@ -52,6 +52,25 @@ int main(int argc, char** argv) {
         std::vector<unsigned char> obs(desc.begin(), desc.begin() + 12 * 32);
         fo::ComputeDistinctiveDescriptors(matcher.handle(), obs, start, best);
         printf("%d %.9g %.9g %.17g %d %d\n", kept, minX, maxY, sx, best[0], best[1]);
+        // ComputeBoW on a two-level tree whose 4 + 16 node descriptors are the first extracted descriptors;
+        // fourth line = "n_words n_nodes sum(bowValue) fvIdx[0]"
+        const int nNodes = 21;
+        std::vector<unsigned char> ndesc(nNodes * 32, 0);
+        for (int i = 1; i < nNodes; ++i) for (int b = 0; b < 32; ++b) ndesc[i * 32 + b] = desc[(size_t)(i * 7) * 32 + b];
+        std::vector<int> cstart(nNodes + 1, 0), kids, wid(nNodes, 0);
+        std::vector<double> wgt(nNodes, 0.0);
+        for (int i = 1; i <= 4; ++i) kids.push_back(i);
+        cstart[1] = 4;
+        for (int p = 1; p <= 4; ++p) { for (int c = 0; c < 4; ++c) kids.push_back(5 + (p - 1) * 4 + c); cstart[p + 1] = (int)kids.size(); }
+        for (int i = 5; i < nNodes; ++i) { cstart[i + 1] = (int)kids.size(); wid[i] = i - 5; wgt[i] = 1.0 + 0.25 * (i - 5); }
+        orbm_vocabulary voc = nullptr;
+        fo::check(orbm_vocabulary_create(matcher.handle(), nNodes, 2, ndesc.data(), cstart.data(), kids.data(), wid.data(), wgt.data(), &voc));
+        fo::BowResult bow;
+        fo::ComputeBoW(matcher.handle(), voc, desc, bow, 1);
+        double sv = 0;
+        for (size_t i = 0; i < bow.bowValue.size(); ++i) sv += bow.bowValue[i];
+        printf("%zu %zu %.17g %d\n", bow.bowWord.size(), bow.fvNode.size(), sv, bow.fvIdx.empty() ? -1 : bow.fvIdx[0]);
+        orbm_vocabulary_destroy(voc);
     } catch (const std::exception& e) {
         fprintf(stderr, "%s\n", e.what());
         return 1;

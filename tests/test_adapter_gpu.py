@@ -46,6 +46,22 @@ def test_adapter_matches_c_abi(tmp_path, matcher):
     assert float(sum_x) == float(np.cumsum(un[:, 0].astype(np.float64))[-1])
     best, _ = matcher.distinctive_descriptors(desc[:12], [0, 5, 12])
     assert [int(best0), int(best1)] == best.tolist()
+    # ComputeBoW through the adapter on the same two-level tree, rebuilt here
+    n_words, n_fv, sum_v, first_idx = out.stdout.split("\n")[3].split()
+    nn = 21
+    ndesc = np.zeros((nn, 32), np.uint8)
+    ndesc[1:] = desc[np.arange(1, nn) * 7]
+    cstart = np.zeros(nn + 1, np.int32)
+    cstart[1:6] = [4, 8, 12, 16, 20]
+    cstart[6:] = 20
+    voc = dict(n_nodes=nn, L=2, desc=ndesc, child_start=cstart, children=np.arange(1, nn, dtype=np.int32),
+               word_id=np.maximum(np.arange(nn) - 5, 0).astype(np.int32),
+               weight=np.where(np.arange(nn) >= 5, 1.0 + 0.25 * (np.arange(nn) - 5), 0.0))
+    v = matcher.vocabulary(voc)
+    bow = matcher.bow_transform(v, desc, 1)
+    assert int(n_words) == len(bow["bow_word"]) and int(n_fv) == len(bow["fv_node"]) and int(first_idx) == bow["fv_idx"][0]
+    assert float(sum_v) == float(np.cumsum(bow["bow_value"])[-1])
+    matcher.vocabulary_destroy(v)
     right.close()
     ex.close()
 

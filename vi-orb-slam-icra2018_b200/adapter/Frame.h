@@ -5,6 +5,7 @@
 //   Frame::ComputeImageBounds(imLeft)      Frame.cc:780-808   mnMinX, mnMaxX, mnMinY, mnMaxY
 //   Frame::ComputeStereoMatches()          Frame.cc:810-984   mvuRight, mvDepth
 //   MapPoint::ComputeDistinctiveDescriptors()  MapPoint.cc:257-322  (batched over map points)
+//   Frame::ComputeBoW()                    Frame.cc:736-745   mBowVec, mFeatVec (DBoW2 vocabulary-tree descent)
 //
 // The reference keeps these as member functions working on the object's own fields; here they are free functions named
 // alike that take exactly the fields the reference reads and write the fields it writes, so the bodies in Frame.cc /
@@ -74,6 +75,29 @@ inline void ComputeDistinctiveDescriptors(orbm_handle matcher, const std::vector
     best.assign(nPoints, -1);
     if (nPoints == 0) return;
     check(orbm_distinctive_descriptors(matcher, descriptors.data(), start.data(), nPoints, best.data(), nullptr));
+}
+
+// Frame::ComputeBoW / KeyFrame::ComputeBoW (Frame.cc:736-745): mBowVec as (ascending word id, L1-normalised value) pairs
+// and mFeatVec as node-sorted CSR (node id, run start, feature indices) -- the form orbm_search_by_bow and
+// orbm_search_for_triangulation take.  `vocabulary` comes from orbm_vocabulary_create (the host project's loader fills it
+// from ORBvoc); levelsup = 4 in the reference.
+struct BowResult {
+    std::vector<int> bowWord;
+    std::vector<double> bowValue;
+    std::vector<int> fvNode, fvStart, fvIdx;
+};
+inline void ComputeBoW(orbm_handle matcher, orbm_vocabulary vocabulary, const std::vector<unsigned char>& mDescriptors,
+                       BowResult& out, int levelsup = 4) {
+    const int n = (int)(mDescriptors.size() / 32);
+    out.bowWord.assign(n + 1, 0); out.bowValue.assign(n + 1, 0.0);
+    out.fvNode.assign(n + 1, 0); out.fvStart.assign(n + 2, 0); out.fvIdx.assign(n + 1, 0);
+    int nWords = 0, nNodes = 0;
+    check(orbm_bow_transform(matcher, vocabulary, mDescriptors.data(), n, levelsup, nullptr, nullptr, nullptr,
+                             out.bowWord.data(), out.bowValue.data(), &nWords, out.fvNode.data(), out.fvStart.data(),
+                             out.fvIdx.data(), &nNodes));
+    out.bowWord.resize(nWords); out.bowValue.resize(nWords);
+    out.fvNode.resize(nNodes); out.fvStart.resize(nNodes + 1);
+    out.fvIdx.resize(out.fvStart[nNodes]);
 }
 
 }  // namespace frame_ops
