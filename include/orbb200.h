@@ -290,7 +290,7 @@ int orbm_distinctive_descriptors(orbm_handle h, const uint8_t* descriptors, cons
 /* Frame::ComputeBoW / KeyFrame::ComputeBoW (Frame.cc:736-745: mpORBvocabulary->transform(vCurrentDesc, mBowVec, mFeatVec, 4)).
  * The vocabulary is DBoW2's m_nodes as flat arrays (node 0 = root): node_desc[n_nodes][32], Node::children as CSR
  * (child_start[n_nodes+1], children[] in vector order), Node::word_id and Node::weight (idf) per node, depth_l = m_L.
- * Loading Vocabulary/ORBvoc.* into these arrays is file I/O and stays with the host project.                          */
+ * adapter/ORBVocabulary.h reads Vocabulary/ORBvoc.txt / .bin (DBoW2's two file formats) into exactly these arrays.      */
 typedef struct orbm_vocabulary_s* orbm_vocabulary;
 int orbm_vocabulary_create(orbm_handle h, int n_nodes, int depth_l, const uint8_t* node_desc, const int* child_start,
                            const int* children, const int* word_id, const double* weight, orbm_vocabulary* out);

@@ -34,6 +34,8 @@ public:
     std::shared_ptr<std::vector<unsigned char>> own;   // null for views onto caller memory
 
     Mat() {}
+    Mat(int r, int c, int type) { *this = alloc(r, c, type); }          // zero-filled (OpenCV leaves it uninitialised)
+    void create(int r, int c, int type) { *this = alloc(r, c, type); }
     Mat(int r, int c, int type, void* p, size_t stepBytes) : rows(r), cols(c), type_(type), step(stepBytes), data((unsigned char*)p) {}
     static Mat alloc(int r, int c, int type) {
         Mat m;
@@ -73,6 +75,7 @@ public:
     template <class T> T& at(int y, int x) { return *(T*)(data + (size_t)y * step + (size_t)x * sizeof(T)); }
     template <class T> const T& at(int y, int x) const { return *(const T*)(data + (size_t)y * step + (size_t)x * sizeof(T)); }
     template <class T> const T* ptr() const { return (const T*)data; }
+    template <class T> T* ptr() { return (T*)data; }
     void convertTo(Mat& dst, int type) const {              // only CV_8U -> CV_32F is used (Frame.cc:909, :926)
         if (type_ != CV_8U || type != CV_32F) abort();
         Mat out = alloc(rows, cols, CV_32F);
