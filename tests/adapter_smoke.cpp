@@ -7,6 +7,7 @@
 #include "ORBextractor.h"
 #include "ORBmatcher.h"
 #include "Frame.h"
+#include "ORBVocabulary.h"
 
 int main(int argc, char** argv) {
     if (argc < 4) return 2;
@@ -71,6 +72,19 @@ int main(int argc, char** argv) {
         for (size_t i = 0; i < bow.bowValue.size(); ++i) sv += bow.bowValue[i];
         printf("%zu %zu %.17g %d\n", bow.bowWord.size(), bow.fvNode.size(), sv, bow.fvIdx.empty() ? -1 : bow.fvIdx[0]);
         orbm_vocabulary_destroy(voc);
+        // ORBVocabulary: argv[4] = vocabulary text file -> load, upload, transform(levelsup 2);
+        // fifth line = "nodes words n_bow n_fv sum(bowValue) fvIdx[0]"
+        if (argc > 4) {
+            ORB_SLAM2::ORBVocabulary orbvoc;
+            if (!orbvoc.loadFromTextFile(argv[4])) return 4;
+            orbvoc.upload(matcher.handle());
+            std::vector<int> bw, fn, fs, fi;
+            std::vector<double> bv;
+            orbvoc.transform(desc, bw, bv, fn, fs, fi, 2);
+            double s2 = 0;
+            for (size_t i = 0; i < bv.size(); ++i) s2 += bv[i];
+            printf("%d %u %zu %zu %.17g %d\n", orbvoc.nodes(), orbvoc.size(), bw.size(), fn.size(), s2, fi.empty() ? -1 : fi[0]);
+        }
     } catch (const std::exception& e) {
         fprintf(stderr, "%s\n", e.what());
         return 1;

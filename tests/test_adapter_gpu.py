@@ -20,7 +20,13 @@ def test_adapter_matches_c_abi(tmp_path, matcher):
     img = synth_frame(0)
     raw = tmp_path / "img.raw"
     img.tofile(raw)
-    out = subprocess.run([exe, str(raw), "752", "480"], capture_output=True, text=True)
+    # a vocabulary file in the reference's text format (adapter/ORBVocabulary.h reads it)
+    from bow_cases import make_vocab
+    from test_vocab_io import write_text
+    voc_file = str(tmp_path / "voc.txt")
+    file_voc = make_vocab(seed=31, k=10, L=3)
+    write_text(file_voc, voc_file, weight_fmt="%.17g")
+    out = subprocess.run([exe, str(raw), "752", "480", voc_file], capture_output=True, text=True)
     assert out.returncode == 0, out.stderr
     n_kp, checksum, n_match, levels, sf7 = out.stdout.split("\n")[0].split()
     ex = orbb200.Extractor(1000)
@@ -62,6 +68,20 @@ def test_adapter_matches_c_abi(tmp_path, matcher):
     assert int(n_words) == len(bow["bow_word"]) and int(n_fv) == len(bow["fv_node"]) and int(first_idx) == bow["fv_idx"][0]
     assert float(sum_v) == float(np.cumsum(bow["bow_value"])[-1])
     matcher.vocabulary_destroy(v)
+    # ORBVocabulary: file -> flat arrays -> device -> transform; expected from DBoW2's own reader + the Python harness
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_vocio
+    nodes, words, n_bow, n_fv2, sum_v2, first2 = out.stdout.split("\n")[4].split()
+    assert int(nodes) == file_voc["n_nodes"] + 1 and int(words) == file_voc["n_words"] + 1   # + the empty-last-line node
+    if ref_vocio.available():
+        loaded = ref_vocio.load(voc_file, False)
+        loaded["L"] = file_voc["L"]
+        v2 = matcher.vocabulary(loaded)
+        bow2 = matcher.bow_transform(v2, desc, 2)
+        assert int(n_bow) == len(bow2["bow_word"]) and int(n_fv2) == len(bow2["fv_node"]) and int(first2) == bow2["fv_idx"][0]
+        assert float(sum_v2) == float(np.cumsum(bow2["bow_value"])[-1])
+        matcher.vocabulary_destroy(v2)
     right.close()
     ex.close()
 
