@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""One invocation of every SURVEY section 8f entry point (device-resident frame, stereo, distinctive descriptors) on the
+"""One invocation of every SURVEY section 8f entry point (device-resident frame, stereo, distinctive descriptors, BoW transform) on the
 bench inputs, for `ncu` launch lists (tools/gpu_frame_side_prof.sh).  Not a benchmark: numbers printed under ncu are
 never bench values."""
 import os
@@ -37,4 +37,10 @@ sizes = rng.integers(2, 41, 300 if "--small" in sys.argv else 20000)
 start = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
 desc = rng.integers(0, 256, (int(start[-1]), 32), dtype=np.uint8)
 best, med = m.distinctive_descriptors(desc, start)
+from bow_cases import make_vocab  # noqa: E402
+voc = make_vocab(seed=1, k=10, L=4)
+v = m.vocabulary(voc)
+bow = m.bow_transform(v, dl, 4)
+m.vocabulary_destroy(v)
+print("bow words", len(bow["bow_word"]), "nodes", len(bow["fv_node"]))
 print("stereo kept", kept, "frame n", f.n, "distinctive", len(best))
