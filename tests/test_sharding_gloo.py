@@ -76,3 +76,51 @@ def test_allpairs_sharded_two_ranks(tmp_path, n_kf):
         assert len(calls) == world
         max_local = -(-n_kf // world)
         assert calls[0][0] == r * max_local                       # own block first
+
+
+def test_cost_balanced_blocks():
+    rng = np.random.default_rng(0)
+    for world in (1, 2, 3, 8):
+        for costs in (rng.integers(1, 1600, 5000), np.ones(7), np.array([100.0, 1, 1, 1]), np.zeros(5), np.zeros(0)):
+            blocks = shard.cost_balanced_blocks(costs, world)
+            assert len(blocks) == world and blocks[0][0] == 0 and blocks[-1][1] == len(costs)
+            assert all(blocks[i][1] == blocks[i + 1][0] and blocks[i][0] <= blocks[i][1] for i in range(world - 1))
+            if len(costs) >= 1000:                                    # many small units: every rank is within 5 % of its share
+                share = [float(np.sum(costs[b:e])) for b, e in blocks]
+                assert max(share) < 1.05 * sum(share) / world
+
+
+def _distinctive_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    from oracle_py import Oracle
+    o = Oracle()
+    rng = np.random.default_rng(4)                                   # every rank rebuilds the same map
+    sizes = rng.integers(0, 30, 301)
+    start = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    desc = rng.integers(0, 256, (int(start[-1]), 32), dtype=np.uint8)
+    best, med, blocks = shard.distinctive_sharded(None, desc, start, dist, compute=lambda d, s: o.distinctive(d, s))
+    np.save(os.path.join(out_dir, "best_%d.npy" % rank), best)
+    np.save(os.path.join(out_dir, "blocks_%d.npy" % rank), np.array(blocks))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_distinctive_sharded_two_ranks(tmp_path, oracle):
+    """map points shard by cost-balanced contiguous blocks with no data-path collective; every rank ends with all results"""
+    world = 2
+    port = 29500 + os.getpid() % 2000 + 17
+    mp.spawn(_distinctive_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    rng = np.random.default_rng(4)
+    sizes = rng.integers(0, 30, 301)
+    start = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    desc = rng.integers(0, 256, (int(start[-1]), 32), dtype=np.uint8)
+    want, _ = oracle.distinctive(desc, start)
+    for r in range(world):
+        assert np.array_equal(np.load(tmp_path / ("best_%d.npy" % r)), want)
+    blocks = np.load(tmp_path / "blocks_0.npy")
+    assert blocks[0][0] == 0 and blocks[-1][1] == 301 and blocks[0][1] == blocks[1][0]
+    cost = sizes.astype(np.float64) ** 2
+    assert abs(cost[: blocks[0][1]].sum() - cost[blocks[0][1]:].sum()) < 0.05 * cost.sum()

@@ -95,3 +95,63 @@ def allpairs_sharded(matcher, local_desc, local_angles, n_kf, dist, ratio=0.75, 
         for r, (b, e) in enumerate(sizes):
             counts[:, b:e] = padded_counts[:, r * max_local: r * max_local + (e - b)]
     return counts
+
+
+def cost_balanced_blocks(costs, world):
+    """Contiguous blocks [begin, end) of units with unequal cost, one per rank, cut where the running cost crosses k/world
+    of the total (every rank gets a block, possibly empty; the blocks cover all units in order)."""
+    costs = np.asarray(costs, np.float64)
+    n = len(costs)
+    if n == 0:
+        return [(0, 0)] * world
+    cum = np.cumsum(costs)
+    total = cum[-1]
+    cuts = [0]
+    for k in range(1, world):
+        cuts.append(int(np.searchsorted(cum, total * k / world, side="left")) + 1 if total > 0 else (n * k) // world)
+    cuts = [min(max(c, cuts[i - 1] if i else 0), n) for i, c in enumerate(cuts)]
+    for i in range(1, len(cuts)):
+        cuts[i] = max(cuts[i], cuts[i - 1])
+    cuts.append(n)
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
+def distinctive_sharded(matcher, desc, start, dist, compute=None):
+    """MapPoint::ComputeDistinctiveDescriptors for a map too large for one GPU's turn-around: map points are independent
+    units, so ranks take contiguous blocks balanced by cost (n^2 distances per point with n observations) and NOTHING of
+    the data path crosses NVLink; only the per-point results (two ints) are all-gathered so that every rank ends with the
+    full answer.  desc: (total, 32) uint8 host array, start: CSR run starts (len = points + 1), both known to every rank.
+
+    compute(desc_block, start_block) -> (best, median) defaults to the CUDA kernel through the C ABI; the gloo tests inject
+    a host stand-in."""
+    import torch
+    world, rank = dist.get_world_size(), dist.get_rank()
+    start = np.asarray(start, np.int64)
+    n_points = len(start) - 1
+    sizes = np.diff(start)
+    blocks = cost_balanced_blocks(sizes.astype(np.float64) ** 2, world)
+    b, e = blocks[rank]
+    if compute is None:
+        def compute(d, s):
+            return matcher.distinctive_descriptors(d, s)
+    if e > b:
+        local_start = (start[b:e + 1] - start[b]).astype(np.int32)
+        best, med = compute(np.ascontiguousarray(desc[start[b]:start[e]]), local_start)
+    else:
+        best, med = np.zeros(0, np.int32), np.zeros(0, np.int32)
+    max_local = max(1, max(y - x for x, y in blocks))
+    pad = torch.full((2, max_local), -2, dtype=torch.int32)
+    pad[0, : e - b] = torch.from_numpy(np.asarray(best, np.int32))
+    pad[1, : e - b] = torch.from_numpy(np.asarray(med, np.int32))
+    backend = dist.get_backend()
+    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    pad = pad.to(dev)
+    gathered = torch.empty((world * 2, max_local), dtype=torch.int32, device=dev)   # rank blocks concatenated along dim 0
+    dist.all_gather_into_tensor(gathered, pad)
+    gathered = gathered.cpu().numpy().reshape(world, 2, max_local)
+    out_best = np.empty(n_points, np.int32)
+    out_med = np.empty(n_points, np.int32)
+    for r, (x, y) in enumerate(blocks):
+        out_best[x:y] = gathered[r, 0, : y - x]
+        out_med[x:y] = gathered[r, 1, : y - x]
+    return out_best, out_med, blocks
