@@ -50,16 +50,33 @@ stereo_match_kernel(StereoParams P, const orb_keypoint* __restrict__ keysL, cons
     if (maxU < 0) return;
     const uint4 a0 = descL[2 * iL], a1 = descL[2 * iL + 1];
     unsigned best = (unsigned)kThHigh << 16;                                    // bestDist = TH_HIGH, strict '<'
-    for (int iR = lane; iR < nR; iR += 32) {
-        const orb_keypoint kpR = keysR[iR];
-        if ((unsigned)kpR.octave >= (unsigned)P.nLevels) continue;
-        const float r = __fmul_rn(2.0f, P.scale[kpR.octave]);                   // :831
-        const int lo = max(band_lo(kpR.y, r), 0), hi = min(band_hi(kpR.y, r), P.nRows - 1);
-        if (row < lo || row > hi) continue;
-        if (kpR.octave < levelL - 1 || kpR.octave > levelL + 1) continue;       // :878
-        if (!(kpR.x >= minU && kpR.x <= maxU)) continue;                        // :883
-        const unsigned key = ((unsigned)hamming256(a0, a1, descR[2 * iR], descR[2 * iR + 1]) << 16) | (unsigned)iR;
-        best = min(best, key);
+    // Four right keypoints per lane and round: their twelve field loads are issued before any test, so a round costs one
+    // memory latency instead of four (the kernel is bound by exactly that latency: ncu long_scoreboard 76 % of samples).
+    for (int base = 0; base < nR; base += 128) {
+        float ry[4], rx[4];
+        int ro[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int iR = base + j * 32 + lane;
+            ro[j] = -1;
+            if (iR < nR) {
+                ry[j] = keysR[iR].y;
+                rx[j] = keysR[iR].x;
+                ro[j] = keysR[iR].octave;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int iR = base + j * 32 + lane;
+            if ((unsigned)ro[j] >= (unsigned)P.nLevels) continue;
+            const float r = __fmul_rn(2.0f, P.scale[ro[j]]);                    // :831
+            const int lo = max(band_lo(ry[j], r), 0), hi = min(band_hi(ry[j], r), P.nRows - 1);
+            if (row < lo || row > hi) continue;
+            if (ro[j] < levelL - 1 || ro[j] > levelL + 1) continue;             // :878
+            if (!(rx[j] >= minU && rx[j] <= maxU)) continue;                    // :883
+            const unsigned key = ((unsigned)hamming256(a0, a1, descR[2 * iR], descR[2 * iR + 1]) << 16) | (unsigned)iR;
+            best = min(best, key);
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
