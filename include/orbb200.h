@@ -159,7 +159,9 @@ int orbm_undistort_points(orbm_handle h, const orb_camera* cam, const float* xy,
 int orbm_image_bounds(orbm_handle h, const orb_camera* cam, int width, int height, float* bounds);
 /* The Frame constructor's work after ExtractORB (Frame.cc:75-109: UndistortKeyPoints, AssignFeaturesToGrid) for
  * keypoints and descriptors that are still where orbx_extract_batch_device left them: d_keys / d_descriptors / d_count
- * are DEVICE pointers of one frame (capacity entries), producer_stream is the stream that extraction was enqueued on.
+ * are DEVICE pointers of one frame (capacity entries), producer_stream is the stream that extraction was enqueued on
+ * (the call waits for it before reading the count; pass NULL only if the producer has already been synchronised --
+ * the extractor's own stream is non-blocking, so the legacy default stream does not order against it).
  * The frame keeps its own undistorted copy; only the 4-byte count crosses PCIe (N is host state of a Frame).      */
 int orbm_frame_create_device(orbm_handle h, const orb_keypoint* d_keys, const uint8_t* d_descriptors, const int* d_count,
                              int capacity, const orb_camera* cam, float min_x, float min_y, float max_x, float max_y,
