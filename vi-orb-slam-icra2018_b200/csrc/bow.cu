@@ -71,12 +71,6 @@ bow_descend_kernel(VocabDev V, const uint4* __restrict__ feat, int n, int levels
 
 }  // namespace orbb
 
-#define ORBM_ENTER(h)                                                                                 \
-    if (!(h)) return fail(ORB_ERR_INVALID, "%s: null matcher handle", __func__);                      \
-    DeviceGuard guard__((h)->device);                                                                 \
-    if (!guard__.ok) return fail(ORB_ERR_CUDA, "%s: cannot select device %d", __func__, (h)->device); \
-    (h)->launches = 0;
-
 namespace {
 
 // m_nodes must be a tree rooted at node 0: every other node reachable exactly once.  Returns its depth, or -1.

@@ -24,3 +24,10 @@ struct orbm_matcher {
     int launches = 0;
     orbb::DevBuf in0, in1, in2, in3, in4, in5, out0, out1, out2, out3, out4, ws0, ws1, ws2;
 };
+
+// Prologue of every matcher entry point: null check, device selection for the duration of the call, launch counter reset.
+#define ORBM_ENTER(h)                                                                                 \
+    if (!(h)) return ::orbb::fail(ORB_ERR_INVALID, "%s: null matcher handle", __func__);              \
+    ::orbb::DeviceGuard guard__((h)->device);                                                         \
+    if (!guard__.ok) return ::orbb::fail(ORB_ERR_CUDA, "%s: cannot select device %d", __func__, (h)->device); \
+    (h)->launches = 0;

@@ -5,12 +5,6 @@
 
 using namespace orbb;
 
-#define ORBM_ENTER(h)                                                          \
-    if (!(h)) return fail(ORB_ERR_INVALID, "%s: null matcher handle", __func__); \
-    DeviceGuard guard__((h)->device);                                          \
-    if (!guard__.ok) return fail(ORB_ERR_CUDA, "%s: cannot select device %d", __func__, (h)->device); \
-    (h)->launches = 0;
-
 extern "C" {
 
 int orbm_create(int device, orbm_handle* out) {

@@ -854,12 +854,6 @@ struct orbm_frame_s {
     }
 };
 
-#define ORBM_ENTER(h)                                                                                     \
-    if (!(h)) return fail(ORB_ERR_INVALID, "%s: null matcher handle", __func__);                          \
-    DeviceGuard guard__((h)->device);                                                                     \
-    if (!guard__.ok) return fail(ORB_ERR_CUDA, "%s: cannot select device %d", __func__, (h)->device);     \
-    (h)->launches = 0;
-
 namespace {
 
 constexpr size_t kReplayFixed = (size_t)kReplayFixedInts * 4;   // candidate / query staging of replay_queries
