@@ -64,3 +64,32 @@ def test_argument_validation_needs_no_device(lib):
     assert lib.orbx_create(1000, C.c_float(1.2), 17, 20, 7, 752, 480, 1, 0, C.byref(h)) == 1   # too many levels
     assert lib.orbx_destroy(None) == 0 and lib.orbm_destroy(None) == 0
     assert lib.orbx_synchronize(None) == 1 and b"null" in lib.orb_last_error()
+
+
+def test_frame_side_entry_points_reject_null_handles(lib):
+    """the SURVEY section-8f entry points: a null handle is an error with a message, never a crash or a silent no-op"""
+    buf = (C.c_float * 8)()
+    ibuf = (C.c_int * 8)()
+    out = C.c_void_p()
+    calls = [
+        lambda: lib.orbm_undistort_points(None, None, buf, 1, buf),
+        lambda: lib.orbm_frame_create_device(None, buf, buf, ibuf, 4, None, C.c_float(0), C.c_float(0), C.c_float(1), C.c_float(1),
+                                             None, C.byref(out)),
+        lambda: lib.orbm_frame_size(None, ibuf),
+        lambda: lib.orbm_frame_download(None, None, None),
+        lambda: lib.orbx_compute_stereo_matches(None, 0, None, 0, buf, buf, 1, buf, buf, 1, C.c_float(0.1), C.c_float(40), buf, buf, ibuf),
+        lambda: lib.orbx_compute_stereo_matches_device(None, 0, None, 0, buf, buf, ibuf, 1, buf, buf, ibuf, 1, C.c_float(0.1),
+                                                       C.c_float(40), buf, buf, ibuf, ibuf, None),
+        lambda: lib.orbm_distinctive_descriptors(None, buf, ibuf, 1, ibuf, ibuf),
+        lambda: lib.orbm_vocabulary_create(None, 2, 1, buf, ibuf, ibuf, ibuf, buf, C.byref(out)),
+        lambda: lib.orbm_bow_transform(None, None, buf, 1, 4, ibuf, buf, ibuf, None, None, None, None, None, None, None),
+        lambda: lib.orbm_bow_transform_device(None, None, buf, 1, 4, ibuf, buf, ibuf, None),
+    ]
+    for call in calls:
+        assert call() == 1                       # ORB_ERR_INVALID
+        assert b"null" in lib.orb_last_error()
+    # orbm_image_bounds needs the device only for a distorted camera: without one it is plain arithmetic (Frame.cc:803-808)
+    b = (C.c_float * 4)()
+    assert lib.orbm_image_bounds(None, None, 752, 480, b) == 0 and list(b) == [0.0, 0.0, 752.0, 480.0]
+    assert lib.orbm_image_bounds(None, None, 0, 480, b) == 1
+    assert lib.orbm_vocabulary_destroy(None) == 0
