@@ -31,6 +31,33 @@ def test_oracle_equals_reference(oracle, name):
     assert np.array_equal(sad >= 0, rur >= 0)
 
 
+@pytest.mark.skipif(not ref_stereo.available() and not os.path.isdir("/root/reference"),
+                    reason="oracle/_ref/libstereo_ref.so is built only where /root/reference is mounted")
+@pytest.mark.parametrize("name", ["euroc_s1", "small_wide"])
+def test_oracle_equals_reference_on_perturbed_keypoints(oracle, name):
+    """the same pin on inputs the extractor would not produce: sub-pixel jitter on both keypoint sets (rounding of the
+    scaled coordinates, row bands and disparity windows move), octaves shifted by +-1, shuffled order (ties go to the lowest
+    index), other baselines"""
+    if not ref_stereo.available():
+        ref_stereo.build()
+    kl, dl, kr, dr, LL, RR, sf, isf, mb, mbf = oracle_inputs(oracle, name)
+    for seed in range(8):
+        rng = np.random.default_rng(seed)
+        a, b = kl.copy(), kr.copy()
+        for k in (a, b):
+            k["x"] += rng.uniform(-1.5, 1.5, len(k)).astype(np.float32)
+            k["y"] += rng.uniform(-1.5, 1.5, len(k)).astype(np.float32)
+        b["octave"] = np.clip(b["octave"] + rng.integers(-1, 2, len(b)), 0, 7)
+        pa, pb = rng.permutation(len(a)), rng.permutation(len(b))
+        a, da, b, db = a[pa], dl[pa], b[pb], dr[pb]
+        mbf2 = float(mbf * rng.uniform(0.3, 2.0))
+        ur, depth, sad, kept = oracle.stereo(a, da, b, db, LL, RR, sf, isf, mb, mbf2)
+        rur, rdepth, rkept = ref_stereo.stereo(a, da, b, db, LL, RR, sf, isf, mb, mbf2)
+        assert kept == rkept and kept > 20
+        assert np.array_equal(ur.view(np.uint32), rur.view(np.uint32))
+        assert np.array_equal(depth.view(np.uint32), rdepth.view(np.uint32))
+
+
 @pytest.mark.parametrize("name", sorted(STEREO_CASES))
 def test_oracle_equals_golden(oracle, name):
     g = np.load(GOLDEN)
