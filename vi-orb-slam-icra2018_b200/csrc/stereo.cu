@@ -10,8 +10,9 @@
 // right keypoints and apply the row-band test directly (nR is one or two thousand: the row table would cost more than
 // the 12 bytes per test it saves); (distance, index) keys are min-reduced by shuffle; the same warp stages the two
 // patches in shared memory, the 11 shifts x 11 patch rows are summed by all lanes in integers (the reference's float
-// differences and its double accumulation are exact on these integer-valued operands), lane 0 fits the parabola with separately rounded
-// float operations.  A second one-block kernel finds the median by a two-pass radix select and withdraws the outliers.
+// differences and its double accumulation are exact on these integer-valued operands), lane 0 fits the parabola with
+// separately rounded float operations.  A second one-block kernel finds the median by a two-pass radix select and
+// withdraws the outliers.
 #include "extractor.h"
 
 namespace orbb {
