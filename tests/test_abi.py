@@ -93,3 +93,15 @@ def test_frame_side_entry_points_reject_null_handles(lib):
     assert lib.orbm_image_bounds(None, None, 752, 480, b) == 0 and list(b) == [0.0, 0.0, 752.0, 480.0]
     assert lib.orbm_image_bounds(None, None, 0, 480, b) == 1
     assert lib.orbm_vocabulary_destroy(None) == 0
+
+
+def test_frame_adapter_opencv_signatures_compile_and_link(lib, tmp_path):
+    """adapter/Frame.h's overloads on the reference's member types, against the OpenCV stand-in; no device needed"""
+    import subprocess
+    pkg = os.path.join(ROOT, "vi-orb-slam-icra2018_b200")
+    exe = str(tmp_path / "adapter_frame_opencv_sig")
+    subprocess.check_call(["g++", "-std=c++11", "-O1", "-I", os.path.join(ROOT, "oracle", "ref_shim", "include"),
+                           "-I", os.path.join(pkg, "adapter"), "-o", exe, os.path.join(ROOT, "tests", "adapter_frame_opencv_sig.cpp"),
+                           os.path.join(ROOT, "oracle", "cvprims.cpp"), "-L", pkg, "-lorbb200", "-Wl,-rpath," + pkg])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.strip() == "ok", (out.returncode, out.stdout, out.stderr)

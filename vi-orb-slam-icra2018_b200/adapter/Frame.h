@@ -13,6 +13,7 @@
 #ifndef ORBB200_ADAPTER_FRAME_H
 #define ORBB200_ADAPTER_FRAME_H
 
+#include <cstring>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -99,6 +100,51 @@ inline void ComputeBoW(orbm_handle matcher, orbm_vocabulary vocabulary, const st
     out.fvNode.resize(nNodes); out.fvStart.resize(nNodes + 1);
     out.fvIdx.resize(out.fvStart[nNodes]);
 }
+
+#ifdef ORBB200_WITH_OPENCV
+// The same with the reference's own member types (cv::Mat mK 3x3 CV_32F, cv::Mat mDistCoef 4x1 or 5x1 CV_32F,
+// std::vector<cv::KeyPoint>, cv::Mat descriptors N x 32 CV_8U), so that the bodies in Frame.cc shrink to one line each.
+inline orb_camera MakeCamera(const cv::Mat& mK, const cv::Mat& mDistCoef) {
+    return MakeCamera(mK.at<float>(0, 0), mK.at<float>(1, 1), mK.at<float>(0, 2), mK.at<float>(1, 2),
+                      mDistCoef.at<float>(0, 0), mDistCoef.at<float>(1, 0), mDistCoef.at<float>(2, 0), mDistCoef.at<float>(3, 0),
+                      mDistCoef.rows > 4 ? mDistCoef.at<float>(4, 0) : 0.f);   // k3 is optional (Tracking.cc:776-781)
+}
+
+inline void UndistortKeyPoints(orbm_handle matcher, const cv::Mat& mK, const cv::Mat& mDistCoef,
+                               const std::vector<cv::KeyPoint>& mvKeys, std::vector<cv::KeyPoint>& mvKeysUn) {
+    static_assert(sizeof(cv::KeyPoint) == sizeof(orb_keypoint), "cv::KeyPoint layout");
+    const int N = (int)mvKeys.size();
+    std::vector<float> xy(2 * (size_t)N), un(2 * (size_t)N);
+    for (int i = 0; i < N; ++i) { xy[2 * i] = mvKeys[i].pt.x; xy[2 * i + 1] = mvKeys[i].pt.y; }
+    const orb_camera cam = MakeCamera(mK, mDistCoef);
+    check(orbm_undistort_points(matcher, &cam, xy.data(), N, un.data()));
+    mvKeysUn = mvKeys;
+    for (int i = 0; i < N; ++i) { mvKeysUn[i].pt.x = un[2 * i]; mvKeysUn[i].pt.y = un[2 * i + 1]; }
+}
+
+inline void ComputeImageBounds(orbm_handle matcher, const cv::Mat& mK, const cv::Mat& mDistCoef, const cv::Mat& imLeft,
+                               float& mnMinX, float& mnMaxX, float& mnMinY, float& mnMaxY) {
+    ComputeImageBounds(matcher, MakeCamera(mK, mDistCoef), imLeft.cols, imLeft.rows, mnMinX, mnMaxX, mnMinY, mnMaxY);
+}
+
+inline int ComputeStereoMatches(ORBextractor& left, ORBextractor& right, const std::vector<cv::KeyPoint>& mvKeys,
+                                const cv::Mat& mDescriptors, const std::vector<cv::KeyPoint>& mvKeysRight,
+                                const cv::Mat& mDescriptorsRight, float mb, float mbf, std::vector<float>& mvuRight,
+                                std::vector<float>& mvDepth) {
+    const int N = (int)mvKeys.size(), Nr = (int)mvKeysRight.size();
+    mvuRight.assign(N, -1.0f);
+    mvDepth.assign(N, -1.0f);
+    // rows of a cv::Mat may be padded: hand the C ABI a dense N x 32 copy
+    std::vector<unsigned char> dl((size_t)N * 32), dr((size_t)Nr * 32);
+    for (int i = 0; i < N; ++i) std::memcpy(&dl[(size_t)i * 32], mDescriptors.ptr(i), 32);
+    for (int i = 0; i < Nr; ++i) std::memcpy(&dr[(size_t)i * 32], mDescriptorsRight.ptr(i), 32);
+    int kept = 0;
+    check(orbx_compute_stereo_matches(left.handle(), 0, right.handle(), 0, reinterpret_cast<const orb_keypoint*>(mvKeys.data()),
+                                      dl.data(), N, reinterpret_cast<const orb_keypoint*>(mvKeysRight.data()), dr.data(), Nr,
+                                      mb, mbf, mvuRight.data(), mvDepth.data(), &kept));
+    return kept;
+}
+#endif  // ORBB200_WITH_OPENCV
 
 }  // namespace frame_ops
 }  // namespace ORB_SLAM2
