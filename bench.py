@@ -143,7 +143,22 @@ def cpu_matcher_reference():
         o.bruteforce(q, qa, t, ta, 0.9, True)
         reps += 1
     out["bruteforce_compares_per_s"] = reps * 2000 * 2000 / (time.perf_counter() - t0)
-    out["bruteforce_kind"] = "port (oracle/match_oracle.cpp, SWAR popcount as ORBmatcher.cc:1675-1691)"
+    out["bruteforce_kind"] = "port (oracle/match_oracle.cpp, SWAR popcount as ORBmatcher.cc:1675-1691), parity build -O2"
+    try:   # the reference's own flags (-O3 -march=native, CMakeLists.txt:10-11), compiled on THIS host: GCC turns the SWAR
+        # count into vector popcounts where the CPU has them, which is worth up to 10x
+        native = os.path.join(ROOT, "oracle", "liborb_oracle_native.so")
+        if os.path.exists(native):
+            os.remove(native)                    # never trust a binary built for another CPU
+        on = Oracle(native=True)
+        t0 = time.perf_counter()
+        reps = 0
+        while time.perf_counter() - t0 < 1.5:
+            on.bruteforce(q, qa, t, ta, 0.9, True)
+            reps += 1
+        out["bruteforce_native_compares_per_s"] = reps * 2000 * 2000 / (time.perf_counter() - t0)
+        out["bruteforce_native_kind"] = "same port, -O3 -march=native compiled on this host"
+    except Exception as ex:
+        out["bruteforce_native_kind"] = "unavailable: %s" % ex
     try:
         import ref_matcher
         if ref_matcher.available():
