@@ -8,7 +8,13 @@
 #include <string>
 #include <vector>
 
+#include <map>
+
 #include "ORBVocabulary.h"
+
+// the map-container overload of transform() must instantiate with DBoW2-shaped containers (it needs a device to run)
+template void ORB_SLAM2::ORBVocabulary::transform(const std::vector<unsigned char>&, std::map<unsigned int, double>&,
+                                                  std::map<unsigned int, std::vector<unsigned int> >&, int) const;
 
 int main(int argc, char** argv) {
     if (argc < 6) return 2;

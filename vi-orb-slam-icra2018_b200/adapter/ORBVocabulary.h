@@ -184,6 +184,23 @@ public:
         fvIdx.resize(fvStart[nNodes]);
     }
 
+    // The reference's call shape, Frame.cc:743-744: transform(vCurrentDesc, mBowVec, mFeatVec, 4) with DBoW2::BowVector
+    // (std::map<WordId, WordValue>) and DBoW2::FeatureVector (std::map<NodeId, std::vector<unsigned int>>).  Templated on
+    // the two container types so that this header does not depend on DBoW2's; any map-like pair works.
+    template <class BowVectorT, class FeatureVectorT>
+    void transform(const std::vector<unsigned char>& features, BowVectorT& v, FeatureVectorT& fv, int levelsup) const {
+        std::vector<int> bw, fn, fs, fi;
+        std::vector<double> bv;
+        transform(features, bw, bv, fn, fs, fi, levelsup);
+        v.clear();
+        fv.clear();
+        for (size_t i = 0; i < bw.size(); ++i) v[bw[i]] = bv[i];
+        for (size_t k = 0; k < fn.size(); ++k) {
+            typename FeatureVectorT::mapped_type& idx = fv[fn[k]];
+            idx.assign(fi.begin() + fs[k], fi.begin() + fs[k + 1]);
+        }
+    }
+
 private:
     std::vector<std::vector<int> > kids_;           // while loading; flattened by finish()
     int nWords_ = 0;
