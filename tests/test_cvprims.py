@@ -119,3 +119,24 @@ def test_undistort_points(oracle, K4, dist, size):
     ref = cv2.undistortPoints(pts.reshape(-1, 1, 2), K, D, None, K).reshape(-1, 2)
     got = oracle.undistort(pts, K4, dist)
     assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+
+
+# Cameras far outside anything real: the radial denominator changes sign inside the image, so OpenCV's guard
+# (icdist < 0 -> keep the normalised input, its regression test 14583) is taken for a large share of the points.
+EXTREME_CAMERAS = [
+    ((100.0, 100.0, 320.0, 240.0), (-5.0, 0.0, 0.0, 0.0), (640, 480)),
+    ((150.0, 140.0, 320.0, 240.0), (-1.2, 0.3, 0.01, -0.02, 0.0), (640, 480)),
+    ((120.0, 120.0, 300.0, 200.0), (2.5, -8.0, 0.0, 0.0, 3.0), (640, 480)),
+]
+
+
+@pytest.mark.parametrize("K4,dist,size", EXTREME_CAMERAS)
+def test_undistort_points_sign_flip_guard(oracle, K4, dist, size):
+    rng = np.random.default_rng(3)
+    w, h = size
+    pts = (rng.random((20000, 2)) * [w, h]).astype(np.float32)
+    K = np.array([[K4[0], 0, K4[2]], [0, K4[1], K4[3]], [0, 0, 1]], np.float32)
+    ref = cv2.undistortPoints(pts.reshape(-1, 1, 2), K, np.array(dist, np.float32).reshape(-1, 1), None, K).reshape(-1, 2)
+    got = oracle.undistort(pts, K4, dist)
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+    assert np.isclose(ref, pts, atol=1e-3).all(1).sum() > 1000          # the guard branch really was exercised
