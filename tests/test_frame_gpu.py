@@ -7,7 +7,7 @@ import pytest
 
 import orbb200
 from orbb200.synth import shifted_pair
-from test_cvprims import CAMERAS
+from test_cvprims import CAMERAS, EXTREME_CAMERAS
 
 pytestmark = pytest.mark.gpu
 
@@ -29,6 +29,17 @@ def test_undistort_points(matcher, oracle, K4, dist, size):
     K = np.array([[K4[0], 0, K4[2]], [0, K4[1], K4[3]], [0, 0, 1]], np.float32)
     cref = cv2.undistortPoints(pts.reshape(-1, 1, 2), K, np.array(dist, np.float32).reshape(-1, 1), None, K).reshape(-1, 2)
     assert np.array_equal(got.view(np.uint32), cref.view(np.uint32))
+
+
+@pytest.mark.parametrize("K4,dist,size", EXTREME_CAMERAS)
+def test_undistort_points_sign_flip_guard(matcher, oracle, K4, dist, size):
+    """cameras whose radial factor changes sign inside the image: OpenCV's icdist < 0 guard is taken"""
+    rng = np.random.default_rng(3)
+    w, h = size
+    pts = (rng.random((20000, 2)) * [w, h]).astype(np.float32)
+    got = matcher.undistort_points(_cam(K4, dist), pts)
+    ref = oracle.undistort(pts, K4, dist)
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
 
 
 def test_undistort_is_a_copy_without_k1(matcher):

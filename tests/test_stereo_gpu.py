@@ -98,6 +98,41 @@ def test_stereo_device_resident(oracle):
     exr.close()
 
 
+@pytest.mark.parametrize("name", ["euroc_s1", "small_wide"])
+def test_stereo_on_perturbed_keypoints(oracle, name):
+    """inputs the extractor would not produce (the oracle is pinned to the reference's text on exactly these by
+    tests/test_stereo_ref.py): sub-pixel jitter, octaves shifted by +-1, shuffled order, other baselines"""
+    w, h, nfeat, mb, mbf = STEREO_CASES[name][:5]
+    left, right = images(name)
+    exl = orbb200.Extractor(nfeat, max_width=w, max_height=h)
+    exr = orbb200.Extractor(nfeat, max_width=w, max_height=h)
+    kl, dl = exl(left)
+    kr, dr = exr(right)
+    el, er = oracle.extractor(nfeat), oracle.extractor(nfeat)
+    el.extract(left)
+    er.extract(right)
+    t = el.tables()
+    LL = [el.level_padded(i) for i in range(8)]
+    RR = [er.level_padded(i) for i in range(8)]
+    for seed in range(8):
+        rng = np.random.default_rng(seed)
+        a, b = kl.copy(), kr.copy()
+        for k in (a, b):
+            k["x"] += rng.uniform(-1.5, 1.5, len(k)).astype(np.float32)
+            k["y"] += rng.uniform(-1.5, 1.5, len(k)).astype(np.float32)
+        b["octave"] = np.clip(b["octave"] + rng.integers(-1, 2, len(b)), 0, 7)
+        pa, pb = rng.permutation(len(a)), rng.permutation(len(b))
+        a, da, b, db = a[pa], dl[pa], b[pb], dr[pb]
+        mbf2 = float(mbf * rng.uniform(0.3, 2.0))
+        ur, depth, n = exl.stereo_matches(exr, a, da, b, db, mb, mbf2)
+        rur, rdepth, rsad, rkept = oracle.stereo(a, da, b, db, LL, RR, t["scale"], t["inv_scale"], mb, mbf2)
+        assert n == rkept and n > 20
+        assert np.array_equal(ur.view(np.uint32), rur.view(np.uint32))
+        assert np.array_equal(depth.view(np.uint32), rdepth.view(np.uint32))
+    exl.close()
+    exr.close()
+
+
 def test_stereo_pair_as_one_batch(oracle):
     """left and right image as ONE batch of two on ONE handle (one launch set instead of two): frames 0 and 1 of the same
     arena, same result as with two extractors"""
