@@ -236,4 +236,14 @@ void undistort_points(const float* xy, int n, float fxF, float fyF, float cxF, f
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// gemm for the 3x3 * 3x1 (+ 3x1) CV_32F case: OpenCV's small-matrix path, float arithmetic in source order
+// ---------------------------------------------------------------------------------------------
+void gemm3_f32(const float* A, const float* b, const float* c, float* d) {
+    for (int r = 0; r < 3; ++r) {
+        const float t = (A[3 * r] * b[0] + A[3 * r + 1] * b[1]) + A[3 * r + 2] * b[2];
+        d[r] = c ? (float)((double)t + (double)c[r]) : t;
+    }
+}
+
 }  // namespace orbo

@@ -13,6 +13,8 @@
 //   cvRound                             :83, 117, 121-122, 444, 462, 1133
 // and, for the Frame post-processing either side of the path (/root/reference/src/Frame.cc):
 //   cv::undistortPoints                 :767, :793
+// and for the projections the matcher's callers do (/root/reference/src/ORBmatcher.cc):
+//   cv::Mat operator* / operator+ (gemm) :1377 (3x3 * 3x1 + 3x1, CV_32F)
 #pragma once
 #include <cstdint>
 #include <vector>
@@ -61,5 +63,11 @@ float fast_atan2(float y, float x);
 // dist = k1 k2 p1 p2 [k3], nDist = 4 or 5
 void undistort_points(const float* xy, int n, float fx, float fy, float cx, float cy, const float* dist, int nDist,
                       float* out);
+
+// cv::Mat expression Rcw * x3Dw + tcw for a 3x3 by 3x1 CV_32F product (ORBmatcher.cc:1377 and every other projection of
+// the matcher): OpenCV evaluates it as ONE gemm(A, b, 1, c, 1), and its small-matrix path (inner dimension 2..4) works in
+// float, not in double: t = (a0*b0 + a1*b1) + a2*b2 with every operation rounded to float, d = (float)((double)t + c).
+void gemm3_f32(const float* A /* 3x3 row-major */, const float* b, const float* c /* may be null: plain product */,
+               float* d);
 
 }  // namespace orbo

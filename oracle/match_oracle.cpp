@@ -417,6 +417,23 @@ int kf_pair_match_count(const uint8_t* d1, const float* a1, int n1, const uint8_
 }
 
 // ---------------------------------------------------------------------------------------------
+// projection of map points into the current frame, ORBmatcher.cc:1376-1393
+// ---------------------------------------------------------------------------------------------
+void project_points(const float* Rcw, const float* tcw, float fx, float fy, float cx, float cy, const float* bounds,
+                    const float* xyzWorld, int n, float* u, float* v, float* invz, int32_t* valid) {
+    for (int i = 0; i < n; ++i) {
+        float x3Dc[3];
+        gemm3_f32(Rcw, xyzWorld + 3 * i, tcw, x3Dc);                  // :1377
+        const float xc = x3Dc[0], yc = x3Dc[1];
+        const float invzc = (float)(1.0 / (double)x3Dc[2]);           // :1381 (1.0 is a double literal)
+        u[i] = fx * xc * invzc + cx;                                  // :1387-1388
+        v[i] = fy * yc * invzc + cy;
+        invz[i] = invzc;
+        valid[i] = !(invzc < 0) && !(u[i] < bounds[0] || u[i] > bounds[2]) && !(v[i] < bounds[1] || v[i] > bounds[3]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // MapPoint::ComputeDistinctiveDescriptors, MapPoint.cc:257-322
 // ---------------------------------------------------------------------------------------------
 int distinctive_descriptor(const uint8_t* desc, int n, int* bestMedian) {

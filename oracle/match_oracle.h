@@ -109,6 +109,14 @@ int bruteforce_match(const uint8_t* q, const float* qAngle, int nq, const uint8_
 int kf_pair_match_count(const uint8_t* d1, const float* a1, int n1, const uint8_t* d2, const float* a2, int n2,
                         float nnratio, bool checkOri, int* matches12 /* may be null */);
 
+// The projection at the head of SearchByProjection(Frame&, const Frame&, th, mono) (ORBmatcher.cc:1376-1393): x3Dc =
+// Rcw * x3Dw + tcw (gemm3_f32), invzc = (float)(1.0 / zc), u = fx*xc*invzc + cx, v = fy*yc*invzc + cy in float, source
+// order.  Fills u, v, invz per point and valid = invzc >= 0 && u, v inside [minX, maxX] x [minY, maxY] -- the fields of
+// ProjQuery that the caller computes today.
+void project_points(const float* Rcw /* 3x3 row-major */, const float* tcw, float fx, float fy, float cx, float cy,
+                    const float* bounds /* minX, minY, maxX, maxY */, const float* xyzWorld, int n, float* u, float* v,
+                    float* invz, int32_t* valid);
+
 // MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:257-322): among the n descriptors observing one map point (in
 // mObservations order, bad keyframes removed) the one whose MEDIAN Hamming distance to all of them (its own 0 included,
 // median = sorted[(size_t)(0.5*(n-1))]) is smallest; the first such row wins.  Returns its index (-1 for n == 0) and

@@ -212,6 +212,11 @@ void orbo_bow_transform(int nNodes, int L, const uint8_t* ndesc, const int* chil
     std::copy(fi.begin(), fi.end(), fvIdx);
     nOut[0] = (int)bw.size(); nOut[1] = (int)fn.size(); nOut[2] = (int)fi.size();
 }
+void orbo_gemm3(const float* A, const float* b, const float* c, float* d) { gemm3_f32(A, b, c, d); }
+void orbo_project(const float* Rcw, const float* tcw, const float* k4, const float* bounds, const float* xyz, int n, float* u,
+                  float* v, float* invz, int32_t* valid) {
+    project_points(Rcw, tcw, k4[0], k4[1], k4[2], k4[3], bounds, xyz, n, u, v, invz, valid);
+}
 void orbo_distinctive(const uint8_t* desc, const int* start, int nPoints, int* best, int* bestMedian) {
     for (int p = 0; p < nPoints; ++p)
         best[p] = distinctive_descriptor(desc + 32 * (size_t)start[p], start[p + 1] - start[p], bestMedian + p);

@@ -207,6 +207,26 @@ class Oracle:
         return dict(word=pw, weight=pwt, node=pn, bow_word=bw[:cnt[0]].copy(), bow_value=bv[:cnt[0]].copy(),
                     fv_node=fn_[:cnt[1]].copy(), fv_start=fs[:cnt[1] + 1].copy(), fv_idx=fi[:cnt[2]].copy())
 
+    def gemm3(self, A, b, c=None):
+        """cv::Mat A(3x3) * b(3x1) [+ c] for CV_32F, as the matcher's projections evaluate it"""
+        A = np.ascontiguousarray(A, np.float32); b = np.ascontiguousarray(b, np.float32).ravel()
+        cc = None if c is None else np.ascontiguousarray(c, np.float32).ravel()
+        d = np.empty(3, np.float32)
+        self.lib.orbo_gemm3.argtypes = [C.c_void_p] * 4
+        self.lib.orbo_gemm3(_p(A), _p(b), _p(cc), _p(d))
+        return d
+
+    def project(self, Rcw, tcw, K4, bounds, xyz):
+        """ORBmatcher.cc:1376-1393 for n world points: (u, v, invz, valid)"""
+        R = np.ascontiguousarray(Rcw, np.float32); t = np.ascontiguousarray(tcw, np.float32).ravel()
+        k = np.ascontiguousarray(K4, np.float32); bd = np.ascontiguousarray(bounds, np.float32)
+        p = np.ascontiguousarray(xyz, np.float32).reshape(-1, 3)
+        n = len(p)
+        u = np.empty(n, np.float32); v = np.empty(n, np.float32); iz = np.empty(n, np.float32); ok = np.empty(n, np.int32)
+        self.lib.orbo_project.argtypes = [C.c_void_p] * 5 + [C.c_int] + [C.c_void_p] * 4
+        self.lib.orbo_project(_p(R), _p(t), _p(k), _p(bd), _p(p), n, _p(u), _p(v), _p(iz), _p(ok))
+        return u, v, iz, ok
+
     def distinctive(self, desc, start):
         """MapPoint::ComputeDistinctiveDescriptors for len(start)-1 map points (CSR runs of `desc`): (best, median)"""
         d = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)

@@ -140,3 +140,31 @@ def test_undistort_points_sign_flip_guard(oracle, K4, dist, size):
     got = oracle.undistort(pts, K4, dist)
     assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
     assert np.isclose(ref, pts, atol=1e-3).all(1).sum() > 1000          # the guard branch really was exercised
+
+
+def test_gemm_3x3_projection(oracle):
+    """x3Dc = Rcw * x3Dw + tcw (ORBmatcher.cc:1377): cv evaluates the expression as one gemm whose small-matrix path is
+    float arithmetic in source order -- NOT a double accumulation.  Pinned on random poses, with and without the + tcw."""
+    rng = np.random.default_rng(0)
+    for i in range(4000):
+        R = rng.normal(size=(3, 3)).astype(np.float32)
+        P = (rng.normal(size=(3, 1)) * 5).astype(np.float32)
+        t = rng.normal(size=(3, 1)).astype(np.float32)
+        assert np.array_equal(oracle.gemm3(R, P, t).view(np.uint32), cv2.gemm(R, P, 1.0, t, 1.0).ravel().view(np.uint32))
+        if i % 4 == 0:
+            assert np.array_equal(oracle.gemm3(R, P).view(np.uint32), cv2.gemm(R, P, 1.0, None, 0.0).ravel().view(np.uint32))
+    # the whole projection on a plausible pose: u, v, invz from float operations in source order
+    T = np.eye(4, dtype=np.float32)
+    T[:3, :3] = cv2.Rodrigues(np.array([0.02, -0.05, 0.01], np.float32))[0].astype(np.float32)
+    T[:3, 3] = [0.1, -0.03, 0.2]
+    K4 = np.array([458.654, 457.296, 367.215, 248.375], np.float32)
+    xyz = (rng.normal(size=(2000, 3)) * [2, 1.5, 1] + [0, 0, 4]).astype(np.float32)
+    u, v, iz, ok = oracle.project(T[:3, :3], T[:3, 3], K4, [0, 0, 752, 480], xyz)
+    for i in range(len(xyz)):
+        c = cv2.gemm(np.ascontiguousarray(T[:3, :3]), xyz[i].reshape(3, 1), 1.0, np.ascontiguousarray(T[:3, 3]).reshape(3, 1), 1.0).ravel()
+        invz = np.float32(1.0 / np.float64(c[2]))
+        uu = np.float32(np.float32(np.float32(K4[0] * c[0]) * invz) + K4[2])
+        vv = np.float32(np.float32(np.float32(K4[1] * c[1]) * invz) + K4[3])
+        assert u[i] == uu and v[i] == vv and iz[i] == invz
+        assert bool(ok[i]) == bool(invz >= 0 and 0 <= uu <= 752 and 0 <= vv <= 480)
+    assert 200 < ok.sum() < 2000
