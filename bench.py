@@ -192,9 +192,8 @@ def cpu_matcher_reference():
     except Exception as ex:  # the .so may be missing on a box that never saw /root/reference
         out["search_kind"] = "unavailable: %s" % ex
     try:   # CPU side of the section-8f rows: the reference's own ComputeStereoMatches text, the oracle's distinctive loop
-        sys.path.insert(0, os.path.join(ROOT, "tests"))
         import ref_stereo
-        from datagen import stereo_pair
+        from orbb200.synth import stereo_pair
         left, right = stereo_pair(1, 752, 480)
         el, er = o.extractor(1200, SCALE, NLEVELS, INI_TH, MIN_TH), o.extractor(1200, SCALE, NLEVELS, INI_TH, MIN_TH)
         kl, dl = el.extract(left)
@@ -220,7 +219,7 @@ def cpu_matcher_reference():
         o.distinctive(desc, start)
         out["distinctive_descriptors_20000_points_ms"] = (time.perf_counter() - t0) * 1e3 * 10
         out["distinctive_kind"] = "port (oracle/match_oracle.cpp), 2000 points timed and scaled x10"
-        from bow_cases import make_vocab
+        from orbb200.synth import make_vocab
         import ref_bow
         voc = make_vocab(seed=1, k=10, L=4)
         kw = dict(lib=ref_bow.lib(), fn="ref_bow_transform") if ref_bow.available() else {}
@@ -295,8 +294,7 @@ def frame_side_latency(device, m, med):
     import numpy as np
     import torch
     import orbb200
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    from datagen import stereo_pair
+    from orbb200.synth import stereo_pair
     out = {}
     w, h = 752, 480
     left, right = stereo_pair(1, w, h)
@@ -345,7 +343,7 @@ def frame_side_latency(device, m, med):
     out["distinctive_descriptors_20000_points"] = med(lambda: m.distinctive_descriptors(desc, start))
     out["distinctive_descriptors_observations"] = int(start[-1])
     # Frame::ComputeBoW: descent + BowVector / FeatureVector assembly, synthetic k=10 L=4 tree (ORBvoc itself is k=10 L=6)
-    from bow_cases import make_vocab
+    from orbb200.synth import make_vocab
     voc = make_vocab(seed=1, k=10, L=4)
     v = m.vocabulary(voc)
     out["bow_transform_%d_features_k10_L4" % len(dl)] = med(lambda: m.bow_transform(v, dl, 4))

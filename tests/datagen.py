@@ -23,18 +23,4 @@ def planted_descriptors(rng, nq, nt, frac=0.6, max_flip=60):
     return q, qa, t, ta
 
 
-def stereo_pair(seed, w=752, h=480, disparities=(6, 14, 27, 41), sigma=2.0):
-    """Rectified stereo pair of one synthetic scene: horizontal bands with different integer disparities (a point at
-    uL in the left image sits at uL - d in the right one), fresh sensor noise per view."""
-    from orbb200.synth import synth_frame
-    rng = np.random.default_rng(seed + 77)
-    dmax = max(disparities)
-    big = synth_frame(seed, w + dmax, h).astype(np.float64)
-    left = big[:, :w].copy()
-    right = np.empty_like(left)
-    edges = np.linspace(0, h, len(disparities) + 1).astype(int)
-    for d, y0, y1 in zip(disparities, edges[:-1], edges[1:]):
-        right[y0:y1] = big[y0:y1, d:d + w]
-    left = np.clip(np.rint(left + rng.normal(0, sigma, left.shape)), 0, 255).astype(np.uint8)
-    right = np.clip(np.rint(right + rng.normal(0, sigma, right.shape)), 0, 255).astype(np.uint8)
-    return np.ascontiguousarray(left), np.ascontiguousarray(right)
+from orbb200.synth import stereo_pair  # noqa: E402,F401  (lives with the other synthetic-input generators)

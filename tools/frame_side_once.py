@@ -8,11 +8,10 @@ import sys
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-for p in ("vi-orb-slam-icra2018_b200", "tests"):
-    sys.path.insert(0, os.path.join(ROOT, p))
+sys.path.insert(0, os.path.join(ROOT, "vi-orb-slam-icra2018_b200"))
 import torch  # noqa: E402
 import orbb200  # noqa: E402
-from datagen import stereo_pair  # noqa: E402
+from orbb200.synth import stereo_pair  # noqa: E402
 
 w, h = 752, 480
 left, right = stereo_pair(1, w, h)
@@ -37,7 +36,7 @@ sizes = rng.integers(2, 41, 300 if "--small" in sys.argv else 20000)
 start = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
 desc = rng.integers(0, 256, (int(start[-1]), 32), dtype=np.uint8)
 best, med = m.distinctive_descriptors(desc, start)
-from bow_cases import make_vocab  # noqa: E402
+from orbb200.synth import make_vocab  # noqa: E402
 voc = make_vocab(seed=1, k=10, L=4)
 v = m.vocabulary(voc)
 bow = m.bow_transform(v, dl, 4)

@@ -43,6 +43,22 @@ def shifted_pair(seed, w=752, h=480, dx=7, dy=3, sigma=2.0):
     return np.ascontiguousarray(a), np.ascontiguousarray(b)
 
 
+def stereo_pair(seed, w=752, h=480, disparities=(6, 14, 27, 41), sigma=2.0):
+    """Rectified stereo pair of one synthetic scene: horizontal bands with different integer disparities (a point at
+    uL in the left image sits at uL - d in the right one), fresh sensor noise per view."""
+    rng = np.random.default_rng(seed + 77)
+    dmax = max(disparities)
+    big = synth_frame(seed, w + dmax, h).astype(np.float64)
+    left = big[:, :w].copy()
+    right = np.empty_like(left)
+    edges = np.linspace(0, h, len(disparities) + 1).astype(int)
+    for d, y0, y1 in zip(disparities, edges[:-1], edges[1:]):
+        right[y0:y1] = big[y0:y1, d:d + w]
+    left = np.clip(np.rint(left + rng.normal(0, sigma, left.shape)), 0, 255).astype(np.uint8)
+    right = np.clip(np.rint(right + rng.normal(0, sigma, right.shape)), 0, 255).astype(np.uint8)
+    return np.ascontiguousarray(left), np.ascontiguousarray(right)
+
+
 def synth_frames_torch(n, w=752, h=480, seed=0, device="cuda"):
     """(n, h, w) uint8 tensor on `device`, same recipe as synth_frame evaluated with torch ops."""
     import torch
@@ -68,3 +84,62 @@ def synth_frames_torch(n, w=752, h=480, seed=0, device="cuda"):
     base = grid(120) * 120 + 60
     img = torch.clamp(torch.round(base + nz * contrast * 55), 0, 255).to(torch.uint8)
     return img[:, 0].contiguous()
+
+
+# ---- synthetic DBoW2 vocabulary trees (the reference's Vocabulary/ORBvoc.bin, k = 10, L = 6, is not in the checkout;
+# parity does not depend on how a tree was trained, only on its arrays)
+def make_vocab(seed, k=10, L=4, ragged=False, stop_fraction=0.02):
+    """Flat arrays of a DBoW2 tree built like HKmeansStep numbers it (children of a node get consecutive ids in creation
+    order, depth first per level); child descriptors are noisy copies of the parent's so that descents are informative.
+    ragged: some inner nodes keep fewer than k children and some branches end early (leaves above level L).
+    stop_fraction of the words get weight 0 (DBoW2 'stopped' words: transform skips them)."""
+    rng = np.random.default_rng(seed)
+    desc = [np.zeros(32, np.uint8)]
+    children = [[]]
+    level = [0]
+    frontier = [0]
+    for lv in range(1, L + 1):
+        nxt = []
+        for parent in frontier:
+            if ragged and lv > 1 and rng.random() < 0.08:
+                continue                                # the branch ends here: `parent` stays a leaf
+            nk = k if not ragged else int(rng.integers(2, k + 1))
+            base = np.unpackbits(desc[parent]) if parent else rng.integers(0, 2, 256, dtype=np.uint8)
+            for _ in range(nk):
+                bits = base.copy() if parent else rng.integers(0, 2, 256, dtype=np.uint8)
+                flip = rng.permutation(256)[:max(4, 96 >> lv)]
+                bits[flip] ^= 1
+                nid = len(desc)
+                desc.append(np.packbits(bits))
+                children.append([])
+                level.append(lv)
+                children[parent].append(nid)
+                nxt.append(nid)
+        frontier = nxt
+    n = len(desc)
+    word_id = np.zeros(n, np.int32)
+    weight = np.zeros(n, np.float64)
+    w = 0
+    for i in range(n):
+        if i and not children[i]:
+            word_id[i] = w
+            w += 1
+            weight[i] = 0.0 if rng.random() < stop_fraction else float(np.log(rng.uniform(1.5, 400.0)))
+    start = np.zeros(n + 1, np.int32)
+    start[1:] = np.cumsum([len(c) for c in children])
+    flat = np.array([c for cs in children for c in cs], np.int32)
+    return dict(n_nodes=n, L=L, k=k, desc=np.ascontiguousarray(np.stack(desc)), child_start=start, children=flat,
+                word_id=word_id, weight=weight, n_words=w)
+
+
+def features_for(voc, seed, n):
+    """descriptors near random tree nodes (so different branches are visited) plus pure noise"""
+    rng = np.random.default_rng(seed)
+    pick = rng.integers(1, voc["n_nodes"], n)
+    bits = np.unpackbits(voc["desc"][pick], axis=1)
+    for i in range(n):
+        k = int(rng.integers(0, 50))
+        bits[i, rng.permutation(256)[:k]] ^= 1
+    out = np.packbits(bits, axis=1)
+    out[::17] = rng.integers(0, 256, (len(out[::17]), 32), dtype=np.uint8)
+    return np.ascontiguousarray(out)
