@@ -57,7 +57,7 @@ struct orbx_extractor {
     int kpCapacity = 0;       // upper bound on keypoints per frame
     int otSmem = 0, otKeyCap = 0, otNodeCap = 0, otCellCap = 0;
     // device memory
-    DevBuf pyr, blur, slots, cellCount, sel, selCount, keyWs, dCells, dTiles, dTabOfs, dTabCoef;
+    DevBuf pyr, blur, slots, cellCount, sel, selCount, keyWs, dCells, dTiles, dTabOfs, dTabCoef, dFastMaps;
     DevBuf dImages, dKps, dDesc, dCount;
     DevBuf stKeysL, stDescL, stKeysR, stDescR, stOut;   // staging of orbx_compute_stereo_matches
     int lastFrames = 0, lastCapacity = 0;
@@ -186,6 +186,15 @@ int configure(orbx_extractor* e, int w, int h, int nFrames) {
     P.maxCellH = 1;
     for (const Cell& c : cells) { P.maxCellW = std::max(P.maxCellW, (int)c.cw); P.maxCellH = std::max(P.maxCellH, (int)c.ch); }
     P.fast = fast_layout(P.maxCellW, P.maxCellH);
+    {
+        int cellW[kMaxLevels] = {0}, cellH[kMaxLevels] = {0}, slotCapMax = 1;
+        for (const Cell& c : cells) {
+            cellW[c.level] = std::max(cellW[c.level], (int)c.cw);
+            cellH[c.level] = std::max(cellH[c.level], (int)c.ch);
+        }
+        for (int l = 0; l < nl; ++l) slotCapMax = std::max(slotCapMax, lv[l].slotCap);
+        ORB_CHECK(fast_warp_plan(nl, cellW, cellH, slotCapMax, &P.fw));
+    }
     P.selPerFrame = selOff;
     P.pyrFrameBytes = pyrOff;
     P.blurFrameBytes = blurOff;
@@ -202,6 +211,14 @@ int configure(orbx_extractor* e, int w, int h, int nFrames) {
     P.tabOfs = e->dTabOfs.as<int>();
     P.tabCoef = e->dTabCoef.as<short2>();
     for (int l = 0; l < nl; ++l) P.lv[l] = lv[l];
+    {   // TMA descriptors of the padded pyramid levels: [arena frame][row][pitch], box = one FAST tile
+        unsigned char hostMaps[128 * kMaxLevels];
+        ORB_CHECK(e->dFastMaps.reserve(sizeof hostMaps));
+        ORB_CHECK(fast_warp_encode_maps(P, (int)F, hostMaps));
+        ORB_CUDA(cudaMemcpyAsync(e->dFastMaps.p, hostMaps, sizeof hostMaps, cudaMemcpyHostToDevice, e->stream));
+        ORB_CUDA(cudaStreamSynchronize(e->stream));
+        P.fw.maps = e->dFastMaps.p;
+    }
     e->cells.swap(cells);
     e->tiles.swap(tiles);
     e->kpCapacity = selOff;
@@ -218,6 +235,7 @@ int enqueue(orbx_extractor* e, const uint8_t* dImages, int nFrames, int w, int h
     ExtractParams P = e->P;
     P.nFrames = nFrames;
     P.outCapacity = capacity;
+    P.fw.frameBase = frameBase;
     if (frameBase) {   // this call works in arena slots [frameBase, frameBase + nFrames)
         P.pyr += (size_t)frameBase * P.pyrFrameBytes;
         P.blur += (size_t)frameBase * P.blurFrameBytes;
@@ -245,7 +263,9 @@ int enqueue(orbx_extractor* e, const uint8_t* dImages, int nFrames, int w, int h
     ORB_CHECK(launch_pyramid(P, dImages, w, h, stride, frameStride, st, &e->launches));
     if (timed) ORB_CUDA(cudaEventRecord(e->ev[1], st));
     if (pe) ORB_CUDA(cudaEventRecord(pe[1], st));
-    ORB_CHECK(launch_fast(P, st, &e->launches));
+    static const bool fastV1 = getenv("ORBB_FAST_V1") != nullptr;   // round-1 CTA-per-cell kernel, kept for A/B timing
+    if (fastV1) ORB_CHECK(launch_fast(P, st, &e->launches));
+    else ORB_CHECK(launch_fast_warp(P, st, &e->launches));
     if (pe) ORB_CUDA(cudaEventRecord(pe[2], st));
     ORB_CHECK(launch_octree(P, e->otSmem, e->otKeyCap, e->otNodeCap, e->otCellCap, st, &e->launches));
     if (timed) ORB_CUDA(cudaEventRecord(e->ev[2], st));
@@ -348,7 +368,7 @@ int orbx_destroy(orbx_handle e) {
     DeviceGuard g(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
     DevBuf* bufs[] = {&e->pyr, &e->blur, &e->slots, &e->cellCount, &e->sel, &e->selCount, &e->keyWs, &e->dCells,
-                      &e->dTiles, &e->dTabOfs, &e->dTabCoef, &e->dImages, &e->dKps, &e->dDesc, &e->dCount,
+                      &e->dTiles, &e->dTabOfs, &e->dTabCoef, &e->dFastMaps, &e->dImages, &e->dKps, &e->dDesc, &e->dCount,
                       &e->stKeysL, &e->stDescL, &e->stKeysR, &e->stDescR, &e->stOut};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < 4; ++i)

@@ -65,6 +65,24 @@ struct FastLayout {      // byte offsets inside the FAST kernel's dynamic shared
     int qCap;            // queue capacity in entries
 };
 
+// Plan of the warp-per-cell FAST kernel (fast_warp.cu), host-computed per image size.  Every warp owns one region of
+// the CTA's dynamic shared memory: two mbarriers, two TMA tile buffers (double-buffered byte tiles of bw x bh), the score
+// map with its 1-px zero ring, the candidate queue (compacted in place into the corner list) and the NMS survivor list.
+struct FastWarpPlan {
+    int bw, bh;              // TMA box: bytes per tile row (48 / 64 / 80) and rows (largest cell + 6)
+    int tileBytes;           // bw * bh = bytes one TMA load delivers
+    int scorePitch;          // bytes per score-map row
+    int scoreVec;            // uint4 count of the score map
+    int offTile, tileStride, offScore, offQueue, offSurv, warpBytes;
+    int queueCap, survCap;   // entries (16 bit each)
+    int smemBytes;
+    // pre-test work items of a level's cells: groups (4-px columns) x bands per cell, 2 * halfRows pixel rows per item;
+    // rcpGroups = ceil(2^16 / groups), rcpBandStep = ceil(2^16 / (2 * bands))
+    struct Level { unsigned short groups, bands, halfRows, pad; unsigned int rcpGroups, rcpBandStep; } lv[kMaxLevels];
+    int frameBase;           // arena slot of this launch's frame 0 (the tensor maps are anchored at the arena base)
+    const void* maps;        // device array of kMaxLevels CUtensorMap (one per pyramid level)
+};
+
 struct SelKey {          // quadtree survivor in level coordinates
     float x, y, response, angle;
 };
@@ -78,6 +96,7 @@ struct ExtractParams {
     int outCapacity;         // caller's per-frame output capacity
     int maxCellW, maxCellH;  // largest FAST cell interior of this image size (sizes the FAST kernel's shared memory)
     FastLayout fast;
+    FastWarpPlan fw;
     long long pyrFrameBytes, blurFrameBytes, slotFrameEntries, keyWsFrameEntries;
     unsigned char* pyr;
     unsigned char* blur;
@@ -109,6 +128,10 @@ int launch_pyramid(const ExtractParams& P, const unsigned char* dImages, int wid
                    size_t frameStride, cudaStream_t st, int* launches);
 int launch_fast(const ExtractParams& P, cudaStream_t st, int* launches);
 FastLayout fast_layout(int maxCellW, int maxCellH);
+int fast_warp_plan(int nLevels, const int* cellW, const int* cellH, int slotCapMax, FastWarpPlan* plan);
+int launch_fast_warp(const ExtractParams& P, cudaStream_t st, int* launches);
+// one CUtensorMap (128 bytes, host copy) per level over [frames][rows][pitch] of the padded pyramid arena
+int fast_warp_encode_maps(const ExtractParams& P, int arenaFrames, void* hostMaps128xLevels);
 void fast_cell_setup(Cell& c, long long levelPyrOff, int pitch);
 int launch_octree(const ExtractParams& P, int smemBytes, int keyCapSmem, int nodeCap, int cellCap, cudaStream_t st,
                   int* launches);
