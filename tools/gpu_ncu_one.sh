@@ -1,5 +1,4 @@
 # usage: gpu_ncu_one.sh <kernel-regex> <out-name> [skip]   -- one `ncu --set full` capture of a 256-frame launch
-set -x
 cd "${GRAFT_REPO_ROOT:-.}"
 mkdir -p gpurun_out
 B="python bench.py --steps 2 --warmup 3 --frames 256 --no-cpu --no-hamming --no-latency"

@@ -22,6 +22,7 @@ LIB = os.path.join(HERE, "liborbb200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
          "-Xcompiler", "-fPIC,-O2,-fno-fast-math,-ffp-contract=off", "-Xptxas", "-v", "--threads", "4"]
+FLAGS += os.environ.get("ORBB_NVCC_EXTRA", "").split()   # e.g. -DORBB_FW_STATS: debug counters of the FAST kernel
 
 
 def _sources():

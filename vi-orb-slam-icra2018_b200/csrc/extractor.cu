@@ -57,7 +57,7 @@ struct orbx_extractor {
     int kpCapacity = 0;       // upper bound on keypoints per frame
     int otSmem = 0, otKeyCap = 0, otNodeCap = 0, otCellCap = 0;
     // device memory
-    DevBuf pyr, blur, slots, cellCount, sel, selCount, keyWs, dCells, dTiles, dTabOfs, dTabCoef, dFastMaps;
+    DevBuf pyr, blur, slots, cellCount, sel, selCount, keyWs, dCells, dTiles, dTabOfs, dTabCoef, dFastMaps, dFastScratch, dFastCounters;
     DevBuf dImages, dKps, dDesc, dCount;
     DevBuf stKeysL, stDescL, stKeysR, stDescR, stOut;   // staging of orbx_compute_stereo_matches
     int lastFrames = 0, lastCapacity = 0;
@@ -218,6 +218,13 @@ int configure(orbx_extractor* e, int w, int h, int nFrames) {
         ORB_CUDA(cudaMemcpyAsync(e->dFastMaps.p, hostMaps, sizeof hostMaps, cudaMemcpyHostToDevice, e->stream));
         ORB_CUDA(cudaStreamSynchronize(e->stream));
         P.fw.maps = e->dFastMaps.p;
+        ORB_CHECK(fast_warp_max_warps(P.fw, &P.fw.maxWarps));
+        ORB_CHECK(e->dFastScratch.reserve((size_t)P.fw.maxWarps * P.fw.scratchCap * 2));
+        P.fw.scratch = e->dFastScratch.as<unsigned short>();
+        ORB_CHECK(e->dFastCounters.reserve(16));
+        ORB_CUDA(cudaMemsetAsync(e->dFastCounters.p, 0, 16, e->stream));
+        ORB_CUDA(cudaStreamSynchronize(e->stream));
+        P.fw.counters = e->dFastCounters.as<unsigned int>();
     }
     e->cells.swap(cells);
     e->tiles.swap(tiles);
@@ -368,7 +375,7 @@ int orbx_destroy(orbx_handle e) {
     DeviceGuard g(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
     DevBuf* bufs[] = {&e->pyr, &e->blur, &e->slots, &e->cellCount, &e->sel, &e->selCount, &e->keyWs, &e->dCells,
-                      &e->dTiles, &e->dTabOfs, &e->dTabCoef, &e->dFastMaps, &e->dImages, &e->dKps, &e->dDesc, &e->dCount,
+                      &e->dTiles, &e->dTabOfs, &e->dTabCoef, &e->dFastMaps, &e->dFastScratch, &e->dFastCounters, &e->dImages, &e->dKps, &e->dDesc, &e->dCount,
                       &e->stKeysL, &e->stDescL, &e->stKeysR, &e->stDescR, &e->stOut};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < 4; ++i)

@@ -67,20 +67,26 @@ struct FastLayout {      // byte offsets inside the FAST kernel's dynamic shared
 
 // Plan of the warp-per-cell FAST kernel (fast_warp.cu), host-computed per image size.  Every warp owns one region of
 // the CTA's dynamic shared memory: two mbarriers, two TMA tile buffers (double-buffered byte tiles of bw x bh), the score
-// map with its 1-px zero ring, the candidate queue (compacted in place into the corner list) and the NMS survivor list.
+// map (same pitch as the tile, so one offset addresses both), the candidate queue (compacted in place into the corner
+// list) and the NMS survivor list.
 struct FastWarpPlan {
-    int bw, bh;              // TMA box: bytes per tile row (48 / 64 / 80) and rows (largest cell + 6)
+    int bw, bh;              // TMA box: bytes per tile row (80 / 96) and rows (largest cell + 6)
     int tileBytes;           // bw * bh = bytes one TMA load delivers
-    int scorePitch;          // bytes per score-map row
+    int scorePitch;          // bytes per score-map row (interior + 1-px zero ring)
     int scoreVec;            // uint4 count of the score map
-    int offTile, tileStride, offScore, offQueue, offSurv, warpBytes;
-    int queueCap, survCap;   // entries (16 bit each)
+    int lutBytes;            // bit -> pixel tables at the start of the CTA's dynamic shared memory (256 bytes per level)
+    int offTile, tileStride, offScore, offQueue, offBitmap, warpBytes;   // inside a warp's region
+    int queueCap;            // entries (16 bit each) of the shared-memory queue
     int smemBytes;
-    // pre-test work items of a level's cells: groups (4-px columns) x bands per cell, 2 * halfRows pixel rows per item;
-    // rcpGroups = ceil(2^16 / groups), rcpBandStep = ceil(2^16 / (2 * bands))
-    struct Level { unsigned short groups, bands, halfRows, pad; unsigned int rcpGroups, rcpBandStep; } lv[kMaxLevels];
     int frameBase;           // arena slot of this launch's frame 0 (the tensor maps are anchored at the arena base)
     const void* maps;        // device array of kMaxLevels CUtensorMap (one per pyramid level)
+    unsigned int* counters;  // {next work item, finished warps}: dynamic cell scheduling; the last warp out zeroes both
+    unsigned short* scratch; // global-memory queues for cells with more candidates than queueCap (one per resident warp)
+    int scratchCap;          // entries per warp: 2 per pixel of the largest cell
+    int maxWarps;            // warps the scratch was sized for
+    // pre-test schedule of a level's cells: a step is one pixel row of 4 adjacent 4-px groups per 8 rows (lane = row r
+    // of 8, group q of 4); T steps cover the width, chunks of `chunkSteps` (a multiple of T, <= 8) fill one 32-bit mask
+    struct Level { unsigned char T, chunkSteps, steps, pad; } lv[kMaxLevels];
 };
 
 struct SelKey {          // quadtree survivor in level coordinates
@@ -129,6 +135,7 @@ int launch_pyramid(const ExtractParams& P, const unsigned char* dImages, int wid
 int launch_fast(const ExtractParams& P, cudaStream_t st, int* launches);
 FastLayout fast_layout(int maxCellW, int maxCellH);
 int fast_warp_plan(int nLevels, const int* cellW, const int* cellH, int slotCapMax, FastWarpPlan* plan);
+int fast_warp_max_warps(const FastWarpPlan& plan, int* warps);   // resident warps of one launch on the current device
 int launch_fast_warp(const ExtractParams& P, cudaStream_t st, int* launches);
 // one CUtensorMap (128 bytes, host copy) per level over [frames][rows][pitch] of the padded pyramid arena
 int fast_warp_encode_maps(const ExtractParams& P, int arenaFrames, void* hostMaps128xLevels);

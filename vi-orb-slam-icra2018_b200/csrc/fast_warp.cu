@@ -26,13 +26,19 @@
 //        is necessary.  8 aligned word loads, 5 PRMT that undo the misalignment (selectors uniform per cell), 10 PRMT
 //        that widen, 12 VIMNMX, 8 threshold ops per 4 pixels; the results of 8 rows x 4 pixels accumulate in one
 //        32-bit mask per polarity (no per-row bookkeeping);
-//     B. the set bits become queue entries (x | y<<6 | polarity<<12), one ballot per round so that consecutive entries
-//        come from different lanes (different banks);
+//     B. the set bits become queue entries (x | y<<6 | polarity<<15).  Lane (r, q) of a step owns row 8m + r and the
+//        4-px group 4t + q, so a step's 32 lanes read 32 different banks; the per-lane counts of a chunk's four step
+//        pairs are prefix-summed over the warp (two packed shuffle scans) and every lane writes its own entries, which
+//        makes the queue block-major, lane-major: 32 consecutive entries = 4-5 pixel rows = distinct bank octets, so
+//        the byte gathers of phase C see ~1.1 wavefronts per load instead of 2.5;
 //     C. exact score of the queued pixels, TWO per lane: the pre-test told the polarity, so entry A rides in the low
 //        and entry B in the high 16-bit half of every operand (d = 256 +- (p - v) by one IMAD each), and the 40
 //        three-input min/max of the 9-arc scan serve both.  Corners (S >= t) go to the score map and are compacted in
 //        place to the front of the queue;
-//     D. NMS over the corner list, survivors listed, ranked by (y, x), packed x:12|y:12|score:8 into the cell's slot.
+//     D. NMS over the corner list, survivors listed, ranked by (y, x), packed x:12|y:12|score:8 into the cell's slot;
+//        the score map is zeroed again through the corner list.
+//   The shared-memory queue holds a typical cell (~300 candidates) with room to spare; a cell with more candidates
+//   than that (up to 2 per pixel) is redone with its queue in a per-warp global scratch area.
 //   A cell with no survivor at iniThFAST simply runs A-D again at minThFAST (the reference's second cv::FAST call).
 #include <cuda.h>
 
@@ -44,7 +50,14 @@
 
 namespace orbb {
 
-constexpr int FW_WARPS = 4;                       // warps per CTA; they share nothing but the 128-byte bit->pixel table
+#ifdef ORBB_FW_STATS
+__device__ unsigned long long gFwStats[8];   // cells, rounds, second rounds, overflows, queue entries, corners, survivors
+#define FW_STAT(i, v) do { if (lane == 0) atomicAdd(&gFwStats[i], (unsigned long long)(v)); } while (0)
+#else
+#define FW_STAT(i, v) do { } while (0)
+#endif
+
+constexpr int FW_WARPS = 7;                       // warps per CTA; they share nothing but the bit -> pixel tables
 constexpr unsigned int FW_FULL = 0xffffffffu;
 constexpr unsigned int FW_PASS = 0x02000200u;     // bit 9 of each 16-bit half
 
@@ -82,14 +95,15 @@ __device__ __forceinline__ void tma_load_tile(unsigned int dst, const void* map,
 // per-cell selectors: selC = 0x3210 + 0x1111*s, selL = selC + 0x1111, and x0+3.. lies in words (1,2) for s < 2 and in
 // words (2,3) otherwise (hiR).  bright / dark get bits 9, 25 (pixels x0, x0+1) and 10, 26 (x0+2, x0+3).
 // K = 0x0200 - (t+1) in both halves: bit 9 of (m - c + K) is set iff m >= c + t + 1; all halves stay in [1, 0x2fe], so
-// no borrow crosses the halves and each expression is one three-input add.
+// no borrow crosses the halves and each expression is one three-input add.  vA / vB are FW_PASS restricted to the
+// pixels that exist (cell edge), so validity costs nothing here.
 struct FwAlign {
     unsigned int selC, selL, selR;
     bool hiR;
 };
 template <int BW>
-__device__ __forceinline__ void pretest_row(const unsigned char* r, const FwAlign& al, unsigned int K, unsigned int& bright,
-                                            unsigned int& dark) {
+__device__ __forceinline__ void pretest_row(const unsigned char* r, const FwAlign& al, unsigned int K, unsigned int vA, unsigned int vB,
+                                            unsigned int& bright, unsigned int& dark) {
     const unsigned int* w = reinterpret_cast<const unsigned int*>(r);
     const unsigned int* wu = reinterpret_cast<const unsigned int*>(r - 3 * BW);
     const unsigned int* wd = reinterpret_cast<const unsigned int*>(r + 3 * BW);
@@ -106,31 +120,16 @@ __device__ __forceinline__ void pretest_row(const unsigned char* r, const FwAlig
     const unsigned int rA = __byte_perm(FR, 0, 0x4140), rB = __byte_perm(FR, 0, 0x4342);
     const unsigned int mmA = __vminu2(__vmaxu2(uA, dA), __vmaxu2(lA, rA)), mmB = __vminu2(__vmaxu2(uB, dB), __vmaxu2(lB, rB));
     const unsigned int nnA = __vmaxu2(__vminu2(uA, dA), __vminu2(lA, rA)), nnB = __vmaxu2(__vminu2(uB, dB), __vminu2(lB, rB));
-    const unsigned int bA = (mmA - cA + K) & FW_PASS, bB = (mmB - cB + K) & FW_PASS;
-    const unsigned int kA = (cA - nnA + K) & FW_PASS, kB = (cB - nnB + K) & FW_PASS;
+    const unsigned int bA = (mmA - cA + K) & vA, bB = (mmB - cB + K) & vB;
+    const unsigned int kA = (cA - nnA + K) & vA, kB = (cB - nnB + K) & vB;
     bright = bA + 2u * bB;
     dark = kA + 2u * kB;
 }
 
-// mask bits of the first n (<= 8) rows of an item: row j owns bits 9+2j, 10+2j, 25+2j, 26+2j (mod 32)
-__device__ __forceinline__ unsigned int rows_mask(int n) {
-    const unsigned int h = (1u << (2 * n)) - 1u;
-    return __funnelshift_l(h * 0x00010001u, h * 0x00010001u, 9);
-}
-
-// B: append the set bits of m to the queue; one ballot per round, so a round's entries come from distinct lanes
-__device__ __forceinline__ int enqueue_bits(unsigned int m, unsigned int baseEntry, const unsigned short* lut, unsigned short* queue,
-                                            int n, unsigned int ltMask) {
-    unsigned int bal;
-    while ((bal = __ballot_sync(FW_FULL, m != 0u)) != 0u) {
-        if (m) {
-            const int k = 31 - __clz(m);
-            m ^= 1u << k;
-            queue[n + __popc(bal & ltMask)] = (unsigned short)(baseEntry + lut[k]);
-        }
-        n += __popc(bal);
-    }
-    return n;
+// FW_PASS restricted to the first n (of 4) pixels of a group: pair A = pixels 0, 1 (bits 9, 25), pair B = pixels 2, 3
+__device__ __forceinline__ void valid_pairs(int n, unsigned int& vA, unsigned int& vB) {
+    vA = (n >= 1 ? 0x00000200u : 0u) | (n >= 2 ? 0x02000000u : 0u);
+    vB = (n >= 3 ? 0x00000200u : 0u) | (n >= 4 ? 0x02000000u : 0u);
 }
 
 // circle offsets in tile bytes, OpenCV order (dx,dy) = (0,3)(1,3)(2,2)(3,1)(3,0)(3,-1)(2,-2)(1,-3)(0,-3)(-1,-3)(-2,-2)
@@ -141,17 +140,64 @@ __device__ __forceinline__ int enqueue_bits(unsigned int m, unsigned int baseEnt
      : (k) == 8 ? -3 * (P) : (k) == 9 ? -3 * (P)-1 : (k) == 10 ? -2 * (P)-2 : (k) == 11 ? -(P)-3           \
      : (k) == 12 ? -3 : (k) == 13 ? (P)-3 : (k) == 14 ? 2 * (P)-2 : 3 * (P)-1)
 
-struct FwWarp {            // the warp's shared-memory arrays
-    const unsigned char* tile;
-    unsigned char* score;
-    unsigned short* queue;
-    unsigned short* surv;
+struct FwWarp {            // the warp's arrays
+    const unsigned char* tile;     // shared memory: current tile buffer
+    unsigned char* scorePix;       // shared memory: score of pixel (x, y) at scorePix[y * scorePitch + x], zero ring around it
+    unsigned short* queue;         // shared memory, or the warp's global scratch for a cell that overflowed it
+    unsigned int* bitmap;          // shared memory: NMS survivors, one 64-bit row per pixel row
+    int queueCap;
+    unsigned short* globalQueue;
+    int globalCap;
 };
 
-// A-D for one cell at threshold th; returns the number of NMS survivors (listed in W.surv)
+struct FwSurvivors {       // a lane's view of the survivor bitmap: pixel rows `lane` and `lane + 32`
+    uint2 rowLo, rowHi;
+    int rankLo, rankHi;    // survivors in the rows before them
+};
+
+// B: the set bits of one chunk's masks become queue entries (x | y << 6 | polarity << 15).  A "unit" is a pair of steps
+// (one 8-row block when T = 2); the four units' per-lane counts are prefix-summed over the warp in two packed shuffle
+// scans.  Returns the new queue length, or -1 (nothing written) if the chunk does not fit.
+__device__ __forceinline__ int enqueue_chunk(unsigned int mb, unsigned int md, unsigned int laneEntry, const unsigned short (*lut)[32],
+                                             unsigned short* queue, int nq, int cap, int lane) {
+    constexpr unsigned int U0 = 0x1E001E00u, U1 = 0xE001E001u, U2 = 0x001E001Eu, U3 = 0x01E001E0u;   // U0 rotated by 4u
+    const unsigned int c0 = __popc(mb & U0) + __popc(md & U0), c1 = __popc(mb & U1) + __popc(md & U1);
+    const unsigned int c2 = __popc(mb & U2) + __popc(md & U2), c3 = __popc(mb & U3) + __popc(md & U3);
+    unsigned int s01 = c0 | (c1 << 16), s23 = c2 | (c3 << 16);
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned int a = __shfl_up_sync(FW_FULL, s01, d), b = __shfl_up_sync(FW_FULL, s23, d);
+        if (lane >= d) { s01 += a; s23 += b; }
+    }
+    const unsigned int t01 = __shfl_sync(FW_FULL, s01, 31), t23 = __shfl_sync(FW_FULL, s23, 31);
+    const int base1 = nq + (int)(t01 & 0xffffu), base2 = base1 + (int)(t01 >> 16), base3 = base2 + (int)(t23 & 0xffffu);
+    const int nqNew = base3 + (int)(t23 >> 16);
+    if (nqNew > cap) return -1;
+    const int pos[4] = {nq + (int)(s01 & 0xffffu) - (int)c0, base1 + (int)(s01 >> 16) - (int)c1, base2 + (int)(s23 & 0xffffu) - (int)c2,
+                        base3 + (int)(s23 >> 16) - (int)c3};
+    const unsigned int um[4] = {U0, U1, U2, U3};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        // bright bits stay, dark bits move 4 up (into the next unit's positions, which are masked out here)
+        unsigned int c = (mb & um[u]) | __funnelshift_l(md & um[u], md & um[u], 4);
+        c = __funnelshift_r(c, c, 4 * u);
+        unsigned short* w = queue + pos[u];
+        const unsigned short* l = lut[u];
+        while (c) {
+            const int k = 31 - __clz(c);
+            c ^= 1u << k;
+            *w++ = (unsigned short)(laneEntry + l[k]);
+        }
+    }
+    return nqNew;
+}
+
+// A-D for one cell at threshold th; returns the number of NMS survivors (bits of W.bitmap, S = this lane's rows of
+// it); nc = corners (W.queue[0, nc)).  A cell with more candidates than the shared-memory queue holds moves its queue
+// to the warp's global scratch.
 template <int BW>
-__device__ __forceinline__ int fast_cell(const FwWarp& W, const FastWarpPlan::Level& F, int scorePitch, const unsigned short* lut,
-                                         int cw, int ch, int mis, int th, int lane, unsigned int ltMask) {
+__device__ __forceinline__ int fast_cell(FwWarp& W, const FastWarpPlan::Level& F, const unsigned short (*lut)[32], int SP, int cw, int ch,
+                                         int mis, int th, int lane, unsigned int ltMask, int& ncOut, FwSurvivors& S) {
     // ---- A + B
     const unsigned int K = FW_PASS - (unsigned int)(th + 1) * 0x00010001u;
     FwAlign al;
@@ -162,59 +208,56 @@ __device__ __forceinline__ int fast_cell(const FwWarp& W, const FastWarpPlan::Le
         al.hiR = sh >= 2u;
         al.selR = 0x3210u + 0x1111u * (al.hiR ? sh - 1u : sh + 3u);
     }
-    const unsigned char* tileAligned = W.tile + (mis & ~3);      // word that holds pixel (-4, -3)
-    const unsigned char* tilePix = W.tile + mis + 3 * BW + 4;    // pixel (0, 0)
-    const int items = F.groups * F.bands;
-    const int pairStep = 2 * F.bands * BW;
+    const int r = lane >> 2, q = lane & 3;
+    const unsigned char* tilePix = W.tile + mis + 3 * BW + 4;              // pixel (0, 0)
+    const unsigned char* rowPtr = W.tile + (mis & ~3) + (r + 3) * BW + 4 * q;   // aligned word of pixel (4q - 4, r)
+    const int T = F.T, chunkSteps = F.chunkSteps, steps = F.steps;
+    const int chunkRows = 8 * (chunkSteps / T);
+    ncOut = 0;
     int nq = 0;
 #pragma unroll 1
-    for (int i0 = 0; i0 < items; i0 += 32) {
-        const int i = min(i0 + lane, items - 1);
-        const int b = (int)(((unsigned int)i * F.rcpGroups) >> 16), g = i - b * F.groups;
-        // valid rows are a prefix of the item's rows y(j) = 2b + 2*bands*(j>>1) + (j&1), valid pixels a prefix of its 4
-        const int rem = ch - 2 * b;
-        int nRows = 0;
-        if (rem >= 2) nRows = 2 * ((int)(((unsigned int)(rem - 2) * F.rcpBandStep) >> 16) + 1);
-        if (rem >= 1) {
-            const int q = (int)(((unsigned int)(rem - 1) * F.rcpBandStep) >> 16);
-            if (q * 2 * F.bands == rem - 1) nRows += 1;
-        }
-        nRows = min(nRows, 2 * F.halfRows);
-        const int nCols = cw - 4 * g;
-        unsigned int colMask = nCols >= 4 ? 0xffffffffu : nCols == 3 ? 0xabfffeaau : nCols == 2 ? 0xaaaaaaaau : nCols == 1 ? 0x00aaaa00u : 0u;
-        if (i0 + lane >= items) colMask = 0u;
-        const unsigned char* r = tileAligned + (2 * b + 3) * BW + 4 * g;
-        unsigned int mb0 = 0, md0 = 0, mb1 = 0, md1 = 0;
+    for (int j0 = 0, y0 = r; j0 < steps; j0 += chunkSteps, y0 += chunkRows, rowPtr += chunkRows * BW) {
+        const int nSteps = min(chunkSteps, steps - j0);
+        unsigned int mb = 0, md = 0;
+        if (T == 2) {
+            // 8 groups per row: step i = (block i>>1, half i&1), everything about the columns is loop-invariant
+            unsigned int vA0, vB0, vA1, vB1;
+            valid_pairs(cw - 4 * q, vA0, vB0);
+            valid_pairs(cw - 16 - 4 * q, vA1, vB1);
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-            if (jj < F.halfRows) {
-                unsigned int tb, td;
-                pretest_row<BW>(r + jj * pairStep, al, K, tb, td);
-                mb0 |= __funnelshift_l(tb, tb, 4 * jj);
-                md0 |= __funnelshift_l(td, td, 4 * jj);
-                pretest_row<BW>(r + jj * pairStep + BW, al, K, tb, td);
-                mb0 |= __funnelshift_l(tb, tb, 4 * jj + 2);
-                md0 |= __funnelshift_l(td, td, 4 * jj + 2);
+            for (int i = 0; i < 8; ++i) {
+                if (i < nSteps) {
+                    const bool rowOk = y0 + 8 * (i >> 1) < ch;
+                    unsigned int tb, td;
+                    pretest_row<BW>(rowPtr + (i >> 1) * 8 * BW + 16 * (i & 1), al, K, rowOk ? ((i & 1) ? vA1 : vA0) : 0u,
+                                    rowOk ? ((i & 1) ? vB1 : vB0) : 0u, tb, td);
+                    mb |= __funnelshift_l(tb, tb, 2 * i);
+                    md |= __funnelshift_l(td, td, 2 * i);
+                }
+            }
+        } else {
+            int t = 0, y = y0;
+            const unsigned char* rp = rowPtr;
+#pragma unroll 1
+            for (int i = 0; i < nSteps; ++i) {
+                unsigned int vA, vB, tb, td;
+                valid_pairs(y < ch ? cw - 16 * t - 4 * q : 0, vA, vB);
+                pretest_row<BW>(rp + 16 * t, al, K, vA, vB, tb, td);
+                mb |= __funnelshift_l(tb, tb, 2 * i);
+                md |= __funnelshift_l(td, td, 2 * i);
+                if (++t == T) { t = 0; y += 8; rp += 8 * BW; }
             }
         }
-#pragma unroll 1
-        for (int jj = 4; jj < F.halfRows; ++jj) {
-            unsigned int tb, td;
-            pretest_row<BW>(r + jj * pairStep, al, K, tb, td);
-            mb1 |= __funnelshift_l(tb, tb, 4 * (jj - 4));
-            md1 |= __funnelshift_l(td, td, 4 * (jj - 4));
-            pretest_row<BW>(r + jj * pairStep + BW, al, K, tb, td);
-            mb1 |= __funnelshift_l(tb, tb, 4 * (jj - 4) + 2);
-            md1 |= __funnelshift_l(td, td, 4 * (jj - 4) + 2);
+        int n2 = enqueue_chunk(mb, md, (unsigned int)((y0 << 6) | (4 * q)), lut, W.queue, nq, W.queueCap, lane);
+        if (n2 < 0) {
+            __syncwarp();
+            for (int i = lane; i < nq; i += 32) W.globalQueue[i] = W.queue[i];
+            W.queue = W.globalQueue;
+            W.queueCap = W.globalCap;
+            __syncwarp();
+            n2 = enqueue_chunk(mb, md, (unsigned int)((y0 << 6) | (4 * q)), lut, W.queue, nq, W.queueCap, lane);
         }
-        const unsigned int v0 = colMask & rows_mask(min(nRows, 8)), v1 = colMask & rows_mask(max(nRows - 8, 0));
-        const unsigned int baseEntry = (unsigned int)(4 * g) | ((unsigned int)(2 * b) << 6);
-        nq = enqueue_bits(mb0 & v0, baseEntry, lut, W.queue, nq, ltMask);
-        nq = enqueue_bits(md0 & v0, baseEntry + 0x1000u, lut, W.queue, nq, ltMask);
-        if (F.halfRows > 4) {
-            nq = enqueue_bits(mb1 & v1, baseEntry, lut + 32, W.queue, nq, ltMask);
-            nq = enqueue_bits(md1 & v1, baseEntry + 0x1000u, lut + 32, W.queue, nq, ltMask);
-        }
+        nq = n2;
     }
     __syncwarp();
 
@@ -229,7 +272,7 @@ __device__ __forceinline__ int fast_cell(const FwWarp& W, const FastWarpPlan::Le
         const unsigned char* pA = tilePix + yA * BW + xA;
         const unsigned char* pB = tilePix + yB * BW + xB;
         // d = 256 + (p - v) for a bright candidate, 256 + (v - p) for a dark one: every half stays in [1, 511]
-        const int mulA = (eA & 0x1000u) ? -1 : 1, mulB = (eB & 0x1000u) ? -65536 : 65536;
+        const int mulA = (eA & 0x8000u) ? -1 : 1, mulB = (eB & 0x8000u) ? -65536 : 65536;
         const unsigned int C = 0x01000100u - (unsigned int)mulA * pA[0] - (unsigned int)mulB * pB[0];
         unsigned int d[16];
 #pragma unroll
@@ -247,8 +290,8 @@ __device__ __forceinline__ int fast_cell(const FwWarp& W, const FastWarpPlan::Le
         }
         const int sA = (int)(best & 0xffffu) - 257, sB = (int)(best >> 16) - 257;
         const bool cA = vA && sA >= th, cB = vB && sB >= th;
-        if (cA) W.score[(yA + 1) * scorePitch + xA + 1] = (unsigned char)sA;
-        if (cB) W.score[(yB + 1) * scorePitch + xB + 1] = (unsigned char)sB;
+        if (cA) W.scorePix[yA * SP + xA] = (unsigned char)sA;
+        if (cB) W.scorePix[yB * SP + xB] = (unsigned char)sB;
         // corners move to the front of the queue (never past the entries already read: nc <= q0 + 64)
         const unsigned int balA = __ballot_sync(FW_FULL, cA), balB = __ballot_sync(FW_FULL, cB);
         if (cA) W.queue[nc + __popc(balA & ltMask)] = (unsigned short)(eA & 0xfffu);
@@ -257,45 +300,72 @@ __device__ __forceinline__ int fast_cell(const FwWarp& W, const FastWarpPlan::Le
         nc += __popc(balB);
         __syncwarp();
     }
+    ncOut = nc;
+    FW_STAT(4, nq);
 
-    // ---- D: non-max suppression over the corners
-    int sn = 0;
+    // ---- D: non-max suppression over the corners; survivors become bits of the row bitmap
+    reinterpret_cast<uint4*>(W.bitmap)[lane] = make_uint4(0, 0, 0, 0);
+    __syncwarp();
 #pragma unroll 1
     for (int q0 = 0; q0 < nc; q0 += 32) {
         const bool v = q0 + lane < nc;
         const unsigned int e = v ? W.queue[q0 + lane] : 0u;
         const int x = e & 63, y = e >> 6;
-        const unsigned char* sc = W.score + (y + 1) * scorePitch + x + 1;
-        const int SP = scorePitch;
+        const unsigned char* sc = W.scorePix + y * SP + x;
+        const unsigned char* up = sc - SP;
+        const unsigned char* dn = sc + SP;
         const int s = sc[0];
-        const int m = max(max(max(sc[-SP - 1], sc[-SP]), max(sc[-SP + 1], sc[-1])), max(max(sc[1], sc[SP - 1]), max(sc[SP], sc[SP + 1])));
-        const bool keep = v && s > m;
-        const unsigned int bal = __ballot_sync(FW_FULL, keep);
-        if (keep) W.surv[sn + __popc(bal & ltMask)] = (unsigned short)e;
-        sn += __popc(bal);
+        const int m = max(max(max(up[-1], up[0]), max(up[1], sc[-1])), max(max(sc[1], dn[-1]), max(dn[0], dn[1])));
+        if (v && s > m) atomicOr(W.bitmap + 2 * y + (x >> 5), 1u << (x & 31));
     }
     __syncwarp();
-    return sn;
+    // survivors per row -> ranks of the rows' first survivors (row-major emission order), one packed warp scan
+    S.rowLo = reinterpret_cast<const uint2*>(W.bitmap)[lane];
+    S.rowHi = reinterpret_cast<const uint2*>(W.bitmap)[lane + 32];
+    const unsigned int cl = __popc(S.rowLo.x) + __popc(S.rowLo.y), chh = __popc(S.rowHi.x) + __popc(S.rowHi.y);
+    unsigned int incl = cl | (chh << 16);
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned int a = __shfl_up_sync(FW_FULL, incl, d);
+        if (lane >= d) incl += a;
+    }
+    const unsigned int tot = __shfl_sync(FW_FULL, incl, 31);
+    S.rankLo = (int)(incl & 0xffffu) - (int)cl;
+    S.rankHi = (int)(tot & 0xffffu) + (int)(incl >> 16) - (int)chh;
+    return (int)(tot & 0xffffu) + (int)(tot >> 16);
 }
 
 template <int BW>
-__global__ void __launch_bounds__(FW_WARPS * 32, 4) fast_warp_kernel(const __grid_constant__ ExtractParams P) {
+__global__ void __launch_bounds__(FW_WARPS * 32, 3) fast_warp_kernel(const __grid_constant__ ExtractParams P) {
     extern __shared__ __align__(128) unsigned char fsm[];
-    __shared__ unsigned short sLut[kMaxLevels][64];   // per level: mask bit -> px | row offset << 6 (second half: rows 8..15)
     const FastWarpPlan& F = P.fw;
+    // per level and unit: normalised mask bit -> x | y << 6 | polarity << 15 relative to the lane's first pixel of the chunk
+    unsigned short (*sLut)[4][32] = reinterpret_cast<unsigned short (*)[4][32]>(fsm);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned int ltMask = (1u << lane) - 1u;
-    unsigned char* wb = fsm + (size_t)warp * F.warpBytes;
+    unsigned char* wb = fsm + F.lutBytes + (size_t)warp * F.warpBytes;
     const unsigned int bar = smem_u32(wb);   // two mbarriers
+    const int SP = F.scorePitch;
     FwWarp W;
-    W.score = wb + F.offScore;
-    W.queue = reinterpret_cast<unsigned short*>(wb + F.offQueue);
-    W.surv = reinterpret_cast<unsigned short*>(wb + F.offSurv);
+    W.scorePix = wb + F.offScore + SP + 16;
+    W.bitmap = reinterpret_cast<unsigned int*>(wb + F.offBitmap);
+    unsigned short* const smemQueue = reinterpret_cast<unsigned short*>(wb + F.offQueue);
 
-    for (int t = threadIdx.x; t < 64 * P.nLevels; t += FW_WARPS * 32) {
-        const int k = t & 31, kk = (k - 9) & 31;
-        const int j = ((kk >> 1) & 7) + 8 * ((t >> 5) & 1), px = ((kk & 1) << 1) | (kk >> 4);
-        sLut[t >> 6][t & 63] = (unsigned short)(px | ((2 * F.lv[t >> 6].bands * (j >> 1) + (j & 1)) << 6));
+    for (int idx = threadIdx.x; idx < P.nLevels * 128; idx += FW_WARPS * 32) {
+        // after the rotation by 4u a unit's bits sit at 9 + kk: kk 0..3 bright pixels 0 / 2 of its steps 0, 1; 4..7 the same
+        // for dark; 16..19 and 20..23 pixels 1 / 3
+        const int level = idx >> 7, u = (idx >> 5) & 3, k = idx & 31, kk = (k - 9) & 31, hi = kk >> 4, low = kk & 15;
+        unsigned short v = 0;
+        if (low < 8) {
+            const int pol = low >> 2, st = (low >> 1) & 1, px = ((low & 1) << 1) | hi;
+            const int i = 2 * u + st, T = F.lv[level].T, dm = i / T, t = i - dm * T;
+            v = (unsigned short)((16 * t + px) | ((8 * dm) << 6) | (pol << 15));
+        }
+        sLut[level][u][k] = v;
+    }
+    {
+        uint4* z = reinterpret_cast<uint4*>(wb + F.offScore);
+        for (int i = lane; i < F.scoreVec; i += 32) z[i] = make_uint4(0, 0, 0, 0);
     }
     if (lane == 0) {
         mbar_init(bar, 1);
@@ -307,29 +377,40 @@ __global__ void __launch_bounds__(FW_WARPS * 32, 4) fast_warp_kernel(const __gri
 
     const unsigned int nCells = (unsigned int)P.nCellsTotal;
     const unsigned int total = (unsigned int)P.nFrames * nCells;
-    const unsigned int stride = gridDim.x * FW_WARPS;
-    unsigned int it = blockIdx.x * FW_WARPS + warp;
-    if (it >= total) return;
-    const unsigned int strideFrames = stride / nCells, strideCells = stride - strideFrames * nCells;
-    unsigned int frame = it / nCells, cell = it - frame * nCells;
+    const unsigned int warpId = blockIdx.x * FW_WARPS + warp;
+    W.globalQueue = F.scratch + (size_t)warpId * F.scratchCap;
+    W.globalCap = F.scratchCap;
     const unsigned char* maps = static_cast<const unsigned char*>(F.maps);
-
-    uint4 c0 = __ldg(reinterpret_cast<const uint4*>(P.cells + cell));
-    if (lane == 0) {
-        mbar_expect_tx(bar, (unsigned int)F.tileBytes);
-        tma_load_tile(smem_u32(wb + F.offTile), maps + 128 * (int)(short)(c0.x & 0xffffu),
-                      (kPadLeft + (int)(short)(c0.x >> 16) - 4) & ~15, kEdge + (int)(short)(c0.y & 0xffffu) - 3,
-                      F.frameBase + (int)frame, bar);
+    // cells are handed out one at a time (their cost varies 10x between a flat and a busy cell); the index of the cell
+    // after the current one is fetched, and its tile requested, before the current one is processed
+    unsigned int it = 0;
+    if (lane == 0) it = atomicAdd(F.counters, 1u);
+    it = __shfl_sync(FW_FULL, it, 0);
+    uint4 c0 = make_uint4(0, 0, 0, 0);
+    unsigned int frame = 0, cell = 0;
+    if (it < total) {
+        frame = it / nCells;
+        cell = it - frame * nCells;
+        c0 = __ldg(reinterpret_cast<const uint4*>(P.cells + cell));
+        if (lane == 0) {
+            mbar_expect_tx(bar, (unsigned int)F.tileBytes);
+            tma_load_tile(smem_u32(wb + F.offTile), maps + 128 * (int)(short)(c0.x & 0xffffu),
+                          (kPadLeft + (int)(short)(c0.x >> 16) - 4) & ~15, kEdge + (int)(short)(c0.y & 0xffffu) - 3,
+                          F.frameBase + (int)frame, bar);
+        }
     }
     unsigned int parity = 0;   // bit b: the phase of buffer b's barrier to wait for
     int buf = 0;
-    for (;;) {
+    while (it < total) {
         // ---- next item: its tile goes into the other buffer (all reads of that buffer ended with the previous cell)
-        unsigned int nFrame = frame + strideFrames, nCell = cell + strideCells;
-        if (nCell >= nCells) { nCell -= nCells; ++nFrame; }
-        const bool more = it + stride < total && it + stride > it;
+        unsigned int nIt = 0;
+        if (lane == 0) nIt = atomicAdd(F.counters, 1u);
+        nIt = __shfl_sync(FW_FULL, nIt, 0);
+        unsigned int nFrame = 0, nCell = 0;
         uint4 n0 = c0;
-        if (more) {
+        if (nIt < total) {
+            nFrame = nIt / nCells;
+            nCell = nIt - nFrame * nCells;
             n0 = __ldg(reinterpret_cast<const uint4*>(P.cells + nCell));
             if (lane == 0) {
                 const unsigned int nb = bar + 8u * (unsigned int)(buf ^ 1);
@@ -343,43 +424,72 @@ __global__ void __launch_bounds__(FW_WARPS * 32, 4) fast_warp_kernel(const __gri
         // ---- this cell
         const int cellX0 = (int)(short)(c0.x >> 16), cellY0 = (int)(short)(c0.y & 0xffffu);
         const int cw = (int)(c0.y >> 16), ch = (int)(c0.z & 0xffffu), cellSlot = (int)c0.w;
-        {
-            uint4* z = reinterpret_cast<uint4*>(W.score);
-#pragma unroll 1
-            for (int i = lane; i < F.scoreVec; i += 32) z[i] = make_uint4(0, 0, 0, 0);
-        }
-        __syncwarp();
         mbar_wait(bar + 8u * (unsigned int)buf, (parity >> buf) & 1u);
         parity ^= 1u << buf;
         W.tile = wb + F.offTile + buf * F.tileStride;
+        W.queue = smemQueue;
+        W.queueCap = F.queueCap;
 
         const int level = (int)(short)(c0.x & 0xffffu);
-        int sn, th = P.iniTh;
-        for (;;) {   // the second round is the reference's second cv::FAST call at minThFAST (:811-818)
-            sn = fast_cell<BW>(W, F.lv[level], F.scorePitch, sLut[level], cw, ch, (kPadLeft + cellX0 - 4) & 15, th, lane, ltMask);
+        FwSurvivors S;
+        int sn, nc, th = P.iniTh;
+        for (;;) {   // a second round at minThFAST is the reference's second cv::FAST call (:811-818)
+            sn = fast_cell<BW>(W, F.lv[level], sLut[level], SP, cw, ch, (kPadLeft + cellX0 - 4) & 15, th, lane, ltMask, nc, S);
+            FW_STAT(1, 1);
             if (sn != 0 || th <= P.minTh) break;
             th = P.minTh;
+            FW_STAT(2, 1);
         }
+        FW_STAT(0, 1);
+        FW_STAT(5, nc);
+        FW_STAT(6, sn);
 
-        // ---- survivors store themselves at their row-major rank = number of survivors with a smaller (y, x) key
+        // ---- every lane emits the survivors of its two pixel rows in x order, starting at the rows' ranks
         if (lane == 0) P.cellCount[(size_t)frame * P.nCellsTotal + cell] = sn;
         unsigned int* slot = P.slots + (size_t)frame * P.slotFrameEntries + cellSlot;
-#pragma unroll 1
-        for (int q = lane; q < sn; q += 32) {
-            const unsigned int e = W.surv[q];
-            const int x = e & 63, y = e >> 6;
-            int rank = 0;                                   // entries are x | y << 6: numeric order == (y, x) order
-            for (int j = 0; j < sn; ++j) rank += W.surv[j] < e;
-            const unsigned int s = W.score[(y + 1) * F.scorePitch + x + 1];
-            slot[rank] = ((unsigned int)(cellX0 + x - 16) << 20) | ((unsigned int)(cellY0 + y - 16) << 8) | s;
+        {
+            unsigned long long bits = (unsigned long long)S.rowLo.x | ((unsigned long long)S.rowLo.y << 32);
+            const unsigned int yKey = (unsigned int)(cellY0 + lane - 16) << 8;
+            const unsigned char* srow = W.scorePix + lane * SP;
+            unsigned int* o = slot + S.rankLo;
+            while (bits) {
+                const int x = __ffsll((long long)bits) - 1;
+                bits &= bits - 1;
+                *o++ = ((unsigned int)(cellX0 + x - 16) << 20) | yKey | srow[x];
+            }
+        }
+        if (ch > 32) {
+            unsigned long long bits = (unsigned long long)S.rowHi.x | ((unsigned long long)S.rowHi.y << 32);
+            const unsigned int yKey = (unsigned int)(cellY0 + lane + 32 - 16) << 8;
+            const unsigned char* srow = W.scorePix + (lane + 32) * SP;
+            unsigned int* o = slot + S.rankHi;
+            while (bits) {
+                const int x = __ffsll((long long)bits) - 1;
+                bits &= bits - 1;
+                *o++ = ((unsigned int)(cellX0 + x - 16) << 20) | yKey | srow[x];
+            }
         }
         __syncwarp();
-        if (!more) break;
-        it += stride;
+        // the score map goes back to zero by the corner list (a second round's corners include the first round's)
+#pragma unroll 1
+        for (int i = lane; i < nc; i += 32) {
+            const unsigned int e = W.queue[i];
+            W.scorePix[(int)(e >> 6) * SP + (int)(e & 63)] = 0;
+        }
+        __syncwarp();
+        it = nIt;
         frame = nFrame;
         cell = nCell;
         c0 = n0;
         buf ^= 1;
+    }
+    // the last warp out re-arms the counters for the next launch
+    if (lane == 0) {
+        __threadfence();
+        if (atomicAdd(F.counters + 1, 1u) == gridDim.x * FW_WARPS - 1) {
+            F.counters[0] = 0;
+            F.counters[1] = 0;
+        }
     }
 }
 
@@ -388,39 +498,34 @@ __global__ void __launch_bounds__(FW_WARPS * 32, 4) fast_warp_kernel(const __gri
 int fast_warp_plan(int nLevels, const int* cellW, const int* cellH, int slotCapMax, FastWarpPlan* plan) {
     FastWarpPlan f;
     std::memset(&f, 0, sizeof f);
-    int maxCellW = 1, maxCellH = 1, maxRows = 0;
+    int maxCellW = 1, maxCellH = 1, maxRows = 0, maxGroups = 1;
     for (int l = 0; l < nLevels; ++l) {
         FastWarpPlan::Level& L = f.lv[l];
         const int w = std::max(cellW[l], 1), h = std::max(cellH[l], 1);
         maxCellW = std::max(maxCellW, w);
         maxCellH = std::max(maxCellH, h);
-        L.groups = (unsigned short)((w + 3) / 4);
-        // bands x rows per item: as few warp passes and masked rows as possible (31x31 cells: 8 groups x 4 bands x 8 rows)
-        long long bestCost = -1;
-        for (int bands = 1; bands <= 32; ++bands) {
-            const int halfRows = (h + 2 * bands - 1) / (2 * bands);
-            if (halfRows > 8) continue;                   // two 32-bit masks hold 16 rows
-            if (2 * bands * halfRows > 64) continue;      // y < 64 in a queue entry
-            const int items = L.groups * bands, passes = (items + 31) / 32;
-            const long long cost = (long long)passes * (2 * halfRows * 10 + 12);
-            if (bestCost < 0 || cost < bestCost) { bestCost = cost; L.bands = (unsigned short)bands; L.halfRows = (unsigned short)halfRows; }
-        }
-        if (bestCost < 0) return fail(ORB_ERR_INVALID, "FAST: no work-item shape for %dx%d cells", w, h);
-        L.rcpGroups = (65536u + L.groups - 1) / L.groups;
-        L.rcpBandStep = (65536u + 2 * L.bands - 1) / (2 * L.bands);
-        maxRows = std::max(maxRows, 2 * L.bands * L.halfRows);
+        const int groups = (w + 3) / 4, T = std::max(2, (groups + 3) / 4), blocks = (h + 7) / 8;
+        if (T > 4 || blocks > 8) return fail(ORB_ERR_INVALID, "FAST: cell %dx%d is larger than 64x64", w, h);
+        L.T = (unsigned char)T;
+        L.chunkSteps = (unsigned char)(8 / T * T);
+        L.steps = (unsigned char)(T * blocks);
+        maxRows = std::max(maxRows, 8 * blocks);
+        maxGroups = std::max(maxGroups, 4 * T);
     }
     // box width: up to 15 bytes of misalignment + pixels -4 .. 4*groups+3 (+ the fourth word of the last group); 80 and
-    // 96 bytes are the pitches whose rows two apart do not share banks
-    f.bw = std::max(80, ((15 + 4 * ((maxCellW + 3) / 4) + 8) + 15) / 16 * 16);
+    // 96 bytes are the pitches whose rows fall into distinct bank octets (20 y mod 32 takes 8 values, 24 y takes 4)
+    f.bw = std::max(80, ((15 + 4 * maxGroups + 12) + 15) / 16 * 16);
+    if (f.bw > 96) return fail(ORB_ERR_INVALID, "FAST: tile pitch %d", f.bw);
     f.bh = maxCellH + 6;
     f.tileBytes = f.bw * f.bh;
     f.scorePitch = ((maxCellW + 2) + 3) / 4 * 4;
-    if (((f.scorePitch / 4) & 1) == 0) f.scorePitch += 4;     // odd word pitch: vertical neighbours in different banks
-    const int scoreBytes = ((maxCellH + 2) * f.scorePitch + 15) / 16 * 16;
+    if ((f.scorePitch / 4) % 2 == 0) f.scorePitch += 4;        // odd word pitch: the rows of a 3x3 neighbourhood in different banks
+    const int scoreBytes = ((maxCellH + 2) * f.scorePitch + 32 + 15) / 16 * 16;
     f.scoreVec = scoreBytes / 16;
-    f.queueCap = 2 * maxCellW * maxCellH;                      // a pixel can pass the pre-test with both polarities
-    f.survCap = slotCapMax;
+    f.lutBytes = nLevels * 256;
+    f.scratchCap = 2 * maxCellW * maxCellH + 64;               // a pixel can pass the pre-test with both polarities
+    f.queueCap = std::min(f.scratchCap, 640);                  // a typical 31x31 cell queues ~300
+    (void)slotCapMax;
     int p = 128;                                               // [0, 16): the two mbarriers
     f.offTile = p;
     f.tileStride = (f.tileBytes + 127) / 128 * 128;
@@ -429,15 +534,15 @@ int fast_warp_plan(int nLevels, const int* cellW, const int* cellH, int slotCapM
     p += scoreBytes;
     f.offQueue = p;
     p += (f.queueCap * 2 + 15) / 16 * 16;
-    f.offSurv = p;
-    p += (f.survCap * 2 + 15) / 16 * 16;
+    f.offBitmap = p;
+    p += 512;                                                  // 64 pixel rows x 64 bits
     // rows past a cell's last one are computed and masked: they read up to maxRows + 6 tile rows, which must stay inside
     // the warp's own region (buffer 0 overhangs into buffer 1, buffer 1 into the arrays behind it)
-    const int overhang = (maxRows + 6 - f.bh) * f.bw;
+    const int overhang = (maxRows + 6 - f.bh) * f.bw + 64;
     if (overhang > p - f.offScore) p = f.offScore + overhang;
     f.warpBytes = (p + 127) / 128 * 128;
-    f.smemBytes = FW_WARPS * f.warpBytes;
-    if (f.smemBytes > 227 * 1024)
+    f.smemBytes = f.lutBytes + FW_WARPS * f.warpBytes;
+    if (f.smemBytes > 220 * 1024)
         return fail(ORB_ERR_INVALID, "FAST: %d bytes of shared memory for %dx%d cells", f.smemBytes, maxCellW, maxCellH);
     *plan = f;
     return ORB_OK;
@@ -472,26 +577,56 @@ int fast_warp_encode_maps(const ExtractParams& P, int arenaFrames, void* hostMap
 }
 
 template <int BW>
-static int launch_fast_warp_bw(const ExtractParams& P, cudaStream_t st) {
-    static thread_local int ctasPerSm = 0, nSm = 0, smemSet = -1, devSet = -1;
+static int fast_warp_occupancy(const FastWarpPlan& f, int* nSm, int* ctasPerSm) {
+    static thread_local int cSm = 0, cCtas = 0, cSmem = -1, cDev = -1;
     int dev = 0;
     ORB_CUDA(cudaGetDevice(&dev));
-    if (smemSet != P.fw.smemBytes || devSet != dev) {
-        ORB_CUDA(cudaFuncSetAttribute(fast_warp_kernel<BW>, cudaFuncAttributeMaxDynamicSharedMemorySize, P.fw.smemBytes));
+    if (cSmem != f.smemBytes || cDev != dev) {
+        ORB_CUDA(cudaFuncSetAttribute(fast_warp_kernel<BW>, cudaFuncAttributeMaxDynamicSharedMemorySize, f.smemBytes));
         ORB_CUDA(cudaFuncSetAttribute(fast_warp_kernel<BW>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        ORB_CUDA(cudaDeviceGetAttribute(&nSm, cudaDevAttrMultiProcessorCount, dev));
-        ORB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSm, fast_warp_kernel<BW>, FW_WARPS * 32, P.fw.smemBytes));
-        if (ctasPerSm < 1) return fail(ORB_ERR_CUDA, "FAST kernel does not fit an SM (%d bytes of shared memory)", P.fw.smemBytes);
-        smemSet = P.fw.smemBytes;
-        devSet = dev;
+        ORB_CUDA(cudaDeviceGetAttribute(&cSm, cudaDevAttrMultiProcessorCount, dev));
+        ORB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cCtas, fast_warp_kernel<BW>, FW_WARPS * 32, f.smemBytes));
+        if (cCtas < 1) return fail(ORB_ERR_CUDA, "FAST kernel does not fit an SM (%d bytes of shared memory)", f.smemBytes);
+        cSmem = f.smemBytes;
+        cDev = dev;
     }
+    *nSm = cSm;
+    *ctasPerSm = cCtas;
+    return ORB_OK;
+}
+
+int fast_warp_max_warps(const FastWarpPlan& f, int* warps) {
+    int nSm = 0, ctas = 0;
+    if (f.bw == 80) ORB_CHECK(fast_warp_occupancy<80>(f, &nSm, &ctas));
+    else ORB_CHECK(fast_warp_occupancy<96>(f, &nSm, &ctas));
+    *warps = nSm * ctas * FW_WARPS;
+    return ORB_OK;
+}
+
+template <int BW>
+static int launch_fast_warp_bw(const ExtractParams& P, cudaStream_t st) {
+    int nSm = 0, ctasPerSm = 0;
+    ORB_CHECK(fast_warp_occupancy<BW>(P.fw, &nSm, &ctasPerSm));
     const long long total = (long long)P.nFrames * P.nCellsTotal;
     const long long want = (total + FW_WARPS - 1) / FW_WARPS;
     const int grid = (int)std::min<long long>(want, (long long)nSm * ctasPerSm);
+    if (grid * FW_WARPS > P.fw.maxWarps) return fail(ORB_ERR_CUDA, "FAST: scratch sized for %d warps, launch has %d", P.fw.maxWarps, grid * FW_WARPS);
     fast_warp_kernel<BW><<<grid, FW_WARPS * 32, P.fw.smemBytes, st>>>(P);
     ORB_CUDA(cudaGetLastError());
     return ORB_OK;
 }
+
+#ifdef ORBB_FW_STATS
+extern "C" int orbx_debug_fast_stats(unsigned long long* out8, int reset) {
+    ORB_CUDA(cudaDeviceSynchronize());
+    ORB_CUDA(cudaMemcpyFromSymbol(out8, gFwStats, sizeof gFwStats));
+    if (reset) {
+        unsigned long long z[8] = {0};
+        ORB_CUDA(cudaMemcpyToSymbol(gFwStats, z, sizeof z));
+    }
+    return ORB_OK;
+}
+#endif
 
 int launch_fast_warp(const ExtractParams& P, cudaStream_t st, int* launches) {
     if (P.nCellsTotal == 0) return ORB_OK;
