@@ -56,6 +56,25 @@ __device__ __forceinline__ unsigned h2add(unsigned a, unsigned b) {
 #define OP_MIX_HI(a, b, c) a = h2max(a, b); a = a * b + c;
 #define OP_MIX_HA(a, b, c) a = h2max(a, b); a = h2add(a, c);
 
+#define OP_R31(a, b, c) a = __vmaxu2(a, b); a = __vminu2(a, c); a = __vmaxu2(a, b); a = a * b + c;
+#define OP_R21(a, b, c) a = __vmaxu2(a, b); a = __vminu2(a, c); a = a * b + c;
+#define OP_R12(a, b, c) a = __vmaxu2(a, b); a = a * b + c; a = a * c + b;
+#define OP_R13(a, b, c) a = __vmaxu2(a, b); a = a * b + c; a = a * c + b; a = a * b + b;
+#define OP_LDSV(a, b, c) a = __vmaxu2(a, b); a = sm[(a & 1023)];
+#define OP_FADD(a, b, c) a = __float_as_uint(__uint_as_float(a) + __uint_as_float(b));
+#define OP_VF(a, b, c) a = __vmaxu2(a, b); a = __float_as_uint(__uint_as_float(a) + __uint_as_float(c));
+#define OP_VH(a, b, c) a = __vmaxu2(a, b); a = h2add(a, c);
+#define OP_PRMTI(a, b, c) a = __byte_perm(a, b, 0x5140); a = a * b + c;
+#define OP_LOPI(a, b, c) a = (a & b) ^ c; a = a * b + c;
+KERNEL(k_r31, OP_R31)
+KERNEL(k_r21, OP_R21)
+KERNEL(k_r12, OP_R12)
+KERNEL(k_r13, OP_R13)
+KERNEL(k_fadd, OP_FADD)
+KERNEL(k_vf, OP_VF)
+KERNEL(k_vh, OP_VH)
+KERNEL(k_prmti, OP_PRMTI)
+KERNEL(k_lopi, OP_LOPI)
 KERNEL(k_vmax, OP_VMAX)
 KERNEL(k_vmin3, OP_VMIN3)
 KERNEL(k_hmax, OP_HMAX)
@@ -128,17 +147,27 @@ int main() {
         {"VIMNMX + IMAD", k_mix_vi, 64}, {"VIMNMX3 + HMNMX2", k_mix_v3h, 64}, {"PRMT + HMNMX2", k_mix_ph, 64},
         {"VIMNMX + PRMT", k_mix_vp, 64}, {"HMNMX2 + IMAD", k_mix_hi, 64}, {"HMNMX2 + HADD2", k_mix_ha, 64},
         {"LDS.32 (conflict-free)", k_lds, 32}, {"SHFL", k_shfl, 32},
+        {"3 VIMNMX : 1 IMAD", k_r31, 128}, {"2 VIMNMX : 1 IMAD", k_r21, 96}, {"1 VIMNMX : 2 IMAD", k_r12, 96}, {"1 VIMNMX : 3 IMAD", k_r13, 128},
+        {"FADD", k_fadd, 32}, {"VIMNMX + FADD", k_vf, 64}, {"VIMNMX + HADD2", k_vh, 64}, {"PRMT + IMAD", k_prmti, 64}, {"LOP3 + IMAD", k_lopi, 64},
     };
     for (auto& t : tests) {
-        for (int rep = 0; rep < 2; ++rep) t.k<<<blocks, threads>>>(out, 0x01000100u, 0x00030005u, cyc);
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        t.k<<<blocks, threads>>>(out, 0x01000100u, 0x00030005u, cyc);
+        cudaEventRecord(e0);
+        t.k<<<blocks, threads>>>(out, 0x01000100u, 0x00030005u, cyc);
+        cudaEventRecord(e1);
         cudaDeviceSynchronize();
+        float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
         cudaMemcpy(h, cyc, blocks * 8, cudaMemcpyDeviceToHost);
         double avg = 0;
         for (int i = 0; i < blocks; ++i) avg += (double)h[i];
         avg /= blocks;
         // 8 CTAs of 8 warps per SM resident = 64 warps; each executes ITER * perIter instructions in `avg` cycles
         const double perSm = 64.0 * ITER * t.perIter / avg;
-        printf("%-26s %6.2f warp-instr/clk/SM  (%.0f cycles per CTA)\n", t.name, perSm, avg);
+        // wall-clock rate: all 148 SMs, 64 warps each
+        const double perSmWall = 64.0 * ITER * t.perIter / (ms * 1e-3 * 1.965e9);
+        printf("%-26s %6.2f warp-instr/clk/SM by clock64 (%.0f cycles per CTA), %6.2f by wall clock at 1.965 GHz (%.3f ms)\n", t.name, perSm, avg, perSmWall, ms);
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { printf("CUDA error: %s\n", cudaGetErrorString(e)); return 1; }

@@ -84,6 +84,8 @@ struct FastWarpPlan {
     unsigned short* scratch; // global-memory queues for cells with more candidates than queueCap (one per resident warp)
     int scratchCap;          // entries per warp: 2 per pixel of the largest cell
     int maxWarps;            // warps the scratch was sized for
+    unsigned int one;        // = 1, opaque to the compiler: adds written as IMAD x, one, y go to the FMA pipe instead of the
+                             // (binding) ALU pipe, which takes one warp instruction every other clock (profiles/r02_microbench_pipes.txt)
     // pre-test schedule of a level's cells: a step is one pixel row of 4 adjacent 4-px groups per 8 rows (lane = row r
     // of 8, group q of 4); T steps cover the width, chunks of `chunkSteps` (a multiple of T, <= 8) fill one 32-bit mask
     struct Level { unsigned char T, chunkSteps, steps, pad; } lv[kMaxLevels];

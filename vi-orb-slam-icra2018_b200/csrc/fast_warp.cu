@@ -57,7 +57,7 @@ __device__ unsigned long long gFwStats[8];   // cells, rounds, second rounds, ov
 #define FW_STAT(i, v) do { } while (0)
 #endif
 
-constexpr int FW_WARPS = 7;                       // warps per CTA; they share nothing but the bit -> pixel tables
+constexpr int FW_WARPS = 8;                       // warps per CTA; they share nothing but the bit -> pixel tables
 constexpr unsigned int FW_FULL = 0xffffffffu;
 constexpr unsigned int FW_PASS = 0x02000200u;     // bit 9 of each 16-bit half
 
@@ -100,7 +100,14 @@ __device__ __forceinline__ void tma_load_tile(unsigned int dst, const void* map,
 struct FwAlign {
     unsigned int selC, selL, selR;
     bool hiR;
+    unsigned int one, neg;   // 1 and -1 the compiler cannot see through (adds as IMAD on the FMA pipe)
 };
+// a * m + b on the FMA pipe (IMAD); m is a runtime +-1 or power of two
+__device__ __forceinline__ unsigned int fma_u32(unsigned int a, unsigned int m, unsigned int b) {
+    unsigned int r;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(m), "r"(b));
+    return r;
+}
 template <int BW>
 __device__ __forceinline__ void pretest_row(const unsigned char* r, const FwAlign& al, unsigned int K, unsigned int vA, unsigned int vB,
                                             unsigned int& bright, unsigned int& dark) {
@@ -120,10 +127,13 @@ __device__ __forceinline__ void pretest_row(const unsigned char* r, const FwAlig
     const unsigned int rA = __byte_perm(FR, 0, 0x4140), rB = __byte_perm(FR, 0, 0x4342);
     const unsigned int mmA = __vminu2(__vmaxu2(uA, dA), __vmaxu2(lA, rA)), mmB = __vminu2(__vmaxu2(uB, dB), __vmaxu2(lB, rB));
     const unsigned int nnA = __vmaxu2(__vminu2(uA, dA), __vminu2(lA, rA)), nnB = __vmaxu2(__vminu2(uB, dB), __vminu2(lB, rB));
-    const unsigned int bA = (mmA - cA + K) & vA, bB = (mmB - cB + K) & vB;
-    const unsigned int kA = (cA - nnA + K) & vA, kB = (cB - nnB + K) & vB;
-    bright = bA + 2u * bB;
-    dark = kA + 2u * kB;
+    // bit 9 / 25 of (mm - c + K) and of (c - nn + K); pair B's bits move one up; the adds run as IMADs (FMA pipe)
+    const unsigned int kmA = fma_u32(cA, al.neg, K), kmB = fma_u32(cB, al.neg, K);     // K - c
+    const unsigned int kpA = fma_u32(cA, al.one, K), kpB = fma_u32(cB, al.one, K);     // K + c
+    const unsigned int bA = fma_u32(mmA, al.one, kmA), bB = fma_u32(mmB, al.one, kmB);
+    const unsigned int kA = fma_u32(nnA, al.neg, kpA), kB = fma_u32(nnB, al.neg, kpB);
+    bright = fma_u32(bB & vB, al.one + al.one, bA & vA);
+    dark = fma_u32(kB & vB, al.one + al.one, kA & vA);
 }
 
 // FW_PASS restricted to the first n (of 4) pixels of a group: pair A = pixels 0, 1 (bits 9, 25), pair B = pixels 2, 3
@@ -155,32 +165,29 @@ struct FwSurvivors {       // a lane's view of the survivor bitmap: pixel rows `
     int rankLo, rankHi;    // survivors in the rows before them
 };
 
-// B: the set bits of one chunk's masks become queue entries (x | y << 6 | polarity << 15).  A "unit" is a pair of steps
-// (one 8-row block when T = 2); the four units' per-lane counts are prefix-summed over the warp in two packed shuffle
-// scans.  Returns the new queue length, or -1 (nothing written) if the chunk does not fit.
+// B: the set bits of one chunk's masks become queue entries (x | y << 6 | polarity << 15).  A "unit" is a group of four
+// steps (two 8-row blocks when T = 2); the two units' per-lane counts are prefix-summed over the warp in one packed
+// shuffle scan.  Returns the new queue length, or -1 (nothing written) if the chunk does not fit.
 __device__ __forceinline__ int enqueue_chunk(unsigned int mb, unsigned int md, unsigned int laneEntry, const unsigned short (*lut)[32],
                                              unsigned short* queue, int nq, int cap, int lane) {
-    constexpr unsigned int U0 = 0x1E001E00u, U1 = 0xE001E001u, U2 = 0x001E001Eu, U3 = 0x01E001E0u;   // U0 rotated by 4u
+    constexpr unsigned int U0 = 0xFE01FE01u, U1 = 0x01FE01FEu;   // steps 0-3: bits 9..16, 25..31, 0; steps 4-7: the rest
     const unsigned int c0 = __popc(mb & U0) + __popc(md & U0), c1 = __popc(mb & U1) + __popc(md & U1);
-    const unsigned int c2 = __popc(mb & U2) + __popc(md & U2), c3 = __popc(mb & U3) + __popc(md & U3);
-    unsigned int s01 = c0 | (c1 << 16), s23 = c2 | (c3 << 16);
+    unsigned int s01 = c0 | (c1 << 16);
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-        const unsigned int a = __shfl_up_sync(FW_FULL, s01, d), b = __shfl_up_sync(FW_FULL, s23, d);
-        if (lane >= d) { s01 += a; s23 += b; }
+        const unsigned int a = __shfl_up_sync(FW_FULL, s01, d);
+        if (lane >= d) s01 += a;
     }
-    const unsigned int t01 = __shfl_sync(FW_FULL, s01, 31), t23 = __shfl_sync(FW_FULL, s23, 31);
-    const int base1 = nq + (int)(t01 & 0xffffu), base2 = base1 + (int)(t01 >> 16), base3 = base2 + (int)(t23 & 0xffffu);
-    const int nqNew = base3 + (int)(t23 >> 16);
+    const unsigned int t01 = __shfl_sync(FW_FULL, s01, 31);
+    const int base1 = nq + (int)(t01 & 0xffffu), nqNew = base1 + (int)(t01 >> 16);
     if (nqNew > cap) return -1;
-    const int pos[4] = {nq + (int)(s01 & 0xffffu) - (int)c0, base1 + (int)(s01 >> 16) - (int)c1, base2 + (int)(s23 & 0xffffu) - (int)c2,
-                        base3 + (int)(s23 >> 16) - (int)c3};
-    const unsigned int um[4] = {U0, U1, U2, U3};
+    const int pos[2] = {nq + (int)(s01 & 0xffffu) - (int)c0, base1 + (int)(s01 >> 16) - (int)c1};
+    const unsigned int um[2] = {U0, U1};
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-        // bright bits stay, dark bits move 4 up (into the next unit's positions, which are masked out here)
-        unsigned int c = (mb & um[u]) | __funnelshift_l(md & um[u], md & um[u], 4);
-        c = __funnelshift_r(c, c, 4 * u);
+    for (int u = 0; u < 2; ++u) {
+        // bright bits stay, dark bits move 8 up (into the other unit's positions, which are masked out here)
+        unsigned int c = (mb & um[u]) | __funnelshift_l(md & um[u], md & um[u], 8);
+        c = __funnelshift_r(c, c, 8 * u);
         unsigned short* w = queue + pos[u];
         const unsigned short* l = lut[u];
         while (c) {
@@ -192,12 +199,12 @@ __device__ __forceinline__ int enqueue_chunk(unsigned int mb, unsigned int md, u
     return nqNew;
 }
 
-// A-D for one cell at threshold th; returns the number of NMS survivors (bits of W.bitmap, S = this lane's rows of
-// it); nc = corners (W.queue[0, nc)).  A cell with more candidates than the shared-memory queue holds moves its queue
-// to the warp's global scratch.
+// A-C for one cell at threshold th: everything that reads the tile.  Returns the number of corners (W.queue[0, nc),
+// scores in the score map).  A cell with more candidates than the shared-memory queue holds moves its queue to the
+// warp's global scratch.
 template <int BW>
-__device__ __forceinline__ int fast_cell(FwWarp& W, const FastWarpPlan::Level& F, const unsigned short (*lut)[32], int SP, int cw, int ch,
-                                         int mis, int th, int lane, unsigned int ltMask, int& ncOut, FwSurvivors& S) {
+__device__ __forceinline__ int fast_front(FwWarp& W, const FastWarpPlan::Level& F, const unsigned short (*lut)[32], int SP, int cw, int ch,
+                                          int mis, int th, int lane, unsigned int ltMask, unsigned int one) {
     // ---- A + B
     const unsigned int K = FW_PASS - (unsigned int)(th + 1) * 0x00010001u;
     FwAlign al;
@@ -207,13 +214,14 @@ __device__ __forceinline__ int fast_cell(FwWarp& W, const FastWarpPlan::Level& F
         al.selL = al.selC + 0x1111u;
         al.hiR = sh >= 2u;
         al.selR = 0x3210u + 0x1111u * (al.hiR ? sh - 1u : sh + 3u);
+        al.one = one;
+        al.neg = 0u - one;
     }
     const int r = lane >> 2, q = lane & 3;
     const unsigned char* tilePix = W.tile + mis + 3 * BW + 4;              // pixel (0, 0)
     const unsigned char* rowPtr = W.tile + (mis & ~3) + (r + 3) * BW + 4 * q;   // aligned word of pixel (4q - 4, r)
     const int T = F.T, chunkSteps = F.chunkSteps, steps = F.steps;
     const int chunkRows = 8 * (chunkSteps / T);
-    ncOut = 0;
     int nq = 0;
 #pragma unroll 1
     for (int j0 = 0, y0 = r; j0 < steps; j0 += chunkSteps, y0 += chunkRows, rowPtr += chunkRows * BW) {
@@ -300,10 +308,13 @@ __device__ __forceinline__ int fast_cell(FwWarp& W, const FastWarpPlan::Level& F
         nc += __popc(balB);
         __syncwarp();
     }
-    ncOut = nc;
     FW_STAT(4, nq);
+    return nc;
+}
 
-    // ---- D: non-max suppression over the corners; survivors become bits of the row bitmap
+// D for one cell: non-max suppression over the corners; survivors become bits of the row bitmap.  Returns their number;
+// S = this lane's rows of the bitmap and the ranks of the rows' first survivors.
+__device__ __forceinline__ int fast_back(const FwWarp& W, int SP, int nc, int lane, FwSurvivors& S) {
     reinterpret_cast<uint4*>(W.bitmap)[lane] = make_uint4(0, 0, 0, 0);
     __syncwarp();
 #pragma unroll 1
@@ -340,28 +351,26 @@ __global__ void __launch_bounds__(FW_WARPS * 32, 3) fast_warp_kernel(const __gri
     extern __shared__ __align__(128) unsigned char fsm[];
     const FastWarpPlan& F = P.fw;
     // per level and unit: normalised mask bit -> x | y << 6 | polarity << 15 relative to the lane's first pixel of the chunk
-    unsigned short (*sLut)[4][32] = reinterpret_cast<unsigned short (*)[4][32]>(fsm);
+    unsigned short (*sLut)[2][32] = reinterpret_cast<unsigned short (*)[2][32]>(fsm);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned int ltMask = (1u << lane) - 1u;
     unsigned char* wb = fsm + F.lutBytes + (size_t)warp * F.warpBytes;
-    const unsigned int bar = smem_u32(wb);   // two mbarriers
+    const unsigned int bar = smem_u32(wb);              // the tile's mbarrier
+    const unsigned int tileAddr = smem_u32(wb + F.offTile);
     const int SP = F.scorePitch;
     FwWarp W;
+    W.tile = wb + F.offTile;
     W.scorePix = wb + F.offScore + SP + 16;
     W.bitmap = reinterpret_cast<unsigned int*>(wb + F.offBitmap);
     unsigned short* const smemQueue = reinterpret_cast<unsigned short*>(wb + F.offQueue);
 
-    for (int idx = threadIdx.x; idx < P.nLevels * 128; idx += FW_WARPS * 32) {
-        // after the rotation by 4u a unit's bits sit at 9 + kk: kk 0..3 bright pixels 0 / 2 of its steps 0, 1; 4..7 the same
-        // for dark; 16..19 and 20..23 pixels 1 / 3
-        const int level = idx >> 7, u = (idx >> 5) & 3, k = idx & 31, kk = (k - 9) & 31, hi = kk >> 4, low = kk & 15;
-        unsigned short v = 0;
-        if (low < 8) {
-            const int pol = low >> 2, st = (low >> 1) & 1, px = ((low & 1) << 1) | hi;
-            const int i = 2 * u + st, T = F.lv[level].T, dm = i / T, t = i - dm * T;
-            v = (unsigned short)((16 * t + px) | ((8 * dm) << 6) | (pol << 15));
-        }
-        sLut[level][u][k] = v;
+    for (int idx = threadIdx.x; idx < P.nLevels * 64; idx += FW_WARPS * 32) {
+        // after the rotation by 8u a unit's bits sit at 9 + kk: kk = 2 * step + (0: pixel 0, 1: pixel 2), + 16 for pixels 1 / 3,
+        // + 8 for the dark polarity
+        const int level = idx >> 6, u = (idx >> 5) & 1, k = idx & 31, kk = (k - 9) & 31;
+        const int pol = (kk >> 3) & 1, st = (kk & 7) >> 1, px = ((kk & 1) << 1) | (kk >> 4);
+        const int i = 4 * u + st, T = F.lv[level].T, dm = i / T, t = i - dm * T;
+        sLut[level][u][k] = (unsigned short)((16 * t + px) | ((8 * dm) << 6) | (pol << 15));
     }
     {
         uint4* z = reinterpret_cast<uint4*>(wb + F.offScore);
@@ -369,7 +378,6 @@ __global__ void __launch_bounds__(FW_WARPS * 32, 3) fast_warp_kernel(const __gri
     }
     if (lane == 0) {
         mbar_init(bar, 1);
-        mbar_init(bar + 8, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -381,8 +389,17 @@ __global__ void __launch_bounds__(FW_WARPS * 32, 3) fast_warp_kernel(const __gri
     W.globalQueue = F.scratch + (size_t)warpId * F.scratchCap;
     W.globalCap = F.scratchCap;
     const unsigned char* maps = static_cast<const unsigned char*>(F.maps);
-    // cells are handed out one at a time (their cost varies 10x between a flat and a busy cell); the index of the cell
-    // after the current one is fetched, and its tile requested, before the current one is processed
+    // one tile buffer per warp: the load of a cell's tile is issued by lane 0 as soon as the previous cell has read its
+    // tile for the last time (end of its last scoring pass), so it overlaps that cell's NMS / emission / clean-up
+    auto request_tile = [&](const uint4& c, unsigned int frame) {
+        if (lane == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(bar, (unsigned int)F.tileBytes);
+            tma_load_tile(tileAddr, maps + 128 * (int)(short)(c.x & 0xffffu), (kPadLeft + (int)(short)(c.x >> 16) - 4) & ~15,
+                          kEdge + (int)(short)(c.y & 0xffffu) - 3, F.frameBase + (int)frame, bar);
+        }
+    };
+    // cells are handed out one at a time (their cost varies 10x between a flat and a busy cell)
     unsigned int it = 0;
     if (lane == 0) it = atomicAdd(F.counters, 1u);
     it = __shfl_sync(FW_FULL, it, 0);
@@ -392,53 +409,59 @@ __global__ void __launch_bounds__(FW_WARPS * 32, 3) fast_warp_kernel(const __gri
         frame = it / nCells;
         cell = it - frame * nCells;
         c0 = __ldg(reinterpret_cast<const uint4*>(P.cells + cell));
-        if (lane == 0) {
-            mbar_expect_tx(bar, (unsigned int)F.tileBytes);
-            tma_load_tile(smem_u32(wb + F.offTile), maps + 128 * (int)(short)(c0.x & 0xffffu),
-                          (kPadLeft + (int)(short)(c0.x >> 16) - 4) & ~15, kEdge + (int)(short)(c0.y & 0xffffu) - 3,
-                          F.frameBase + (int)frame, bar);
-        }
+        request_tile(c0, frame);
     }
-    unsigned int parity = 0;   // bit b: the phase of buffer b's barrier to wait for
-    int buf = 0;
+    unsigned int parity = 0;
     while (it < total) {
-        // ---- next item: its tile goes into the other buffer (all reads of that buffer ended with the previous cell)
+        // ---- ticket of the next cell: asked for now, looked at after this cell's first scoring pass
         unsigned int nIt = 0;
         if (lane == 0) nIt = atomicAdd(F.counters, 1u);
-        nIt = __shfl_sync(FW_FULL, nIt, 0);
-        unsigned int nFrame = 0, nCell = 0;
-        uint4 n0 = c0;
-        if (nIt < total) {
-            nFrame = nIt / nCells;
-            nCell = nIt - nFrame * nCells;
-            n0 = __ldg(reinterpret_cast<const uint4*>(P.cells + nCell));
-            if (lane == 0) {
-                const unsigned int nb = bar + 8u * (unsigned int)(buf ^ 1);
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                mbar_expect_tx(nb, (unsigned int)F.tileBytes);
-                tma_load_tile(smem_u32(wb + F.offTile + (buf ^ 1) * F.tileStride), maps + 128 * (int)(short)(n0.x & 0xffffu),
-                              (kPadLeft + (int)(short)(n0.x >> 16) - 4) & ~15, kEdge + (int)(short)(n0.y & 0xffffu) - 3,
-                              F.frameBase + (int)nFrame, nb);
-            }
-        }
         // ---- this cell
         const int cellX0 = (int)(short)(c0.x >> 16), cellY0 = (int)(short)(c0.y & 0xffffu);
         const int cw = (int)(c0.y >> 16), ch = (int)(c0.z & 0xffffu), cellSlot = (int)c0.w;
-        mbar_wait(bar + 8u * (unsigned int)buf, (parity >> buf) & 1u);
-        parity ^= 1u << buf;
-        W.tile = wb + F.offTile + buf * F.tileStride;
+        const int level = (int)(short)(c0.x & 0xffffu), mis = (kPadLeft + cellX0 - 4) & 15;
+        mbar_wait(bar, parity);
+        parity ^= 1u;
         W.queue = smemQueue;
         W.queueCap = F.queueCap;
 
-        const int level = (int)(short)(c0.x & 0xffffu);
         FwSurvivors S;
+        unsigned int nFrame = 0, nCell = 0;
+        uint4 n0 = c0;
+        bool nextKnown = false, nextRequested = false;
         int sn, nc, th = P.iniTh;
         for (;;) {   // a second round at minThFAST is the reference's second cv::FAST call (:811-818)
-            sn = fast_cell<BW>(W, F.lv[level], sLut[level], SP, cw, ch, (kPadLeft + cellX0 - 4) & 15, th, lane, ltMask, nc, S);
+            nc = fast_front<BW>(W, F.lv[level], sLut[level], SP, cw, ch, mis, th, lane, ltMask, F.one);
             FW_STAT(1, 1);
-            if (sn != 0 || th <= P.minTh) break;
+            if (!nextKnown) {
+                nIt = __shfl_sync(FW_FULL, nIt, 0);
+                if (nIt < total) {
+                    nFrame = nIt / nCells;
+                    nCell = nIt - nFrame * nCells;
+                    n0 = __ldg(reinterpret_cast<const uint4*>(P.cells + nCell));
+                }
+                nextKnown = true;
+            }
+            const bool lastRound = th <= P.minTh;
+            // the tile is dead unless a second round follows, which needs nc == 0 or (rarely) every corner losing its NMS
+            if (nIt < total && !nextRequested && (lastRound || nc > 0)) {
+                __syncwarp();
+                request_tile(n0, nFrame);
+                nextRequested = true;
+            }
+            sn = fast_back(W, SP, nc, lane, S);
+            if (sn != 0 || lastRound) break;
             th = P.minTh;
             FW_STAT(2, 1);
+            if (nextRequested) {   // the next cell's tile is on its way into the buffer: let it land, then fetch this cell's again
+                mbar_wait(bar, parity);
+                parity ^= 1u;
+                __syncwarp();
+                request_tile(c0, frame);
+                mbar_wait(bar, parity);
+                parity ^= 1u;
+                nextRequested = false;
+            }
         }
         FW_STAT(0, 1);
         FW_STAT(5, nc);
@@ -481,7 +504,6 @@ __global__ void __launch_bounds__(FW_WARPS * 32, 3) fast_warp_kernel(const __gri
         frame = nFrame;
         cell = nCell;
         c0 = n0;
-        buf ^= 1;
     }
     // the last warp out re-arms the counters for the next launch
     if (lane == 0) {
@@ -522,14 +544,15 @@ int fast_warp_plan(int nLevels, const int* cellW, const int* cellH, int slotCapM
     if ((f.scorePitch / 4) % 2 == 0) f.scorePitch += 4;        // odd word pitch: the rows of a 3x3 neighbourhood in different banks
     const int scoreBytes = ((maxCellH + 2) * f.scorePitch + 32 + 15) / 16 * 16;
     f.scoreVec = scoreBytes / 16;
-    f.lutBytes = nLevels * 256;
+    f.lutBytes = nLevels * 128;
+    f.one = 1u;
     f.scratchCap = 2 * maxCellW * maxCellH + 64;               // a pixel can pass the pre-test with both polarities
     f.queueCap = std::min(f.scratchCap, 640);                  // a typical 31x31 cell queues ~300
     (void)slotCapMax;
-    int p = 128;                                               // [0, 16): the two mbarriers
+    int p = 128;                                               // [0, 8): the tile's mbarrier
     f.offTile = p;
     f.tileStride = (f.tileBytes + 127) / 128 * 128;
-    p += 2 * f.tileStride;
+    p += f.tileStride;
     f.offScore = p;
     p += scoreBytes;
     f.offQueue = p;
@@ -537,7 +560,7 @@ int fast_warp_plan(int nLevels, const int* cellW, const int* cellH, int slotCapM
     f.offBitmap = p;
     p += 512;                                                  // 64 pixel rows x 64 bits
     // rows past a cell's last one are computed and masked: they read up to maxRows + 6 tile rows, which must stay inside
-    // the warp's own region (buffer 0 overhangs into buffer 1, buffer 1 into the arrays behind it)
+    // the warp's own region (the tile buffer overhangs into the arrays behind it)
     const int overhang = (maxRows + 6 - f.bh) * f.bw + 64;
     if (overhang > p - f.offScore) p = f.offScore + overhang;
     f.warpBytes = (p + 127) / 128 * 128;
