@@ -1,10 +1,11 @@
-set -x
 cd "${GRAFT_REPO_ROOT:-.}"
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -c 600 gpurun_out/bench.err; python - <<'PY'
-import json
-d=json.loads(open('gpurun_out/bench.json').read().strip().split('\n')[-1])
-print('value %.0f e2e %.0f ms/step %.2f'%(d['value'],d['e2e']['value'],d['ms_per_step']))
-print(d['kernels_ms_per_step']); print(d['clocks']); print(d['roofline']); print(d.get('latency_ms')); print(d.get('cpu_baseline')); print(d['hamming']['value'], d['hamming']['roofline']['frac'])
-PY
+{
+timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -15
+timeout 300 python __graft_entry__.py --smoke 2>&1 | tail -2
+for tool in memcheck racecheck; do
+  timeout 900 compute-sanitizer --tool $tool --print-limit 5 python tools/sanitize_case.py > gpurun_out/sanitize_$tool.log 2>&1
+  echo "== $tool exit $?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|^ok|Error|hazard" gpurun_out/sanitize_$tool.log | head -8
+done
+} > gpurun_out/full.log 2>&1
+tail -40 gpurun_out/full.log

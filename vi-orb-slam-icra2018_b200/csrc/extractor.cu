@@ -1,7 +1,7 @@
 // Extractor handle: constructor tables, per-image-size geometry, device arena, launch sequencing, C-ABI entry points.
 //   ORBextractor::ORBextractor   ORBextractor.cc:412-472     (scale tables, features per level, umax)
 //   ORBextractor::operator()     ORBextractor.cc:1045-1126   (pyramid -> keypoints -> blur + descriptors)
-// Everything per pixel / per keypoint runs in the kernels of pyramid.cu, fast.cu, octree.cu, blur.cu, brief.cu; the
+// Everything per pixel / per keypoint runs in the kernels of pyramid.cu, fast_warp.cu, octree.cu, blur.cu, brief.cu; the
 // host code here only derives sizes and tables (the same float expressions as the reference, compiled without FMA
 // contraction) and enqueues 12 launches per batch on one stream.
 #include <cmath>
@@ -119,7 +119,7 @@ int configure(orbx_extractor* e, int w, int h, int nFrames) {
                 c.cw = (short)std::min(wCell, (L.w - kEdge) - c.x0);
                 c.ch = (short)std::min(hCell, (L.h - kEdge) - c.y0);
                 if (c.cw <= 0 || c.ch <= 0) continue;   // the reference skips it or FAST sees a ROI thinner than 7 px
-                fast_cell_setup(c, L.pyrOff, L.pitch);
+                c.pad = 0;
                 c.slot = (int)slotOff;
                 slotOff += L.slotCap;
                 cells.push_back(c);
@@ -185,7 +185,6 @@ int configure(orbx_extractor* e, int w, int h, int nFrames) {
     P.maxCellW = 1;
     P.maxCellH = 1;
     for (const Cell& c : cells) { P.maxCellW = std::max(P.maxCellW, (int)c.cw); P.maxCellH = std::max(P.maxCellH, (int)c.ch); }
-    P.fast = fast_layout(P.maxCellW, P.maxCellH);
     {
         int cellW[kMaxLevels] = {0}, cellH[kMaxLevels] = {0}, slotCapMax = 1;
         for (const Cell& c : cells) {
@@ -270,9 +269,7 @@ int enqueue(orbx_extractor* e, const uint8_t* dImages, int nFrames, int w, int h
     ORB_CHECK(launch_pyramid(P, dImages, w, h, stride, frameStride, st, &e->launches));
     if (timed) ORB_CUDA(cudaEventRecord(e->ev[1], st));
     if (pe) ORB_CUDA(cudaEventRecord(pe[1], st));
-    static const bool fastV1 = getenv("ORBB_FAST_V1") != nullptr;   // round-1 CTA-per-cell kernel, kept for A/B timing
-    if (fastV1) ORB_CHECK(launch_fast(P, st, &e->launches));
-    else ORB_CHECK(launch_fast_warp(P, st, &e->launches));
+    ORB_CHECK(launch_fast_warp(P, st, &e->launches));
     if (pe) ORB_CUDA(cudaEventRecord(pe[2], st));
     ORB_CHECK(launch_octree(P, e->otSmem, e->otKeyCap, e->otNodeCap, e->otCellCap, st, &e->launches));
     if (timed) ORB_CUDA(cudaEventRecord(e->ev[2], st));

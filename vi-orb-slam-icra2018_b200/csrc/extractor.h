@@ -41,34 +41,18 @@ struct LevelGeom {
     float patchSize;     // (float)(int)(31*scale)
 };
 
-struct alignas(16) Cell {    // one FAST cell with a non-empty interior; 32 bytes = two 128-bit loads
+struct alignas(16) Cell {    // one FAST cell with a non-empty interior; 16 bytes = one 128-bit load
     short level;
     short x0, y0;        // interior origin in level coordinates (first pixel that can be a keypoint)
     short cw, ch;        // interior size
-    unsigned short pitch;    // padded row pitch of the level (bytes)
+    short pad;
     int slot;            // entry offset of its slot inside one frame's slot block
-    // precomputed for the FAST kernel so that its prologue has no divisions and no level-table reads
-    int tileOff;         // byte offset inside one frame's pyramid block of the aligned word that holds pixel (x0-4, y0-3)
-    unsigned char shift8;    // funnel shift (bits) that brings that pixel to byte 0
-    unsigned char quads;     // 4-pixel groups per staged tile row, ceil((cw+8)/4)
-    unsigned char rowsStage; // tile rows staged per pass of the CTA = threads / quads
-    unsigned char groups;    // 4-pixel groups per interior row, ceil(cw/4)
-    unsigned char pad, pad1;
-    unsigned short rq;       // ceil(2^15 / quads):  t / quads == (t * rq) >> 15 for t < threads
-    unsigned int rci;        // ceil(2^20 / n), n = 2 * ceil(ch / 2) items per pair of group columns: i / n == (i * rci) >> 20
 };
-static_assert(sizeof(Cell) == 32, "Cell is read as two uint4");
-
-struct FastLayout {      // byte offsets inside the FAST kernel's dynamic shared memory (host-computed, see fast.cu)
-    int tile, score, queue, alive, total;
-    int zeroVec;         // uint4 count of [score, queue): the score map starts as zero
-    int qCap;            // queue capacity in entries
-};
+static_assert(sizeof(Cell) == 16, "Cell is read as one uint4");
 
 // Plan of the warp-per-cell FAST kernel (fast_warp.cu), host-computed per image size.  Every warp owns one region of
-// the CTA's dynamic shared memory: two mbarriers, two TMA tile buffers (double-buffered byte tiles of bw x bh), the score
-// map (same pitch as the tile, so one offset addresses both), the candidate queue (compacted in place into the corner
-// list) and the NMS survivor list.
+// the CTA's dynamic shared memory: the tile's mbarrier, the TMA tile buffer (byte tile of bw x bh), the score map with
+// its zero ring, the candidate queue (compacted in place into the corner list) and the NMS survivor bitmap.
 struct FastWarpPlan {
     int bw, bh;              // TMA box: bytes per tile row (80 / 96) and rows (largest cell + 6)
     int tileBytes;           // bw * bh = bytes one TMA load delivers
@@ -103,7 +87,6 @@ struct ExtractParams {
     int selPerFrame;         // entries
     int outCapacity;         // caller's per-frame output capacity
     int maxCellW, maxCellH;  // largest FAST cell interior of this image size (sizes the FAST kernel's shared memory)
-    FastLayout fast;
     FastWarpPlan fw;
     long long pyrFrameBytes, blurFrameBytes, slotFrameEntries, keyWsFrameEntries;
     unsigned char* pyr;
@@ -134,14 +117,11 @@ struct BlurTile { int level, cta; };   // one CTA of the blur kernel: level and 
 // launchers (each returns orb_status and bumps *launches)
 int launch_pyramid(const ExtractParams& P, const unsigned char* dImages, int width, int height, int stride,
                    size_t frameStride, cudaStream_t st, int* launches);
-int launch_fast(const ExtractParams& P, cudaStream_t st, int* launches);
-FastLayout fast_layout(int maxCellW, int maxCellH);
 int fast_warp_plan(int nLevels, const int* cellW, const int* cellH, int slotCapMax, FastWarpPlan* plan);
 int fast_warp_max_warps(const FastWarpPlan& plan, int* warps);   // resident warps of one launch on the current device
 int launch_fast_warp(const ExtractParams& P, cudaStream_t st, int* launches);
 // one CUtensorMap (128 bytes, host copy) per level over [frames][rows][pitch] of the padded pyramid arena
 int fast_warp_encode_maps(const ExtractParams& P, int arenaFrames, void* hostMaps128xLevels);
-void fast_cell_setup(Cell& c, long long levelPyrOff, int pitch);
 int launch_octree(const ExtractParams& P, int smemBytes, int keyCapSmem, int nodeCap, int cellCap, cudaStream_t st,
                   int* launches);
 int launch_blur(const ExtractParams& P, const BlurTile* dTiles, int nTiles, cudaStream_t st, int* launches);

@@ -16,8 +16,8 @@
 //   barrier was the top stall.  Here a warp walks a strided list of (frame, cell) items; every phase is warp-synchronous:
 //     0. the cell's tile (interior + 3-px ring) is fetched by ONE TMA tensor load (cp.async.bulk.tensor.3d, box
 //        bw x bh x 1 out of [frame][row][pitch]) into the warp's own shared-memory buffer; the load of the NEXT cell is
-//        issued before the current one is processed (two buffers, two mbarriers), so global latency is hidden without
-//        holding registers.  A TMA box must start on a 16-byte boundary of global memory (measured: an unaligned
+//        issued as soon as the current one has read its tile for the last time (end of its last scoring pass), so
+//        the copy overlaps the current cell's NMS / emission / clean-up without holding registers.  A TMA box must start on a 16-byte boundary of global memory (measured: an unaligned
 //        innermost coordinate raises "illegal instruction", tools/microbench/tma_probe.cu), so the box starts at the
 //        aligned column below x0-4 and the cell carries its misalignment `mis` (0..15); the tile pitch is 80 or 96
 //        bytes (20 / 24 words), for which rows two apart fall into disjoint bank octets;
@@ -276,6 +276,7 @@ __device__ __forceinline__ int fast_front(FwWarp& W, const FastWarpPlan::Level& 
         const int iA = q0 + lane, iB = iA + 32;
         const bool vA = iA < nq, vB = iB < nq;
         const unsigned int eA = vA ? W.queue[iA] : 0u, eB = vB ? W.queue[iB] : 0u;
+        __syncwarp();   // every lane has read its entries before any lane overwrites them with corners below
         const int xA = eA & 63, yA = (eA >> 6) & 63, xB = eB & 63, yB = (eB >> 6) & 63;
         const unsigned char* pA = tilePix + yA * BW + xA;
         const unsigned char* pB = tilePix + yB * BW + xB;
