@@ -353,6 +353,127 @@ def frame_side_latency(device, m, med):
     return out
 
 
+def bind_to_gpu_numa(local):
+    """Pin this process to the CPU cores next to its GPU before any pinned buffer is allocated: pinned pages are placed
+    by first touch, and eight ranks copying from one NUMA node's memory is what halves the per-GPU H2D rate."""
+    info = {"bound": False}
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(local)
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        node = int(open(path + "numa_node").read())
+        cpus = set()
+        for part in open(path + "local_cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        info.update({"numa_node": node, "local_cpus": len(cpus)})
+        if cpus and node >= 0:
+            os.sched_setaffinity(0, cpus)
+            info["bound"] = True
+    except Exception as ex:     # not fatal: the benchmark runs unbound
+        info["error"] = str(ex)[:80]
+    return info
+
+
+def allpairs_leg(orbb200, dist, world, rank, local, dev, stream, barrier, max_over_ranks, steps):
+    """configs[4]: all-pairs keyframe matching, 8192 keyframes x 1000 descriptors sharded by query block over the ranks, the
+    descriptor table all-gathered in chunks over NVLink (NCCL) under the matching of the chunks that have landed.  The full
+    matrix is 6.7e13 compares (15 s on 8 GPUs), so every rank matches a SAMPLE of 64 of its query keyframes against ALL
+    8192 db keyframes; the collective is the full one (every rank receives the other ranks' whole blocks)."""
+    import torch
+    from orbb200 import shard
+    n_kf, n_desc, q_per_rank, chunk_kf = 8192, 1000, 64, 512
+    per = [e - b for b, e in (shard.block_range(n_kf, r, world) for r in range(world))]
+    n_loc = per[rank]
+    m = orbb200.Matcher(local)
+    if dist:
+        comm = shard.make_comm(dist, local)
+    else:
+        comm = orbb200.Comm(orbb200.Comm.unique_id(), 0, 1, local)
+    g = torch.Generator(device=dev)
+    g.manual_seed(4242)
+    # a shared "map" of 1000 descriptors that every keyframe sees through 25 % bit noise in its first 400 slots, so that
+    # keyframe pairs do have matches and the sequential one-to-one rule runs
+    world_desc = torch.randint(0, 256, (n_desc, 32), dtype=torch.uint8, device=dev, generator=g)
+    g.manual_seed(4243 + rank)
+    desc = torch.randint(0, 256, (n_loc, n_desc, 32), dtype=torch.uint8, device=dev, generator=g)
+    noise = (torch.randint(0, 256, (n_loc, 400, 32), dtype=torch.uint8, device=dev, generator=g)
+             & torch.randint(0, 256, (n_loc, 400, 32), dtype=torch.uint8, device=dev, generator=g)
+             & torch.randint(0, 256, (n_loc, 400, 32), dtype=torch.uint8, device=dev, generator=g))
+    desc[:, :400] = world_desc[None, :400] ^ noise
+    ang = torch.rand((n_loc, n_desc), device=dev, generator=g) * 360
+    counts = torch.empty((q_per_rank, n_kf), dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+
+    def step():
+        m.allpairs_sharded(comm, desc, ang, per, 0.75, True, counts, chunk_kf=chunk_kf, q_count=q_per_rank, stream=stream.cuda_stream)
+
+    step()
+    stream.synchronize()
+    popc = m.popc_peak()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        step()
+    e1.record(stream)
+    stream.synchronize()
+    gather = comm.last_gather()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1)) / steps
+    gather_ms = max_over_ranks(gather["ms"])
+    compares = world * q_per_rank * n_kf * n_desc * n_desc
+    out = {"workload": "configs[4]: %d keyframes x %d descriptors, query blocks of %d keyframes per rank, %d sampled query "
+                       "keyframes per rank against all db keyframes; table all-gathered in %d chunks of %d keyframes per rank"
+                       % (n_kf, n_desc, n_loc, q_per_rank, gather["chunks"], chunk_kf),
+           "value": compares / (ms * 1e-3), "unit": "compares/s", "ms_per_step": ms, "scaling": "weak (queries per rank fixed)",
+           "roofline": {"bound": "popc", "achieved": compares / world / (ms * 1e-3) * 8 / 1e9, "peak": popc / 1e9, "unit": "GPOPC32/s",
+                        "frac": compares / world / (ms * 1e-3) * 8 / popc, "peak_source": "orbm_popc_peak microbenchmark in this run"},
+           "collective": {"op": "ncclAllGather (C++ host, orbm_allpairs_sharded)", "nccl_version": comm.nccl_version(),
+                          "bytes_received_per_rank": gather["bytes_received"], "gather_ms": gather_ms,
+                          "nvlink_gbs_per_rank": (gather["bytes_received"] / (gather_ms * 1e-3) / 1e9) if gather_ms > 0 else None,
+                          "gather_share_of_step": gather_ms / ms if ms > 0 else None},
+           "gpu_launches": m.launch_count() * steps, "matches_mean": float(counts.float().mean().item())}
+    # correctness on a small table: the sharded tile equals the single-GPU kernel on the gathered table
+    if dist:
+        small_kf, small_desc = 32 * world, 300
+        sper = [e - b for b, e in (shard.block_range(small_kf, r, world) for r in range(world))]
+        sd = desc[: sper[rank], :small_desc].contiguous()
+        sa = ang[: sper[rank], :small_desc].contiguous()
+        tile = torch.full((sper[rank], small_kf), -1, dtype=torch.int32, device=dev)
+        ref = torch.full((sper[rank], small_kf), -1, dtype=torch.int32, device=dev)
+        torch.cuda.synchronize()     # the fills above run on torch's current stream, the matcher on `stream`
+        m.allpairs_sharded(comm, sd, sa, sper, 0.75, True, tile, chunk_kf=8, stream=stream.cuda_stream)
+        stream.synchronize()
+        gd = torch.empty((small_kf, small_desc, 32), dtype=torch.uint8, device=dev)
+        ga = torch.empty((small_kf, small_desc), dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(gd, sd)
+        dist.all_gather_into_tensor(ga, sa)
+        torch.cuda.synchronize()
+        q0 = sum(sper[:rank])
+        m.allpairs_device(gd, ga, q0, q0 + sper[rank], 0, small_kf, 0.75, True, ref, stream=stream.cuda_stream)
+        stream.synchronize()
+        same = torch.tensor([int(torch.equal(tile, ref))], device=dev)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        out["check"] = {"sharded_equals_single_gpu": bool(same.item()), "keyframes": small_kf, "descriptors": small_desc}
+    comm.close()
+    m.close()
+    if dist and rank == 0:
+        try:
+            import glob
+            import re
+            lines = []
+            for f in sorted(glob.glob("/tmp/orbb_nccl_rank0_*.log"), key=os.path.getmtime)[-1:]:
+                for ln in open(f, errors="replace"):
+                    if re.search(r"NVLS|Channel 0[01]/|Connected all|nRanks|via P2P|Trees|Rings|comm 0x", ln):
+                        lines.append(ln.strip()[-160:])
+            out["collective"]["nccl_log"] = lines[:6] + lines[-6:] if len(lines) > 12 else lines
+        except Exception as ex:
+            out["collective"]["nccl_log"] = ["unavailable: %s" % str(ex)[:80]]
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -390,6 +511,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--no-hamming", action="store_true")
     ap.add_argument("--no-latency", action="store_true", help="skip the single-frame latency leg")
+    ap.add_argument("--no-allpairs", action="store_true", help="skip the configs[4] all-pairs leg")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -405,8 +527,14 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa(local)
     dist = None
     if world > 1:
+        # NCCL's own communicator lines (rings / NVLS, channel counts) go to a file per rank; rank 0 quotes them in the
+        # JSON line (allpairs.collective.nccl_log) so that the transport the gather used is on record
+        os.environ["NCCL_DEBUG"] = "INFO"
+        os.environ["NCCL_DEBUG_SUBSYS"] = "INIT,GRAPH"
+        os.environ["NCCL_DEBUG_FILE"] = "/tmp/orbb_nccl_rank%d_%%p.log" % rank
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
@@ -496,7 +624,31 @@ def main():
     c1.record()
     torch.cuda.synchronize()
     h2d_gbs = 3 * B * W * H / (c0.elapsed_time(c1) * 1e-3) / 1e9
+    # ... and with every rank copying at the same time: the ceiling the e2e number of this N can reach
+    barrier()
+    c0.record()
+    for _ in range(3):
+        d_images.copy_(h_images, non_blocking=True)
+    c1.record()
+    torch.cuda.synchronize()
+    conc_ms = max_over_ranks(c0.elapsed_time(c1))
+    h2d_conc_gbs = 3 * B * W * H / (conc_ms * 1e-3) / 1e9      # per GPU, slowest rank
     e2e_launches = ex.launch_count() * e2e_steps
+
+    # ---- strong scaling of configs[2]: the SAME 4096 frames in total, cut over the ranks (device resident)
+    Bs = max(1, B // world)
+    for _ in range(2):
+        ex.extract_batch_device(d_images[:Bs], d_kps, d_desc, d_n, stream=stream.cuda_stream)
+    stream.synchronize()
+    barrier()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record(stream)
+    for _ in range(K):
+        ex.extract_batch_device(d_images[:Bs], d_kps, d_desc, d_n, stream=stream.cuda_stream)
+    s1.record(stream)
+    stream.synchronize()
+    barrier()
+    strong_ms = max_over_ranks(s0.elapsed_time(s1))
 
     line = None
     if rank == 0:
@@ -530,7 +682,12 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": B * W * H,
                     "d2h_bytes_per_step": B * (cap * 60 + 4), "steps": e2e_steps,
-                    "h2d_gbs_in_e2e": e2e_value / world * W * H / 1e9, "h2d_gbs_link_alone": h2d_gbs},
+                    "h2d_gbs_in_e2e": e2e_value / world * W * H / 1e9, "h2d_gbs_link_alone": h2d_gbs,
+                    "h2d_gbs_all_ranks_copying": h2d_conc_gbs,
+                    "frames_per_s_ceiling_of_the_link": world * h2d_conc_gbs * 1e9 / (W * H),
+                    "frac_of_link_ceiling": (e2e_value / world * W * H / 1e9) / h2d_conc_gbs, "numa": numa},
+            "strong_scaling": {"workload": "configs[2]: %d frames in total, %d per GPU" % (Bs * world, Bs),
+                               "value": Bs * world * K / (strong_ms * 1e-3), "unit": "frames/s", "ms_per_step": strong_ms / K},
             "gpu_launches": launches_per_step * K,
             "roofline": {"bound": "hbm", "kernel": dom_bw, "achieved": ach, "peak": hbm, "unit": "GB/s",
                          "frac": ach / hbm, "traffic": traffic,
@@ -589,6 +746,12 @@ def main():
                                             "peak_source": "orbm_popc_peak microbenchmark in this run"},
                                "gpu_launches": 2 * K, "matches_per_pair": float(nm.float().mean().item())}
         m.close()
+
+    # ---- configs[4]: all-pairs keyframe matching with the NCCL all-gather of the descriptor table
+    if not args.no_allpairs:
+        ap_line = allpairs_leg(orbb200, dist, world, rank, local, dev, stream, barrier, max_over_ranks, max(2, K // 5))
+        if rank == 0:
+            line["allpairs"] = ap_line
 
     # ---- single-frame latency of configs[0] / configs[1] through the host C ABI (what a live SLAM loop sees)
     if rank == 0 and world == 1 and not args.no_latency:

@@ -281,6 +281,31 @@ int orbm_allpairs_device(orbm_handle h, const uint8_t* d_table, const float* d_a
                          int q_begin, int q_end, int db_begin, int db_end, float nnratio, int check_orientation,
                          int* d_counts, void* stream);
 
+/* Config 5, multi-GPU: all-pairs keyframe matching sharded by query block, one process per GPU.  The only exchange of the
+ * path is the all-gather of the keyframe descriptor table (NCCL over NVLink); it is cut into chunks of chunk_kf keyframes
+ * per rank so that matching against the chunks that have landed overlaps the transfer of the next ones, and the rank's
+ * own block (no communication) is matched first.  NCCL is loaded at run time (libnccl.so.2); single-GPU callers never
+ * touch it.  Semantics of every (query keyframe, db keyframe) count as in orbm_allpairs_device.
+ *   orbm_comm_unique_id: rank 0 makes the 128-byte ncclUniqueId, the caller hands it to the other ranks (MPI, a file,
+ *                        torch.distributed.broadcast, ...)
+ *   orbm_comm_create:    ncclCommInitRank on `device` (collective: every rank calls it)
+ *   orbm_allpairs_sharded: d_local_desc = this rank's block [kf_per_rank[rank]][n_desc][32], d_local_angles likewise;
+ *                        kf_per_rank[world] (host) = block sizes, blocks are contiguous in rank order;
+ *                        q_count = how many keyframes from the start of the local block are queries (-1 = all of them:
+ *                        the full matrix; a smaller number matches new keyframes against the whole map);
+ *                        d_counts = [q_count][sum(kf_per_rank)] int32.  Enqueues on `stream` (NULL = the matcher's
+ *                        stream) and on the communicator's own copy stream; returns without synchronising.
+ *   orbm_comm_last_gather: time the copy stream spent in the last call's gathers, bytes received, chunk count.       */
+typedef struct orbm_comm_s* orbm_comm;
+int orbm_comm_unique_id(uint8_t* id128);
+int orbm_comm_create(const uint8_t* id128, int rank, int world, int device, orbm_comm* out);
+int orbm_comm_destroy(orbm_comm c);
+int orbm_comm_info(orbm_comm c, int* rank, int* world, int* nccl_version);
+int orbm_allpairs_sharded(orbm_handle h, orbm_comm c, const uint8_t* d_local_desc, const float* d_local_angles,
+                          const int* kf_per_rank, int n_desc, int q_count, int chunk_kf, float nnratio,
+                          int check_orientation, int* d_counts, void* stream);
+int orbm_comm_last_gather(orbm_comm c, double* ms, double* bytes_received, int* chunks);
+
 /* MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:257-322) for n_points map points in one call (LocalMapping runs it
  * for every point a new keyframe touches): point p is observed by descriptors[start[p] .. start[p+1]) -- rows of 32 B in
  * mObservations order, bad keyframes already dropped; start[0] = 0.  best[p] = index INSIDE the point's run of the

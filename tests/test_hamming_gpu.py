@@ -103,6 +103,35 @@ def test_allpairs_counts(matcher, oracle):
     assert np.array_equal(part.cpu().numpy(), ref[4:8])
 
 
+def test_allpairs_sharded_single_rank(matcher, oracle):
+    """orbm_allpairs_sharded through the C ABI with a one-rank NCCL communicator: the own-block path, q_count, and the
+    segment launches agree with the oracle (the N > 1 gathers are checked against the single-GPU kernel by
+    bench.py --gpus N, allpairs.check, and by tools/gpu_multi_ap.sh)."""
+    rng = np.random.default_rng(23)
+    nkf, nd = 9, 200
+    table = np.zeros((nkf, nd, 32), np.uint8)
+    ang = np.zeros((nkf, nd), np.float32)
+    for k in range(0, nkf - 1, 2):
+        q, qa, t, ta = planted_descriptors(rng, nd, nd, frac=0.5, max_flip=40)
+        table[k], ang[k], table[k + 1], ang[k + 1] = q, qa, t, ta
+    table[8] = rng.integers(0, 256, (nd, 32), dtype=np.uint8)
+    d_table, d_ang = torch.from_numpy(table).cuda(), torch.from_numpy(ang).cuda()
+    ref = np.array([[oracle.kf_pair(table[i], ang[i], table[j], ang[j], 0.75, True)[0] for j in range(nkf)] for i in range(nkf)])
+    comm = orbb200.Comm(orbb200.Comm.unique_id(), 0, 1, 0)
+    try:
+        assert comm.nccl_version() >= 21000
+        for q_count in (-1, 4):
+            rows = nkf if q_count < 0 else q_count
+            counts = torch.full((rows, nkf), -7, dtype=torch.int32, device="cuda")
+            torch.cuda.synchronize()
+            matcher.allpairs_sharded(comm, d_table, d_ang, [nkf], 0.75, True, counts, chunk_kf=4, q_count=q_count)
+            matcher.synchronize()
+            assert np.array_equal(counts.cpu().numpy(), ref[:rows])
+        assert comm.last_gather()["chunks"] == 0          # one rank: nothing to gather
+    finally:
+        comm.close()
+
+
 def test_popc_peak_plausible(matcher):
     v = matcher.popc_peak()
     assert 1e12 < v < 2e13

@@ -152,9 +152,22 @@ struct ApShared {
     int nCand;
 };
 
+// db keyframe d of the launch -> row of `table` and column of `counts`.  n == 0: row = d, column = colOffset + d; otherwise
+// d runs over the concatenation of n segments (the other ranks' parts of one gathered chunk of the sharded table).
+__device__ __forceinline__ void ap_locate(const ApSegments& sg, int d, int colOffset, int& row, int& col) {
+    row = d;
+    col = colOffset + d;
+    for (int s = 0; s < sg.n; ++s)
+        if (d >= sg.start[s] && d < sg.start[s + 1]) {
+            row = sg.row[s] + d - sg.start[s];
+            col = sg.col[s] + d - sg.start[s];
+        }
+}
+
 __global__ void __launch_bounds__(AP_THREADS)
-allpairs_kernel(const uint4* __restrict__ table, const float* __restrict__ angles, int nDesc, int qBegin, int dbBegin,
-                int dbEnd, int dbPerBlock, int nKfTotal, float ratio, int checkOri, int* __restrict__ counts) {
+allpairs_kernel(const uint4* __restrict__ qTable, const float* __restrict__ qAngles, const uint4* __restrict__ table,
+                const float* __restrict__ angles, int nDesc, int qBegin, int dbBegin, int dbEnd, int dbPerBlock, int nKfTotal,
+                int colOffset, const __grid_constant__ ApSegments segs, float ratio, int checkOri, int* __restrict__ counts) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     ApShared& S = *reinterpret_cast<ApShared*>(smemRaw);
     const int qkf = qBegin + blockIdx.x;
@@ -163,7 +176,7 @@ allpairs_kernel(const uint4* __restrict__ table, const float* __restrict__ angle
     if (j0 >= j1) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-    const uint4* q = table + (size_t)qkf * nDesc * 2;
+    const uint4* q = qTable + (size_t)qkf * nDesc * 2;
     uint4 qa[AP_QPT], qb[AP_QPT];
 #pragma unroll
     for (int k = 0; k < AP_QPT; ++k) {
@@ -172,13 +185,17 @@ allpairs_kernel(const uint4* __restrict__ table, const float* __restrict__ angle
         qb[k] = __ldg(q + 2 * (size_t)qi + 1);
     }
     auto prefetch = [&](int j, int buf) {
-        const uint4* src = table + (size_t)j * nDesc * 2;
+        int row, col;
+        ap_locate(segs, j, colOffset, row, col);
+        const uint4* src = table + (size_t)row * nDesc * 2;
         for (int i = tid; i < nDesc * 2; i += AP_THREADS) cp_async16(&S.db[buf][i], src + i);
         cp_async_commit();
     };
     prefetch(j0, 0);
     for (int j = j0; j < j1; ++j) {
         const int buf = (j - j0) & 1;
+        int dbRow, dbCol;
+        ap_locate(segs, j, colOffset, dbRow, dbCol);
         if (j + 1 < j1) { prefetch(j + 1, buf ^ 1); cp_async_wait<1>(); }
         else cp_async_wait<0>();
         __syncthreads();
@@ -215,8 +232,8 @@ allpairs_kernel(const uint4* __restrict__ table, const float* __restrict__ angle
             if (warp == 0) {
                 // sequential replay in query order (i1 ascending); lanes cooperate on the rare recomputation
                 int nMatched = 0, accepted = 0;
-                const float* a1 = angles + (size_t)qkf * nDesc;
-                const float* a2 = angles + (size_t)j * nDesc;
+                const float* a1 = qAngles + (size_t)qkf * nDesc;
+                const float* a2 = angles + (size_t)dbRow * nDesc;
                 for (int qbase = 0; qbase < nDesc; qbase += 32) {
                     const int qi = qbase + lane;
                     unsigned cand = __ballot_sync(0xffffffffu, qi < nDesc && S.bestKey[qi] != kNoKey);
@@ -273,7 +290,7 @@ allpairs_kernel(const uint4* __restrict__ table, const float* __restrict__ angle
             __syncthreads();
             result = S.nCand;
         }
-        if (tid == 0) counts[(size_t)blockIdx.x * nKfTotal + j] = result;
+        if (tid == 0) counts[(size_t)blockIdx.x * nKfTotal + dbCol] = result;
         __syncthreads();   // db[buf] and the key arrays are reused two iterations later / next iteration
     }
 }
@@ -318,26 +335,41 @@ int launch_bruteforce(const uint8_t* dq, const float* dqa, int nq, const uint8_t
     return ORB_OK;
 }
 
-int launch_allpairs(const uint8_t* dTable, const float* dAngles, int nKf, int nDesc, int qBegin, int qEnd, int dbBegin,
-                    int dbEnd, float ratio, int checkOri, int* dCounts, cudaStream_t st, int* launches) {
+// Query keyframes [qBegin, qEnd) of (dQTable, dQAngles) against db keyframes [dbBegin, dbEnd) of (dTable, dAngles);
+// counts[(q - qBegin) * ldCounts + colOffset + db].  The two tables may be the same one (single GPU) or the local block
+// and a gathered chunk of another rank's block (sharded all-pairs).
+int launch_allpairs_ex(const uint8_t* dQTable, const float* dQAngles, int qBegin, int qEnd, const uint8_t* dTable,
+                       const float* dAngles, int dbBegin, int dbEnd, int nDesc, int ldCounts, int colOffset, float ratio,
+                       int checkOri, int* dCounts, cudaStream_t st, int* launches, const ApSegments* segs) {
     if (nDesc < 1 || nDesc > AP_MAXQ) return fail(ORB_ERR_INVALID, "allpairs: n_desc=%d must be in 1..%d", nDesc, AP_MAXQ);
-    if (qBegin < 0 || qEnd > nKf || dbBegin < 0 || dbEnd > nKf || qBegin > qEnd || dbBegin > dbEnd)
-        return fail(ORB_ERR_INVALID, "allpairs: bad ranges");
+    if (qBegin < 0 || dbBegin < 0 || qBegin > qEnd || dbBegin > dbEnd) return fail(ORB_ERR_INVALID, "allpairs: bad ranges");
     const int nQ = qEnd - qBegin, nDb = dbEnd - dbBegin;
     if (nQ == 0 || nDb == 0) return ORB_OK;
     // per device and cheap; set every time so that matchers on different GPUs of one process all get it
     ORB_CUDA(cudaFuncSetAttribute(allpairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ApShared)));
-    // enough blocks to fill the GPU several times over, long enough runs that the query registers are amortised
+    // long enough runs that the query registers are amortised, and at least ~8 waves of blocks (3 resident per SM): a
+    // launch's last wave is only partly filled, which cost 10 % of a 64 x 512 keyframe launch at 2.3 waves
     int dbPerBlock = 64;
-    while (dbPerBlock > 8 && (long long)nQ * ceil_div(nDb, dbPerBlock) < 148 * 6) dbPerBlock >>= 1;
+    while (dbPerBlock > 8 && (long long)nQ * ceil_div(nDb, dbPerBlock) < 148 * 3 * 8) dbPerBlock >>= 1;
     const int chunks = ceil_div(nDb, dbPerBlock);
     if (chunks > 65535) return fail(ORB_ERR_INVALID, "allpairs: too many db chunks");
     dim3 grid(nQ, chunks);
-    allpairs_kernel<<<grid, AP_THREADS, sizeof(ApShared), st>>>((const uint4*)dTable, dAngles, nDesc, qBegin, dbBegin,
-                                                                dbEnd, dbPerBlock, nKf, ratio, checkOri, dCounts);
+    ApSegments sg;
+    if (segs) sg = *segs;
+    else sg.n = 0;
+    allpairs_kernel<<<grid, AP_THREADS, sizeof(ApShared), st>>>((const uint4*)dQTable, dQAngles, (const uint4*)dTable, dAngles,
+                                                                nDesc, qBegin, dbBegin, dbEnd, dbPerBlock, ldCounts, colOffset,
+                                                                sg, ratio, checkOri, dCounts);
     if (launches) *launches += 1;
     ORB_CUDA(cudaGetLastError());
     return ORB_OK;
+}
+
+int launch_allpairs(const uint8_t* dTable, const float* dAngles, int nKf, int nDesc, int qBegin, int qEnd, int dbBegin,
+                    int dbEnd, float ratio, int checkOri, int* dCounts, cudaStream_t st, int* launches) {
+    if (qEnd > nKf || dbEnd > nKf) return fail(ORB_ERR_INVALID, "allpairs: bad ranges");
+    return launch_allpairs_ex(dTable, dAngles, qBegin, qEnd, dTable, dAngles, dbBegin, dbEnd, nDesc, nKf, 0, ratio, checkOri,
+                              dCounts, st, launches, nullptr);
 }
 
 int launch_distance(const uint8_t* da, const uint8_t* db, int n, int* dOut, cudaStream_t st, int* launches) {

@@ -9,6 +9,15 @@ int launch_bruteforce(const uint8_t* dq, const float* dqa, int nq, const uint8_t
                       int* dIdx, int* dM12, int* dN, cudaStream_t st, int* launches);
 int launch_allpairs(const uint8_t* dTable, const float* dAngles, int nKf, int nDesc, int qBegin, int qEnd, int dbBegin,
                     int dbEnd, float ratio, int checkOri, int* dCounts, cudaStream_t st, int* launches);
+// db keyframes of one all-pairs launch as a concatenation of up to 16 segments: dense index [start[s], start[s+1]) ->
+// rows row[s].. of the db table, columns col[s].. of the count matrix
+struct ApSegments {
+    int n;
+    int start[17], row[16], col[16];
+};
+int launch_allpairs_ex(const uint8_t* dQTable, const float* dQAngles, int qBegin, int qEnd, const uint8_t* dTable,
+                       const float* dAngles, int dbBegin, int dbEnd, int nDesc, int ldCounts, int colOffset, float ratio,
+                       int checkOri, int* dCounts, cudaStream_t st, int* launches, const ApSegments* segs = nullptr);
 int launch_distance(const uint8_t* da, const uint8_t* db, int n, int* dOut, cudaStream_t st, int* launches);
 int launch_distinctive(const uint8_t* dDesc, const int* dStart, int nPoints, int* dBest, int* dBestMedian, cudaStream_t st,
                        int* launches);

@@ -345,6 +345,14 @@ class Matcher:
         _check(self.L.orbm_allpairs_device(self.h, _dp(d_table), _dp(d_angles), n_kf, n_desc, q_begin, q_end, db_begin,
                                            db_end, C.c_float(ratio), int(check_ori), _dp(d_counts), _dp(stream)))
 
+    def allpairs_sharded(self, comm, d_local_desc, d_local_angles, kf_per_rank, ratio, check_ori, d_counts, chunk_kf=128,
+                         q_count=-1, stream=None):
+        """Config 5 through the C ABI: this rank's (n_local x n_kf) tile; chunked ncclAllGather overlapped with matching."""
+        n_desc = d_local_desc.shape[1]
+        per = np.ascontiguousarray(kf_per_rank, np.int32)
+        _check(self.L.orbm_allpairs_sharded(self.h, comm.h, _dp(d_local_desc), _dp(d_local_angles), _p(per), n_desc, q_count, chunk_kf,
+                                            C.c_float(ratio), int(check_ori), _dp(d_counts), C.c_void_p(stream or 0)))
+
     def distinctive_descriptors(self, desc, start):
         """MapPoint::ComputeDistinctiveDescriptors for len(start)-1 map points: (best index inside each run, median)"""
         d = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
@@ -474,3 +482,35 @@ class Matcher:
 
 
 BEST_QUERY_DTYPE = np.dtype([("u", "<f4"), ("v", "<f4"), ("radius", "<f4"), ("ur", "<f4"), ("level", "<i4"), ("valid", "<i4")])
+
+
+class Comm:
+    """NCCL communicator of the sharded all-pairs path (orbm_comm_*): one per process / GPU."""
+
+    @staticmethod
+    def unique_id():
+        buf = np.zeros(128, np.uint8)
+        _check(lib().orbm_comm_unique_id(_p(buf)))
+        return buf
+
+    def __init__(self, unique_id, rank, world, device):
+        self.L = lib()
+        self.h = C.c_void_p()
+        uid = np.ascontiguousarray(unique_id, np.uint8)
+        _check(self.L.orbm_comm_create(_p(uid), rank, world, device, C.byref(self.h)))
+        self.rank, self.world = rank, world
+
+    def close(self):
+        if self.h:
+            self.L.orbm_comm_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def nccl_version(self):
+        v = C.c_int()
+        _check(self.L.orbm_comm_info(self.h, None, None, C.byref(v)))
+        return v.value
+
+    def last_gather(self):
+        ms, by, ch = C.c_double(), C.c_double(), C.c_int()
+        _check(self.L.orbm_comm_last_gather(self.h, C.byref(ms), C.byref(by), C.byref(ch)))
+        return {"ms": ms.value, "bytes_received": by.value, "chunks": ch.value}

@@ -53,6 +53,12 @@ SIGNATURES = {
     "orbm_bruteforce":(i32, [vp, vp, vp, i32, vp, vp, i32, i32, f32, i32, vp, vp, vp, vp, vp]),
     "orbm_bruteforce_device": (i32, [vp, vp, vp, i32, vp, vp, i32, i32, f32, i32, vp, vp, vp, vp, vp, vp]),
     "orbm_allpairs_device": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, f32, i32, vp, vp]),
+    "orbm_comm_unique_id": (i32, [vp]),
+    "orbm_comm_create": (i32, [vp, i32, i32, i32, vp]),
+    "orbm_comm_destroy": (i32, [vp]),
+    "orbm_comm_info": (i32, [vp, vp, vp, vp]),
+    "orbm_allpairs_sharded": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, f32, i32, vp, vp]),
+    "orbm_comm_last_gather": (i32, [vp, vp, vp, vp]),
     "orbm_distinctive_descriptors": (i32, [vp, vp, vp, i32, vp, vp]),
     "orbm_vocabulary_create": (i32, [vp, i32, i32, vp, vp, vp, vp, vp, vp]),
     "orbm_vocabulary_destroy": (i32, [vp]),

@@ -47,53 +47,70 @@ def all_gather_table(local_desc, local_angles, n_kf, dist, async_op=True):
     return gd, ga, [w for w in works if w is not None], max_local, sizes
 
 
+def make_comm(dist, device):
+    """orbm_comm for this process: rank 0 creates the ncclUniqueId, torch.distributed only carries its 128 bytes."""
+    import torch
+    import orbb200
+    world, rank = dist.get_world_size(), dist.get_rank()
+    uid = torch.zeros(128, dtype=torch.uint8)
+    if rank == 0:
+        uid = torch.from_numpy(orbb200.Comm.unique_id().copy())
+    dev = torch.device("cuda", device)
+    uid = uid.to(dev)
+    dist.broadcast(uid, 0)
+    return orbb200.Comm(uid.cpu().numpy(), rank, world, device)
+
+
 def allpairs_sharded(matcher, local_desc, local_angles, n_kf, dist, ratio=0.75, check_ori=True, compute=None,
-                     torch_stream=None):
+                     torch_stream=None, comm=None, chunk_kf=128):
     """Config 5: this rank's (n_local x n_kf) tile of the keyframe match-count matrix.
 
-    compute(table, angles, q_begin, q_end, db_begin, db_end, counts) defaults to the CUDA all-pairs kernel through the C ABI;
-    the gloo tests inject a host stand-in to exercise the plumbing without a GPU.
-    On CUDA everything (gather, kernels) is ordered on `torch_stream`, a NON-default torch stream (the C ABI treats a
-    NULL stream as "the matcher's own stream", so the legacy default stream cannot be passed); the call returns with the
-    work enqueued and `torch_stream` holding it.
+    On CUDA this is a thin caller of the C ABI (orbm_allpairs_sharded: chunked ncclAllGather on the communicator's copy
+    stream, matching of the landed chunks on `torch_stream`); `comm` is an orbb200.Comm (made here if None).  The call
+    returns with the work enqueued.
+    With `compute` given (the gloo tests: a host stand-in for the kernel) the same block layout is exercised through
+    torch.distributed instead: compute(table, angles, q_begin, q_end, db_begin, db_end, counts).
     """
-    import contextlib
     import torch
     world, rank = dist.get_world_size(), dist.get_rank()
-    on_gpu = local_desc.is_cuda
-    ctx = contextlib.nullcontext()
-    if on_gpu:
+    sizes = [block_range(n_kf, r, world) for r in range(world)]
+    qb, qe = sizes[rank]
+    if compute is None:
+        if not local_desc.is_cuda:
+            raise RuntimeError("allpairs_sharded: the CUDA path needs device tensors (there is no CPU fallback)")
+        own_comm = comm is None
+        if own_comm:
+            comm = make_comm(dist, local_desc.device.index)
         if torch_stream is None:
             torch_stream = torch.cuda.Stream(device=local_desc.device)
         torch_stream.wait_stream(torch.cuda.current_stream(local_desc.device))   # the producers of local_desc
-        ctx = torch.cuda.stream(torch_stream)
-    with ctx:
-        gd, ga, works, max_local, sizes = all_gather_table(local_desc, local_angles, n_kf, dist)
-        qb, qe = sizes[rank]
         counts = torch.full((qe - qb, n_kf), -1, dtype=torch.int32, device=local_desc.device)
-        padded_rows = world * max_local
-        if compute is None:
-            raw_stream = torch_stream.cuda_stream
-
-            def compute(table, angles, q0, q1, d0, d1, out):
-                # `out` has one column per row of the padded table; only [d0, d1) is written by this call
-                matcher.allpairs_device(table, angles, q0, q1, d0, d1, ratio, check_ori, out, stream=raw_stream)
-
-        # rows of the padded table: rank r's keyframes start at r*max_local
-        padded_counts = torch.full((qe - qb, padded_rows), -1, dtype=torch.int32, device=local_desc.device)
-        first = True
-        for (b, e) in column_schedule(n_kf, rank, world):
-            r = next(i for i, s in enumerate(sizes) if s == (b, e))
-            if not first:
-                for w in works:
-                    w.wait()          # makes the current (= torch_stream) stream wait for the gather
-                works = []
-            compute(gd, ga, rank * max_local, rank * max_local + (qe - qb), r * max_local, r * max_local + (e - b), padded_counts)
-            first = False
-        for w in works:
-            w.wait()
-        for r, (b, e) in enumerate(sizes):
-            counts[:, b:e] = padded_counts[:, r * max_local: r * max_local + (e - b)]
+        per = [e - b for b, e in sizes]
+        with torch.cuda.stream(torch_stream):
+            matcher.allpairs_sharded(comm, local_desc.contiguous(), local_angles.contiguous(), per, ratio, check_ori, counts,
+                                     chunk_kf=chunk_kf, stream=torch_stream.cuda_stream)
+        if own_comm:
+            torch_stream.synchronize()
+            comm.close()
+        return counts
+    gd, ga, works, max_local, sizes = all_gather_table(local_desc, local_angles, n_kf, dist)
+    counts = torch.full((qe - qb, n_kf), -1, dtype=torch.int32, device=local_desc.device)
+    padded_rows = world * max_local
+    # rows of the padded table: rank r's keyframes start at r*max_local
+    padded_counts = torch.full((qe - qb, padded_rows), -1, dtype=torch.int32, device=local_desc.device)
+    first = True
+    for (b, e) in column_schedule(n_kf, rank, world):
+        r = next(i for i, s in enumerate(sizes) if s == (b, e))
+        if not first:
+            for w in works:
+                w.wait()
+            works = []
+        compute(gd, ga, rank * max_local, rank * max_local + (qe - qb), r * max_local, r * max_local + (e - b), padded_counts)
+        first = False
+    for w in works:
+        w.wait()
+    for r, (b, e) in enumerate(sizes):
+        counts[:, b:e] = padded_counts[:, r * max_local: r * max_local + (e - b)]
     return counts
 
 
