@@ -107,6 +107,8 @@ def test_allpairs_sharded_single_rank(matcher, oracle):
     """orbm_allpairs_sharded through the C ABI with a one-rank NCCL communicator: the own-block path, q_count, and the
     segment launches agree with the oracle (the N > 1 gathers are checked against the single-GPU kernel by
     bench.py --gpus N, allpairs.check, and by tools/gpu_multi_ap.sh)."""
+    import torch
+    import orbb200
     rng = np.random.default_rng(23)
     nkf, nd = 9, 200
     table = np.zeros((nkf, nd, 32), np.uint8)
