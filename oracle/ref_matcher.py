@@ -62,6 +62,25 @@ class RefMatcher:
         L.refm_search_projection_sim3.argtypes = [vp, vp, i32, vp, vp, i32, i32, vp, vp]
         L.refm_fuse.argtypes = [vp, vp, vp, i32, vp, f32, vp, vp, i32, f32, i32, vp]
         L.refm_search_sim3.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, f32, vp]
+        if not adapter:   # the reference's own grid (Frame.cc / KeyFrame.cc text, oracle/ref_shim/grid)
+            L._lib.refm_grid_csr.argtypes = [vp, i32, f32, f32, f32, f32, vp, vp]
+            L._lib.refm_features_in_area.argtypes = [vp, i32, f32, f32, f32, f32, i32, f32, f32, f32, i32, i32, vp, i32]
+
+    def grid_csr(self, keys_un, bounds):
+        """Frame::AssignFeaturesToGrid (Frame.cc:574-589) as CSR over cells ix * 48 + iy, members in push order."""
+        k = np.ascontiguousarray(keys_un, KP_DTYPE)
+        start = np.empty(64 * 48 + 1, np.int32)
+        idx = np.empty(max(len(k), 1), np.int32)
+        n = self.lib._lib.refm_grid_csr(_p(k), len(k), *[float(b) for b in bounds], _p(start), _p(idx))
+        return start, idx[:n]
+
+    def features_in_area(self, keys_un, bounds, x, y, r, min_level=-1, max_level=-1, keyframe=False):
+        """Frame::GetFeaturesInArea (Frame.cc:671-724) or, keyframe=True, KeyFrame::GetFeaturesInArea (KeyFrame.cc:1138-1177)."""
+        k = np.ascontiguousarray(keys_un, KP_DTYPE)
+        out = np.empty(max(len(k), 1), np.int32)
+        n = self.lib._lib.refm_features_in_area(_p(k), len(k), *[float(b) for b in bounds], int(keyframe), float(x), float(y),
+                                                float(r), int(min_level), int(max_level), _p(out), len(out))
+        return out[:n]
 
     def distance(self, a, b):
         a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)

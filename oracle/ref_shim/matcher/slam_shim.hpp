@@ -2,8 +2,11 @@
 // Stand-ins for ORB_SLAM2::MapPoint / KeyFrame / Frame with exactly the members /root/reference/src/ORBmatcher.cc reads,
 // so that the reference's search loops can be compiled in place and run on flat arrays.  The reference's own headers
 // need Eigen, DBoW2's vocabulary, g2o and the IMU classes; they are kept out by pre-defining their include guards.
-// GetFeaturesInArea / the 64x48 grid live in Frame.cc / KeyFrame.cc, which cannot be compiled here: the stand-ins call
-// the oracle's restatement (oracle/match_oracle.cpp), so the grid lookup itself stays pinned by known-answer tests only.
+// GetFeaturesInArea / the 64x48 grid live in Frame.cc / KeyFrame.cc, which cannot be compiled whole here.  With
+// ORB_REF_GRID (libmatch_ref.so) the stand-ins carry the reference's own member names and the reference's own text of
+// Frame::AssignFeaturesToGrid / PosInGrid / GetFeaturesInArea and KeyFrame::GetFeaturesInArea is streamed into the build
+// (Makefile: grid_ref.o), so the reference's searches run on the reference's grid.  Without it (libmatch_adapter.so, whose
+// ORBmatcher never asks the stand-ins for the grid) the members call the oracle's restatement.
 #pragma once
 #define MAPPOINT_H
 #define KEYFRAME_H
@@ -65,6 +68,8 @@ struct FrameData {
     float mnMinX = 0, mnMinY = 0, mnMaxX = 0, mnMaxY = 0;
     orbo::FrameArrays fa;
 
+    virtual ~FrameData() {}
+    virtual void afterSet() {}          // ORB_REF_GRID: the reference's AssignFeaturesToGrid on the reference's members
     void set(const cv::KeyPoint* keys, const uint8_t* desc, int n, float minX, float minY, float maxX, float maxY) {
         N = n;
         mvKeysUn.assign(keys, keys + n);
@@ -81,6 +86,7 @@ struct FrameData {
         fa.invW = (float)orbo::GRID_COLS / (maxX - minX);    // Frame.cc:104-105 / KeyFrame ctor
         fa.invH = (float)orbo::GRID_ROWS / (maxY - minY);
         fa.buildGrid();
+        afterSet();
     }
     std::vector<size_t> area(float x, float y, float r, int minLevel, int maxLevel) const {
         std::vector<int> v;
@@ -88,6 +94,39 @@ struct FrameData {
         return std::vector<size_t>(v.begin(), v.end());
     }
     bool inImage(float x, float y) const { return x >= mnMinX && x < mnMaxX && y >= mnMinY && y < mnMaxY; }
+};
+
+#ifdef ORB_REF_GRID
+#define FRAME_GRID_ROWS 48    // Frame.h:41-42
+#define FRAME_GRID_COLS 64
+#endif
+
+class Frame : public FrameData {
+public:
+    std::vector<MapPoint*> mvpMapPoints;
+    std::vector<bool> mvbOutlier;
+    cv::Mat mTcw = cv::Mat::eye(4, 4, CV_32F);
+#ifdef ORB_REF_GRID
+    // the reference's members (Frame.h:233-235); the three functions are the reference's own text (grid_ref.o)
+    static float mfGridElementWidthInv, mfGridElementHeightInv;
+    std::vector<std::size_t> mGrid[FRAME_GRID_COLS][FRAME_GRID_ROWS];
+    void AssignFeaturesToGrid();
+    bool PosInGrid(const cv::KeyPoint& kp, int& posX, int& posY);
+    std::vector<size_t> GetFeaturesInArea(const float& x, const float& y, const float& r, const int minLevel = -1,
+                                          const int maxLevel = -1) const;
+    void afterSet() override {
+        mfGridElementWidthInv = static_cast<float>(FRAME_GRID_COLS) / (mnMaxX - mnMinX);     // Frame.cc:445-446
+        mfGridElementHeightInv = static_cast<float>(FRAME_GRID_ROWS) / (mnMaxY - mnMinY);
+        for (int i = 0; i < FRAME_GRID_COLS; ++i)
+            for (int j = 0; j < FRAME_GRID_ROWS; ++j) mGrid[i][j].clear();
+        AssignFeaturesToGrid();
+    }
+#else
+    std::vector<size_t> GetFeaturesInArea(const float& x, const float& y, const float& r, const int minLevel = -1,
+                                          const int maxLevel = -1) const {
+        return area(x, y, r, minLevel, maxLevel);
+    }
+#endif
 };
 
 class KeyFrame : public FrameData {
@@ -108,19 +147,28 @@ public:
     cv::Mat GetTranslation() { return tcw.clone(); }
     cv::Mat GetCameraCenter() { return Ow.clone(); }
     bool IsInImage(const float& x, const float& y) const { return inImage(x, y); }
-    std::vector<size_t> GetFeaturesInArea(const float& x, const float& y, const float& r) const { return area(x, y, r, -1, -1); }
-    void AddMapPoint(MapPoint* p, const size_t& idx) { added.push_back(std::make_pair(p, idx)); }
-};
-
-class Frame : public FrameData {
-public:
-    std::vector<MapPoint*> mvpMapPoints;
-    std::vector<bool> mvbOutlier;
-    cv::Mat mTcw = cv::Mat::eye(4, 4, CV_32F);
-    std::vector<size_t> GetFeaturesInArea(const float& x, const float& y, const float& r, const int minLevel = -1,
-                                          const int maxLevel = -1) const {
-        return area(x, y, r, minLevel, maxLevel);
+#ifdef ORB_REF_GRID
+    // the reference's members (KeyFrame.h:226-229, :306), filled as the KeyFrame constructor does from a Frame
+    // (KeyFrame.cc:55-56, :84-90); GetFeaturesInArea is the reference's own text (grid_ref.o)
+    int mnGridCols = FRAME_GRID_COLS, mnGridRows = FRAME_GRID_ROWS;
+    float mfGridElementWidthInv = 0, mfGridElementHeightInv = 0;
+    std::vector<std::vector<std::vector<size_t> > > mGrid;
+    std::vector<size_t> GetFeaturesInArea(const float& x, const float& y, const float& r) const;
+    void afterSet() override {
+        Frame F;
+        F.set(mvKeysUn.data(), mDescriptors.ptr<uchar>(0), N, mnMinX, mnMinY, mnMaxX, mnMaxY);
+        mfGridElementWidthInv = F.mfGridElementWidthInv;
+        mfGridElementHeightInv = F.mfGridElementHeightInv;
+        mGrid.resize(mnGridCols);
+        for (int i = 0; i < mnGridCols; i++) {
+            mGrid[i].resize(mnGridRows);
+            for (int j = 0; j < mnGridRows; j++) mGrid[i][j] = F.mGrid[i][j];
+        }
     }
+#else
+    std::vector<size_t> GetFeaturesInArea(const float& x, const float& y, const float& r) const { return area(x, y, r, -1, -1); }
+#endif
+    void AddMapPoint(MapPoint* p, const size_t& idx) { added.push_back(std::make_pair(p, idx)); }
 };
 
 }  // namespace ORB_SLAM2

@@ -5,7 +5,8 @@ Extractor vectors come from oracle/_ref/orb_ref = the reference's OWN src/ORBext
 OpenCV stand-in (oracle/ref_shim), i.e. they are outputs of the reference itself, not of our restatement.
 Matcher vectors: matcher_ref_vectors.npz holds outputs of oracle/_ref/libmatch_ref.so = the reference's OWN
 src/ORBmatcher.cc compiled in place against the stand-ins of oracle/ref_shim/matcher (seeded cases of
-tests/matcher_cases.py); matcher_vectors.npz (grid CSR, brute force) is produced by oracle/match_oracle.cpp and says so.
+tests/matcher_cases.py); matcher_vectors.npz holds the grid CSR and area queries of the reference's own Frame.cc / KeyFrame.cc text
+and oracle-generated brute-force vectors (its pinned_by field says which is which).
 Stereo vectors: stereo_ref_vectors.npz holds outputs of oracle/_ref/libstereo_ref.so = the reference's OWN text of
 Frame::ComputeStereoMatches compiled in place (seeded cases of tests/stereo_cases.py; --stereo-only regenerates just these).
 """
@@ -90,18 +91,32 @@ def main():
     n, m12, p = f1.search_init(f2, prev, 100, 0.9, True)
     q, qa, t, ta = planted_descriptors(np.random.default_rng(1), 300, 280)
     bn, best, second, idx, bm12 = o.bruteforce(q, qa, t, ta, 0.9, True)
-    gs, gi = f2.grid()
-    np.savez_compressed(os.path.join(OUT, "matcher_vectors.npz"), ka=ka, da=da, kb=kb, db=db, bounds=np.array(bounds),
-                        init_n=n, init_m12=m12, init_prev=p, grid_start=gs, grid_idx=gi,
-                        bf_q=q, bf_qa=qa, bf_t=t, bf_ta=ta, bf_n=bn, bf_best=best, bf_second=second, bf_idx=idx, bf_m12=bm12,
-                        pinned_by="oracle (grid CSR and brute force; the search loops are in matcher_ref_vectors.npz)")
-    print("matcher vectors: init", n, "bruteforce", bn)
-    # ---- matcher vectors from the reference's own ORBmatcher.cc
+    # ---- the grid and its area queries come from the reference's own Frame.cc / KeyFrame.cc text (oracle/ref_shim/grid)
     import ref_matcher
     from matcher_cases import CASES, run_case
     if not ref_matcher.available():
         ref_matcher.build()
     rm = ref_matcher.RefMatcher()
+    gs, gi = rm.grid_csr(kb, bounds)
+    rng = np.random.default_rng(5)
+    aq = np.zeros(64, [("x", "f4"), ("y", "f4"), ("r", "f4"), ("min_level", "i4"), ("max_level", "i4")])
+    aq["x"], aq["y"] = rng.uniform(-30, 430, 64), rng.uniform(-30, 330, 64)
+    aq["r"] = rng.choice([3, 15, 40, 100], 64)
+    aq["min_level"], aq["max_level"] = rng.choice([-1, 0, 2, 4], 64), rng.choice([-1, 1, 3, 7], 64)
+    area = [rm.features_in_area(kb, bounds, float(a["x"]), float(a["y"]), float(a["r"]), int(a["min_level"]), int(a["max_level"]))
+            for a in aq]
+    area_kf = [rm.features_in_area(kb, bounds, float(a["x"]), float(a["y"]), float(a["r"]), keyframe=True) for a in aq]
+    np.savez_compressed(os.path.join(OUT, "matcher_vectors.npz"), ka=ka, da=da, kb=kb, db=db, bounds=np.array(bounds),
+                        init_n=n, init_m12=m12, init_prev=p, grid_start=gs, grid_idx=gi,
+                        area_queries=aq, area_start=np.cumsum([0] + [len(a) for a in area]), area_idx=np.concatenate(area),
+                        area_kf_start=np.cumsum([0] + [len(a) for a in area_kf]), area_kf_idx=np.concatenate(area_kf),
+                        bf_q=q, bf_qa=qa, bf_t=t, bf_ta=ta, bf_n=bn, bf_best=best, bf_second=second, bf_idx=idx, bf_m12=bm12,
+                        pinned_by="grid CSR and area queries: reference (oracle/_ref/libmatch_ref.so = the text of Frame.cc:574-589, "
+                                  "671-736 and KeyFrame.cc:1138-1177 compiled in place); init_*: equal to the reference's "
+                                  "SearchForInitialization case in matcher_ref_vectors.npz; bf_*: oracle (brute force has no reference "
+                                  "function of its own: DescriptorDistance + the accept rules of ORBmatcher.cc:432-512)")
+    print("matcher vectors: init", n, "bruteforce", bn, "grid members", len(gi), "area hits", sum(len(a) for a in area))
+    # ---- matcher vectors from the reference's own ORBmatcher.cc
     r1, r2 = rm.frame(ka, da, bounds), rm.frame(kb, db, bounds)
     save = {}
     for c in CASES:
