@@ -97,7 +97,9 @@ int orbx_stage_times(orbx_handle h, double* ms3);
  * the closest right descriptor on its row band, refined by the 11x11 SAD search and the parabola fit on the pyramid
  * level of the left keypoint, then the 1.5*1.4*median SAD filter.  The pyramids are read in place from frame
  * `left_frame` / `right_frame` of the LAST extract call of the two handles (same device, same image size and ctor
- * arguments; the host call waits for the right handle's stream).  keys_* are mvKeys / mvKeysRight (not undistorted),
+ * arguments; the host call waits for the right handle's stream).  Only that call's frames are resident: an index
+ * past its frame count is ORB_ERR_INVALID, and of a call with more frames than max_batch only the last max_batch-sized
+ * part is (frame 0 = the first frame of that part).  keys_* are mvKeys / mvKeysRight (not undistorted),
  * mb = baseline in metres, mbf = baseline * fx.  u_right[n_left], depth[n_left]: mvuRight, mvDepth (-1 = no match).
  * Where the reference has undefined behaviour the result is defined: a search window that leaves the level image is
  * no match (cv::Mat::colRange would assert), and with no match at all the median filter is skipped.                */

@@ -311,6 +311,9 @@ inline int ORBmatcher::Fuse(KeyFrame* pKF, const std::vector<MapPoint*>& vpMapPo
     for (size_t i = 0; i < vpMapPoints.size(); ++i) {
         if (!q[i].valid || bestIdx[i] < 0 || bestDist[i] > TH_LOW) continue;
         MapPoint* pMP = vpMapPoints[i];
+        // the reference tests these at the top of every iteration (:849), i.e. AFTER the Replace / AddMapPoint of earlier
+        // iterations: a repeated pointer, or a point an earlier Replace made bad, is skipped
+        if (pMP->isBad() || pMP->IsInKeyFrame(pKF)) continue;
         MapPoint* pMPinKF = pKF->GetMapPoint(bestIdx[i]);
         if (pMPinKF) {                                            // :949-958
             if (!pMPinKF->isBad()) {
@@ -357,6 +360,7 @@ inline int ORBmatcher::Fuse(KeyFrame* pKF, cv::Mat Scw, const std::vector<MapPoi
     int nFused = 0;
     for (size_t i = 0; i < vpPoints.size(); ++i) {
         if (!q[i].valid || bestIdx[i] < 0 || bestDist[i] > TH_LOW) continue;
+        if (vpPoints[i]->isBad()) continue;                       // re-evaluated per iteration as the reference does (:1005)
         MapPoint* pMPinKF = pKF->GetMapPoint(bestIdx[i]);
         if (pMPinKF) {                                            // :1082-1086
             if (!pMPinKF->isBad()) vpReplacePoint[i] = pMPinKF;

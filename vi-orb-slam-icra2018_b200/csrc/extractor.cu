@@ -60,7 +60,8 @@ struct orbx_extractor {
     DevBuf pyr, blur, slots, cellCount, sel, selCount, keyWs, dCells, dTiles, dTabOfs, dTabCoef, dFastMaps, dFastScratch, dFastCounters;
     DevBuf dImages, dKps, dDesc, dCount;
     DevBuf stKeysL, stDescL, stKeysR, stDescR, stOut;   // staging of orbx_compute_stereo_matches
-    int lastFrames = 0, lastCapacity = 0;
+    int lastFrames = 0, lastCapacity = 0;   // arena capacity in frames / caller capacity of the last call
+    int residentFrames = 0;                 // frames of the last call whose pyramids are in the arena (slots 0 .. residentFrames-1)
     int launches = 0;
     double stageMs[3] = {0, 0, 0};
     bool timed = false;
@@ -252,6 +253,7 @@ int enqueue(orbx_extractor* e, const uint8_t* dImages, int nFrames, int w, int h
         P.keyWs += (size_t)frameBase * P.keyWsFrameEntries;
     }
     e->lastCapacity = capacity;
+    e->residentFrames = frameBase + nFrames;   // extract_batch's chunks fill the arena front to back
     e->timed = timed;
     cudaEvent_t* pe = nullptr;
     if (e->profiling && e->profCalls < 4096) {
@@ -516,7 +518,6 @@ int orbx_extract_batch(orbx_handle e, const uint8_t* images, int nFrames, int w,
             }
     }
     for (auto& ev : tev) cudaEventDestroy(ev);
-    e->lastFrames = std::max(e->lastFrames, 1);
     return status;
 }
 
@@ -532,8 +533,10 @@ static int stereo_params(orbx_extractor* l, int frameL, orbx_extractor* r, int f
     if (l->curW <= 0 || r->curW <= 0) return fail(ORB_ERR_INVALID, "%s: extract first (no pyramid yet)", who);
     if (l->curW != r->curW || l->curH != r->curH || l->nlevels != r->nlevels || l->scaleFactor != r->scaleFactor)
         return fail(ORB_ERR_INVALID, "%s: left and right extractor differ in image size, levels or scale factor", who);
-    if (frameL < 0 || frameL >= l->lastFrames || frameR < 0 || frameR >= r->lastFrames)
-        return fail(ORB_ERR_INVALID, "%s: frame index outside the last batch", who);
+    // only the frames of the last extraction call are resident (of a call larger than max_batch: its last max_batch-sized part)
+    if (frameL < 0 || frameL >= l->residentFrames || frameR < 0 || frameR >= r->residentFrames)
+        return fail(ORB_ERR_INVALID, "%s: frame index outside the last batch (%d / %d frames resident)", who, l->residentFrames,
+                    r->residentFrames);
     if (!(mb > 0.0f) || !(mbf > 0.0f)) return fail(ORB_ERR_INVALID, "%s: baseline mb and mbf must be positive", who);
     const ExtractParams& P = l->P;
     S->pyrL = P.pyr + (size_t)frameL * P.pyrFrameBytes;
@@ -642,11 +645,13 @@ int orbx_get_scale_tables(orbx_handle e, float* sf, float* inv, float* s2, float
 int orbx_get_level(orbx_handle e, int frame, int level, uint8_t* out, int* w, int* hgt) {
     ORBX_ENTER(e);
     if (e->curW < 0) return fail(ORB_ERR_INVALID, "orbx_get_level: no image processed yet");
-    if (level < 0 || level >= e->nlevels || frame < 0 || frame >= e->lastFrames) return fail(ORB_ERR_INVALID, "orbx_get_level: bad frame/level");
+    if (level < 0 || level >= e->nlevels || frame < 0 || frame >= std::max(e->residentFrames, 1))
+        return fail(ORB_ERR_INVALID, "orbx_get_level: bad frame/level (%d frames resident)", e->residentFrames);
     const LevelGeom& L = e->P.lv[level];
     if (w) *w = L.w;
     if (hgt) *hgt = L.h;
     if (!out) return ORB_OK;
+    if (frame >= e->residentFrames) return fail(ORB_ERR_INVALID, "orbx_get_level: frame %d is not resident (%d are)", frame, e->residentFrames);
     ORB_CUDA(cudaStreamSynchronize(e->stream));
     const unsigned char* src = e->P.pyr + (size_t)frame * e->P.pyrFrameBytes + L.pyrOff + (kPadLeft - kEdge);
     ORB_CUDA(cudaMemcpy2D(out, L.w + 2 * kEdge, src, L.pitch, L.w + 2 * kEdge, L.h + 2 * kEdge, cudaMemcpyDeviceToHost));
@@ -661,7 +666,7 @@ int orbx_stage_times(orbx_handle e, double* ms3) {
 
 int orbx_debug_candidates(orbx_handle e, int frame, int level, orb_keypoint* out, int cap, int* n) {
     ORBX_ENTER(e);
-    if (e->curW < 0 || level < 0 || level >= e->nlevels || frame < 0 || frame >= e->lastFrames || !n)
+    if (e->curW < 0 || level < 0 || level >= e->nlevels || frame < 0 || frame >= e->residentFrames || !n)
         return fail(ORB_ERR_INVALID, "orbx_debug_candidates: bad arguments");
     const LevelGeom& L = e->P.lv[level];
     ORB_CUDA(cudaStreamSynchronize(e->stream));
@@ -689,7 +694,7 @@ int orbx_debug_candidates(orbx_handle e, int frame, int level, orb_keypoint* out
 
 int orbx_debug_blurred(orbx_handle e, int frame, int level, uint8_t* out) {
     ORBX_ENTER(e);
-    if (e->curW < 0 || level < 0 || level >= e->nlevels || frame < 0 || frame >= e->lastFrames || !out)
+    if (e->curW < 0 || level < 0 || level >= e->nlevels || frame < 0 || frame >= e->residentFrames || !out)
         return fail(ORB_ERR_INVALID, "orbx_debug_blurred: bad arguments");
     const LevelGeom& L = e->P.lv[level];
     ORB_CUDA(cudaStreamSynchronize(e->stream));

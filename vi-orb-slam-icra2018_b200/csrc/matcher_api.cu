@@ -87,6 +87,7 @@ int orbm_bruteforce(orbm_handle h, const uint8_t* q, const float* qa, int nq, co
                     int nPairs, float ratio, int checkOri, int* best, int* second, int* idx, int* m12, int* nmatches) {
     ORBM_ENTER(h);
     if (nq < 0 || nt < 0 || nPairs < 0) return fail(ORB_ERR_INVALID, "orbm_bruteforce: negative size");
+    if (nPairs > 0 && !nmatches) return fail(ORB_ERR_INVALID, "orbm_bruteforce: null nmatches");
     if (nq == 0 || nPairs == 0) {
         for (int p = 0; p < nPairs; ++p) nmatches[p] = 0;
         return ORB_OK;

@@ -293,7 +293,9 @@ __global__ void proj_queries_kernel(FrameDev cur, const orbm_proj_query* __restr
     a.active = p.valid != 0;
     if (p.u < cur.minX || p.u > cur.maxX) a.active = 0;   // ORBmatcher.cc:1390-1393
     if (p.v < cur.minY || p.v > cur.maxY) a.active = 0;
-    const int o = p.octave;
+    // a skipped query (valid == 0) may carry any octave: the header says the flag gates the whole entry, so the scale
+    // table is only indexed for active ones (the host has range-checked those)
+    const int o = a.active ? p.octave : 0;
     a.r = __fmul_rn(th, sf[o]);                           // :1398
     if (mode == 1) { a.minLevel = o; a.maxLevel = -1; }   // forward  (:1409)
     else if (mode == 2) { a.minLevel = 0; a.maxLevel = o; }   // backward (:1411)
@@ -313,9 +315,10 @@ __global__ void point_queries_kernel(const orbm_point_query* __restrict__ pq, in
     float r = ((double)p.view_cos > 0.998) ? 2.5f : 4.0f;   // RadiusByViewingCos, ORBmatcher.cc:131-137
     if (th != 1.0f) r = __fmul_rn(r, th);                    // bFactor (:49, 65-66)
     a.x = p.proj_x; a.y = p.proj_y;
-    a.r = __fmul_rn(r, sf[p.level]);
-    a.minLevel = p.level - 1; a.maxLevel = p.level;          // :69
     a.active = p.in_view != 0;
+    const int level = a.active ? p.level : 0;                // a skipped entry's level is not looked at (see above)
+    a.r = __fmul_rn(r, sf[level]);
+    a.minLevel = level - 1; a.maxLevel = level;              // :69
     a.stereoCenter = p.proj_xr; a.stereoTol = a.r;           // :94-99
     q[i] = a;
 }
