@@ -209,6 +209,33 @@ int orbm_search_by_projection_ex(orbm_handle h, orbm_frame cur, const float* sca
                                  const uint8_t* query_desc, int nq, float th, int mode, int max_distance,
                                  const uint8_t* occupied, int* cur_match, int check_orientation, int* nmatches);
 
+/* Batched forms: n independent searches in one call.  Every phase (query construction, candidate enumeration, the
+ * order-dependent bookkeeping with one CTA per job) runs once for the whole batch, so the call costs the launches and the
+ * one host synchronisation of a single search while the whole GPU works; each job's results are exactly those of the
+ * single call with the same arguments.  All frames must belong to matcher h.  *candidates (may be NULL) receives the number
+ * of (query, keypoint) pairs whose descriptors were compared.                                                       */
+typedef struct {
+    orbm_frame cur;                  /* CurrentFrame */
+    const orbm_proj_query* queries;  /* host, nq entries */
+    const uint8_t* query_desc;       /* host, nq x 32 */
+    int nq;
+    const float* u_right;            /* host, cur's mvuRight or NULL */
+    const uint8_t* occupied;         /* host, cur's occupancy flags or NULL */
+    int* cur_match;                  /* host out: cur's n entries */
+    int nmatches;                    /* out */
+} orbm_projection_job;
+int orbm_search_by_projection_batch(orbm_handle h, orbm_projection_job* jobs, int n_jobs, const float* scale_factors,
+                                    int nlevels, float mbf, float th, int mode, int max_distance, int check_orientation,
+                                    long long* candidates);
+typedef struct {
+    orbm_frame f1, f2;
+    float* prev_xy;                  /* host in/out: vbPrevMatched of f1 */
+    int* matches12;                  /* host out: f1's n entries */
+    int nmatches;                    /* out */
+} orbm_init_job;
+int orbm_search_for_initialization_batch(orbm_handle h, orbm_init_job* jobs, int n_jobs, int window_size, float nnratio,
+                                         int check_orientation, long long* candidates);
+
 typedef struct {
     float proj_x, proj_y, proj_xr;
     float view_cos;

@@ -258,3 +258,64 @@ def test_search_by_projection_keyframe_sim3_window(matcher, oracle, pair):
     n, match = matcher.search_by_projection(g, SF, q, da, 10.0, 3, occ, None, 0.0, False, max_distance=50)
     rn, rmatch = o.search_projection(SF, oq, da, 10.0, 3, occ, None, 0.0, False, max_distance=50)
     assert n == rn and np.array_equal(match, rmatch) and n > 50
+
+
+def _oq(q):
+    return q.view(np.dtype([(a, b) for a, b in zip(("u", "v", "invz", "octave", "valid", "obsPositive", "angle"),
+                                                   ("<f4", "<f4", "<f4", "<i4", "<i4", "<i4", "<f4"))]))
+
+
+def test_search_by_projection_batch(matcher, oracle, pair):
+    """orbm_search_by_projection_batch: 72 jobs of different sizes (two scenes, query subsets, with and without occupancy
+    / stereo, an empty query set) give exactly the results of 72 single searches -- checked against the oracle."""
+    rng = np.random.default_rng(606)
+    frames = {}
+    for name in ("kitti", "euroc"):
+        ka, da, kb, db, bounds = pair[name]
+        frames[name] = (ka, da, kb, db) + _frames(matcher, oracle, kb, db, bounds)
+    jobs, want = [], []
+    for j in range(72):
+        name = "kitti" if j % 3 else "euroc"
+        ka, da, kb, db, g, o = frames[name]
+        q = _proj_queries(rng, ka)
+        take = len(ka) if j % 5 else int(rng.integers(0, len(ka) // 2))        # j = 0: possibly empty
+        if j == 7:
+            take = 0
+        q, qd = q[:take].copy(), da[:take].copy()
+        occ = (rng.random(len(kb)) < 0.1).astype(np.uint8) if j % 2 else None
+        ur = None
+        if j % 4 == 1:
+            ur = np.where(rng.random(len(kb)) < 0.6, kb["x"] - 40.0 * rng.uniform(0.02, 0.5, len(kb)), -1).astype(np.float32)
+        jobs.append((g, q, qd, occ, ur))
+        want.append(o.search_projection(SF, _oq(q), qd, 15.0, 0, occ, ur, 40.0, True) if take else (0, np.full(len(kb), -1, np.int32)))
+    got, cand = matcher.search_by_projection_batch(jobs, SF, 15.0, mode=0, mbf=40.0, check_ori=True)
+    assert cand > 100000
+    for j, ((n, match), (rn, rmatch)) in enumerate(zip(got, want)):
+        assert n == rn, j
+        assert np.array_equal(match, rmatch), j
+    assert sum(n for n, _ in got) > 10000
+    # a batch of one is the single call
+    n1, m1 = matcher.search_by_projection(jobs[1][0], SF, jobs[1][1], jobs[1][2], 15.0, 0, jobs[1][3], jobs[1][4], 40.0, True)
+    assert n1 == got[1][0] and np.array_equal(m1, got[1][1])
+
+
+def test_search_for_initialization_batch(matcher, oracle, pair):
+    """orbm_search_for_initialization_batch over 64 frame pairs (both scenes, both directions, perturbed vbPrevMatched)."""
+    rng = np.random.default_rng(707)
+    pairs, want = [], []
+    fr = {}
+    for name in ("kitti", "euroc"):
+        ka, da, kb, db, bounds = pair[name]
+        fr[name] = (ka, kb) + _frames(matcher, oracle, ka, da, bounds) + _frames(matcher, oracle, kb, db, bounds)
+    for j in range(64):
+        ka, kb, g1, o1, g2, o2 = fr["kitti" if j % 2 else "euroc"]
+        if j % 4 >= 2:
+            ka, kb, g1, o1, g2, o2 = kb, ka, g2, o2, g1, o1
+        prev = (np.stack([ka["x"], ka["y"]], 1) + rng.normal(0, 4.0 * (j % 3), (len(ka), 2))).astype(np.float32)
+        pairs.append((g1, g2, prev))
+        want.append(o1.search_init(o2, prev, 100, 0.9, True))
+    got, cand = matcher.search_for_initialization_batch(pairs, 100, 0.9, True)
+    assert cand > 100000
+    for j, ((n, m12, p), (rn, rm12, rp)) in enumerate(zip(got, want)):
+        assert n == rn and np.array_equal(m12, rm12) and np.array_equal(p, rp), j
+    assert sum(n for n, _, _ in got) > 5000

@@ -234,11 +234,9 @@ __device__ __forceinline__ int warp_enumerate(const FrameDev& f, const AreaQuery
 
 // count (cand == nullptr) or fill the per-query candidate lists: (train index, distance) in reference order.
 // stereoInFill: the stereo filter is static, so it is applied here; the dynamic filters wait for phase 2.
-__global__ void __launch_bounds__(256)
-candidates_kernel(FrameDev f, const AreaQuery* __restrict__ queries, const uint4* __restrict__ qdesc, int nq,
-                  const float* __restrict__ uRight, int* __restrict__ counts, const int* __restrict__ offsets,
-                  int2* __restrict__ cand) {
-    const int qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+__device__ __forceinline__ void candidates_body(const FrameDev& f, const AreaQuery* __restrict__ queries, const uint4* __restrict__ qdesc,
+                                                int nq, const float* __restrict__ uRight, int* __restrict__ counts,
+                                                const int* __restrict__ offsets, int2* __restrict__ cand, int qi) {
     if (qi >= nq) return;
     const AreaQuery q = queries[qi];
     int n = 0;
@@ -256,6 +254,30 @@ candidates_kernel(FrameDev f, const AreaQuery* __restrict__ queries, const uint4
     if (!cand && (threadIdx.x & 31) == 0) counts[qi] = n;
 }
 
+__global__ void __launch_bounds__(256)
+candidates_kernel(FrameDev f, const AreaQuery* __restrict__ queries, const uint4* __restrict__ qdesc, int nq,
+                  const float* __restrict__ uRight, int* __restrict__ counts, const int* __restrict__ offsets,
+                  int2* __restrict__ cand) {
+    candidates_body(f, queries, qdesc, nq, uRight, counts, offsets, cand, blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));
+}
+
+// Batched searches: job j's queries are entries [qBase, qBase + nq) of ONE concatenated AreaQuery / counts / offsets array,
+// so the whole batch shares a single scan and a single candidate buffer (offsets are global positions in it).
+struct CandJob {
+    FrameDev f;              // frame whose grid is searched
+    const uint4* qdesc;      // the job's query descriptors
+    const float* uRight;     // or nullptr
+    int nq, qBase;
+};
+
+__global__ void __launch_bounds__(256)
+candidates_batch_kernel(const CandJob* __restrict__ jobs, const AreaQuery* __restrict__ queries, int* __restrict__ counts,
+                        const int* __restrict__ offsets, int2* __restrict__ cand) {
+    const CandJob& j = jobs[blockIdx.y];
+    candidates_body(j.f, queries + j.qBase, j.qdesc, j.nq, j.uRight, counts ? counts + j.qBase : nullptr,
+                    offsets ? offsets + j.qBase : nullptr, cand, blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));
+}
+
 // GetFeaturesInArea as an API of its own (tests, adapter)
 __global__ void __launch_bounds__(256)
 area_kernel(FrameDev f, const float* __restrict__ xyr, int nq, int minLevel, int maxLevel, int* __restrict__ idxOut,
@@ -271,23 +293,23 @@ area_kernel(FrameDev f, const float* __restrict__ xyr, int nq, int minLevel, int
 }
 
 // ------------------------------------------------------------------------------------------------ query builders
-__global__ void init_queries_kernel(FrameDev f1, const float* __restrict__ prevXY, int window, AreaQuery* __restrict__ q) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= f1.n) return;
+__device__ __forceinline__ AreaQuery init_query(const FrameDev& f1, const float* __restrict__ prevXY, int window, int i) {
     AreaQuery a;
     const int level1 = f1.keys[i].octave;
     a.x = prevXY[2 * i]; a.y = prevXY[2 * i + 1]; a.r = (float)window;
     a.minLevel = level1; a.maxLevel = level1;
     a.active = level1 > 0 ? 0 : 1;                        // ORBmatcher.cc:421-423
     a.stereoCenter = 0; a.stereoTol = 0;
-    q[i] = a;
+    return a;
 }
 
-__global__ void proj_queries_kernel(FrameDev cur, const orbm_proj_query* __restrict__ pq, int nq,
-                                    const float* __restrict__ sf, float th, int mode, float mbf, AreaQuery* __restrict__ q) {
+__global__ void init_queries_kernel(FrameDev f1, const float* __restrict__ prevXY, int window, AreaQuery* __restrict__ q) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nq) return;
-    const orbm_proj_query p = pq[i];
+    if (i < f1.n) q[i] = init_query(f1, prevXY, window, i);
+}
+
+__device__ __forceinline__ AreaQuery proj_query(const FrameDev& cur, const orbm_proj_query& p, const float* __restrict__ sf, float th,
+                                                int mode, float mbf) {
     AreaQuery a;
     a.x = p.u; a.y = p.v;
     a.active = p.valid != 0;
@@ -303,7 +325,13 @@ __global__ void proj_queries_kernel(FrameDev cur, const orbm_proj_query* __restr
     else { a.minLevel = o - 1; a.maxLevel = o + 1; }      // :1413
     a.stereoCenter = __fsub_rn(p.u, __fmul_rn(mbf, p.invz));   // :1435
     a.stereoTol = a.r;
-    q[i] = a;
+    return a;
+}
+
+__global__ void proj_queries_kernel(FrameDev cur, const orbm_proj_query* __restrict__ pq, int nq,
+                                    const float* __restrict__ sf, float th, int mode, float mbf, AreaQuery* __restrict__ q) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nq) q[i] = proj_query(cur, pq[i], sf, th, mode, mbf);
 }
 
 __global__ void point_queries_kernel(const orbm_point_query* __restrict__ pq, int nq, const float* __restrict__ sf, float th,
@@ -489,10 +517,9 @@ __device__ __forceinline__ void replay_queries(const AreaQuery* __restrict__ q, 
 }
 
 // SearchForInitialization replay (ORBmatcher.cc:417-517). m21 / vMatchedDistance in shared memory.
-__global__ void __launch_bounds__(RP_THREADS)
-init_replay_kernel(FrameDev f1, FrameDev f2, const AreaQuery* __restrict__ q, const int* __restrict__ offsets,
-                   const int2* __restrict__ cand, float ratio, int checkOri, float* prevXY, int* m12, int* pushA,
-                   int* pushB, int* nmatchesOut) {
+__device__ __forceinline__ void init_replay_body(const FrameDev& f1, const FrameDev& f2, const AreaQuery* __restrict__ q,
+                                                 const int* __restrict__ offsets, const int2* __restrict__ cand, float ratio,
+                                                 int checkOri, float* prevXY, int* m12, int* pushA, int* pushB, int* nmatchesOut) {
     extern __shared__ int dyn[];
     int* m21 = dyn + kReplayFixedInts;
     int* matchedDist = m21 + f2.n;
@@ -533,12 +560,41 @@ init_replay_kernel(FrameDev f1, FrameDev f2, const AreaQuery* __restrict__ q, co
         }
 }
 
+__global__ void __launch_bounds__(RP_THREADS)
+init_replay_kernel(FrameDev f1, FrameDev f2, const AreaQuery* __restrict__ q, const int* __restrict__ offsets,
+                   const int2* __restrict__ cand, float ratio, int checkOri, float* prevXY, int* m12, int* pushA,
+                   int* pushB, int* nmatchesOut) {
+    init_replay_body(f1, f2, q, offsets, cand, ratio, checkOri, prevXY, m12, pushA, pushB, nmatchesOut);
+}
+
+struct InitJob {           // one frame pair of orbm_search_for_initialization_batch (all pointers device memory)
+    FrameDev f1, f2;
+    float* prevXY;
+    int* m12;
+    int* pushA;
+    int* pushB;
+    int* nmatchesOut;
+    int qBase;
+};
+__global__ void __launch_bounds__(RP_THREADS)
+init_queries_batch_kernel(const InitJob* __restrict__ jobs, int window, AreaQuery* __restrict__ q) {
+    const InitJob& j = jobs[blockIdx.y];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < j.f1.n) q[j.qBase + i] = init_query(j.f1, j.prevXY, window, i);
+}
+__global__ void __launch_bounds__(RP_THREADS)
+init_replay_batch_kernel(const InitJob* __restrict__ jobs, const AreaQuery* __restrict__ q, const int* __restrict__ offsets,
+                         const int2* __restrict__ cand, float ratio, int checkOri) {
+    const InitJob j = jobs[blockIdx.x];
+    init_replay_body(j.f1, j.f2, q + j.qBase, offsets + j.qBase, cand, ratio, checkOri, j.prevXY, j.m12, j.pushA, j.pushB, j.nmatchesOut);
+}
+
 // SearchByProjection(Frame, Frame) replay (ORBmatcher.cc:1363-1495), also the relocalisation overload (:1500-1627, where
 // the acceptance threshold is ORBdist instead of TH_HIGH). Occupancy flags in shared memory.
-__global__ void __launch_bounds__(RP_THREADS)
-proj_replay_kernel(FrameDev cur, const AreaQuery* __restrict__ q, const orbm_proj_query* __restrict__ pq, int nq,
-                   const int* __restrict__ offsets, const int2* __restrict__ cand, int checkOri, int maxDist,
-                   const unsigned char* __restrict__ occIn, int* curMatch, int* pushA, int* pushB, int* nmatchesOut) {
+__device__ __forceinline__ void proj_replay_body(const FrameDev& cur, const AreaQuery* __restrict__ q, const orbm_proj_query* __restrict__ pq,
+                                                 int nq, const int* __restrict__ offsets, const int2* __restrict__ cand, int checkOri,
+                                                 int maxDist, const unsigned char* __restrict__ occIn, int* curMatch, int* pushA,
+                                                 int* pushB, int* nmatchesOut) {
     extern __shared__ int dyn[];
     int* stamp = dyn + kReplayFixedInts;
     unsigned char* occ = reinterpret_cast<unsigned char*>(stamp + 2 * cur.n);
@@ -565,6 +621,37 @@ proj_replay_kernel(FrameDev cur, const AreaQuery* __restrict__ q, const orbm_pro
         histogram_prune(pushA, pushB, pushB, nPush, hist, curMatch, false, &nmatches,
                         [&](int i) { return pq[i].angle; }, [&](int i2) { return cur.keys[i2].angle; });
     if (tid == 0) *nmatchesOut = nmatches;
+}
+
+__global__ void __launch_bounds__(RP_THREADS)
+proj_replay_kernel(FrameDev cur, const AreaQuery* __restrict__ q, const orbm_proj_query* __restrict__ pq, int nq,
+                   const int* __restrict__ offsets, const int2* __restrict__ cand, int checkOri, int maxDist,
+                   const unsigned char* __restrict__ occIn, int* curMatch, int* pushA, int* pushB, int* nmatchesOut) {
+    proj_replay_body(cur, q, pq, nq, offsets, cand, checkOri, maxDist, occIn, curMatch, pushA, pushB, nmatchesOut);
+}
+
+struct ProjJob {           // one (current frame, query set) of orbm_search_by_projection_batch (all pointers device memory)
+    FrameDev cur;
+    const orbm_proj_query* pq;
+    const unsigned char* occIn;
+    int* curMatch;
+    int* pushA;
+    int* pushB;
+    int* nmatchesOut;
+    int nq, qBase;
+};
+__global__ void proj_queries_batch_kernel(const ProjJob* __restrict__ jobs, const float* __restrict__ sf, float th, int mode, float mbf,
+                                          AreaQuery* __restrict__ q) {
+    const ProjJob& j = jobs[blockIdx.y];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < j.nq) q[j.qBase + i] = proj_query(j.cur, j.pq[i], sf, th, mode, mbf);
+}
+__global__ void __launch_bounds__(RP_THREADS)
+proj_replay_batch_kernel(const ProjJob* __restrict__ jobs, const AreaQuery* __restrict__ q, const int* __restrict__ offsets,
+                         const int2* __restrict__ cand, int checkOri, int maxDist) {
+    const ProjJob j = jobs[blockIdx.x];
+    proj_replay_body(j.cur, q + j.qBase, j.pq, j.nq, offsets + j.qBase, cand, checkOri, maxDist, j.occIn, j.curMatch, j.pushA, j.pushB,
+                     j.nmatchesOut);
 }
 
 // SearchByProjection(Frame, MapPoints) replay (ORBmatcher.cc:51-126).
@@ -1176,6 +1263,241 @@ int orbm_search_by_projection_ex(orbm_handle h, orbm_frame cur, const float* sf,
     ORB_CUDA(cudaMemcpyAsync(curMatch, h->out0.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
     ORB_CUDA(cudaMemcpyAsync(nmatches, h->out3.p, 4, cudaMemcpyDeviceToHost, st));
     ORB_CUDA(cudaStreamSynchronize(st));
+    return ORB_OK;
+}
+
+// ---- batched windowed searches: n independent jobs share ONE pass of every phase (query build, candidate count, scan,
+// candidate fill, replay with one CTA per job), so a batch costs the launches and the single host synchronisation of one
+// search while all 148 SMs work (the single-pair calls keep one CTA busy).  Results are those of n single calls.
+namespace {
+
+// phase 1 for a whole batch whose AreaQuery array (nqAll entries) is in h->ws0 and whose CandJob table is at dJobs
+int run_candidates_batch(orbm_matcher* h, const CandJob* dJobs, int nJobs, int maxNq, int nqAll, int* totalOut) {
+    cudaStream_t st = h->stream;
+    ORB_CHECK(h->out4.reserve((size_t)(nqAll + 1) * 4));
+    ORB_CHECK(h->ws1.reserve((size_t)(nqAll + 2) * 4));
+    int* counts = h->out4.as<int>();
+    int* offsets = h->ws1.as<int>();
+    const int wpb = 8;
+    const dim3 grid(ceil_div(maxNq, wpb), nJobs);
+    candidates_batch_kernel<<<grid, wpb * 32, 0, st>>>(dJobs, h->ws0.as<AreaQuery>(), counts, nullptr, nullptr);
+    scan_kernel<<<1, 1024, 0, st>>>(counts, offsets, nqAll);
+    int total = 0;
+    ORB_CUDA(cudaMemcpyAsync(&total, offsets + nqAll, 4, cudaMemcpyDeviceToHost, st));
+    ORB_CUDA(cudaStreamSynchronize(st));
+    ORB_CHECK(h->ws2.reserve((size_t)(total + 1) * sizeof(int2)));
+    candidates_batch_kernel<<<grid, wpb * 32, 0, st>>>(dJobs, h->ws0.as<AreaQuery>(), nullptr, offsets, h->ws2.as<int2>());
+    h->launches += 3;
+    ORB_CUDA(cudaGetLastError());
+    *totalOut = total;
+    return ORB_OK;
+}
+
+}  // namespace
+
+int orbm_search_by_projection_batch(orbm_handle h, orbm_projection_job* jobs, int nJobs, const float* sf, int nlevels, float mbf,
+                                    float th, int mode, int maxDist, int checkOri, long long* candidatesOut) {
+    ORBM_ENTER(h);
+    if (nJobs < 0 || (nJobs > 0 && !jobs) || !sf || nlevels < 1) return fail(ORB_ERR_INVALID, "orbm_search_by_projection_batch: bad arguments");
+    if (candidatesOut) *candidatesOut = 0;
+    if (nJobs > 65535) return fail(ORB_ERR_INVALID, "orbm_search_by_projection_batch: at most 65535 jobs per call");
+    size_t nqAll = 0, nCurAll = 0;
+    int maxNq = 0, maxN = 0;
+    bool anyRight = false;
+    for (int j = 0; j < nJobs; ++j) {
+        orbm_projection_job& J = jobs[j];
+        if (!J.cur || !J.cur_match || J.nq < 0 || (J.nq > 0 && (!J.queries || !J.query_desc)))
+            return fail(ORB_ERR_INVALID, "orbm_search_by_projection_batch: job %d has bad arguments", j);
+        if (J.cur->m != h) return fail(ORB_ERR_INVALID, "orbm_search_by_projection_batch: job %d: frame belongs to another matcher", j);
+        for (int i = 0; i < J.nq; ++i)
+            if (J.queries[i].valid && (J.queries[i].octave < 0 || J.queries[i].octave >= nlevels))
+                return fail(ORB_ERR_INVALID, "orbm_search_by_projection_batch: job %d query %d has octave %d outside 0..%d", j, i,
+                            J.queries[i].octave, nlevels - 1);
+        J.nmatches = 0;
+        for (int i = 0; i < J.cur->n; ++i) J.cur_match[i] = -1;
+        nqAll += (size_t)J.nq;
+        nCurAll += (size_t)J.cur->n;
+        maxNq = std::max(maxNq, J.nq);
+        maxN = std::max(maxN, J.cur->n);
+        anyRight = anyRight || J.u_right;
+    }
+    if (nqAll == 0 || nCurAll == 0) return ORB_OK;
+    if (nqAll > (size_t)1 << 30) return fail(ORB_ERR_INVALID, "orbm_search_by_projection_batch: too many queries in one call");
+    if (9 * (size_t)maxN + 32 > kReplaySmemMax) return fail(ORB_ERR_CAPACITY, "orbm_search_by_projection_batch: %d keypoints exceed the replay state", maxN);
+    cudaStream_t st = h->stream;
+    // concatenated inputs
+    std::vector<orbm_proj_query> hq(nqAll);
+    std::vector<uint8_t> hd(nqAll * 32), hocc(nCurAll, 0);
+    std::vector<float> hur(anyRight ? nCurAll : 0, -1.0f);
+    {
+        size_t qo = 0, co = 0;
+        for (int j = 0; j < nJobs; ++j) {
+            const orbm_projection_job& J = jobs[j];
+            if (J.nq) {
+                std::memcpy(&hq[qo], J.queries, (size_t)J.nq * sizeof(orbm_proj_query));
+                std::memcpy(&hd[qo * 32], J.query_desc, (size_t)J.nq * 32);
+            }
+            if (J.occupied && J.cur->n) std::memcpy(&hocc[co], J.occupied, (size_t)J.cur->n);
+            if (J.u_right && J.cur->n) std::memcpy(&hur[co], J.u_right, (size_t)J.cur->n * 4);
+            qo += (size_t)J.nq;
+            co += (size_t)J.cur->n;
+        }
+    }
+    ORB_CHECK(upload(h->in0, hq.data(), nqAll * sizeof(orbm_proj_query), st));
+    ORB_CHECK(upload(h->in1, hd.data(), nqAll * 32, st));
+    ORB_CHECK(upload(h->in2, sf, (size_t)nlevels * 4, st));
+    if (anyRight) ORB_CHECK(upload(h->in3, hur.data(), nCurAll * 4, st));
+    ORB_CHECK(upload(h->in4, hocc.data(), nCurAll, st));
+    ORB_CHECK(h->ws0.reserve(nqAll * sizeof(AreaQuery)));
+    ORB_CHECK(h->out0.reserve((nCurAll + 1) * 4));
+    ORB_CHECK(h->out2.reserve((nqAll + (size_t)nJobs) * 4 * 2));
+    ORB_CHECK(h->out3.reserve((size_t)nJobs * 4 + 16));
+    // job tables
+    std::vector<ProjJob> pj(nJobs);
+    std::vector<CandJob> cj(nJobs);
+    {
+        size_t qo = 0, co = 0;
+        for (int j = 0; j < nJobs; ++j) {
+            const orbm_projection_job& J = jobs[j];
+            ProjJob& P = pj[j];
+            P.cur = J.cur->dev();
+            P.pq = h->in0.as<orbm_proj_query>() + qo;
+            P.occIn = h->in4.as<unsigned char>() + co;
+            P.curMatch = h->out0.as<int>() + co;
+            P.pushA = h->out2.as<int>() + 2 * (qo + j);
+            P.pushB = P.pushA + J.nq + 1;
+            P.nmatchesOut = h->out3.as<int>() + j;
+            P.nq = J.nq;
+            P.qBase = (int)qo;
+            CandJob& C = cj[j];
+            C.f = P.cur;
+            C.qdesc = h->in1.as<uint4>() + 2 * qo;
+            C.uRight = (anyRight && J.u_right) ? h->in3.as<float>() + co : nullptr;
+            C.nq = J.nq;
+            C.qBase = (int)qo;
+            qo += (size_t)J.nq;
+            co += (size_t)J.cur->n;
+        }
+    }
+    ORB_CHECK(h->in5.reserve((size_t)nJobs * (sizeof(ProjJob) + sizeof(CandJob)) + 64));
+    ProjJob* dPj = h->in5.as<ProjJob>();
+    CandJob* dCj = reinterpret_cast<CandJob*>(dPj + nJobs);
+    ORB_CUDA(cudaMemcpyAsync(dPj, pj.data(), (size_t)nJobs * sizeof(ProjJob), cudaMemcpyHostToDevice, st));
+    ORB_CUDA(cudaMemcpyAsync(dCj, cj.data(), (size_t)nJobs * sizeof(CandJob), cudaMemcpyHostToDevice, st));
+    proj_queries_batch_kernel<<<dim3(ceil_div(maxNq, 256), nJobs), 256, 0, st>>>(dPj, h->in2.as<float>(), th, mode, mbf, h->ws0.as<AreaQuery>());
+    h->launches += 1;
+    int total = 0;
+    ORB_CHECK(run_candidates_batch(h, dCj, nJobs, maxNq, (int)nqAll, &total));
+    if (candidatesOut) *candidatesOut = total;
+    ORB_CUDA(cudaFuncSetAttribute(proj_replay_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kReplayFixed + kReplaySmemMax)));
+    proj_replay_batch_kernel<<<nJobs, RP_THREADS, kReplayFixed + 9 * (size_t)maxN + 32, st>>>(dPj, h->ws0.as<AreaQuery>(), h->ws1.as<int>(), h->ws2.as<int2>(),
+                                                                                      checkOri, maxDist);
+    h->launches += 1;
+    ORB_CUDA(cudaGetLastError());
+    std::vector<int> hm(nCurAll), hn(nJobs);
+    ORB_CUDA(cudaMemcpyAsync(hm.data(), h->out0.p, nCurAll * 4, cudaMemcpyDeviceToHost, st));
+    ORB_CUDA(cudaMemcpyAsync(hn.data(), h->out3.p, (size_t)nJobs * 4, cudaMemcpyDeviceToHost, st));
+    ORB_CUDA(cudaStreamSynchronize(st));
+    size_t co = 0;
+    for (int j = 0; j < nJobs; ++j) {
+        orbm_projection_job& J = jobs[j];
+        if (J.nq > 0 && J.cur->n > 0) {
+            std::memcpy(J.cur_match, &hm[co], (size_t)J.cur->n * 4);
+            J.nmatches = hn[j];
+        }
+        co += (size_t)J.cur->n;
+    }
+    return ORB_OK;
+}
+
+int orbm_search_for_initialization_batch(orbm_handle h, orbm_init_job* jobs, int nJobs, int windowSize, float ratio, int checkOri,
+                                         long long* candidatesOut) {
+    ORBM_ENTER(h);
+    if (nJobs < 0 || (nJobs > 0 && !jobs)) return fail(ORB_ERR_INVALID, "orbm_search_for_initialization_batch: bad arguments");
+    if (candidatesOut) *candidatesOut = 0;
+    if (nJobs > 65535) return fail(ORB_ERR_INVALID, "orbm_search_for_initialization_batch: at most 65535 jobs per call");
+    size_t n1All = 0;
+    int maxN1 = 0, maxN2 = 0;
+    for (int j = 0; j < nJobs; ++j) {
+        orbm_init_job& J = jobs[j];
+        if (!J.f1 || !J.f2 || !J.prev_xy || !J.matches12) return fail(ORB_ERR_INVALID, "orbm_search_for_initialization_batch: job %d has a null argument", j);
+        if (J.f1->m != h || J.f2->m != h) return fail(ORB_ERR_INVALID, "orbm_search_for_initialization_batch: job %d: frame belongs to another matcher", j);
+        J.nmatches = 0;
+        n1All += (size_t)J.f1->n;
+        maxN1 = std::max(maxN1, J.f1->n);
+        maxN2 = std::max(maxN2, J.f2->n);
+    }
+    if (n1All == 0) return ORB_OK;
+    const size_t replaySmem = (size_t)std::max(maxN2, 1) * 16 + 16;
+    if (replaySmem > kReplaySmemMax) return fail(ORB_ERR_CAPACITY, "orbm_search_for_initialization_batch: %d keypoints exceed the replay state", maxN2);
+    cudaStream_t st = h->stream;
+    std::vector<float> hprev(n1All * 2);
+    {
+        size_t o = 0;
+        for (int j = 0; j < nJobs; ++j) {
+            if (jobs[j].f1->n) std::memcpy(&hprev[o * 2], jobs[j].prev_xy, (size_t)jobs[j].f1->n * 8);
+            o += (size_t)jobs[j].f1->n;
+        }
+    }
+    ORB_CHECK(upload(h->in0, hprev.data(), n1All * 8, st));
+    ORB_CHECK(h->ws0.reserve(n1All * sizeof(AreaQuery)));
+    ORB_CHECK(h->out0.reserve((n1All + 1) * 4));
+    ORB_CHECK(h->out2.reserve((n1All + (size_t)nJobs) * 4 * 2));
+    ORB_CHECK(h->out3.reserve((size_t)nJobs * 4 + 16));
+    std::vector<InitJob> ij(nJobs);
+    std::vector<CandJob> cj(nJobs);
+    {
+        size_t o = 0;
+        for (int j = 0; j < nJobs; ++j) {
+            const orbm_init_job& J = jobs[j];
+            InitJob& I = ij[j];
+            I.f1 = J.f1->dev();
+            I.f2 = J.f2->dev();
+            I.prevXY = h->in0.as<float>() + 2 * o;
+            I.m12 = h->out0.as<int>() + o;
+            I.pushA = h->out2.as<int>() + 2 * (o + j);
+            I.pushB = I.pushA + J.f1->n + 1;
+            I.nmatchesOut = h->out3.as<int>() + j;
+            I.qBase = (int)o;
+            CandJob& C = cj[j];
+            C.f = I.f2;
+            C.qdesc = I.f1.desc;
+            C.uRight = nullptr;
+            C.nq = J.f1->n;
+            C.qBase = (int)o;
+            o += (size_t)J.f1->n;
+        }
+    }
+    ORB_CHECK(h->in5.reserve((size_t)nJobs * (sizeof(InitJob) + sizeof(CandJob)) + 64));
+    InitJob* dIj = h->in5.as<InitJob>();
+    CandJob* dCj = reinterpret_cast<CandJob*>(dIj + nJobs);
+    ORB_CUDA(cudaMemcpyAsync(dIj, ij.data(), (size_t)nJobs * sizeof(InitJob), cudaMemcpyHostToDevice, st));
+    ORB_CUDA(cudaMemcpyAsync(dCj, cj.data(), (size_t)nJobs * sizeof(CandJob), cudaMemcpyHostToDevice, st));
+    init_queries_batch_kernel<<<dim3(ceil_div(maxN1, RP_THREADS), nJobs), RP_THREADS, 0, st>>>(dIj, windowSize, h->ws0.as<AreaQuery>());
+    h->launches += 1;
+    int total = 0;
+    ORB_CHECK(run_candidates_batch(h, dCj, nJobs, maxN1, (int)n1All, &total));
+    if (candidatesOut) *candidatesOut = total;
+    ORB_CUDA(cudaFuncSetAttribute(init_replay_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kReplayFixed + kReplaySmemMax)));
+    init_replay_batch_kernel<<<nJobs, RP_THREADS, kReplayFixed + replaySmem, st>>>(dIj, h->ws0.as<AreaQuery>(), h->ws1.as<int>(), h->ws2.as<int2>(), ratio,
+                                                                               checkOri);
+    h->launches += 1;
+    ORB_CUDA(cudaGetLastError());
+    std::vector<int> hm(n1All), hn(nJobs);
+    ORB_CUDA(cudaMemcpyAsync(hm.data(), h->out0.p, n1All * 4, cudaMemcpyDeviceToHost, st));
+    ORB_CUDA(cudaMemcpyAsync(hprev.data(), h->in0.p, n1All * 8, cudaMemcpyDeviceToHost, st));
+    ORB_CUDA(cudaMemcpyAsync(hn.data(), h->out3.p, (size_t)nJobs * 4, cudaMemcpyDeviceToHost, st));
+    ORB_CUDA(cudaStreamSynchronize(st));
+    size_t o = 0;
+    for (int j = 0; j < nJobs; ++j) {
+        orbm_init_job& J = jobs[j];
+        if (J.f1->n) {
+            std::memcpy(J.matches12, &hm[o], (size_t)J.f1->n * 4);
+            std::memcpy(J.prev_xy, &hprev[o * 2], (size_t)J.f1->n * 8);
+        }
+        J.nmatches = hn[j];
+        o += (size_t)J.f1->n;
+    }
     return ORB_OK;
 }
 

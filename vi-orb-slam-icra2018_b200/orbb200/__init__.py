@@ -404,6 +404,43 @@ class Matcher:
                                                      int(check_ori), C.byref(n)))
         return n.value, m12, prev
 
+    def search_for_initialization_batch(self, pairs, window=100, ratio=0.9, check_ori=True):
+        """pairs: [(f1, f2, prev_xy)]; returns ([(n, matches12, prev_xy)], candidate compares) -- orbm_search_for_initialization_batch"""
+        jobs = (_abi.InitJob * len(pairs))()
+        keep = []
+        for j, (f1, f2, prev_xy) in enumerate(pairs):
+            prev = np.ascontiguousarray(prev_xy, np.float32).copy()
+            m12 = np.empty(f1.n, np.int32)
+            keep.append((prev, m12))
+            jobs[j].f1, jobs[j].f2 = f1.f, f2.f
+            jobs[j].prev_xy, jobs[j].matches12 = prev.ctypes.data, m12.ctypes.data
+        cand = C.c_longlong()
+        _check(self.L.orbm_search_for_initialization_batch(self.h, jobs, len(pairs), window, C.c_float(ratio), int(check_ori),
+                                                           C.byref(cand)))
+        return [(jobs[j].nmatches, keep[j][1], keep[j][0]) for j in range(len(pairs))], cand.value
+
+    def search_by_projection_batch(self, jobs_in, scale_factors, th, mode=0, mbf=0.0, check_ori=True, max_distance=100):
+        """jobs_in: [(cur, queries, qdesc, occupied or None, u_right or None)]; returns ([(n, cur_match)], candidate
+        compares) -- orbm_search_by_projection_batch"""
+        sf = np.ascontiguousarray(scale_factors, np.float32)
+        jobs = (_abi.ProjectionJob * len(jobs_in))()
+        keep = []
+        for j, (cur, queries, qdesc, occupied, u_right) in enumerate(jobs_in):
+            q = np.ascontiguousarray(queries, PROJ_QUERY_DTYPE)
+            qd = np.ascontiguousarray(qdesc, np.uint8)
+            occ = None if occupied is None else np.ascontiguousarray(occupied, np.uint8)
+            ur = None if u_right is None else np.ascontiguousarray(u_right, np.float32)
+            match = np.empty(cur.n, np.int32)
+            keep.append((q, qd, occ, ur, match))
+            jobs[j].cur, jobs[j].queries, jobs[j].query_desc, jobs[j].nq = cur.f, q.ctypes.data, qd.ctypes.data, len(q)
+            jobs[j].u_right = None if ur is None else ur.ctypes.data
+            jobs[j].occupied = None if occ is None else occ.ctypes.data
+            jobs[j].cur_match = match.ctypes.data
+        cand = C.c_longlong()
+        _check(self.L.orbm_search_by_projection_batch(self.h, jobs, len(jobs_in), _p(sf), len(sf), C.c_float(mbf), C.c_float(th), mode,
+                                                      max_distance, int(check_ori), C.byref(cand)))
+        return [(jobs[j].nmatches, keep[j][4]) for j in range(len(jobs_in))], cand.value
+
     def search_by_projection(self, cur, scale_factors, queries, qdesc, th, mode=0, occupied=None, u_right=None,
                              mbf=0.0, check_ori=True, max_distance=100):
         sf = np.ascontiguousarray(scale_factors, np.float32)

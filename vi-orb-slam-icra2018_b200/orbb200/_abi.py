@@ -45,6 +45,8 @@ SIGNATURES = {
     "orbm_search_for_initialization": (i32, [vp, vp, vp, vp, vp, i32, f32, i32, vp]),
     "orbm_search_by_projection": (i32, [vp, vp, vp, i32, vp, f32, vp, vp, i32, f32, i32, vp, vp, i32, vp]),
     "orbm_search_by_projection_ex": (i32, [vp, vp, vp, i32, vp, f32, vp, vp, i32, f32, i32, i32, vp, vp, i32, vp]),
+    "orbm_search_by_projection_batch": (i32, [vp, vp, i32, vp, i32, f32, f32, i32, i32, i32, vp]),
+    "orbm_search_for_initialization_batch": (i32, [vp, vp, i32, i32, f32, i32, vp]),
     "orbm_search_by_projection_points": (i32, [vp, vp, vp, i32, vp, vp, vp, i32, f32, f32, vp, vp, vp]),
     "orbm_search_for_triangulation": (i32, [vp, vp, vp, i32, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, f32, f32,
                                             vp, vp, i32, i32, i32, vp, vp]),
@@ -79,3 +81,12 @@ def declare(lib):
         fn.restype = res
         fn.argtypes = args
     return missing
+
+
+class ProjectionJob(C.Structure):      # orbm_projection_job
+    _fields_ = [("cur", vp), ("queries", vp), ("query_desc", vp), ("nq", i32), ("u_right", vp), ("occupied", vp),
+                ("cur_match", vp), ("nmatches", i32)]
+
+
+class InitJob(C.Structure):            # orbm_init_job
+    _fields_ = [("f1", vp), ("f2", vp), ("prev_xy", vp), ("matches12", vp), ("nmatches", i32)]
