@@ -474,6 +474,87 @@ def allpairs_leg(orbb200, dist, world, rank, local, dev, stream, barrier, max_ov
     return out
 
 
+def kitti_leg(orbb200, rank, local, dev, stream, barrier, max_over_ranks, steps, hbm):
+    """configs[1]: KITTI-shaped 1241x376 frames, ORBextractor(2000, 1.2, 8, 20, 7): extraction throughput of a device-resident
+    batch with its own HBM roofline, and windowed SearchByProjection (th = 15, mono) as a batch of frame pairs through
+    orbm_search_by_projection_batch (host query arrays in, host matches out: the call a tracker would make for a batch)."""
+    import numpy as np
+    import torch
+    from orbb200.synth import synth_frames_torch, shifted_pair
+    w, h, nfeat, nb = 1241, 376, 2000, 1024
+    out = {}
+    d_img = torch.cat([synth_frames_torch(min(128, nb - i), w, h, seed=5000 + 1000 * rank + i, device=dev) for i in range(0, nb, 128)])
+    ex = orbb200.Extractor(nfeat, SCALE, NLEVELS, INI_TH, MIN_TH, max_width=w, max_height=h, max_batch=nb, device=local)
+    cap = ex.capacity
+    d_kps = torch.empty((nb, cap, 7), dtype=torch.int32, device=dev)
+    d_desc = torch.empty((nb, cap, 32), dtype=torch.uint8, device=dev)
+    d_n = torch.empty(nb, dtype=torch.int32, device=dev)
+    for _ in range(3):
+        ex.extract_batch_device(d_img, d_kps, d_desc, d_n, stream=stream.cuda_stream)
+    stream.synchronize()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        ex.extract_batch_device(d_img, d_kps, d_desc, d_n, stream=stream.cuda_stream)
+    e1.record(stream)
+    stream.synchronize()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1)) / steps
+    nkp = float(d_n.float().mean().item())
+    alg = algorithmic_bytes(w, h, nkp)
+    fps = nb / (ms * 1e-3)
+    out["extraction"] = {"workload": "batch of %d synthetic KITTI 1241x376 frames per GPU, ORBextractor(2000,1.2,8,20,7), device resident" % nb,
+                         "value_per_gpu": fps, "unit": "frames/s", "ms_per_step": ms, "keypoints_per_frame": nkp,
+                         "roofline": {"bound": "hbm", "algorithmic_bytes_per_frame": alg["total"], "achieved_gbs": alg["total"] * fps / 1e9,
+                                      "peak": hbm, "frac": alg["total"] * fps / 1e9 / hbm}}
+    ex.close()
+    del d_img, d_kps, d_desc
+    # ---- SearchByProjection on 64 distinct frame pairs (shifted scenes), the batch repeated 4 x = 256 jobs per call
+    m = orbb200.Matcher(local)
+    exs = orbb200.Extractor(nfeat, SCALE, NLEVELS, INI_TH, MIN_TH, max_width=w, max_height=h, max_batch=2, device=local)
+    sf = np.array([1.2 ** i for i in range(8)], np.float32)
+    bounds = (0.0, 0.0, float(w), float(h))
+    jobs, keep = [], []
+    for k in range(64):
+        a, b = shifted_pair(100 + 64 * rank + k, w, h)
+        (ka, da), (kb, db) = exs.extract_batch(np.stack([a, b]))
+        f2 = m.frame(kb, db, bounds)
+        q = np.zeros(len(ka), orbb200.PROJ_QUERY_DTYPE)
+        q["u"], q["v"], q["invz"], q["octave"], q["valid"], q["obs_positive"], q["angle"] = \
+            ka["x"] + 7, ka["y"] + 3, 0.1, ka["octave"], 1, 1, ka["angle"]
+        keep.append(f2)
+        jobs.append((f2, q, da, None, None))
+    jobs = jobs * 4
+    res, cand = m.search_by_projection_batch(jobs, sf, 15.0, mode=0, mbf=0.0, check_ori=True)
+    n1, m1 = m.search_by_projection(jobs[5][0], sf, jobs[5][1], jobs[5][2], 15.0, 0, None, None, 0.0, True)
+    same = bool(n1 == res[5][0] and np.array_equal(m1, res[5][1]))
+    barrier()
+    t0 = time.perf_counter()
+    reps = max(2, steps // 2)
+    for _ in range(reps):
+        res, cand = m.search_by_projection_batch(jobs, sf, 15.0, mode=0, mbf=0.0, check_ori=True)
+    barrier()
+    dt = max_over_ranks(time.perf_counter() - t0) / reps
+    nq = sum(len(j[1]) for j in jobs)
+    out["search_by_projection"] = {"workload": "%d frame pairs per call (64 distinct, 2000 features each), th = 15, mono, rotation check; host query "
+                                               "arrays in, host matches out" % len(jobs),
+                                   "pairs_per_s_per_gpu": len(jobs) / dt, "queries_per_s_per_gpu": nq / dt,
+                                   "candidate_compares_per_s_per_gpu": cand / dt, "candidates_per_query": cand / max(nq, 1),
+                                   "ms_per_call": dt * 1e3, "matches_per_pair": float(np.mean([r[0] for r in res])),
+                                   "gpu_launches_per_call": m.launch_count(), "batch_equals_single_call": same,
+                                   "single_call_ms": None}
+    t0 = time.perf_counter()
+    for k in range(16):
+        m.search_by_projection(jobs[k][0], sf, jobs[k][1], jobs[k][2], 15.0, 0, None, None, 0.0, True)
+    out["search_by_projection"]["single_call_ms"] = (time.perf_counter() - t0) / 16 * 1e3
+    for f in keep:
+        f.close()
+    exs.close()
+    m.close()
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -512,6 +593,7 @@ def main():
     ap.add_argument("--no-hamming", action="store_true")
     ap.add_argument("--no-latency", action="store_true", help="skip the single-frame latency leg")
     ap.add_argument("--no-allpairs", action="store_true", help="skip the configs[4] all-pairs leg")
+    ap.add_argument("--no-kitti", action="store_true", help="skip the configs[1] KITTI extraction + batched search leg")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -752,6 +834,14 @@ def main():
         ap_line = allpairs_leg(orbb200, dist, world, rank, local, dev, stream, barrier, max_over_ranks, max(2, K // 5))
         if rank == 0:
             line["allpairs"] = ap_line
+
+    # ---- configs[1]: KITTI-shaped extraction + batched windowed SearchByProjection
+    if not args.no_kitti:
+        kl = kitti_leg(orbb200, rank, local, dev, stream, barrier, max_over_ranks, K,
+                       float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0))
+                       if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0)
+        if rank == 0:
+            line["kitti"] = kl
 
     # ---- single-frame latency of configs[0] / configs[1] through the host C ABI (what a live SLAM loop sees)
     if rank == 0 and world == 1 and not args.no_latency:

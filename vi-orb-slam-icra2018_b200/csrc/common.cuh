@@ -62,6 +62,28 @@ struct DevBuf {
     template <class T> T* as() const { return (T*)p; }
 };
 
+// growable page-locked host staging (batched host entry points: one memcpy into it, one full-rate H2D out of it)
+struct PinnedBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return ORB_OK;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        ORB_CUDA(cudaHostAlloc(&p, want, cudaHostAllocDefault));
+        cap = want;
+        return ORB_OK;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T> T* as() const { return (T*)p; }
+};
+
 constexpr int kEdge = 19;         // EDGE_THRESHOLD, ORBextractor.cc:76
 constexpr int kHalfPatch = 15;    // HALF_PATCH_SIZE
 constexpr int kPatch = 31;        // PATCH_SIZE

@@ -31,7 +31,8 @@ struct orbm_matcher {
     int device = 0;
     cudaStream_t stream = nullptr;
     int launches = 0;
-    orbb::DevBuf in0, in1, in2, in3, in4, in5, out0, out1, out2, out3, out4, ws0, ws1, ws2;
+    orbb::DevBuf in0, in1, in2, in3, in4, in5, out0, out1, out2, out3, out4, ws0, ws1, ws2, ws3;
+    orbb::PinnedBuf pin0, pin1, pin2, pin3, pin4;   // staging of the batched searches
 };
 
 // Prologue of every matcher entry point: null check, device selection for the duration of the call, launch counter reset.

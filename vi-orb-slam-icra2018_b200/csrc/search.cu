@@ -80,6 +80,61 @@ __global__ void __launch_bounds__(1024) scan_kernel(const int* in, int* out, int
     if (threadIdx.x == 0) out[n] = carry;
 }
 
+// exclusive scan of a long array in three launches (the batched searches scan the candidate counts of all jobs at once:
+// 512 k entries took 0.53 ms in the one-block kernel above): per-block sums, scan of the sums, per-block scan + offset
+constexpr int kScanTile = 4096;      // entries per block (1024 threads x 4)
+__global__ void __launch_bounds__(1024) scan_tile_sums_kernel(const int* __restrict__ in, int n, int* __restrict__ sums) {
+    __shared__ int warpSums[32];
+    const int base = blockIdx.x * kScanTile;
+    int v = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int i = base + k * 1024 + threadIdx.x;
+        if (i < n) v += in[i];
+    }
+    v = __reduce_add_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31) == 0) warpSums[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const int t = __reduce_add_sync(0xffffffffu, warpSums[threadIdx.x]);
+        if (threadIdx.x == 0) sums[blockIdx.x] = t;
+    }
+}
+__global__ void __launch_bounds__(1024) scan_tiles_kernel(const int* __restrict__ in, int n, const int* __restrict__ tileOffsets,
+                                                           int* __restrict__ out) {
+    __shared__ int warpSums[32];
+    const int base = blockIdx.x * kScanTile + threadIdx.x * 4;     // 4 consecutive entries per thread
+    int v[4], t = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { v[k] = base + k < n ? in[base + k] : 0; t += v[k]; }
+    int incl = t;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((threadIdx.x & 31) >= o) incl += u;
+    }
+    if ((threadIdx.x & 31) == 31) warpSums[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const int w = warpSums[threadIdx.x];
+        int wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, wi, o);
+            if ((int)threadIdx.x >= o) wi += u;
+        }
+        warpSums[threadIdx.x] = wi - w;
+    }
+    __syncthreads();
+    int run = tileOffsets[blockIdx.x] + warpSums[threadIdx.x >> 5] + incl - t;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (base + k < n) out[base + k] = run;
+        run += v[k];
+    }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 1023) out[n] = run;   // total (entries past n are zeros)
+}
+
 __global__ void grid_fill_kernel(int n, const int* cellOf, const int* cellStart, int* cursor, int* cellIdx) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -1281,7 +1336,14 @@ int run_candidates_batch(orbm_matcher* h, const CandJob* dJobs, int nJobs, int m
     const int wpb = 8;
     const dim3 grid(ceil_div(maxNq, wpb), nJobs);
     candidates_batch_kernel<<<grid, wpb * 32, 0, st>>>(dJobs, h->ws0.as<AreaQuery>(), counts, nullptr, nullptr);
-    scan_kernel<<<1, 1024, 0, st>>>(counts, offsets, nqAll);
+    const int tiles = ceil_div(nqAll, kScanTile);
+    ORB_CHECK(h->ws3.reserve((size_t)(2 * tiles + 2) * 4));
+    int* tileSums = h->ws3.as<int>();
+    int* tileOffsets = tileSums + tiles;
+    scan_tile_sums_kernel<<<tiles, 1024, 0, st>>>(counts, nqAll, tileSums);
+    scan_kernel<<<1, 1024, 0, st>>>(tileSums, tileOffsets, tiles);
+    scan_tiles_kernel<<<tiles, 1024, 0, st>>>(counts, nqAll, tileOffsets, offsets);
+    h->launches += 2;
     int total = 0;
     ORB_CUDA(cudaMemcpyAsync(&total, offsets + nqAll, 4, cudaMemcpyDeviceToHost, st));
     ORB_CUDA(cudaStreamSynchronize(st));
@@ -1314,7 +1376,7 @@ int orbm_search_by_projection_batch(orbm_handle h, orbm_projection_job* jobs, in
                 return fail(ORB_ERR_INVALID, "orbm_search_by_projection_batch: job %d query %d has octave %d outside 0..%d", j, i,
                             J.queries[i].octave, nlevels - 1);
         J.nmatches = 0;
-        for (int i = 0; i < J.cur->n; ++i) J.cur_match[i] = -1;
+        if (J.nq == 0) std::fill(J.cur_match, J.cur_match + J.cur->n, -1);   // a job that runs overwrites all of it
         nqAll += (size_t)J.nq;
         nCurAll += (size_t)J.cur->n;
         maxNq = std::max(maxNq, J.nq);
@@ -1325,10 +1387,15 @@ int orbm_search_by_projection_batch(orbm_handle h, orbm_projection_job* jobs, in
     if (nqAll > (size_t)1 << 30) return fail(ORB_ERR_INVALID, "orbm_search_by_projection_batch: too many queries in one call");
     if (9 * (size_t)maxN + 32 > kReplaySmemMax) return fail(ORB_ERR_CAPACITY, "orbm_search_by_projection_batch: %d keypoints exceed the replay state", maxN);
     cudaStream_t st = h->stream;
-    // concatenated inputs
-    std::vector<orbm_proj_query> hq(nqAll);
-    std::vector<uint8_t> hd(nqAll * 32), hocc(nCurAll, 0);
-    std::vector<float> hur(anyRight ? nCurAll : 0, -1.0f);
+    // inputs concatenated in page-locked staging (kept by the handle): one memcpy per array and job, one full-rate H2D each
+    ORB_CHECK(h->pin0.reserve(nqAll * sizeof(orbm_proj_query)));
+    ORB_CHECK(h->pin1.reserve(nqAll * 32));
+    ORB_CHECK(h->pin2.reserve(nCurAll));
+    if (anyRight) ORB_CHECK(h->pin3.reserve(nCurAll * 4));
+    orbm_proj_query* hq = h->pin0.as<orbm_proj_query>();
+    uint8_t* hd = h->pin1.as<uint8_t>();
+    uint8_t* hocc = h->pin2.as<uint8_t>();
+    float* hur = h->pin3.as<float>();
     {
         size_t qo = 0, co = 0;
         for (int j = 0; j < nJobs; ++j) {
@@ -1337,17 +1404,23 @@ int orbm_search_by_projection_batch(orbm_handle h, orbm_projection_job* jobs, in
                 std::memcpy(&hq[qo], J.queries, (size_t)J.nq * sizeof(orbm_proj_query));
                 std::memcpy(&hd[qo * 32], J.query_desc, (size_t)J.nq * 32);
             }
-            if (J.occupied && J.cur->n) std::memcpy(&hocc[co], J.occupied, (size_t)J.cur->n);
-            if (J.u_right && J.cur->n) std::memcpy(&hur[co], J.u_right, (size_t)J.cur->n * 4);
+            if (J.cur->n) {
+                if (J.occupied) std::memcpy(&hocc[co], J.occupied, (size_t)J.cur->n);
+                else std::memset(&hocc[co], 0, (size_t)J.cur->n);
+                if (anyRight) {
+                    if (J.u_right) std::memcpy(&hur[co], J.u_right, (size_t)J.cur->n * 4);
+                    else std::fill(hur + co, hur + co + J.cur->n, -1.0f);
+                }
+            }
             qo += (size_t)J.nq;
             co += (size_t)J.cur->n;
         }
     }
-    ORB_CHECK(upload(h->in0, hq.data(), nqAll * sizeof(orbm_proj_query), st));
-    ORB_CHECK(upload(h->in1, hd.data(), nqAll * 32, st));
+    ORB_CHECK(upload(h->in0, hq, nqAll * sizeof(orbm_proj_query), st));
+    ORB_CHECK(upload(h->in1, hd, nqAll * 32, st));
     ORB_CHECK(upload(h->in2, sf, (size_t)nlevels * 4, st));
-    if (anyRight) ORB_CHECK(upload(h->in3, hur.data(), nCurAll * 4, st));
-    ORB_CHECK(upload(h->in4, hocc.data(), nCurAll, st));
+    if (anyRight) ORB_CHECK(upload(h->in3, hur, nCurAll * 4, st));
+    ORB_CHECK(upload(h->in4, hocc, nCurAll, st));
     ORB_CHECK(h->ws0.reserve(nqAll * sizeof(AreaQuery)));
     ORB_CHECK(h->out0.reserve((nCurAll + 1) * 4));
     ORB_CHECK(h->out2.reserve((nqAll + (size_t)nJobs) * 4 * 2));
@@ -1394,9 +1467,11 @@ int orbm_search_by_projection_batch(orbm_handle h, orbm_projection_job* jobs, in
                                                                                       checkOri, maxDist);
     h->launches += 1;
     ORB_CUDA(cudaGetLastError());
-    std::vector<int> hm(nCurAll), hn(nJobs);
-    ORB_CUDA(cudaMemcpyAsync(hm.data(), h->out0.p, nCurAll * 4, cudaMemcpyDeviceToHost, st));
-    ORB_CUDA(cudaMemcpyAsync(hn.data(), h->out3.p, (size_t)nJobs * 4, cudaMemcpyDeviceToHost, st));
+    ORB_CHECK(h->pin4.reserve((nCurAll + (size_t)nJobs) * 4));
+    int* hm = h->pin4.as<int>();
+    int* hn = hm + nCurAll;
+    ORB_CUDA(cudaMemcpyAsync(hm, h->out0.p, nCurAll * 4, cudaMemcpyDeviceToHost, st));
+    ORB_CUDA(cudaMemcpyAsync(hn, h->out3.p, (size_t)nJobs * 4, cudaMemcpyDeviceToHost, st));
     ORB_CUDA(cudaStreamSynchronize(st));
     size_t co = 0;
     for (int j = 0; j < nJobs; ++j) {
