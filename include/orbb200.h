@@ -89,8 +89,10 @@ int orbx_get_scale_tables(orbx_handle h, float* scale_factors, float* inv_scale_
 /* mvImagePyramid[level] of frame `frame` of the last call (ORBextractor.h:103): the padded (w+38)x(h+38) buffer is
  * copied to `out` (may be NULL to query the size); *w,*h are the level size without the 19-px frame.           */
 int orbx_get_level(orbx_handle h, int frame, int level, uint8_t* out, int* w, int* hgt);
-/* GetTimeOfComputePyramid / ...KeyPointsOctTree / ...Descriptor (ORBextractor.h:51-53), milliseconds of the last
- * host call measured with CUDA events on the handle's stream.                                                  */
+/* GetTimeOfComputePyramid / ...KeyPointsOctTree / ...Descriptor (ORBextractor.h:51-53), milliseconds measured with CUDA
+ * events on the handle's stream.  Host calls of up to 4 frames replay a captured CUDA graph from their second call of an
+ * image size on (events cannot be read out of a graph): they leave the times of the last un-captured call in place;
+ * ORBB_NO_GRAPH=1 in the environment keeps every call un-captured.                                                */
 int orbx_stage_times(orbx_handle h, double* ms3);
 
 /* Frame::ComputeStereoMatches (Frame.cc:810-984), the one consumer of the padded mvImagePyramid: for every left keypoint
