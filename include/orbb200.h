@@ -211,6 +211,32 @@ int orbm_search_by_projection_ex(orbm_handle h, orbm_frame cur, const float* sca
                                  const uint8_t* query_desc, int nq, float th, int mode, int max_distance,
                                  const uint8_t* occupied, int* cur_match, int check_orientation, int* nmatches);
 
+/* The same search with the projection of ORBmatcher.cc:1376-1393 done on the device: the caller hands over world points
+ * and the current pose instead of projected coordinates (no per-point host loop, no cv::Mat temporaries).  The arithmetic
+ * is the reference's: x3Dc = Rcw * x3Dw + tcw as OpenCV's CV_32F 3x3 . 3x1 + 3x1 gemm evaluates it (products summed in
+ * float in source order, addend joined in double, one rounding), invzc = 1.0 / z in double, u = fx * xc * invzc + cx in
+ * float.  mode as above: the caller derives it from tlc = Rlw * twc + tlw against CurrentFrame.mb (:1361-1364).      */
+typedef struct {
+    float x, y, z;         /* pMP->GetWorldPos() */
+    int32_t octave;        /* LastFrame.mvKeys[i].octave */
+    int32_t valid;         /* pMP && !LastFrame.mvbOutlier[i] */
+    int32_t obs_positive;  /* pMP->Observations() > 0 */
+    float angle;           /* LastFrame.mvKeysUn[i].angle */
+} orbm_world_query;
+typedef struct {
+    float Rcw[9];          /* CurrentFrame.mTcw.rowRange(0,3).colRange(0,3), row-major */
+    float tcw[3];          /* CurrentFrame.mTcw.rowRange(0,3).col(3) */
+    float fx, fy, cx, cy;  /* CurrentFrame.fx .. cy */
+} orbm_pose;
+int orbm_search_by_projection_world(orbm_handle h, orbm_frame cur, const float* scale_factors, int nlevels,
+                                    const float* u_right, float mbf, const orbm_pose* pose,
+                                    const orbm_world_query* queries, const uint8_t* query_desc, int nq, float th, int mode,
+                                    int max_distance, const uint8_t* occupied, int* cur_match, int check_orientation,
+                                    int* nmatches);
+
+/* The projection alone (ORBmatcher.cc:1376-1388): u, v, invz of n world points (xyz: n x 3 floats) in the given pose. */
+int orbm_project_points(orbm_handle h, const orbm_pose* pose, const float* xyz, int n, float* u, float* v, float* invz);
+
 /* Batched forms: n independent searches in one call.  Every phase (query construction, candidate enumeration, the
  * order-dependent bookkeeping with one CTA per job) runs once for the whole batch, so the call costs the launches and the
  * one host synchronisation of a single search while the whole GPU works; each job's results are exactly those of the

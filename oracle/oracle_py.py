@@ -17,6 +17,8 @@ assert KP_DTYPE.itemsize == 28
 
 PROJ_QUERY_DTYPE = np.dtype([("u", "<f4"), ("v", "<f4"), ("invz", "<f4"), ("octave", "<i4"), ("valid", "<i4"),
                              ("obsPositive", "<i4"), ("angle", "<f4")])
+WORLD_QUERY_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("octave", "<i4"), ("valid", "<i4"),
+                              ("obsPositive", "<i4"), ("angle", "<f4")])
 MP_QUERY_DTYPE = np.dtype([("projX", "<f4"), ("projY", "<f4"), ("projXR", "<f4"), ("viewCos", "<f4"),
                            ("level", "<i4"), ("inView", "<i4"), ("obsPositive", "<i4")])
 
@@ -385,6 +387,20 @@ class OracleFrame:
         n = self.lib.orbo_search_projection_ex(self.h, _p(sf), _p(ur), mbf, _p(q), _p(qd), len(q), th, mode, max_distance,
                                                _p(occ), _p(match), int(check_ori))
         return n, match
+
+    def search_projection_world(self, scale_factors, Rcw, tcw, K4, queries, qdesc, th, mode=0, occupied=None, u_right=None,
+                                mbf=0.0, check_ori=True, max_distance=100):
+        """ORBmatcher.cc:1341-1498 from world points: project (:1376-1393, match_oracle.cpp::project_points; the image
+        bounds test is the search's own), then the windowed search."""
+        wq = np.ascontiguousarray(queries, WORLD_QUERY_DTYPE)
+        xyz = np.stack([wq["x"], wq["y"], wq["z"]], axis=1)
+        big = np.array([-np.inf, -np.inf, np.inf, np.inf], np.float32)
+        u, v, iz, _ = self.o.project(Rcw, tcw, K4, big, xyz)
+        q = np.zeros(len(wq), PROJ_QUERY_DTYPE)
+        q["u"], q["v"], q["invz"] = u, v, iz
+        q["octave"], q["obsPositive"], q["angle"] = wq["octave"], wq["obsPositive"], wq["angle"]
+        q["valid"] = (wq["valid"] != 0) & ~(iz < 0)
+        return self.search_projection(scale_factors, q, qdesc, th, mode, occupied, u_right, mbf, check_ori, max_distance)
 
     def search_points(self, scale_factors, queries, qdesc, th, ratio, occupied=None, u_right=None):
         sf = np.ascontiguousarray(scale_factors, np.float32)

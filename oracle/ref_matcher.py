@@ -7,7 +7,7 @@ import subprocess
 
 import numpy as np
 
-from oracle_py import KP_DTYPE, MP_QUERY_DTYPE, PROJ_QUERY_DTYPE
+from oracle_py import KP_DTYPE, MP_QUERY_DTYPE, PROJ_QUERY_DTYPE, WORLD_QUERY_DTYPE
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "_ref", "libmatch_ref.so")
@@ -58,6 +58,7 @@ class RefMatcher:
         L.refm_search_points.argtypes = [vp, vp, i32, vp, vp, vp, i32, f32, f32, vp, vp]
         L.refm_search_triangulation.argtypes = ([vp, vp] + [i32, vp, vp, vp] * 2 + [vp] * 5 + [f32, f32, vp, vp, i32, i32, i32, vp])
         L.refm_search_bow.argtypes = ([vp, vp] + [i32, vp, vp, vp] * 2 + [vp, vp, f32, i32, i32, vp, vp])
+        L.refm_search_projection_world.argtypes = [vp, vp, i32, vp, f32, vp, vp, vp, vp, i32, f32, i32, vp, vp, i32]
         L.refm_search_projection_kf.argtypes = [vp, vp, i32, vp, vp, i32, f32, i32, vp, vp, i32]
         L.refm_search_projection_sim3.argtypes = [vp, vp, i32, vp, vp, i32, i32, vp, vp]
         L.refm_fuse.argtypes = [vp, vp, vp, i32, vp, f32, vp, vp, i32, f32, i32, vp]
@@ -120,6 +121,22 @@ class RefFrame:
         n = self.lib.refm_search_projection(self.h, _p(sf), len(sf), _p(ur), mbf, _p(q), _p(qd), len(q), th, mode, _p(occ),
                                             _p(match), int(check_ori))
         assert n != -2, "refm_search_projection needs invz == 1"
+        return n, match
+
+    def search_projection_world(self, scale_factors, Rcw, tcw, K4, queries, qdesc, th, mode=0, occupied=None, u_right=None,
+                                mbf=0.0, check_ori=True):
+        """SearchByProjection(Current, Last, th, bMono) with world points, a real pose and intrinsics: the reference's own
+        projection lines (ORBmatcher.cc:1376-1393) run."""
+        sf = np.ascontiguousarray(scale_factors, np.float32)
+        q = np.ascontiguousarray(queries, WORLD_QUERY_DTYPE)
+        qd = np.ascontiguousarray(qdesc, np.uint8)
+        pose = np.concatenate([np.asarray(Rcw, np.float32).ravel(), np.asarray(tcw, np.float32).ravel()])
+        k4 = np.asarray(K4, np.float32)
+        occ = np.zeros(self.n, np.uint8) if occupied is None else np.ascontiguousarray(occupied, np.uint8)
+        ur = None if u_right is None else np.ascontiguousarray(u_right, np.float32)
+        match = np.empty(self.n, np.int32)
+        n = self.lib.refm_search_projection_world(self.h, _p(sf), len(sf), _p(ur), mbf, _p(pose), _p(k4), _p(q), _p(qd), len(q),
+                                                  th, mode, _p(occ), _p(match), int(check_ori))
         return n, match
 
     def search_points(self, scale_factors, queries, qdesc, th, ratio, occupied=None, u_right=None):

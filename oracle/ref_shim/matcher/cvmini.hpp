@@ -2,8 +2,10 @@
 // A minimal stand-in for the slice of the OpenCV C++ API that /root/reference/src/ORBmatcher.cc uses, so that the
 // reference's own file can be compiled IN PLACE (never copied) into oracle/_ref/libmatch_ref.so.  cv::Mat here is a
 // small dense matrix of either bytes (descriptor tables: row(), ptr<>) or floats (poses and points: * + - t() dot norm).
-// Float products accumulate in double and round once, as cv::gemm does for CV_32F; the pinned test cases only use
-// identity rotations and unit depths, where every rounding choice gives the same bits.
+// A * b (+ c) on 3x3 . 3x1 (+ 3x1) CV_32F operands -- every matrix product ORBmatcher.cc forms -- follows OpenCV's
+// small-matrix gemm: the expression template fuses the addend, the products are summed in float in source order and the
+// addend joins in double with one rounding (oracle/cvprims.cpp::gemm3_f32, pinned against cv2.gemm on 4000 poses in
+// tests/test_cvprims.py::test_gemm_3x3_projection).  Other shapes accumulate in double (not used by the pinned cases).
 #pragma once
 #include <cassert>
 #include <cmath>
@@ -91,17 +93,33 @@ private:
     std::shared_ptr<std::vector<uchar> > buf_;
 };
 
-inline Mat operator*(const Mat& a, const Mat& b) {
+inline Mat gemm_(const Mat& a, const Mat& b, const Mat* c) {
     assert(a.cols == b.rows);
     Mat m(a.rows, b.cols, CV_32F);
+    const bool small = a.rows == 3 && a.cols == 3 && b.cols == 1;
     for (int r = 0; r < a.rows; ++r)
-        for (int c = 0; c < b.cols; ++c) {
-            double s = 0;
-            for (int k = 0; k < a.cols; ++k) s += (double)a.at<float>(r, k) * (double)b.at<float>(k, c);
-            m.at<float>(r, c) = (float)s;
+        for (int col = 0; col < b.cols; ++col) {
+            if (small) {
+                const float t = (a.at<float>(r, 0) * b.at<float>(0, 0) + a.at<float>(r, 1) * b.at<float>(1, 0)) + a.at<float>(r, 2) * b.at<float>(2, 0);
+                m.at<float>(r, col) = c ? (float)((double)t + (double)c->at<float>(r, 0)) : t;
+            } else {
+                double s = 0;
+                for (int k = 0; k < a.cols; ++k) s += (double)a.at<float>(r, k) * (double)b.at<float>(k, col);
+                if (c) s += (double)c->at<float>(r, col);
+                m.at<float>(r, col) = (float)s;
+            }
         }
     return m;
 }
+// cv::MatExpr for the one fusion that matters: (A * b) + c is a single gemm
+struct MatMul {
+    Mat a, b;
+    operator Mat() const { return gemm_(a, b, nullptr); }
+    template <class T> T at(int i) const { return Mat(*this).at<T>(i); }
+};
+inline MatMul operator*(const Mat& a, const Mat& b) { return MatMul{a, b}; }
+inline MatMul operator*(const MatMul& m, const Mat& b) { return MatMul{Mat(m), b}; }
+inline Mat operator+(const MatMul& m, const Mat& c) { return gemm_(m.a, m.b, &c); }
 template <class F> inline Mat map2(const Mat& a, const Mat& b, F f) {
     Mat m(a.rows, a.cols, CV_32F);
     for (int r = 0; r < a.rows; ++r)

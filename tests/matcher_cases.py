@@ -27,7 +27,21 @@ def feature_vector(keys, dx, dy, cell=48):
 
 CASES = ["init_w100", "init_w30_noori", "init_ratio06", "proj_window", "proj_forward_stereo", "proj_backward_stereo",
          "points_th1", "points_th3", "tri_mono", "tri_only_stereo", "bow_kf_frame", "bow_kf_kf", "bow_kf_kf_noori",
-         "reloc_orbdist64", "reloc_orbdist100_noori", "loop_window", "fuse_mono", "fuse_stereo", "fuse_scw", "sim3"]
+         "reloc_orbdist64", "reloc_orbdist100_noori", "loop_window", "fuse_mono", "fuse_stereo", "fuse_scw", "sim3",
+         "projw_window", "projw_forward_stereo", "projw_backward_stereo"]
+WORLD = np.dtype([("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("octave", "<i4"), ("valid", "<i4"), ("obsPositive", "<i4"),
+                  ("angle", "<f4")])
+
+
+def camera_pose(rng):
+    """A non-trivial current pose (Rcw, tcw) in float32 and EuRoC-like intrinsics (fx, fy, cx, cy)."""
+    ax = rng.normal(0, 1, 3)
+    ax /= np.linalg.norm(ax)
+    ang = 0.35
+    Kx = np.array([[0, -ax[2], ax[1]], [ax[2], 0, -ax[0]], [-ax[1], ax[0], 0]])
+    R = np.eye(3) + np.sin(ang) * Kx + (1 - np.cos(ang)) * Kx @ Kx
+    t = np.array([0.31, -0.12, 0.57])
+    return R.astype(np.float32), t.astype(np.float32), np.array([458.654, 457.296, 367.215, 248.375], np.float32)
 BEST = np.dtype([("u", "<f4"), ("v", "<f4"), ("radius", "<f4"), ("ur", "<f4"), ("level", "<i4"), ("valid", "<i4")])
 TH_LOW, TH_HIGH = 50, 100
 
@@ -43,6 +57,32 @@ def run_case(name, f1, f2, ka, da, kb, db, shift=(7.0, 3.0)):
         n, m12, p = f1.search_init(f2, prev, window, ratio, ori)
         n_b, m12_b, p_b = f1.search_init(f2, p, window, ratio, ori)      # next frame: vbPrevMatched as updated
         return n, m12, p, n_b, m12_b, p_b
+    if name.startswith("projw"):
+        # SearchByProjection(Current, Last, th, bMono) from WORLD points through a real pose and intrinsics: the reference's
+        # own projection lines (:1376-1393) produce the window centres; points behind the camera and outside the image included
+        th, mode, stereo, ori = {"projw_window": (15.0, 0, False, True), "projw_forward_stereo": (7.0, 1, True, True),
+                                 "projw_backward_stereo": (15.0, 2, True, False)}[name]
+        R, t, K4 = camera_pose(rng)
+        u = ka["x"].astype(np.float64) + dx + rng.normal(0, 1.5, n1)
+        v = ka["y"].astype(np.float64) + dy + rng.normal(0, 1.5, n1)
+        z = rng.uniform(9.5, 10.5, n1)
+        z[3:40:4] *= -1                                    # behind the camera: invzc < 0
+        u[:3] = [-500, 1e4, 10]
+        v[:3] = [10, 10, -800]                             # outside the image bounds
+        xc = np.stack([(u - K4[2]) / K4[0] * z, (v - K4[3]) / K4[1] * z, z], 1)
+        xw = (xc - t.astype(np.float64)) @ R.astype(np.float64)          # R^T (xc - t)
+        q = np.zeros(n1, WORLD)
+        q["x"], q["y"], q["z"] = xw[:, 0], xw[:, 1], xw[:, 2]
+        q["octave"] = ka["octave"]
+        q["valid"] = rng.random(n1) < 0.8
+        q["obsPositive"] = rng.random(n1) < 0.9
+        q["angle"] = ka["angle"]
+        occ = (rng.random(n2) < 0.1).astype(np.uint8)
+        ur, mbf = None, 0.0
+        if stereo:
+            mbf = 40.0
+            ur = np.where(rng.random(n2) < 0.6, kb["x"] - mbf / 10.0 + rng.normal(0, th / 2, n2), -1).astype(np.float32)
+        return f2.search_projection_world(SF, R, t, K4, q, da, th, mode, occ, ur, mbf, ori)
     if name.startswith("proj"):
         th, mode, stereo, ori = {"proj_window": (15.0, 0, False, True), "proj_forward_stereo": (7.0, 1, True, True),
                                  "proj_backward_stereo": (15.0, 2, True, False)}[name]
@@ -183,6 +223,12 @@ class GpuFrame:
         import orbb200
         return self.m.search_by_projection(self.f, sf, q.view(orbb200.PROJ_QUERY_DTYPE), qdesc, th, mode, occupied, u_right,
                                            mbf, check_ori, max_distance)
+
+    def search_projection_world(self, sf, Rcw, tcw, K4, q, qdesc, th, mode=0, occupied=None, u_right=None, mbf=0.0,
+                                check_ori=True, max_distance=100):
+        import orbb200
+        return self.m.search_by_projection_world(self.f, sf, Rcw, tcw, K4, q.view(orbb200.WORLD_QUERY_DTYPE), qdesc, th, mode,
+                                                 occupied, u_right, mbf, check_ori, max_distance)
 
     def search_best(self, q, qdesc, chi2=False, u_right=None, inv_sigma2=None):
         import orbb200

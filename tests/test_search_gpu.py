@@ -103,6 +103,34 @@ def test_search_by_projection(matcher, oracle, pair, name, th, mode, stereo, ori
         assert n > 100
 
 
+def test_project_points_bits(matcher, oracle):
+    """orbm_project_points == match_oracle.cpp::project_points (ORBmatcher.cc:1376-1388; the oracle's arithmetic is pinned
+    against cv2.gemm in test_cvprims.py), bit for bit, incl. points at and behind the camera plane."""
+    from matcher_cases import camera_pose
+    rng = np.random.default_rng(5)
+    R, t, K4 = camera_pose(rng)
+    xyz = (rng.normal(size=(50000, 3)) * [4, 3, 6] + [0, 0, 5]).astype(np.float32)
+    xyz[:4] = [[0, 0, 0], [1, 2, -3], [1e6, -1e6, 1e-3], [0.5, 0.5, 1e-30]]
+    u, v, iz = matcher.project_points(R, t, K4, xyz)
+    ru, rv, riz, _ = oracle.project(R, t, K4, [-np.inf, -np.inf, np.inf, np.inf], xyz)
+    for a, b in ((u, ru), (v, rv), (iz, riz)):
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    assert (iz < 0).sum() > 1000
+
+
+@pytest.mark.parametrize("case", ["projw_window", "projw_forward_stereo", "projw_backward_stereo"])
+def test_search_by_projection_world(matcher, oracle, pair, case):
+    """orbm_search_by_projection_world (projection on the device) == oracle projection + search, through a non-identity
+    pose with points behind the camera and outside the image."""
+    from matcher_cases import GpuFrame, run_case, same
+    for name in ("kitti", "euroc"):
+        ka, da, kb, db, bounds = pair[name]
+        got = run_case(case, GpuFrame(matcher, ka, da, bounds), GpuFrame(matcher, kb, db, bounds), ka, da, kb, db)
+        want = run_case(case, oracle.frame(ka, da, bounds), oracle.frame(kb, db, bounds), ka, da, kb, db)
+        same(got, want)
+        assert got[0] > 100
+
+
 def test_search_by_projection_relocalisation_threshold(matcher, oracle, pair):
     """SearchByProjection(Frame, KeyFrame, sAlreadyFound, th, ORBdist) (ORBmatcher.cc:1500-1627): predicted levels come
     from the host, any assigned keypoint is occupied, acceptance threshold ORBdist = 64 (Tracking.cc:2691)."""

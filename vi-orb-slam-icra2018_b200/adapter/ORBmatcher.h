@@ -87,6 +87,18 @@ public:
         return n;
     }
 
+    // the same with world points + current pose: the projection of ORBmatcher.cc:1376-1393 runs on the device
+    int SearchByProjection(const FrameView& Current, const std::vector<float>& scaleFactors, const float* uRight, float mbf,
+                           const orbm_pose& pose, const std::vector<orbm_world_query>& queries, const unsigned char* queryDescriptors,
+                           float th, int mode, const unsigned char* occupied, std::vector<int>& curMatch) {
+        curMatch.assign(Current.size(), -1);
+        int n = 0;
+        check(orbm_search_by_projection_world(h_, Current.get(), scaleFactors.data(), (int)scaleFactors.size(), uRight, mbf, &pose,
+                                              queries.data(), queryDescriptors, (int)queries.size(), th, mode, TH_HIGH, occupied,
+                                              curMatch.data(), mbCheckOrientation, &n));
+        return n;
+    }
+
     // SearchByProjection(F, vpMapPoints, th)   ORBmatcher.cc:45-129
     int SearchByProjection(const FrameView& F, const std::vector<float>& scaleFactors, const float* uRight,
                            const std::vector<orbm_point_query>& queries, const unsigned char* queryDescriptors, float th,

@@ -83,7 +83,9 @@ inline int ORBmatcher::SearchForInitialization(Frame& F1, Frame& F2, std::vector
     return n;
 }
 
-// ORBmatcher.cc:1341-1498. The projection (:1352-1388) is cv::Mat arithmetic on the host, as in the reference.
+// ORBmatcher.cc:1341-1498. The per-point projection (:1376-1393) runs on the device (orbm_search_by_projection_world, the
+// arithmetic of cv::gemm's CV_32F 3x3 path restated); only the once-per-call forward / backward decision (:1352-1364) is
+// cv::Mat arithmetic on the host.
 inline int ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, const float th, const bool bMono) {
     const cv::Mat Rcw = CurrentFrame.mTcw.rowRange(0, 3).colRange(0, 3);
     const cv::Mat tcw = CurrentFrame.mTcw.rowRange(0, 3).col(3);
@@ -94,20 +96,21 @@ inline int ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& Last
     const bool bForward = tlc.at<float>(2) > CurrentFrame.mb && !bMono;
     const bool bBackward = -tlc.at<float>(2) > CurrentFrame.mb && !bMono;
 
-    std::vector<orbm_proj_query> q(LastFrame.N);
+    orbm_pose pose;
+    for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 3; ++c) pose.Rcw[3 * r + c] = Rcw.at<float>(r, c);
+        pose.tcw[r] = tcw.at<float>(r);
+    }
+    pose.fx = CurrentFrame.fx; pose.fy = CurrentFrame.fy; pose.cx = CurrentFrame.cx; pose.cy = CurrentFrame.cy;
+    std::vector<orbm_world_query> q(LastFrame.N);
     std::vector<unsigned char> qdesc((size_t)LastFrame.N * 32, 0);
     for (int i = 0; i < LastFrame.N; ++i) {
-        orbm_proj_query& a = q[i];
-        a = orbm_proj_query();
+        orbm_world_query& a = q[i];
+        a = orbm_world_query();
         MapPoint* pMP = LastFrame.mvpMapPoints[i];
         if (!pMP || LastFrame.mvbOutlier[i]) continue;
-        cv::Mat x3Dc = Rcw * pMP->GetWorldPos() + tcw;
-        const float xc = x3Dc.at<float>(0), yc = x3Dc.at<float>(1);
-        const float invzc = 1.0 / x3Dc.at<float>(2);
-        if (invzc < 0) continue;
-        a.u = CurrentFrame.fx * xc * invzc + CurrentFrame.cx;
-        a.v = CurrentFrame.fy * yc * invzc + CurrentFrame.cy;
-        a.invz = invzc;
+        const cv::Mat x3Dw = pMP->GetWorldPos();
+        a.x = x3Dw.at<float>(0); a.y = x3Dw.at<float>(1); a.z = x3Dw.at<float>(2);
         a.octave = LastFrame.mvKeys[i].octave;
         a.valid = 1;
         a.obs_positive = pMP->Observations() > 0;
@@ -119,7 +122,7 @@ inline int ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& Last
         occupied[i] = CurrentFrame.mvpMapPoints[i] && CurrentFrame.mvpMapPoints[i]->Observations() > 0;
     FrameView cur = orbb_detail::view_of(h_, CurrentFrame);
     std::vector<int> curMatch;
-    const int n = SearchByProjection(cur, CurrentFrame.mvScaleFactors, CurrentFrame.mvuRight.data(), CurrentFrame.mbf, q,
+    const int n = SearchByProjection(cur, CurrentFrame.mvScaleFactors, CurrentFrame.mvuRight.data(), CurrentFrame.mbf, pose, q,
                                      qdesc.data(), th, bForward ? 1 : (bBackward ? 2 : 0), occupied.data(), curMatch);
     for (int i2 = 0; i2 < CurrentFrame.N; ++i2)
         if (curMatch[i2] >= 0) CurrentFrame.mvpMapPoints[i2] = LastFrame.mvpMapPoints[curMatch[i2]];   // :1455

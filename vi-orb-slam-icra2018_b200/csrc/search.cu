@@ -389,6 +389,33 @@ __global__ void proj_queries_kernel(FrameDev cur, const orbm_proj_query* __restr
     if (i < nq) q[i] = proj_query(cur, pq[i], sf, th, mode, mbf);
 }
 
+// ORBmatcher.cc:1376-1393 on the device: x3Dc = Rcw * x3Dw + tcw is cv::gemm on CV_32F 3x3 . 3x1 + 3x1 operands, whose
+// small-matrix path sums the three products in float in source order and adds the addend in double with one rounding
+// (oracle/cvprims.cpp::gemm3_f32, pinned against cv2.gemm); invzc = 1.0 / z is a double division rounded once; u and v
+// are float expressions in source order.  The image-bounds test (:1390-1393) stays in proj_query.
+struct PoseDev { float R[9], t[3], fx, fy, cx, cy; };
+__global__ void project_world_kernel(PoseDev P, const orbm_world_query* __restrict__ wq, int nq, orbm_proj_query* __restrict__ pq) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    const orbm_world_query w = wq[i];
+    float c[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const float s = __fadd_rn(__fadd_rn(__fmul_rn(P.R[3 * r], w.x), __fmul_rn(P.R[3 * r + 1], w.y)), __fmul_rn(P.R[3 * r + 2], w.z));
+        c[r] = (float)__dadd_rn((double)s, (double)P.t[r]);
+    }
+    const float invz = (float)__ddiv_rn(1.0, (double)c[2]);
+    orbm_proj_query o;
+    o.u = __fadd_rn(__fmul_rn(__fmul_rn(P.fx, c[0]), invz), P.cx);
+    o.v = __fadd_rn(__fmul_rn(__fmul_rn(P.fy, c[1]), invz), P.cy);
+    o.invz = invz;
+    o.octave = w.octave;
+    o.valid = (w.valid != 0 && !(invz < 0.f)) ? 1 : 0;    // :1383-1384; a NaN depth passes here and fails the bounds test
+    o.obs_positive = w.obs_positive;
+    o.angle = w.angle;
+    pq[i] = o;
+}
+
 __global__ void point_queries_kernel(const orbm_point_query* __restrict__ pq, int nq, const float* __restrict__ sf, float th,
                                      AreaQuery* __restrict__ q) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1276,22 +1303,13 @@ int orbm_search_by_projection(orbm_handle h, orbm_frame cur, const float* sf, in
                                         curMatch, checkOri, nmatches);
 }
 
-int orbm_search_by_projection_ex(orbm_handle h, orbm_frame cur, const float* sf, int nlevels, const float* uRight, float mbf,
-                                 const orbm_proj_query* queries, const uint8_t* qdesc, int nq, float th, int mode, int maxDist,
-                                 const uint8_t* occupied, int* curMatch, int checkOri, int* nmatches) {
-    ORBM_ENTER(h);
-    if (!cur || !sf || nlevels < 1 || !curMatch || !nmatches || nq < 0 || (nq > 0 && (!queries || !qdesc)))
-        return fail(ORB_ERR_INVALID, "orbm_search_by_projection: bad arguments");
-    for (int i = 0; i < nq; ++i)
-        if (queries[i].valid && (queries[i].octave < 0 || queries[i].octave >= nlevels))
-            return fail(ORB_ERR_INVALID, "orbm_search_by_projection: query %d has octave %d outside 0..%d", i, queries[i].octave, nlevels - 1);
-    *nmatches = 0;
+namespace {
+
+// everything after the queries (device, h->in0) and their descriptors (h->in1) are in place
+int projection_search_device(orbm_matcher* h, orbm_frame cur, const float* sf, int nlevels, const float* uRight, float mbf, int nq,
+                             float th, int mode, int maxDist, const uint8_t* occupied, int* curMatch, int checkOri, int* nmatches) {
     const int n = cur->n;
-    for (int i = 0; i < n; ++i) curMatch[i] = -1;
-    if (nq == 0 || n == 0) return ORB_OK;
     cudaStream_t st = h->stream;
-    ORB_CHECK(upload(h->in0, queries, (size_t)nq * sizeof(orbm_proj_query), st));
-    ORB_CHECK(upload(h->in1, qdesc, (size_t)nq * 32, st));
     ORB_CHECK(upload(h->in2, sf, (size_t)nlevels * 4, st));
     if (uRight) ORB_CHECK(upload(h->in3, uRight, (size_t)n * 4, st));
     ORB_CHECK(h->in4.reserve((size_t)n + 16));
@@ -1318,6 +1336,81 @@ int orbm_search_by_projection_ex(orbm_handle h, orbm_frame cur, const float* sf,
     ORB_CUDA(cudaMemcpyAsync(curMatch, h->out0.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
     ORB_CUDA(cudaMemcpyAsync(nmatches, h->out3.p, 4, cudaMemcpyDeviceToHost, st));
     ORB_CUDA(cudaStreamSynchronize(st));
+    return ORB_OK;
+}
+
+}  // namespace
+
+int orbm_search_by_projection_ex(orbm_handle h, orbm_frame cur, const float* sf, int nlevels, const float* uRight, float mbf,
+                                 const orbm_proj_query* queries, const uint8_t* qdesc, int nq, float th, int mode, int maxDist,
+                                 const uint8_t* occupied, int* curMatch, int checkOri, int* nmatches) {
+    ORBM_ENTER(h);
+    if (!cur || !sf || nlevels < 1 || !curMatch || !nmatches || nq < 0 || (nq > 0 && (!queries || !qdesc)))
+        return fail(ORB_ERR_INVALID, "orbm_search_by_projection: bad arguments");
+    for (int i = 0; i < nq; ++i)
+        if (queries[i].valid && (queries[i].octave < 0 || queries[i].octave >= nlevels))
+            return fail(ORB_ERR_INVALID, "orbm_search_by_projection: query %d has octave %d outside 0..%d", i, queries[i].octave, nlevels - 1);
+    *nmatches = 0;
+    const int n = cur->n;
+    for (int i = 0; i < n; ++i) curMatch[i] = -1;
+    if (nq == 0 || n == 0) return ORB_OK;
+    cudaStream_t st = h->stream;
+    ORB_CHECK(upload(h->in0, queries, (size_t)nq * sizeof(orbm_proj_query), st));
+    ORB_CHECK(upload(h->in1, qdesc, (size_t)nq * 32, st));
+    return projection_search_device(h, cur, sf, nlevels, uRight, mbf, nq, th, mode, maxDist, occupied, curMatch, checkOri, nmatches);
+}
+
+int orbm_search_by_projection_world(orbm_handle h, orbm_frame cur, const float* sf, int nlevels, const float* uRight, float mbf,
+                                    const orbm_pose* pose, const orbm_world_query* queries, const uint8_t* qdesc, int nq, float th,
+                                    int mode, int maxDist, const uint8_t* occupied, int* curMatch, int checkOri, int* nmatches) {
+    ORBM_ENTER(h);
+    if (!cur || !sf || nlevels < 1 || !pose || !curMatch || !nmatches || nq < 0 || (nq > 0 && (!queries || !qdesc)))
+        return fail(ORB_ERR_INVALID, "orbm_search_by_projection_world: bad arguments");
+    for (int i = 0; i < nq; ++i)
+        if (queries[i].valid && (queries[i].octave < 0 || queries[i].octave >= nlevels))
+            return fail(ORB_ERR_INVALID, "orbm_search_by_projection_world: query %d has octave %d outside 0..%d", i, queries[i].octave,
+                        nlevels - 1);
+    *nmatches = 0;
+    const int n = cur->n;
+    for (int i = 0; i < n; ++i) curMatch[i] = -1;
+    if (nq == 0 || n == 0) return ORB_OK;
+    cudaStream_t st = h->stream;
+    ORB_CHECK(upload(h->in5, queries, (size_t)nq * sizeof(orbm_world_query), st));
+    ORB_CHECK(upload(h->in1, qdesc, (size_t)nq * 32, st));
+    ORB_CHECK(h->in0.reserve((size_t)nq * sizeof(orbm_proj_query)));
+    PoseDev P;
+    for (int i = 0; i < 9; ++i) P.R[i] = pose->Rcw[i];
+    for (int i = 0; i < 3; ++i) P.t[i] = pose->tcw[i];
+    P.fx = pose->fx; P.fy = pose->fy; P.cx = pose->cx; P.cy = pose->cy;
+    project_world_kernel<<<ceil_div(nq, 256), 256, 0, st>>>(P, h->in5.as<orbm_world_query>(), nq, h->in0.as<orbm_proj_query>());
+    h->launches += 1;
+    return projection_search_device(h, cur, sf, nlevels, uRight, mbf, nq, th, mode, maxDist, occupied, curMatch, checkOri, nmatches);
+}
+
+int orbm_project_points(orbm_handle h, const orbm_pose* pose, const float* xyz, int n, float* u, float* v, float* invz) {
+    ORBM_ENTER(h);
+    if (!pose || n < 0 || (n > 0 && (!xyz || !u || !v || !invz))) return fail(ORB_ERR_INVALID, "orbm_project_points: bad arguments");
+    if (n == 0) return ORB_OK;
+    cudaStream_t st = h->stream;
+    std::vector<orbm_world_query> wq((size_t)n);
+    for (int i = 0; i < n; ++i) {
+        wq[i] = orbm_world_query();
+        wq[i].x = xyz[3 * i]; wq[i].y = xyz[3 * i + 1]; wq[i].z = xyz[3 * i + 2];
+        wq[i].valid = 1;
+    }
+    ORB_CHECK(upload(h->in5, wq.data(), (size_t)n * sizeof(orbm_world_query), st));
+    ORB_CHECK(h->in0.reserve((size_t)n * sizeof(orbm_proj_query)));
+    PoseDev P;
+    for (int i = 0; i < 9; ++i) P.R[i] = pose->Rcw[i];
+    for (int i = 0; i < 3; ++i) P.t[i] = pose->tcw[i];
+    P.fx = pose->fx; P.fy = pose->fy; P.cx = pose->cx; P.cy = pose->cy;
+    project_world_kernel<<<ceil_div(n, 256), 256, 0, st>>>(P, h->in5.as<orbm_world_query>(), n, h->in0.as<orbm_proj_query>());
+    h->launches += 1;
+    ORB_CUDA(cudaGetLastError());
+    std::vector<orbm_proj_query> pq((size_t)n);
+    ORB_CUDA(cudaMemcpyAsync(pq.data(), h->in0.p, (size_t)n * sizeof(orbm_proj_query), cudaMemcpyDeviceToHost, st));
+    ORB_CUDA(cudaStreamSynchronize(st));
+    for (int i = 0; i < n; ++i) { u[i] = pq[i].u; v[i] = pq[i].v; invz[i] = pq[i].invz; }
     return ORB_OK;
 }
 

@@ -17,6 +17,9 @@ KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4
                      ("octave", "<i4"), ("class_id", "<i4")])
 PROJ_QUERY_DTYPE = np.dtype([("u", "<f4"), ("v", "<f4"), ("invz", "<f4"), ("octave", "<i4"), ("valid", "<i4"),
                              ("obs_positive", "<i4"), ("angle", "<f4")])
+WORLD_QUERY_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("octave", "<i4"), ("valid", "<i4"),
+                              ("obs_positive", "<i4"), ("angle", "<f4")])
+POSE_DTYPE = np.dtype([("Rcw", "<f4", (9,)), ("tcw", "<f4", (3,)), ("fx", "<f4"), ("fy", "<f4"), ("cx", "<f4"), ("cy", "<f4")])
 POINT_QUERY_DTYPE = np.dtype([("proj_x", "<f4"), ("proj_y", "<f4"), ("proj_xr", "<f4"), ("view_cos", "<f4"),
                               ("level", "<i4"), ("in_view", "<i4"), ("obs_positive", "<i4")])
 
@@ -453,6 +456,37 @@ class Matcher:
         _check(self.L.orbm_search_by_projection_ex(self.h, cur.f, _p(sf), len(sf), _p(ur), C.c_float(mbf), _p(q), _p(qd),
                                                    len(q), C.c_float(th), mode, max_distance, _p(occ), _p(match),
                                                    int(check_ori), C.byref(n)))
+        return n.value, match
+
+    def project_points(self, Rcw, tcw, K4, xyz):
+        """ORBmatcher.cc:1376-1388 on the device: (u, v, invz) of n world points"""
+        pose = np.zeros(1, POSE_DTYPE)
+        pose["Rcw"][0] = np.asarray(Rcw, np.float32).ravel()
+        pose["tcw"][0] = np.asarray(tcw, np.float32).ravel()
+        pose["fx"], pose["fy"], pose["cx"], pose["cy"] = [np.float32(v) for v in K4]
+        p = np.ascontiguousarray(xyz, np.float32).reshape(-1, 3)
+        u = np.empty(len(p), np.float32); v = np.empty(len(p), np.float32); iz = np.empty(len(p), np.float32)
+        _check(self.L.orbm_project_points(self.h, _p(pose), _p(p), len(p), _p(u), _p(v), _p(iz)))
+        return u, v, iz
+
+    def search_by_projection_world(self, cur, scale_factors, Rcw, tcw, K4, queries, qdesc, th, mode=0, occupied=None,
+                                   u_right=None, mbf=0.0, check_ori=True, max_distance=100):
+        """SearchByProjection(Current, Last, th, bMono) with the projection (ORBmatcher.cc:1376-1393) on the device:
+        queries = world points (WORLD_QUERY_DTYPE), Rcw / tcw = the current pose, K4 = (fx, fy, cx, cy)."""
+        sf = np.ascontiguousarray(scale_factors, np.float32)
+        q = np.ascontiguousarray(queries, WORLD_QUERY_DTYPE)
+        qd = np.ascontiguousarray(qdesc, np.uint8)
+        pose = np.zeros(1, POSE_DTYPE)
+        pose["Rcw"][0] = np.asarray(Rcw, np.float32).ravel()
+        pose["tcw"][0] = np.asarray(tcw, np.float32).ravel()
+        pose["fx"], pose["fy"], pose["cx"], pose["cy"] = [np.float32(v) for v in K4]
+        occ = np.zeros(cur.n, np.uint8) if occupied is None else np.ascontiguousarray(occupied, np.uint8)
+        ur = None if u_right is None else np.ascontiguousarray(u_right, np.float32)
+        match = np.empty(cur.n, np.int32)
+        n = C.c_int()
+        _check(self.L.orbm_search_by_projection_world(self.h, cur.f, _p(sf), len(sf), _p(ur), C.c_float(mbf), _p(pose), _p(q),
+                                                      _p(qd), len(q), C.c_float(th), mode, max_distance, _p(occ), _p(match),
+                                                      int(check_ori), C.byref(n)))
         return n.value, match
 
     def search_by_projection_points(self, f, scale_factors, queries, qdesc, th, ratio, occupied=None, u_right=None):

@@ -45,6 +45,8 @@ SIGNATURES = {
     "orbm_search_for_initialization": (i32, [vp, vp, vp, vp, vp, i32, f32, i32, vp]),
     "orbm_search_by_projection": (i32, [vp, vp, vp, i32, vp, f32, vp, vp, i32, f32, i32, vp, vp, i32, vp]),
     "orbm_search_by_projection_ex": (i32, [vp, vp, vp, i32, vp, f32, vp, vp, i32, f32, i32, i32, vp, vp, i32, vp]),
+    "orbm_search_by_projection_world": (i32, [vp, vp, vp, i32, vp, f32, vp, vp, vp, i32, f32, i32, i32, vp, vp, i32, vp]),
+    "orbm_project_points": (i32, [vp, vp, vp, i32, vp, vp, vp]),
     "orbm_search_by_projection_batch": (i32, [vp, vp, i32, vp, i32, f32, f32, i32, i32, i32, vp]),
     "orbm_search_for_initialization_batch": (i32, [vp, vp, i32, i32, f32, i32, vp]),
     "orbm_search_by_projection_points": (i32, [vp, vp, vp, i32, vp, vp, vp, i32, f32, f32, vp, vp, vp]),
