@@ -22,7 +22,8 @@ for r in rows:
     line, src = r[0], r[1]
     try:
         ie = int(r[hdr["Instructions Executed"]]); sm = int(r[hdr["# Samples"]])
-        wf = int(r[hdr["L1 Wavefronts Shared"]] or 0); wfi = int(r[hdr["L1 Wavefronts Shared Ideal"]] or 0)
+        wf = int(r[hdr["L1 Wavefronts Shared"]] or 0) if "L1 Wavefronts Shared" in hdr else 0
+        wfi = int(r[hdr["L1 Wavefronts Shared Ideal"]] or 0) if "L1 Wavefronts Shared Ideal" in hdr else 0
     except ValueError:
         continue
     if not line:   # SASS row: already counted in its CUDA line

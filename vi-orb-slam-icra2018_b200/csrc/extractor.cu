@@ -57,7 +57,7 @@ struct orbx_extractor {
     int kpCapacity = 0;       // upper bound on keypoints per frame
     int otSmem = 0, otKeyCap = 0, otNodeCap = 0, otCellCap = 0;
     // device memory
-    DevBuf pyr, blur, slots, cellCount, sel, selCount, keyWs, dCells, dTiles, dTabOfs, dTabCoef, dFastMaps, dFastScratch, dFastCounters;
+    DevBuf pyr, blur, slots, cellCount, sel, selCount, keyWs, dCells, dTiles, dTabOfs, dTabCoef, dPyCol, dPyRow, dPyBand, dFastMaps, dFastScratch, dFastCounters;
     DevBuf dImages, dKps, dDesc, dCount;
     DevBuf stKeysL, stDescL, stKeysR, stDescR, stOut;   // staging of orbx_compute_stereo_matches
     int lastFrames = 0, lastCapacity = 0;   // arena capacity in frames / caller capacity of the last call
@@ -171,6 +171,21 @@ int configure(orbx_extractor* e, int w, int h, int nFrames) {
         resize_axis_table(lv[l - 1].h, lv[l].h, &tabOfs[lv[l].yTab], &tabCoef[lv[l].yTab]);
     }
 
+    std::vector<uint4> pyCol, pyRow;
+    std::vector<int4> pyBand;
+    for (int l = 1; l < nl; ++l) {
+        const size_t c0 = pyCol.size(), r0 = pyRow.size();
+        lv[l].pyCol = (int)c0;
+        lv[l].pyRow = (int)r0;
+        lv[l].pyFast = pyramid_level_plan(lv[l - 1], lv[l], &tabOfs[lv[l].xTab], &tabCoef[lv[l].xTab], &tabOfs[lv[l].yTab],
+                                          &tabCoef[lv[l].yTab], pyCol, pyRow) ? 1 : 0;
+        if (!lv[l].pyFast) { pyCol.resize(c0); pyRow.resize(r0); }
+        lv[l].pyBand = (int)pyBand.size();
+        lv[l].pyBufBytes = round_up(pyramid_band_plan(lv[l - 1], lv[l], &tabOfs[lv[l].yTab], pyBand), 128);
+        lv[l].pyBulkCtas = lv[l].pyFast ? pyramid_bulk_ctas(lv[l].pitch / 4, lv[l].pyBufBytes) : 0;
+        lv[l].pyBulk = lv[l].pyBulkCtas > 0;
+    }
+
     // arena
     const long long F = std::max(nFrames, e->maxBatch);
     ORB_CHECK(e->pyr.reserve((size_t)(pyrOff * F) + 256));
@@ -188,6 +203,12 @@ int configure(orbx_extractor* e, int w, int h, int nFrames) {
     ORB_CUDA(cudaMemcpyAsync(e->dTiles.p, tiles.data(), tiles.size() * sizeof(BlurTile), cudaMemcpyHostToDevice, e->stream));
     ORB_CUDA(cudaMemcpyAsync(e->dTabOfs.p, tabOfs.data(), tabOfs.size() * 4, cudaMemcpyHostToDevice, e->stream));
     ORB_CUDA(cudaMemcpyAsync(e->dTabCoef.p, tabCoef.data(), tabCoef.size() * 4, cudaMemcpyHostToDevice, e->stream));
+    ORB_CHECK(e->dPyCol.reserve(pyCol.size() * 16 + 16));
+    ORB_CHECK(e->dPyRow.reserve(pyRow.size() * 16 + 16));
+    if (!pyCol.empty()) ORB_CUDA(cudaMemcpyAsync(e->dPyCol.p, pyCol.data(), pyCol.size() * 16, cudaMemcpyHostToDevice, e->stream));
+    if (!pyRow.empty()) ORB_CUDA(cudaMemcpyAsync(e->dPyRow.p, pyRow.data(), pyRow.size() * 16, cudaMemcpyHostToDevice, e->stream));
+    ORB_CHECK(e->dPyBand.reserve(pyBand.size() * 16 + 16));
+    if (!pyBand.empty()) ORB_CUDA(cudaMemcpyAsync(e->dPyBand.p, pyBand.data(), pyBand.size() * 16, cudaMemcpyHostToDevice, e->stream));
     ORB_CUDA(cudaStreamSynchronize(e->stream));   // the host vectors go out of scope
 
     std::memset(&P, 0, sizeof P);
@@ -222,6 +243,13 @@ int configure(orbx_extractor* e, int w, int h, int nFrames) {
     P.cells = e->dCells.as<Cell>();
     P.tabOfs = e->dTabOfs.as<int>();
     P.tabCoef = e->dTabCoef.as<short2>();
+    P.pyColTab = e->dPyCol.as<uint4>();
+    P.pyRowTab = e->dPyRow.as<uint4>();
+    P.pyBandTab = e->dPyBand.as<int4>();
+    {
+        const char* v = getenv("ORBB_PYR_BULK_MIN");      // tuning aid: smallest batch that takes the staged resize kernel
+        P.pyBulkMinFrames = v ? atoi(v) : 8;
+    }
     for (int l = 0; l < nl; ++l) P.lv[l] = lv[l];
     {   // TMA descriptors of the padded pyramid levels: [arena frame][row][pitch], box = one FAST tile
         unsigned char hostMaps[128 * kMaxLevels];
@@ -386,7 +414,7 @@ int orbx_destroy(orbx_handle e) {
     DeviceGuard g(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
     DevBuf* bufs[] = {&e->pyr, &e->blur, &e->slots, &e->cellCount, &e->sel, &e->selCount, &e->keyWs, &e->dCells,
-                      &e->dTiles, &e->dTabOfs, &e->dTabCoef, &e->dFastMaps, &e->dFastScratch, &e->dFastCounters, &e->dImages, &e->dKps, &e->dDesc, &e->dCount,
+                      &e->dTiles, &e->dTabOfs, &e->dTabCoef, &e->dPyCol, &e->dPyRow, &e->dPyBand, &e->dFastMaps, &e->dFastScratch, &e->dFastCounters, &e->dImages, &e->dKps, &e->dDesc, &e->dCount,
                       &e->stKeysL, &e->stDescL, &e->stKeysR, &e->stDescR, &e->stOut};
     for (DevBuf* b : bufs) b->release();
     if (e->graphExec) cudaGraphExecDestroy(e->graphExec);

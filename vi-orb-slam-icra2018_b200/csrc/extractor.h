@@ -12,6 +12,8 @@
 //   selcnt [frame][level]
 //   keyws  [frame][level]  spill space for candidate lists that do not fit shared memory
 #pragma once
+#include <vector>
+
 #include "common.cuh"
 
 namespace orbb {
@@ -27,6 +29,12 @@ struct LevelGeom {
     long long pyrOff;    // byte offset of the padded buffer inside one frame's pyramid block
     long long blurOff;   // byte offset inside one frame's blur block
     int xTab, yTab;      // offsets into the resize tables (entries)
+    int pyCol, pyRow;    // offsets of the level's column / row records of the resize kernel (uint4 entries)
+    int pyFast;          // 1: the level is resized by pyramid_resize2_kernel from those records
+    int pyBand;          // offset of the level's band records (int4 entries) of the staged kernel
+    int pyBulk;          // 1: batches are resized by pyramid_resize3_kernel (source rows staged by bulk-async copies)
+    int pyBufBytes;      // bytes of one staging buffer
+    int pyBulkCtas;      // resident CTAs of that kernel on the device
     int cellBase, nCells;    // this level's cells inside the frame's cell table
     int slotCap;         // entries per cell slot
     long long slotBase;  // entry offset of the level's first slot inside one frame's slot block
@@ -99,6 +107,10 @@ struct ExtractParams {
     const Cell* cells;
     const int* tabOfs;       // resize tables: source index per destination index
     const short2* tabCoef;   // 11-bit coefficient pairs
+    const uint4* pyColTab;   // pyramid_resize2_kernel: per 4-byte destination group {base, shift, sel01, sel23}, {cf[0..3]}
+    const uint4* pyRowTab;   //                         per padded destination row {off(sy0), off(sy0+1), b0 << 12, b1 << 12}
+    const int4* pyBandTab;   // pyramid_resize3_kernel: per band of 16 destination rows {source offset, bytes, offset(first sy0), -}
+    int pyBulkMinFrames;     // batches of at least this many frames use the staged kernel
     LevelGeom lv[kMaxLevels];
 };
 
@@ -117,6 +129,10 @@ struct BlurTile { int level, cta; };   // one CTA of the blur kernel: level and 
 // launchers (each returns orb_status and bumps *launches)
 int launch_pyramid(const ExtractParams& P, const unsigned char* dImages, int width, int height, int stride,
                    size_t frameStride, cudaStream_t st, int* launches);
+bool pyramid_level_plan(const LevelGeom& S, const LevelGeom& D, const int* xofs, const short2* xcoef, const int* yofs,
+                        const short2* ycoef, std::vector<uint4>& col, std::vector<uint4>& row);
+int pyramid_band_plan(const LevelGeom& S, const LevelGeom& D, const int* yofs, std::vector<int4>& bands);
+int pyramid_bulk_ctas(int groups, int bufBytes);
 int fast_warp_plan(int nLevels, const int* cellW, const int* cellH, int slotCapMax, FastWarpPlan* plan);
 int fast_warp_max_warps(const FastWarpPlan& plan, int* warps);   // resident warps of one launch on the current device
 int launch_fast_warp(const ExtractParams& P, cudaStream_t st, int* launches);

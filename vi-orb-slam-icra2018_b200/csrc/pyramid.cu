@@ -21,6 +21,9 @@
 //   * the vertical pass is two multiply-high per pixel: hi32((T & ~15) * (b << 12)) == (b * (T >> 4)) >> 16.
 // Reading S[x+1] / row y+1 one past the level is harmless: the table's coefficient there is 0 and the source level
 // has its own frame.
+#include <algorithm>
+#include <vector>
+
 #include "extractor.h"
 
 namespace orbb {
@@ -179,6 +182,237 @@ pyramid_resize_kernel(unsigned char* __restrict__ pyr, long long pyrFrameBytes, 
     }
 }
 
+// ---- the resize kernel of the usual case (every 4-byte group of the level reads an 8-byte source window: scale <= 2) ----
+// Same arithmetic as pyramid_resize_kernel; what changed is everything around it (22 -> 13 thread-instructions per pixel):
+// the per-group column invariants and the per-row source offsets / vertical coefficients are host-built records (one or
+// two 128-bit loads instead of table look-ups, reflections and 64-bit multiplies per row), and the only 64-bit address
+// arithmetic left per row is one add per source row and one for the destination.
+//   colTab[2g], colTab[2g+1] : {window base (bytes from the source pixel (0,0), multiple of 4), shift, sel01, sel23}, {cf[0..3]}
+//   rowTab[by]               : {byte offset of source row sy0, of row sy0+1, b0 << 12, b1 << 12}   (by = padded row)
+__global__ void __launch_bounds__(PY_THREADS)
+pyramid_resize2_kernel(unsigned char* __restrict__ pyr, long long pyrFrameBytes, long long srcPix0, long long dstOff, int dstPitch,
+                       int rowsTotal, int groups, int nItems, const uint4* __restrict__ colTab, const uint4* __restrict__ rowTab) {
+    const int item = blockIdx.x * PY_THREADS + threadIdx.x;
+    if (item >= nItems) return;
+    const int band = item / groups, g = item - band * groups;
+    unsigned char* frame = pyr + (size_t)blockIdx.y * pyrFrameBytes;
+    const uint4 ca = __ldg(colTab + 2 * g), cb = __ldg(colTab + 2 * g + 1);
+    const unsigned char* srcCol = frame + srcPix0 + ca.x;
+    const int by0 = band * PY_ROWS;
+    unsigned char* dst = frame + dstOff + 4 * g + (size_t)by0 * dstPitch;
+    const uint4* rt = rowTab + by0;
+    const int rows = min(PY_ROWS, rowsTotal - by0);
+    const unsigned int shift = ca.y, sel01 = ca.z, sel23 = ca.w;
+    auto hsum = [&](const unsigned char* row, unsigned int (&t)[4]) {
+        const unsigned int* p = reinterpret_cast<const unsigned int*>(row);
+        const unsigned int w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2);
+        const unsigned int X = __funnelshift_r(w0, w1, shift), Y = __funnelshift_r(w1, w2, shift);
+        const unsigned int v01 = __byte_perm(X, Y, sel01), v23 = __byte_perm(X, Y, sel23);
+        t[0] = __dp2a_lo(cb.x, v01, 0u) & ~15u;
+        t[1] = __dp2a_hi(cb.y, v01, 0u) & ~15u;
+        t[2] = __dp2a_lo(cb.z, v23, 0u) & ~15u;
+        t[3] = __dp2a_hi(cb.w, v23, 0u) & ~15u;
+    };
+    unsigned int keptOff = 0xffffffffu;
+    unsigned int kept[4] = {0, 0, 0, 0};
+#pragma unroll 2
+    for (int r = 0; r < rows; ++r) {
+        const uint4 rr = __ldg(rt + r);
+        unsigned int t0[4], t1[4];
+        if (rr.x == keptOff) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) t0[k] = kept[k];
+        } else {
+            hsum(srcCol + rr.x, t0);
+        }
+        hsum(srcCol + rr.y, t1);
+        keptOff = rr.y;
+        unsigned int s[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            kept[k] = t1[k];
+            s[k] = __umulhi(t0[k], rr.z) + __umulhi(t1[k], rr.w) + 2u;    // <= 1023
+        }
+        const unsigned int q01 = __byte_perm(s[0], s[1], 0x5410) >> 2, q23 = __byte_perm(s[2], s[3], 0x5410) >> 2;
+        *reinterpret_cast<unsigned int*>(dst) = __byte_perm(q01, q23, 0x6420);
+        dst += dstPitch;
+    }
+}
+
+// host: the records of one level (dst) resized from the level above it (src); returns false if a group needs more than the
+// 8-byte window (scale factor > 2), in which case the level keeps the table-driven kernel
+bool pyramid_level_plan(const LevelGeom& S, const LevelGeom& D, const int* xofs, const short2* xcoef, const int* yofs,
+                        const short2* ycoef, std::vector<uint4>& col, std::vector<uint4>& row) {
+    auto reflect = [](int i, int n) { if (i < 0) i = -i; if (i >= n) i = 2 * n - 2 - i; return i; };
+    const int groups = D.pitch / 4;
+    for (int g = 0; g < groups; ++g) {
+        int ofs[4], omin = 0x7fffffff, omax = 0;
+        unsigned int cf[4];
+        for (int k = 0; k < 4; ++k) {
+            const int dx = std::min(std::max(reflect(4 * g - kPadLeft + k, D.w), 0), D.w - 1);
+            ofs[k] = xofs[dx];
+            cf[k] = (unsigned int)(unsigned short)xcoef[dx].x | ((unsigned int)(unsigned short)xcoef[dx].y << 16);
+            omin = std::min(omin, ofs[k]);
+            omax = std::max(omax, ofs[k]);
+        }
+        if (omax - omin > 6) return false;
+        const unsigned int i0 = ofs[0] - omin, i1 = ofs[1] - omin, i2 = ofs[2] - omin, i3 = ofs[3] - omin;
+        col.push_back(make_uint4((unsigned int)(omin & ~3), (unsigned int)(omin & 3) * 8u, i0 | ((i0 + 1) << 4) | (i1 << 8) | ((i1 + 1) << 12),
+                                 i2 | ((i2 + 1) << 4) | (i3 << 8) | ((i3 + 1) << 12)));
+        col.push_back(make_uint4(cf[0], cf[1], cf[2], cf[3]));
+    }
+    for (int by = 0; by < D.h + 2 * kEdge; ++by) {
+        const int dy = reflect(by - kEdge, D.h);
+        const unsigned int off0 = (unsigned int)yofs[dy] * (unsigned int)S.pitch;
+        row.push_back(make_uint4(off0, off0 + (unsigned int)S.pitch, (unsigned int)ycoef[dy].x << 12, (unsigned int)ycoef[dy].y << 12));
+    }
+    row.push_back(make_uint4(0, 0, 0, 0));     // spare entry: the staged kernel reads one record ahead
+    return true;
+}
+
+// ---- the same resize with the source rows staged through shared memory by bulk-async copies (TMA engine) ------------
+// pyramid_resize2_kernel issues 3 word loads per source row per thread straight to L1/L2: a warp's windows overlap, every
+// source byte is requested ~3.6 times and the kernel sits at the latency x requests-in-flight limit (measured: 40 % fewer
+// instructions changed nothing, 5.16 -> 5.18 ms).  Here a CTA owns a band of 16 destination rows over the full width; the
+// source rows that band needs are CONTIGUOUS in the padded source level, so one cp.async.bulk (global -> shared, completion
+// on an mbarrier) fetches them, each byte once, without holding registers, and the next band's copy is in flight while
+// this one is computed (two buffers, persistent CTAs striding over (frame, band)).  The arithmetic reads shared memory.
+//   bandTab[b] : {byte offset of the band's first source row inside the source level buffer, bytes, offset(sy0 = first), -}
+__device__ __forceinline__ unsigned int py_smem_u32(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
+
+__global__ void __launch_bounds__(512)
+pyramid_resize3_kernel(unsigned char* __restrict__ pyr, long long pyrFrameBytes, long long srcOff, long long dstOff, int dstPitch,
+                       int rowsTotal, int groups, int nBands, int nTiles, int bufBytes, const uint4* __restrict__ colTab,
+                       const uint4* __restrict__ rowTab, const int4* __restrict__ bandTab) {
+    extern __shared__ __align__(128) unsigned char psm[];
+    const int tid = threadIdx.x;
+    const unsigned int bar0 = py_smem_u32(psm);                    // two mbarriers at bytes 0 and 8, tiles from byte 128
+    const unsigned int tile0 = bar0 + 128;
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const bool active = tid < groups;
+    uint4 ca = make_uint4(0, 0, 0, 0), cb = ca;
+    if (active) { ca = __ldg(colTab + 2 * tid); cb = __ldg(colTab + 2 * tid + 1); }
+    const unsigned int shift = ca.y, sel01 = ca.z, sel23 = ca.w;
+    auto issue = [&](int tile, int buf) {
+        if (tid == 0) {
+            const int frame = tile / nBands, band = tile - frame * nBands;
+            const int4 bt = __ldg(bandTab + band);
+            const unsigned char* src = pyr + (size_t)frame * pyrFrameBytes + srcOff + bt.x;
+            const unsigned int bar = bar0 + 8 * buf, dstS = tile0 + buf * bufBytes;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the buffer's last generic-proxy reads are behind the CTA barrier
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bt.y) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dstS), "l"(src),
+                         "r"(bt.y), "r"(bar)
+                         : "memory");
+        }
+    };
+    auto hsum = [&](unsigned int addr, unsigned int (&t)[4]) {
+        unsigned int w0, w1, w2;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(addr));
+        asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(w1) : "r"(addr));
+        asm volatile("ld.shared.u32 %0, [%1+8];" : "=r"(w2) : "r"(addr));
+        const unsigned int X = __funnelshift_r(w0, w1, shift), Y = __funnelshift_r(w1, w2, shift);
+        const unsigned int v01 = __byte_perm(X, Y, sel01), v23 = __byte_perm(X, Y, sel23);
+        t[0] = __dp2a_lo(cb.x, v01, 0u) & ~15u;
+        t[1] = __dp2a_hi(cb.y, v01, 0u) & ~15u;
+        t[2] = __dp2a_lo(cb.z, v23, 0u) & ~15u;
+        t[3] = __dp2a_hi(cb.w, v23, 0u) & ~15u;
+    };
+    int tile = blockIdx.x;
+    if (tile < nTiles) issue(tile, 0);
+    for (int it = 0; tile < nTiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        if (tile + (int)gridDim.x < nTiles) issue(tile + gridDim.x, buf ^ 1);
+        {
+            const unsigned int bar = bar0 + 8 * buf, parity = (unsigned int)(it >> 1) & 1u;
+            asm volatile(
+                "{\n"
+                ".reg .pred p;\n"
+                "PY_WAIT_%=:\n"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                "@p bra PY_DONE_%=;\n"
+                "bra PY_WAIT_%=;\n"
+                "PY_DONE_%=:\n"
+                "}\n" ::"r"(bar),
+                "r"(parity)
+                : "memory");
+        }
+        if (active) {
+            const int frame = tile / nBands, band = tile - frame * nBands;
+            const int by0 = band * PY_ROWS;
+            const int4 bt = __ldg(bandTab + band);
+            // shared-memory address of the window of source row sy0 = (offset in rowTab) + this
+            const unsigned int colBase = tile0 + buf * bufBytes + kPadLeft + ca.x - (unsigned int)bt.z;
+            unsigned char* dst = pyr + (size_t)frame * pyrFrameBytes + dstOff + 4 * tid + (size_t)by0 * dstPitch;
+            const uint4* rt = rowTab + by0;
+            const int rows = min(PY_ROWS, rowsTotal - by0);
+            unsigned int keptOff = 0xffffffffu;
+            unsigned int kept[4] = {0, 0, 0, 0};
+            uint4 rrNext = __ldg(rt);
+#pragma unroll 2
+            for (int r = 0; r < rows; ++r) {
+                const uint4 rr = rrNext;
+                rrNext = __ldg(rt + r + 1);      // the next row's record is requested before this row is computed (rowTab has a spare entry)
+                unsigned int t0[4], t1[4];
+                if (rr.x == keptOff) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) t0[k] = kept[k];
+                } else {
+                    hsum(colBase + rr.x, t0);
+                }
+                hsum(colBase + rr.y, t1);
+                keptOff = rr.y;
+                unsigned int s[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    kept[k] = t1[k];
+                    s[k] = __umulhi(t0[k], rr.z) + __umulhi(t1[k], rr.w) + 2u;    // <= 1023
+                }
+                const unsigned int q01 = __byte_perm(s[0], s[1], 0x5410) >> 2, q23 = __byte_perm(s[2], s[3], 0x5410) >> 2;
+                *reinterpret_cast<unsigned int*>(dst) = __byte_perm(q01, q23, 0x6420);
+                dst += dstPitch;
+            }
+        }
+        __syncthreads();   // every thread is done with this buffer before its next refill is issued
+    }
+}
+
+// host: band records of one level; returns the largest number of source bytes a band needs
+int pyramid_band_plan(const LevelGeom& S, const LevelGeom& D, const int* yofs, std::vector<int4>& bands) {
+    auto reflect = [](int i, int n) { if (i < 0) i = -i; if (i >= n) i = 2 * n - 2 - i; return i; };
+    const int rowsTotal = D.h + 2 * kEdge;
+    int maxBytes = 0;
+    for (int by0 = 0; by0 < rowsTotal; by0 += PY_ROWS) {
+        int lo = 0x7fffffff, hi = 0;
+        for (int by = by0; by < std::min(by0 + PY_ROWS, rowsTotal); ++by) {
+            const int sy = yofs[reflect(by - kEdge, D.h)];
+            lo = std::min(lo, sy);
+            hi = std::max(hi, sy);
+        }
+        const int bytes = (hi + 2 - lo) * S.pitch;
+        bands.push_back(make_int4((kEdge + lo) * S.pitch, bytes, lo * S.pitch, 0));
+        maxBytes = std::max(maxBytes, bytes);
+    }
+    return maxBytes;
+}
+
+// resident CTAs of the staged kernel on the current device for a level's block size and shared memory (0: does not fit)
+int pyramid_bulk_ctas(int groups, int bufBytes) {
+    const int threads = (groups + 31) / 32 * 32, smem = 128 + 2 * bufBytes;
+    if (threads > 512 || smem > 200 * 1024) return 0;
+    int dev = 0, nSm = 0, perSm = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaFuncSetAttribute(pyramid_resize3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&nSm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, pyramid_resize3_kernel, threads, smem) != cudaSuccess) return 0;
+    return nSm * perSm;
+}
+
 int launch_pyramid(const ExtractParams& P, const unsigned char* dImages, int width, int height, int stride,
                    size_t frameStride, cudaStream_t st, int* launches) {
     {
@@ -195,6 +429,24 @@ int launch_pyramid(const ExtractParams& P, const unsigned char* dImages, int wid
         const LevelGeom& D = P.lv[l];
         const int groups = D.pitch / 4, nItems = groups * ceil_div(D.h + 2 * kEdge, PY_ROWS);
         dim3 grid(ceil_div(nItems, PY_THREADS), P.nFrames);
+        if (D.pyFast && D.pyBulk && P.nFrames >= P.pyBulkMinFrames) {
+            const int threads = (groups + 31) / 32 * 32, nBands = ceil_div(D.h + 2 * kEdge, PY_ROWS);
+            const int smem = 128 + 2 * D.pyBufBytes;
+            const long long nTiles = (long long)nBands * P.nFrames;
+            const int gridX = (int)std::min<long long>(nTiles, (long long)D.pyBulkCtas);
+            pyramid_resize3_kernel<<<gridX, threads, smem, st>>>(P.pyr, P.pyrFrameBytes, S.pyrOff, D.pyrOff, D.pitch, D.h + 2 * kEdge, groups,
+                                                                 nBands, (int)nTiles, D.pyBufBytes, P.pyColTab + D.pyCol, P.pyRowTab + D.pyRow,
+                                                                 P.pyBandTab + D.pyBand);
+            ++*launches;
+            continue;
+        }
+        if (D.pyFast) {
+            pyramid_resize2_kernel<<<grid, PY_THREADS, 0, st>>>(P.pyr, P.pyrFrameBytes, S.pyrOff + (long long)kEdge * S.pitch + kPadLeft,
+                                                                D.pyrOff, D.pitch, D.h + 2 * kEdge, groups, nItems, P.pyColTab + D.pyCol,
+                                                                P.pyRowTab + D.pyRow);
+            ++*launches;
+            continue;
+        }
         pyramid_resize_kernel<<<grid, PY_THREADS, 0, st>>>(P.pyr, P.pyrFrameBytes, S.pyrOff, S.pitch, D.pyrOff, D.pitch, D.w,
                                                            D.h, groups, nItems, P.tabOfs + D.xTab,
                                                            reinterpret_cast<const unsigned int*>(P.tabCoef + D.xTab),
