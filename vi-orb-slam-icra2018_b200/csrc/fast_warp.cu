@@ -222,27 +222,39 @@ __device__ __forceinline__ int fast_front(FwWarp& W, const FastWarpPlan::Level& 
     const unsigned char* rowPtr = W.tile + (mis & ~3) + (r + 3) * BW + 4 * q;   // aligned word of pixel (4q - 4, r)
     const int T = F.T, chunkSteps = F.chunkSteps, steps = F.steps;
     const int chunkRows = 8 * (chunkSteps / T);
+    unsigned int colMask2 = 0;      // T == 2: the mask bits of this lane's pixels that lie inside the cell
+    if (T == 2) {
+        unsigned int vA0, vB0, vA1, vB1;
+        valid_pairs(cw - 4 * q, vA0, vB0);
+        valid_pairs(cw - 16 - 4 * q, vA1, vB1);
+        const unsigned int m0 = vA0 | (vB0 << 1), m1 = vA1 | (vB1 << 1);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) colMask2 |= __funnelshift_l((i & 1) ? m1 : m0, (i & 1) ? m1 : m0, 2 * i);
+    }
     int nq = 0;
 #pragma unroll 1
     for (int j0 = 0, y0 = r; j0 < steps; j0 += chunkSteps, y0 += chunkRows, rowPtr += chunkRows * BW) {
         const int nSteps = min(chunkSteps, steps - j0);
         unsigned int mb = 0, md = 0;
         if (T == 2) {
-            // 8 groups per row: step i = (block i>>1, half i&1), everything about the columns is loop-invariant
-            unsigned int vA0, vB0, vA1, vB1;
-            valid_pairs(cw - 4 * q, vA0, vB0);
-            valid_pairs(cw - 16 - 4 * q, vA1, vB1);
+            // 8 groups per row: step i = (block i>>1, half i&1).  Pixels past the cell's right edge and rows past its last
+            // one are computed like the others and struck from the finished masks: step i's bits sit at 9, 10, 25, 26 rotated
+            // by 2i, so the valid rows of the chunk are two runs of 4 bits per 8-row block, and the columns' mask is the
+            // same for every chunk of the cell
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 if (i < nSteps) {
-                    const bool rowOk = y0 + 8 * (i >> 1) < ch;
                     unsigned int tb, td;
-                    pretest_row<BW>(rowPtr + (i >> 1) * 8 * BW + 16 * (i & 1), al, K, rowOk ? ((i & 1) ? vA1 : vA0) : 0u,
-                                    rowOk ? ((i & 1) ? vB1 : vB0) : 0u, tb, td);
+                    pretest_row<BW>(rowPtr + (i >> 1) * 8 * BW + 16 * (i & 1), al, K, FW_PASS, FW_PASS, tb, td);
                     mb |= __funnelshift_l(tb, tb, 2 * i);
                     md |= __funnelshift_l(td, td, 2 * i);
                 }
             }
+            const int nb = (ch - y0 + 7) >> 3;                      // 8-row blocks of this chunk with a row inside the cell (for this lane)
+            const unsigned int run = nb >= 8 ? 0xffffffffu : nb <= 0 ? 0u : (1u << (4 * nb)) - 1u;
+            const unsigned int ok = colMask2 & (__funnelshift_l(run, run, 9) | __funnelshift_l(run, run, 25));
+            mb &= ok;
+            md &= ok;
         } else {
             int t = 0, y = y0;
             const unsigned char* rp = rowPtr;
@@ -281,12 +293,13 @@ __device__ __forceinline__ int fast_front(FwWarp& W, const FastWarpPlan::Level& 
         const unsigned char* pA = tilePix + yA * BW + xA;
         const unsigned char* pB = tilePix + yB * BW + xB;
         // d = 256 + (p - v) for a bright candidate, 256 + (v - p) for a dark one: every half stays in [1, 511]
-        const int mulA = (eA & 0x8000u) ? -1 : 1, mulB = (eB & 0x8000u) ? -65536 : 65536;
-        const unsigned int C = 0x01000100u - (unsigned int)mulA * pA[0] - (unsigned int)mulB * pB[0];
+        // the multipliers go through an opaque mad (fma_u32): seeing the +-1, the compiler rewrote every d[k] as
+        // (pA - vA) -> predicated negate -> (pB - vB) * mulB + .. + constant, five instructions where two do
+        const unsigned int mulA = (eA & 0x8000u) ? 0xffffffffu : 1u, mulB = (eB & 0x8000u) ? 0xffff0000u : 0x00010000u;
+        const unsigned int C = 0x01000100u - mulA * pA[0] - mulB * pB[0];
         unsigned int d[16];
 #pragma unroll
-        for (int k = 0; k < 16; ++k)
-            d[k] = (unsigned int)pA[FW_CIRCLE(k, BW)] * (unsigned int)mulA + ((unsigned int)pB[FW_CIRCLE(k, BW)] * (unsigned int)mulB + C);
+        for (int k = 0; k < 16; ++k) d[k] = fma_u32(pA[FW_CIRCLE(k, BW)], mulA, fma_u32(pB[FW_CIRCLE(k, BW)], mulB, C));
         unsigned int m3[16];
 #pragma unroll
         for (int k = 0; k < 16; ++k) m3[k] = __vimin3_u16x2(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
