@@ -168,6 +168,8 @@ struct FwSurvivors {       // a lane's view of the survivor bitmap: pixel rows `
 // B: the set bits of one chunk's masks become queue entries (x | y << 6 | polarity << 15).  A "unit" is a group of four
 // steps (two 8-row blocks when T = 2); the two units' per-lane counts are prefix-summed over the warp in one packed
 // shuffle scan.  Returns the new queue length, or -1 (nothing written) if the chunk does not fit.
+// SMEM: the queue is the warp's shared-memory one (the common case): 32-bit addresses and st.shared instead of generic stores.
+template <bool SMEM>
 __device__ __forceinline__ int enqueue_chunk(unsigned int mb, unsigned int md, unsigned int laneEntry, const unsigned short (*lut)[32],
                                              unsigned short* queue, int nq, int cap, int lane) {
     constexpr unsigned int U0 = 0xFE01FE01u, U1 = 0x01FE01FEu;   // steps 0-3: bits 9..16, 25..31, 0; steps 4-7: the rest
@@ -188,12 +190,26 @@ __device__ __forceinline__ int enqueue_chunk(unsigned int mb, unsigned int md, u
         // bright bits stay, dark bits move 8 up (into the other unit's positions, which are masked out here)
         unsigned int c = (mb & um[u]) | __funnelshift_l(md & um[u], md & um[u], 8);
         c = __funnelshift_r(c, c, 8 * u);
-        unsigned short* w = queue + pos[u];
-        const unsigned short* l = lut[u];
-        while (c) {
-            const int k = 31 - __clz(c);
-            c ^= 1u << k;
-            *w++ = (unsigned short)(laneEntry + l[k]);
+        if (SMEM) {
+            unsigned int w = smem_u32(queue) + 2u * (unsigned int)pos[u];
+            const unsigned int l = smem_u32(lut[u]);
+            while (c) {
+                const unsigned int k = 31u - (unsigned int)__clz(c);
+                c ^= 1u << k;
+                unsigned short v;
+                asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(l + 2u * k));
+                v = (unsigned short)(laneEntry + v);
+                asm volatile("st.shared.u16 [%0], %1;" ::"r"(w), "h"(v) : "memory");
+                w += 2;
+            }
+        } else {
+            unsigned short* w = queue + pos[u];
+            const unsigned short* l = lut[u];
+            while (c) {
+                const int k = 31 - __clz(c);
+                c ^= 1u << k;
+                *w++ = (unsigned short)(laneEntry + l[k]);
+            }
         }
     }
     return nqNew;
@@ -202,9 +218,20 @@ __device__ __forceinline__ int enqueue_chunk(unsigned int mb, unsigned int md, u
 // A-C for one cell at threshold th: everything that reads the tile.  Returns the number of corners (W.queue[0, nc),
 // scores in the score map).  A cell with more candidates than the shared-memory queue holds moves its queue to the
 // warp's global scratch.
+// T == 2: the mask bits of this lane's pixels (4-px groups q and q + 4 of every row) that lie inside a cell of width cw
+__device__ __forceinline__ unsigned int column_mask2(int cw, int q) {
+    unsigned int vA0, vB0, vA1, vB1;
+    valid_pairs(cw - 4 * q, vA0, vB0);
+    valid_pairs(cw - 16 - 4 * q, vA1, vB1);
+    const unsigned int m0 = vA0 | (vB0 << 1), m1 = vA1 | (vB1 << 1);   // step 0 and step 1; steps 2i, 2i + 1 are these rotated by 4i
+    const unsigned int m = m0 | __funnelshift_l(m1, m1, 2);
+    const unsigned int m2 = m | __funnelshift_l(m, m, 4);
+    return m2 | __funnelshift_l(m2, m2, 8);
+}
+
 template <int BW>
 __device__ __forceinline__ int fast_front(FwWarp& W, const FastWarpPlan::Level& F, const unsigned short (*lut)[32], int SP, int cw, int ch,
-                                          int mis, int th, int lane, unsigned int ltMask, unsigned int one) {
+                                          int mis, int th, int lane, unsigned int ltMask, unsigned int one, unsigned int colMask2) {
     // ---- A + B
     const unsigned int K = FW_PASS - (unsigned int)(th + 1) * 0x00010001u;
     FwAlign al;
@@ -222,15 +249,6 @@ __device__ __forceinline__ int fast_front(FwWarp& W, const FastWarpPlan::Level& 
     const unsigned char* rowPtr = W.tile + (mis & ~3) + (r + 3) * BW + 4 * q;   // aligned word of pixel (4q - 4, r)
     const int T = F.T, chunkSteps = F.chunkSteps, steps = F.steps;
     const int chunkRows = 8 * (chunkSteps / T);
-    unsigned int colMask2 = 0;      // T == 2: the mask bits of this lane's pixels that lie inside the cell
-    if (T == 2) {
-        unsigned int vA0, vB0, vA1, vB1;
-        valid_pairs(cw - 4 * q, vA0, vB0);
-        valid_pairs(cw - 16 - 4 * q, vA1, vB1);
-        const unsigned int m0 = vA0 | (vB0 << 1), m1 = vA1 | (vB1 << 1);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) colMask2 |= __funnelshift_l((i & 1) ? m1 : m0, (i & 1) ? m1 : m0, 2 * i);
-    }
     int nq = 0;
 #pragma unroll 1
     for (int j0 = 0, y0 = r; j0 < steps; j0 += chunkSteps, y0 += chunkRows, rowPtr += chunkRows * BW) {
@@ -268,14 +286,15 @@ __device__ __forceinline__ int fast_front(FwWarp& W, const FastWarpPlan::Level& 
                 if (++t == T) { t = 0; y += 8; rp += 8 * BW; }
             }
         }
-        int n2 = enqueue_chunk(mb, md, (unsigned int)((y0 << 6) | (4 * q)), lut, W.queue, nq, W.queueCap, lane);
+        int n2 = W.queue != W.globalQueue ? enqueue_chunk<true>(mb, md, (unsigned int)((y0 << 6) | (4 * q)), lut, W.queue, nq, W.queueCap, lane)
+                                           : enqueue_chunk<false>(mb, md, (unsigned int)((y0 << 6) | (4 * q)), lut, W.queue, nq, W.queueCap, lane);
         if (n2 < 0) {
             __syncwarp();
             for (int i = lane; i < nq; i += 32) W.globalQueue[i] = W.queue[i];
             W.queue = W.globalQueue;
             W.queueCap = W.globalCap;
             __syncwarp();
-            n2 = enqueue_chunk(mb, md, (unsigned int)((y0 << 6) | (4 * q)), lut, W.queue, nq, W.queueCap, lane);
+            n2 = enqueue_chunk<false>(mb, md, (unsigned int)((y0 << 6) | (4 * q)), lut, W.queue, nq, W.queueCap, lane);
         }
         nq = n2;
     }
@@ -426,6 +445,8 @@ __global__ void __launch_bounds__(FW_WARPS * 32, 3) fast_warp_kernel(const __gri
         request_tile(c0, frame);
     }
     unsigned int parity = 0;
+    int maskCw = -1;
+    unsigned int colMask2 = 0;
     while (it < total) {
         // ---- ticket of the next cell: asked for now, looked at after this cell's first scoring pass
         unsigned int nIt = 0;
@@ -434,6 +455,10 @@ __global__ void __launch_bounds__(FW_WARPS * 32, 3) fast_warp_kernel(const __gri
         const int cellX0 = (int)(short)(c0.x >> 16), cellY0 = (int)(short)(c0.y & 0xffffu);
         const int cw = (int)(c0.y >> 16), ch = (int)(c0.z & 0xffffu), cellSlot = (int)c0.w;
         const int level = (int)(short)(c0.x & 0xffffu), mis = (kPadLeft + cellX0 - 4) & 15;
+        if (cw != maskCw) {   // the column mask of the pre-test changes only at a cell of another width (the last column of a level)
+            maskCw = cw;
+            colMask2 = column_mask2(cw, lane & 3);
+        }
         mbar_wait(bar, parity);
         parity ^= 1u;
         W.queue = smemQueue;
@@ -445,7 +470,7 @@ __global__ void __launch_bounds__(FW_WARPS * 32, 3) fast_warp_kernel(const __gri
         bool nextKnown = false, nextRequested = false;
         int sn, nc, th = P.iniTh;
         for (;;) {   // a second round at minThFAST is the reference's second cv::FAST call (:811-818)
-            nc = fast_front<BW>(W, F.lv[level], sLut[level], SP, cw, ch, mis, th, lane, ltMask, F.one);
+            nc = fast_front<BW>(W, F.lv[level], sLut[level], SP, cw, ch, mis, th, lane, ltMask, F.one, colMask2);
             FW_STAT(1, 1);
             if (!nextKnown) {
                 nIt = __shfl_sync(FW_FULL, nIt, 0);
