@@ -123,6 +123,12 @@ int orbx_compute_stereo_matches_device(orbx_handle left, int left_frame, orbx_ha
 int orbx_debug_candidates(orbx_handle h, int frame, int level, orb_keypoint* out, int cap, int* n);
 int orbx_debug_blurred(orbx_handle h, int frame, int level, uint8_t* out /* w*h */);
 /* number of kernel launches issued by the last extract call */
+/* Device copies of what the last HOST extract call returned (orbx_extract / orbx_extract_batch): keypoints, descriptors
+ * and count of frame `frame`, valid until the next call on the handle; *stream = the handle's stream (already synchronised
+ * when the host call returned).  With orbm_frame_create_device the Frame constructor's remaining work (UndistortKeyPoints,
+ * AssignFeaturesToGrid, Frame.cc:75-109) runs on these without a second upload.                                     */
+int orbx_last_device_outputs(orbx_handle h, int frame, const orb_keypoint** d_keys, const uint8_t** d_descriptors,
+                             const int** d_count, int* capacity, void** stream);
 int orbx_last_launch_count(orbx_handle h, int* n);
 /* Per-kernel device timing for benchmarks: when on, every extract call brackets its kernels with CUDA events on the
  * launching stream (no synchronisation added).  orbx_kernel_times synchronises, returns the milliseconds summed over

@@ -91,6 +91,26 @@ class RefMatcher:
         return RefFrame(self, keys_un, desc, bounds)
 
 
+def adapter_chain_init(img_a, img_b, nfeatures=1000, window=100, ratio=0.9, cap=4096):
+    """adpm_chain_init (adapter build only): extraction -> RegisterFrame -> SearchForInitialization twice on cached device
+    frames.  Returns (keysA, descA, keysB, descB, matches12 of call 1, n1, n2, cache hits, cache misses)."""
+    L = C.CDLL(ADAPTER_LIB)
+    h, w = img_a.shape
+    ka = np.zeros(cap, KP_DTYPE); kb = np.zeros(cap, KP_DTYPE)
+    da = np.zeros((cap, 32), np.uint8); db = np.zeros((cap, 32), np.uint8)
+    m12 = np.full(cap, -1, np.int32)
+    counts = np.zeros(4, np.int32)
+    stats = np.zeros(2, np.int64)
+    a = np.ascontiguousarray(img_a, np.uint8); b = np.ascontiguousarray(img_b, np.uint8)
+    L.adpm_chain_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float] + [C.c_void_p] * 4 + \
+                                 [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    rc = L.adpm_chain_init(_p(a), _p(b), w, h, nfeatures, window, ratio, _p(ka), _p(da), _p(kb), _p(db), cap, _p(m12), _p(counts),
+                           _p(stats))
+    assert rc == 0
+    na, nb = int(counts[0]), int(counts[1])
+    return ka[:na], da[:na], kb[:nb], db[:nb], m12[:na], int(counts[2]), int(counts[3]), int(stats[0]), int(stats[1])
+
+
 class RefFrame:
     def __init__(self, ref, keys_un, desc, bounds):
         self.lib = ref.lib

@@ -9,8 +9,10 @@
 using namespace std;
 
 #define ORBB200_WITH_ORBSLAM
+#include "ORBextractor.h"
 #include "ORBmatcher.h"
 #include "ORBmatcher_orbslam.inl"
 
+#define GLUE_ADAPTER
 #define GLUE(name) adpm_##name
 #include "match_glue.inc"

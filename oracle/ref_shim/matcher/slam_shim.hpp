@@ -66,6 +66,10 @@ struct FrameData {
     DBoW2::FeatureVector mFeatVec;
     float fx = 1, fy = 1, cx = 0, cy = 0, mbf = 0, mb = 0;
     float mnMinX = 0, mnMinY = 0, mnMaxX = 0, mnMaxY = 0;
+    // Frame.h:190 / KeyFrame.h: every object gets the next id at construction, copies keep it
+    static unsigned long& nNextId() { static unsigned long n = 0; return n; }
+    unsigned long mnId = nNextId()++;
+    cv::Mat mDistCoef = cv::Mat(4, 1, CV_32F);   // zero-initialised: no distortion
     orbo::FrameArrays fa;
 
     virtual ~FrameData() {}

@@ -112,6 +112,33 @@ def test_reference_signatures_on_object_graphs():
             same(got, run_case(c, live.frame(ka, da, bounds), live.frame(kb, db, bounds), ka, da, kb, db))
 
 
+def test_adapter_frame_cache_and_device_hand_over(oracle):
+    """adapter: ORBextractor::operator() -> ORBmatcher::RegisterFrame (device frame built from what the extractor left on the
+    device, cached under Frame::mnId) -> SearchForInitialization from two ORBmatcher objects, the second on a copy of the
+    Frame.  No search uploads keypoints (4 cache hits, 0 misses), the handle pool hands the same matcher back, and the matches
+    equal the oracle's on the host keypoints the extractor returned."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_matcher
+    from orbb200.synth import shifted_pair
+    if not ref_matcher.adapter_available():
+        pytest.skip("oracle/_ref/libmatch_adapter.so is built only where /root/reference is mounted")
+    a, b = shifted_pair(4)
+    ka, da, kb, db, m12, n1, n2, hits, misses = ref_matcher.adapter_chain_init(a, b)
+    assert (hits, misses) == (4, 0)
+    ex = orbb200.Extractor(1000)
+    k, d = ex(a)
+    assert k.tobytes() == ka.tobytes() and np.array_equal(d, da)
+    ex.close()
+    bounds = (0.0, 0.0, 752.0, 480.0)
+    o1, o2 = oracle.frame(ka, da, bounds), oracle.frame(kb, db, bounds)
+    prev = np.stack([ka["x"], ka["y"]], 1).astype(np.float32)
+    rn, rm12, rp = o1.search_init(o2, prev, 100, 0.9, True)
+    assert n1 == rn and np.array_equal(m12, rm12) and rn > 50
+    rn2, _, _ = o1.search_init(o2, rp, 100, 0.9, True)           # the second call sees the updated vbPrevMatched
+    assert n2 == rn2
+
+
 def test_extractor_opencv_signature(tmp_path):
     """adapter/ORBextractor.h with -DORBB200_WITH_OPENCV, compiled against the OpenCV stand-in the reference's own
     ORBextractor.cc is built against (oracle/ref_shim/include): operator()(InputArray, InputArray, vector<KeyPoint>&,

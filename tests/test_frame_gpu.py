@@ -107,6 +107,40 @@ def test_device_resident_frame(matcher, oracle, distorted):
     ex.close()
 
 
+def test_host_extract_then_device_frame(matcher, oracle):
+    """The live loop without a second upload: orbx_extract (host keypoints out, as ORBextractor::operator() must) leaves its
+    outputs on the device; orbx_last_device_outputs + orbm_frame_create_device build the Frame from them, and the search on
+    two such frames equals the host chain.  A device call or a stale index is refused."""
+    K4, dist, (w, h) = CAMERAS[0]
+    cam = _cam(K4, dist)
+    a, b = shifted_pair(6, w, h)
+    bounds = matcher.image_bounds(cam, w, h)
+    ex = orbb200.Extractor(1000, max_width=w, max_height=h, max_batch=1)
+    frames, host = [], []
+    for img in (a, b):
+        k, d = ex(img)
+        dk, dd, dc, cap, st = ex.last_device_outputs(0)
+        frames.append(orbb200.Frame.from_device(matcher, dk, dd, dc, cap, bounds, cam, st))
+        host.append((k, d))
+    with pytest.raises(orbb200.OrbError):
+        ex.last_device_outputs(1)
+    oframes = []
+    for (k, d), f in zip(host, frames):
+        ru = k.copy()
+        xy = oracle.undistort(np.stack([k["x"], k["y"]], 1), K4, dist)
+        ru["x"], ru["y"] = xy[:, 0], xy[:, 1]
+        fk, fd = f.download()
+        assert fk.tobytes() == ru.tobytes() and np.array_equal(fd, d)
+        oframes.append(oracle.frame(ru, d, tuple(bounds)))
+    prev = np.stack([oframes[0].keys["x"], oframes[0].keys["y"]], 1).copy()
+    n_gpu, m_gpu, p_gpu = matcher.search_for_initialization(frames[0], frames[1], prev.copy(), 100, 0.9, True)
+    n_ref, m_ref, p_ref = oframes[0].search_init(oframes[1], prev.copy(), 100, 0.9, True)
+    assert n_gpu == n_ref and n_ref > 20 and np.array_equal(m_gpu, m_ref) and np.array_equal(p_gpu, p_ref)
+    for f in frames:
+        f.close()
+    ex.close()
+
+
 def test_device_frame_rejects_bad_arguments(matcher):
     torch = pytest.importorskip("torch")
     d_k = torch.zeros((4, 7), dtype=torch.int32, device="cuda")

@@ -9,6 +9,10 @@
 #ifndef ORBB200_ADAPTER_ORBMATCHER_H
 #define ORBB200_ADAPTER_ORBMATCHER_H
 
+#include <list>
+#include <map>
+#include <memory>
+#include <mutex>
 #include <set>
 #include <stdexcept>
 #include <string>
@@ -19,6 +23,8 @@
 
 namespace ORB_SLAM2 {
 
+class ORBextractor;
+
 // What a search reads of a Frame or KeyFrame. Owns the device copy + 64x48 grid (Frame.cc:574-589).
 class FrameView {
 public:
@@ -28,6 +34,8 @@ public:
         if (orbm_frame_create(m, keysUn, descriptors, n, minX, minY, maxX, maxY, &f_) != ORB_OK)
             throw std::runtime_error(std::string("orbb200: ") + orb_last_error());
     }
+    // adopts a frame that already lives on the device (orbm_frame_create_device)
+    FrameView(orbm_frame f, int n) : f_(f), n_(n) {}
     ~FrameView() { orbm_frame_destroy(f_); }
     FrameView(const FrameView&) = delete;
     FrameView& operator=(const FrameView&) = delete;
@@ -40,6 +48,97 @@ private:
     int n_ = 0;
 };
 
+namespace orbb_detail {
+
+// The reference constructs an ORBmatcher on the stack at every call site (Tracking.cc:1644, 2084, ...; LocalMapping.cc,
+// LoopClosing.cc), and a Frame / KeyFrame is searched many times over its life.  Two process-wide pieces keep that cheap:
+//   * a pool of matcher handles per device (stream + workspaces are created once, an ORBmatcher borrows one);
+//   * per handle, an LRU cache of device-resident frames keyed by (Frame | KeyFrame, mnId, N): the upload of mvKeysUn /
+//     mDescriptors and the grid build happen on the first search that sees the object, not on every call.  A Frame's
+//     keypoints never change after construction and copies of a Frame keep its mnId (Frame.cc:38-72).
+struct ViewRef {
+    std::shared_ptr<FrameView> p;
+    operator const FrameView&() const { return *p; }
+};
+
+class FrameCache {
+public:
+    struct Key {
+        int kind;
+        unsigned long id;
+        int n;
+        bool operator<(const Key& o) const { return kind != o.kind ? kind < o.kind : id != o.id ? id < o.id : n < o.n; }
+    };
+    std::shared_ptr<FrameView> find(const Key& k) {
+        std::map<Key, std::list<Entry>::iterator>::iterator it = index_.find(k);
+        if (it == index_.end()) { ++misses; return std::shared_ptr<FrameView>(); }
+        lru_.splice(lru_.begin(), lru_, it->second);
+        ++hits;
+        return it->second->view;
+    }
+    void insert(const Key& k, const std::shared_ptr<FrameView>& v) {
+        std::map<Key, std::list<Entry>::iterator>::iterator it = index_.find(k);
+        if (it != index_.end()) { lru_.erase(it->second); index_.erase(it); }
+        lru_.push_front(Entry{k, v});
+        index_[k] = lru_.begin();
+        while (lru_.size() > capacity) { index_.erase(lru_.back().key); lru_.pop_back(); }
+    }
+    void clear() { lru_.clear(); index_.clear(); }
+    size_t capacity = 256;
+    long hits = 0, misses = 0;
+
+private:
+    struct Entry { Key key; std::shared_ptr<FrameView> view; };
+    std::list<Entry> lru_;
+    std::map<Key, std::list<Entry>::iterator> index_;
+};
+
+struct MatcherSlot {
+    orbm_handle h = nullptr;
+    int device = 0;
+    FrameCache cache;
+};
+
+class HandlePool {
+public:
+    static HandlePool& get() { static HandlePool p; return p; }
+    MatcherSlot* acquire(int device) {
+        {
+            std::lock_guard<std::mutex> g(m_);
+            std::vector<MatcherSlot*>& f = free_[device];
+            if (!f.empty()) { MatcherSlot* s = f.back(); f.pop_back(); return s; }   // LIFO: a thread gets its last handle back
+        }
+        MatcherSlot* s = new MatcherSlot;
+        s->device = device;
+        if (orbm_create(device, &s->h) != ORB_OK) { delete s; throw std::runtime_error(std::string("orbb200: ") + orb_last_error()); }
+        std::lock_guard<std::mutex> g(m_);
+        all_.push_back(s);
+        return s;
+    }
+    void release(MatcherSlot* s) {
+        std::lock_guard<std::mutex> g(m_);
+        free_[s->device].push_back(s);
+    }
+    // cache statistics over all handles (tests, tuning)
+    void stats(long* hits, long* misses) {
+        std::lock_guard<std::mutex> g(m_);
+        *hits = *misses = 0;
+        for (size_t i = 0; i < all_.size(); ++i) { *hits += all_[i]->cache.hits; *misses += all_[i]->cache.misses; }
+    }
+    // drops every cached frame and idle handle (call before the CUDA context goes away, or to bound memory)
+    void clear() {
+        std::lock_guard<std::mutex> g(m_);
+        for (size_t i = 0; i < all_.size(); ++i) all_[i]->cache.clear();
+    }
+
+private:
+    std::mutex m_;
+    std::map<int, std::vector<MatcherSlot*> > free_;
+    std::vector<MatcherSlot*> all_;
+};
+
+}  // namespace orbb_detail
+
 class ORBmatcher {
 public:
     static const int TH_LOW = 50;
@@ -47,9 +146,10 @@ public:
     static const int HISTO_LENGTH = 30;
 
     ORBmatcher(float nnratio = 0.6, bool checkOri = true, int device = 0) : mfNNratio(nnratio), mbCheckOrientation(checkOri) {
-        check(orbm_create(device, &h_));
+        slot_ = orbb_detail::HandlePool::get().acquire(device);
+        h_ = slot_->h;
     }
-    ~ORBmatcher() { orbm_destroy(h_); }
+    ~ORBmatcher() { orbb_detail::HandlePool::get().release(slot_); }
     ORBmatcher(const ORBmatcher&) = delete;
     ORBmatcher& operator=(const ORBmatcher&) = delete;
     orbm_handle handle() { return h_; }
@@ -192,6 +292,11 @@ public:
     int SearchBySim3(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<MapPoint*>& vpMatches12, const float& s12, const cv::Mat& R12,
                      const cv::Mat& t12, const float th);
     static int DescriptorDistance(const cv::Mat& a, const cv::Mat& b);
+    // Hand-over from the extractor without a second upload: call right after ExtractORB in Frame's constructor, once
+    // mnId, N, mK, mDistCoef and the image bounds are set (Frame.cc:75-109).  The Frame's device copy (undistorted
+    // keypoints, descriptors, grid) is built from what `extractor`'s last call left on the device and cached under the
+    // Frame's mnId; the searches then find it instead of uploading mvKeysUn / mDescriptors.  frameIndex: 0 = left image.
+    static void RegisterFrame(const Frame& F, ORBextractor& extractor, int frameIndex = 0, int device = 0);
 #endif
 
 protected:
@@ -200,6 +305,10 @@ protected:
 
 private:
     orbm_handle h_ = nullptr;
+    orbb_detail::MatcherSlot* slot_ = nullptr;
+#ifdef ORBB200_WITH_ORBSLAM
+    template <class F> orbb_detail::ViewRef view_of(const F& f);
+#endif
     static void check(int st) {
         if (st != ORB_OK) throw std::runtime_error(std::string("orbb200: ") + orb_last_error());
     }

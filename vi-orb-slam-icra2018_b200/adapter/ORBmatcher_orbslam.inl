@@ -21,10 +21,8 @@ inline std::vector<unsigned char> rows_of(const cv::Mat& d) {
     for (int i = 0; i < d.rows; ++i) std::memcpy(&out[(size_t)i * 32], d.ptr(i), 32);
     return out;
 }
-template <class F> inline FrameView view_of(orbm_handle h, const F& f) {
-    return FrameView(h, keys_of(f.mvKeysUn).data(), rows_of(f.mDescriptors).data(), (int)f.mvKeysUn.size(), f.mnMinX, f.mnMinY,
-                     f.mnMaxX, f.mnMaxY);
-}
+inline int frame_kind(const Frame&) { return 0; }
+inline int frame_kind(const KeyFrame&) { return 1; }
 
 inline ORBmatcher::FeatureVectorCSR flatten(const DBoW2::FeatureVector& fv) {
     ORBmatcher::FeatureVectorCSR c;
@@ -63,6 +61,48 @@ inline Projected project_into(MapPoint* pMP, const cv::Mat& X, const cv::Mat& p3
 
 }  // namespace orbb_detail
 
+// The device copy of a Frame / KeyFrame: from this handle's cache, else uploaded (mvKeysUn, mDescriptors, grid) and cached.
+template <class F> inline orbb_detail::ViewRef ORBmatcher::view_of(const F& f) {
+    const orbb_detail::FrameCache::Key key = {orbb_detail::frame_kind(f), (unsigned long)f.mnId, (int)f.mvKeysUn.size()};
+    orbb_detail::ViewRef r;
+    r.p = slot_->cache.find(key);
+    if (!r.p) {
+        r.p = std::make_shared<FrameView>(h_, orbb_detail::keys_of(f.mvKeysUn).data(), orbb_detail::rows_of(f.mDescriptors).data(),
+                                          (int)f.mvKeysUn.size(), f.mnMinX, f.mnMinY, f.mnMaxX, f.mnMaxY);
+        slot_->cache.insert(key, r.p);
+    }
+    return r;
+}
+
+inline void ORBmatcher::RegisterFrame(const Frame& F, ORBextractor& extractor, int frameIndex, int device) {
+    const orb_keypoint* dKeys = nullptr;
+    const unsigned char* dDesc = nullptr;
+    const int* dCount = nullptr;
+    int capacity = 0;
+    void* stream = nullptr;
+    check(orbx_last_device_outputs(extractor.handle(), frameIndex, &dKeys, &dDesc, &dCount, &capacity, &stream));
+    orb_camera cam = orb_camera();
+    cam.fx = F.fx; cam.fy = F.fy; cam.cx = F.cx; cam.cy = F.cy;
+    const int nd = F.mDistCoef.rows * F.mDistCoef.cols;
+    if (nd > 0) cam.k1 = F.mDistCoef.at<float>(0);
+    if (nd > 1) cam.k2 = F.mDistCoef.at<float>(1);
+    if (nd > 2) cam.p1 = F.mDistCoef.at<float>(2);
+    if (nd > 3) cam.p2 = F.mDistCoef.at<float>(3);
+    if (nd > 4) cam.k3 = F.mDistCoef.at<float>(4);
+    orbb_detail::MatcherSlot* slot = orbb_detail::HandlePool::get().acquire(device);
+    orbm_frame f = nullptr;
+    const int st = orbm_frame_create_device(slot->h, dKeys, dDesc, dCount, capacity, &cam, F.mnMinX, F.mnMinY, F.mnMaxX, F.mnMaxY,
+                                            stream, &f);
+    if (st == ORB_OK) {
+        int n = 0;
+        orbm_frame_size(f, &n);
+        const orbb_detail::FrameCache::Key key = {0, (unsigned long)F.mnId, n};
+        slot->cache.insert(key, std::make_shared<FrameView>(f, n));
+    }
+    orbb_detail::HandlePool::get().release(slot);
+    check(st);
+}
+
 // ORBmatcher.cc:1675-1691. One pair is host work; batches go through DescriptorDistances().
 inline int ORBmatcher::DescriptorDistance(const cv::Mat& a, const cv::Mat& b) {
     const unsigned int* pa = a.ptr<unsigned int>();
@@ -75,7 +115,7 @@ inline int ORBmatcher::DescriptorDistance(const cv::Mat& a, const cv::Mat& b) {
 // ORBmatcher.cc:405-520
 inline int ORBmatcher::SearchForInitialization(Frame& F1, Frame& F2, std::vector<cv::Point2f>& vbPrevMatched,
                                                std::vector<int>& vnMatches12, int windowSize) {
-    FrameView v1 = orbb_detail::view_of(h_, F1), v2 = orbb_detail::view_of(h_, F2);
+    orbb_detail::ViewRef v1 = view_of(F1), v2 = view_of(F2);
     std::vector<float> prev(vbPrevMatched.size() * 2);
     for (size_t i = 0; i < vbPrevMatched.size(); ++i) { prev[2 * i] = vbPrevMatched[i].x; prev[2 * i + 1] = vbPrevMatched[i].y; }
     const int n = SearchForInitialization(v1, v2, prev, vnMatches12, windowSize);
@@ -120,7 +160,7 @@ inline int ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& Last
     std::vector<unsigned char> occupied(CurrentFrame.N, 0);
     for (int i = 0; i < CurrentFrame.N; ++i)
         occupied[i] = CurrentFrame.mvpMapPoints[i] && CurrentFrame.mvpMapPoints[i]->Observations() > 0;
-    FrameView cur = orbb_detail::view_of(h_, CurrentFrame);
+    orbb_detail::ViewRef cur = view_of(CurrentFrame);
     std::vector<int> curMatch;
     const int n = SearchByProjection(cur, CurrentFrame.mvScaleFactors, CurrentFrame.mvuRight.data(), CurrentFrame.mbf, pose, q,
                                      qdesc.data(), th, bForward ? 1 : (bBackward ? 2 : 0), occupied.data(), curMatch);
@@ -147,7 +187,7 @@ inline int ORBmatcher::SearchByProjection(Frame& F, const std::vector<MapPoint*>
     }
     std::vector<unsigned char> occupied(F.N, 0);
     for (int i = 0; i < F.N; ++i) occupied[i] = F.mvpMapPoints[i] && F.mvpMapPoints[i]->Observations() > 0;
-    FrameView v = orbb_detail::view_of(h_, F);
+    orbb_detail::ViewRef v = view_of(F);
     std::vector<int> match;
     const int n = SearchByProjection(v, F.mvScaleFactors, F.mvuRight.data(), q, qdesc.data(), th, occupied.data(), match);
     for (int i = 0; i < F.N; ++i)
@@ -170,7 +210,7 @@ inline int ORBmatcher::SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, cv
     float f12[9];
     for (int r = 0; r < 3; ++r)
         for (int c = 0; c < 3; ++c) f12[3 * r + c] = F12.at<float>(r, c);
-    FrameView v1 = orbb_detail::view_of(h_, *pKF1), v2 = orbb_detail::view_of(h_, *pKF2);
+    orbb_detail::ViewRef v1 = view_of(*pKF1), v2 = view_of(*pKF2);
     return SearchForTriangulation(v1, v2, fv1, fv2, has1.data(), has2.data(), pKF1->mvuRight.data(), pKF2->mvuRight.data(), f12,
                                   ex, ey, pKF2->mvScaleFactors, pKF2->mvLevelSigma2, vMatchedPairs, bOnlyStereo);
 }
@@ -182,7 +222,7 @@ inline int ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, std::vector<MapPoint
     vpMapPointMatches = std::vector<MapPoint*>(F.N, static_cast<MapPoint*>(NULL));
     std::vector<unsigned char> valid1(vpMapPointsKF.size());
     for (size_t i = 0; i < vpMapPointsKF.size(); ++i) valid1[i] = vpMapPointsKF[i] && !vpMapPointsKF[i]->isBad();
-    FrameView v1 = orbb_detail::view_of(h_, *pKF), v2 = orbb_detail::view_of(h_, F);
+    orbb_detail::ViewRef v1 = view_of(*pKF), v2 = view_of(F);
     std::vector<int> m12, m21;
     const int n = SearchByBoW(v1, v2, orbb_detail::flatten(pKF->mFeatVec), orbb_detail::flatten(F.mFeatVec), valid1.data(), NULL,
                               false, m12, m21);
@@ -198,7 +238,7 @@ inline int ORBmatcher::SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<M
     std::vector<unsigned char> valid1(vp1.size()), valid2(vp2.size());
     for (size_t i = 0; i < vp1.size(); ++i) valid1[i] = vp1[i] && !vp1[i]->isBad();
     for (size_t i = 0; i < vp2.size(); ++i) valid2[i] = vp2[i] && !vp2[i]->isBad();
-    FrameView v1 = orbb_detail::view_of(h_, *pKF1), v2 = orbb_detail::view_of(h_, *pKF2);
+    orbb_detail::ViewRef v1 = view_of(*pKF1), v2 = view_of(*pKF2);
     std::vector<int> m12, m21;
     const int n = SearchByBoW(v1, v2, orbb_detail::flatten(pKF1->mFeatVec), orbb_detail::flatten(pKF2->mFeatVec), valid1.data(),
                               valid2.data(), true, m12, m21);
@@ -239,7 +279,7 @@ inline int ORBmatcher::SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, co
     }
     std::vector<unsigned char> occupied(CurrentFrame.N, 0);
     for (int i = 0; i < CurrentFrame.N; ++i) occupied[i] = CurrentFrame.mvpMapPoints[i] != NULL;
-    FrameView cur = orbb_detail::view_of(h_, CurrentFrame);
+    orbb_detail::ViewRef cur = view_of(CurrentFrame);
     std::vector<int> curMatch;
     const int n = SearchByProjection(cur, CurrentFrame.mvScaleFactors, q, qdesc.data(), th, 0, ORBdist, occupied.data(), curMatch);
     for (int i2 = 0; i2 < CurrentFrame.N; ++i2)
@@ -276,10 +316,10 @@ inline int ORBmatcher::SearchByProjection(KeyFrame* pKF, cv::Mat Scw, const std:
     }
     std::vector<unsigned char> occupied(pKF->N, 0);
     for (int i = 0; i < pKF->N; ++i) occupied[i] = vpMatched[i] != NULL;
-    FrameView kf = orbb_detail::view_of(h_, *pKF);
+    orbb_detail::ViewRef kf = view_of(*pKF);
     std::vector<int> match(pKF->N, -1);
     int n = 0;
-    check(orbm_search_by_projection_ex(h_, kf.get(), pKF->mvScaleFactors.data(), (int)pKF->mvScaleFactors.size(), NULL, 0.f,
+    check(orbm_search_by_projection_ex(h_, kf.p->get(), pKF->mvScaleFactors.data(), (int)pKF->mvScaleFactors.size(), NULL, 0.f,
                                        q.data(), qdesc.data(), (int)q.size(), (float)th, 3, TH_LOW, occupied.data(), match.data(),
                                        0, &n));
     for (int i = 0; i < pKF->N; ++i)
@@ -307,7 +347,7 @@ inline int ORBmatcher::Fuse(KeyFrame* pKF, const std::vector<MapPoint*>& vpMapPo
         a.valid = 1;
         std::memcpy(&qdesc[i * 32], pMP->GetDescriptor().ptr(0), 32);
     }
-    FrameView kf = orbb_detail::view_of(h_, *pKF);
+    orbb_detail::ViewRef kf = view_of(*pKF);
     std::vector<int> bestIdx, bestDist;
     ProjectedBest(kf, q, qdesc.data(), true, pKF->mvuRight.data(), pKF->mvInvLevelSigma2, bestIdx, bestDist);
     int nFused = 0;
@@ -357,7 +397,7 @@ inline int ORBmatcher::Fuse(KeyFrame* pKF, cv::Mat Scw, const std::vector<MapPoi
         a.valid = 1;
         std::memcpy(&qdesc[i * 32], pMP->GetDescriptor().ptr(0), 32);
     }
-    FrameView kf = orbb_detail::view_of(h_, *pKF);
+    orbb_detail::ViewRef kf = view_of(*pKF);
     std::vector<int> bestIdx, bestDist;
     ProjectedBest(kf, q, qdesc.data(), false, NULL, pKF->mvInvLevelSigma2, bestIdx, bestDist);
     int nFused = 0;
@@ -421,7 +461,7 @@ inline int ORBmatcher::SearchBySim3(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<
     std::vector<unsigned char> d1, d2;
     Side::queries(vp1, done1, R1w, t1w, sR21, t21, pKF2, th, q1, d1);   // :1141-1219
     Side::queries(vp2, done2, R2w, t2w, sR12, t12, pKF1, th, q2, d2);   // :1222-1299
-    FrameView v1 = orbb_detail::view_of(h_, *pKF1), v2 = orbb_detail::view_of(h_, *pKF2);
+    orbb_detail::ViewRef v1 = view_of(*pKF1), v2 = view_of(*pKF2);
     std::vector<int> b1, dist1, b2, dist2;
     ProjectedBest(v2, q1, d1.data(), false, NULL, pKF2->mvInvLevelSigma2, b1, dist1);
     ProjectedBest(v1, q2, d2.data(), false, NULL, pKF1->mvInvLevelSigma2, b2, dist2);

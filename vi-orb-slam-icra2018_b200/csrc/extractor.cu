@@ -62,6 +62,7 @@ struct orbx_extractor {
     DevBuf stKeysL, stDescL, stKeysR, stDescR, stOut;   // staging of orbx_compute_stereo_matches
     int lastFrames = 0, lastCapacity = 0;   // arena capacity in frames / caller capacity of the last call
     int residentFrames = 0;                 // frames of the last call whose pyramids are in the arena (slots 0 .. residentFrames-1)
+    bool lastWasHost = false;               // the last call was a host call: its outputs are still in dKps / dDesc / dCount
     int launches = 0;
     double stageMs[3] = {0, 0, 0};
     bool timed = false;
@@ -450,6 +451,7 @@ int orbx_extract_batch_device(orbx_handle e, const uint8_t* dImages, int nFrames
         return fail(ORB_ERR_INVALID, "orbx_extract_batch_device: bad arguments");
     e->launches = 0;
     cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
+    e->lastWasHost = false;
     return enqueue(e, dImages, nFrames, w, h, stride, frameStride, dKps, dDesc, capacity, dCount, st, stream == nullptr);
 }
 
@@ -465,6 +467,7 @@ int orbx_extract_batch(orbx_handle e, const uint8_t* images, int nFrames, int w,
     }
     if (!kps || !desc || stride < w || capacity < 1) return fail(ORB_ERR_INVALID, "orbx_extract_batch: bad arguments");
     e->launches = 0;
+    e->lastWasHost = true;
     // The arena holds `super` frames; inside it the batch is cut into pipeline chunks so that the H2D copy of chunk k+1
     // and the D2H copy of chunk k-1 overlap the kernels of chunk k (three streams, events between them).
     const int super = std::min(e->maxBatch, 65535);
@@ -823,6 +826,20 @@ int orbx_kernel_times(orbx_handle e, double* ms5, int* nCalls) {
     }
     *nCalls = e->profCalls;
     e->profCalls = 0;
+    return ORB_OK;
+}
+
+int orbx_last_device_outputs(orbx_handle e, int frame, const orb_keypoint** dKeys, const uint8_t** dDesc, const int** dCount,
+                             int* capacity, void** stream) {
+    if (!e || !dKeys || !dDesc || !dCount || !capacity) return fail(ORB_ERR_INVALID, "orbx_last_device_outputs: null argument");
+    if (!e->lastWasHost) return fail(ORB_ERR_INVALID, "orbx_last_device_outputs: the last call on this handle was not a host extract call");
+    if (frame < 0 || frame >= e->residentFrames)
+        return fail(ORB_ERR_INVALID, "orbx_last_device_outputs: frame %d is not resident (%d are)", frame, e->residentFrames);
+    *dKeys = e->dKps.as<orb_keypoint>() + (size_t)frame * e->lastCapacity;
+    *dDesc = e->dDesc.as<uint8_t>() + (size_t)frame * e->lastCapacity * 32;
+    *dCount = e->dCount.as<int>() + frame;
+    *capacity = e->lastCapacity;
+    if (stream) *stream = e->stream;
     return ORB_OK;
 }
 

@@ -201,6 +201,14 @@ class Extractor:
         _check(self.L.orbx_last_launch_count(self.h, C.byref(n)))
         return n.value
 
+    def last_device_outputs(self, frame=0):
+        """Device pointers (ints) of what the last HOST extract call returned for `frame`:
+        (d_keys, d_descriptors, d_count, capacity, stream)"""
+        k, d, c, st = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+        cap = C.c_int()
+        _check(self.L.orbx_last_device_outputs(self.h, frame, C.byref(k), C.byref(d), C.byref(c), C.byref(cap), C.byref(st)))
+        return k.value, d.value, c.value, cap.value, st.value
+
     def set_profiling(self, on):
         _check(self.L.orbx_set_profiling(self.h, int(on)))
 

@@ -24,6 +24,7 @@ SIGNATURES = {
                                                  vp, vp, vp]),
     "orbx_debug_candidates": (i32, [vp, i32, i32, vp, i32, vp]),
     "orbx_debug_blurred": (i32, [vp, i32, i32, vp]),
+    "orbx_last_device_outputs": (i32, [vp, i32, vp, vp, vp, vp, vp]),
     "orbx_last_launch_count": (i32, [vp, vp]),
     "orbx_set_profiling": (i32, [vp, i32]),
     "orbx_kernel_times": (i32, [vp, vp, vp]),
