@@ -5,7 +5,7 @@ import sys
 from collections import OrderedDict
 
 src, cmd = sys.argv[1], (sys.argv[2] if len(sys.argv) > 2 else "")
-rows = [r for r in csv.reader(open(src)) if len(r) > 10 and r[0].isdigit()]
+rows = [r for r in csv.reader(open(src)) if len(r) > 10 and r[0].isdigit() and r[-3] == "gpu__time_duration.sum"]
 acc = OrderedDict()
 for r in rows:
     name = r[4].split("(")[0]
