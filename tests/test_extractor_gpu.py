@@ -111,6 +111,30 @@ def test_size_sweep(oracle):
         ex.close()
 
 
+def test_staged_batch_kernels_size_sweep(oracle):
+    """Batches of 8 frames and more take the bulk-async staged pyramid and blur kernels (one band of rows per CTA, staged
+    through shared memory): every padded pyramid level, every blurred level and the final keypoints / descriptors of the
+    first and of the last frame of a 9-frame batch equal the oracle, for EuRoC, KITTI and odd sizes (level widths that are
+    not multiples of 4 or 16, heights that are not multiples of the 16- and 32-row bands, odd band heights)."""
+    for i, (w, h, nf) in enumerate([(752, 480, 1000), (1241, 376, 2000), (331, 203, 300), (255, 257, 200), (640, 367, 500),
+                                    (513, 383, 400)]):
+        nlev = min(8, int(np.log(min(w, h) / 63.0) / np.log(1.2)) + 1)
+        frames = np.stack([synth_frame(900 + 10 * i + j, w, h) for j in range(9)])
+        ex = orbb200.Extractor(nf, 1.2, nlev, 20, 7, max_width=w, max_height=h, max_batch=9)
+        oe = oracle.extractor(nf, 1.2, nlev, 20, 7)
+        res = ex.extract_batch(frames)
+        for f in (0, 8):
+            rk, rd = oe.extract(frames[f])
+            for l in range(nlev):
+                assert np.array_equal(ex.level(l, f), oe.level_padded(l)), (w, h, f, "pyramid level %d" % l)
+                rb = oe.level_blurred(l)
+                if rb is not None:
+                    assert np.array_equal(ex.blurred(l, f), rb), (w, h, f, "blur level %d" % l)
+            _assert_same_keypoints(res[f][0], rk)
+            assert np.array_equal(res[f][1], rd)
+        ex.close()
+
+
 def test_batch_equals_single_and_oracle(oracle):
     frames = np.stack([synth_frame(100 + i, 752, 480) for i in range(5)] + [synth_frame(200, 752, 480, noise_only=True)])
     ex = orbb200.Extractor(1000, max_width=752, max_height=480, max_batch=4)   # 6 frames -> chunks of 4 + 2

@@ -15,6 +15,8 @@
 //     column is four IDP.2A (16-bit sums x 8-bit taps) over the last four row pairs; the accumulator starts at 2^15 so
 //     the rounding is free, and the four result bytes are picked with PRMT.
 // No shared memory, no barriers; all levels in one launch.
+#include <algorithm>
+
 #include "extractor.h"
 
 namespace orbb {
@@ -104,8 +106,138 @@ __global__ void __launch_bounds__(BL_THREADS) blur_kernel(const __grid_constant_
     }
 }
 
+// ---- batches: the same arithmetic with the input rows staged through shared memory --------------------------------
+// blur_kernel requests every input byte three times (a thread's three words overlap its neighbours') and pays 64-bit
+// address arithmetic and a row clamp per input row.  Here a CTA owns a band of 32 output rows over the full width of one
+// level of one frame: the 38 input rows of the band are CONTIGUOUS in the padded pyramid level, one cp.async.bulk brings
+// them into shared memory (each byte once, no registers held), and thread g walks down its 4-pixel column with 32-bit
+// shared-memory addresses.  One buffer per CTA and several CTAs per SM: while one waits for its copy the others compute.
+// Persistent CTAs stride over (frame, band); one launch per level (block size = the level's column groups).
+__global__ void __launch_bounds__(512)
+blur_staged_kernel(const __grid_constant__ ExtractParams P, int level, int nBands, int nTiles) {
+    extern __shared__ __align__(128) unsigned char bsm[];
+    const LevelGeom& L = P.lv[level];
+    const int tid = threadIdx.x;
+    const int groups = (L.w + 3) >> 2;
+    const int pitch = L.pitch, bpitch = L.bpitch;
+    const unsigned int bar = (unsigned int)__cvta_generic_to_shared(bsm), tile = bar + 128;
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const bool active = tid < groups;
+    const unsigned int colAddr = tile + kPadLeft + 4 * tid - 4;      // word that holds pixels 4g-4 .. 4g-1 of the band's first input row
+    unsigned int parity = 0;
+    for (int t = blockIdx.x; t < nTiles; t += gridDim.x) {
+        const int frame = t / nBands, band = t - frame * nBands;
+        const int y0 = band * BL_ROWS;
+        const int rowsOut = min(BL_ROWS, L.h - y0);
+        if (tid == 0) {
+            // input rows y0-3 .. y0+rowsOut+2 = padded rows y0+16 .. ; rowsOut + 6 of them
+            const unsigned char* src = P.pyr + (size_t)frame * P.pyrFrameBytes + L.pyrOff + (size_t)(y0 + kEdge - 3) * pitch;
+            const unsigned int bytes = (unsigned int)(rowsOut + 6) * (unsigned int)pitch;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(tile), "l"(src),
+                         "r"(bytes), "r"(bar)
+                         : "memory");
+        }
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "BL_WAIT_%=:\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+            "@p bra BL_DONE_%=;\n"
+            "bra BL_WAIT_%=;\n"
+            "BL_DONE_%=:\n"
+            "}\n" ::"r"(bar),
+            "r"(parity)
+            : "memory");
+        parity ^= 1u;
+        if (active) {
+            unsigned char* out = P.blur + (size_t)frame * P.blurFrameBytes + L.blurOff + (size_t)y0 * bpitch + 4 * tid;
+            unsigned int rowAddr = colAddr;
+            auto load_row = [&](unsigned int (&w)[3]) {
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w[0]) : "r"(rowAddr));
+                asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(w[1]) : "r"(rowAddr));
+                asm volatile("ld.shared.u32 %0, [%1+8];" : "=r"(w[2]) : "r"(rowAddr));
+                rowAddr += pitch;
+            };
+            auto hrow = [&](const unsigned int (&w)[3], unsigned int (&h)[4]) {
+                h[0] = __dp4a(__funnelshift_r(w[0], w[1], 8), TAP_H_LO, __dp4a(__funnelshift_r(w[1], w[2], 8), TAP_H_HI, 0u));
+                h[1] = __dp4a(__funnelshift_r(w[0], w[1], 16), TAP_H_LO, __dp4a(__funnelshift_r(w[1], w[2], 16), TAP_H_HI, 0u));
+                h[2] = __dp4a(__funnelshift_r(w[0], w[1], 24), TAP_H_LO, __dp4a(__funnelshift_r(w[1], w[2], 24), TAP_H_HI, 0u));
+                h[3] = __dp4a(w[1], TAP_H_LO, __dp4a(w[2], TAP_H_HI, 0u));
+            };
+            auto make_pair = [&](unsigned int (&pr)[4]) {      // the next two input rows, packed per pixel (even row in the low half)
+                unsigned int we[3], wo[3], he[4], ho[4];
+                load_row(we);
+                load_row(wo);
+                hrow(we, he);
+                hrow(wo, ho);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) pr[k] = __byte_perm(he[k], ho[k], 0x5410);
+            };
+            unsigned int p0[4], p1[4], p2[4], p3[4];
+            make_pair(p0);
+            make_pair(p1);
+            make_pair(p2);
+            // pair i completes output rows 2i-6 and 2i-5; the band's buffer holds rowsOut + 6 input rows, so the odd row of
+            // the last pair of an odd-height band is read from the row behind them (inside the buffer's slack) and unused
+#pragma unroll 2
+            for (int o = 0; o < rowsOut; o += 2) {
+                make_pair(p3);
+                unsigned int ve[4], vo[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    ve[k] = __dp2a_lo(p0[k], TAP_V_E0, __dp2a_hi(p1[k], TAP_V_E0, __dp2a_lo(p2[k], TAP_V_E1, __dp2a_hi(p3[k], TAP_V_E1, 32768u))));
+                    vo[k] = __dp2a_lo(p0[k], TAP_V_O0, __dp2a_hi(p1[k], TAP_V_O0, __dp2a_lo(p2[k], TAP_V_O1, __dp2a_hi(p3[k], TAP_V_O1, 32768u))));
+                    p0[k] = p1[k]; p1[k] = p2[k]; p2[k] = p3[k];
+                }
+                *reinterpret_cast<unsigned int*>(out) = __byte_perm(__byte_perm(ve[0], ve[1], 0x0062), __byte_perm(ve[2], ve[3], 0x0062), 0x5410);
+                if (o + 1 < rowsOut)
+                    *reinterpret_cast<unsigned int*>(out + bpitch) =
+                        __byte_perm(__byte_perm(vo[0], vo[1], 0x0062), __byte_perm(vo[2], vo[3], 0x0062), 0x5410);
+                out += 2 * bpitch;
+            }
+        }
+        __syncthreads();   // every thread is done with the buffer before the next band's copy is issued
+    }
+}
+
+// shared memory of the staged kernel for a level: barrier block + (BL_ROWS + 6 input rows + 1 row of slack) * pitch
+static int blur_staged_smem(const LevelGeom& L) { return 128 + (BL_ROWS + 7) * L.pitch; }
+
+int blur_staged_ctas(const LevelGeom& L) {
+    const int threads = (((L.w + 3) >> 2) + 31) / 32 * 32, smem = blur_staged_smem(L);
+    if (threads > 512 || smem > 200 * 1024) return 0;
+    int dev = 0, nSm = 0, perSm = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaFuncSetAttribute(blur_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&nSm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, blur_staged_kernel, threads, smem) != cudaSuccess) return 0;
+    return nSm * perSm;
+}
+
 int launch_blur(const ExtractParams& P, const BlurTile* dTiles, int nTiles, cudaStream_t st, int* launches) {
     if (nTiles == 0) return ORB_OK;
+    if (P.nFrames >= P.pyBulkMinFrames) {
+        bool all = true;
+        for (int l = 0; l < P.nLevels; ++l) all = all && P.lv[l].blCtas > 0;
+        if (all) {
+            for (int l = 0; l < P.nLevels; ++l) {
+                const LevelGeom& L = P.lv[l];
+                const int threads = (((L.w + 3) >> 2) + 31) / 32 * 32, nBands = ceil_div(L.h, BL_ROWS);
+                const long long tiles = (long long)nBands * P.nFrames;
+                const int grid = (int)std::min<long long>(tiles, (long long)L.blCtas);
+                blur_staged_kernel<<<grid, threads, blur_staged_smem(L), st>>>(P, l, nBands, (int)tiles);
+                ++*launches;
+            }
+            ORB_CUDA(cudaGetLastError());
+            return ORB_OK;
+        }
+    }
     dim3 grid(nTiles, P.nFrames);
     blur_kernel<<<grid, BL_THREADS, 0, st>>>(P, dTiles);
     ++*launches;

@@ -251,6 +251,7 @@ int configure(orbx_extractor* e, int w, int h, int nFrames) {
         const char* v = getenv("ORBB_PYR_BULK_MIN");      // tuning aid: smallest batch that takes the staged resize kernel
         P.pyBulkMinFrames = v ? atoi(v) : 8;
     }
+    for (int l = 0; l < nl; ++l) lv[l].blCtas = blur_staged_ctas(lv[l]);
     for (int l = 0; l < nl; ++l) P.lv[l] = lv[l];
     {   // TMA descriptors of the padded pyramid levels: [arena frame][row][pitch], box = one FAST tile
         unsigned char hostMaps[128 * kMaxLevels];

@@ -35,6 +35,7 @@ struct LevelGeom {
     int pyBulk;          // 1: batches are resized by pyramid_resize3_kernel (source rows staged by bulk-async copies)
     int pyBufBytes;      // bytes of one staging buffer
     int pyBulkCtas;      // resident CTAs of that kernel on the device
+    int blCtas;          // resident CTAs of the staged blur kernel for this level (0: the level does not fit it)
     int cellBase, nCells;    // this level's cells inside the frame's cell table
     int slotCap;         // entries per cell slot
     long long slotBase;  // entry offset of the level's first slot inside one frame's slot block
@@ -148,6 +149,7 @@ int launch_stereo(const StereoParams& P, const orb_keypoint* dKeysL, const unsig
                   float* dDepth, int* dSad, int* dKept, cudaStream_t st, int* launches);
 int octree_smem_plan(int nodeCap, int cellCap, int* smemBytes, int* keyCapSmem);
 int blur_cta_count(int w, int h);
+int blur_staged_ctas(const LevelGeom& L);
 int upload_brief_pattern();
 int upload_orientation_table(const int* umax);
 
