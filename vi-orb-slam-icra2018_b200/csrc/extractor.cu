@@ -57,7 +57,7 @@ struct orbx_extractor {
     int kpCapacity = 0;       // upper bound on keypoints per frame
     int otSmem = 0, otKeyCap = 0, otNodeCap = 0, otCellCap = 0;
     // device memory
-    DevBuf pyr, blur, slots, cellCount, sel, selCount, keyWs, dCells, dTiles, dTabOfs, dTabCoef, dPyCol, dPyRow, dPyBand, dFastMaps, dFastScratch, dFastCounters;
+    DevBuf pyr, blur, slots, cellCount, sel, selCount, keyWs, dCells, dTiles, dTabOfs, dTabCoef, dPyCol, dPyRow, dPyBand, dFastMaps, dBriefMaps, dFastScratch, dFastCounters;
     DevBuf dImages, dKps, dDesc, dCount;
     DevBuf stKeysL, stDescL, stKeysR, stDescR, stOut;   // staging of orbx_compute_stereo_matches
     int lastFrames = 0, lastCapacity = 0;   // arena capacity in frames / caller capacity of the last call
@@ -260,6 +260,11 @@ int configure(orbx_extractor* e, int w, int h, int nFrames) {
         ORB_CUDA(cudaMemcpyAsync(e->dFastMaps.p, hostMaps, sizeof hostMaps, cudaMemcpyHostToDevice, e->stream));
         ORB_CUDA(cudaStreamSynchronize(e->stream));
         P.fw.maps = e->dFastMaps.p;
+        ORB_CHECK(e->dBriefMaps.reserve(sizeof hostMaps));
+        ORB_CHECK(brief_encode_maps(P, (int)F, hostMaps));
+        ORB_CUDA(cudaMemcpyAsync(e->dBriefMaps.p, hostMaps, sizeof hostMaps, cudaMemcpyHostToDevice, e->stream));
+        ORB_CUDA(cudaStreamSynchronize(e->stream));
+        P.brMaps = e->dBriefMaps.p;
         ORB_CHECK(fast_warp_max_warps(P.fw, &P.fw.maxWarps));
         ORB_CHECK(e->dFastScratch.reserve((size_t)P.fw.maxWarps * P.fw.scratchCap * 2));
         P.fw.scratch = e->dFastScratch.as<unsigned short>();
@@ -416,7 +421,7 @@ int orbx_destroy(orbx_handle e) {
     DeviceGuard g(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
     DevBuf* bufs[] = {&e->pyr, &e->blur, &e->slots, &e->cellCount, &e->sel, &e->selCount, &e->keyWs, &e->dCells,
-                      &e->dTiles, &e->dTabOfs, &e->dTabCoef, &e->dPyCol, &e->dPyRow, &e->dPyBand, &e->dFastMaps, &e->dFastScratch, &e->dFastCounters, &e->dImages, &e->dKps, &e->dDesc, &e->dCount,
+                      &e->dTiles, &e->dTabOfs, &e->dTabCoef, &e->dPyCol, &e->dPyRow, &e->dPyBand, &e->dFastMaps, &e->dBriefMaps, &e->dFastScratch, &e->dFastCounters, &e->dImages, &e->dKps, &e->dDesc, &e->dCount,
                       &e->stKeysL, &e->stDescL, &e->stKeysR, &e->stDescR, &e->stOut};
     for (DevBuf* b : bufs) b->release();
     if (e->graphExec) cudaGraphExecDestroy(e->graphExec);

@@ -110,6 +110,7 @@ struct ExtractParams {
     const short2* tabCoef;   // 11-bit coefficient pairs
     const uint4* pyColTab;   // pyramid_resize2_kernel: per 4-byte destination group {base, shift, sel01, sel23}, {cf[0..3]}
     const uint4* pyRowTab;   //                         per padded destination row {off(sy0), off(sy0+1), b0 << 12, b1 << 12}
+    const void* brMaps;      // brief_staged_kernel: device array of kMaxLevels CUtensorMap over the blurred levels (or null)
     const int4* pyBandTab;   // pyramid_resize3_kernel: per band of 16 destination rows {source offset, bytes, offset(first sy0), -}
     int pyBulkMinFrames;     // batches of at least this many frames use the staged kernel
     LevelGeom lv[kMaxLevels];
@@ -151,6 +152,7 @@ int octree_smem_plan(int nodeCap, int cellCap, int* smemBytes, int* keyCapSmem);
 int blur_cta_count(int w, int h);
 int blur_staged_ctas(const LevelGeom& L);
 int upload_brief_pattern();
+int brief_encode_maps(const ExtractParams& P, int arenaFrames, void* hostMaps128xLevels);
 int upload_orientation_table(const int* umax);
 
 }  // namespace orbb
