@@ -32,6 +32,17 @@ constexpr unsigned int TAP_V_E1 = 0x00122230u;   //                             
 constexpr unsigned int TAP_V_O0 = 0x30221200u;   // odd output row:                   ( 0,18) (34,48)
 constexpr unsigned int TAP_V_O1 = 0x12223038u;   //                                   (56,48) (34,18)
 
+// Horizontal sums of one input row for four adjacent pixels from the three aligned words that hold bytes x-4 .. x+7:
+// pixel k needs bytes k+1 .. k+7 of that window.  Instead of shifting the window to the pixel (6 funnel shifts) the TAPS
+// are shifted: per pixel two or three dot products of the unshifted words with tap vectors that are zero outside the
+// pixel's seven bytes (10 IDP.4A, no shifts; integer sums, so the result is the same).
+__device__ __forceinline__ void blur_hrow(unsigned int w0, unsigned int w1, unsigned int w2, unsigned int (&h)[4]) {
+    h[0] = __dp4a(w0, 0x30221200u, __dp4a(w1, 0x12223038u, 0u));                              // bytes 1..3 | 4..7
+    h[1] = __dp4a(w0, 0x22120000u, __dp4a(w1, 0x22303830u, __dp4a(w2, 0x00000012u, 0u)));     // bytes 2..3 | 4..7 | 8
+    h[2] = __dp4a(w0, 0x12000000u, __dp4a(w1, 0x30383022u, __dp4a(w2, 0x00001222u, 0u)));     // byte 3 | 4..7 | 8..9
+    h[3] = __dp4a(w1, TAP_H_LO, __dp4a(w2, TAP_H_HI, 0u));                                    // bytes 4..7 | 8..10
+}
+
 int blur_cta_count(int w, int h) { return ceil_div(((w + 3) / 4) * ceil_div(h, BL_ROWS), BL_THREADS); }
 
 __global__ void __launch_bounds__(BL_THREADS) blur_kernel(const __grid_constant__ ExtractParams P, const BlurTile* __restrict__ tiles) {
@@ -164,18 +175,12 @@ blur_staged_kernel(const __grid_constant__ ExtractParams P, int level, int nBand
                 asm volatile("ld.shared.u32 %0, [%1+8];" : "=r"(w[2]) : "r"(rowAddr));
                 rowAddr += pitch;
             };
-            auto hrow = [&](const unsigned int (&w)[3], unsigned int (&h)[4]) {
-                h[0] = __dp4a(__funnelshift_r(w[0], w[1], 8), TAP_H_LO, __dp4a(__funnelshift_r(w[1], w[2], 8), TAP_H_HI, 0u));
-                h[1] = __dp4a(__funnelshift_r(w[0], w[1], 16), TAP_H_LO, __dp4a(__funnelshift_r(w[1], w[2], 16), TAP_H_HI, 0u));
-                h[2] = __dp4a(__funnelshift_r(w[0], w[1], 24), TAP_H_LO, __dp4a(__funnelshift_r(w[1], w[2], 24), TAP_H_HI, 0u));
-                h[3] = __dp4a(w[1], TAP_H_LO, __dp4a(w[2], TAP_H_HI, 0u));
-            };
             auto make_pair = [&](unsigned int (&pr)[4]) {      // the next two input rows, packed per pixel (even row in the low half)
                 unsigned int we[3], wo[3], he[4], ho[4];
                 load_row(we);
                 load_row(wo);
-                hrow(we, he);
-                hrow(wo, ho);
+                blur_hrow(we[0], we[1], we[2], he);
+                blur_hrow(wo[0], wo[1], wo[2], ho);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) pr[k] = __byte_perm(he[k], ho[k], 0x5410);
             };
@@ -185,8 +190,8 @@ blur_staged_kernel(const __grid_constant__ ExtractParams P, int level, int nBand
             make_pair(p2);
             // pair i completes output rows 2i-6 and 2i-5; the band's buffer holds rowsOut + 6 input rows, so the odd row of
             // the last pair of an odd-height band is read from the row behind them (inside the buffer's slack) and unused
-#pragma unroll 2
-            for (int o = 0; o < rowsOut; o += 2) {
+#pragma unroll 4
+            for (int o = 0; o < rowsOut; o += 2) {      // unrolled by the period of the four-pair ring: no register moves
                 make_pair(p3);
                 unsigned int ve[4], vo[4];
 #pragma unroll
