@@ -22,6 +22,7 @@
 // Reading S[x+1] / row y+1 one past the level is harmless: the table's coefficient there is 0 and the source level
 // has its own frame.
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "extractor.h"
@@ -282,7 +283,7 @@ __device__ __forceinline__ unsigned int py_smem_u32(const void* p) { return (uns
 
 __global__ void __launch_bounds__(512)
 pyramid_resize3_kernel(unsigned char* __restrict__ pyr, long long pyrFrameBytes, long long srcOff, long long dstOff, int dstPitch,
-                       int rowsTotal, int groups, int nBands, int nTiles, int bufBytes, const uint4* __restrict__ colTab,
+                       int rowsTotal, int groups, int nBands, int nTiles, int bufBytes, int nBuf, const uint4* __restrict__ colTab,
                        const uint4* __restrict__ rowTab, const int4* __restrict__ bandTab) {
     extern __shared__ __align__(128) unsigned char psm[];
     const int tid = threadIdx.x;
@@ -323,13 +324,18 @@ pyramid_resize3_kernel(unsigned char* __restrict__ pyr, long long pyrFrameBytes,
         t[2] = __dp2a_lo(cb.z, v23, 0u) & ~15u;
         t[3] = __dp2a_hi(cb.w, v23, 0u) & ~15u;
     };
+    // nBuf == 2: the next band's copy is in flight while this one is computed; nBuf == 1: one buffer, twice the CTAs per SM
     int tile = blockIdx.x;
-    if (tile < nTiles) issue(tile, 0);
+    if (nBuf == 2 && tile < nTiles) issue(tile, 0);
     for (int it = 0; tile < nTiles; tile += gridDim.x, ++it) {
-        const int buf = it & 1;
-        if (tile + (int)gridDim.x < nTiles) issue(tile + gridDim.x, buf ^ 1);
+        const int buf = nBuf == 2 ? (it & 1) : 0;
+        if (nBuf == 2) {
+            if (tile + (int)gridDim.x < nTiles) issue(tile + gridDim.x, buf ^ 1);
+        } else {
+            issue(tile, 0);
+        }
         {
-            const unsigned int bar = bar0 + 8 * buf, parity = (unsigned int)(it >> 1) & 1u;
+            const unsigned int bar = bar0 + 8 * buf, parity = (unsigned int)(nBuf == 2 ? it >> 1 : it) & 1u;
             asm volatile(
                 "{\n"
                 ".reg .pred p;\n"
@@ -402,8 +408,13 @@ int pyramid_band_plan(const LevelGeom& S, const LevelGeom& D, const int* yofs, s
 }
 
 // resident CTAs of the staged kernel on the current device for a level's block size and shared memory (0: does not fit)
+int pyramid_bulk_buffers() {
+    static const int n = getenv("ORBB_PYR_NBUF") ? std::max(1, std::min(2, atoi(getenv("ORBB_PYR_NBUF")))) : 2;   // tuning aid
+    return n;
+}
+
 int pyramid_bulk_ctas(int groups, int bufBytes) {
-    const int threads = (groups + 31) / 32 * 32, smem = 128 + 2 * bufBytes;
+    const int threads = (groups + 31) / 32 * 32, smem = 128 + pyramid_bulk_buffers() * bufBytes;
     if (threads > 512 || smem > 200 * 1024) return 0;
     int dev = 0, nSm = 0, perSm = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return 0;
@@ -431,11 +442,11 @@ int launch_pyramid(const ExtractParams& P, const unsigned char* dImages, int wid
         dim3 grid(ceil_div(nItems, PY_THREADS), P.nFrames);
         if (D.pyFast && D.pyBulk && P.nFrames >= P.pyBulkMinFrames) {
             const int threads = (groups + 31) / 32 * 32, nBands = ceil_div(D.h + 2 * kEdge, PY_ROWS);
-            const int smem = 128 + 2 * D.pyBufBytes;
+            const int nBuf = pyramid_bulk_buffers(), smem = 128 + nBuf * D.pyBufBytes;
             const long long nTiles = (long long)nBands * P.nFrames;
             const int gridX = (int)std::min<long long>(nTiles, (long long)D.pyBulkCtas);
             pyramid_resize3_kernel<<<gridX, threads, smem, st>>>(P.pyr, P.pyrFrameBytes, S.pyrOff, D.pyrOff, D.pitch, D.h + 2 * kEdge, groups,
-                                                                 nBands, (int)nTiles, D.pyBufBytes, P.pyColTab + D.pyCol, P.pyRowTab + D.pyRow,
+                                                                 nBands, (int)nTiles, D.pyBufBytes, nBuf, P.pyColTab + D.pyCol, P.pyRowTab + D.pyRow,
                                                                  P.pyBandTab + D.pyBand);
             ++*launches;
             continue;
