@@ -56,7 +56,7 @@ def test_extract_matches_oracle(oracle, seed, w, h, nf, noise):
     assert np.array_equal(kps["angle"].view(np.uint32), rk["angle"].view(np.uint32)), "angles not bit-exact"
     assert np.array_equal(desc, rd)
     assert len(kps) <= ex.capacity
-    assert ex.launch_count() == 12
+    assert ex.launch_count() == 5      # fused pyramid, FAST, quadtree, blur, orientation + BRIEF
     ex.close()
 
 

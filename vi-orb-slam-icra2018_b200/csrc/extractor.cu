@@ -57,7 +57,7 @@ struct orbx_extractor {
     int kpCapacity = 0;       // upper bound on keypoints per frame
     int otSmem = 0, otKeyCap = 0, otNodeCap = 0, otCellCap = 0;
     // device memory
-    DevBuf pyr, blur, slots, cellCount, sel, selCount, keyWs, dCells, dTiles, dTabOfs, dTabCoef, dPyCol, dPyRow, dPyBand, dFastMaps, dBriefMaps, dFastScratch, dFastCounters;
+    DevBuf pyr, blur, slots, cellCount, sel, selCount, keyWs, dCells, dTiles, dTabOfs, dTabCoef, dPyCol, dPyRow, dPyBand, dPyBarrier, dFastMaps, dBriefMaps, dFastScratch, dFastCounters;
     DevBuf dImages, dKps, dDesc, dCount;
     DevBuf stKeysL, stDescL, stKeysR, stDescR, stOut;   // staging of orbx_compute_stereo_matches
     int lastFrames = 0, lastCapacity = 0;   // arena capacity in frames / caller capacity of the last call
@@ -247,6 +247,8 @@ int configure(orbx_extractor* e, int w, int h, int nFrames) {
     P.pyColTab = e->dPyCol.as<uint4>();
     P.pyRowTab = e->dPyRow.as<uint4>();
     P.pyBandTab = e->dPyBand.as<int4>();
+    ORB_CHECK(e->dPyBarrier.reserve(sizeof(unsigned int) * kMaxLevels));
+    P.pyBarrier = e->dPyBarrier.as<unsigned int>();
     {
         const char* v = getenv("ORBB_PYR_BULK_MIN");      // tuning aid: smallest batch that takes the staged resize kernel
         P.pyBulkMinFrames = v ? atoi(v) : 8;
@@ -421,7 +423,7 @@ int orbx_destroy(orbx_handle e) {
     DeviceGuard g(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
     DevBuf* bufs[] = {&e->pyr, &e->blur, &e->slots, &e->cellCount, &e->sel, &e->selCount, &e->keyWs, &e->dCells,
-                      &e->dTiles, &e->dTabOfs, &e->dTabCoef, &e->dPyCol, &e->dPyRow, &e->dPyBand, &e->dFastMaps, &e->dBriefMaps, &e->dFastScratch, &e->dFastCounters, &e->dImages, &e->dKps, &e->dDesc, &e->dCount,
+                      &e->dTiles, &e->dTabOfs, &e->dTabCoef, &e->dPyCol, &e->dPyRow, &e->dPyBand, &e->dPyBarrier, &e->dFastMaps, &e->dBriefMaps, &e->dFastScratch, &e->dFastCounters, &e->dImages, &e->dKps, &e->dDesc, &e->dCount,
                       &e->stKeysL, &e->stDescL, &e->stKeysR, &e->stDescR, &e->stOut};
     for (DevBuf* b : bufs) b->release();
     if (e->graphExec) cudaGraphExecDestroy(e->graphExec);

@@ -113,6 +113,7 @@ struct ExtractParams {
     const void* brMaps;      // brief_staged_kernel: device array of kMaxLevels CUtensorMap over the blurred levels (or null)
     const int4* pyBandTab;   // pyramid_resize3_kernel: per band of 16 destination rows {source offset, bytes, offset(first sy0), -}
     int pyBulkMinFrames;     // batches of at least this many frames use the staged kernel
+    unsigned int* pyBarrier; // kMaxLevels counters of the fused small-batch pyramid kernel's grid barrier
     LevelGeom lv[kMaxLevels];
 };
 

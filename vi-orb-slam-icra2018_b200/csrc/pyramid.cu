@@ -407,6 +407,143 @@ int pyramid_band_plan(const LevelGeom& S, const LevelGeom& D, const int* yofs, s
     return maxBytes;
 }
 
+// ---- small batches (the live loop: one frame or a stereo pair): all levels in ONE launch -----------------------------
+// Eight dependent launches of a few microseconds each cost a single frame ~100 us, most of it launch gaps and kernel
+// tails.  Here one grid of co-resident CTAs walks the levels; between levels every CTA passes a grid-wide barrier (arrive
+// on a zeroed counter with a release fence, spin with acquire loads).  Level l's items (the work items of
+// pyramid_level0_kernel / pyramid_resize2_kernel, frame-major) are dealt over the whole grid.  Data written earlier in
+// the same launch is read with ld.global.cg (never through the non-coherent path).
+constexpr int PYF_ROWS = 4;      // rows per work item of the fused kernel: latency matters here, not instruction count
+struct PyFusedLevel {
+    long long srcPix0, dstOff;   // source pixel (0,0) / destination buffer inside a frame's pyramid block
+    int dstPitch, rowsTotal, groups, nItems;
+    const uint4* colTab;
+    const uint4* rowTab;
+};
+struct PyFusedArgs {
+    const unsigned char* images;
+    size_t frameStride;
+    int w, h, stride, wordLoads, nFrames, nLevels;
+    unsigned char* pyr;
+    long long pyrFrameBytes;
+    unsigned int* barrier;       // nLevels counters, zeroed before the launch
+    PyFusedLevel lv[kMaxLevels];
+};
+
+__global__ void __launch_bounds__(PY_THREADS)
+pyramid_fused_kernel(const __grid_constant__ PyFusedArgs A) {
+    const int nThreads = gridDim.x * PY_THREADS, tid0 = blockIdx.x * PY_THREADS + threadIdx.x;
+    {   // level 0: copy with the reflect-101 frame
+        const PyFusedLevel& L = A.lv[0];
+        for (int it = tid0; it < L.nItems * A.nFrames; it += nThreads) {
+            const int frame = it / L.nItems, item = it - frame * L.nItems;
+            const int band = item / L.groups, g = item - band * L.groups;
+            const int bx = 4 * g, lx0 = bx - kPadLeft;
+            const unsigned char* img = A.images + (size_t)frame * A.frameStride;
+            unsigned char* dst = A.pyr + (size_t)frame * A.pyrFrameBytes + L.dstOff + bx;
+            int col[4], cmin = 0x7fffffff;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { col[k] = frame_column(lx0 + k, A.w); cmin = min(cmin, col[k]); }
+            const int base = cmin & ~3;
+            unsigned int sel = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) sel |= (unsigned int)(col[k] - base) << (4 * k);
+            const int by0 = band * PYF_ROWS;
+            const bool second = base + 4 < ((A.w + 3) & ~3);
+            for (int r = 0; r < PYF_ROWS; ++r) {
+                const int by = by0 + r;
+                if (by >= L.rowsTotal) break;
+                const unsigned char* src = img + (size_t)reflect101(by - kEdge, A.h) * A.stride;
+                unsigned int word;
+                if (A.wordLoads) {
+                    const unsigned int* sw = reinterpret_cast<const unsigned int*>(src + base);
+                    word = __byte_perm(__ldg(sw), second ? __ldg(sw + 1) : 0u, sel);
+                } else {
+                    word = 0;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) word |= (unsigned int)__ldg(src + col[k]) << (8 * k);
+                }
+                *reinterpret_cast<unsigned int*>(dst + (size_t)by * L.dstPitch) = word;
+            }
+        }
+    }
+    for (int l = 1; l < A.nLevels; ++l) {
+        // grid barrier: level l-1 is complete (and visible) before anyone reads it
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            atomicAdd(A.barrier + l, 1u);
+            unsigned int seen;
+            do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(A.barrier + l) : "memory");
+            } while (seen < gridDim.x);
+        }
+        __syncthreads();
+        const PyFusedLevel& L = A.lv[l];
+        for (int it = tid0; it < L.nItems * A.nFrames; it += nThreads) {
+            const int frame = it / L.nItems, item = it - frame * L.nItems;
+            const int band = item / L.groups, g = item - band * L.groups;
+            unsigned char* fb = A.pyr + (size_t)frame * A.pyrFrameBytes;
+            const uint4 ca = __ldg(L.colTab + 2 * g), cb = __ldg(L.colTab + 2 * g + 1);
+            const unsigned char* srcCol = fb + L.srcPix0 + ca.x;
+            const int by0 = band * PYF_ROWS;
+            unsigned char* dst = fb + L.dstOff + 4 * g + (size_t)by0 * L.dstPitch;
+            const uint4* rt = L.rowTab + by0;
+            const int rows = min(PYF_ROWS, L.rowsTotal - by0);
+            const unsigned int shift = ca.y, sel01 = ca.z, sel23 = ca.w;
+            auto hsum = [&](const unsigned char* row, unsigned int (&t)[4]) {
+                const unsigned int* q = reinterpret_cast<const unsigned int*>(row);
+                const unsigned int w0 = __ldcg(q), w1 = __ldcg(q + 1), w2 = __ldcg(q + 2);
+                const unsigned int X = __funnelshift_r(w0, w1, shift), Y = __funnelshift_r(w1, w2, shift);
+                const unsigned int v01 = __byte_perm(X, Y, sel01), v23 = __byte_perm(X, Y, sel23);
+                t[0] = __dp2a_lo(cb.x, v01, 0u) & ~15u;
+                t[1] = __dp2a_hi(cb.y, v01, 0u) & ~15u;
+                t[2] = __dp2a_lo(cb.z, v23, 0u) & ~15u;
+                t[3] = __dp2a_hi(cb.w, v23, 0u) & ~15u;
+            };
+            unsigned int keptOff = 0xffffffffu;
+            unsigned int kept[4] = {0, 0, 0, 0};
+#pragma unroll 2
+            for (int r = 0; r < rows; ++r) {
+                const uint4 rr = __ldg(rt + r);
+                unsigned int t0[4], t1[4];
+                if (rr.x == keptOff) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) t0[k] = kept[k];
+                } else {
+                    hsum(srcCol + rr.x, t0);
+                }
+                hsum(srcCol + rr.y, t1);
+                keptOff = rr.y;
+                unsigned int sv[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    kept[k] = t1[k];
+                    sv[k] = __umulhi(t0[k], rr.z) + __umulhi(t1[k], rr.w) + 2u;
+                }
+                const unsigned int q01 = __byte_perm(sv[0], sv[1], 0x5410) >> 2, q23 = __byte_perm(sv[2], sv[3], 0x5410) >> 2;
+                *reinterpret_cast<unsigned int*>(dst) = __byte_perm(q01, q23, 0x6420);
+                dst += L.dstPitch;
+            }
+        }
+    }
+}
+
+// co-resident CTAs the fused kernel may use on the current device (0: unknown)
+static int pyramid_fused_capacity() {
+    static thread_local int cached = -1, cachedDev = -1;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cached < 0 || cachedDev != dev) {
+        int nSm = 0, perSm = 0;
+        if (cudaDeviceGetAttribute(&nSm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, pyramid_fused_kernel, PY_THREADS, 0) != cudaSuccess) return 0;
+        cached = nSm * perSm;
+        cachedDev = dev;
+    }
+    return cached;
+}
+
 // resident CTAs of the staged kernel on the current device for a level's block size and shared memory (0: does not fit)
 int pyramid_bulk_buffers() {
     static const int n = getenv("ORBB_PYR_NBUF") ? std::max(1, std::min(2, atoi(getenv("ORBB_PYR_NBUF")))) : 2;   // tuning aid
@@ -426,6 +563,44 @@ int pyramid_bulk_ctas(int groups, int bufBytes) {
 
 int launch_pyramid(const ExtractParams& P, const unsigned char* dImages, int width, int height, int stride,
                    size_t frameStride, cudaStream_t st, int* launches) {
+    static const bool noFuse = getenv("ORBB_PYR_NOFUSE") != nullptr;    // A/B aid: one launch per level for small batches too
+    bool allFast = P.pyBarrier != nullptr && !noFuse && P.nFrames < P.pyBulkMinFrames;
+    for (int l = 1; l < P.nLevels; ++l) allFast = allFast && P.lv[l].pyFast;
+    if (allFast) {
+        const int cap = pyramid_fused_capacity();
+        if (cap > 0) {
+            PyFusedArgs A;
+            A.images = dImages;
+            A.frameStride = frameStride;
+            A.w = width; A.h = height; A.stride = stride;
+            A.wordLoads = ((((size_t)dImages) | (size_t)stride | frameStride) & 3) == 0 ? 1 : 0;
+            A.nFrames = P.nFrames;
+            A.nLevels = P.nLevels;
+            A.pyr = P.pyr;
+            A.pyrFrameBytes = P.pyrFrameBytes;
+            A.barrier = P.pyBarrier;
+            int maxItems = 0;
+            for (int l = 0; l < P.nLevels; ++l) {
+                const LevelGeom& D = P.lv[l];
+                PyFusedLevel& F = A.lv[l];
+                F.dstOff = D.pyrOff;
+                F.dstPitch = D.pitch;
+                F.rowsTotal = D.h + 2 * kEdge;
+                F.groups = D.pitch / 4;
+                F.nItems = F.groups * ceil_div(F.rowsTotal, PYF_ROWS);
+                F.srcPix0 = l ? P.lv[l - 1].pyrOff + (long long)kEdge * P.lv[l - 1].pitch + kPadLeft : 0;
+                F.colTab = l ? P.pyColTab + D.pyCol : nullptr;
+                F.rowTab = l ? P.pyRowTab + D.pyRow : nullptr;
+                maxItems = std::max(maxItems, F.nItems * P.nFrames);
+            }
+            const int grid = std::max(1, std::min(cap, ceil_div(maxItems, PY_THREADS)));
+            ORB_CUDA(cudaMemsetAsync(P.pyBarrier, 0, sizeof(unsigned int) * kMaxLevels, st));
+            pyramid_fused_kernel<<<grid, PY_THREADS, 0, st>>>(A);
+            ++*launches;
+            ORB_CUDA(cudaGetLastError());
+            return ORB_OK;
+        }
+    }
     {
         const LevelGeom& L = P.lv[0];
         const int groups = L.pitch / 4, nItems = groups * ceil_div(L.h + 2 * kEdge, PY_ROWS);
