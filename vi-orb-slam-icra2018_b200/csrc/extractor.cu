@@ -42,6 +42,8 @@ struct orbx_extractor {
     cudaStream_t streamIn = nullptr, streamOut = nullptr;   // H2D / D2H of the host entry points, overlapped with compute
     std::vector<cudaEvent_t> pipeEvents;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t streamSide = nullptr;      // small calls: the blur (needs only the pyramid) runs beside FAST + quadtree
+    cudaEvent_t evFork = nullptr, evJoin = nullptr;
     // ctor state
     int nfeatures = 0, nlevels = 0, iniTh = 0, minTh = 0;
     double scaleFactor = 1;
@@ -320,12 +322,22 @@ int enqueue(orbx_extractor* e, const uint8_t* dImages, int nFrames, int w, int h
     ORB_CHECK(launch_pyramid(P, dImages, w, h, stride, frameStride, st, &e->launches));
     if (timed) ORB_CUDA(cudaEventRecord(e->ev[1], st));
     if (pe) ORB_CUDA(cudaEventRecord(pe[1], st));
+    // a small call leaves most SMs idle during FAST + quadtree: its blur (which needs only the pyramid) runs beside them
+    static const bool noFork = getenv("ORBB_NO_FORK") != nullptr;
+    const bool fork = !noFork && !pe && nFrames < P.pyBulkMinFrames && e->streamSide && st == e->stream;
+    if (fork) {
+        ORB_CUDA(cudaEventRecord(e->evFork, st));
+        ORB_CUDA(cudaStreamWaitEvent(e->streamSide, e->evFork, 0));
+        ORB_CHECK(launch_blur(P, e->dTiles.as<BlurTile>(), (int)e->tiles.size(), e->streamSide, &e->launches));
+        ORB_CUDA(cudaEventRecord(e->evJoin, e->streamSide));
+    }
     ORB_CHECK(launch_fast_warp(P, st, &e->launches));
     if (pe) ORB_CUDA(cudaEventRecord(pe[2], st));
     ORB_CHECK(launch_octree(P, e->otSmem, e->otKeyCap, e->otNodeCap, e->otCellCap, st, &e->launches));
     if (timed) ORB_CUDA(cudaEventRecord(e->ev[2], st));
     if (pe) ORB_CUDA(cudaEventRecord(pe[3], st));
-    ORB_CHECK(launch_blur(P, e->dTiles.as<BlurTile>(), (int)e->tiles.size(), st, &e->launches));
+    if (fork) ORB_CUDA(cudaStreamWaitEvent(st, e->evJoin, 0));
+    else ORB_CHECK(launch_blur(P, e->dTiles.as<BlurTile>(), (int)e->tiles.size(), st, &e->launches));
     if (pe) ORB_CUDA(cudaEventRecord(pe[4], st));
     ORB_CHECK(launch_brief(P, std::min(capacity, e->kpCapacity), dKps, dDesc, dCount, st, &e->launches));
     if (timed) ORB_CUDA(cudaEventRecord(e->ev[3], st));
@@ -403,6 +415,9 @@ int orbx_create(int nfeatures, float scaleFactor, int nlevels, int iniTh, int mi
     if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&e->streamIn, cudaStreamNonBlocking);
     if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&e->streamOut, cudaStreamNonBlocking);
     for (int i = 0; i < 4 && ce == cudaSuccess; ++i) ce = cudaEventCreate(&e->ev[i]);
+    if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&e->streamSide, cudaStreamNonBlocking);
+    if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&e->evFork, cudaEventDisableTiming);
+    if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&e->evJoin, cudaEventDisableTiming);
     if (ce != cudaSuccess) {
         delete e;
         return fail(ORB_ERR_CUDA, "orbx_create: %s", cudaGetErrorString(ce));
@@ -431,6 +446,9 @@ int orbx_destroy(orbx_handle e) {
         if (e->ev[i]) cudaEventDestroy(e->ev[i]);
     for (cudaEvent_t ev : e->profEvents) cudaEventDestroy(ev);
     for (cudaEvent_t ev : e->pipeEvents) cudaEventDestroy(ev);
+    if (e->evFork) cudaEventDestroy(e->evFork);
+    if (e->evJoin) cudaEventDestroy(e->evJoin);
+    if (e->streamSide) cudaStreamDestroy(e->streamSide);
     if (e->streamIn) cudaStreamDestroy(e->streamIn);
     if (e->streamOut) cudaStreamDestroy(e->streamOut);
     if (e->stream) cudaStreamDestroy(e->stream);
