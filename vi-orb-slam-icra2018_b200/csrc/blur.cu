@@ -16,6 +16,7 @@
 //     the rounding is free, and the four result bytes are picked with PRMT.
 // No shared memory, no barriers; all levels in one launch.
 #include <algorithm>
+#include <cstdlib>
 
 #include "extractor.h"
 
@@ -125,35 +126,51 @@ __global__ void __launch_bounds__(BL_THREADS) blur_kernel(const __grid_constant_
 // shared-memory addresses.  One buffer per CTA and several CTAs per SM: while one waits for its copy the others compute.
 // Persistent CTAs stride over (frame, band); one launch per level (block size = the level's column groups).
 __global__ void __launch_bounds__(512)
-blur_staged_kernel(const __grid_constant__ ExtractParams P, int level, int nBands, int nTiles) {
+blur_staged_kernel(const __grid_constant__ ExtractParams P, int level, int nBands, int nTiles, int nBuf, int bufBytes) {
     extern __shared__ __align__(128) unsigned char bsm[];
     const LevelGeom& L = P.lv[level];
     const int tid = threadIdx.x;
     const int groups = (L.w + 3) >> 2;
     const int pitch = L.pitch, bpitch = L.bpitch;
-    const unsigned int bar = (unsigned int)__cvta_generic_to_shared(bsm), tile = bar + 128;
+    const unsigned int bar0 = (unsigned int)__cvta_generic_to_shared(bsm), tile0 = bar0 + 128;
     if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     const bool active = tid < groups;
-    const unsigned int colAddr = tile + kPadLeft + 4 * tid - 4;      // word that holds pixels 4g-4 .. 4g-1 of the band's first input row
-    unsigned int parity = 0;
-    for (int t = blockIdx.x; t < nTiles; t += gridDim.x) {
+    auto issue = [&](int t, int buf) {      // the band's input rows y0-3 .. y0+rowsOut+2 = padded rows y0+16 .. ; rowsOut + 6 of them
+        if (tid == 0) {
+            const int frame = t / nBands, band = t - frame * nBands;
+            const int y0 = band * BL_ROWS;
+            const int rowsOut = min(BL_ROWS, L.h - y0);
+            const unsigned char* src = P.pyr + (size_t)frame * P.pyrFrameBytes + L.pyrOff + (size_t)(y0 + kEdge - 3) * pitch;
+            const unsigned int bytes = (unsigned int)(rowsOut + 6) * (unsigned int)pitch;
+            const unsigned int bar = bar0 + 8 * buf;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             tile0 + buf * bufBytes),
+                         "l"(src), "r"(bytes), "r"(bar)
+                         : "memory");
+        }
+    };
+    // nBuf == 2: the next band's rows are in flight while this band is computed; nBuf == 1: one buffer, twice the CTAs per SM
+    if (nBuf == 2 && (int)blockIdx.x < nTiles) issue(blockIdx.x, 0);
+    int it = 0;
+    for (int t = blockIdx.x; t < nTiles; t += gridDim.x, ++it) {
         const int frame = t / nBands, band = t - frame * nBands;
         const int y0 = band * BL_ROWS;
         const int rowsOut = min(BL_ROWS, L.h - y0);
-        if (tid == 0) {
-            // input rows y0-3 .. y0+rowsOut+2 = padded rows y0+16 .. ; rowsOut + 6 of them
-            const unsigned char* src = P.pyr + (size_t)frame * P.pyrFrameBytes + L.pyrOff + (size_t)(y0 + kEdge - 3) * pitch;
-            const unsigned int bytes = (unsigned int)(rowsOut + 6) * (unsigned int)pitch;
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(tile), "l"(src),
-                         "r"(bytes), "r"(bar)
-                         : "memory");
+        const int buf = nBuf == 2 ? (it & 1) : 0;
+        if (nBuf == 2) {
+            if (t + (int)gridDim.x < nTiles) issue(t + gridDim.x, buf ^ 1);
+        } else {
+            issue(t, 0);
         }
+        const unsigned int bar = bar0 + 8 * buf, parity = (unsigned int)(nBuf == 2 ? it >> 1 : it) & 1u;
+        const unsigned int colAddr = tile0 + buf * bufBytes + kPadLeft + 4 * tid - 4;   // word of pixels 4g-4 .. 4g-1 of the first input row
         asm volatile(
             "{\n"
             ".reg .pred p;\n"
@@ -165,7 +182,6 @@ blur_staged_kernel(const __grid_constant__ ExtractParams P, int level, int nBand
             "}\n" ::"r"(bar),
             "r"(parity)
             : "memory");
-        parity ^= 1u;
         if (active) {
             unsigned char* out = P.blur + (size_t)frame * P.blurFrameBytes + L.blurOff + (size_t)y0 * bpitch + 4 * tid;
             unsigned int rowAddr = colAddr;
@@ -211,8 +227,13 @@ blur_staged_kernel(const __grid_constant__ ExtractParams P, int level, int nBand
     }
 }
 
-// shared memory of the staged kernel for a level: barrier block + (BL_ROWS + 6 input rows + 1 row of slack) * pitch
-static int blur_staged_smem(const LevelGeom& L) { return 128 + (BL_ROWS + 7) * L.pitch; }
+// shared memory of the staged kernel for a level: barrier block + nBuf buffers of (BL_ROWS + 6 input rows + 1 row of slack)
+static int blur_staged_buffers() {
+    static const int n = getenv("ORBB_BLUR_NBUF") ? std::max(1, std::min(2, atoi(getenv("ORBB_BLUR_NBUF")))) : 1;   // tuning aid (2 measured slower)
+    return n;
+}
+static int blur_staged_buf_bytes(const LevelGeom& L) { return ((BL_ROWS + 7) * L.pitch + 127) / 128 * 128; }
+static int blur_staged_smem(const LevelGeom& L) { return 128 + blur_staged_buffers() * blur_staged_buf_bytes(L); }
 
 int blur_staged_ctas(const LevelGeom& L) {
     const int threads = (((L.w + 3) >> 2) + 31) / 32 * 32, smem = blur_staged_smem(L);
@@ -236,7 +257,8 @@ int launch_blur(const ExtractParams& P, const BlurTile* dTiles, int nTiles, cuda
                 const int threads = (((L.w + 3) >> 2) + 31) / 32 * 32, nBands = ceil_div(L.h, BL_ROWS);
                 const long long tiles = (long long)nBands * P.nFrames;
                 const int grid = (int)std::min<long long>(tiles, (long long)L.blCtas);
-                blur_staged_kernel<<<grid, threads, blur_staged_smem(L), st>>>(P, l, nBands, (int)tiles);
+                blur_staged_kernel<<<grid, threads, blur_staged_smem(L), st>>>(P, l, nBands, (int)tiles, blur_staged_buffers(),
+                                                                               blur_staged_buf_bytes(L));
                 ++*launches;
             }
             ORB_CUDA(cudaGetLastError());
