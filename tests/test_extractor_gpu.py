@@ -135,6 +135,25 @@ def test_staged_batch_kernels_size_sweep(oracle):
         ex.close()
 
 
+def test_host_pipeline_chunks_take_the_staged_kernels(oracle, monkeypatch):
+    """The end-to-end path of bench.py: orbx_extract_batch cuts a host batch into pipeline chunks that work in arena slots
+    [frameBase, frameBase + n).  With 16-frame chunks every chunk takes the staged pyramid / blur kernels and the TMA loads of
+    FAST and BRIEF address the arena by frameBase + frame: 40 frames (chunks at frameBase 0, 16, ...), every frame's
+    keypoints and descriptors equal the oracle's on the 5 distinct images the batch repeats."""
+    monkeypatch.setenv("ORBB_PIPE_CHUNK", "16")
+    base = [synth_frame(950 + i, 752, 480) for i in range(5)]
+    frames = np.stack([base[i % 5] for i in range(40)])
+    ex = orbb200.Extractor(1000, max_width=752, max_height=480, max_batch=40)
+    oe = oracle.extractor(1000)
+    ref = [oe.extract(b) for b in base]
+    res = ex.extract_batch(frames)
+    for i, (k, d) in enumerate(res):
+        rk, rd = ref[i % 5]
+        _assert_same_keypoints(k, rk)
+        assert np.array_equal(d, rd), i
+    ex.close()
+
+
 def test_batch_equals_single_and_oracle(oracle):
     frames = np.stack([synth_frame(100 + i, 752, 480) for i in range(5)] + [synth_frame(200, 752, 480, noise_only=True)])
     ex = orbb200.Extractor(1000, max_width=752, max_height=480, max_batch=4)   # 6 frames -> chunks of 4 + 2

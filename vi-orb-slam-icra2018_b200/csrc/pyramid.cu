@@ -85,6 +85,55 @@ pyramid_level0_kernel(const unsigned char* __restrict__ images, int w, int h, in
     }
 }
 
+// Level 0 for images whose rows are 16-byte aligned and a multiple of 16 wide (EuRoC: 752): the interior of a padded row is
+// a straight copy, so an interior work item is 16 bytes x 16 rows (one 128-bit load and store per row); the frame left and
+// right of it is dealt out in 4-byte groups that take pyramid_level0_kernel's two-word path with the reflected columns.
+// Items of a band: nInt = w / 16 interior groups, then (pitch - w) / 4 frame groups (8 on the left, the rest on the right).
+__global__ void __launch_bounds__(PY_THREADS)
+pyramid_level0_wide_kernel(const unsigned char* __restrict__ images, int w, int h, int stride, size_t frameStride,
+                           unsigned char* __restrict__ pyr, long long pyrFrameBytes, long long pyrOff, int pitch, int groups,
+                           int nItems) {
+    const int item = blockIdx.x * PY_THREADS + threadIdx.x;
+    if (item >= nItems) return;
+    const int band = item / groups, g = item - band * groups;
+    const int nInt = w >> 4;
+    const unsigned char* img = images + (size_t)blockIdx.y * frameStride;
+    unsigned char* dstFrame = pyr + (size_t)blockIdx.y * pyrFrameBytes + pyrOff;
+    const int by0 = band * PY_ROWS, rowsTotal = h + 2 * kEdge;
+    if (g < nInt) {
+        const int lx0 = 16 * g;
+        unsigned char* dst = dstFrame + kPadLeft + lx0;
+#pragma unroll 4
+        for (int r = 0; r < PY_ROWS; ++r) {
+            const int by = by0 + r;
+            if (by >= rowsTotal) break;
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(img + (size_t)reflect101(by - kEdge, h) * stride + lx0));
+            *reinterpret_cast<uint4*>(dst + (size_t)by * pitch) = v;
+        }
+        return;
+    }
+    const int j = g - nInt;
+    const int bx = j < kPadLeft / 4 ? 4 * j : w + 4 * j;      // left: columns 0 .. 31; right: from column 32 + w on
+    const int lx0 = bx - kPadLeft;
+    int col[4], cmin = 0x7fffffff;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { col[k] = frame_column(lx0 + k, w); cmin = min(cmin, col[k]); }
+    const int base = cmin & ~3;
+    unsigned int sel = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) sel |= (unsigned int)(col[k] - base) << (4 * k);
+    const bool second = base + 4 < w;
+    unsigned char* dst = dstFrame + bx;
+#pragma unroll 4
+    for (int r = 0; r < PY_ROWS; ++r) {
+        const int by = by0 + r;
+        if (by >= rowsTotal) break;
+        const unsigned int* src = reinterpret_cast<const unsigned int*>(img + (size_t)reflect101(by - kEdge, h) * stride + base);
+        const unsigned int w0 = __ldg(src), w1 = second ? __ldg(src + 1) : 0u;
+        *reinterpret_cast<unsigned int*>(dst + (size_t)by * pitch) = __byte_perm(w0, w1, sel);
+    }
+}
+
 __global__ void __launch_bounds__(PY_THREADS)
 pyramid_resize_kernel(unsigned char* __restrict__ pyr, long long pyrFrameBytes, long long srcOff, int srcPitch,
                       long long dstOff, int dstPitch, int dw, int dh, int groups, int nItems, const int* __restrict__ xofs,
@@ -605,9 +654,17 @@ int launch_pyramid(const ExtractParams& P, const unsigned char* dImages, int wid
         const LevelGeom& L = P.lv[0];
         const int groups = L.pitch / 4, nItems = groups * ceil_div(L.h + 2 * kEdge, PY_ROWS);
         const int wordLoads = ((((size_t)dImages) | (size_t)stride | frameStride) & 3) == 0 ? 1 : 0;
-        dim3 grid(ceil_div(nItems, PY_THREADS), P.nFrames);
-        pyramid_level0_kernel<<<grid, PY_THREADS, 0, st>>>(dImages, width, height, stride, frameStride, P.pyr, P.pyrFrameBytes,
-                                                           L.pyrOff, L.pitch, groups, nItems, wordLoads);
+        static const bool noWide = getenv("ORBB_PYR_NOWIDE") != nullptr;     // A/B aid
+        if (!noWide && ((((size_t)dImages) | (size_t)stride | frameStride | (size_t)width) & 15) == 0 && (L.pitch & 15) == 0) {
+            const int groups16 = width / 16 + (L.pitch - width) / 4, nItems16 = groups16 * ceil_div(L.h + 2 * kEdge, PY_ROWS);
+            dim3 grid16(ceil_div(nItems16, PY_THREADS), P.nFrames);
+            pyramid_level0_wide_kernel<<<grid16, PY_THREADS, 0, st>>>(dImages, width, height, stride, frameStride, P.pyr,
+                                                                      P.pyrFrameBytes, L.pyrOff, L.pitch, groups16, nItems16);
+        } else {
+            dim3 grid(ceil_div(nItems, PY_THREADS), P.nFrames);
+            pyramid_level0_kernel<<<grid, PY_THREADS, 0, st>>>(dImages, width, height, stride, frameStride, P.pyr, P.pyrFrameBytes,
+                                                               L.pyrOff, L.pitch, groups, nItems, wordLoads);
+        }
         ++*launches;
     }
     for (int l = 1; l < P.nLevels; ++l) {
