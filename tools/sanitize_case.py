@@ -13,6 +13,11 @@ a, b = shifted_pair(3, 400, 300)
 ex = orbb200.Extractor(600, max_width=400, max_height=300, max_batch=2)
 (ka, da), (kb, db) = ex.extract_batch(np.stack([a, b]))
 kn, dn = ex(synth_frame(5, 400, 300, noise_only=True))       # many candidates: quadtree spill path on level 0
+# a batch of 9 takes the staged pyramid / blur kernels (bulk-async copies, mbarriers) and the wide level-0 copy (400 = 25 * 16)
+ex9 = orbb200.Extractor(300, max_width=400, max_height=300, max_batch=9)
+r9 = ex9.extract_batch(np.stack([synth_frame(20 + i, 400, 300) for i in range(9)]))
+n9 = sum(len(k) for k, _ in r9)
+ex9.close()
 m = orbb200.Matcher(0)
 bounds = (0.0, 0.0, 400.0, 300.0)
 f1, f2 = m.frame(ka, da, bounds), m.frame(kb, db, bounds)
@@ -38,6 +43,14 @@ n_proj_kf = m.search_by_projection(f2, sf, q, da, 10.0, mode=3, check_ori=False,
 bq = np.zeros(len(ka), orbb200.BEST_QUERY_DTYPE)
 bq["u"], bq["v"], bq["radius"], bq["ur"], bq["level"], bq["valid"] = ka["x"] + 7, ka["y"] + 3, 12.0, -1.0, ka["octave"], 1
 best_idx, best_dist = m.search_projected_best(f2, bq, da, chi2=True, inv_sigma2=1.0 / (sf * sf))
+# round-2 entry points: projection on the device, batched windowed searches
+wq = np.zeros(len(ka), orbb200.WORLD_QUERY_DTYPE)
+wq["x"], wq["y"], wq["z"] = (ka["x"] + 7 - 200.0) / 300.0 * 5.0, (ka["y"] + 3 - 150.0) / 300.0 * 5.0, 5.0
+wq["octave"], wq["valid"], wq["obs_positive"], wq["angle"] = ka["octave"], 1, 1, ka["angle"]
+n_world = m.search_by_projection_world(f2, sf, np.eye(3, dtype=np.float32), np.zeros(3, np.float32), (300.0, 300.0, 200.0, 150.0), wq, da, 15.0)[0]
+jobs = [(f2, q, da, None, None), (f1, q[:100], da[:100], None, None), (f2, q[:0], da[:0], None, None)]
+n_pbatch = sum(r[0] for r in m.search_by_projection_batch(jobs, sf, 15.0)[0])
+n_ibatch = sum(r[0] for r in m.search_for_initialization_batch([(f1, f2, prev), (f2, f1, np.stack([kb["x"], kb["y"]], 1).astype(np.float32))], 100, 0.9, True)[0])
 rng = np.random.default_rng(0)
 qd, qa, td, ta = planted_descriptors(rng, 300, 270)
 n_bf = int(m.bruteforce(qd, qa, td, ta, 0.9, True)["nmatches"])
@@ -50,4 +63,4 @@ cnt = torch.zeros((3, 3), dtype=torch.int32, device="cuda")
 torch.cuda.synchronize()
 m.allpairs_device(tab, ang, 0, 3, 0, 3, 0.75, True, cnt)
 m.synchronize()
-print("ok", len(ka), len(kn), n_init, n_proj, n_pts, n_tri, n_bow, n_proj_kf, int((best_idx >= 0).sum()), n_bf, int(d.sum()), cnt.cpu().numpy().tolist())
+print("ok", n9, n_world, n_pbatch, n_ibatch, len(ka), len(kn), n_init, n_proj, n_pts, n_tri, n_bow, n_proj_kf, int((best_idx >= 0).sum()), n_bf, int(d.sum()), cnt.cpu().numpy().tolist())
