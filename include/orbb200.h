@@ -69,9 +69,10 @@ int orbx_extract(orbx_handle h, const uint8_t* image, int width, int height, int
 /* The same operator over n_frames independent frames of one size (frame f at images + f*frame_stride).
  * Outputs for frame f start at keypoints + f*capacity and descriptors + f*capacity*32; n_out[f] = count.
  * Host buffers (pinned for full speed): the batch is cut into pipeline chunks of growing size so that the H2D copy of
- * one chunk, the kernels of the previous one and the D2H copy of the one before overlap.  Two environment variables are
- * read as tuning / debugging aids: ORBB_PIPE_CHUNK = size of the first chunk in frames, ORBB_PIPE_TRACE = print the
- * per-chunk timeline to stderr.                                                                                  */
+ * one chunk, the kernels of the previous ones (two compute streams, alternating) and the D2H copy of the one before
+ * overlap; towards the end of the batch the chunks shrink again so that little is left to do after the last copy.
+ * Environment variables read as tuning / debugging aids: ORBB_PIPE_CHUNK = size of the first chunk in frames,
+ * ORBB_PIPE_TAIL = smallest chunk at the end, ORBB_PIPE_STREAMS = 1 or 2, ORBB_PIPE_TRACE = print the per-chunk timeline. */
 int orbx_extract_batch(orbx_handle h, const uint8_t* images, int n_frames, int width, int height, int stride,
                        size_t frame_stride, orb_keypoint* keypoints, uint8_t* descriptors, int capacity, int* n_out);
 

@@ -43,6 +43,7 @@ struct orbx_extractor {
     std::vector<cudaEvent_t> pipeEvents;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaStream_t streamSide = nullptr;      // small calls: the blur (needs only the pyramid) runs beside FAST + quadtree
+    cudaStream_t stream2 = nullptr;         // host pipeline: odd chunks' kernels (their launch gaps and tails hide under the even ones')
     cudaEvent_t evFork = nullptr, evJoin = nullptr;
     // ctor state
     int nfeatures = 0, nlevels = 0, iniTh = 0, minTh = 0;
@@ -270,10 +271,11 @@ int configure(orbx_extractor* e, int w, int h, int nFrames) {
         ORB_CUDA(cudaStreamSynchronize(e->stream));
         P.brMaps = e->dBriefMaps.p;
         ORB_CHECK(fast_warp_max_warps(P.fw, &P.fw.maxWarps));
-        ORB_CHECK(e->dFastScratch.reserve((size_t)P.fw.maxWarps * P.fw.scratchCap * 2));
+        // two sets (scratch queues, ticket counters): two chunks of the host pipeline may run their FAST kernels at the same time
+        ORB_CHECK(e->dFastScratch.reserve((size_t)P.fw.maxWarps * P.fw.scratchCap * 2 * 2));
         P.fw.scratch = e->dFastScratch.as<unsigned short>();
-        ORB_CHECK(e->dFastCounters.reserve(16));
-        ORB_CUDA(cudaMemsetAsync(e->dFastCounters.p, 0, 16, e->stream));
+        ORB_CHECK(e->dFastCounters.reserve(512));
+        ORB_CUDA(cudaMemsetAsync(e->dFastCounters.p, 0, 512, e->stream));
         ORB_CUDA(cudaStreamSynchronize(e->stream));
         P.fw.counters = e->dFastCounters.as<unsigned int>();
     }
@@ -288,12 +290,17 @@ int configure(orbx_extractor* e, int w, int h, int nFrames) {
 
 // enqueue one batch (device pointers), no synchronisation
 int enqueue(orbx_extractor* e, const uint8_t* dImages, int nFrames, int w, int h, int stride, size_t frameStride,
-            orb_keypoint* dKps, uint8_t* dDesc, int capacity, int* dCount, cudaStream_t st, bool timed, int frameBase = 0) {
+            orb_keypoint* dKps, uint8_t* dDesc, int capacity, int* dCount, cudaStream_t st, bool timed, int frameBase = 0,
+            int set = 0) {
     ORB_CHECK(configure(e, w, h, frameBase + nFrames));
     ExtractParams P = e->P;
     P.nFrames = nFrames;
     P.outCapacity = capacity;
     P.fw.frameBase = frameBase;
+    if (set) {         // the second set of the FAST kernel's scratch queues and ticket counters (256 bytes apart)
+        P.fw.scratch += (size_t)P.fw.maxWarps * P.fw.scratchCap;
+        P.fw.counters += 64;
+    }
     if (frameBase) {   // this call works in arena slots [frameBase, frameBase + nFrames)
         P.pyr += (size_t)frameBase * P.pyrFrameBytes;
         P.blur += (size_t)frameBase * P.blurFrameBytes;
@@ -416,6 +423,7 @@ int orbx_create(int nfeatures, float scaleFactor, int nlevels, int iniTh, int mi
     if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&e->streamOut, cudaStreamNonBlocking);
     for (int i = 0; i < 4 && ce == cudaSuccess; ++i) ce = cudaEventCreate(&e->ev[i]);
     if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&e->streamSide, cudaStreamNonBlocking);
+    if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking);
     if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&e->evFork, cudaEventDisableTiming);
     if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&e->evJoin, cudaEventDisableTiming);
     if (ce != cudaSuccess) {
@@ -449,6 +457,7 @@ int orbx_destroy(orbx_handle e) {
     if (e->evFork) cudaEventDestroy(e->evFork);
     if (e->evJoin) cudaEventDestroy(e->evJoin);
     if (e->streamSide) cudaStreamDestroy(e->streamSide);
+    if (e->stream2) cudaStreamDestroy(e->stream2);
     if (e->streamIn) cudaStreamDestroy(e->streamIn);
     if (e->streamOut) cudaStreamDestroy(e->streamOut);
     if (e->stream) cudaStreamDestroy(e->stream);
@@ -569,6 +578,10 @@ int orbx_extract_batch(orbx_handle e, const uint8_t* images, int nFrames, int w,
     if (const char* envChunk = getenv("ORBB_PIPE_CHUNK")) chunk0 = std::max(1, std::min(atoi(envChunk), super));   // tuning knob
     const double chunkGrowth = nPipe >= 2048 ? 1.1 : 1.2;
     const int chunkCap = std::min(768, 8 * chunk0);
+    int nStreams = 2, tailMin = 128;
+    if (const char* v = getenv("ORBB_PIPE_STREAMS")) nStreams = atoi(v) == 1 ? 1 : 2;       // tuning knobs
+    if (const char* v = getenv("ORBB_PIPE_TAIL")) tailMin = std::max(1, atoi(v));
+    if (nStreams == 1) tailMin = 1 << 30;
     auto pipe_event = [&](int i) -> cudaEvent_t {
         while ((int)e->pipeEvents.size() <= i) {
             cudaEvent_t ev;
@@ -577,7 +590,7 @@ int orbx_extract_batch(orbx_handle e, const uint8_t* images, int nFrames, int w,
         }
         return e->pipeEvents[i];
     };
-    const int maxChunks = nPipe / std::max(1, chunk0) + 4;
+    const int maxChunks = nPipe / std::max(1, std::min(chunk0, tailMin)) + 24;
     int status = ORB_OK;
     static const bool trace = getenv("ORBB_PIPE_TRACE") != nullptr;   // debugging aid: per-chunk timeline on stderr
     std::vector<cudaEvent_t> tev;
@@ -593,7 +606,10 @@ int orbx_extract_batch(orbx_handle e, const uint8_t* images, int nFrames, int w,
         for (int f0 = 0, nf = 0; f0 < ns; f0 += nf, ++k) {
             const int remaining = ns - f0;
             nf = std::min(std::max(1, (int)want), remaining);
-            if (remaining - nf > 0 && remaining - nf < nf / 3) nf = remaining;    // no sliver at the end
+            // what is left after the last copy -- the last chunk's kernels and its copy back -- is pure latency: towards
+            // the end a chunk takes at most a third of what remains, down to tailMin frames
+            if (nStreams == 2) nf = std::min(nf, std::max(tailMin, remaining / 3));
+            if (remaining - nf > 0 && remaining - nf < std::min(nf / 3, tailMin)) nf = remaining;    // no sliver at the end
             want = std::min(want * chunkGrowth, (double)chunkCap);
             if (!pipe_event(2 * k + 1)) return fail(ORB_ERR_CUDA, "orbx_extract_batch: cannot create pipeline events");
             uint8_t* dImg = e->dImages.as<uint8_t>() + (size_t)f0 * imgBytes;
@@ -605,12 +621,17 @@ int orbx_extract_batch(orbx_handle e, const uint8_t* images, int nFrames, int w,
             }
             ORB_CUDA(cudaEventRecord(e->pipeEvents[2 * k], e->streamIn));
             if (trace) cudaEventRecord(tev[3 * k], e->streamIn);
-            cudaStream_t cs = e->stream;   // one compute stream: kernels of two chunks sharing the SMs ran 8 % slower
+            // Two compute streams, alternating: sharing the SMs costs the kernels ~8 %, but since the kernels outrun the
+            // link the stream that is ahead only ever waits for its copy, while a chunk's launch gaps and kernel tails
+            // (~0.2 ms per chunk) hide under the other chunk's kernels -- which is what lets the chunks shrink towards
+            // the end of the batch (below) without the kernels falling behind the copies.
+            cudaStream_t cs = (nStreams == 2 && (k & 1)) ? e->stream2 : e->stream;
             ORB_CUDA(cudaStreamWaitEvent(cs, e->pipeEvents[2 * k], 0));
             orb_keypoint* dK = e->dKps.as<orb_keypoint>() + (size_t)f0 * capacity;
             uint8_t* dD = e->dDesc.as<uint8_t>() + (size_t)f0 * capacity * 32;
             int* dN = e->dCount.as<int>() + f0;
-            ORB_CHECK(enqueue(e, dImg, nf, w, h, stride, imgBytes, dK, dD, capacity, dN, cs, s0 == 0 && f0 == 0, f0));
+            ORB_CHECK(enqueue(e, dImg, nf, w, h, stride, imgBytes, dK, dD, capacity, dN, cs, s0 == 0 && f0 == 0, f0,
+                              cs == e->stream2 ? 1 : 0));
             ORB_CUDA(cudaEventRecord(e->pipeEvents[2 * k + 1], cs));
             if (trace) cudaEventRecord(tev[3 * k + 1], cs);
             ORB_CUDA(cudaStreamWaitEvent(e->streamOut, e->pipeEvents[2 * k + 1], 0));
@@ -623,6 +644,7 @@ int orbx_extract_batch(orbx_handle e, const uint8_t* images, int nFrames, int w,
         // the next super-chunk reuses the arena and the staging buffers: drain everything first
         ORB_CUDA(cudaStreamSynchronize(e->streamOut));
         ORB_CUDA(cudaStreamSynchronize(e->stream));
+        ORB_CUDA(cudaStreamSynchronize(e->stream2));
         if (trace && s0 == 0) {
             for (int c = 0; c < k; ++c) {
                 float a = 0, b = 0, d = 0;
