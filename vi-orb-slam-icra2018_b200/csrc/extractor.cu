@@ -44,6 +44,7 @@ struct orbx_extractor {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaStream_t streamSide = nullptr;      // small calls: the blur (needs only the pyramid) runs beside FAST + quadtree
     cudaStream_t stream2 = nullptr;         // host pipeline: odd chunks' kernels (their launch gaps and tails hide under the even ones')
+    PinnedBuf pinIn, pinOut;                // small calls: staging of pageable images / outputs
     cudaEvent_t evFork = nullptr, evJoin = nullptr;
     // ctor state
     int nfeatures = 0, nlevels = 0, iniTh = 0, minTh = 0;
@@ -456,6 +457,8 @@ int orbx_destroy(orbx_handle e) {
     for (cudaEvent_t ev : e->pipeEvents) cudaEventDestroy(ev);
     if (e->evFork) cudaEventDestroy(e->evFork);
     if (e->evJoin) cudaEventDestroy(e->evJoin);
+    e->pinIn.release();
+    e->pinOut.release();
     if (e->streamSide) cudaStreamDestroy(e->streamSide);
     if (e->stream2) cudaStreamDestroy(e->stream2);
     if (e->streamIn) cudaStreamDestroy(e->streamIn);
@@ -518,8 +521,26 @@ int orbx_extract_batch(orbx_handle e, const uint8_t* images, int nFrames, int w,
     if (nFrames <= 4 && nFrames <= super) {
         cudaStream_t st = e->stream;
         uint8_t* dImg = e->dImages.as<uint8_t>();
-        if (frameStride == imgBytes) ORB_CUDA(cudaMemcpyAsync(dImg, images, (size_t)nFrames * imgBytes, cudaMemcpyHostToDevice, st));
-        else ORB_CUDA(cudaMemcpy2DAsync(dImg, imgBytes, images, frameStride, imgBytes, nFrames, cudaMemcpyHostToDevice, st));
+        // A live loop hands over pageable memory (a cv::Mat's data, std::vector outputs), for which every cudaMemcpyAsync is a
+        // synchronous staged copy inside the driver.  Staging through the handle's own pinned buffers -- one memcpy in, three
+        // truly asynchronous copies out into pinned memory, then memcpy of the n valid entries -- takes ~30 us off a frame.
+        static const bool noStage = getenv("ORBB_NO_STAGE") != nullptr;
+        bool stage = !noStage;
+        if (stage) {
+            cudaPointerAttributes at;
+            if (cudaPointerGetAttributes(&at, images) == cudaSuccess && at.type != cudaMemoryTypeUnregistered) stage = false;   // already pinned
+            else cudaGetLastError();
+        }
+        if (stage) {
+            ORB_CHECK(e->pinIn.reserve((size_t)nFrames * imgBytes));
+            ORB_CHECK(e->pinOut.reserve((size_t)nFrames * ((size_t)capacity * 60 + 64)));
+            for (int f = 0; f < nFrames; ++f) std::memcpy(e->pinIn.as<uint8_t>() + (size_t)f * imgBytes, images + (size_t)f * frameStride, imgBytes);
+            ORB_CUDA(cudaMemcpyAsync(dImg, e->pinIn.p, (size_t)nFrames * imgBytes, cudaMemcpyHostToDevice, st));
+        } else if (frameStride == imgBytes) {
+            ORB_CUDA(cudaMemcpyAsync(dImg, images, (size_t)nFrames * imgBytes, cudaMemcpyHostToDevice, st));
+        } else {
+            ORB_CUDA(cudaMemcpy2DAsync(dImg, imgBytes, images, frameStride, imgBytes, nFrames, cudaMemcpyHostToDevice, st));
+        }
         orb_keypoint* dK = e->dKps.as<orb_keypoint>();
         uint8_t* dD = e->dDesc.as<uint8_t>();
         int* dN = e->dCount.as<int>();
@@ -552,10 +573,27 @@ int orbx_extract_batch(orbx_handle e, const uint8_t* images, int nFrames, int w,
             timedCall = true;
             ORB_CHECK(enqueue(e, dImg, nFrames, w, h, stride, imgBytes, dK, dD, capacity, dN, st, true, 0));
         }
-        ORB_CUDA(cudaMemcpyAsync(nOut, dN, (size_t)nFrames * 4, cudaMemcpyDeviceToHost, st));
-        ORB_CUDA(cudaMemcpyAsync(kps, dK, (size_t)nFrames * capacity * sizeof(orb_keypoint), cudaMemcpyDeviceToHost, st));
-        ORB_CUDA(cudaMemcpyAsync(desc, dD, (size_t)nFrames * capacity * 32, cudaMemcpyDeviceToHost, st));
-        ORB_CUDA(cudaStreamSynchronize(st));
+        if (stage) {
+            uint8_t* po = e->pinOut.as<uint8_t>();
+            int* pn = reinterpret_cast<int*>(po);
+            orb_keypoint* pk = reinterpret_cast<orb_keypoint*>(po + 64);
+            uint8_t* pd = po + 64 + (size_t)nFrames * capacity * sizeof(orb_keypoint);
+            ORB_CUDA(cudaMemcpyAsync(pn, dN, (size_t)nFrames * 4, cudaMemcpyDeviceToHost, st));
+            ORB_CUDA(cudaMemcpyAsync(pk, dK, (size_t)nFrames * capacity * sizeof(orb_keypoint), cudaMemcpyDeviceToHost, st));
+            ORB_CUDA(cudaMemcpyAsync(pd, dD, (size_t)nFrames * capacity * 32, cudaMemcpyDeviceToHost, st));
+            ORB_CUDA(cudaStreamSynchronize(st));
+            for (int f = 0; f < nFrames; ++f) {
+                nOut[f] = pn[f];
+                const size_t n = (size_t)std::min(std::max(pn[f], 0), capacity);
+                std::memcpy(kps + (size_t)f * capacity, pk + (size_t)f * capacity, n * sizeof(orb_keypoint));
+                std::memcpy(desc + (size_t)f * capacity * 32, pd + (size_t)f * capacity * 32, n * 32);
+            }
+        } else {
+            ORB_CUDA(cudaMemcpyAsync(nOut, dN, (size_t)nFrames * 4, cudaMemcpyDeviceToHost, st));
+            ORB_CUDA(cudaMemcpyAsync(kps, dK, (size_t)nFrames * capacity * sizeof(orb_keypoint), cudaMemcpyDeviceToHost, st));
+            ORB_CUDA(cudaMemcpyAsync(desc, dD, (size_t)nFrames * capacity * 32, cudaMemcpyDeviceToHost, st));
+            ORB_CUDA(cudaStreamSynchronize(st));
+        }
         if (timedCall) {
             float ms;
             for (int i = 0; i < 3; ++i)
