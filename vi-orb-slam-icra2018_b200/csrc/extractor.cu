@@ -75,9 +75,10 @@ struct orbx_extractor {
     struct GraphKey {
         int w = 0, h = 0, stride = 0, nFrames = 0, capacity = 0;
         const void *img = nullptr, *kps = nullptr, *desc = nullptr, *cnt = nullptr, *pyr = nullptr;
+        const void *pinIn = nullptr, *pinOut = nullptr;     // staged calls: the copies in and out are nodes of the graph
         bool operator==(const GraphKey& o) const {
             return w == o.w && h == o.h && stride == o.stride && nFrames == o.nFrames && capacity == o.capacity && img == o.img &&
-                   kps == o.kps && desc == o.desc && cnt == o.cnt && pyr == o.pyr;
+                   kps == o.kps && desc == o.desc && cnt == o.cnt && pyr == o.pyr && pinIn == o.pinIn && pinOut == o.pinOut;
         }
     } graphKey, graphSeen;
     cudaGraphExec_t graphExec = nullptr;
@@ -531,25 +532,43 @@ int orbx_extract_batch(orbx_handle e, const uint8_t* images, int nFrames, int w,
             if (cudaPointerGetAttributes(&at, images) == cudaSuccess && at.type != cudaMemoryTypeUnregistered) stage = false;   // already pinned
             else cudaGetLastError();
         }
+        orb_keypoint* dK = e->dKps.as<orb_keypoint>();
+        uint8_t* dD = e->dDesc.as<uint8_t>();
+        int* dN = e->dCount.as<int>();
+        int* pn = nullptr;
+        orb_keypoint* pk = nullptr;
+        uint8_t* pd = nullptr;
         if (stage) {
             ORB_CHECK(e->pinIn.reserve((size_t)nFrames * imgBytes));
             ORB_CHECK(e->pinOut.reserve((size_t)nFrames * ((size_t)capacity * 60 + 64)));
             for (int f = 0; f < nFrames; ++f) std::memcpy(e->pinIn.as<uint8_t>() + (size_t)f * imgBytes, images + (size_t)f * frameStride, imgBytes);
-            ORB_CUDA(cudaMemcpyAsync(dImg, e->pinIn.p, (size_t)nFrames * imgBytes, cudaMemcpyHostToDevice, st));
-        } else if (frameStride == imgBytes) {
-            ORB_CUDA(cudaMemcpyAsync(dImg, images, (size_t)nFrames * imgBytes, cudaMemcpyHostToDevice, st));
-        } else {
-            ORB_CUDA(cudaMemcpy2DAsync(dImg, imgBytes, images, frameStride, imgBytes, nFrames, cudaMemcpyHostToDevice, st));
+            uint8_t* po = e->pinOut.as<uint8_t>();
+            pn = reinterpret_cast<int*>(po);
+            pk = reinterpret_cast<orb_keypoint*>(po + 64);
+            pd = po + 64 + (size_t)nFrames * capacity * sizeof(orb_keypoint);
         }
-        orb_keypoint* dK = e->dKps.as<orb_keypoint>();
-        uint8_t* dD = e->dDesc.as<uint8_t>();
-        int* dN = e->dCount.as<int>();
+        // the copies of a call: into the arena, and (staged) out into the pinned buffer -- issued eagerly or captured
+        auto copy_in = [&]() -> int {
+            if (stage) ORB_CUDA(cudaMemcpyAsync(dImg, e->pinIn.p, (size_t)nFrames * imgBytes, cudaMemcpyHostToDevice, st));
+            else if (frameStride == imgBytes) ORB_CUDA(cudaMemcpyAsync(dImg, images, (size_t)nFrames * imgBytes, cudaMemcpyHostToDevice, st));
+            else ORB_CUDA(cudaMemcpy2DAsync(dImg, imgBytes, images, frameStride, imgBytes, nFrames, cudaMemcpyHostToDevice, st));
+            return ORB_OK;
+        };
+        auto copy_out_staged = [&]() -> int {
+            ORB_CUDA(cudaMemcpyAsync(pn, dN, (size_t)nFrames * 4, cudaMemcpyDeviceToHost, st));
+            ORB_CUDA(cudaMemcpyAsync(pk, dK, (size_t)nFrames * capacity * sizeof(orb_keypoint), cudaMemcpyDeviceToHost, st));
+            ORB_CUDA(cudaMemcpyAsync(pd, dD, (size_t)nFrames * capacity * 32, cudaMemcpyDeviceToHost, st));
+            return ORB_OK;
+        };
         orbx_extractor::GraphKey key;
         key.w = w; key.h = h; key.stride = stride; key.nFrames = nFrames; key.capacity = capacity;
         key.img = dImg; key.kps = dK; key.desc = dD; key.cnt = dN; key.pyr = e->P.pyr;
+        key.pinIn = stage ? e->pinIn.p : nullptr;
+        key.pinOut = stage ? e->pinOut.p : nullptr;
         bool timedCall = false;
         if (!noGraph && !e->profiling && e->graphExec && key == e->graphKey) {
-            ORB_CUDA(cudaGraphLaunch(e->graphExec, st));
+            if (!stage) ORB_CHECK(copy_in());
+            ORB_CUDA(cudaGraphLaunch(e->graphExec, st));     // staged: copy in, kernels and copies out are ONE launch
             e->launches = e->graphLaunches;
             e->residentFrames = nFrames;
             e->lastCapacity = capacity;
@@ -557,8 +576,11 @@ int orbx_extract_batch(orbx_handle e, const uint8_t* images, int nFrames, int w,
             // second call with these buffers: capture (attributes and occupancy caches were set by the first, eager call)
             if (e->graphExec) { cudaGraphExecDestroy(e->graphExec); e->graphExec = nullptr; }
             cudaGraph_t graph = nullptr;
+            if (!stage) ORB_CHECK(copy_in());
             ORB_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
-            const int stEnq = enqueue(e, dImg, nFrames, w, h, stride, imgBytes, dK, dD, capacity, dN, st, false, 0);
+            int stEnq = stage ? copy_in() : ORB_OK;
+            if (stEnq == ORB_OK) stEnq = enqueue(e, dImg, nFrames, w, h, stride, imgBytes, dK, dD, capacity, dN, st, false, 0);
+            if (stEnq == ORB_OK && stage) stEnq = copy_out_staged();
             const cudaError_t ce = cudaStreamEndCapture(st, &graph);
             if (stEnq != ORB_OK) { if (graph) cudaGraphDestroy(graph); return stEnq; }
             if (ce != cudaSuccess) return fail(ORB_ERR_CUDA, "orbx_extract_batch: stream capture failed: %s", cudaGetErrorString(ce));
@@ -571,16 +593,11 @@ int orbx_extract_batch(orbx_handle e, const uint8_t* images, int nFrames, int w,
         } else {
             e->graphSeen = key;
             timedCall = true;
+            ORB_CHECK(copy_in());
             ORB_CHECK(enqueue(e, dImg, nFrames, w, h, stride, imgBytes, dK, dD, capacity, dN, st, true, 0));
+            if (stage) ORB_CHECK(copy_out_staged());
         }
         if (stage) {
-            uint8_t* po = e->pinOut.as<uint8_t>();
-            int* pn = reinterpret_cast<int*>(po);
-            orb_keypoint* pk = reinterpret_cast<orb_keypoint*>(po + 64);
-            uint8_t* pd = po + 64 + (size_t)nFrames * capacity * sizeof(orb_keypoint);
-            ORB_CUDA(cudaMemcpyAsync(pn, dN, (size_t)nFrames * 4, cudaMemcpyDeviceToHost, st));
-            ORB_CUDA(cudaMemcpyAsync(pk, dK, (size_t)nFrames * capacity * sizeof(orb_keypoint), cudaMemcpyDeviceToHost, st));
-            ORB_CUDA(cudaMemcpyAsync(pd, dD, (size_t)nFrames * capacity * 32, cudaMemcpyDeviceToHost, st));
             ORB_CUDA(cudaStreamSynchronize(st));
             for (int f = 0; f < nFrames; ++f) {
                 nOut[f] = pn[f];
