@@ -33,6 +33,15 @@ struct orbm_matcher {
     int launches = 0;
     orbb::DevBuf in0, in1, in2, in3, in4, in5, out0, out1, out2, out3, out4, ws0, ws1, ws2, ws3;
     orbb::PinnedBuf pin0, pin1, pin2, pin3, pin4;   // staging of the batched searches
+    // Single calls take pageable host arrays, for which every cudaMemcpyAsync is a synchronous staged copy inside the driver.
+    // stage_upload / stage_download go through this pinned area instead (bump-allocated per call, reset by ORBM_ENTER):
+    // one memcpy + a truly asynchronous copy in; asynchronous copies out, handed to the caller's arrays by stage_finish()
+    // after the call's one synchronisation.
+    orbb::PinnedBuf stage;
+    size_t stageOff = 0;
+    struct PendingOut { void* dst; const void* src; size_t bytes; };
+    PendingOut pending[8];
+    int nPending = 0;
 };
 
 // Prologue of every matcher entry point: null check, device selection for the duration of the call, launch counter reset.
@@ -40,4 +49,6 @@ struct orbm_matcher {
     if (!(h)) return ::orbb::fail(ORB_ERR_INVALID, "%s: null matcher handle", __func__);              \
     ::orbb::DeviceGuard guard__((h)->device);                                                         \
     if (!guard__.ok) return ::orbb::fail(ORB_ERR_CUDA, "%s: cannot select device %d", __func__, (h)->device); \
-    (h)->launches = 0;
+    (h)->launches = 0;                                                                                \
+    (h)->stageOff = 0;                                                                                \
+    (h)->nPending = 0;

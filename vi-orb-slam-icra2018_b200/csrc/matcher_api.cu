@@ -33,7 +33,7 @@ int orbm_destroy(orbm_handle h) {
     DevBuf* bufs[] = {&h->in0, &h->in1, &h->in2, &h->in3, &h->in4, &h->in5, &h->out0, &h->out1, &h->out2, &h->out3,
                       &h->out4, &h->ws0, &h->ws1, &h->ws2, &h->ws3};
     for (DevBuf* b : bufs) b->release();
-    PinnedBuf* pins[] = {&h->pin0, &h->pin1, &h->pin2, &h->pin3, &h->pin4};
+    PinnedBuf* pins[] = {&h->pin0, &h->pin1, &h->pin2, &h->pin3, &h->pin4, &h->stage};
     for (PinnedBuf* b : pins) b->release();
     cudaStreamDestroy(h->stream);
     delete h;

@@ -1031,6 +1031,8 @@ namespace {
 constexpr size_t kReplayFixed = (size_t)kReplayFixedInts * 4;   // candidate / query staging of replay_queries
 constexpr size_t kReplaySmemMax = 160 * 1024;   // shared-memory state of the replays (10k keypoints for init, 18k for the others)
 
+void* stage_take(orbm_matcher* h, size_t bytes);
+
 // phase 1 for nq queries already built in h->ws0 (AreaQuery[nq]); leaves offsets in ws1 and candidates in ws2
 int run_candidates(orbm_matcher* h, const FrameDev& f, const uint4* dQdesc, int nq, const float* dURight, int* totalOut) {
     cudaStream_t st = h->stream;
@@ -1042,8 +1044,12 @@ int run_candidates(orbm_matcher* h, const FrameDev& f, const uint4* dQdesc, int 
     candidates_kernel<<<blocks, wpb * 32, 0, st>>>(f, h->ws0.as<AreaQuery>(), dQdesc, nq, dURight, counts, nullptr, nullptr);
     scan_kernel<<<1, 1024, 0, st>>>(counts, offsets, nq);
     int total = 0;
-    ORB_CUDA(cudaMemcpyAsync(&total, offsets + nq, 4, cudaMemcpyDeviceToHost, st));
-    ORB_CUDA(cudaStreamSynchronize(st));
+    {
+        int* pinnedTotal = static_cast<int*>(stage_take(h, 4));
+        ORB_CUDA(cudaMemcpyAsync(pinnedTotal ? pinnedTotal : &total, offsets + nq, 4, cudaMemcpyDeviceToHost, st));
+        ORB_CUDA(cudaStreamSynchronize(st));
+        if (pinnedTotal) total = *pinnedTotal;
+    }
     ORB_CHECK(h->ws2.reserve((size_t)(total + 1) * sizeof(int2)));
     candidates_kernel<<<blocks, wpb * 32, 0, st>>>(f, h->ws0.as<AreaQuery>(), dQdesc, nq, dURight, nullptr, offsets, h->ws2.as<int2>());
     h->launches += 3;
@@ -1055,6 +1061,40 @@ int run_candidates(orbm_matcher* h, const FrameDev& f, const uint4* dQdesc, int 
 int upload(DevBuf& b, const void* src, size_t bytes, cudaStream_t st) {
     ORB_CHECK(b.reserve(bytes + 16));
     if (bytes) ORB_CUDA(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, st));
+    return ORB_OK;
+}
+
+// ---- pinned staging of a single call's pageable inputs and outputs (matcher.h) -----------------------------------------
+constexpr size_t kStageBytes = 4u << 20;
+// a slot of the call's staging area, or nullptr when it is full (the caller then copies directly)
+void* stage_take(orbm_matcher* h, size_t bytes) {
+    if (!h->stage.p && h->stage.reserve(kStageBytes) != ORB_OK) return nullptr;
+    const size_t need = (bytes + 255) & ~(size_t)255;
+    if (h->stageOff + need > kStageBytes) return nullptr;
+    void* p = (char*)h->stage.p + h->stageOff;
+    h->stageOff += need;
+    return p;
+}
+int stage_upload(orbm_matcher* h, DevBuf& b, const void* src, size_t bytes, cudaStream_t st) {
+    ORB_CHECK(b.reserve(bytes + 16));
+    if (!bytes) return ORB_OK;
+    void* s = stage_take(h, bytes);
+    if (s) std::memcpy(s, src, bytes);
+    ORB_CUDA(cudaMemcpyAsync(b.p, s ? s : src, bytes, cudaMemcpyHostToDevice, st));
+    return ORB_OK;
+}
+int stage_download(orbm_matcher* h, void* dst, const void* dsrc, size_t bytes, cudaStream_t st) {
+    if (!bytes) return ORB_OK;
+    void* s = h->nPending < 8 ? stage_take(h, bytes) : nullptr;
+    ORB_CUDA(cudaMemcpyAsync(s ? s : dst, dsrc, bytes, cudaMemcpyDeviceToHost, st));
+    if (s) h->pending[h->nPending++] = orbm_matcher::PendingOut{dst, s, bytes};
+    return ORB_OK;
+}
+// the call's synchronisation; afterwards the staged outputs are handed to the caller's arrays
+int stage_finish(orbm_matcher* h, cudaStream_t st) {
+    ORB_CUDA(cudaStreamSynchronize(st));
+    for (int i = 0; i < h->nPending; ++i) std::memcpy(h->pending[i].dst, h->pending[i].src, h->pending[i].bytes);
+    h->nPending = 0;
     return ORB_OK;
 }
 
@@ -1271,7 +1311,7 @@ int orbm_search_for_initialization(orbm_handle h, orbm_frame f1, orbm_frame f2, 
     const int n1 = f1->n, n2 = f2->n;
     if (n1 == 0) return ORB_OK;
     cudaStream_t st = h->stream;
-    ORB_CHECK(upload(h->in0, prevXY, (size_t)n1 * 8, st));
+    ORB_CHECK(stage_upload(h, h->in0, prevXY, (size_t)n1 * 8, st));
     ORB_CHECK(h->ws0.reserve((size_t)n1 * sizeof(AreaQuery)));
     const FrameDev d1 = f1->dev(), d2 = f2->dev();
     init_queries_kernel<<<ceil_div(n1, 256), 256, 0, st>>>(d1, h->in0.as<float>(), windowSize, h->ws0.as<AreaQuery>());
@@ -1289,11 +1329,10 @@ int orbm_search_for_initialization(orbm_handle h, orbm_frame f1, orbm_frame f2, 
                                                   h->in0.as<float>(), h->out0.as<int>(), pushBin, pushBin + n1 + 1, h->out3.as<int>());
     h->launches += 1;
     ORB_CUDA(cudaGetLastError());
-    ORB_CUDA(cudaMemcpyAsync(matches12, h->out0.p, (size_t)n1 * 4, cudaMemcpyDeviceToHost, st));
-    ORB_CUDA(cudaMemcpyAsync(prevXY, h->in0.p, (size_t)n1 * 8, cudaMemcpyDeviceToHost, st));
-    ORB_CUDA(cudaMemcpyAsync(nmatches, h->out3.p, 4, cudaMemcpyDeviceToHost, st));
-    ORB_CUDA(cudaStreamSynchronize(st));
-    return ORB_OK;
+    ORB_CHECK(stage_download(h, matches12, h->out0.p, (size_t)n1 * 4, st));
+    ORB_CHECK(stage_download(h, prevXY, h->in0.p, (size_t)n1 * 8, st));
+    ORB_CHECK(stage_download(h, nmatches, h->out3.p, 4, st));
+    return stage_finish(h, st);
 }
 
 int orbm_search_by_projection(orbm_handle h, orbm_frame cur, const float* sf, int nlevels, const float* uRight, float mbf,
@@ -1310,10 +1349,10 @@ int projection_search_device(orbm_matcher* h, orbm_frame cur, const float* sf, i
                              float th, int mode, int maxDist, const uint8_t* occupied, int* curMatch, int checkOri, int* nmatches) {
     const int n = cur->n;
     cudaStream_t st = h->stream;
-    ORB_CHECK(upload(h->in2, sf, (size_t)nlevels * 4, st));
-    if (uRight) ORB_CHECK(upload(h->in3, uRight, (size_t)n * 4, st));
+    ORB_CHECK(stage_upload(h, h->in2, sf, (size_t)nlevels * 4, st));
+    if (uRight) ORB_CHECK(stage_upload(h, h->in3, uRight, (size_t)n * 4, st));
     ORB_CHECK(h->in4.reserve((size_t)n + 16));
-    if (occupied) ORB_CUDA(cudaMemcpyAsync(h->in4.p, occupied, (size_t)n, cudaMemcpyHostToDevice, st));
+    if (occupied) ORB_CHECK(stage_upload(h, h->in4, occupied, (size_t)n, st));
     else ORB_CUDA(cudaMemsetAsync(h->in4.p, 0, (size_t)n, st));
     ORB_CHECK(h->ws0.reserve((size_t)nq * sizeof(AreaQuery)));
     const FrameDev d = cur->dev();
@@ -1333,10 +1372,9 @@ int projection_search_device(orbm_matcher* h, orbm_frame cur, const float* sf, i
                                                       pushBin, pushBin + nq + 1, h->out3.as<int>());
     h->launches += 1;
     ORB_CUDA(cudaGetLastError());
-    ORB_CUDA(cudaMemcpyAsync(curMatch, h->out0.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-    ORB_CUDA(cudaMemcpyAsync(nmatches, h->out3.p, 4, cudaMemcpyDeviceToHost, st));
-    ORB_CUDA(cudaStreamSynchronize(st));
-    return ORB_OK;
+    ORB_CHECK(stage_download(h, curMatch, h->out0.p, (size_t)n * 4, st));
+    ORB_CHECK(stage_download(h, nmatches, h->out3.p, 4, st));
+    return stage_finish(h, st);
 }
 
 }  // namespace
@@ -1355,8 +1393,8 @@ int orbm_search_by_projection_ex(orbm_handle h, orbm_frame cur, const float* sf,
     for (int i = 0; i < n; ++i) curMatch[i] = -1;
     if (nq == 0 || n == 0) return ORB_OK;
     cudaStream_t st = h->stream;
-    ORB_CHECK(upload(h->in0, queries, (size_t)nq * sizeof(orbm_proj_query), st));
-    ORB_CHECK(upload(h->in1, qdesc, (size_t)nq * 32, st));
+    ORB_CHECK(stage_upload(h, h->in0, queries, (size_t)nq * sizeof(orbm_proj_query), st));
+    ORB_CHECK(stage_upload(h, h->in1, qdesc, (size_t)nq * 32, st));
     return projection_search_device(h, cur, sf, nlevels, uRight, mbf, nq, th, mode, maxDist, occupied, curMatch, checkOri, nmatches);
 }
 
@@ -1375,8 +1413,8 @@ int orbm_search_by_projection_world(orbm_handle h, orbm_frame cur, const float* 
     for (int i = 0; i < n; ++i) curMatch[i] = -1;
     if (nq == 0 || n == 0) return ORB_OK;
     cudaStream_t st = h->stream;
-    ORB_CHECK(upload(h->in5, queries, (size_t)nq * sizeof(orbm_world_query), st));
-    ORB_CHECK(upload(h->in1, qdesc, (size_t)nq * 32, st));
+    ORB_CHECK(stage_upload(h, h->in5, queries, (size_t)nq * sizeof(orbm_world_query), st));
+    ORB_CHECK(stage_upload(h, h->in1, qdesc, (size_t)nq * 32, st));
     ORB_CHECK(h->in0.reserve((size_t)nq * sizeof(orbm_proj_query)));
     PoseDev P;
     for (int i = 0; i < 9; ++i) P.R[i] = pose->Rcw[i];
