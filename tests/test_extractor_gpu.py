@@ -141,7 +141,9 @@ def test_host_pipeline_chunks_take_the_staged_kernels(oracle, monkeypatch):
     FAST and BRIEF address the arena by frameBase + frame: 40 frames (chunks at frameBase 0, 16, ...), every frame's
     keypoints and descriptors equal the oracle's on the 5 distinct images the batch repeats."""
     monkeypatch.setenv("ORBB_PIPE_CHUNK", "16")
-    base = [synth_frame(950 + i, 752, 480) for i in range(5)]
+    # two of the five images are pure noise: their cells overflow the FAST kernel's shared-memory queue into the per-warp
+    # global scratch, of which the two compute streams of the pipeline each own a set
+    base = [synth_frame(950 + i, 752, 480, noise_only=(i in (1, 3))) for i in range(5)]
     frames = np.stack([base[i % 5] for i in range(40)])
     ex = orbb200.Extractor(1000, max_width=752, max_height=480, max_batch=40)
     oe = oracle.extractor(1000)
