@@ -140,8 +140,9 @@ blur_staged_kernel(const __grid_constant__ ExtractParams P, int level, int nBand
     }
     __syncthreads();
     const bool active = tid < groups;
+    const int issuerTid = (int)blockDim.x > groups ? (int)blockDim.x - 1 : 0;     // a thread without pixels, if the block has one
     auto issue = [&](int t, int buf) {      // the band's input rows y0-3 .. y0+rowsOut+2 = padded rows y0+16 .. ; rowsOut + 6 of them
-        if (tid == 0) {
+        if (tid == issuerTid) {
             const int frame = t / nBands, band = t - frame * nBands;
             const int y0 = band * BL_ROWS;
             const int rowsOut = min(BL_ROWS, L.h - y0);

@@ -345,11 +345,15 @@ pyramid_resize3_kernel(unsigned char* __restrict__ pyr, long long pyrFrameBytes,
     }
     __syncthreads();
     const bool active = tid < groups;
+    // the copies are issued by a thread that has no pixels to compute when the block has one (block size = groups rounded up
+    // to a warp): looking up the band record and issuing the copy is a chain of ~600 cycles that would otherwise delay one
+    // working warp, and with it the whole CTA at the barrier, on every band
+    const int issuerTid = (int)blockDim.x > groups ? (int)blockDim.x - 1 : 0;
     uint4 ca = make_uint4(0, 0, 0, 0), cb = ca;
     if (active) { ca = __ldg(colTab + 2 * tid); cb = __ldg(colTab + 2 * tid + 1); }
     const unsigned int shift = ca.y, sel01 = ca.z, sel23 = ca.w;
     auto issue = [&](int tile, int buf) {
-        if (tid == 0) {
+        if (tid == issuerTid) {
             const int frame = tile / nBands, band = tile - frame * nBands;
             const int4 bt = __ldg(bandTab + band);
             const unsigned char* src = pyr + (size_t)frame * pyrFrameBytes + srcOff + bt.x;
