@@ -1160,8 +1160,8 @@ int orbm_frame_create(orbm_handle h, const orb_keypoint* keys, const uint8_t* de
     orbm_frame_s* f = new_frame(h, n, minX, minY, maxX, maxY);
     cudaStream_t st = h->stream;
     auto body = [&]() -> int {
-        ORB_CHECK(upload(f->keys, keys, (size_t)n * sizeof(orb_keypoint), st));
-        ORB_CHECK(upload(f->desc, desc, (size_t)n * 32, st));
+        ORB_CHECK(stage_upload(h, f->keys, keys, (size_t)n * sizeof(orb_keypoint), st));
+        ORB_CHECK(stage_upload(h, f->desc, desc, (size_t)n * 32, st));
         int *counts, *cursor;
         ORB_CHECK(grid_workspace(h, f, &counts, &cursor, st));
         if (n > 0) grid_count_kernel<<<ceil_div(n, 256), 256, 0, st>>>(f->dev(), h->ws0.as<int>(), counts);
