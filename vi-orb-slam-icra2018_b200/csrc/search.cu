@@ -1721,12 +1721,12 @@ int orbm_search_by_projection_points(orbm_handle h, orbm_frame f, const float* s
     for (int i = 0; i < n; ++i) match[i] = -1;
     if (nq == 0 || n == 0) return ORB_OK;
     cudaStream_t st = h->stream;
-    ORB_CHECK(upload(h->in0, queries, (size_t)nq * sizeof(orbm_point_query), st));
-    ORB_CHECK(upload(h->in1, qdesc, (size_t)nq * 32, st));
-    ORB_CHECK(upload(h->in2, sf, (size_t)nlevels * 4, st));
-    if (uRight) ORB_CHECK(upload(h->in3, uRight, (size_t)n * 4, st));
+    ORB_CHECK(stage_upload(h, h->in0, queries, (size_t)nq * sizeof(orbm_point_query), st));
+    ORB_CHECK(stage_upload(h, h->in1, qdesc, (size_t)nq * 32, st));
+    ORB_CHECK(stage_upload(h, h->in2, sf, (size_t)nlevels * 4, st));
+    if (uRight) ORB_CHECK(stage_upload(h, h->in3, uRight, (size_t)n * 4, st));
     ORB_CHECK(h->in4.reserve((size_t)n + 16));
-    if (occupied) ORB_CUDA(cudaMemcpyAsync(h->in4.p, occupied, (size_t)n, cudaMemcpyHostToDevice, st));
+    if (occupied) ORB_CHECK(stage_upload(h, h->in4, occupied, (size_t)n, st));
     else ORB_CUDA(cudaMemsetAsync(h->in4.p, 0, (size_t)n, st));
     ORB_CHECK(h->ws0.reserve((size_t)nq * sizeof(AreaQuery)));
     const FrameDev d = f->dev();
@@ -1743,10 +1743,9 @@ int orbm_search_by_projection_points(orbm_handle h, orbm_frame f, const float* s
                                                        h->out3.as<int>());
     h->launches += 1;
     ORB_CUDA(cudaGetLastError());
-    ORB_CUDA(cudaMemcpyAsync(match, h->out0.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-    ORB_CUDA(cudaMemcpyAsync(nmatches, h->out3.p, 4, cudaMemcpyDeviceToHost, st));
-    ORB_CUDA(cudaStreamSynchronize(st));
-    return ORB_OK;
+    ORB_CHECK(stage_download(h, match, h->out0.p, (size_t)n * 4, st));
+    ORB_CHECK(stage_download(h, nmatches, h->out3.p, 4, st));
+    return stage_finish(h, st);
 }
 
 int orbm_search_for_triangulation(orbm_handle h, orbm_frame k1, orbm_frame k2, int nNodes1, const int* nodeId1,
@@ -1773,7 +1772,7 @@ int orbm_search_for_triangulation(orbm_handle h, orbm_frame k1, orbm_frame k2, i
     auto putInts = [&](const int* p, int n) { size_t o = ints.size(); ints.insert(ints.end(), p, p + n); return o; };
     const size_t oId1 = putInts(nodeId1, nNodes1), oS1 = putInts(start1, nNodes1 + 1), oI1 = putInts(idx1, e1);
     const size_t oId2 = putInts(nodeId2, nNodes2), oS2 = putInts(start2, nNodes2 + 1), oI2 = putInts(idx2, e2);
-    ORB_CHECK(upload(h->in0, ints.data(), ints.size() * 4, st));
+    ORB_CHECK(stage_upload(h, h->in0, ints.data(), ints.size() * 4, st));
     std::vector<float> fl;
     fl.insert(fl.end(), sf2, sf2 + nlevels);
     fl.insert(fl.end(), sigma2, sigma2 + nlevels);
@@ -1781,9 +1780,9 @@ int orbm_search_for_triangulation(orbm_handle h, orbm_frame k1, orbm_frame k2, i
     if (uR1) fl.insert(fl.end(), uR1, uR1 + n1);
     const size_t oU2 = fl.size();
     if (uR2) fl.insert(fl.end(), uR2, uR2 + n2);
-    ORB_CHECK(upload(h->in1, fl.data(), fl.size() * 4, st));
-    ORB_CHECK(upload(h->in2, has1, (size_t)n1, st));
-    ORB_CHECK(upload(h->in3, has2, (size_t)n2, st));
+    ORB_CHECK(stage_upload(h, h->in1, fl.data(), fl.size() * 4, st));
+    ORB_CHECK(stage_upload(h, h->in2, has1, (size_t)n1, st));
+    ORB_CHECK(stage_upload(h, h->in3, has2, (size_t)n2, st));
     ORB_CHECK(h->ws0.reserve((size_t)(e1 + 1) * 4));              // entryNode
     ORB_CHECK(h->out0.reserve((size_t)(n1 + 1) * 4));             // m12
     ORB_CHECK(h->out1.reserve((kHistoLength + 2) * 4));           // hist, nmatches
@@ -1807,10 +1806,9 @@ int orbm_search_for_triangulation(orbm_handle h, orbm_frame k1, orbm_frame k2, i
     tri_finish_kernel<<<1, 256, 0, st>>>(P.k1, P.k2, checkOri, h->out0.as<int>(), hist, hist + kHistoLength);
     h->launches += 4;
     ORB_CUDA(cudaGetLastError());
-    ORB_CUDA(cudaMemcpyAsync(matches12, h->out0.p, (size_t)n1 * 4, cudaMemcpyDeviceToHost, st));
-    ORB_CUDA(cudaMemcpyAsync(nmatches, hist + kHistoLength, 4, cudaMemcpyDeviceToHost, st));
-    ORB_CUDA(cudaStreamSynchronize(st));
-    return ORB_OK;
+    ORB_CHECK(stage_download(h, matches12, h->out0.p, (size_t)n1 * 4, st));
+    ORB_CHECK(stage_download(h, nmatches, hist + kHistoLength, 4, st));
+    return stage_finish(h, st);
 }
 
 int orbm_search_by_bow(orbm_handle h, orbm_frame k1, orbm_frame k2, int nNodes1, const int* nodeId1, const int* start1,
@@ -1838,9 +1836,9 @@ int orbm_search_by_bow(orbm_handle h, orbm_frame k1, orbm_frame k2, int nNodes1,
     auto putInts = [&](const int* p, int n) { size_t o = ints.size(); ints.insert(ints.end(), p, p + n); return o; };
     const size_t oId1 = putInts(nodeId1, nNodes1), oS1 = putInts(start1, nNodes1 + 1), oI1 = putInts(idx1, e1);
     const size_t oId2 = putInts(nodeId2, nNodes2), oS2 = putInts(start2, nNodes2 + 1), oI2 = putInts(idx2, e2);
-    ORB_CHECK(upload(h->in0, ints.data(), ints.size() * 4, st));
-    if (valid1) ORB_CHECK(upload(h->in2, valid1, (size_t)n1, st));
-    if (valid2) ORB_CHECK(upload(h->in3, valid2, (size_t)n2, st));
+    ORB_CHECK(stage_upload(h, h->in0, ints.data(), ints.size() * 4, st));
+    if (valid1) ORB_CHECK(stage_upload(h, h->in2, valid1, (size_t)n1, st));
+    if (valid2) ORB_CHECK(stage_upload(h, h->in3, valid2, (size_t)n2, st));
     ORB_CHECK(h->in5.reserve((size_t)(e1 + 1) * 4));                     // entry -> node position
     ORB_CHECK(h->ws0.reserve((size_t)e1 * sizeof(AreaQuery)));
     ORB_CHECK(h->out4.reserve((size_t)(e1 + 1) * 4));
@@ -1874,11 +1872,10 @@ int orbm_search_by_bow(orbm_handle h, orbm_frame k1, orbm_frame k2, int nNodes1,
                                                       pushA + e1 + 1, h->out3.as<int>());
     h->launches += 5;
     ORB_CUDA(cudaGetLastError());
-    ORB_CUDA(cudaMemcpyAsync(matches12, h->out0.p, (size_t)n1 * 4, cudaMemcpyDeviceToHost, st));
-    ORB_CUDA(cudaMemcpyAsync(matches21, h->out1.p, (size_t)n2 * 4, cudaMemcpyDeviceToHost, st));
-    ORB_CUDA(cudaMemcpyAsync(nmatches, h->out3.p, 4, cudaMemcpyDeviceToHost, st));
-    ORB_CUDA(cudaStreamSynchronize(st));
-    return ORB_OK;
+    ORB_CHECK(stage_download(h, matches12, h->out0.p, (size_t)n1 * 4, st));
+    ORB_CHECK(stage_download(h, matches21, h->out1.p, (size_t)n2 * 4, st));
+    ORB_CHECK(stage_download(h, nmatches, h->out3.p, 4, st));
+    return stage_finish(h, st);
 }
 
 int orbm_search_projected_best(orbm_handle h, orbm_frame kf, const orbm_best_query* queries, const uint8_t* qdesc, int nq,
@@ -1894,10 +1891,10 @@ int orbm_search_projected_best(orbm_handle h, orbm_frame kf, const orbm_best_que
         return ORB_OK;
     }
     cudaStream_t st = h->stream;
-    ORB_CHECK(upload(h->in0, queries, (size_t)nq * sizeof(orbm_best_query), st));
-    ORB_CHECK(upload(h->in1, qdesc, (size_t)nq * 32, st));
-    if (chi2Filter) ORB_CHECK(upload(h->in2, invSigma2, (size_t)nlevels * 4, st));
-    if (chi2Filter && uRight) ORB_CHECK(upload(h->in3, uRight, (size_t)n * 4, st));
+    ORB_CHECK(stage_upload(h, h->in0, queries, (size_t)nq * sizeof(orbm_best_query), st));
+    ORB_CHECK(stage_upload(h, h->in1, qdesc, (size_t)nq * 32, st));
+    if (chi2Filter) ORB_CHECK(stage_upload(h, h->in2, invSigma2, (size_t)nlevels * 4, st));
+    if (chi2Filter && uRight) ORB_CHECK(stage_upload(h, h->in3, uRight, (size_t)n * 4, st));
     ORB_CHECK(h->out0.reserve((size_t)nq * 4));
     ORB_CHECK(h->out1.reserve((size_t)nq * 4));
     projected_best_kernel<<<ceil_div(nq, 8), 256, 0, st>>>(kf->dev(), h->in0.as<orbm_best_query>(), h->in1.as<uint4>(), nq, chi2Filter,
@@ -1905,10 +1902,9 @@ int orbm_search_projected_best(orbm_handle h, orbm_frame kf, const orbm_best_que
                                                            chi2Filter ? h->in2.as<float>() : nullptr, h->out0.as<int>(), h->out1.as<int>());
     h->launches += 1;
     ORB_CUDA(cudaGetLastError());
-    ORB_CUDA(cudaMemcpyAsync(bestIdx, h->out0.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
-    ORB_CUDA(cudaMemcpyAsync(bestDist, h->out1.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
-    ORB_CUDA(cudaStreamSynchronize(st));
-    return ORB_OK;
+    ORB_CHECK(stage_download(h, bestIdx, h->out0.p, (size_t)nq * 4, st));
+    ORB_CHECK(stage_download(h, bestDist, h->out1.p, (size_t)nq * 4, st));
+    return stage_finish(h, st);
 }
 
 }  // extern "C"
