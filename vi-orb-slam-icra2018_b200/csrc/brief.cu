@@ -192,7 +192,7 @@ constexpr int BRS_PER_WARP = 8;      // consecutive keypoints of a frame per war
 
 __global__ void __launch_bounds__(BR_WARPS * 32, 4)
 brief_staged_kernel(const __grid_constant__ ExtractParams P, orb_keypoint* __restrict__ kps, unsigned char* __restrict__ desc,
-                    int* __restrict__ nOut) {
+                    int* __restrict__ nOut, int perWarp) {
     __shared__ __align__(128) unsigned char tiles[BR_WARPS * BRS_TILE_STRIDE];
     __shared__ __align__(8) unsigned long long bars[BR_WARPS];
     const int frame = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -213,7 +213,7 @@ brief_staged_kernel(const __grid_constant__ ExtractParams P, orb_keypoint* __res
     }
     const int total = min(__shfl_sync(0xffffffffu, incl, kMaxLevels - 1), P.outCapacity);
     if (blockIdx.x == 0 && tid == 0) nOut[frame] = __shfl_sync(1u, incl, 0) * 0 + total;
-    const int g0 = (blockIdx.x * BR_WARPS + warp) * BRS_PER_WARP;
+    const int g0 = (blockIdx.x * BR_WARPS + warp) * perWarp;
     if (g0 >= total) return;
     char4 pat[8];
 #pragma unroll
@@ -223,7 +223,7 @@ brief_staged_kernel(const __grid_constant__ ExtractParams P, orb_keypoint* __res
     const int oriV0 = lane / 9 - kHalfPatch, oriW0 = lane % 9;
     const unsigned char* pyrFrame = P.pyr + (size_t)frame * P.pyrFrameBytes;
     const SelKey* selFrame = P.sel + (size_t)frame * P.selPerFrame;
-    const int gEnd = min(g0 + BRS_PER_WARP, total);
+    const int gEnd = min(g0 + perWarp, total);
     unsigned int parity = 0;
     for (int g = g0; g < gEnd; ++g) {
         const unsigned int below = __ballot_sync(0xffffffffu, incl <= g);     // levels wholly before keypoint g
@@ -348,10 +348,13 @@ int brief_encode_maps(const ExtractParams& P, int arenaFrames, void* hostMaps) {
 int launch_brief(const ExtractParams& P, int maxKeypoints, orb_keypoint* dKps, unsigned char* dDesc, int* dCount,
                  cudaStream_t st, int* launches) {
     dim3 grid(ceil_div(maxKeypoints > 0 ? maxKeypoints : 1, BR_WARPS), P.nFrames);
-    const dim3 gridStaged(ceil_div(maxKeypoints > 0 ? maxKeypoints : 1, BR_WARPS * BRS_PER_WARP), P.nFrames);
+    // batches: 8 consecutive keypoints per warp (pattern, level scan and tables loaded once); small calls: one per warp, so
+    // that a single frame's ~1000 keypoints spread over the whole GPU instead of running eight deep
+    const int perWarp = P.nFrames >= P.pyBulkMinFrames ? BRS_PER_WARP : 1;
+    const dim3 gridStaged(ceil_div(maxKeypoints > 0 ? maxKeypoints : 1, BR_WARPS * perWarp), P.nFrames);
     static const bool noStage = getenv("ORBB_BRIEF_DIRECT") != nullptr;      // A/B aid: the direct-gather kernel
     if (P.brMaps && !noStage && P.nLevels <= kMaxLevels) {
-        brief_staged_kernel<<<gridStaged, BR_WARPS * 32, 0, st>>>(P, dKps, dDesc, dCount);
+        brief_staged_kernel<<<gridStaged, BR_WARPS * 32, 0, st>>>(P, dKps, dDesc, dCount, perWarp);
         ++*launches;
         ORB_CUDA(cudaGetLastError());
         return ORB_OK;
