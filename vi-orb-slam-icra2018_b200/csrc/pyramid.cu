@@ -466,7 +466,7 @@ int pyramid_band_plan(const LevelGeom& S, const LevelGeom& D, const int* yofs, s
 // on a zeroed counter with a release fence, spin with acquire loads).  Level l's items (the work items of
 // pyramid_level0_kernel / pyramid_resize2_kernel, frame-major) are dealt over the whole grid.  Data written earlier in
 // the same launch is read with ld.global.cg (never through the non-coherent path).
-constexpr int PYF_ROWS = 4;      // rows per work item of the fused kernel: latency matters here, not instruction count
+constexpr int PYF_ROWS = 2;      // rows per work item of the fused kernel: latency matters here, not instruction count
 struct PyFusedLevel {
     long long srcPix0, dstOff;   // source pixel (0,0) / destination buffer inside a frame's pyramid block
     int dstPitch, rowsTotal, groups, nItems;
