@@ -13,6 +13,7 @@
 // mvScaleFactor[level] only after the descriptor is taken, as the reference does.
 #include <cuda.h>
 
+#include <algorithm>
 #include <cfloat>
 #include <cstdlib>
 #include <cstring>
@@ -350,7 +351,8 @@ int launch_brief(const ExtractParams& P, int maxKeypoints, orb_keypoint* dKps, u
     dim3 grid(ceil_div(maxKeypoints > 0 ? maxKeypoints : 1, BR_WARPS), P.nFrames);
     // batches: 8 consecutive keypoints per warp (pattern, level scan and tables loaded once); small calls: one per warp, so
     // that a single frame's ~1000 keypoints spread over the whole GPU instead of running eight deep
-    const int perWarp = P.nFrames >= P.pyBulkMinFrames ? BRS_PER_WARP : 1;
+    static const int batchPerWarp = getenv("ORBB_BRIEF_PERWARP") ? std::max(1, atoi(getenv("ORBB_BRIEF_PERWARP"))) : BRS_PER_WARP;   // tuning aid
+    const int perWarp = P.nFrames >= P.pyBulkMinFrames ? batchPerWarp : 1;
     const dim3 gridStaged(ceil_div(maxKeypoints > 0 ? maxKeypoints : 1, BR_WARPS * perWarp), P.nFrames);
     static const bool noStage = getenv("ORBB_BRIEF_DIRECT") != nullptr;      // A/B aid: the direct-gather kernel
     if (P.brMaps && !noStage && P.nLevels <= kMaxLevels) {
