@@ -14,7 +14,9 @@
 //   * vertical pass: the sums of two consecutive input rows are packed into one 16x2 register per pixel, so a 7-tap
 //     column is four IDP.2A (16-bit sums x 8-bit taps) over the last four row pairs; the accumulator starts at 2^15 so
 //     the rounding is free, and the four result bytes are picked with PRMT.
-// No shared memory, no barriers; all levels in one launch.
+// blur_kernel (small calls): no shared memory, no barriers; all levels in one launch.
+// blur_staged_kernel (batches, round 2): the same arithmetic with a band's input rows staged in shared memory by one
+// cp.async.bulk, one launch per level -- see the comment at the kernel.
 #include <algorithm>
 #include <cstdlib>
 

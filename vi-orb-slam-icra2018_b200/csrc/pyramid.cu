@@ -21,6 +21,14 @@
 //   * the vertical pass is two multiply-high per pixel: hi32((T & ~15) * (b << 12)) == (b * (T >> 4)) >> 16.
 // Reading S[x+1] / row y+1 one past the level is harmless: the table's coefficient there is 0 and the source level
 // has its own frame.
+//
+// Kernels in this file (round 2), all with the arithmetic above:
+//   pyramid_level0_kernel / _wide_kernel  level 0 = copy + frame (wide: 128-bit interior copies for 16-byte aligned rows)
+//   pyramid_resize3_kernel                batches: a band of 16 destination rows per CTA, its contiguous source rows staged
+//                                         in shared memory by one cp.async.bulk (mbarrier, persistent CTAs)
+//   pyramid_fused_kernel                  small calls: all levels in ONE launch, grid-wide barrier between levels
+//   pyramid_resize2_kernel                record-driven, straight from global memory (fallback)
+//   pyramid_resize_kernel                 table-driven, any scale factor (fallback)
 #include <algorithm>
 #include <cstdlib>
 #include <vector>
