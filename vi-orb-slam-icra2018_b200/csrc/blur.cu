@@ -36,14 +36,24 @@ constexpr unsigned int TAP_V_O0 = 0x30221200u;   // odd output row:             
 constexpr unsigned int TAP_V_O1 = 0x12223038u;   //                                   (56,48) (34,18)
 
 // Horizontal sums of one input row for four adjacent pixels from the three aligned words that hold bytes x-4 .. x+7:
-// pixel k needs bytes k+1 .. k+7 of that window.  Instead of shifting the window to the pixel (6 funnel shifts) the TAPS
-// are shifted: per pixel two or three dot products of the unshifted words with tap vectors that are zero outside the
-// pixel's seven bytes (10 IDP.4A, no shifts; integer sums, so the result is the same).
+// pixel k needs bytes k+1 .. k+7 of that window.  The kernel's busiest pipe is the FMA-heavy one (IDP issues there every
+// other clock), so the row costs as few dot products as possible: pixels 0 and 3 take the unshifted words with shifted
+// TAP vectors (zero outside the pixel's seven bytes), pixels 1 and 2 share ONE window shifted by two bytes (two funnel
+// shifts on the ALU pipe) with the two tap alignments -- 8 IDP.4A + 2 SHF per 4 pixels (integer sums: same result as
+// any other split; 10 IDP.4A without shifts was 2.70 ms per 4096 frames, 6 shifts + 8 IDP.4A more instructions).
 __device__ __forceinline__ void blur_hrow(unsigned int w0, unsigned int w1, unsigned int w2, unsigned int (&h)[4]) {
+#ifdef BL_HROW10
     h[0] = __dp4a(w0, 0x30221200u, __dp4a(w1, 0x12223038u, 0u));                              // bytes 1..3 | 4..7
     h[1] = __dp4a(w0, 0x22120000u, __dp4a(w1, 0x22303830u, __dp4a(w2, 0x00000012u, 0u)));     // bytes 2..3 | 4..7 | 8
     h[2] = __dp4a(w0, 0x12000000u, __dp4a(w1, 0x30383022u, __dp4a(w2, 0x00001222u, 0u)));     // byte 3 | 4..7 | 8..9
     h[3] = __dp4a(w1, TAP_H_LO, __dp4a(w2, TAP_H_HI, 0u));                                    // bytes 4..7 | 8..10
+#else
+    const unsigned int X = __funnelshift_r(w0, w1, 16), Y = __funnelshift_r(w1, w2, 16);      // bytes 2..5, 6..9
+    h[0] = __dp4a(w0, 0x30221200u, __dp4a(w1, 0x12223038u, 0u));                              // bytes 1..3 | 4..7
+    h[1] = __dp4a(X, TAP_H_LO, __dp4a(Y, TAP_H_HI, 0u));                                      // bytes 2..5 | 6..8
+    h[2] = __dp4a(X, 0x30221200u, __dp4a(Y, 0x12223038u, 0u));                                // bytes 3..5 | 6..9
+    h[3] = __dp4a(w1, TAP_H_LO, __dp4a(w2, TAP_H_HI, 0u));                                    // bytes 4..7 | 8..10
+#endif
 }
 
 int blur_cta_count(int w, int h) { return ceil_div(((w + 3) / 4) * ceil_div(h, BL_ROWS), BL_THREADS); }
@@ -70,12 +80,7 @@ __global__ void __launch_bounds__(BL_THREADS) blur_kernel(const __grid_constant_
         w[0] = __ldg(p); w[1] = __ldg(p + 1); w[2] = __ldg(p + 2);
     };
     // horizontal sums of one input row for the item's four pixels
-    auto hrow = [&](const unsigned int (&w)[3], unsigned int (&h)[4]) {
-        h[0] = __dp4a(__funnelshift_r(w[0], w[1], 8), TAP_H_LO, __dp4a(__funnelshift_r(w[1], w[2], 8), TAP_H_HI, 0u));
-        h[1] = __dp4a(__funnelshift_r(w[0], w[1], 16), TAP_H_LO, __dp4a(__funnelshift_r(w[1], w[2], 16), TAP_H_HI, 0u));
-        h[2] = __dp4a(__funnelshift_r(w[0], w[1], 24), TAP_H_LO, __dp4a(__funnelshift_r(w[1], w[2], 24), TAP_H_HI, 0u));
-        h[3] = __dp4a(w[1], TAP_H_LO, __dp4a(w[2], TAP_H_HI, 0u));
-    };
+    auto hrow = [&](const unsigned int (&w)[3], unsigned int (&h)[4]) { blur_hrow(w[0], w[1], w[2], h); };
     // row pair = input rows 2i, 2i+1 packed per pixel (even row in the low half)
     auto make_pair = [&](const unsigned int (&we)[3], const unsigned int (&wo)[3], unsigned int (&pr)[4]) {
         unsigned int he[4], ho[4];

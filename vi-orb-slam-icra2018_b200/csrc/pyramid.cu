@@ -18,7 +18,10 @@
 //     four IDP.2A (16-bit coefficient pair x two bytes) give the four horizontal sums;
 //   * consecutive output rows usually step one source row (scale 1.2: five times out of six), so the lower row's sums
 //     are kept for the next output row;
-//   * the vertical pass is two multiply-high per pixel: hi32((T & ~15) * (b << 12)) == (b * (T >> 4)) >> 16.
+//   * the vertical pass (b0 * (T0 >> 4) >> 16) + (b1 * (T1 >> 4) >> 16) + 2 uses 32-bit products (T >> 4 < 2^15, b <= 2^11):
+//     two IMAD, one PRMT that picks the two high halves, one IDP.2A that adds them and the rounding term.  (Until late in
+//     round 2 this was two multiply-high per pixel; IMAD.HI turned out to be a quarter-rate instruction that made the
+//     FMA-heavy pipe the kernel's busiest one: 3.95 -> 3.71 ms per 4096 frames.)
 // Reading S[x+1] / row y+1 one past the level is harmless: the table's coefficient there is 0 and the source level
 // has its own frame.
 //
@@ -38,6 +41,11 @@
 namespace orbb {
 
 constexpr int PY_ROWS = 16;       // output rows per work item
+
+// one output pixel of the vertical pass from the two source rows' horizontal sums (already >> 4) and coefficients
+__device__ __forceinline__ unsigned int py_vsum(unsigned int t0, unsigned int b0, unsigned int t1, unsigned int b1) {
+    return __dp2a_lo(__byte_perm(t0 * b0, t1 * b1, 0x7632), 0x0101u, 2u);
+}
 constexpr int PY_THREADS = 128;
 
 __device__ __forceinline__ int reflect101(int i, int n) {
@@ -181,10 +189,10 @@ pyramid_resize_kernel(unsigned char* __restrict__ pyr, long long pyrFrameBytes, 
             const unsigned int w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2);
             const unsigned int X = __funnelshift_r(w0, w1, shift), Y = __funnelshift_r(w1, w2, shift);
             const unsigned int v01 = __byte_perm(X, Y, sel01), v23 = __byte_perm(X, Y, sel23);
-            t[0] = __dp2a_lo(cf[0], v01, 0u) & ~15u;          // S[x0]*a0 + S[x0+1]*a1
-            t[1] = __dp2a_hi(cf[1], v01, 0u) & ~15u;
-            t[2] = __dp2a_lo(cf[2], v23, 0u) & ~15u;
-            t[3] = __dp2a_hi(cf[3], v23, 0u) & ~15u;
+            t[0] = __dp2a_lo(cf[0], v01, 0u) >> 4;          // S[x0]*a0 + S[x0+1]*a1
+            t[1] = __dp2a_hi(cf[1], v01, 0u) >> 4;
+            t[2] = __dp2a_lo(cf[2], v23, 0u) >> 4;
+            t[3] = __dp2a_hi(cf[3], v23, 0u) >> 4;
         };
         int keptRow = -0x40000000;
         unsigned int kept[4] = {0, 0, 0, 0};
@@ -195,7 +203,7 @@ pyramid_resize_kernel(unsigned char* __restrict__ pyr, long long pyrFrameBytes, 
             const int dy = reflect101(by - kEdge, dh);
             const int sy0 = __ldg(yofs + dy);
             const short2 b = __ldg(ycoef + dy);
-            const unsigned int B0 = (unsigned int)b.x << 12, B1 = (unsigned int)b.y << 12;
+            const unsigned int B0 = (unsigned int)b.x, B1 = (unsigned int)b.y;
             const unsigned char* r0 = src0 + (size_t)sy0 * srcPitch;
             unsigned int t0[4], t1[4];
             if (sy0 == keptRow) {
@@ -210,7 +218,7 @@ pyramid_resize_kernel(unsigned char* __restrict__ pyr, long long pyrFrameBytes, 
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 kept[k] = t1[k];
-                s[k] = __umulhi(t0[k], B0) + __umulhi(t1[k], B1) + 2u;    // <= 1023
+                s[k] = py_vsum(t0[k], B0, t1[k], B1);    // <= 1023
             }
             const unsigned int q01 = __byte_perm(s[0], s[1], 0x5410) >> 2, q23 = __byte_perm(s[2], s[3], 0x5410) >> 2;
             *reinterpret_cast<unsigned int*>(dst + (size_t)by * dstPitch) = __byte_perm(q01, q23, 0x6420);
@@ -246,7 +254,7 @@ pyramid_resize_kernel(unsigned char* __restrict__ pyr, long long pyrFrameBytes, 
 // two 128-bit loads instead of table look-ups, reflections and 64-bit multiplies per row), and the only 64-bit address
 // arithmetic left per row is one add per source row and one for the destination.
 //   colTab[2g], colTab[2g+1] : {window base (bytes from the source pixel (0,0), multiple of 4), shift, sel01, sel23}, {cf[0..3]}
-//   rowTab[by]               : {byte offset of source row sy0, of row sy0+1, b0 << 12, b1 << 12}   (by = padded row)
+//   rowTab[by]               : {byte offset of source row sy0, of row sy0+1, b0, b1}   (by = padded row)
 __global__ void __launch_bounds__(PY_THREADS)
 pyramid_resize2_kernel(unsigned char* __restrict__ pyr, long long pyrFrameBytes, long long srcPix0, long long dstOff, int dstPitch,
                        int rowsTotal, int groups, int nItems, const uint4* __restrict__ colTab, const uint4* __restrict__ rowTab) {
@@ -266,10 +274,10 @@ pyramid_resize2_kernel(unsigned char* __restrict__ pyr, long long pyrFrameBytes,
         const unsigned int w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2);
         const unsigned int X = __funnelshift_r(w0, w1, shift), Y = __funnelshift_r(w1, w2, shift);
         const unsigned int v01 = __byte_perm(X, Y, sel01), v23 = __byte_perm(X, Y, sel23);
-        t[0] = __dp2a_lo(cb.x, v01, 0u) & ~15u;
-        t[1] = __dp2a_hi(cb.y, v01, 0u) & ~15u;
-        t[2] = __dp2a_lo(cb.z, v23, 0u) & ~15u;
-        t[3] = __dp2a_hi(cb.w, v23, 0u) & ~15u;
+        t[0] = __dp2a_lo(cb.x, v01, 0u) >> 4;
+        t[1] = __dp2a_hi(cb.y, v01, 0u) >> 4;
+        t[2] = __dp2a_lo(cb.z, v23, 0u) >> 4;
+        t[3] = __dp2a_hi(cb.w, v23, 0u) >> 4;
     };
     unsigned int keptOff = 0xffffffffu;
     unsigned int kept[4] = {0, 0, 0, 0};
@@ -289,7 +297,7 @@ pyramid_resize2_kernel(unsigned char* __restrict__ pyr, long long pyrFrameBytes,
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             kept[k] = t1[k];
-            s[k] = __umulhi(t0[k], rr.z) + __umulhi(t1[k], rr.w) + 2u;    // <= 1023
+            s[k] = py_vsum(t0[k], rr.z, t1[k], rr.w);    // <= 1023
         }
         const unsigned int q01 = __byte_perm(s[0], s[1], 0x5410) >> 2, q23 = __byte_perm(s[2], s[3], 0x5410) >> 2;
         *reinterpret_cast<unsigned int*>(dst) = __byte_perm(q01, q23, 0x6420);
@@ -322,7 +330,7 @@ bool pyramid_level_plan(const LevelGeom& S, const LevelGeom& D, const int* xofs,
     for (int by = 0; by < D.h + 2 * kEdge; ++by) {
         const int dy = reflect(by - kEdge, D.h);
         const unsigned int off0 = (unsigned int)yofs[dy] * (unsigned int)S.pitch;
-        row.push_back(make_uint4(off0, off0 + (unsigned int)S.pitch, (unsigned int)ycoef[dy].x << 12, (unsigned int)ycoef[dy].y << 12));
+        row.push_back(make_uint4(off0, off0 + (unsigned int)S.pitch, (unsigned int)ycoef[dy].x, (unsigned int)ycoef[dy].y));
     }
     row.push_back(make_uint4(0, 0, 0, 0));     // spare entry: the staged kernel reads one record ahead
     return true;
@@ -380,10 +388,10 @@ pyramid_resize3_kernel(unsigned char* __restrict__ pyr, long long pyrFrameBytes,
         asm volatile("ld.shared.u32 %0, [%1+8];" : "=r"(w2) : "r"(addr));
         const unsigned int X = __funnelshift_r(w0, w1, shift), Y = __funnelshift_r(w1, w2, shift);
         const unsigned int v01 = __byte_perm(X, Y, sel01), v23 = __byte_perm(X, Y, sel23);
-        t[0] = __dp2a_lo(cb.x, v01, 0u) & ~15u;
-        t[1] = __dp2a_hi(cb.y, v01, 0u) & ~15u;
-        t[2] = __dp2a_lo(cb.z, v23, 0u) & ~15u;
-        t[3] = __dp2a_hi(cb.w, v23, 0u) & ~15u;
+        t[0] = __dp2a_lo(cb.x, v01, 0u) >> 4;
+        t[1] = __dp2a_hi(cb.y, v01, 0u) >> 4;
+        t[2] = __dp2a_lo(cb.z, v23, 0u) >> 4;
+        t[3] = __dp2a_hi(cb.w, v23, 0u) >> 4;
     };
     // nBuf == 2: the next band's copy is in flight while this one is computed; nBuf == 1: one buffer, twice the CTAs per SM
     int tile = blockIdx.x;
@@ -438,7 +446,7 @@ pyramid_resize3_kernel(unsigned char* __restrict__ pyr, long long pyrFrameBytes,
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     kept[k] = t1[k];
-                    s[k] = __umulhi(t0[k], rr.z) + __umulhi(t1[k], rr.w) + 2u;    // <= 1023
+                    s[k] = py_vsum(t0[k], rr.z, t1[k], rr.w);    // <= 1023
                 }
                 const unsigned int q01 = __byte_perm(s[0], s[1], 0x5410) >> 2, q23 = __byte_perm(s[2], s[3], 0x5410) >> 2;
                 *reinterpret_cast<unsigned int*>(dst) = __byte_perm(q01, q23, 0x6420);
@@ -557,10 +565,10 @@ pyramid_fused_kernel(const __grid_constant__ PyFusedArgs A) {
                 const unsigned int w0 = __ldcg(q), w1 = __ldcg(q + 1), w2 = __ldcg(q + 2);
                 const unsigned int X = __funnelshift_r(w0, w1, shift), Y = __funnelshift_r(w1, w2, shift);
                 const unsigned int v01 = __byte_perm(X, Y, sel01), v23 = __byte_perm(X, Y, sel23);
-                t[0] = __dp2a_lo(cb.x, v01, 0u) & ~15u;
-                t[1] = __dp2a_hi(cb.y, v01, 0u) & ~15u;
-                t[2] = __dp2a_lo(cb.z, v23, 0u) & ~15u;
-                t[3] = __dp2a_hi(cb.w, v23, 0u) & ~15u;
+                t[0] = __dp2a_lo(cb.x, v01, 0u) >> 4;
+                t[1] = __dp2a_hi(cb.y, v01, 0u) >> 4;
+                t[2] = __dp2a_lo(cb.z, v23, 0u) >> 4;
+                t[3] = __dp2a_hi(cb.w, v23, 0u) >> 4;
             };
             unsigned int keptOff = 0xffffffffu;
             unsigned int kept[4] = {0, 0, 0, 0};
@@ -580,7 +588,7 @@ pyramid_fused_kernel(const __grid_constant__ PyFusedArgs A) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     kept[k] = t1[k];
-                    sv[k] = __umulhi(t0[k], rr.z) + __umulhi(t1[k], rr.w) + 2u;
+                    sv[k] = py_vsum(t0[k], rr.z, t1[k], rr.w);
                 }
                 const unsigned int q01 = __byte_perm(sv[0], sv[1], 0x5410) >> 2, q23 = __byte_perm(sv[2], sv[3], 0x5410) >> 2;
                 *reinterpret_cast<unsigned int*>(dst) = __byte_perm(q01, q23, 0x6420);
