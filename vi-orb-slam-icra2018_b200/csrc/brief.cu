@@ -287,15 +287,30 @@ brief_staged_kernel(const __grid_constant__ ExtractParams P, orb_keypoint* __res
             "r"(parity)
             : "memory");
         parity ^= 1u;
+#ifdef BRS_F2I
         const unsigned int center = tileAddr + 18 * BRS_TILE_W + (unsigned int)(x - x0a);
+#else
+        // cvRound without the conversion pipe (F2I issues on the XU pipe, the kernel's busiest): for |v| < 2^22 the float
+        // v + 1.5 * 2^23 has its integer value, rounded to nearest-even like lrintf, in its low mantissa bits; the bias
+        // 0x4B400000 of both coordinates is taken out of the tile address once (32-bit wrap-around arithmetic)
+        const float kRound = 12582912.f;
+        const unsigned int center = tileAddr + 18 * BRS_TILE_W + (unsigned int)(x - x0a) - 0x4B400000u * (unsigned int)(BRS_TILE_W + 1);
+#endif
         unsigned int val = 0;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const float px = (float)pat[j].x, py = (float)pat[j].y, pz = (float)pat[j].z, pw = (float)pat[j].w;
+#ifdef BRS_F2I
             const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(px, b), __fmul_rn(py, a)));
             const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(px, a), __fmul_rn(py, b)));
             const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(pz, b), __fmul_rn(pw, a)));
             const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(pz, a), __fmul_rn(pw, b)));
+#else
+            const unsigned int r0 = __float_as_uint(__fadd_rn(__fadd_rn(__fmul_rn(px, b), __fmul_rn(py, a)), kRound));
+            const unsigned int c0 = __float_as_uint(__fadd_rn(__fsub_rn(__fmul_rn(px, a), __fmul_rn(py, b)), kRound));
+            const unsigned int r1 = __float_as_uint(__fadd_rn(__fadd_rn(__fmul_rn(pz, b), __fmul_rn(pw, a)), kRound));
+            const unsigned int c1 = __float_as_uint(__fadd_rn(__fsub_rn(__fmul_rn(pz, a), __fmul_rn(pw, b)), kRound));
+#endif
             unsigned int t0, t1;
             asm volatile("ld.shared.u8 %0, [%1];" : "=r"(t0) : "r"(center + (unsigned int)(r0 * BRS_TILE_W + c0)));
             asm volatile("ld.shared.u8 %0, [%1];" : "=r"(t1) : "r"(center + (unsigned int)(r1 * BRS_TILE_W + c1)));
