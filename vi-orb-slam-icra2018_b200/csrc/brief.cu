@@ -226,12 +226,21 @@ brief_staged_kernel(const __grid_constant__ ExtractParams P, orb_keypoint* __res
     const SelKey* selFrame = P.sel + (size_t)frame * P.selPerFrame;
     const int gEnd = min(g0 + perWarp, total);
     unsigned int parity = 0;
-    for (int g = g0; g < gEnd; ++g) {
+    // the record of keypoint g + 1 is requested at the end of keypoint g, before its descriptor byte and keypoint go out
+    // (3.04 -> 2.92 ms per 4096 frames; requested earlier -- at the top of g: 3.19 ms with 60 bytes of spills, before the
+    // tile wait: 2.98 ms)
+    auto locate = [&](int g, int& level) -> const SelKey* {
         const unsigned int below = __ballot_sync(0xffffffffu, incl <= g);     // levels wholly before keypoint g
-        const int level = __popc(below & ((1u << kMaxLevels) - 1u));
+        level = __popc(below & ((1u << kMaxLevels) - 1u));
         const int idx = g - (__shfl_sync(0xffffffffu, incl, level) - __shfl_sync(0xffffffffu, cnt, level));
+        return selFrame + P.lv[level].selBase + idx;
+    };
+    int level, levelNext;
+    SelKey k, kNext = *locate(g0, levelNext);
+    for (int g = g0; g < gEnd; ++g) {
+        k = kNext;
+        level = levelNext;
         const LevelGeom& L = P.lv[level];
-        const SelKey k = selFrame[L.selBase + idx];
         const int x = (int)k.x, y = (int)k.y;
         const int x0a = (x - 18) & ~15;
         if (lane == 0) {
@@ -317,6 +326,7 @@ brief_staged_kernel(const __grid_constant__ ExtractParams P, orb_keypoint* __res
             val |= (unsigned int)(t0 < t1) << j;
         }
         __syncwarp();      // every lane has read its samples: the tile may be refilled
+        if (g + 1 < gEnd) kNext = *locate(g + 1, levelNext);
         desc[((size_t)frame * P.outCapacity + g) * 32 + lane] = (unsigned char)val;
         if (lane == 0) {
             orb_keypoint o;
