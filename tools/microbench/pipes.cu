@@ -66,6 +66,18 @@ __device__ __forceinline__ unsigned h2add(unsigned a, unsigned b) {
 #define OP_VH(a, b, c) a = __vmaxu2(a, b); a = h2add(a, c);
 #define OP_PRMTI(a, b, c) a = __byte_perm(a, b, 0x5140); a = a * b + c;
 #define OP_LOPI(a, b, c) a = (a & b) ^ c; a = a * b + c;
+#define OP_IMADHI(a, b, c) a = __umulhi(a, b) ^ c;
+#define OP_IDP4(a, b, c) a = __dp4a(a, b, c);
+#define OP_IDP2(a, b, c) a = __dp2a_lo(a, b, c);
+#define OP_F2I(a, b, c) a = (unsigned)__float2int_rn(__uint_as_float(a)) + b;
+#define OP_I2F(a, b, c) a = __float_as_uint((float)(int)a) ^ b;
+#define OP_FFMA(a, b, c) a = __float_as_uint(fmaf(__uint_as_float(a), __uint_as_float(b), __uint_as_float(c)));
+KERNEL(k_imadhi, OP_IMADHI)
+KERNEL(k_idp4, OP_IDP4)
+KERNEL(k_idp2, OP_IDP2)
+KERNEL(k_f2i, OP_F2I)
+KERNEL(k_i2f, OP_I2F)
+KERNEL(k_ffma, OP_FFMA)
 KERNEL(k_r31, OP_R31)
 KERNEL(k_r21, OP_R21)
 KERNEL(k_r12, OP_R12)
@@ -148,6 +160,8 @@ int main() {
         {"VIMNMX + PRMT", k_mix_vp, 64}, {"HMNMX2 + IMAD", k_mix_hi, 64}, {"HMNMX2 + HADD2", k_mix_ha, 64},
         {"LDS.32 (conflict-free)", k_lds, 32}, {"SHFL", k_shfl, 32},
         {"3 VIMNMX : 1 IMAD", k_r31, 128}, {"2 VIMNMX : 1 IMAD", k_r21, 96}, {"1 VIMNMX : 2 IMAD", k_r12, 96}, {"1 VIMNMX : 3 IMAD", k_r13, 128},
+        {"IMAD.HI + LOP3", k_imadhi, 64}, {"IDP.4A", k_idp4, 32}, {"IDP.2A", k_idp2, 32}, {"F2I + IADD", k_f2i, 64},
+        {"I2F + LOP3", k_i2f, 64}, {"FFMA", k_ffma, 32},
         {"FADD", k_fadd, 32}, {"VIMNMX + FADD", k_vf, 64}, {"VIMNMX + HADD2", k_vh, 64}, {"PRMT + IMAD", k_prmti, 64}, {"LOP3 + IMAD", k_lopi, 64},
     };
     for (auto& t : tests) {
