@@ -20,8 +20,8 @@
 //     are kept for the next output row;
 //   * the vertical pass (b0 * (T0 >> 4) >> 16) + (b1 * (T1 >> 4) >> 16) + 2 uses 32-bit products (T >> 4 < 2^15, b <= 2^11):
 //     two IMAD, one PRMT that picks the two high halves, one IDP.2A that adds them and the rounding term.  (Until late in
-//     round 2 this was two multiply-high per pixel; IMAD.HI turned out to be a quarter-rate instruction that made the
-//     FMA-heavy pipe the kernel's busiest one: 3.95 -> 3.71 ms per 4096 frames.)
+//     round 2 this was two multiply-high per pixel; IMAD.HI issues at about half the rate of IMAD and made the
+//     FMA-heavy pipe the kernel's busiest one: 3.95 -> 3.49 ms per 4096 frames.)
 // Reading S[x+1] / row y+1 one past the level is harmless: the table's coefficient there is 0 and the source level
 // has its own frame.
 //
