@@ -27,6 +27,8 @@
 //
 // Kernels in this file (round 2), all with the arithmetic above:
 //   pyramid_level0_kernel / _wide_kernel  level 0 = copy + frame (wide: 128-bit interior copies for 16-byte aligned rows)
+//   pyramid_level0_bulk_kernel            level 0 of a batch with 16-byte aligned rows: bulk copies in, frame filled in shared
+//                                         memory, one bulk store per band of 16 padded rows
 //   pyramid_resize3_kernel                batches: a band of 16 destination rows per CTA, its contiguous source rows staged
 //                                         in shared memory by one cp.async.bulk (mbarrier, persistent CTAs)
 //   pyramid_fused_kernel                  small calls: all levels in ONE launch, grid-wide barrier between levels
@@ -345,6 +347,75 @@ bool pyramid_level_plan(const LevelGeom& S, const LevelGeom& D, const int* xofs,
 // this one is computed (two buffers, persistent CTAs striding over (frame, band)).  The arithmetic reads shared memory.
 //   bandTab[b] : {byte offset of the band's first source row inside the source level buffer, bytes, offset(sy0 = first), -}
 __device__ __forceinline__ unsigned int py_smem_u32(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
+
+// Level 0 for BATCHES of images with 16-byte aligned rows (EuRoC: 752): the copy engine moves the pixels.  A CTA owns a band
+// of 16 padded rows: one cp.async.bulk per row brings the (reflected) source row to its place inside the padded row in
+// shared memory, the threads fill the 2 x 32 frame bytes of every row from there, and since the padded rows of a level
+// are contiguous in the arena ONE bulk store writes the whole band back.  No pixel passes through a register; persistent
+// CTAs stride over (frame, band), several per SM so that one CTA's store drains under the others' loads.
+constexpr int PY0_THREADS = 64;
+__global__ void __launch_bounds__(PY0_THREADS)
+pyramid_level0_bulk_kernel(const unsigned char* __restrict__ images, int w, int h, int stride, size_t frameStride,
+                           unsigned char* __restrict__ pyr, long long pyrFrameBytes, long long pyrOff, int pitch, int nBands, int nTiles) {
+    extern __shared__ __align__(128) unsigned char l0sm[];
+    const int tid = threadIdx.x;
+    const unsigned int bar = py_smem_u32(l0sm), buf = bar + 128;
+    unsigned char* rowsSm = l0sm + 128;
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int rowsTotal = h + 2 * kEdge, nb = (pitch - w) >> 2;      // frame groups of 4 bytes per row: 8 left, the rest right
+    unsigned int parity = 0;
+    for (int tile = blockIdx.x; tile < nTiles; tile += gridDim.x) {
+        const int frame = tile / nBands, band = tile - frame * nBands;
+        const int by0 = band * PY_ROWS, rows = min(PY_ROWS, rowsTotal - by0);
+        if (tid == 0) {
+            const unsigned char* img = images + (size_t)frame * frameStride;
+            // the previous band's store has read the buffer, and every thread's accesses to it are behind the CTA barrier below
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((unsigned int)(rows * w)) : "memory");
+            for (int r = 0; r < rows; ++r) {
+                const unsigned char* src = img + (size_t)reflect101(by0 + r - kEdge, h) * stride;
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                 buf + (unsigned int)(r * pitch + kPadLeft)),
+                             "l"(src), "r"((unsigned int)w), "r"(bar)
+                             : "memory");
+            }
+        }
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "PY0_WAIT_%=:\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+            "@p bra PY0_DONE_%=;\n"
+            "bra PY0_WAIT_%=;\n"
+            "PY0_DONE_%=:\n"
+            "}\n" ::"r"(bar),
+            "r"(parity)
+            : "memory");
+        parity ^= 1u;
+        for (int i = tid; i < rows * nb; i += PY0_THREADS) {
+            const int r = i / nb, j = i - r * nb;
+            const int bx = j < kPadLeft / 4 ? 4 * j : w + 4 * j;      // left: bytes 0 .. 31 of the padded row; right: from byte 32 + w on
+            unsigned char* row = rowsSm + r * pitch;
+            unsigned int word = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) word |= (unsigned int)row[kPadLeft + frame_column(bx - kPadLeft + k, w)] << (8 * k);
+            *reinterpret_cast<unsigned int*>(row + bx) = word;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the frame bytes, before the copy engine reads the band
+        __syncthreads();
+        if (tid == 0) {
+            unsigned char* dst = pyr + (size_t)frame * pyrFrameBytes + pyrOff + (size_t)by0 * pitch;
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(buf), "r"((unsigned int)(rows * pitch)) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+    }
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
 
 __global__ void __launch_bounds__(512)
 pyramid_resize3_kernel(unsigned char* __restrict__ pyr, long long pyrFrameBytes, long long srcOff, long long dstOff, int dstPitch,
@@ -675,7 +746,26 @@ int launch_pyramid(const ExtractParams& P, const unsigned char* dImages, int wid
         const int groups = L.pitch / 4, nItems = groups * ceil_div(L.h + 2 * kEdge, PY_ROWS);
         const int wordLoads = ((((size_t)dImages) | (size_t)stride | frameStride) & 3) == 0 ? 1 : 0;
         static const bool noWide = getenv("ORBB_PYR_NOWIDE") != nullptr;     // A/B aid
-        if (!noWide && ((((size_t)dImages) | (size_t)stride | frameStride | (size_t)width) & 15) == 0 && (L.pitch & 15) == 0) {
+        static const bool noBulk0 = getenv("ORBB_PYR_NOBULK0") != nullptr;   // A/B aid
+        const bool aligned16 = ((((size_t)dImages) | (size_t)stride | frameStride | (size_t)width) & 15) == 0 && (L.pitch & 15) == 0;
+        const int l0Smem = 128 + PY_ROWS * L.pitch;
+        if (!noWide && !noBulk0 && aligned16 && P.nFrames >= P.pyBulkMinFrames && ((L.pitch - width) & 3) == 0 && kPadLeft % 16 == 0 &&
+            l0Smem <= 48 * 1024) {
+            static thread_local int cDev = -1, cCtas = 0;
+            int dev = 0;
+            ORB_CUDA(cudaGetDevice(&dev));
+            if (cDev != dev) {
+                int nSm = 0;
+                ORB_CUDA(cudaDeviceGetAttribute(&nSm, cudaDevAttrMultiProcessorCount, dev));
+                cCtas = nSm * 8;
+                cDev = dev;
+            }
+            const int nBands = ceil_div(L.h + 2 * kEdge, PY_ROWS);
+            const long long nTiles = (long long)nBands * P.nFrames;
+            const int gridB = (int)std::min<long long>(nTiles, cCtas);
+            pyramid_level0_bulk_kernel<<<gridB, PY0_THREADS, l0Smem, st>>>(dImages, width, height, stride, frameStride, P.pyr, P.pyrFrameBytes,
+                                                                          L.pyrOff, L.pitch, nBands, (int)nTiles);
+        } else if (!noWide && aligned16) {
             const int groups16 = width / 16 + (L.pitch - width) / 4, nItems16 = groups16 * ceil_div(L.h + 2 * kEdge, PY_ROWS);
             dim3 grid16(ceil_div(nItems16, PY_THREADS), P.nFrames);
             pyramid_level0_wide_kernel<<<grid16, PY_THREADS, 0, st>>>(dImages, width, height, stride, frameStride, P.pyr,
