@@ -757,7 +757,7 @@ int launch_pyramid(const ExtractParams& P, const unsigned char* dImages, int wid
             if (cDev != dev) {
                 int nSm = 0;
                 ORB_CUDA(cudaDeviceGetAttribute(&nSm, cudaDevAttrMultiProcessorCount, dev));
-                cCtas = nSm * 8;
+                cCtas = nSm * (getenv("ORBB_PYR_L0CTAS") ? std::max(1, atoi(getenv("ORBB_PYR_L0CTAS"))) : 6);   // tuning aid (4: 3.46, 6: 3.34, 8: 3.37, 12: 3.38, 16: 3.37 ms for the whole pyramid of 4096 frames)
                 cDev = dev;
             }
             const int nBands = ceil_div(L.h + 2 * kEdge, PY_ROWS);
