@@ -14,7 +14,7 @@ for k in fast_warp octree_kernel brief_staged; do
 done
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:blur_staged -s 16 -c 1 -f -o gpurun_out/r02_final_blur_staged $B > /dev/null 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:pyramid_resize3 -s 14 -c 1 -f -o gpurun_out/r02_final_pyramid_resize3 $B > /dev/null 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:pyramid_level0_wide -s 2 -c 1 -f -o gpurun_out/r02_final_pyramid_level0 $B > /dev/null 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:pyramid_level0_bulk -s 2 -c 1 -f -o gpurun_out/r02_final_pyramid_level0 $B > /dev/null 2>&1
 # whole-stage DRAM traffic: every launch of two steps, dram bytes per kernel
 timeout 600 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k "regex:pyramid|fast_warp|octree|blur_|brief" -s 57 -c 19 --csv --log-file gpurun_out/r02_traffic_final.csv $B > /dev/null 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:bf_scan -s 1 -c 1 -f -o gpurun_out/r02_final_bf_scan python bench.py --steps 1 --warmup 3 --frames 64 --no-cpu --no-latency --no-allpairs --no-kitti > /dev/null 2>&1
