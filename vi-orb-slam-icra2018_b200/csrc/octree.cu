@@ -23,7 +23,7 @@ constexpr int OT_THREADS = 256;
 constexpr int OT_WARPS = OT_THREADS / 32;
 
 struct OtLayout {   // byte offsets into dynamic shared memory
-    int boxA, boxB, cntA, cntB, newA, newB, child, thr, t0, t1, t2, t3, cellOff, keyVal, keyNode, total;
+    int boxA, boxB, cntA, cntB, newA, newB, child, t0, t1, t2, t3, cellOff, keyVal, keyNode, total;
 };
 
 __host__ __device__ inline OtLayout ot_layout(int nodeCap, int cellCap, int keyCap) {
@@ -34,7 +34,6 @@ __host__ __device__ inline OtLayout ot_layout(int nodeCap, int cellCap, int keyC
     o.cntA = take(nodeCap * 4); o.cntB = take(nodeCap * 4);
     o.newA = take(nodeCap); o.newB = take(nodeCap);
     o.child = take(nodeCap * 16);
-    o.thr = take(nodeCap * 8);
     o.t0 = take(nodeCap * 4); o.t1 = take(nodeCap * 4); o.t2 = take(nodeCap * 4); o.t3 = take(nodeCap * 4);
     o.cellOff = take((cellCap + 1) * 4);
     o.keyVal = take(keyCap * 4);
@@ -47,22 +46,22 @@ __device__ __forceinline__ int key_x(unsigned int k) { return (int)(k >> 20); }
 __device__ __forceinline__ int key_y(unsigned int k) { return (int)((k >> 8) & 0xfffu); }
 __device__ __forceinline__ int key_s(unsigned int k) { return (int)(k & 0xffu); }
 
-// child of a node for a key: 0 = n1 (upper-left), 1 = n2 (upper-right), 2 = n3 (lower-left), 3 = n4 (lower-right)
+// child of a node for a key: 0 = n1 (upper-left), 1 = n2 (upper-right), 2 = n3 (lower-left), 3 = n4 (lower-right):
+//   mx = b.x + ((b.z - b.x + 1) >> 1)  (UL.x + ceil((UR.x-UL.x)/2)), my likewise;  (key_x < mx ? 0 : 1) + (key_y < my ? 0 : 2)
+// The same decision on the packed words: the box is two words (x | y << 16), (z | w << 16) of non-negative shorts, so one
+// three-input add gives (x + z + 1) | (y + w + 1) << 16, and mx = (x + z + 1) >> 1, my = (y + w + 1) >> 1 are the midpoints
+// above (b.x + ((b.z - b.x + 1) >> 1) == (b.x + b.z + 1) >> 1).  A key holds x in bits 20..31 and y in bits 8..19, so
+//   key_x(key) < mx  <=>  key < (mx << 20)   and   key_y(key) < my  <=>  (key & 0xfff00) < (my << 8):
+// no field extraction and no sign extension per (key, round); child_of was 18 % of the kernel's instructions
+// (2.23 -> 2.04 ms per 4096 frames with the thresholds kept per node in shared memory, which cost levels with many keys
+// their place there; this form needs no table).
 __device__ __forceinline__ int child_of(short4 b, unsigned int key) {
-    const int mx = b.x + ((b.z - b.x + 1) >> 1);   // UL.x + ceil((UR.x-UL.x)/2)
-    const int my = b.y + ((b.w - b.y + 1) >> 1);
-    return (key_x(key) < mx ? 0 : 1) + (key_y(key) < my ? 0 : 2);
+    const uint2 w = *reinterpret_cast<const uint2*>(&b);
+    const unsigned int s = w.x + w.y + 0x00010001u;
+    const unsigned int tx = (s & 0xfffeu) << 19;          // ((s & 0xffff) >> 1) << 20
+    const unsigned int ty = (s >> 9) & 0xffffff00u;       // (s >> 17) << 8
+    return (key < tx ? 0 : 1) + ((key & 0xfff00u) < ty ? 0 : 2);
 }
-// The same decision against thresholds prepared once per node and round: a key holds x in bits 20..31 and y in bits 8..19,
-// so  key_x(key) < mx  <=>  key < (mx << 20)  and  key_y(key) < my  <=>  (key & 0xfff00) < (my << 8)  -- no field extraction and
-// no midpoint arithmetic per (key, round): child_of was 18 % of the kernel's instructions.
-__device__ __forceinline__ uint2 child_thresholds(short4 b) {
-    const int mx = b.x + ((b.z - b.x + 1) >> 1);
-    const int my = b.y + ((b.w - b.y + 1) >> 1);
-    // a midpoint past the 12-bit key range (never with keys that fit their fields) keeps every key on the low side
-    return make_uint2(mx > 0xfff ? 0xffffffffu : (unsigned int)mx << 20, my > 0xfff ? 0xffffffffu : (unsigned int)my << 8);
-}
-__device__ __forceinline__ int child_of(uint2 t, unsigned int key) { return (key < t.x ? 0 : 1) + ((key & 0xfff00u) < t.y ? 0 : 2); }
 __device__ __forceinline__ short4 child_box(short4 b, int c) {
     const short mx = (short)(b.x + ((b.z - b.x + 1) >> 1));
     const short my = (short)(b.y + ((b.w - b.y + 1) >> 1));
@@ -125,7 +124,6 @@ octree_kernel(const __grid_constant__ ExtractParams P, int nodeCap, int cellCap,
     unsigned char* isNew = sm + lay.newA;
     unsigned char* isNewN = sm + lay.newB;
     int* child = reinterpret_cast<int*>(sm + lay.child);
-    uint2* thr = reinterpret_cast<uint2*>(sm + lay.thr);   // per node: the midpoints as key thresholds (child_thresholds)
     int* t0 = reinterpret_cast<int*>(sm + lay.t0);   // children per processed node -> position base
     int* t1 = reinterpret_cast<int*>(sm + lay.t1);   // processing rank per node (-1: not processed)
     int* t2 = reinterpret_cast<int*>(sm + lay.t2);   // survivor index per node
@@ -206,13 +204,12 @@ octree_kernel(const __grid_constant__ ExtractParams P, int nodeCap, int cellCap,
     bool careful = false;
     while (true) {
         for (int i = tid; i < 4 * S; i += OT_THREADS) child[i] = 0;
-        for (int i = tid; i < S; i += OT_THREADS) thr[i] = child_thresholds(box[i]);
         if (tid == 0) { ctl[0] = 0; ctl[1] = 0x7fffffff; }
         __syncthreads();
         // children sizes of every candidate node
         for (int k = tid; k < n; k += OT_THREADS) {
             const int i = kn[k];
-            if (cnt[i] > 1 && (!careful || isNew[i])) atomicAdd(&child[4 * i + child_of(thr[i], kv[k])], 1);
+            if (cnt[i] > 1 && (!careful || isNew[i])) atomicAdd(&child[4 * i + child_of(box[i], kv[k])], 1);
         }
         __syncthreads();
         // t0 = 1 for candidates (scanned below), t1 = -1
@@ -295,7 +292,7 @@ octree_kernel(const __grid_constant__ ExtractParams P, int nodeCap, int cellCap,
         __syncthreads();
         for (int k = tid; k < n; k += OT_THREADS) {
             const int i = kn[k];
-            kn[k] = (unsigned short)(t1[i] < 0 ? t2[i] : child[4 * i + child_of(thr[i], kv[k])]);
+            kn[k] = (unsigned short)(t1[i] < 0 ? t2[i] : child[4 * i + child_of(box[i], kv[k])]);
         }
         const int newS = E + (S - nProc);
         const int nToExpand = ctl[0];
