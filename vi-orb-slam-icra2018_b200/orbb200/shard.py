@@ -98,17 +98,13 @@ def allpairs_sharded(matcher, local_desc, local_angles, n_kf, dist, ratio=0.75, 
     padded_rows = world * max_local
     # rows of the padded table: rank r's keyframes start at r*max_local
     padded_counts = torch.full((qe - qb, padded_rows), -1, dtype=torch.int32, device=local_desc.device)
-    first = True
-    for (b, e) in column_schedule(n_kf, rank, world):
-        r = next(i for i, s in enumerate(sizes) if s == (b, e))
-        if not first:
-            for w in works:
-                w.wait()
-            works = []
-        compute(gd, ga, rank * max_local, rank * max_local + (qe - qb), r * max_local, r * max_local + (e - b), padded_counts)
-        first = False
+    # the gather's output includes this rank's own slot: wait for it before anything reads the table (this path is the host
+    # stand-in of the tests; the CUDA path orders its reads against the chunked gathers by events in csrc/shard.cu)
     for w in works:
         w.wait()
+    for (b, e) in column_schedule(n_kf, rank, world):
+        r = next(i for i, s in enumerate(sizes) if s == (b, e))
+        compute(gd, ga, rank * max_local, rank * max_local + (qe - qb), r * max_local, r * max_local + (e - b), padded_counts)
     for r, (b, e) in enumerate(sizes):
         counts[:, b:e] = padded_counts[:, r * max_local: r * max_local + (e - b)]
     return counts
